@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200: fused quantize -> decode -> mean throughput (coords/s)
+of the unbiased type quantizer at d = 2^24, n = 128 clients per GPU (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--d D] [--n N] [--rate R]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic client vectors resident in HBM
+(N(0,1) i.i.d., torch.Generator seed 42 + rank).  Rank 0 prints ONE JSON line.
+  value     : whole-job coords/s = N_gpus * n * d * K / (max-over-ranks device time), inputs in HBM
+  e2e       : same metric through the public host-buffer call (pinned host rows -> H2D -> fused path -> D2H of the mean)
+  roofline  : dominant kernel (scan/quantize/pack), algorithmic bytes 4*n*d + 4*d per launch / its CUDA-event time,
+              against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline : oracle port (oracle/dme_oracle.c, pthreads over clients) on the box's host cores, bounded sample
+--impl reference times that CPU port alone (the reference is pure Python/torch and cannot travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "quantize+decode+mean coords/s (unbiased type quantizer, R=1)"
+UNIT = "coords/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--d", type=int, default=1 << 24)
+    ap.add_argument("--n", type=int, default=128, help="clients per GPU")
+    ap.add_argument("--rate", type=float, default=1)
+    ap.add_argument("--mode", default="unbiased", choices=["unbiased", "biased"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"type_{a.mode} R={a.rate:g} d={a.d} n={a.n}/gpu N(0,1) synthetic"
+
+
+def rate_key(r):
+    return int(r) if float(r) == int(r) else float(r)
+
+
+# ------------------------------------------------------------------ CPU arm (oracle port; the checker, timed)
+def cpu_arm(a, steps, warmup, budget_s):
+    """Times the oracle's quantize->dequantize->mean loop (ND:133-147 with Type_unbiased_quantize) on host cores.
+    Sample: `cores` clients (at most a.n) of the full length d per step."""
+    from oracle import oracle as orc
+    cores = os.cpu_count() or 1
+    d = a.d
+    ns = max(1, min(a.n, cores))
+    rng = np.random.default_rng(42)
+    X = rng.standard_normal((ns, d), dtype=np.float32)
+    Xs = rng.random(ns, dtype=np.float32)
+    m = orc.m_for(rate_key(a.rate), d)
+    times = []
+    t_start = time.perf_counter()
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.quantize_mean_unbiased(X, m, Xs, threads=cores)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if budget_s and time.perf_counter() - t_start > budget_s and len(times) >= 1:
+            break
+    t = float(np.mean(times))
+    return {"value": ns * d / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{ns} clients x d={d} per step, {len(times)} timed steps, oracle/dme_oracle.c with {cores} pthreads",
+            "ms_per_step": t * 1e3, "steps": len(times)}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(a.steps, 5)), max(1, min(a.warmup, 1))
+    cb = cpu_arm(a, steps, warmup, budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": cb["steps"],
+            "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+f64acc", "data": "synthetic", "config": {"workload": workload_name(a), "sample": cb["sample"]},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ clocks sampler
+class Clocks:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import dme_b200 as dme
+    from dme_b200 import _cabi
+    import ctypes as C
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n, d, R = a.n, a.d, rate_key(a.rate)
+    n_total = n * world
+    client0 = rank * n
+    gen = torch.Generator(device=dev).manual_seed(42 + rank)
+    X = torch.empty((n, d), dtype=torch.float32, device=dev)
+    for c in range(n):                                   # row by row: keeps the generator's scratch small
+        X[c].normal_(generator=gen)
+    mean = torch.empty(d, dtype=torch.float32, device=dev)
+    L = _cabi.lib()
+
+    def step(i):
+        dme.quantize_mean(X, R, mode=a.mode, seed=1234 + i, client0=client0, n_total=n_total, out=mean, check=False)
+        if world > 1:
+            dist.all_reduce(mean, op=dist.ReduceOp.SUM)          # the path's one exchange step
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(a.warmup):
+        step(i)
+    dme.Workspace.get(dev).status()                      # a kernel-side error in warm-up fails loudly here
+    sync()
+    launches0 = L.dme_launch_count()
+    clk = Clocks(local)
+    if rank == 0:
+        clk.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        step(a.warmup + i)
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1)
+    clocks = clk.stop() if rank == 0 else None
+    launches = L.dme_launch_count() - launches0
+    dme.Workspace.get(dev).status()
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_step = ms / a.steps
+    value = n_total * d / (ms_step * 1e-3)
+
+    # ---- roofline leg: per-kernel CUDA-event times (events on the launching stream), outside the timed region
+    peak, peak_src = peaks()
+    B_alg = 4.0 * n * d + 4.0 * d
+    L.dme_profile_enable(1)
+    per = []
+    for i in range(5):
+        step(1000 + i)
+        buf = (C.c_float * 8)()
+        k = L.dme_profile_read(buf, 8)
+        per.append([buf[j] for j in range(k)])
+    L.dme_profile_enable(0)
+    per = np.array(per[1:])
+    kern_ms = per.mean(axis=0) if per.size else np.array([ms_step])
+    names = ["l1_kernel", "scan_kernel", "decode_mean_kernel"][: len(kern_ms)]
+    dom = int(np.argmax(kern_ms))
+    ach = B_alg / (kern_ms[dom] * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": B_alg,
+            "kernel_ms": {nm: float(v) for nm, v in zip(names, kern_ms)},
+            "step_achieved": B_alg / (ms_step * 1e-3) / 1e9, "step_frac": B_alg / (ms_step * 1e-3) / 1e9 / peak}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roof["traffic"] = json.load(open(tr)).get(names[dom])
+        except Exception:
+            pass
+
+    # ---- e2e: host buffers, H2D + D2H inside the timed region
+    e2e = None
+    if not a.no_e2e:
+        try:
+            Xh = torch.empty((n, d), dtype=torch.float32, pin_memory=True)
+            Xh.copy_(X)
+            outh = torch.empty(d, dtype=torch.float32, pin_memory=True)
+            Xd2 = X                                               # reuse the device buffer as the H2D target
+            def e2e_step(i):
+                Xd2.copy_(Xh, non_blocking=True)
+                dme.quantize_mean(Xd2, R, mode=a.mode, seed=77 + i, client0=client0, n_total=n_total, out=mean, check=False)
+                if world > 1:
+                    dist.all_reduce(mean, op=dist.ReduceOp.SUM)
+                outh.copy_(mean, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            e2e_step(0)
+            sync()
+            t0 = time.perf_counter()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for i in range(a.e2e_steps):
+                e2e_step(1 + i)
+            s1.record()
+            sync()
+            ems = max(s0.elapsed_time(s1), (time.perf_counter() - t0) * 1e3) / a.e2e_steps
+            if world > 1:
+                t = torch.tensor([ems], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ems = float(t.item())
+            e2e = {"value": n_total * d / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(4 * n * d), "d2h_bytes_per_step": int(4 * d),
+                   "ms_per_step": ems, "steps": a.e2e_steps, "api": "dme_b200.quantize_mean on pinned host rows (copy in, fused path, copy out)"}
+            del Xh
+        except Exception as ex:  # pinned allocation can fail on a small host
+            e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        cb = cpu_arm(a, steps=3, warmup=1, budget_s=a.cpu_seconds)
+        cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 accumulate)", "data": "synthetic",
+                "config": {"workload": workload_name(a), "clients_total": n_total, "m": dme.m_for_rate(R, d), "parallelism": f"clients sharded x{world}",
+                           "l2_hygiene": f"inputs ({4 * n * d / 2**30:.1f} GiB/GPU) larger than L2; no flush needed"},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "e2e": e2e, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

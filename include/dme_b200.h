@@ -1,0 +1,158 @@
+/*
+ * dme_b200.h -- C ABI of libdme_b200.so: the B200 (sm_100a) implementation of the distributed-mean-
+ * estimation hot path of Ritesh622/Unbiased-Quantization-Distributed-Mean-Estimation.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + a CUDA stream handle
+ * (void* == cudaStream_t), enqueues work on that stream and returns immediately.  No torch types.
+ * Return value: 0 = OK, <0 = DME_E* (message via dme_last_error(), thread-local).  The library never
+ * allocates user-visible memory: outputs and scratch are caller-owned.  There is NO CPU fallback: a
+ * call without a usable CUDA device fails with DME_ECUDA.
+ *
+ * Reference interface each entry replaces (AS = NMSE_Results/Codes/All_Schemes.py,
+ * ND = NMSE_Results/Codes/Normal_dist.py of the reference tree):
+ *   dme_l1_norms            AS:624, AS:681          input_vector.abs().sum()
+ *   dme_type_quantize       AS:609-641 (mode 0), AS:644-687 (mode 1); returns what the reference returns
+ *                           (deq) and/or the integer type vector + signs it only implies
+ *   dme_type_encode         same arithmetic, emits the packed code "DMEP1" (no reference counterpart)
+ *   dme_decode_mean         AS:640 / AS:687 dequantise + ND:133-147 `est += q / n`
+ *   dme_quantize_mean       fused: the whole server loop ND:133-147 for the type quantizers
+ *   dme_hadamard            AS:100-115   Hadamard.hadamard
+ *   dme_rht / dme_irht      AS:127-144 / AS:151-156 (diagonal AS:117-120: Philox or injected)
+ *   dme_pair_transform      AS:37-59 as it executes
+ *   dme_drive               AS:707-752
+ *   dme_eden_encode/decode  AS:335-350,370-390 / AS:398-426
+ *   dme_quicfl_decode       AS:526-535
+ *   dme_scalar_quantize     AS:755-790
+ *   dme_mean_accumulate     ND:133-147 for schemes that return a dequantised vector
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Layout conventions: client vectors are rows of a row-major matrix X[n][ld], ld >= d, ld % 4 == 0,
+ * X 16-byte aligned (the Python shim copies when that does not hold).  All vectors are fp32.
+ */
+#ifndef DME_B200_H
+#define DME_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DME_OK 0
+#define DME_EINVAL (-1)    /* bad argument (message says which) */
+#define DME_ECUDA (-2)     /* CUDA runtime error / no device */
+#define DME_EWORKSPACE (-3)/* workspace or code arena too small */
+#define DME_EOVERFLOW (-4) /* a magnitude does not fit the requested output (reported by dme_status) */
+
+#define DME_MODE_UNBIASED 0
+#define DME_MODE_BIASED 1
+
+#define DME_TILE 4096      /* coordinates per tile of the packed code and of every row kernel */
+
+typedef void *dme_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define DME_API __attribute__((visibility("default")))
+#else
+#define DME_API
+#endif
+
+DME_API const char *dme_last_error(void);
+DME_API int dme_version(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+DME_API int64_t dme_launch_count(void);
+
+/* Per-kernel timing of the type-quantizer path with CUDA events on the caller's stream (bench.py's roofline leg;
+ * keep it off inside timed regions).  dme_profile_read returns the number of intervals written: for
+ * dme_quantize_mean they are {L1 reduce, scan/quantize/pack, decode+mean} in milliseconds. */
+DME_API int dme_profile_enable(int on);
+DME_API int dme_profile_read(float *ms, int cap);
+
+/* X_c, the single uniform of client c (AS:634): Philox4x32-10, key = seed, counter = (client, 0, 0, 0x584D44),
+ * top 24 bits -> [0,1).  Host-side helper so callers/tests can reproduce the draws. */
+DME_API float dme_uniform_x(uint64_t seed, uint64_t client);
+
+/* Scratch for the type-quantizer entry points (bytes). */
+DME_API int64_t dme_workspace_bytes(int64_t n, int64_t d);
+/* Arena size for packed codes: expect=1 -> sized for the field width the rate m/d suggests (+50 %),
+ * expect=0 -> worst case (32-bit fields everywhere). */
+DME_API int64_t dme_codes_bytes(int64_t n, int64_t d, int64_t m, int expect);
+/* Entries (uint64) of the tile directory: n * ceil(d / DME_TILE). */
+DME_API int64_t dme_dir_entries(int64_t n, int64_t d);
+
+/* After the stream has been synchronised: 0, or DME_EOVERFLOW / DME_EWORKSPACE raised by a kernel of the
+ * last call that used this workspace. */
+DME_API int dme_status(const void *ws, dme_stream_t stream);
+
+DME_API int dme_l1_norms(const float *X, int64_t n, int64_t d, int64_t ld, float *l1_out,
+                 void *ws, int64_t ws_bytes, dme_stream_t stream);
+
+/* x_inject (n floats, device, nullable): X_c to use instead of Philox(seed, client0 + c).
+ * l1_inject (n floats, device, nullable): fp32 L1 norms to use instead of the computed ones.
+ * k_out (int32, nullable), sgn_out (uint8, nullable), deq_out (float, nullable): rows of ld_out elements.
+ * l1_out (n floats, nullable): the fp32 L1 norms used. */
+DME_API int dme_type_quantize(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, int mode,
+                      const float *x_inject, const float *l1_inject, uint64_t seed, uint64_t client0,
+                      int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out, float *l1_out,
+                      void *ws, int64_t ws_bytes, dme_stream_t stream);
+
+/* Packed code DMEP1.  dir[c * T + t] = (byte offset of the tile in `codes` / 16) << 8 | field width,
+ * T = ceil(d / DME_TILE); a tile of width w holds 128*w uint32 words: word q of 16-coordinate chunk j at
+ * [q * 256 + j], field i of the chunk at bits [w*i, w*i + w) = sign << (w-1) | magnitude. */
+DME_API int dme_type_encode(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, int mode,
+                    const float *x_inject, const float *l1_inject, uint64_t seed, uint64_t client0,
+                    void *codes, int64_t codes_bytes, uint64_t *dir, float *l1_out,
+                    void *ws, int64_t ws_bytes, dme_stream_t stream);
+
+/* mean[i] (+)= sum_c deq(c, i) / n_total, clients in order, fp32.  accumulate=0 overwrites. */
+DME_API int dme_decode_mean(const void *codes, const uint64_t *dir, const float *l1, int64_t n, int64_t d,
+                    int64_t m, int mode, int64_t n_total, float *mean, int accumulate, dme_stream_t stream);
+
+/* quantize -> pack -> decode -> mean in one call (the north-star path).  `codes`/`dir` are scratch here. */
+DME_API int dme_quantize_mean(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, int mode,
+                      const float *x_inject, uint64_t seed, uint64_t client0, int64_t n_total,
+                      float *mean, int accumulate, void *codes, int64_t codes_bytes, uint64_t *dir,
+                      float *l1_out, void *ws, int64_t ws_bytes, dme_stream_t stream);
+
+/* mean[i] (+)= sum_c Q[c][i] / n_total for already-dequantised rows (DRIVE/EDEN/... ND:133-147). */
+DME_API int dme_mean_accumulate(const float *Q, int64_t n, int64_t d, int64_t ld, int64_t n_total, float *mean,
+                        int accumulate, dme_stream_t stream);
+
+/* ---- rotations ---- */
+/* In-place normalised natural-order Walsh-Hadamard transform of n rows of dpad (power of two) floats. */
+DME_API int dme_hadamard(float *V, int64_t n, int64_t dpad, int64_t ld, dme_stream_t stream);
+/* out[c][0..dpad) = H(diag * pad(x[c])).  diag: Philox(seed, coordinate) sign, or diag_inject (dpad floats, +-1). */
+DME_API int dme_rht(const float *X, int64_t n, int64_t d, int64_t ld, float *out, int64_t dpad, int64_t ld_out,
+            uint64_t seed, const float *diag_inject, dme_stream_t stream);
+DME_API int dme_irht(float *V, int64_t n, int64_t dpad, int64_t ld, uint64_t seed, const float *diag_inject,
+             dme_stream_t stream);
+DME_API int dme_rademacher(float *diag, int64_t dpad, uint64_t seed, dme_stream_t stream);
+/* The reference's `fast_walsh_hadamard_transform` as it executes: log2(len) stages on adjacent pairs. */
+DME_API int dme_pair_transform(float *V, int64_t n, int64_t len, int64_t ld, dme_stream_t stream);
+
+/* ---- comparison quantizers ---- */
+/* dsign_inject: +-1 per padded coordinate, chunk after chunk (2048-chunks, last padded to pow2), nullable.
+ * compat 0 = the reference's transform, 1 = true WHT (real DRIVE). */
+DME_API int dme_drive(const float *X, int64_t n, int64_t d, int64_t ld, float *out, int64_t ld_out, uint64_t seed,
+              const float *dsign_inject, int compat, dme_stream_t stream);
+/* rot: n x dpad scratch/out (rotated vectors); bins: uint8 n x dpad; scale: n floats. nbits in {1,2}. */
+DME_API int dme_eden_encode(const float *X, int64_t n, int64_t d, int64_t ld, int64_t dpad, int nbits, uint64_t seed,
+                    const float *diag_inject, const float *norm_inject, float *rot, uint8_t *bins, float *scale,
+                    dme_stream_t stream);
+DME_API int dme_eden_decode(const uint8_t *bins, const float *scale, int64_t n, int64_t d, int64_t dpad, int nbits,
+                    uint64_t seed, const float *diag_inject, float *work, float *out, int64_t ld_out,
+                    dme_stream_t stream);
+/* Xq: int32 n x dpad table rows; h: int32 n x dpad shared randomness; recv_table: (2^nbits) x h_len floats;
+ * exact_mask (uint8, nullable) / exact_vals (per row: exact_off[c] .. exact_off[c+1]). */
+DME_API int dme_quicfl_decode(const int32_t *Xq, const int32_t *h, int64_t n, int64_t d, int64_t dpad, int h_len,
+                      const float *recv_table, int table_len, const uint8_t *exact_mask, const float *exact_vals,
+                      const int64_t *exact_off, const float *scale, uint64_t rotation_seed,
+                      const float *diag_inject, float *work, float *out, int64_t ld_out, dme_stream_t stream);
+/* u_inject: n x d uniforms (nullable -> Philox(seed, client, coordinate)). nlevels = 2^bits - 1. */
+DME_API int dme_scalar_quantize(const float *X, int64_t n, int64_t d, int64_t ld, float nlevels, uint64_t seed,
+                        uint64_t client0, const float *u_inject, float *out, int64_t ld_out, dme_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DME_B200_H */

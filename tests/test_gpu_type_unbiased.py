@@ -1,0 +1,169 @@
+"""GPU parity (through the C ABI): unbiased type quantizer, packed code, decode + mean vs the CPU oracle
+and the committed golden fixtures.  Integer / index / byte outputs and the fp32 outputs are BIT-EXACT."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as orc  # noqa: E402  (checker only)
+
+
+@pytest.fixture(scope="module")
+def dme():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import dme_b200
+    return dme_b200
+
+
+def _R(v):
+    v = float(v)
+    return int(v) if v == int(v) else v
+
+
+def _u32(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def test_golden_unbiased_bit_exact(dme, golden_dir):
+    g = np.load(os.path.join(golden_dir, "type_quantizers.npz"))
+    n = int(g["n_unbiased"])
+    for i in range(n):
+        x, R, X, L1, q = g[f"u{i}_x"], _R(g[f"u{i}_R"]), float(g[f"u{i}_X"]), g[f"u{i}_L1"], g[f"u{i}_q"]
+        out = dme.type_quantize(x, R, x_inject=[X], l1_inject=[L1], want=("deq", "k", "sgn"))
+        assert np.array_equal(_u32(out["deq"].cpu().numpy()), _u32(q)), (i, str(g[f"u{i}_name"]), R, X)
+        o = orc.type_unbiased(x, out["m"], X, l1_inject=L1)
+        assert np.array_equal(out["k"].cpu().numpy(), o["k"].astype(np.int32))
+        assert np.array_equal(out["sgn"].cpu().numpy(), o["sgn"])
+
+
+@pytest.mark.parametrize("n,d", [(1, 1), (3, 15), (2, 16), (2, 17), (3, 4095), (2, 4096), (3, 4097), (5, 65536), (2, 100003), (7, 122626)])
+@pytest.mark.parametrize("R", [0.5, 1, 2, 4])
+def test_random_rows_bit_exact_own_l1(dme, n, d, R):
+    rng = np.random.default_rng(1000 * n + d)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    Xs = dme.client_uniforms(seed=42, client0=5, n=n)
+    out = dme.type_quantize(X, R, seed=42, client0=5, want=("deq", "k", "sgn", "l1"))
+    for c in range(n):
+        o = orc.type_unbiased(X[c], out["m"], float(Xs[c]))
+        assert float(out["l1"][c]) == float(o["L1"])
+        assert np.array_equal(out["k"][c].cpu().numpy(), o["k"].astype(np.int32)), (c, d, R)
+        assert np.array_equal(out["sgn"][c].cpu().numpy(), o["sgn"])
+        assert np.array_equal(_u32(out["deq"][c].cpu().numpy()), _u32(o["deq"]))
+
+
+@pytest.mark.parametrize("dist", ["uniform", "exponential", "lognormal", "lognormal12", "bernoulli", "sparse", "zeros", "onehot"])
+def test_distributions_and_edge_inputs(dme, dist):
+    rng = np.random.default_rng(5)
+    d = 20000
+    x = {"uniform": rng.uniform(-1, 1, d), "exponential": rng.exponential(1.0, d), "lognormal": rng.lognormal(0, 1, d),
+         "lognormal12": rng.lognormal(1, 2, d) * rng.choice([-1, 1], d), "bernoulli": (rng.random(d) < 0.7).astype(np.float64),
+         "sparse": rng.standard_normal(d) * (rng.random(d) < 0.01), "zeros": np.zeros(d),
+         "onehot": np.eye(1, d, 777)[0] * -2.5}[dist].astype(np.float32)
+    for R in (1, 2, 6):
+        out = dme.type_quantize(x, R, x_inject=[0.37], want=("deq", "k", "sgn"))
+        o = orc.type_unbiased(x, out["m"], 0.37)
+        assert np.array_equal(out["k"].cpu().numpy(), o["k"].astype(np.int32)), (dist, R)
+        assert np.array_equal(_u32(out["deq"].cpu().numpy()), _u32(o["deq"])), (dist, R)
+
+
+def test_packed_code_matches_oracle_and_roundtrips(dme):
+    rng = np.random.default_rng(9)
+    n, d = 4, 3 * 4096 + 100
+    X = np.stack([rng.standard_normal(d), rng.lognormal(1, 2, d), rng.uniform(-1, 1, d), rng.exponential(1, d)]).astype(np.float32)
+    Xs = [0.1, 0.5, 0.9, 0.25]
+    for R in (1, 2, 5):
+        pc = dme.type_encode(X, R, x_inject=Xs)
+        T = (d + 4095) // 4096
+        for c in range(n):
+            o = orc.type_unbiased(X[c], pc.m, Xs[c])
+            tiles = orc.pack_row(o["k"], o["sgn"])
+            for t in range(T):
+                w, words = pc.tile(c, t)
+                assert w == tiles[t][0], (R, c, t)
+                assert np.array_equal(words, tiles[t][1]), (R, c, t)       # packed code bit-exact vs the oracle
+                cnt = min(4096, d - 4096 * t)
+                kk, ss = orc.unpack_tile(words, w, cnt)
+                assert np.array_equal(kk, o["k"][4096 * t: 4096 * t + cnt])
+        mean = dme.decode_mean(pc).cpu().numpy()
+        ref = orc.mean_of([orc.type_unbiased(X[c], pc.m, Xs[c])["deq"] for c in range(n)])
+        assert np.array_equal(_u32(mean), _u32(ref)), R
+
+
+def test_golden_server_mean_config1(dme, golden_dir):
+    """BASELINE config 1 shape (n=10, d=1024): the reference's own server loop, L1 and X injected."""
+    g = np.load(os.path.join(golden_dir, "scalar_mean.npz"))
+    Xm, Xs, L1, R = g["mean_X"], g["mean_Xs"], g["mean_L1"], _R(g["mean_R"])
+    pc = dme.type_encode(Xm, R, x_inject=Xs, l1_inject=L1)
+    est = dme.decode_mean(pc).cpu().numpy()
+    assert np.array_equal(_u32(est), _u32(g["mean_est"]))
+
+
+def test_fused_quantize_mean_and_determinism(dme):
+    rng = np.random.default_rng(11)
+    n, d = 16, 70001
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    Xd = torch.from_numpy(X).cuda()
+    a = dme.quantize_mean(Xd, 1, seed=3).cpu().numpy()
+    b = dme.quantize_mean(Xd, 1, seed=3).cpu().numpy()
+    assert np.array_equal(_u32(a), _u32(b))
+    Xs = dme.client_uniforms(3, 0, n)
+    ref = orc.mean_of([orc.type_unbiased(X[c], dme.m_for_rate(1, d), float(Xs[c]))["deq"] for c in range(n)])
+    assert np.array_equal(_u32(a), _u32(ref))
+    # sharding: two halves with global client ids, summed, equal the single call up to fp32 addition order
+    h1 = dme.quantize_mean(Xd[:8], 1, seed=3, client0=0, n_total=n)
+    h2 = dme.quantize_mean(Xd[8:], 1, seed=3, client0=8, n_total=n)
+    assert np.allclose((h1 + h2).cpu().numpy(), a, rtol=0, atol=4e-7 * np.abs(X).max())
+    host = dme.quantize_mean_host(torch.from_numpy(X).pin_memory(), 1, seed=3).numpy()
+    assert np.array_equal(_u32(host), _u32(a))
+
+
+def test_arena_growth_on_heavy_tails(dme):
+    rng = np.random.default_rng(13)
+    X = (rng.lognormal(1, 2, (3, 50000)) * rng.choice([-1, 1], (3, 50000))).astype(np.float32)
+    pc = dme.type_encode(X, 1, x_inject=[0.2, 0.4, 0.6], codes_bytes=4096)      # far too small: must retry, not corrupt
+    ref = orc.mean_of([orc.type_unbiased(X[c], pc.m, xx)["deq"] for c, xx in enumerate((0.2, 0.4, 0.6))])
+    assert np.array_equal(_u32(dme.decode_mean(pc).cpu().numpy()), _u32(ref))
+
+
+@pytest.mark.parametrize("d,R", [(1 << 20, 1), (1 << 20, 2), (1 << 22, 1)])
+def test_large_rows_vs_oracle(dme, d, R):
+    rng = np.random.default_rng(d + int(R))
+    n = 2
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    Xs = dme.client_uniforms(1, 0, n)
+    out = dme.type_quantize(X, R, seed=1, want=("k", "l1"))
+    for c in range(n):
+        o = orc.type_unbiased(X[c], out["m"], float(Xs[c]))
+        k = out["k"][c].cpu().numpy()
+        assert float(out["l1"][c]) == float(o["L1"])
+        assert int((k != o["k"]).sum()) == 0
+        assert abs(int(k.sum()) - out["m"]) <= 1             # exact mass up to the reference's own fp32 slack
+
+
+def test_full_size_row_properties(dme):
+    """d = 2^24 (BASELINE metric shape, 2 clients): size-independent properties + oracle equality on one row."""
+    d, n, R = 1 << 24, 2, 1
+    g = torch.Generator(device="cuda").manual_seed(42)
+    X = torch.randn((n, d), generator=g, device="cuda", dtype=torch.float32)
+    out = dme.type_quantize(X, R, seed=1234, want=("k", "sgn", "deq", "l1"))
+    m = out["m"]
+    k = out["k"]
+    assert (k >= 0).all()
+    mass = k.sum(dim=1, dtype=torch.int64).cpu().numpy()
+    assert np.all(np.abs(mass - m) <= 1), mass
+    nz = k != 0
+    assert torch.equal(out["sgn"][nz].bool(), (X < 0)[nz])                      # sign preserved
+    fl = torch.floor((X.abs().double() / out["l1"].double()[:, None]) * m).to(torch.int32)
+    assert int(((k - fl) < -1).sum()) == 0 and int(((k - fl) > 2).sum()) == 0   # k in floor(mp) + {0,1} up to fp32 vs fp64 slack
+    # encode -> decode round trip equals the dequantised output
+    pc = dme.type_encode(X[:1], R, seed=1234)
+    mean = dme.decode_mean(pc, n_total=1)
+    assert torch.equal(mean, out["deq"][0])
+    Xs = dme.client_uniforms(1234, 0, 1)
+    o = orc.type_unbiased(X[0].cpu().numpy(), m, float(Xs[0]))
+    assert float(out["l1"][0]) == float(o["L1"])
+    assert int((k[0].cpu().numpy() != o["k"]).sum()) == 0

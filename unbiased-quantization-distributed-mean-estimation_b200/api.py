@@ -1,0 +1,486 @@
+"""Batched host API over the C ABI (include/dme_b200.h).  PyTorch supplies device memory and streams only.
+
+Client vectors are rows of X[n, d] (a single vector is accepted as shape (d,)).  `bits_per_dimension`
+keeps the reference's meaning: m = int(table[R] * d) (AS:614-623); `m=` overrides it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+TILE = 4096
+MODE = {"unbiased": 0, "biased": 1, 0: 0, 1: 1}
+
+# AS:614-620 (the API of the reference: R -> m/d; kept verbatim because it IS the interface)
+RATE_TABLE = {
+    0.5: 0.08282, 1: 0.21403, 1.5: 0.39443, 2: 0.63752, 2.5: 0.96656, 3: 1.41725, 3.5: 2.04187,
+    4: 2.91504, 4.5: 4.14217, 5: 5.87195, 5.5: 8.31416, 6: 11.76507, 6.5: 16.64332, 7: 23.54075,
+    7.5: 33.29414, 8: 47.0868, 8.5: 66.59204, 9: 94.17625, 9.5: 133.18596, 10: 188.35383,
+}
+
+
+class DmeError(RuntimeError):
+    pass
+
+
+def m_for_rate(bits_per_dimension, d: int) -> int:
+    """AS:622-623.  Unknown rates raise KeyError exactly like the reference's dict lookup."""
+    return int(RATE_TABLE[bits_per_dimension] * d)
+
+
+def _check(rc: int):
+    if rc == 0:
+        return
+    msg = _cabi.last_error()
+    if rc == -1:
+        raise ValueError(msg)
+    if rc == -3:
+        raise MemoryError(msg)
+    if rc == -4:
+        raise OverflowError(msg)
+    raise DmeError(f"libdme_b200 error {rc}: {msg}")
+
+
+def _device(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise DmeError("no CUDA device: this package has no CPU fallback (the oracle under oracle/ is test-only)")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _rows(x, device=None):
+    """-> (X2 [n, ld] fp32 contiguous on CUDA with ld % 4 == 0 and 16-byte aligned rows, n, d, was_1d)."""
+    dev = _device(device)
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    elif not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(x)
+    was_1d = x.dim() == 1
+    if was_1d:
+        x = x.unsqueeze(0)
+    if x.dim() != 2:
+        raise ValueError("expected a vector (d,) or a matrix of client rows (n, d)")
+    x = x.to(device=dev, dtype=torch.float32)
+    n, d = x.shape
+    if d == 0 or n == 0:
+        raise ValueError("empty input")
+    ok = x.stride(1) == 1 and (n == 1 or x.stride(0) % 4 == 0) and x.data_ptr() % 16 == 0 and (n == 1 or x.stride(0) >= d)
+    if not ok:
+        ld = (d + 3) // 4 * 4
+        buf = torch.zeros((n, ld), dtype=torch.float32, device=dev)
+        buf[:, :d] = x
+        x = buf[:, :d]
+    return x, n, d, was_1d
+
+
+def _ld(x) -> int:
+    n, d = x.shape
+    return x.stride(0) if n > 1 else (d + 3) // 4 * 4
+
+
+class Workspace:
+    """Caller-owned scratch for the type-quantizer entry points (grown on demand, one per device)."""
+    _cache = {}
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = None
+
+    @classmethod
+    def get(cls, device) -> "Workspace":
+        key = (device.type, device.index)
+        if key not in cls._cache:
+            cls._cache[key] = Workspace(device)
+        return cls._cache[key]
+
+    def ensure(self, n: int, d: int):
+        need = int(_cabi.lib().dme_workspace_bytes(n, d))
+        if self.buf is None or self.buf.numel() < need + 256:
+            self.buf = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+        off = (-self.buf.data_ptr()) % 256
+        return C.c_void_p(self.buf.data_ptr() + off), need
+
+    def status(self):
+        off = (-self.buf.data_ptr()) % 256
+        _check(_cabi.lib().dme_status(C.c_void_p(self.buf.data_ptr() + off), C.c_void_p(_stream())))
+
+
+def client_uniforms(seed: int, client0: int, n: int) -> np.ndarray:
+    """X_c for clients client0 .. client0+n-1: the same Philox draw the kernels make (AS:634)."""
+    L = _cabi.lib()
+    return np.array([L.dme_uniform_x(seed, client0 + c) for c in range(n)], dtype=np.float32)
+
+
+def _resolve_m(d, bits_per_dimension, m):
+    return int(m) if m is not None else m_for_rate(bits_per_dimension, d)
+
+
+def _opt_vec(v, n, dev):
+    if v is None:
+        return None
+    t = torch.as_tensor(np.asarray(v, dtype=np.float32) if not isinstance(v, torch.Tensor) else v, dtype=torch.float32).to(dev).reshape(-1).contiguous()
+    if t.numel() != n:
+        raise ValueError(f"expected {n} injected values, got {t.numel()}")
+    return t
+
+
+def l1_norms(x):
+    """AS:624: per-row sum |x| (fp64 accumulate, fp32 result)."""
+    X, n, d, _ = _rows(x)
+    ws, wsb = Workspace.get(X.device).ensure(n, d)
+    out = torch.empty(n, dtype=torch.float32, device=X.device)
+    _check(_cabi.lib().dme_l1_norms(_ptr(X), n, d, _ld(X), _ptr(out), ws, wsb, C.c_void_p(_stream())))
+    return out
+
+
+def type_quantize(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, client0=0, x_inject=None, l1_inject=None,
+                  want=("deq",), check=True):
+    """Type_unbiased_quantize / Type_biased_quantize (AS:609-641, AS:669-687) on every row.
+
+    want: any of "deq" (what the reference returns), "k" (int32 magnitudes), "sgn" (uint8 sign bits), "l1".
+    Returns a dict of CUDA tensors shaped like the input."""
+    X, n, d, was_1d = _rows(x)
+    mm = _resolve_m(d, bits_per_dimension, m)
+    dev = X.device
+    ws, wsb = Workspace.get(dev).ensure(n, d)
+    ldo = (d + 3) // 4 * 4
+    k = torch.empty((n, ldo), dtype=torch.int32, device=dev) if "k" in want else None
+    s = torch.empty((n, ldo), dtype=torch.uint8, device=dev) if "sgn" in want else None
+    q = torch.empty((n, ldo), dtype=torch.float32, device=dev) if "deq" in want else None
+    l1 = torch.empty(n, dtype=torch.float32, device=dev)
+    xi, li = _opt_vec(x_inject, n, dev), _opt_vec(l1_inject, n, dev)
+    _check(_cabi.lib().dme_type_quantize(_ptr(X), n, d, _ld(X), mm, MODE[mode], _ptr(xi), _ptr(li), seed, client0,
+                                         _ptr(k), _ptr(s), _ptr(q), ldo, _ptr(l1), ws, wsb, C.c_void_p(_stream())))
+    if check and k is not None:
+        Workspace.get(dev).status()
+    out = {"m": mm, "l1": l1}
+    for name, t in (("k", k), ("sgn", s), ("deq", q)):
+        if t is not None:
+            t = t[:, :d]
+            out[name] = t[0] if was_1d else t
+    return out
+
+
+@dataclass
+class PackedCodes:
+    """Packed code DMEP1 of n client rows (include/dme_b200.h): arena + tile directory + fp32 L1 norms."""
+    codes: torch.Tensor     # uint8 arena
+    dir: torch.Tensor       # int64 view of uint64 entries: (offset/16) << 8 | width
+    l1: torch.Tensor        # float32 [n]
+    n: int
+    d: int
+    m: int
+    mode: int
+
+    def tile(self, c: int, t: int):
+        """(width, uint32 words) of one tile, on the host (tests / serialisation)."""
+        T = (self.d + TILE - 1) // TILE
+        e = int(self.dir[c * T + t].item()) & 0xFFFFFFFFFFFFFFFF
+        w, off = e & 0xFF, (e >> 8) * 16
+        words = self.codes[off: off + 512 * w].cpu().numpy().view(np.uint32)
+        return w, words
+
+    def payload_bytes(self) -> int:
+        w = (self.dir & 0xFF).sum().item()
+        return int(w) * 512
+
+
+def type_encode(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, client0=0, x_inject=None, l1_inject=None,
+                codes_bytes=None, check=True) -> PackedCodes:
+    """Quantize every row and emit the packed code (sign/magnitude fields, per-tile width)."""
+    X, n, d, _ = _rows(x)
+    mm = _resolve_m(d, bits_per_dimension, m)
+    dev = X.device
+    L = _cabi.lib()
+    ws, wsb = Workspace.get(dev).ensure(n, d)
+    cb = int(codes_bytes) if codes_bytes is not None else int(L.dme_codes_bytes(n, d, mm, 1))
+    xi, li = _opt_vec(x_inject, n, dev), _opt_vec(l1_inject, n, dev)
+    while True:
+        codes = torch.empty(cb, dtype=torch.uint8, device=dev)
+        dr = torch.empty(int(L.dme_dir_entries(n, d)), dtype=torch.int64, device=dev)
+        l1 = torch.empty(n, dtype=torch.float32, device=dev)
+        _check(L.dme_type_encode(_ptr(X), n, d, _ld(X), mm, MODE[mode], _ptr(xi), _ptr(li), seed, client0, _ptr(codes), cb,
+                                 _ptr(dr), _ptr(l1), ws, wsb, C.c_void_p(_stream())))
+        if not check:
+            break
+        try:
+            Workspace.get(dev).status()
+            break
+        except MemoryError:
+            worst = int(L.dme_codes_bytes(n, d, mm, 0))
+            if cb >= worst:
+                raise
+            cb = worst                       # heavy-tailed input: retry with the worst-case arena
+    return PackedCodes(codes, dr, l1, n, d, mm, MODE[mode])
+
+
+def decode_mean(pc: PackedCodes, *, n_total=None, out=None, accumulate=False):
+    """Server side: dequantise (AS:640 / AS:687) and average, `est += q / n` in client order (ND:133-147)."""
+    dev = pc.codes.device
+    if out is None:
+        out = torch.empty(pc.d, dtype=torch.float32, device=dev)
+        accumulate = False
+    nt = pc.n if n_total is None else int(n_total)
+    _check(_cabi.lib().dme_decode_mean(_ptr(pc.codes), _ptr(pc.dir), _ptr(pc.l1), pc.n, pc.d, pc.m, pc.mode, nt, _ptr(out),
+                                       int(bool(accumulate)), C.c_void_p(_stream())))
+    return out
+
+
+class _MeanPlan:
+    """Reusable buffers of the fused quantize->decode->mean call for one (n, d, m) shape."""
+    _cache = {}
+
+    def __init__(self, n, d, m, dev):
+        L = _cabi.lib()
+        self.cb = int(L.dme_codes_bytes(n, d, m, 1))
+        self.codes = torch.empty(self.cb, dtype=torch.uint8, device=dev)
+        self.dir = torch.empty(int(L.dme_dir_entries(n, d)), dtype=torch.int64, device=dev)
+        self.l1 = torch.empty(n, dtype=torch.float32, device=dev)
+
+    @classmethod
+    def get(cls, n, d, m, dev):
+        key = (n, d, m, dev.index)
+        if key not in cls._cache:
+            cls._cache.clear()              # keep one plan: the arena can be GiBs
+            cls._cache[key] = _MeanPlan(n, d, m, dev)
+        return cls._cache[key]
+
+    def grow_worst_case(self, n, d, m, dev):
+        self.cb = int(_cabi.lib().dme_codes_bytes(n, d, m, 0))
+        self.codes = torch.empty(self.cb, dtype=torch.uint8, device=dev)
+
+
+def quantize_mean(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, client0=0, n_total=None, x_inject=None,
+                  out=None, accumulate=False, check=True):
+    """The north-star path: quantize all rows, pack, decode and average -> mean[d] (fp32, CUDA).
+
+    n_total: divisor of the mean (defaults to the number of rows; pass the global client count when the rows are
+    one GPU's shard and the partial results are summed with one all-reduce, see `distributed.py`)."""
+    X, n, d, _ = _rows(x)
+    mm = _resolve_m(d, bits_per_dimension, m)
+    dev = X.device
+    L = _cabi.lib()
+    ws, wsb = Workspace.get(dev).ensure(n, d)
+    plan = _MeanPlan.get(n, d, mm, dev)
+    if out is None:
+        out = torch.empty(d, dtype=torch.float32, device=dev)
+        accumulate = False
+    xi = _opt_vec(x_inject, n, dev)
+    nt = n if n_total is None else int(n_total)
+    while True:
+        _check(L.dme_quantize_mean(_ptr(X), n, d, _ld(X), mm, MODE[mode], _ptr(xi), seed, client0, nt, _ptr(out),
+                                   int(bool(accumulate)), _ptr(plan.codes), plan.cb, _ptr(plan.dir), _ptr(plan.l1), ws, wsb,
+                                   C.c_void_p(_stream())))
+        if not check:
+            return out
+        try:
+            Workspace.get(dev).status()
+            return out
+        except MemoryError:
+            if accumulate or plan.cb >= int(L.dme_codes_bytes(n, d, mm, 0)):
+                raise
+            plan.grow_worst_case(n, d, mm, dev)
+
+
+def quantize_mean_host(x_host, bits_per_dimension=1, *, out_host=None, **kw):
+    """End-to-end call with HOST buffers: H2D copy of the client rows, fused path, D2H copy of the mean."""
+    dev = _device()
+    xh = x_host if isinstance(x_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x_host, dtype=np.float32))
+    xd = xh.to(dev, non_blocking=True)
+    mean = quantize_mean(xd, bits_per_dimension, **kw)
+    if out_host is None:
+        out_host = torch.empty(mean.shape, dtype=torch.float32, pin_memory=True)
+    out_host.copy_(mean, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return out_host
+
+
+def mean_accumulate(q, *, n_total=None, out=None, accumulate=False):
+    """ND:133-147 for dequantised rows: out (+)= sum_c q[c] / n_total, clients in order."""
+    Q, n, d, _ = _rows(q)
+    if out is None:
+        out = torch.empty(d, dtype=torch.float32, device=Q.device)
+        accumulate = False
+    _check(_cabi.lib().dme_mean_accumulate(_ptr(Q), n, d, _ld(Q), n if n_total is None else int(n_total), _ptr(out),
+                                           int(bool(accumulate)), C.c_void_p(_stream())))
+    return out
+
+
+# ------------------------------------------------------------------ rotations
+def _pow2_ceil(d: int) -> int:
+    return 1 << max(0, math.ceil(math.log2(d))) if d > 1 else 1
+
+
+def _diag(diag_inject, dpad, dev):
+    if diag_inject is None:
+        return None
+    t = torch.as_tensor(diag_inject, dtype=torch.float32).to(dev).reshape(-1).contiguous()
+    if t.numel() != dpad:
+        raise ValueError(f"diag_inject must have {dpad} entries")
+    return t
+
+
+def hadamard(v):
+    """Hadamard.hadamard (AS:100-115): normalised natural-order WHT of every row; a copy is returned."""
+    V, n, d, was_1d = _rows(v)
+    if d & (d - 1):
+        raise Exception("input numel must be a power of 2")      # AS:103-104, same type and message
+    V = V.clone() if V.data_ptr() == (v.data_ptr() if isinstance(v, torch.Tensor) else 0) else V
+    V = V.contiguous()
+    _check(_cabi.lib().dme_hadamard(_ptr(V), n, d, _ld(V), C.c_void_p(_stream())))
+    return V[0] if was_1d else V
+
+
+def rademacher(dpad: int, seed: int):
+    """The +-1 diagonal the kernels derive from Philox(seed, coordinate) (stands in for AS:117-120)."""
+    out = torch.empty(dpad, dtype=torch.float32, device=_device())
+    _check(_cabi.lib().dme_rademacher(_ptr(out), dpad, seed, C.c_void_p(_stream())))
+    return out
+
+
+def rht(x, seed=0, *, diag_inject=None):
+    """HadamardSender.randomized_hadamard_transform (AS:127-144): pad to a power of two, H(D x)/sqrt(dpad)."""
+    X, n, d, was_1d = _rows(x)
+    dpad = _pow2_ceil(d)
+    out = torch.empty((n, dpad), dtype=torch.float32, device=X.device)
+    dg = _diag(diag_inject, dpad, X.device)
+    _check(_cabi.lib().dme_rht(_ptr(X), n, d, _ld(X), _ptr(out), dpad, max(dpad, 4) if n > 1 else (dpad + 3) // 4 * 4, seed, _ptr(dg),
+                               C.c_void_p(_stream())) if dpad >= 4 or n == 1 else -1)
+    return out[0] if was_1d else out
+
+
+def irht(v, seed=0, *, diag_inject=None):
+    """HadamardReceiver.randomized_inverse_hadamard_transform (AS:151-156); returns a new tensor."""
+    V, n, d, was_1d = _rows(v)
+    if d & (d - 1):
+        raise Exception("input numel must be a power of 2")
+    V = V.clone().contiguous()
+    dg = _diag(diag_inject, d, V.device)
+    _check(_cabi.lib().dme_irht(_ptr(V), n, d, _ld(V), seed, _ptr(dg), C.c_void_p(_stream())))
+    return V[0] if was_1d else V
+
+
+def pair_transform(v):
+    """`fast_walsh_hadamard_transform` as the reference executes it (AS:37-59)."""
+    V, n, d, was_1d = _rows(v)
+    if d & (d - 1):
+        raise Exception("input numel must be a power of 2")
+    V = V.clone().contiguous()
+    _check(_cabi.lib().dme_pair_transform(_ptr(V), n, d, _ld(V), C.c_void_p(_stream())))
+    return V[0] if was_1d else V
+
+
+# ------------------------------------------------------------------ comparison quantizers
+def drive_padded_len(d: int) -> int:
+    tot, s0 = 0, 0
+    while s0 < d:
+        tot += _pow2_ceil(min(2048, d - s0))
+        s0 += 2048
+    return tot
+
+
+def drive(x, *, seed=0, dsign_inject=None, compat="reference"):
+    """DRIVE_quantize_Hadamard (AS:707-752).  compat="reference" reproduces the reference's transform,
+    compat="correct" uses a true Walsh-Hadamard transform."""
+    X, n, d, was_1d = _rows(x)
+    out = torch.empty((n, (d + 3) // 4 * 4), dtype=torch.float32, device=X.device)
+    ds = None
+    if dsign_inject is not None:
+        ds = torch.as_tensor(dsign_inject, dtype=torch.float32).to(X.device).reshape(-1).contiguous()
+        if ds.numel() != n * drive_padded_len(d):
+            raise ValueError("dsign_inject has the wrong length")
+    _check(_cabi.lib().dme_drive(_ptr(X), n, d, _ld(X), _ptr(out), out.stride(0), seed, _ptr(ds), {"reference": 0, "correct": 1}[compat],
+                                 C.c_void_p(_stream())))
+    out = out[:, :d]
+    return out[0] if was_1d else out
+
+
+def eden_encode(x, nbits=1, *, seed=0, diag_inject=None, norm_inject=None):
+    """EdenSender.compress (AS:370-390, integer nbits in {1,2}) -> dict(bins uint8 [n,dpad], scale [n], rot [n,dpad])."""
+    if nbits not in (1, 2):
+        raise KeyError(nbits)           # AS:301-320 defines centroids for 1 and 2 bits only
+    X, n, d, was_1d = _rows(x)
+    dpad = max(_pow2_ceil(d), 4)
+    dev = X.device
+    rot = torch.empty((n, dpad), dtype=torch.float32, device=dev)
+    bins = torch.empty((n, dpad), dtype=torch.uint8, device=dev)
+    scale = torch.empty(n, dtype=torch.float32, device=dev)
+    dg = _diag(diag_inject, dpad, dev)
+    ni = _opt_vec(norm_inject, n, dev)
+    _check(_cabi.lib().dme_eden_encode(_ptr(X), n, d, _ld(X), dpad, nbits, seed, _ptr(dg), _ptr(ni), _ptr(rot), _ptr(bins), _ptr(scale),
+                                       C.c_void_p(_stream())))
+    return {"bins": bins, "scale": scale, "rot": rot, "d": d, "dpad": dpad, "nbits": nbits, "seed": seed, "was_1d": was_1d}
+
+
+def eden_decode(enc, *, diag_inject=None):
+    """EdenReceiver.decompress (AS:398-426)."""
+    bins, scale = enc["bins"], enc["scale"]
+    n, dpad = bins.shape
+    d = enc["d"]
+    dev = bins.device
+    work = torch.empty((n, dpad), dtype=torch.float32, device=dev)
+    out = torch.empty((n, (d + 3) // 4 * 4), dtype=torch.float32, device=dev)
+    dg = _diag(diag_inject, dpad, dev)
+    _check(_cabi.lib().dme_eden_decode(_ptr(bins), _ptr(scale), n, d, dpad, enc["nbits"], enc["seed"], _ptr(dg), _ptr(work), _ptr(out),
+                                       out.stride(0), C.c_void_p(_stream())))
+    out = out[:, :d]
+    return out[0] if enc.get("was_1d") else out
+
+
+def eden(x, nbits=1, *, seed=0, diag_inject=None):
+    return eden_decode(eden_encode(x, nbits, seed=seed, diag_inject=diag_inject), diag_inject=diag_inject)
+
+
+def quicfl_decode(Xq, h, d, recv_table, scale, *, exact_mask=None, exact_vals=None, rotation_seed=123, diag_inject=None):
+    """QuicFLReceiver.decompress (AS:526-535) for rows Xq[n, dpad]."""
+    dev = _device()
+    Xq = torch.as_tensor(Xq).to(dev, torch.int32)
+    was_1d = Xq.dim() == 1
+    if was_1d:
+        Xq = Xq.unsqueeze(0)
+    Xq = Xq.contiguous()
+    n, dpad = Xq.shape
+    h = torch.as_tensor(h).to(dev, torch.int32).reshape(n, dpad).contiguous()
+    tab = torch.as_tensor(recv_table, dtype=torch.float32).to(dev).contiguous()
+    h_len = tab.shape[-1]
+    sc = torch.as_tensor(scale, dtype=torch.float32).to(dev).reshape(-1).contiguous()
+    em = ev = eo = None
+    if exact_mask is not None:
+        em = torch.as_tensor(exact_mask).to(dev, torch.uint8).reshape(n, dpad).contiguous()
+        cnt = em.sum(dim=1, dtype=torch.int64)
+        eo = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        eo[1:] = torch.cumsum(cnt, 0)
+        ev = torch.as_tensor(exact_vals, dtype=torch.float32).to(dev).reshape(-1).contiguous()
+    work = torch.empty((n, dpad), dtype=torch.float32, device=dev)
+    out = torch.empty((n, (d + 3) // 4 * 4), dtype=torch.float32, device=dev)
+    dg = _diag(diag_inject, dpad, dev)
+    _check(_cabi.lib().dme_quicfl_decode(_ptr(Xq), _ptr(h), n, d, dpad, h_len, _ptr(tab), tab.numel(), _ptr(em), _ptr(ev), _ptr(eo),
+                                         _ptr(sc), rotation_seed, _ptr(dg), _ptr(work), _ptr(out), out.stride(0), C.c_void_p(_stream())))
+    out = out[:, :d]
+    return out[0] if was_1d else out
+
+
+def scalar_quantize(x, bits_per_dimension=1, *, seed=0, client0=0, u_inject=None):
+    """Scalar_quantize (AS:755-790)."""
+    X, n, d, was_1d = _rows(x)
+    out = torch.empty((n, (d + 3) // 4 * 4), dtype=torch.float32, device=X.device)
+    u = None
+    if u_inject is not None:
+        u = torch.as_tensor(u_inject, dtype=torch.float32).to(X.device).reshape(n, d).contiguous()
+    _check(_cabi.lib().dme_scalar_quantize(_ptr(X), n, d, _ld(X), float(2 ** bits_per_dimension - 1), seed, client0, _ptr(u), _ptr(out),
+                                           out.stride(0), C.c_void_p(_stream())))
+    out = out[:, :d]
+    return out[0] if was_1d else out

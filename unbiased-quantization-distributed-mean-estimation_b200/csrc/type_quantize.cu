@@ -1,0 +1,525 @@
+// type_quantize.cu -- unbiased type-based L1-ball quantizer (AS:609-641), packed-code emit, decode + mean
+// (AS:640 + ND:133-147).  Hand-written for sm_100a; no CPU fallback.
+//
+// Numerics contract (oracle/dme_oracle.c header): fp64-accumulated L1 rounded to fp32; the elementwise chain
+// of AS:625-631 in fp32 with IEEE division; prefix of fractional parts accumulated in fp64 and rounded to
+// fp32 (what torch.cumsum does on CPU); r_i = [floor(c_i - X) - floor(c_{i-1} - X) == 1] in fp32.
+//
+// Kernel structure (one row = one client vector, tiles of 4096 coordinates, thread t owns 16 consecutive
+// coordinates so that the in-thread part of the prefix is a plain sequential sum):
+//   l1_kernel      : per-tile fp64 partial sums; the LAST tile of a row to finish reduces the partials in
+//                    index order and publishes the row constants (deterministic, no float atomics).
+//   scan_kernel<E> : single pass over the row in ticket order with a decoupled look-back across tiles.
+//                    The exclusive prefix of a tile is the canonical left-to-right sum of tile aggregates
+//                    (start at the nearest published inclusive prefix, add the aggregates after it in
+//                    order), so the result does not depend on timing.  floor(c - X) of a tile's last
+//                    coordinate is handed to the next tile through the descriptor (each a_i is computed once).
+//   decode_mean_kernel : tile-major over d, clients in order in registers, one write of the mean.
+#include "type_quantize.cuh"
+
+namespace dme {
+
+// ------------------------------------------------------------------ tile load (blocked: 16 / thread)
+__device__ __forceinline__ void load_tile(const float *__restrict__ row, int64_t d, int64_t tile0, float (&x)[kEpt]) {
+    const int64_t i0 = tile0 + (int64_t)threadIdx.x * kEpt;
+    if (i0 + kEpt <= d) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 v = ldg_stream_f4(row + i0 + 4 * q);
+            x[4 * q + 0] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) x[j] = (i0 + j < d) ? row[i0 + j] : 0.0f;
+    }
+}
+
+// ------------------------------------------------------------------ K1: L1 norms
+// grid (T, n).  partial[c*T + t] = sum over the tile of |x| in fp64 (fixed association).
+__global__ void __launch_bounds__(kThreads)
+l1_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t m, int64_t T,
+          double *__restrict__ partial, uint32_t *__restrict__ a_done, RowConst *__restrict__ consts,
+          const float *__restrict__ x_inject, const float *__restrict__ l1_inject, uint64_t seed,
+          uint64_t client0, float *__restrict__ l1_out) {
+    __shared__ double s_red[kWarps];
+    __shared__ uint32_t s_last;
+    const int64_t c = blockIdx.y, t = blockIdx.x;
+    const float *row = X + c * ld;
+    float x[kEpt];
+    load_tile(row, d, t * kTile, x);
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < kEpt; ++j) s += (double)fabsf(x[j]);
+    s = block_sum_f64(s, s_red);
+    if (threadIdx.x == 0) {
+        partial[c * T + t] = s;
+        __threadfence();
+        s_last = (atomicAdd(&a_done[c], 1u) == (uint32_t)(T - 1)) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // Last tile of the row: reduce the T partials in a fixed order (thread-strided, then block tree).
+    const volatile double *pp = partial + c * T;
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < T; i += kThreads) acc += pp[i];
+    acc = block_sum_f64(acc, s_red);
+    if (threadIdx.x == 0) {
+        RowConst rc;
+        rc.L1f = l1_inject ? l1_inject[c] : (float)acc;               // AS:624
+        rc.D = __fadd_rn(rc.L1f, 1e-12f);                             // AS:625
+        rc.mf = (float)m;
+        rc.X = x_inject ? x_inject[c] : philox_client_uniform(seed, client0 + (uint64_t)c);   // AS:634
+        rc.rcpD = __frcp_rn(rc.D);
+        rc.pad[0] = rc.pad[1] = rc.pad[2] = 0.0f;
+        consts[c] = rc;
+        if (l1_out) l1_out[c] = rc.L1f;
+    }
+}
+
+// ------------------------------------------------------------------ look-back (warp 0 of a tile CTA)
+// Returns the canonical exclusive prefix of tile t: ((incl_{t-f-1} + A_{t-f}) + ...) + A_{t-1}.
+__device__ __forceinline__ double lookback_exclusive(TileDesc *rowdesc, int64_t t, int lane) {
+    while (true) {
+        const int64_t idx = t - 1 - lane;
+        const uint32_t st = idx >= 0 ? ld_acquire_u32(&rowdesc[idx].state) : 2u;   // virtual tile -1: inclusive 0
+        const unsigned incl = __ballot_sync(0xffffffffu, st >= 2u);
+        const unsigned zero = __ballot_sync(0xffffffffu, st == 0u);
+        if (incl == 0u) { __nanosleep(40); continue; }
+        const int f = __ffs(incl) - 1;
+        const unsigned need = (f == 31) ? 0xffffffffu : ((1u << (f + 1)) - 1u);
+        if (zero & need) { __nanosleep(40); continue; }
+        double v = 0.0;
+        if (lane < f) v = ld_relaxed_f64(&rowdesc[idx].aggregate);
+        else if (lane == f && idx >= 0) v = ld_relaxed_f64(&rowdesc[idx].inclusive);
+        double P = __shfl_sync(0xffffffffu, v, f);
+        for (int l = f - 1; l >= 0; --l) P += __shfl_sync(0xffffffffu, v, l);
+        return P;
+    }
+}
+
+enum Emit { kEmitArrays = 0, kEmitPacked = 1 };
+
+struct ScanArgs {
+    const float *X; int64_t d, ld, T, n;
+    const RowConst *consts; TileDesc *desc; WsHeader *hdr;
+    // arrays
+    int32_t *k_out; uint8_t *sgn_out; float *deq_out; int64_t ld_out;
+    // packed
+    uint32_t *codes; int64_t codes_bytes; uint64_t *dir;
+};
+
+// Pack 16 (magnitude, sign) pairs of one thread with field width W into W/2 words.
+template <int W>
+__device__ __forceinline__ void pack_store(const uint32_t (&k)[kEpt], const uint32_t (&sg)[kEpt], uint32_t *tile_words) {
+    constexpr int kPerWord = 32 / W;
+#pragma unroll
+    for (int q = 0; q < W / 2; ++q) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int e = 0; e < kPerWord; ++e) {
+            const int j = q * kPerWord + e;
+            const uint32_t field = (W == 32) ? ((sg[j] << 31) | k[j]) : ((sg[j] << (W - 1)) | k[j]);
+            word |= field << ((W * e) & 31);
+        }
+        tile_words[q * kThreads + threadIdx.x] = word;
+    }
+}
+
+// ------------------------------------------------------------------ K2+K3+K5(+K6): scan / quantize / emit
+template <int EMIT>
+__global__ void __launch_bounds__(kThreads)
+scan_kernel(ScanArgs a) {
+    __shared__ double s_wtot[kWarps];
+    __shared__ double s_P;
+    __shared__ int s_alast[kWarps];
+    __shared__ uint32_t s_u32[kWarps];
+    __shared__ uint32_t s_ticket;
+    __shared__ unsigned long long s_off16;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&a.hdr->ticket, 1u);
+    __syncthreads();
+    const int64_t ticket = s_ticket;
+    const int64_t c = ticket / a.T, t = ticket - c * a.T;
+    const RowConst rc = a.consts[c];
+    TileDesc *rowdesc = a.desc + c * a.T;
+    const float *row = a.X + c * a.ld;
+
+    float x[kEpt];
+    load_tile(row, a.d, t * kTile, x);
+
+    // AS:625-631, fp32, one rounding per operation
+    float fl[kEpt], fr[kEpt];
+    double S = 0.0;
+#pragma unroll
+    for (int j = 0; j < kEpt; ++j) {
+        const float v = __fdiv_rn(x[j], rc.D);
+        const float p = fabsf(v);
+        const float mp = __fmul_rn(rc.mf, p);
+        fl[j] = floorf(mp);
+        fr[j] = __fsub_rn(mp, fl[j]);
+        S += (double)fr[j];
+    }
+    // block scan of the thread sums (Kogge-Stone inside a warp, warps in order)
+    double incl = S;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 0.0;
+    if (lane == 31) s_wtot[warp] = incl;
+    __syncthreads();
+    double wbase = 0.0, A = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        if (w == warp) wbase = A;
+        A += s_wtot[w];
+    }
+    if (warp == 0) {
+        TileDesc *me = rowdesc + t;
+        double P = 0.0;
+        if (t == 0) {
+            if (lane == 0) { me->aggregate = A; me->inclusive = A; st_release_u32(&me->state, 2u); }
+        } else {
+            if (lane == 0) { me->aggregate = A; st_release_u32(&me->state, 1u); }
+            P = lookback_exclusive(rowdesc, t, lane);
+            if (lane == 0) { me->inclusive = P + A; st_release_u32(&me->state, 2u); }
+        }
+        if (lane == 0) s_P = P;
+    }
+    __syncthreads();
+    // prefix -> fp32 -> floor(c - X)   (AS:635-636)
+    double C = s_P + (wbase + excl);
+    int av[kEpt];
+#pragma unroll
+    for (int j = 0; j < kEpt; ++j) {
+        C += (double)fr[j];
+        const float c32 = (float)C;
+        av[j] = __float2int_rd(__fsub_rn(c32, rc.X));
+    }
+    if (threadIdx.x == kThreads - 1) {
+        TileDesc *me = rowdesc + t;
+        me->a_last = av[kEpt - 1];
+        st_release_u32(&me->a_state, 1u);
+    }
+    int aprev = __shfl_up_sync(0xffffffffu, av[kEpt - 1], 1);
+    if (lane == 31) s_alast[warp] = av[kEpt - 1];
+    __syncthreads();
+    if (lane == 0) {
+        if (warp > 0) aprev = s_alast[warp - 1];
+        else if (t == 0) aprev = __float2int_rd(__fsub_rn(0.0f, rc.X));            // c_0 = 0 (AS:635)
+        else {
+            const TileDesc *pv = rowdesc + (t - 1);
+            while (ld_acquire_u32(&pv->a_state) == 0u) __nanosleep(40);
+            aprev = ld_relaxed_s32(&pv->a_last);
+        }
+    }
+    float kf[kEpt];
+#pragma unroll
+    for (int j = 0; j < kEpt; ++j) {
+        const int r = (av[j] - aprev == 1) ? 1 : 0;                                 // AS:636-637
+        aprev = av[j];
+        kf[j] = __fadd_rn(fl[j], (float)r);
+    }
+
+    const int64_t i0 = t * kTile + (int64_t)threadIdx.x * kEpt;
+    if (EMIT == kEmitArrays) {
+        bool ovf = false;
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) {
+            const int64_t i = i0 + j;
+            if (i >= a.d) break;
+            if (a.deq_out) {
+                const float v = __fdiv_rn(x[j], rc.D);
+                const float sg = (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f);
+                a.deq_out[c * a.ld_out + i] = __fdiv_rn(__fmul_rn(__fmul_rn(rc.L1f, sg), kf[j]), rc.mf);   // AS:640
+            }
+            if (a.k_out) {
+                if (kf[j] >= 2147483648.0f) { ovf = true; a.k_out[c * a.ld_out + i] = 0x7fffffff; }
+                else a.k_out[c * a.ld_out + i] = (int32_t)kf[j];
+            }
+            if (a.sgn_out) a.sgn_out[c * a.ld_out + i] = (uint8_t)(__float_as_uint(x[j]) >> 31);
+        }
+        if (ovf) atomicOr(&a.hdr->status, 1u);
+    } else {
+        uint32_t k[kEpt], sg[kEpt], kmax = 0;
+        bool ovf = false;
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) {
+            if (kf[j] >= 2147483648.0f) { ovf = true; k[j] = 0x7fffffffu; } else k[j] = (uint32_t)kf[j];
+            sg[j] = __float_as_uint(x[j]) >> 31;
+            kmax = max(kmax, k[j]);
+        }
+        if (ovf) atomicOr(&a.hdr->status, 1u);
+        kmax = __reduce_max_sync(0xffffffffu, kmax);
+        if (lane == 0) s_u32[warp] = kmax;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) kmax = max(kmax, s_u32[w]);
+        int W = 2;
+        while (W < 32 && kmax >= (1u << (W - 1))) W <<= 1;
+        if (threadIdx.x == 0) {
+            const unsigned long long units = 32ull * W;                      // 512*W bytes / 16
+            unsigned long long off = atomicAdd(&a.hdr->arena_top, units);
+            if ((long long)((off + units) * 16ull) > a.codes_bytes) { atomicOr(&a.hdr->status, 2u); off = ~0ull; }
+            s_off16 = off;
+            a.dir[c * a.T + t] = (off == ~0ull) ? 0ull : ((off << 8) | (unsigned long long)W);
+        }
+        __syncthreads();
+        if (s_off16 != ~0ull) {
+            uint32_t *tw = a.codes + s_off16 * 4ull;
+            switch (W) {
+                case 2: pack_store<2>(k, sg, tw); break;
+                case 4: pack_store<4>(k, sg, tw); break;
+                case 8: pack_store<8>(k, sg, tw); break;
+                case 16: pack_store<16>(k, sg, tw); break;
+                default: pack_store<32>(k, sg, tw); break;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K7: decode + mean (tile-major)
+template <int W>
+__device__ __forceinline__ void decode_accumulate(const uint32_t *__restrict__ tw, float L1f, float mf, float nf, int biased,
+                                                  float (&acc)[kEpt]) {
+    constexpr int kPerWord = 32 / W;
+#pragma unroll
+    for (int q = 0; q < W / 2; ++q) {
+        const uint32_t word = __ldg(tw + q * kThreads + threadIdx.x);
+#pragma unroll
+        for (int e = 0; e < kPerWord; ++e) {
+            const int j = q * kPerWord + e;
+            const uint32_t field = (W == 32) ? word : ((word >> (W * e)) & ((1u << W) - 1u));
+            const uint32_t mag = (W == 32) ? (field & 0x7fffffffu) : (field & ((1u << (W - 1)) - 1u));
+            if (mag != 0u) {
+                const float sg = (field >> (W - 1)) ? -1.0f : 1.0f;
+                const float kf = (float)mag;
+                const float q32 = biased ? __fmul_rn(__fmul_rn(L1f, sg), __fdiv_rn(kf, mf))          // AS:687
+                                         : __fdiv_rn(__fmul_rn(__fmul_rn(L1f, sg), kf), mf);        // AS:640
+                acc[j] = __fadd_rn(acc[j], __fdiv_rn(q32, nf));                                       // ND:137
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+decode_mean_kernel(const uint32_t *__restrict__ codes, const uint64_t *__restrict__ dir, const float *__restrict__ l1,
+                   int64_t n, int64_t d, int64_t T, float mf, float nf, int biased, float *__restrict__ mean, int accumulate) {
+    const int64_t t = blockIdx.x;
+    const int64_t i0 = t * kTile + (int64_t)threadIdx.x * kEpt;
+    float acc[kEpt];
+#pragma unroll
+    for (int j = 0; j < kEpt; ++j) acc[j] = (accumulate && i0 + j < d) ? mean[i0 + j] : 0.0f;
+    for (int64_t c = 0; c < n; ++c) {
+        const uint64_t e = __ldg(dir + c * T + t);
+        const int W = (int)(e & 0xffu);
+        const uint32_t *tw = codes + (e >> 8) * 4ull;
+        const float L1f = __ldg(l1 + c);
+        switch (W) {
+            case 2: decode_accumulate<2>(tw, L1f, mf, nf, biased, acc); break;
+            case 4: decode_accumulate<4>(tw, L1f, mf, nf, biased, acc); break;
+            case 8: decode_accumulate<8>(tw, L1f, mf, nf, biased, acc); break;
+            case 16: decode_accumulate<16>(tw, L1f, mf, nf, biased, acc); break;
+            case 32: decode_accumulate<32>(tw, L1f, mf, nf, biased, acc); break;
+            default: break;   // width 0: tile was dropped (arena exhausted; status bit 2 is set)
+        }
+    }
+    if (i0 + kEpt <= d) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4 *>(mean + i0 + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j)
+            if (i0 + j < d) mean[i0 + j] = acc[j];
+    }
+}
+
+// mean (+)= sum_c Q[c] / n for dequantised rows (ND:133-147), coalesced, clients in order.
+__global__ void mean_accumulate_kernel(const float *__restrict__ Q, int64_t n, int64_t d, int64_t ld, float nf,
+                                       float *__restrict__ mean, int accumulate) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d) return;
+    float acc = accumulate ? mean[i] : 0.0f;
+    for (int64_t c = 0; c < n; ++c) acc = __fadd_rn(acc, __fdiv_rn(Q[c * ld + i], nf));
+    mean[i] = acc;
+}
+
+// ------------------------------------------------------------------ host side
+// Optional per-kernel timing (bench.py's roofline leg): CUDA events recorded on the caller's stream around each
+// kernel of the type-quantizer path.  Off by default; never enabled inside a timed region.
+struct Profile { bool on = false; cudaEvent_t ev[8]; bool have = false; int marks = 0; };
+static Profile g_prof;
+static void prof_mark(cudaStream_t st) {
+    if (!g_prof.on) return;
+    if (!g_prof.have) { for (auto &e : g_prof.ev) cudaEventCreate(&e); g_prof.have = true; }
+    if (g_prof.marks < 8) cudaEventRecord(g_prof.ev[g_prof.marks++], st);
+}
+static void prof_reset() { g_prof.marks = 0; }
+
+static int check_rows(const void *X, int64_t n, int64_t d, int64_t ld) {
+    DME_REQUIRE(X != nullptr, "X is null");
+    DME_REQUIRE(n >= 1 && n <= 65535, "n=%lld out of range [1, 65535]", (long long)n);
+    DME_REQUIRE(d >= 1 && d <= ((int64_t)1 << 31), "d=%lld out of range [1, 2^31]", (long long)d);
+    DME_REQUIRE(ld >= d && ld % 4 == 0, "ld=%lld must be >= d and a multiple of 4", (long long)ld);
+    DME_REQUIRE(((uintptr_t)X & 15u) == 0, "X must be 16-byte aligned");
+    return DME_OK;
+}
+
+int ws_prepare(void *ws, int64_t ws_bytes, int64_t n, int64_t d, cudaStream_t st, WsLayout *out, bool need_desc, bool need_sel) {
+    const WsLayout L = ws_layout(n, d);
+    DME_REQUIRE(ws != nullptr && ((uintptr_t)ws & 255u) == 0, "workspace must be non-null and 256-byte aligned");
+    if (ws_bytes < L.total) {
+        set_error("workspace too small: %lld < %lld bytes", (long long)ws_bytes, (long long)L.total);
+        return DME_EWORKSPACE;
+    }
+    char *base = (char *)ws;
+    DME_CUDA(cudaMemsetAsync(base, 0, (size_t)L.zero_bytes, st));
+    if (need_desc) DME_CUDA(cudaMemsetAsync(base + L.off_desc, 0, sizeof(TileDesc) * (size_t)(n * L.T), st));
+    if (need_sel) DME_CUDA(cudaMemsetAsync(base + L.off_sel, 0, sizeof(RowSelect) * (size_t)n, st));
+    *out = L;
+    return DME_OK;
+}
+
+int launch_l1(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
+              const float *x_inject, const float *l1_inject, uint64_t seed, uint64_t client0, float *l1_out, cudaStream_t st) {
+    char *base = (char *)ws;
+    dim3 grid((unsigned)L.T, (unsigned)n);
+    l1_kernel<<<grid, kThreads, 0, st>>>(X, d, ld, m, L.T, (double *)(base + L.off_partial), (uint32_t *)(base + L.off_done),
+                                         (RowConst *)(base + L.off_consts), x_inject, l1_inject, seed, client0, l1_out);
+    DME_LAUNCH_CHECK("l1_kernel");
+    return DME_OK;
+}
+
+int biased_quantize(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
+                    int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
+                    uint32_t *codes, int64_t codes_bytes, uint64_t *dir, cudaStream_t st);   // reznik.cu
+
+}  // namespace dme
+
+using namespace dme;
+
+extern "C" int dme_l1_norms(const float *X, int64_t n, int64_t d, int64_t ld, float *l1_out, void *ws, int64_t ws_bytes,
+                            dme_stream_t stream) {
+    int rc = check_rows(X, n, d, ld);
+    if (rc) return rc;
+    DME_REQUIRE(l1_out != nullptr, "l1_out is null");
+    cudaStream_t st = (cudaStream_t)stream;
+    WsLayout L;
+    rc = ws_prepare(ws, ws_bytes, n, d, st, &L, false, false);
+    if (rc) return rc;
+    return launch_l1(X, n, d, ld, 1, L, ws, nullptr, nullptr, 0, 0, l1_out, st);
+}
+
+static int quantize_common(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, int mode, const float *x_inject,
+                           const float *l1_inject, uint64_t seed, uint64_t client0, int32_t *k_out, uint8_t *sgn_out,
+                           float *deq_out, int64_t ld_out, uint32_t *codes, int64_t codes_bytes, uint64_t *dir,
+                           float *l1_out, void *ws, int64_t ws_bytes, cudaStream_t st, bool packed) {
+    int rc = check_rows(X, n, d, ld);
+    if (rc) return rc;
+    DME_REQUIRE(m >= 1 && m < ((int64_t)1 << 40), "m=%lld out of range [1, 2^40)", (long long)m);
+    DME_REQUIRE(mode == DME_MODE_UNBIASED || mode == DME_MODE_BIASED, "mode=%d unknown", mode);
+    DME_REQUIRE(n * ((d + kTile - 1) / kTile) < ((int64_t)1 << 31), "n * tiles must be < 2^31");
+    if (packed) {
+        DME_REQUIRE(codes != nullptr && dir != nullptr && ((uintptr_t)codes & 15u) == 0, "codes/dir null or codes not 16-byte aligned");
+        DME_REQUIRE(codes_bytes >= 1024, "codes_bytes too small");
+    } else {
+        DME_REQUIRE(k_out || sgn_out || deq_out, "no output requested");
+        DME_REQUIRE(ld_out >= d, "ld_out=%lld < d", (long long)ld_out);
+    }
+    WsLayout L;
+    rc = ws_prepare(ws, ws_bytes, n, d, st, &L, true, mode == DME_MODE_BIASED);
+    if (rc) return rc;
+    prof_reset();
+    prof_mark(st);
+    rc = launch_l1(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, l1_out, st);
+    if (rc) return rc;
+    prof_mark(st);
+    char *base = (char *)ws;
+    if (mode == DME_MODE_BIASED)
+        return biased_quantize(X, n, d, ld, m, L, ws, k_out, sgn_out, deq_out, ld_out, codes, codes_bytes, dir, st);
+    ScanArgs a;
+    a.X = X; a.d = d; a.ld = ld; a.T = L.T; a.n = n;
+    a.consts = (const RowConst *)(base + L.off_consts);
+    a.desc = (TileDesc *)(base + L.off_desc);
+    a.hdr = (WsHeader *)base;
+    a.k_out = k_out; a.sgn_out = sgn_out; a.deq_out = deq_out; a.ld_out = ld_out;
+    a.codes = codes; a.codes_bytes = codes_bytes; a.dir = dir;
+    const unsigned grid = (unsigned)(n * L.T);
+    if (packed) scan_kernel<kEmitPacked><<<grid, kThreads, 0, st>>>(a);
+    else scan_kernel<kEmitArrays><<<grid, kThreads, 0, st>>>(a);
+    DME_LAUNCH_CHECK("scan_kernel");
+    prof_mark(st);
+    return DME_OK;
+}
+
+extern "C" int dme_type_quantize(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, int mode, const float *x_inject,
+                                 const float *l1_inject, uint64_t seed, uint64_t client0, int32_t *k_out, uint8_t *sgn_out,
+                                 float *deq_out, int64_t ld_out, float *l1_out, void *ws, int64_t ws_bytes, dme_stream_t stream) {
+    return quantize_common(X, n, d, ld, m, mode, x_inject, l1_inject, seed, client0, k_out, sgn_out, deq_out, ld_out, nullptr, 0,
+                           nullptr, l1_out, ws, ws_bytes, (cudaStream_t)stream, false);
+}
+
+extern "C" int dme_type_encode(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, int mode, const float *x_inject,
+                               const float *l1_inject, uint64_t seed, uint64_t client0, void *codes, int64_t codes_bytes,
+                               uint64_t *dir, float *l1_out, void *ws, int64_t ws_bytes, dme_stream_t stream) {
+    DME_REQUIRE(l1_out != nullptr, "l1_out is required by dme_type_encode (the decoder needs the norms)");
+    return quantize_common(X, n, d, ld, m, mode, x_inject, l1_inject, seed, client0, nullptr, nullptr, nullptr, 0,
+                           (uint32_t *)codes, codes_bytes, dir, l1_out, ws, ws_bytes, (cudaStream_t)stream, true);
+}
+
+extern "C" int dme_decode_mean(const void *codes, const uint64_t *dir, const float *l1, int64_t n, int64_t d, int64_t m, int mode,
+                               int64_t n_total, float *mean, int accumulate, dme_stream_t stream) {
+    DME_REQUIRE(codes && dir && l1 && mean, "null pointer argument");
+    DME_REQUIRE(n >= 1 && d >= 1 && m >= 1 && n_total >= 1, "n, d, m, n_total must be >= 1");
+    DME_REQUIRE(((uintptr_t)mean & 15u) == 0 && ((uintptr_t)codes & 15u) == 0, "mean and codes must be 16-byte aligned");
+    const int64_t T = (d + kTile - 1) / kTile;
+    decode_mean_kernel<<<(unsigned)T, kThreads, 0, (cudaStream_t)stream>>>((const uint32_t *)codes, dir, l1, n, d, T, (float)m,
+                                                                           (float)n_total, mode == DME_MODE_BIASED, mean, accumulate);
+    DME_LAUNCH_CHECK("decode_mean_kernel");
+    prof_mark((cudaStream_t)stream);
+    return DME_OK;
+}
+
+extern "C" int dme_profile_enable(int on) { g_prof.on = on != 0; prof_reset(); return DME_OK; }
+// ms[i] = time between mark i and mark i+1 of the last profiled call (l1, scan, decode for dme_quantize_mean).
+extern "C" int dme_profile_read(float *ms, int cap) {
+    DME_REQUIRE(ms != nullptr && cap >= 1, "bad argument");
+    int k = 0;
+    for (; k + 1 < g_prof.marks && k < cap; ++k) {
+        DME_CUDA(cudaEventSynchronize(g_prof.ev[k + 1]));
+        DME_CUDA(cudaEventElapsedTime(&ms[k], g_prof.ev[k], g_prof.ev[k + 1]));
+    }
+    return k;
+}
+
+extern "C" int dme_quantize_mean(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, int mode, const float *x_inject,
+                                 uint64_t seed, uint64_t client0, int64_t n_total, float *mean, int accumulate, void *codes,
+                                 int64_t codes_bytes, uint64_t *dir, float *l1_out, void *ws, int64_t ws_bytes, dme_stream_t stream) {
+    int rc = dme_type_encode(X, n, d, ld, m, mode, x_inject, nullptr, seed, client0, codes, codes_bytes, dir, l1_out, ws, ws_bytes, stream);
+    if (rc) return rc;
+    return dme_decode_mean(codes, dir, l1_out, n, d, m, mode, n_total, mean, accumulate, stream);
+}
+
+extern "C" int dme_mean_accumulate(const float *Q, int64_t n, int64_t d, int64_t ld, int64_t n_total, float *mean, int accumulate,
+                                   dme_stream_t stream) {
+    DME_REQUIRE(Q && mean && n >= 1 && d >= 1 && ld >= d && n_total >= 1, "bad argument");
+    const int64_t blocks = (d + 255) / 256;
+    mean_accumulate_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(Q, n, d, ld, (float)n_total, mean, accumulate);
+    DME_LAUNCH_CHECK("mean_accumulate_kernel");
+    return DME_OK;
+}
+
+extern "C" int dme_status(const void *ws, dme_stream_t stream) {
+    DME_REQUIRE(ws != nullptr, "ws is null");
+    uint32_t st = 0;
+    DME_CUDA(cudaMemcpyAsync(&st, &((const WsHeader *)ws)->status, sizeof(st), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    DME_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (st & 2u) { set_error("code arena exhausted: enlarge codes_bytes (dme_codes_bytes(..., expect=0) is always enough)"); return DME_EWORKSPACE; }
+    if (st & 1u) { set_error("a magnitude does not fit the requested integer output"); return DME_EOVERFLOW; }
+    return DME_OK;
+}

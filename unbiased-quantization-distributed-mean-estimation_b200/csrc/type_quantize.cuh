@@ -1,0 +1,77 @@
+// type_quantize.cuh -- data structures shared by the type-quantizer kernels (unbiased scan, Reznik select,
+// packed-code emit, decode-mean).
+#pragma once
+#include "common.cuh"
+
+namespace dme {
+
+// Per-client constants, written by the kernel that finishes the client's L1 reduction.
+struct __align__(32) RowConst {
+    float L1f;   // fp32(sum |x|)  (AS:624) or injected
+    float D;     // L1f + 1e-12f   (AS:625)
+    float mf;    // float(m)
+    float X;     // the client's uniform (AS:634)
+    float rcpD;  // RN(1 / D) for the Markstein fast division
+    float pad[3];
+};
+
+// Decoupled look-back record of one (client, tile).  state: 0 = nothing, 1 = aggregate valid,
+// 2 = aggregate + inclusive valid.  a_state: 1 = a_last valid.
+struct __align__(32) TileDesc {
+    double aggregate;   // sum of fractional parts inside the tile
+    double inclusive;   // canonical (left-to-right) sum of aggregates 0..t
+    int a_last;         // floor(c - X) of the tile's last coordinate
+    uint32_t state;
+    uint32_t a_state;
+    uint32_t pad;
+};
+
+struct __align__(256) WsHeader {
+    uint32_t ticket;          // scan-order ticket dispenser
+    uint32_t status;          // sticky error bits: 1 = magnitude overflow, 2 = arena exhausted
+    unsigned long long arena_top;   // bump pointer of the code arena, in 16-byte units
+    uint32_t ticket2;         // second dispenser (Reznik passes)
+    uint32_t pad[59];
+};
+
+struct WsLayout {
+    int64_t T;            // tiles per row
+    int64_t off_done;     // uint32 a_done[n]
+    int64_t off_consts;   // RowConst consts[n]
+    int64_t off_partial;  // double partial[n*T]
+    int64_t off_desc;     // TileDesc desc[n*T]
+    int64_t off_sel;      // RowSelect sel[n] (biased mode)
+    int64_t zero_bytes;   // prefix that must be zeroed before each call (header + a_done)
+    int64_t total;
+};
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// Radix-select state of one client row (biased / Reznik mode).
+struct __align__(16) RowSelect {
+    unsigned long long mprime;   // sum of round-to-nearest k'
+    long long Delta;             // m' - m
+    uint32_t prefix;             // selected key prefix so far
+    uint32_t remaining;          // how many still to pick among keys matching the prefix
+    uint32_t tie_key;            // final threshold key
+    uint32_t tie_take;           // how many threshold-equal elements (lowest index first) are adjusted
+    uint32_t hist[4][256];       // per-pass histograms
+    uint32_t done[4];            // tiles finished per pass
+    uint32_t tie_seen;           // running count for the ordered tie scan
+    uint32_t pad[3];
+};
+
+inline WsLayout ws_layout(int64_t n, int64_t d) {
+    WsLayout L;
+    L.T = (d + kTile - 1) / kTile;
+    int64_t o = (int64_t)sizeof(WsHeader);
+    L.off_done = o; o = align_up(o + 4 * n, 256);
+    L.zero_bytes = o;
+    L.off_consts = o; o = align_up(o + (int64_t)sizeof(RowConst) * n, 256);
+    L.off_partial = o; o = align_up(o + 8 * n * L.T, 256);
+    L.off_desc = o; o = align_up(o + (int64_t)sizeof(TileDesc) * n * L.T, 256);
+    L.off_sel = o; o = align_up(o + (int64_t)sizeof(RowSelect) * n, 256);
+    L.total = o;
+    return L;
+}
+
+}  // namespace dme

@@ -1,0 +1,244 @@
+// hadamard.cu -- normalised natural-order Walsh-Hadamard transform (AS:100-115), the randomized transform and its
+// inverse (AS:127-156), the Rademacher diagonal (AS:117-120, Philox instead of torch.Generator), and the
+// reference's pair transform (AS:37-59 as it executes).
+//
+// Bit-exactness: the reference runs stages h = 2, 4, .., d; each butterfly is a' = a + b, b' = a' - 2b (one
+// rounding), then divides by float(sqrt(d)).  Butterflies of one stage are independent, so any schedule that
+// keeps the stage ORDER and these two operations reproduces the reference bit for bit:
+//   fwht_contig_kernel : stages with distance 1 .. 2048 on contiguous 4096-blocks, radix-16 in registers, two
+//                        shared-memory transposes (padded, conflict-free)
+//   fwht_strided_kernel: 4 further stages per pass (distance 2^s .. 2^(s+3)), 16 strided elements per thread,
+//                        warp-coalesced columns
+// The +-1 diagonal, the zero padding and the final 1/sqrt(d) are fused into the first load / last store.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace dme {
+
+__device__ __forceinline__ void bfly(float &a, float &b) {
+    const float s = __fadd_rn(a, b);          // AS:110
+    b = __fmaf_rn(-2.0f, b, s);               // AS:111: (a + b) - 2b, 2b exact -> one rounding
+    a = s;
+}
+template <int NB>   // NB butterfly stages over the 2^NB-point register array, distance 1 first
+__device__ __forceinline__ void reg_stages(float (&v)[16], int nb) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        if (b < nb) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (!(i & (1 << b))) bfly(v[i], v[i | (1 << b)]);
+        }
+    }
+}
+
+struct FwhtIo {
+    const float *src; int64_t src_d, src_ld;   // source rows (length src_d <= d, zero padded)
+    float *dst; int64_t d, dst_ld;             // destination rows (length d = power of two)
+    const float *diag;                         // injected +-1 diagonal (d entries) or null
+    uint64_t seed; int use_philox;             // Philox diagonal when diag == null and use_philox
+    int pre_diag, post_diag;                   // multiply by the diagonal before the first stage / after the scaling
+    int finalize; float sq;                    // divide by sq = float(sqrt(d)) after the last stage
+};
+
+__device__ __forceinline__ float diag_at(const FwhtIo &io, int64_t col) {
+    if (io.diag) return io.diag[col];
+    return philox_sign(io.seed, (uint64_t)col, kStreamDiag);
+}
+
+constexpr int kPad = 4096 + 4096 / 32;   // +1 float every 32: transposes are conflict-free
+__device__ __forceinline__ int padded(int e) { return e + (e >> 5); }
+
+// One CTA = one 4096-element block of the flattened (row-major, dense) index space of n rows x d.
+// logL = min(log2 d, 12) stages are done here.
+__global__ void __launch_bounds__(256) fwht_contig_kernel(FwhtIo io, int64_t n, int logL) {
+    __shared__ float sm[kPad];
+    const int t = threadIdx.x;
+    const int64_t g0 = (int64_t)blockIdx.x * 4096 + 16 * t;      // first flattened element of this thread
+    const int64_t total = n * io.d;
+    float v[16];
+    // ---- load (+ zero padding, + diagonal)
+    if (io.d >= 16) {
+        const int64_t row = g0 / io.d, col = g0 - row * io.d;
+        const bool live = g0 < total;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t c0 = col + 4 * q;
+            if (live && c0 + 4 <= io.src_d && ((io.src_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(io.src) & 15) == 0)) {
+                const float4 x = *reinterpret_cast<const float4 *>(io.src + row * io.src_ld + c0);
+                v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[4 * q + j] = (live && c0 + j < io.src_d) ? io.src[row * io.src_ld + c0 + j] : 0.0f;
+            }
+        }
+        if (io.pre_diag && live) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], diag_at(io, col + j));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int64_t g = g0 + j;
+            const int64_t row = g / io.d, col = g - row * io.d;
+            float x = (g < total && col < io.src_d) ? io.src[row * io.src_ld + col] : 0.0f;
+            if (io.pre_diag && g < total) x = __fmul_rn(x, diag_at(io, col));
+            v[j] = x;
+        }
+    }
+    // ---- phase A: element bits 0..3 (thread-local)
+    reg_stages<4>(v, logL);
+    if (logL > 4) {
+        // ---- phase B: bits 4..7.  thread (lo = t & 15, hi = t >> 4) takes e = hi*256 + j*16 + lo
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sm[padded(16 * t + j)] = v[j];
+        __syncthreads();
+        const int lo = t & 15, hi = t >> 4;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = sm[padded(hi * 256 + j * 16 + lo)];
+        reg_stages<4>(v, logL - 4);
+        if (logL > 8) {
+            // ---- phase C: bits 8..11.  thread t takes e = j*256 + t
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sm[padded(hi * 256 + j * 16 + lo)] = v[j];
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = sm[padded(j * 256 + t)];
+            reg_stages<4>(v, logL - 8);
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sm[padded(j * 256 + t)] = v[j];
+        } else {
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sm[padded(hi * 256 + j * 16 + lo)] = v[j];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = sm[padded(16 * t + j)];
+    }
+    // ---- store (+ scaling, + diagonal)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int64_t g = g0 + j;
+        if (g >= total) break;
+        const int64_t row = g / io.d, col = g - row * io.d;
+        float y = v[j];
+        if (io.finalize) {
+            y = __fdiv_rn(y, io.sq);                                        // AS:113
+            if (io.post_diag) y = __fmul_rn(y, diag_at(io, col));           // AS:154
+        }
+        io.dst[row * io.dst_ld + col] = y;
+    }
+}
+
+// Stages with distance 2^s .. 2^(s+p-1), p <= 4, s >= 12, in place on dst.  One thread = one column, 2^p rows.
+__global__ void __launch_bounds__(256) fwht_strided_kernel(FwhtIo io, int64_t n, int s, int p) {
+    const int64_t cols_per_row = io.d >> p;                     // independent (hi, col) groups per row
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n * cols_per_row) return;
+    const int64_t row = gid / cols_per_row, w = gid - row * cols_per_row;
+    const int64_t col = w & (((int64_t)1 << s) - 1), hi = w >> s;
+    float *base = io.dst + row * io.dst_ld + (hi << (s + p)) + col;
+    const int R = 1 << p;
+    float v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = (r < R) ? base[(int64_t)r << s] : 0.0f;
+    reg_stages<4>(v, p);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        if (r < R) {
+            float y = v[r];
+            if (io.finalize) {
+                y = __fdiv_rn(y, io.sq);
+                if (io.post_diag) y = __fmul_rn(y, diag_at(io, (hi << (s + p)) + ((int64_t)r << s) + col));
+            }
+            base[(int64_t)r << s] = y;
+        }
+    }
+}
+
+__global__ void rademacher_kernel(float *out, int64_t d, uint64_t seed) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < d) out[i] = philox_sign(seed, (uint64_t)i, kStreamDiag);
+}
+
+// AS:37-59 as executed: log2(len) times (a, b) -> (a + b, (a + b) - b) on every adjacent pair.
+__global__ void pair_transform_kernel(float *V, int64_t n, int64_t len, int64_t ld, int stages) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t pairs = len >> 1;
+    if (gid >= n * pairs) return;
+    const int64_t row = gid / pairs, j = gid - row * pairs;
+    float *p = V + row * ld + 2 * j;
+    float a = p[0], b = p[1];
+    for (int s = 0; s < stages; ++s) {
+        const float t = __fadd_rn(a, b);     // AS:51
+        b = __fsub_rn(t, b);                 // AS:52 (reads the already-updated a)
+        a = t;
+    }
+    p[0] = a; p[1] = b;
+}
+
+static int ilog2(int64_t v) { int l = 0; while (((int64_t)1 << l) < v) ++l; return l; }
+
+// Full transform of n rows: src (length src_d, stride src_ld) -> dst (length d = 2^k, stride dst_ld).
+int fwht_rows(const float *src, int64_t src_d, int64_t src_ld, float *dst, int64_t d, int64_t dst_ld, int64_t n,
+              const float *diag, uint64_t seed, int pre_diag, int post_diag, cudaStream_t st) {
+    DME_REQUIRE(d >= 1 && (d & (d - 1)) == 0, "input numel must be a power of 2");
+    DME_REQUIRE(src && dst && n >= 1 && src_d >= 1 && src_d <= d && src_ld >= src_d && dst_ld >= d, "bad row geometry");
+    DME_REQUIRE(n * d < ((int64_t)1 << 40), "problem too large");
+    const int logd = ilog2(d);
+    FwhtIo io;
+    io.src = src; io.src_d = src_d; io.src_ld = src_ld; io.dst = dst; io.d = d; io.dst_ld = dst_ld;
+    io.diag = diag; io.seed = seed; io.use_philox = diag == nullptr; io.pre_diag = pre_diag; io.post_diag = post_diag;
+    io.sq = (float)std::sqrt((double)d);
+    const int logL = logd < 12 ? logd : 12;
+    io.finalize = (logd <= 12);
+    const int64_t blocks = (n * d + 4095) / 4096;
+    fwht_contig_kernel<<<(unsigned)blocks, 256, 0, st>>>(io, n, logL);
+    DME_LAUNCH_CHECK("fwht_contig_kernel");
+    io.src = dst; io.src_d = d; io.src_ld = dst_ld; io.pre_diag = 0;
+    for (int s = 12; s < logd; s += 4) {
+        const int p = (logd - s) < 4 ? (logd - s) : 4;
+        io.finalize = (s + p >= logd);
+        const int64_t threads = n * (d >> p);
+        fwht_strided_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(io, n, s, p);
+        DME_LAUNCH_CHECK("fwht_strided_kernel");
+    }
+    return DME_OK;
+}
+
+}  // namespace dme
+
+using namespace dme;
+
+extern "C" int dme_hadamard(float *V, int64_t n, int64_t dpad, int64_t ld, dme_stream_t stream) {
+    DME_REQUIRE(V != nullptr, "V is null");
+    return fwht_rows(V, dpad, ld, V, dpad, ld, n, nullptr, 0, 0, 0, (cudaStream_t)stream);
+}
+extern "C" int dme_rht(const float *X, int64_t n, int64_t d, int64_t ld, float *out, int64_t dpad, int64_t ld_out, uint64_t seed,
+                       const float *diag_inject, dme_stream_t stream) {
+    DME_REQUIRE(X && out, "null pointer argument");
+    DME_REQUIRE(dpad >= d, "dpad < d");
+    return fwht_rows(X, d, ld, out, dpad, ld_out, n, diag_inject, seed, 1, 0, (cudaStream_t)stream);
+}
+extern "C" int dme_irht(float *V, int64_t n, int64_t dpad, int64_t ld, uint64_t seed, const float *diag_inject, dme_stream_t stream) {
+    DME_REQUIRE(V != nullptr, "V is null");
+    return fwht_rows(V, dpad, ld, V, dpad, ld, n, diag_inject, seed, 0, 1, (cudaStream_t)stream);
+}
+extern "C" int dme_rademacher(float *diag, int64_t dpad, uint64_t seed, dme_stream_t stream) {
+    DME_REQUIRE(diag && dpad >= 1, "bad argument");
+    rademacher_kernel<<<(unsigned)((dpad + 255) / 256), 256, 0, (cudaStream_t)stream>>>(diag, dpad, seed);
+    DME_LAUNCH_CHECK("rademacher_kernel");
+    return DME_OK;
+}
+extern "C" int dme_pair_transform(float *V, int64_t n, int64_t len, int64_t ld, dme_stream_t stream) {
+    DME_REQUIRE(V && n >= 1 && len >= 1 && (len & (len - 1)) == 0 && ld >= len, "len must be a power of two, ld >= len");
+    if (len < 2) return DME_OK;
+    const int64_t work = n * (len >> 1);
+    pair_transform_kernel<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(V, n, len, ld, ilog2(len));
+    DME_LAUNCH_CHECK("pair_transform_kernel");
+    return DME_OK;
+}

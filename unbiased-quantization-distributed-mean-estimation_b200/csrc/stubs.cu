@@ -6,11 +6,6 @@ int biased_quantize(const float *, int64_t, int64_t, int64_t, int64_t, const WsL
 }
 #define NOTYET(name) { dme::set_error(name ": not built yet"); return DME_EINVAL; }
 extern "C" {
-int dme_hadamard(float *, int64_t, int64_t, int64_t, dme_stream_t) NOTYET("dme_hadamard")
-int dme_rht(const float *, int64_t, int64_t, int64_t, float *, int64_t, int64_t, uint64_t, const float *, dme_stream_t) NOTYET("dme_rht")
-int dme_irht(float *, int64_t, int64_t, int64_t, uint64_t, const float *, dme_stream_t) NOTYET("dme_irht")
-int dme_rademacher(float *, int64_t, uint64_t, dme_stream_t) NOTYET("dme_rademacher")
-int dme_pair_transform(float *, int64_t, int64_t, int64_t, dme_stream_t) NOTYET("dme_pair_transform")
 int dme_drive(const float *, int64_t, int64_t, int64_t, float *, int64_t, uint64_t, const float *, int, dme_stream_t) NOTYET("dme_drive")
 int dme_eden_encode(const float *, int64_t, int64_t, int64_t, int64_t, int, uint64_t, const float *, const float *, float *, uint8_t *, float *, dme_stream_t) NOTYET("dme_eden_encode")
 int dme_eden_decode(const uint8_t *, const float *, int64_t, int64_t, int64_t, int, uint64_t, const float *, float *, float *, int64_t, dme_stream_t) NOTYET("dme_eden_decode")

@@ -19,7 +19,8 @@
 
 namespace dme {
 
-// ------------------------------------------------------------------ tile load (blocked: 16 / thread)
+// ------------------------------------------------------------------ tile loads
+// blocked: thread t owns coordinates [16t, 16t+16) of the tile (the scan needs consecutive coordinates per thread)
 __device__ __forceinline__ void load_tile(const float *__restrict__ row, int64_t d, int64_t tile0, float (&x)[kEpt]) {
     const int64_t i0 = tile0 + (int64_t)threadIdx.x * kEpt;
     if (i0 + kEpt <= d) {
@@ -31,6 +32,24 @@ __device__ __forceinline__ void load_tile(const float *__restrict__ row, int64_t
     } else {
 #pragma unroll
         for (int j = 0; j < kEpt; ++j) x[j] = (i0 + j < d) ? row[i0 + j] : 0.0f;
+    }
+}
+// striped: fully coalesced 128-bit loads; used where the order inside the tile does not matter (L1 norm)
+__device__ __forceinline__ void load_tile_striped(const float *__restrict__ row, int64_t d, int64_t tile0, float (&x)[kEpt]) {
+    if (tile0 + kTile <= d) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 v = ldg_stream_f4(row + tile0 + q * 1024 + 4 * threadIdx.x);
+            x[4 * q + 0] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t i = tile0 + q * 1024 + 4 * threadIdx.x + e;
+                x[4 * q + e] = (i < d) ? row[i] : 0.0f;
+            }
     }
 }
 
@@ -46,7 +65,7 @@ l1_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t m, int64_t
     const int64_t c = blockIdx.y, t = blockIdx.x;
     const float *row = X + c * ld;
     float x[kEpt];
-    load_tile(row, d, t * kTile, x);
+    load_tile_striped(row, d, t * kTile, x);
     double s = 0.0;
 #pragma unroll
     for (int j = 0; j < kEpt; ++j) s += (double)fabsf(x[j]);
@@ -71,31 +90,56 @@ l1_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t m, int64_t
         rc.mf = (float)m;
         rc.X = x_inject ? x_inject[c] : philox_client_uniform(seed, client0 + (uint64_t)c);   // AS:634
         rc.rcpD = __frcp_rn(rc.D);
-        rc.pad[0] = rc.pad[1] = rc.pad[2] = 0.0f;
+        uint32_t fl = 0;
+        // The fast chain (Markstein division, magic-number floor) is proven for these operand ranges only;
+        // anything else takes the IEEE-div / floorf instantiation.  See DESIGN.md "Exactness of the fast chain".
+        if (!(rc.D >= 9.5367431640625e-07f && rc.D <= 1.2676506e30f)) fl |= kRowExact;            // 2^-20 .. 2^100
+        if ((__float_as_uint(rc.D) & 0x7fffffu) == 0x7fffffu) fl |= kRowExact;                      // 1/D rounding exception
+        if (!(rc.X == 0.0f || (rc.X >= 5.9604644775390625e-08f && rc.X < 1.0f))) fl |= kRowExact;  // X on torch.rand's grid
+        if (!(rc.mf <= 4194304.0f) || l1_inject) fl |= kRowGuardFloor;                              // m*p may reach 2^23
+        rc.flags = fl;
+        int lg = 0;
+        while (((int64_t)1 << lg) < d) ++lg;
+        rc.qshift = min(50, 62 - lg);
+        rc.pad0 = 0;
+        rc.q_up = scalbn(1.0, rc.qshift);
+        rc.q_dn = scalbn(1.0, -rc.qshift);
+        rc.pad1[0] = rc.pad1[1] = 0.0;
         consts[c] = rc;
         if (l1_out) l1_out[c] = rc.L1f;
     }
 }
 
 // ------------------------------------------------------------------ look-back (warp 0 of a tile CTA)
-// Returns the canonical exclusive prefix of tile t: ((incl_{t-f-1} + A_{t-f}) + ...) + A_{t-1}.
-__device__ __forceinline__ double lookback_exclusive(TileDesc *rowdesc, int64_t t, int lane) {
-    while (true) {
-        const int64_t idx = t - 1 - lane;
-        const uint32_t st = idx >= 0 ? ld_acquire_u32(&rowdesc[idx].state) : 2u;   // virtual tile -1: inclusive 0
-        const unsigned incl = __ballot_sync(0xffffffffu, st >= 2u);
-        const unsigned zero = __ballot_sync(0xffffffffu, st == 0u);
-        if (incl == 0u) { __nanosleep(40); continue; }
-        const int f = __ffs(incl) - 1;
-        const unsigned need = (f == 31) ? 0xffffffffu : ((1u << (f + 1)) - 1u);
-        if (zero & need) { __nanosleep(40); continue; }
-        double v = 0.0;
-        if (lane < f) v = ld_relaxed_f64(&rowdesc[idx].aggregate);
-        else if (lane == f && idx >= 0) v = ld_relaxed_f64(&rowdesc[idx].inclusive);
-        double P = __shfl_sync(0xffffffffu, v, f);
-        for (int l = f - 1; l >= 0; --l) P += __shfl_sync(0xffffffffu, v, l);
-        return P;
+// Standard decoupled look-back over int64 fixed-point aggregates: integer addition is associative, so the
+// exclusive prefix is the same whichever mixture of aggregates / inclusive prefixes happens to be visible.
+__device__ __forceinline__ long long lookback_exclusive(TileDesc *rowdesc, int64_t t, int lane) {
+    long long P = 0;
+    int64_t top = t - 1;                       // nearest predecessor not yet accounted for
+    while (top >= 0) {
+        const int64_t idx = top - lane;
+        uint32_t st;
+        while (true) {
+            st = idx >= 0 ? ld_acquire_u32(&rowdesc[idx].state) : 2u;          // virtual tiles < 0: inclusive 0
+            const unsigned incl = __ballot_sync(0xffffffffu, st >= 2u);
+            const unsigned zero = __ballot_sync(0xffffffffu, st == 0u);
+            const int f = incl ? (__ffs(incl) - 1) : 32;                       // nearest inclusive in the window
+            const unsigned need = (f >= 31) ? 0xffffffffu : ((1u << (f + 1)) - 1u);
+            if ((zero & need) == 0u) {
+                long long v = 0;
+                if (lane < f) v = *reinterpret_cast<volatile long long *>(&rowdesc[idx].aggregate);
+                else if (lane == f && idx >= 0) v = *reinterpret_cast<volatile long long *>(&rowdesc[idx].inclusive);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                P += v;
+                if (f < 32) return P;
+                break;
+            }
+            __nanosleep(20);
+        }
+        top -= 32;
     }
+    return P;
 }
 
 enum Emit { kEmitArrays = 0, kEmitPacked = 1 };
@@ -126,42 +170,68 @@ __device__ __forceinline__ void pack_store(const uint32_t (&k)[kEpt], const uint
     }
 }
 
+// AS:625-631 for one coordinate.  EXACT: IEEE division + floorf.  Fast: x/D by Markstein's correction of x*rcp
+// (correctly rounded for D in [2^-20, 2^100], 1/D correctly rounded, quotient normal) and floor by adding 2^23
+// toward zero (exact for 0 <= mp < 2^23).
+template <bool EXACT>
+__device__ __forceinline__ void chain(float x, const RowConst &rc, float &flf, float &fr) {
+    float mp;
+    if (EXACT) {
+        const float v = __fdiv_rn(x, rc.D);
+        mp = __fmul_rn(rc.mf, fabsf(v));
+        flf = floorf(mp);
+    } else {
+        const float ax = fabsf(x);
+        const float q0 = __fmul_rn(ax, rc.rcpD);
+        const float rem = __fmaf_rn(-q0, rc.D, ax);
+        const float p = __fmaf_rn(rem, rc.rcpD, q0);
+        mp = __fmul_rn(rc.mf, p);
+        flf = __fsub_rn(__fadd_rz(mp, 8388608.0f), 8388608.0f);
+    }
+    fr = __fsub_rn(mp, flf);
+}
+
 // ------------------------------------------------------------------ K2+K3+K5(+K6): scan / quantize / emit
-template <int EMIT>
-__global__ void __launch_bounds__(kThreads)
-scan_kernel(ScanArgs a) {
+template <int EMIT, bool EXACT>
+__device__ __forceinline__ void scan_tile(const ScanArgs &a, const RowConst &rc, int64_t c, int64_t t) {
     __shared__ double s_wtot[kWarps];
     __shared__ double s_P;
     __shared__ int s_alast[kWarps];
     __shared__ uint32_t s_u32[kWarps];
-    __shared__ uint32_t s_ticket;
     __shared__ unsigned long long s_off16;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    if (threadIdx.x == 0) s_ticket = atomicAdd(&a.hdr->ticket, 1u);
-    __syncthreads();
-    const int64_t ticket = s_ticket;
-    const int64_t c = ticket / a.T, t = ticket - c * a.T;
-    const RowConst rc = a.consts[c];
     TileDesc *rowdesc = a.desc + c * a.T;
     const float *row = a.X + c * a.ld;
 
     float x[kEpt];
     load_tile(row, a.d, t * kTile, x);
 
-    // AS:625-631, fp32, one rounding per operation
-    float fl[kEpt], fr[kEpt];
+    float fl[kEpt];
+    double frd[kEpt];
     double S = 0.0;
+    if (!EXACT && (rc.flags & kRowGuardFloor)) {
+        // m*p can reach 2^23 in this row: fall back to floorf for threads that actually see such a value
+        float mx = 0.0f;
 #pragma unroll
-    for (int j = 0; j < kEpt; ++j) {
-        const float v = __fdiv_rn(x[j], rc.D);
-        const float p = fabsf(v);
-        const float mp = __fmul_rn(rc.mf, p);
-        fl[j] = floorf(mp);
-        fr[j] = __fsub_rn(mp, fl[j]);
-        S += (double)fr[j];
+        for (int j = 0; j < kEpt; ++j) mx = fmaxf(mx, fabsf(x[j]));
+        const bool big = !(__fmul_rn(rc.mf, __fmul_rn(mx, rc.rcpD)) < 4194304.0f);
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) {
+            float fr;
+            if (big) chain<true>(x[j], rc, fl[j], fr); else chain<false>(x[j], rc, fl[j], fr);
+            frd[j] = (double)fr;
+            S += frd[j];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) {
+            float fr;
+            chain<EXACT>(x[j], rc, fl[j], fr);
+            frd[j] = (double)fr;
+            S += frd[j];
+        }
     }
-    // block scan of the thread sums (Kogge-Stone inside a warp, warps in order)
+    // block scan of the thread sums (Kogge-Stone inside a warp, warps in order): fixed association
     double incl = S;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -180,15 +250,16 @@ scan_kernel(ScanArgs a) {
     }
     if (warp == 0) {
         TileDesc *me = rowdesc + t;
-        double P = 0.0;
+        const long long Aq = __double2ll_rn(A * rc.q_up);            // fixed point, 2^-qshift resolution
+        long long P = 0;
         if (t == 0) {
-            if (lane == 0) { me->aggregate = A; me->inclusive = A; st_release_u32(&me->state, 2u); }
+            if (lane == 0) { me->aggregate = Aq; me->inclusive = Aq; st_release_u32(&me->state, 2u); }
         } else {
-            if (lane == 0) { me->aggregate = A; st_release_u32(&me->state, 1u); }
+            if (lane == 0) { me->aggregate = Aq; st_release_u32(&me->state, 1u); }
             P = lookback_exclusive(rowdesc, t, lane);
-            if (lane == 0) { me->inclusive = P + A; st_release_u32(&me->state, 2u); }
+            if (lane == 0) { me->inclusive = P + Aq; st_release_u32(&me->state, 2u); }
         }
-        if (lane == 0) s_P = P;
+        if (lane == 0) s_P = __ll2double_rn(P) * rc.q_dn;
     }
     __syncthreads();
     // prefix -> fp32 -> floor(c - X)   (AS:635-636)
@@ -196,8 +267,8 @@ scan_kernel(ScanArgs a) {
     int av[kEpt];
 #pragma unroll
     for (int j = 0; j < kEpt; ++j) {
-        C += (double)fr[j];
-        const float c32 = (float)C;
+        C += frd[j];
+        const float c32 = __double2float_rn(C);
         av[j] = __float2int_rd(__fsub_rn(c32, rc.X));
     }
     if (threadIdx.x == kThreads - 1) {
@@ -213,7 +284,7 @@ scan_kernel(ScanArgs a) {
         else if (t == 0) aprev = __float2int_rd(__fsub_rn(0.0f, rc.X));            // c_0 = 0 (AS:635)
         else {
             const TileDesc *pv = rowdesc + (t - 1);
-            while (ld_acquire_u32(&pv->a_state) == 0u) __nanosleep(40);
+            while (ld_acquire_u32(&pv->a_state) == 0u) __nanosleep(20);
             aprev = ld_relaxed_s32(&pv->a_last);
         }
     }
@@ -280,6 +351,19 @@ scan_kernel(ScanArgs a) {
             }
         }
     }
+}
+
+template <int EMIT>
+__global__ void __launch_bounds__(kThreads)
+scan_kernel(ScanArgs a) {
+    __shared__ uint32_t s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&a.hdr->ticket, 1u);
+    __syncthreads();
+    const int64_t ticket = s_ticket;
+    const int64_t c = ticket / a.T, t = ticket - c * a.T;
+    const RowConst rc = a.consts[c];
+    if (rc.flags & kRowExact) scan_tile<EMIT, true>(a, rc, c, t);
+    else scan_tile<EMIT, false>(a, rc, c, t);
 }
 
 // ------------------------------------------------------------------ K7: decode + mean (tile-major)
@@ -421,7 +505,7 @@ static int quantize_common(const float *X, int64_t n, int64_t d, int64_t ld, int
                            float *l1_out, void *ws, int64_t ws_bytes, cudaStream_t st, bool packed) {
     int rc = check_rows(X, n, d, ld);
     if (rc) return rc;
-    DME_REQUIRE(m >= 1 && m < ((int64_t)1 << 40), "m=%lld out of range [1, 2^40)", (long long)m);
+    DME_REQUIRE(m >= (packed ? 1 : 0) && m < ((int64_t)1 << 40), "m=%lld out of range [%d, 2^40)", (long long)m, packed ? 1 : 0);
     DME_REQUIRE(mode == DME_MODE_UNBIASED || mode == DME_MODE_BIASED, "mode=%d unknown", mode);
     DME_REQUIRE(n * ((d + kTile - 1) / kTile) < ((int64_t)1 << 31), "n * tiles must be < 2^31");
     if (packed) {

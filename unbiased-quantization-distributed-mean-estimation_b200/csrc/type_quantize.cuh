@@ -6,20 +6,26 @@
 namespace dme {
 
 // Per-client constants, written by the kernel that finishes the client's L1 reduction.
-struct __align__(32) RowConst {
+struct __align__(64) RowConst {
     float L1f;   // fp32(sum |x|)  (AS:624) or injected
     float D;     // L1f + 1e-12f   (AS:625)
     float mf;    // float(m)
     float X;     // the client's uniform (AS:634)
-    float rcpD;  // RN(1 / D) for the Markstein fast division
-    float pad[3];
+    float rcpD;  // RN(1 / D) for the Markstein division  x/D = fma(fma(-q0, D, x), rcp, q0), q0 = x*rcp
+    uint32_t flags;      // kRowExact: use IEEE div / floorf (operands outside the proven range of the fast chain)
+                         // kRowGuardFloor: mp may reach 2^23 -> per-thread check before the magic floor
+    int32_t qshift;      // tile aggregates are exchanged as int64 fixed point with 2^-qshift resolution
+    uint32_t pad0;
+    double q_up, q_dn;   // 2^qshift, 2^-qshift
+    double pad1[2];
 };
+constexpr uint32_t kRowExact = 1u, kRowGuardFloor = 2u;
 
 // Decoupled look-back record of one (client, tile).  state: 0 = nothing, 1 = aggregate valid,
 // 2 = aggregate + inclusive valid.  a_state: 1 = a_last valid.
 struct __align__(32) TileDesc {
-    double aggregate;   // sum of fractional parts inside the tile
-    double inclusive;   // canonical (left-to-right) sum of aggregates 0..t
+    long long aggregate;   // sum of fractional parts inside the tile, fixed point (exact associativity =>
+    long long inclusive;   // the look-back result does not depend on timing); inclusive = sum of aggregates 0..t
     int a_last;         // floor(c - X) of the tile's last coordinate
     uint32_t state;
     uint32_t a_state;

@@ -9,7 +9,7 @@ One "step" = one pass of the hot path over one batch of synthetic client vectors
 (N(0,1) i.i.d., torch.Generator seed 42 + rank).  Rank 0 prints ONE JSON line.
   value     : whole-job coords/s = N_gpus * n * d * K / (max-over-ranks device time), inputs in HBM
   e2e       : same metric through the public host-buffer call (pinned host rows -> H2D -> fused path -> D2H of the mean)
-  roofline  : dominant kernel (scan/quantize/pack), algorithmic bytes 4*n*d + 4*d per launch / its CUDA-event time,
+  roofline  : dominant kernel (persistent L1+scan+quantize+pack), algorithmic bytes 4*n*d + 4*d per launch / its CUDA-event time,
               against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline : oracle port (oracle/dme_oracle.c, pthreads over clients) on the box's host cores, bounded sample
 --impl reference times that CPU port alone (the reference is pure Python/torch and cannot travel to the GPU box).
@@ -225,7 +225,7 @@ def run_ours(a):
     L.dme_profile_enable(0)
     per = np.array(per[1:])
     kern_ms = per.mean(axis=0) if per.size else np.array([ms_step])
-    names = ["l1_kernel", "scan_kernel", "decode_mean_kernel"][: len(kern_ms)]
+    names = ["quantize_stream_kernel", "decode_mean_kernel"][: len(kern_ms)]
     dom = int(np.argmax(kern_ms))
     ach = B_alg / (kern_ms[dom] * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,

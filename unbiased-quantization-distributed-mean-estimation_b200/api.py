@@ -212,12 +212,11 @@ def type_encode(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, cli
         codes = torch.empty(cb, dtype=torch.uint8, device=dev)
         dr = torch.empty(int(L.dme_dir_entries(n, d)), dtype=torch.int64, device=dev)
         l1 = torch.empty(n, dtype=torch.float32, device=dev)
-        _check(L.dme_type_encode(_ptr(X), n, d, _ld(X), mm, MODE[mode], _ptr(xi), _ptr(li), seed, client0, _ptr(codes), cb,
-                                 _ptr(dr), _ptr(l1), ws, wsb, C.c_void_p(_stream())))
-        if not check:
-            break
         try:
-            Workspace.get(dev).status()
+            _check(L.dme_type_encode(_ptr(X), n, d, _ld(X), mm, MODE[mode], _ptr(xi), _ptr(li), seed, client0, _ptr(codes), cb,
+                                     _ptr(dr), _ptr(l1), ws, wsb, C.c_void_p(_stream())))
+            if check:
+                Workspace.get(dev).status()
             break
         except MemoryError:
             worst = int(L.dme_codes_bytes(n, d, mm, 0))
@@ -281,13 +280,12 @@ def quantize_mean(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, c
     xi = _opt_vec(x_inject, n, dev)
     nt = n if n_total is None else int(n_total)
     while True:
-        _check(L.dme_quantize_mean(_ptr(X), n, d, _ld(X), mm, MODE[mode], _ptr(xi), seed, client0, nt, _ptr(out),
-                                   int(bool(accumulate)), _ptr(plan.codes), plan.cb, _ptr(plan.dir), _ptr(plan.l1), ws, wsb,
-                                   C.c_void_p(_stream())))
-        if not check:
-            return out
         try:
-            Workspace.get(dev).status()
+            _check(L.dme_quantize_mean(_ptr(X), n, d, _ld(X), mm, MODE[mode], _ptr(xi), seed, client0, nt, _ptr(out),
+                                       int(bool(accumulate)), _ptr(plan.codes), plan.cb, _ptr(plan.dir), _ptr(plan.l1), ws, wsb,
+                                       C.c_void_p(_stream())))
+            if check:
+                Workspace.get(dev).status()
             return out
         except MemoryError:
             if accumulate or plan.cb >= int(L.dme_codes_bytes(n, d, mm, 0)):

@@ -42,14 +42,9 @@ extern "C" int64_t dme_dir_entries(int64_t n, int64_t d) {
 extern "C" int64_t dme_codes_bytes(int64_t n, int64_t d, int64_t m, int expect) {
     if (n < 1 || d < 1 || m < 1) return 0;
     const int64_t T = (d + kTile - 1) / kTile;
-    int w = 32;
-    if (expect) {
-        // expected largest magnitude in a 4096-tile ~ (m/d) * (max|x| / mean|x|); light tails: factor ~6
-        const double ell = (double)m / (double)d;
-        w = 2;
-        while (w < 32 && 6.0 * ell + 1.0 >= (double)(1u << (w - 1))) w <<= 1;
-    }
-    int64_t bytes = n * T * 512 * w;
-    if (expect && w < 32) bytes += bytes / 2;
-    return bytes + 4096;
+    // primary slots (expected width) + overflow space for wider tiles
+    const int w0 = expected_width(m, d);
+    const int64_t primary = n * T * 512 * w0;
+    const int64_t overflow = expect ? (n * T * 512 * (w0 < 32 ? 2 * w0 : 0)) / 4 + 65536 : n * T * 512 * 32;
+    return primary + overflow + 4096;
 }

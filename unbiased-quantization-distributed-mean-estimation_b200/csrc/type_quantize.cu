@@ -15,6 +15,8 @@
 //                    order), so the result does not depend on timing.  floor(c - X) of a tile's last
 //                    coordinate is handed to the next tile through the descriptor (each a_i is computed once).
 //   decode_mean_kernel : tile-major over d, clients in order in registers, one write of the mean.
+#include <cstdlib>
+
 #include "type_quantize.cuh"
 
 namespace dme {
@@ -144,14 +146,49 @@ __device__ __forceinline__ long long lookback_exclusive(TileDesc *rowdesc, int64
 
 enum Emit { kEmitArrays = 0, kEmitPacked = 1 };
 
-struct ScanArgs {
-    const float *X; int64_t d, ld, T, n;
-    const RowConst *consts; TileDesc *desc; WsHeader *hdr;
+// Arguments of the persistent quantize kernel.
+struct StreamArgs {
+    const float *X; int64_t d, ld, T, n, m;
+    RowConst *consts; TileDesc *desc; WsHeader *hdr; double *partial; uint32_t *a_done; uint32_t *row_ready;
+    const float *x_inject; const float *l1_inject; uint64_t seed, client0; float *l1_out;
+    int64_t lag, total_items;          // the B stream trails the A stream by `lag` tiles
     // arrays
     int32_t *k_out; uint8_t *sgn_out; float *deq_out; int64_t ld_out;
     // packed
-    uint32_t *codes; int64_t codes_bytes; uint64_t *dir;
+    uint32_t *codes; int64_t codes_bytes; uint64_t *dir; int W0;
+    unsigned long long arena_base16;   // first 16-byte unit behind the primary slots
+    int dbg;
 };
+
+// ---- async-copy / mbarrier primitives (TMA 1-D bulk copy, SASS UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
 
 // Pack 16 (magnitude, sign) pairs of one thread with field width W into W/2 words.
 template <int W>
@@ -191,20 +228,110 @@ __device__ __forceinline__ void chain(float x, const RowConst &rc, float &flf, f
     fr = __fsub_rn(mp, flf);
 }
 
-// ------------------------------------------------------------------ K2+K3+K5(+K6): scan / quantize / emit
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+struct TileScratch {
+    unsigned long long tacc[8];
+    double wtot[kWarps];
+    double red[kWarps];
+    double P;
+    long long Pq;
+    int alast[kWarps];
+    uint32_t u32[kWarps];
+    unsigned long long off16;
+    uint32_t flag;
+};
+
+// Row constants from the finished L1 reduction (run by thread 0 of the CTA that completed the row).
+__device__ __forceinline__ void make_row_const(const StreamArgs &a, int64_t c, double l1sum) {
+    RowConst rc;
+    rc.L1f = a.l1_inject ? a.l1_inject[c] : (float)l1sum;           // AS:624
+    rc.D = __fadd_rn(rc.L1f, 1e-12f);                               // AS:625
+    rc.mf = (float)a.m;
+    rc.X = a.x_inject ? a.x_inject[c] : philox_client_uniform(a.seed, a.client0 + (uint64_t)c);   // AS:634
+    rc.rcpD = __frcp_rn(rc.D);
+    uint32_t fl = 0;
+    // The fast chain (Markstein division, magic-number floor) is proven for these operand ranges only;
+    // anything else takes the IEEE-div / floorf instantiation.  See DESIGN.md "Exactness of the fast chain".
+    if (!(rc.D >= 9.5367431640625e-07f && rc.D <= 1.2676506e30f)) fl |= kRowExact;            // 2^-20 .. 2^100
+    if ((__float_as_uint(rc.D) & 0x7fffffu) == 0x7fffffu) fl |= kRowExact;                      // 1/D rounding exception
+    if (!(rc.X == 0.0f || (rc.X >= 5.9604644775390625e-08f && rc.X < 1.0f))) fl |= kRowExact;  // X on torch.rand's grid
+    if (!(rc.mf <= 4194304.0f) || a.l1_inject) fl |= kRowGuardFloor;                            // m*p may reach 2^23
+    rc.flags = fl;
+    int lg = 0;
+    while (((int64_t)1 << lg) < a.d) ++lg;
+    rc.qshift = min(50, 62 - lg);
+    rc.pad0 = 0;
+    rc.q_up = scalbn(1.0, rc.qshift);
+    rc.q_dn = scalbn(1.0, -rc.qshift);
+    rc.pad1[0] = rc.pad1[1] = 0.0;
+    a.consts[c] = rc;
+    if (a.l1_out) a.l1_out[c] = rc.L1f;
+}
+
+// value of tile-local coordinate e (0..4095) from the staged tile; beyond `copied` floats fall back to global / zero
+__device__ __forceinline__ float staged(const float *buf, int e, int copied, const float *row, int64_t tile0, int64_t d) {
+    if (e < copied) return buf[e];
+    const int64_t i = tile0 + e;
+    return i < d ? row[i] : 0.0f;
+}
+
+// ---- pass A of one tile: |x| partial sum; the tile that completes a row reduces the partials and publishes the row
+__device__ __forceinline__ void pass_a_tile(const StreamArgs &a, int64_t c, int64_t t, const float *buf, int copied, TileScratch &sc) {
+    const float *row = a.X + c * a.ld;
+    const int64_t tile0 = t * kTile;
+    double s = 0.0;
+    if (copied == kTile) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4 *>(buf + q * 1024 + 4 * threadIdx.x);
+            s += (double)fabsf(v.x); s += (double)fabsf(v.y); s += (double)fabsf(v.z); s += (double)fabsf(v.w);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s += (double)fabsf(staged(buf, q * 1024 + 4 * threadIdx.x + e, copied, row, tile0, a.d));
+    }
+    s = block_sum_f64(s, sc.red);
+    if (threadIdx.x == 0) {
+        a.partial[c * a.T + t] = s;
+        __threadfence();
+        sc.flag = (atomicAdd(&a.a_done[c], 1u) == (uint32_t)(a.T - 1)) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!sc.flag) return;
+    __threadfence();
+    const volatile double *pp = a.partial + c * a.T;
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < a.T; i += kThreads) acc += pp[i];
+    acc = block_sum_f64(acc, sc.red);
+    if (threadIdx.x == 0) {
+        make_row_const(a, c, acc);
+        __threadfence();
+        st_release_u32(&a.row_ready[c], 1u);
+    }
+}
+
+// ---- pass B of one tile: AS:625-637 + emit
 template <int EMIT, bool EXACT>
-__device__ __forceinline__ void scan_tile(const ScanArgs &a, const RowConst &rc, int64_t c, int64_t t) {
-    __shared__ double s_wtot[kWarps];
-    __shared__ double s_P;
-    __shared__ int s_alast[kWarps];
-    __shared__ uint32_t s_u32[kWarps];
-    __shared__ unsigned long long s_off16;
+__device__ __forceinline__ void pass_b_tile(const StreamArgs &a, const RowConst &rc, int64_t c, int64_t t, const float *buf,
+                                            int copied, TileScratch &sc) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     TileDesc *rowdesc = a.desc + c * a.T;
     const float *row = a.X + c * a.ld;
+    const int64_t tile0 = t * kTile;
 
     float x[kEpt];
-    load_tile(row, a.d, t * kTile, x);
+    if (copied == kTile) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4 *>(buf + kEpt * threadIdx.x + 4 * q);
+            x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) x[j] = staged(buf, kEpt * threadIdx.x + j, copied, row, tile0, a.d);
+    }
 
     float fl[kEpt];
     double frd[kEpt];
@@ -240,53 +367,51 @@ __device__ __forceinline__ void scan_tile(const ScanArgs &a, const RowConst &rc,
     }
     double excl = __shfl_up_sync(0xffffffffu, incl, 1);
     if (lane == 0) excl = 0.0;
-    if (lane == 31) s_wtot[warp] = incl;
+    if (lane == 31) sc.wtot[warp] = incl;
     __syncthreads();
     double wbase = 0.0, A = 0.0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
         if (w == warp) wbase = A;
-        A += s_wtot[w];
+        A += sc.wtot[w];
     }
+    const long long Aq = __double2ll_rn(A * rc.q_up);                // fixed point, 2^-qshift resolution
     if (warp == 0) {
         TileDesc *me = rowdesc + t;
-        const long long Aq = __double2ll_rn(A * rc.q_up);            // fixed point, 2^-qshift resolution
         long long P = 0;
+        unsigned long long t0 = 0, t1 = 0, t2 = 0;
+        if ((a.dbg & 32) && lane == 0) t0 = gtime();
         if (t == 0) {
             if (lane == 0) { me->aggregate = Aq; me->inclusive = Aq; st_release_u32(&me->state, 2u); }
         } else {
             if (lane == 0) { me->aggregate = Aq; st_release_u32(&me->state, 1u); }
-            P = lookback_exclusive(rowdesc, t, lane);
+            if ((a.dbg & 32) && lane == 0) t1 = gtime();
+            P = (a.dbg & 8) ? 0 : lookback_exclusive(rowdesc, t, lane);
+            if ((a.dbg & 32) && lane == 0) t2 = gtime();
             if (lane == 0) { me->inclusive = P + Aq; st_release_u32(&me->state, 2u); }
         }
-        if (lane == 0) s_P = __ll2double_rn(P) * rc.q_dn;
+        if ((a.dbg & 32) && lane == 0 && t > 0) { sc.tacc[2] += t1 - t0; sc.tacc[3] += t2 - t1; sc.tacc[4] += gtime() - t2; }
+        if (lane == 0) { sc.Pq = P; sc.P = __ll2double_rn(P) * rc.q_dn; }
     }
     __syncthreads();
     // prefix -> fp32 -> floor(c - X)   (AS:635-636)
-    double C = s_P + (wbase + excl);
+    double C = sc.P + (wbase + excl);
     int av[kEpt];
 #pragma unroll
     for (int j = 0; j < kEpt; ++j) {
         C += frd[j];
+        // The prefix at a tile's last coordinate is DEFINED as the fixed-point inclusive prefix, so that the next
+        // tile derives the same floor(c - X) from its own exclusive prefix (no hand-off between tiles).
+        if (j == kEpt - 1 && threadIdx.x == kThreads - 1) C = __ll2double_rn(sc.Pq + Aq) * rc.q_dn;
         const float c32 = __double2float_rn(C);
         av[j] = __float2int_rd(__fsub_rn(c32, rc.X));
     }
-    if (threadIdx.x == kThreads - 1) {
-        TileDesc *me = rowdesc + t;
-        me->a_last = av[kEpt - 1];
-        st_release_u32(&me->a_state, 1u);
-    }
     int aprev = __shfl_up_sync(0xffffffffu, av[kEpt - 1], 1);
-    if (lane == 31) s_alast[warp] = av[kEpt - 1];
+    if (lane == 31) sc.alast[warp] = av[kEpt - 1];
     __syncthreads();
     if (lane == 0) {
-        if (warp > 0) aprev = s_alast[warp - 1];
-        else if (t == 0) aprev = __float2int_rd(__fsub_rn(0.0f, rc.X));            // c_0 = 0 (AS:635)
-        else {
-            const TileDesc *pv = rowdesc + (t - 1);
-            while (ld_acquire_u32(&pv->a_state) == 0u) __nanosleep(20);
-            aprev = ld_relaxed_s32(&pv->a_last);
-        }
+        if (warp > 0) aprev = sc.alast[warp - 1];
+        else aprev = __float2int_rd(__fsub_rn(__double2float_rn(sc.P), rc.X));     // t == 0: c_0 = 0 (AS:635)
     }
     float kf[kEpt];
 #pragma unroll
@@ -296,7 +421,7 @@ __device__ __forceinline__ void scan_tile(const ScanArgs &a, const RowConst &rc,
         kf[j] = __fadd_rn(fl[j], (float)r);
     }
 
-    const int64_t i0 = t * kTile + (int64_t)threadIdx.x * kEpt;
+    const int64_t i0 = tile0 + (int64_t)threadIdx.x * kEpt;
     if (EMIT == kEmitArrays) {
         bool ovf = false;
 #pragma unroll
@@ -326,22 +451,30 @@ __device__ __forceinline__ void scan_tile(const ScanArgs &a, const RowConst &rc,
         }
         if (ovf) atomicOr(&a.hdr->status, 1u);
         kmax = __reduce_max_sync(0xffffffffu, kmax);
-        if (lane == 0) s_u32[warp] = kmax;
+        if (lane == 0) sc.u32[warp] = kmax;
         __syncthreads();
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) kmax = max(kmax, s_u32[w]);
+        for (int w = 0; w < kWarps; ++w) kmax = max(kmax, sc.u32[w]);
         int W = 2;
         while (W < 32 && kmax >= (1u << (W - 1))) W <<= 1;
-        if (threadIdx.x == 0) {
-            const unsigned long long units = 32ull * W;                      // 512*W bytes / 16
-            unsigned long long off = atomicAdd(&a.hdr->arena_top, units);
-            if ((long long)((off + units) * 16ull) > a.codes_bytes) { atomicOr(&a.hdr->status, 2u); off = ~0ull; }
-            s_off16 = off;
-            a.dir[c * a.T + t] = (off == ~0ull) ? 0ull : ((off << 8) | (unsigned long long)W);
+        // Tiles no wider than the expected width W0 live in their fixed primary slot; wider ones take overflow space.
+        unsigned long long off16;
+        if (W <= a.W0) {
+            off16 = (unsigned long long)(c * a.T + t) * (32ull * a.W0);
+            if (threadIdx.x == 0) a.dir[c * a.T + t] = (off16 << 8) | (unsigned long long)W;
+        } else {
+            if (threadIdx.x == 0) {
+                const unsigned long long units = 32ull * W;                  // 512*W bytes / 16
+                unsigned long long off = a.arena_base16 + atomicAdd(&a.hdr->arena_top, units);
+                if ((long long)((off + units) * 16ull) > a.codes_bytes) { atomicOr(&a.hdr->status, 2u); off = ~0ull; }
+                sc.off16 = off;
+                a.dir[c * a.T + t] = (off == ~0ull) ? 0ull : ((off << 8) | (unsigned long long)W);
+            }
+            __syncthreads();
+            off16 = sc.off16;
         }
-        __syncthreads();
-        if (s_off16 != ~0ull) {
-            uint32_t *tw = a.codes + s_off16 * 4ull;
+        if (off16 != ~0ull) {
+            uint32_t *tw = a.codes + off16 * 4ull;
             switch (W) {
                 case 2: pack_store<2>(k, sg, tw); break;
                 case 4: pack_store<4>(k, sg, tw); break;
@@ -353,17 +486,96 @@ __device__ __forceinline__ void scan_tile(const ScanArgs &a, const RowConst &rc,
     }
 }
 
+// ------------------------------------------------------------------ the persistent quantize kernel
+// Work items are handed out in ONE global order by an atomic ticket: even tickets are pass-A tiles (stream the row
+// from HBM, L2 evict_last, partial L1 norm), odd tickets are pass-B tiles of the row `lag` tiles behind (re-read
+// from L2, evict_first, scan + quantize + pack).  Every wait (row constants, look-back) is on a smaller ticket,
+// and a ticket is only taken by a running CTA, so the schedule cannot deadlock.  Each CTA prefetches the tile of
+// its NEXT ticket with a 1-D bulk async copy (TMA) while it works on the current one.
+struct Item { int valid; int is_b; int64_t c, t; int copied; const float *src; };
+__device__ __forceinline__ Item decode_item(const StreamArgs &a, int64_t i) {
+    Item it; it.valid = 0; it.is_b = (int)(i & 1); it.c = 0; it.t = 0; it.copied = 0; it.src = nullptr;
+    if (i >= a.total_items) return it;
+    const int64_t s = it.is_b ? ((i >> 1) - a.lag) : (i >> 1);
+    if (s < 0 || s >= a.n * a.T) return it;
+    it.valid = 1;
+    it.c = s / a.T; it.t = s - it.c * a.T;
+    const int64_t rem = a.d - it.t * kTile;
+    it.copied = rem >= kTile ? kTile : (int)(rem & ~(int64_t)3);
+    it.src = a.X + it.c * a.ld + it.t * kTile;
+    return it;
+}
+
 template <int EMIT>
-__global__ void __launch_bounds__(kThreads)
-scan_kernel(ScanArgs a) {
-    __shared__ uint32_t s_ticket;
-    if (threadIdx.x == 0) s_ticket = atomicAdd(&a.hdr->ticket, 1u);
+__global__ void __launch_bounds__(kThreads, 2)
+quantize_stream_kernel(StreamArgs a) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    float *buf0 = reinterpret_cast<float *>(dyn_smem);
+    float *buf1 = reinterpret_cast<float *>(dyn_smem + kTile * 4);
+    __shared__ uint64_t mbar[2];
+    __shared__ long long s_ticket[2];
+    __shared__ TileScratch sc;
+
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < 8; ++q) sc.tacc[q] = 0;
+        mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_ticket[0] = (long long)atomicAdd(&a.hdr->ticket, 1u);
+    }
     __syncthreads();
-    const int64_t ticket = s_ticket;
-    const int64_t c = ticket / a.T, t = ticket - c * a.T;
-    const RowConst rc = a.consts[c];
-    if (rc.flags & kRowExact) scan_tile<EMIT, true>(a, rc, c, t);
-    else scan_tile<EMIT, false>(a, rc, c, t);
+    uint64_t pol_a = policy_evict_last(), pol_b = policy_evict_first();
+    if (a.dbg & 1) { pol_b = pol_a; }                     // dbg: same policy for both passes
+    if (a.dbg & 2) { pol_a = pol_b; }
+    int64_t cur = s_ticket[0];
+    Item it = decode_item(a, cur);
+    if (threadIdx.x == 0 && it.valid && it.copied > 0) {
+        mbar_expect_tx(&mbar[0], (uint32_t)it.copied * 4u);
+        bulk_g2s(buf0, it.src, (uint32_t)it.copied * 4u, &mbar[0], it.is_b ? pol_b : pol_a);
+    }
+    uint32_t parity[2] = {0u, 0u};
+    int stage = 0;
+    while (cur < a.total_items) {
+        if (it.valid) {
+            const float *buf = stage ? buf1 : buf0;
+            unsigned long long tq0 = 0, tq1 = 0;
+            if ((a.dbg & 32) && threadIdx.x == 0) tq0 = gtime();
+            if (it.is_b) {
+                // row constants: published by the CTA that finished the row's pass A (a smaller ticket)
+                if (threadIdx.x == 0) while (ld_acquire_u32(&a.row_ready[it.c]) == 0u) __nanosleep(50);
+                __syncthreads();
+            }
+            if ((a.dbg & 32) && threadIdx.x == 0) tq1 = gtime();
+            if (it.copied > 0) { mbar_wait(&mbar[stage], parity[stage]); parity[stage] ^= 1u; }
+            if ((a.dbg & 32) && threadIdx.x == 0) { sc.tacc[0] += tq1 - tq0; sc.tacc[1] += gtime() - tq1; sc.tacc[it.is_b ? 6 : 5] -= gtime(); }
+            if (!it.is_b) pass_a_tile(a, it.c, it.t, buf, it.copied, sc);
+            else {
+                RowConst rc;                  // L2 load: a neighbouring row's constants may sit stale in L1
+                {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(&a.consts[it.c]);
+                    uint4 *dst = reinterpret_cast<uint4 *>(&rc);
+#pragma unroll
+                    for (int q = 0; q < (int)(sizeof(RowConst) / 16); ++q) dst[q] = __ldcg(src + q);
+                }
+                if (rc.flags & kRowExact) pass_b_tile<EMIT, true>(a, rc, it.c, it.t, buf, it.copied, sc);
+                else pass_b_tile<EMIT, false>(a, rc, it.c, it.t, buf, it.copied, sc);
+            }
+            if ((a.dbg & 32) && threadIdx.x == 0) sc.tacc[it.is_b ? 6 : 5] += gtime();
+        }
+        // Take the next ticket only now: a ticket that is held but not yet started would stall every later tile
+        // of its row in the look-back (they wait for its aggregate).
+        if (threadIdx.x == 0) s_ticket[stage ^ 1] = (long long)atomicAdd(&a.hdr->ticket, 1u);
+        __syncthreads();
+        cur = s_ticket[stage ^ 1];
+        it = decode_item(a, cur);
+        stage ^= 1;
+        if (threadIdx.x == 0 && it.valid && it.copied > 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&mbar[stage], (uint32_t)it.copied * 4u);
+            bulk_g2s(stage ? buf1 : buf0, it.src, (uint32_t)it.copied * 4u, &mbar[stage], it.is_b ? pol_b : pol_a);
+        }
+    }
+    if ((a.dbg & 32) && threadIdx.x == 0)
+        for (int q = 0; q < 8; ++q) atomicAdd(reinterpret_cast<unsigned long long *>(a.hdr->pad + 1) + q, sc.tacc[q]);
 }
 
 // ------------------------------------------------------------------ K7: decode + mean (tile-major)
@@ -507,7 +719,7 @@ static int quantize_common(const float *X, int64_t n, int64_t d, int64_t ld, int
     if (rc) return rc;
     DME_REQUIRE(m >= (packed ? 1 : 0) && m < ((int64_t)1 << 40), "m=%lld out of range [%d, 2^40)", (long long)m, packed ? 1 : 0);
     DME_REQUIRE(mode == DME_MODE_UNBIASED || mode == DME_MODE_BIASED, "mode=%d unknown", mode);
-    DME_REQUIRE(n * ((d + kTile - 1) / kTile) < ((int64_t)1 << 31), "n * tiles must be < 2^31");
+    DME_REQUIRE(n * ((d + kTile - 1) / kTile) < ((int64_t)1 << 30), "n * tiles must be < 2^30");
     if (packed) {
         DME_REQUIRE(codes != nullptr && dir != nullptr && ((uintptr_t)codes & 15u) == 0, "codes/dir null or codes not 16-byte aligned");
         DME_REQUIRE(codes_bytes >= 1024, "codes_bytes too small");
@@ -520,23 +732,56 @@ static int quantize_common(const float *X, int64_t n, int64_t d, int64_t ld, int
     if (rc) return rc;
     prof_reset();
     prof_mark(st);
-    rc = launch_l1(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, l1_out, st);
-    if (rc) return rc;
-    prof_mark(st);
     char *base = (char *)ws;
+    if (mode == DME_MODE_BIASED) {
+        rc = launch_l1(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, l1_out, st);
+        if (rc) return rc;
+    }
     if (mode == DME_MODE_BIASED)
         return biased_quantize(X, n, d, ld, m, L, ws, k_out, sgn_out, deq_out, ld_out, codes, codes_bytes, dir, st);
-    ScanArgs a;
-    a.X = X; a.d = d; a.ld = ld; a.T = L.T; a.n = n;
-    a.consts = (const RowConst *)(base + L.off_consts);
+    StreamArgs a;
+    a.X = X; a.d = d; a.ld = ld; a.T = L.T; a.n = n; a.m = m;
+    a.consts = (RowConst *)(base + L.off_consts);
     a.desc = (TileDesc *)(base + L.off_desc);
     a.hdr = (WsHeader *)base;
+    a.partial = (double *)(base + L.off_partial);
+    a.a_done = (uint32_t *)(base + L.off_done);
+    a.row_ready = (uint32_t *)(base + L.off_ready);
+    a.x_inject = x_inject; a.l1_inject = l1_inject; a.seed = seed; a.client0 = client0; a.l1_out = l1_out;
     a.k_out = k_out; a.sgn_out = sgn_out; a.deq_out = deq_out; a.ld_out = ld_out;
-    a.codes = codes; a.codes_bytes = codes_bytes; a.dir = dir;
-    const unsigned grid = (unsigned)(n * L.T);
-    if (packed) scan_kernel<kEmitPacked><<<grid, kThreads, 0, st>>>(a);
-    else scan_kernel<kEmitArrays><<<grid, kThreads, 0, st>>>(a);
-    DME_LAUNCH_CHECK("scan_kernel");
+    a.codes = codes; a.codes_bytes = codes_bytes; a.dir = dir; a.W0 = expected_width(m > 0 ? m : 1, d);
+    a.arena_base16 = 0;
+    static int s_sms = 0, s_occ[2] = {0, 0};
+    const size_t dyn = 2 * kTile * sizeof(float);
+    if (s_sms == 0) {
+        int dev = 0;
+        DME_CUDA(cudaGetDevice(&dev));
+        DME_CUDA(cudaDeviceGetAttribute(&s_sms, cudaDevAttrMultiProcessorCount, dev));
+        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s_occ[0], quantize_stream_kernel<kEmitArrays>, kThreads, dyn));
+        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s_occ[1], quantize_stream_kernel<kEmitPacked>, kThreads, dyn));
+    }
+    int64_t G = (int64_t)s_sms * (s_occ[packed ? 1 : 0] > 0 ? s_occ[packed ? 1 : 0] : 1);
+    const int64_t nT = n * L.T;
+    a.lag = L.T + G;
+    a.dbg = 0;
+    if (const char *e = getenv("DME_DBG")) a.dbg = atoi(e);            // development knobs (bit field)
+    if (const char *e = getenv("DME_DBG_LAG")) a.lag = L.T + atoll(e);
+    if (const char *e = getenv("DME_DBG_G")) G = atoll(e);
+    a.total_items = 2 * (nT + a.lag);
+    if (G > a.total_items) G = a.total_items;
+    if (packed) {
+        // primary slots occupy the front of the arena; the bump allocator hands out the space behind them
+        const unsigned long long primary16 = (unsigned long long)nT * 32ull * (unsigned long long)a.W0;
+        if ((long long)(primary16 * 16ull) > codes_bytes) {
+            set_error("code arena too small for the primary slots: %lld < %llu bytes", (long long)codes_bytes, primary16 * 16ull);
+            return DME_EWORKSPACE;
+        }
+        a.arena_base16 = primary16;
+        quantize_stream_kernel<kEmitPacked><<<(unsigned)G, kThreads, dyn, st>>>(a);
+    } else {
+        quantize_stream_kernel<kEmitArrays><<<(unsigned)G, kThreads, dyn, st>>>(a);
+    }
+    DME_LAUNCH_CHECK("quantize_stream_kernel");
     prof_mark(st);
     return DME_OK;
 }

@@ -43,6 +43,7 @@ struct __align__(256) WsHeader {
 struct WsLayout {
     int64_t T;            // tiles per row
     int64_t off_done;     // uint32 a_done[n]
+    int64_t off_ready;    // uint32 row_ready[n]
     int64_t off_consts;   // RowConst consts[n]
     int64_t off_partial;  // double partial[n*T]
     int64_t off_desc;     // TileDesc desc[n*T]
@@ -66,11 +67,21 @@ struct __align__(16) RowSelect {
     uint32_t pad[3];
 };
 
+// Field width the packed code is expected to need for rate m/d on light-tailed data (largest magnitude in a
+// 4096-tile ~ 6 m/d + 1).  Tiles up to this width use fixed primary slots of the arena; wider tiles overflow.
+inline int expected_width(int64_t m, int64_t d) {
+    const double ell = (double)m / (double)d;
+    int w = 2;
+    while (w < 32 && 4.0 * ell + 1.0 >= (double)(1u << (w - 1))) w <<= 1;
+    return w;
+}
+
 inline WsLayout ws_layout(int64_t n, int64_t d) {
     WsLayout L;
     L.T = (d + kTile - 1) / kTile;
     int64_t o = (int64_t)sizeof(WsHeader);
     L.off_done = o; o = align_up(o + 4 * n, 256);
+    L.off_ready = o; o = align_up(o + 4 * n, 256);
     L.zero_bytes = o;
     L.off_consts = o; o = align_up(o + (int64_t)sizeof(RowConst) * n, 256);
     L.off_partial = o; o = align_up(o + 8 * n * L.T, 256);

@@ -131,7 +131,9 @@ def _resolve_m(d, bits_per_dimension, m):
 def _opt_vec(v, n, dev):
     if v is None:
         return None
-    t = torch.as_tensor(np.asarray(v, dtype=np.float32) if not isinstance(v, torch.Tensor) else v, dtype=torch.float32).to(dev).reshape(-1).contiguous()
+    if not isinstance(v, torch.Tensor):
+        v = np.array([float(e) for e in np.asarray(v, dtype=object).reshape(-1)], dtype=np.float32) if not isinstance(v, np.ndarray) else v.astype(np.float32)
+    t = torch.as_tensor(v, dtype=torch.float32).to(dev).reshape(-1).contiguous()
     if t.numel() != n:
         raise ValueError(f"expected {n} injected values, got {t.numel()}")
     return t
@@ -336,8 +338,7 @@ def hadamard(v):
     V, n, d, was_1d = _rows(v)
     if d & (d - 1):
         raise Exception("input numel must be a power of 2")      # AS:103-104, same type and message
-    V = V.clone() if V.data_ptr() == (v.data_ptr() if isinstance(v, torch.Tensor) else 0) else V
-    V = V.contiguous()
+    V = V.clone().contiguous()
     _check(_cabi.lib().dme_hadamard(_ptr(V), n, d, _ld(V), C.c_void_p(_stream())))
     return V[0] if was_1d else V
 
@@ -355,8 +356,7 @@ def rht(x, seed=0, *, diag_inject=None):
     dpad = _pow2_ceil(d)
     out = torch.empty((n, dpad), dtype=torch.float32, device=X.device)
     dg = _diag(diag_inject, dpad, X.device)
-    _check(_cabi.lib().dme_rht(_ptr(X), n, d, _ld(X), _ptr(out), dpad, max(dpad, 4) if n > 1 else (dpad + 3) // 4 * 4, seed, _ptr(dg),
-                               C.c_void_p(_stream())) if dpad >= 4 or n == 1 else -1)
+    _check(_cabi.lib().dme_rht(_ptr(X), n, d, _ld(X), _ptr(out), dpad, dpad, seed, _ptr(dg), C.c_void_p(_stream())))
     return out[0] if was_1d else out
 
 
@@ -411,7 +411,7 @@ def eden_encode(x, nbits=1, *, seed=0, diag_inject=None, norm_inject=None):
     if nbits not in (1, 2):
         raise KeyError(nbits)           # AS:301-320 defines centroids for 1 and 2 bits only
     X, n, d, was_1d = _rows(x)
-    dpad = max(_pow2_ceil(d), 4)
+    dpad = _pow2_ceil(d)
     dev = X.device
     rot = torch.empty((n, dpad), dtype=torch.float32, device=dev)
     bins = torch.empty((n, dpad), dtype=torch.uint8, device=dev)
@@ -454,7 +454,7 @@ def quicfl_decode(Xq, h, d, recv_table, scale, *, exact_mask=None, exact_vals=No
     h = torch.as_tensor(h).to(dev, torch.int32).reshape(n, dpad).contiguous()
     tab = torch.as_tensor(recv_table, dtype=torch.float32).to(dev).contiguous()
     h_len = tab.shape[-1]
-    sc = torch.as_tensor(scale, dtype=torch.float32).to(dev).reshape(-1).contiguous()
+    sc = _opt_vec(scale, n, dev)
     em = ev = eo = None
     if exact_mask is not None:
         em = torch.as_tensor(exact_mask).to(dev, torch.uint8).reshape(n, dpad).contiguous()

@@ -1,0 +1,301 @@
+// reznik.cu -- biased type quantizer: nearest-type rounding with mass repair (Reznik, AS:644-666) behind
+// Type_biased_quantize (AS:669-687).
+//
+// The reference repairs the mass with torch.topk(delta, |Delta|); |Delta| is Theta(d), so this is an
+// order-statistic problem, solved here without sorting:
+//   rz_sum     : k' = floor(m p + 1/2), m' = sum k' (exact, integer atomics)             one pass
+//   rz_hist x4 : MSB-first radix select of the |Delta|-th largest residual key            four passes, 8 bits each
+//                (key = order-preserving uint32 of v, v = delta for Delta>0, -delta for Delta<0)
+//   rz_tiecnt  : per-tile count of residuals equal to the threshold                        one pass
+//   rz_apply   : k = k' -/+ 1 for keys above the threshold and for the FIRST tie_take threshold-equal
+//                coordinates in index order (torch.topk leaves ties unspecified; documented deviation), emit
+// Everything that decides the result is integer arithmetic, so the outcome is independent of scheduling.
+#include "type_quantize.cuh"
+
+namespace dme {
+
+__device__ __forceinline__ void load_tile_blocked(const float *__restrict__ row, int64_t d, int64_t tile0, float (&x)[kEpt]) {
+    const int64_t i0 = tile0 + (int64_t)threadIdx.x * kEpt;
+    if (i0 + kEpt <= d) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4 *>(row + i0 + 4 * q);
+            x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) x[j] = (i0 + j < d) ? row[i0 + j] : 0.0f;
+    }
+}
+
+// AS:648 + AS:654 for one coordinate: k' and the residual delta' = k' - m p (fp32, one rounding per op).
+__device__ __forceinline__ void rz_round(float x, const RowConst &rc, float &kp, float &delta) {
+    const float p = __fdiv_rn(fabsf(x), rc.D);                 // AS:683
+    const float mp = __fmul_rn(rc.mf, p);
+    kp = floorf(__fadd_rn(mp, 0.5f));                          // AS:648
+    delta = __fsub_rn(kp, mp);                                 // AS:654
+}
+// Order-preserving key of the value that torch.topk ranks: delta (Delta > 0) or -delta (Delta < 0).
+__device__ __forceinline__ uint32_t rz_key(float delta, bool neg) {
+    float v = neg ? -delta : delta;
+    v = __fadd_rn(v, 0.0f);                                    // -0 -> +0: equal floats must get equal keys
+    const uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(kThreads)
+rz_sum_kernel(const float *__restrict__ X, int64_t d, int64_t ld, const RowConst *__restrict__ consts, RowSelect *sel) {
+    __shared__ unsigned long long s_red[kWarps];
+    const int64_t c = blockIdx.y, t = blockIdx.x;
+    const RowConst rc = consts[c];
+    float x[kEpt];
+    load_tile_blocked(X + c * ld, d, t * kTile, x);
+    unsigned long long s = 0;
+#pragma unroll
+    for (int j = 0; j < kEpt; ++j) {
+        float kp, dl;
+        rz_round(x[j], rc, kp, dl);
+        s += (unsigned long long)kp;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long tot = 0;
+        for (int w = 0; w < kWarps; ++w) tot += s_red[w];
+        if (tot) atomicAdd(&sel[c].mprime, tot);
+    }
+}
+
+__global__ void rz_init_kernel(RowSelect *sel, int64_t n, int64_t m, int64_t d) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const long long Delta = (long long)sel[c].mprime - (long long)m;       // AS:655
+    sel[c].Delta = Delta;
+    long long need = Delta < 0 ? -Delta : Delta;
+    if (need > d) need = d;            // the reference's topk raises when |Delta| > d; here every coordinate is adjusted once
+    sel[c].remaining = (uint32_t)need;
+    sel[c].prefix = 0;
+}
+
+// One radix digit: histogram of byte `pass` (0 = most significant) over keys that match the prefix so far.
+__global__ void __launch_bounds__(kThreads)
+rz_hist_kernel(const float *__restrict__ X, int64_t d, int64_t ld, const RowConst *__restrict__ consts, RowSelect *sel, int pass) {
+    __shared__ uint32_t s_hist[256];
+    const int64_t c = blockIdx.y, t = blockIdx.x;
+    const long long Delta = sel[c].Delta;
+    if (Delta == 0 || sel[c].remaining == 0) return;
+    const RowConst rc = consts[c];
+    const uint32_t prefix = sel[c].prefix;
+    s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    float x[kEpt];
+    load_tile_blocked(X + c * ld, d, t * kTile, x);
+    const int64_t i0 = t * kTile + (int64_t)threadIdx.x * kEpt;
+    const int shift = 24 - 8 * pass;
+#pragma unroll
+    for (int j = 0; j < kEpt; ++j) {
+        if (i0 + j >= d) break;
+        float kp, dl;
+        rz_round(x[j], rc, kp, dl);
+        const uint32_t key = rz_key(dl, Delta < 0);
+        const bool match = pass == 0 ? true : ((key >> (shift + 8)) == prefix);
+        if (match) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    const uint32_t v = s_hist[threadIdx.x];
+    if (v) atomicAdd(&sel[c].hist[pass][threadIdx.x], v);
+}
+
+// Choose the digit: walk the bins from the top until the wanted rank falls inside one.
+__global__ void rz_pick_kernel(RowSelect *sel, int pass) {
+    RowSelect &s = sel[blockIdx.x];
+    if (threadIdx.x != 0 || s.Delta == 0 || s.remaining == 0) return;
+    uint32_t rem = s.remaining, cum = 0;
+    int b = 255;
+    for (; b > 0; --b) {
+        const uint32_t h = s.hist[pass][b];
+        if (cum + h >= rem) break;
+        cum += h;
+    }
+    s.prefix = (s.prefix << 8) | (uint32_t)b;
+    s.remaining = rem - cum;                     // keys in higher bins are all selected
+    if (pass == 3) { s.tie_key = s.prefix; s.tie_take = s.remaining; }
+}
+
+__global__ void __launch_bounds__(kThreads)
+rz_tiecnt_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T, const RowConst *__restrict__ consts,
+                 const RowSelect *__restrict__ sel, uint32_t *__restrict__ tie_cnt) {
+    __shared__ uint32_t s_red[kWarps];
+    const int64_t c = blockIdx.y, t = blockIdx.x;
+    const long long Delta = sel[c].Delta;
+    uint32_t cnt = 0;
+    if (Delta != 0) {
+        const RowConst rc = consts[c];
+        const uint32_t tie = sel[c].tie_key;
+        float x[kEpt];
+        load_tile_blocked(X + c * ld, d, t * kTile, x);
+        const int64_t i0 = t * kTile + (int64_t)threadIdx.x * kEpt;
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) {
+            if (i0 + j >= d) break;
+            float kp, dl;
+            rz_round(x[j], rc, kp, dl);
+            cnt += (rz_key(dl, Delta < 0) == tie) ? 1u : 0u;
+        }
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < kWarps; ++w) tot += s_red[w];
+        tie_cnt[c * T + t] = tot;
+    }
+}
+
+// Exclusive prefix of the per-tile tie counts of one row (one CTA per row, in place).
+__global__ void __launch_bounds__(kThreads) rz_tiescan_kernel(uint32_t *tie_cnt, int64_t T) {
+    __shared__ uint32_t s_w[kWarps];
+    __shared__ uint32_t s_carry;
+    uint32_t *row = tie_cnt + (int64_t)blockIdx.x * T;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < T; base += kThreads) {
+        const int64_t i = base + threadIdx.x;
+        const uint32_t v = i < T ? row[i] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((threadIdx.x & 31) >= o) inc += up;
+        }
+        if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += s_w[w];
+        const uint32_t carry = s_carry;
+        if (i < T) row[i] = carry + wbase + inc - v;
+        __syncthreads();
+        if (threadIdx.x == kThreads - 1) s_carry = carry + wbase + inc;
+        __syncthreads();
+    }
+}
+
+struct RzEmit {
+    int32_t *k_out; uint8_t *sgn_out; float *deq_out; int64_t ld_out;
+    PackTarget pack; int packed;
+};
+
+__global__ void __launch_bounds__(kThreads)
+rz_apply_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T, const RowConst *__restrict__ consts,
+                const RowSelect *__restrict__ sel, const uint32_t *__restrict__ tie_base, RzEmit e) {
+    __shared__ uint32_t s_w[kWarps];
+    __shared__ PackScratch s_pack;
+    const int64_t c = blockIdx.y, t = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const RowConst rc = consts[c];
+    const long long Delta = sel[c].Delta;
+    const uint32_t tie = sel[c].tie_key, take = sel[c].tie_take;
+    float x[kEpt];
+    load_tile_blocked(X + c * ld, d, t * kTile, x);
+    const int64_t i0 = t * kTile + (int64_t)threadIdx.x * kEpt;
+    float kp[kEpt];
+    uint32_t key[kEpt];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < kEpt; ++j) {
+        float dl;
+        rz_round(x[j], rc, kp[j], dl);
+        key[j] = rz_key(dl, Delta < 0);
+        if (Delta != 0 && i0 + j < d && key[j] == tie) ++mine;
+    }
+    // ordered rank of this thread's first threshold-equal coordinate inside the row
+    uint32_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += up;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    uint32_t rank = (Delta != 0 ? tie_base[c * T + t] : 0u) + inc - mine;
+    for (int w = 0; w < warp; ++w) rank += s_w[w];
+    const float adj = Delta > 0 ? -1.0f : 1.0f;
+#pragma unroll
+    for (int j = 0; j < kEpt; ++j) {
+        if (Delta == 0 || i0 + j >= d) continue;
+        bool selct = key[j] > tie;
+        if (key[j] == tie) { selct = rank < take; ++rank; }
+        if (selct) kp[j] = __fadd_rn(kp[j], adj);                              // AS:660 / AS:664
+    }
+    if (!e.packed) {
+        bool ovf = false;
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) {
+            const int64_t i = i0 + j;
+            if (i >= d) break;
+            if (e.deq_out) {
+                const float sg = (x[j] > 0.0f) ? 1.0f : ((x[j] < 0.0f) ? -1.0f : 0.0f);     // AS:682 signs of the input
+                e.deq_out[c * e.ld_out + i] = __fmul_rn(__fmul_rn(rc.L1f, sg), __fdiv_rn(kp[j], rc.mf));   // AS:666, AS:687
+            }
+            if (e.k_out) {
+                if (kp[j] >= 2147483648.0f) { ovf = true; e.k_out[c * e.ld_out + i] = 0x7fffffff; }
+                else e.k_out[c * e.ld_out + i] = (int32_t)kp[j];
+            }
+            if (e.sgn_out) e.sgn_out[c * e.ld_out + i] = (uint8_t)(__float_as_uint(x[j]) >> 31);
+        }
+        if (ovf) atomicOr(&e.pack.hdr->status, 1u);
+    } else {
+        uint32_t k[kEpt], sg[kEpt];
+        bool ovf = false;
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) {
+            const float kk = (i0 + j < d) ? kp[j] : 0.0f;
+            if (kk >= 2147483648.0f) { ovf = true; k[j] = 0x7fffffffu; } else k[j] = (uint32_t)kk;
+            sg[j] = __float_as_uint(x[j]) >> 31;
+        }
+        emit_packed_tile(e.pack, c * T + t, k, sg, ovf, s_pack);
+    }
+}
+
+// Called after l1_kernel has published the row constants.
+int biased_quantize(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
+                    int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
+                    uint32_t *codes, int64_t codes_bytes, uint64_t *dir, cudaStream_t st) {
+    char *base = (char *)ws;
+    const RowConst *consts = (const RowConst *)(base + L.off_consts);
+    RowSelect *sel = (RowSelect *)(base + L.off_sel);
+    uint32_t *tie_cnt = (uint32_t *)(base + L.off_partial);         // the L1 partials are dead by now
+    const dim3 grid((unsigned)L.T, (unsigned)n);
+    rz_sum_kernel<<<grid, kThreads, 0, st>>>(X, d, ld, consts, sel);
+    DME_LAUNCH_CHECK("rz_sum_kernel");
+    rz_init_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sel, n, m, d);
+    DME_LAUNCH_CHECK("rz_init_kernel");
+    for (int pass = 0; pass < 4; ++pass) {
+        rz_hist_kernel<<<grid, kThreads, 0, st>>>(X, d, ld, consts, sel, pass);
+        DME_LAUNCH_CHECK("rz_hist_kernel");
+        rz_pick_kernel<<<(unsigned)n, 32, 0, st>>>(sel, pass);
+        DME_LAUNCH_CHECK("rz_pick_kernel");
+    }
+    rz_tiecnt_kernel<<<grid, kThreads, 0, st>>>(X, d, ld, L.T, consts, sel, tie_cnt);
+    DME_LAUNCH_CHECK("rz_tiecnt_kernel");
+    rz_tiescan_kernel<<<(unsigned)n, kThreads, 0, st>>>(tie_cnt, L.T);
+    DME_LAUNCH_CHECK("rz_tiescan_kernel");
+    RzEmit e;
+    e.k_out = k_out; e.sgn_out = sgn_out; e.deq_out = deq_out; e.ld_out = ld_out;
+    e.packed = codes != nullptr;
+    e.pack.codes = codes; e.pack.codes_bytes = codes_bytes; e.pack.dir = dir; e.pack.hdr = (WsHeader *)base;
+    e.pack.W0 = expected_width(m, d);
+    e.pack.arena_base16 = (unsigned long long)(n * L.T) * 32ull * (unsigned long long)e.pack.W0;
+    if (e.packed && (long long)(e.pack.arena_base16 * 16ull) > codes_bytes) {
+        set_error("code arena too small for the primary slots: %lld bytes", (long long)codes_bytes);
+        return DME_EWORKSPACE;
+    }
+    rz_apply_kernel<<<grid, kThreads, 0, st>>>(X, d, ld, L.T, consts, sel, tie_cnt, e);
+    DME_LAUNCH_CHECK("rz_apply_kernel");
+    return DME_OK;
+}
+
+}  // namespace dme

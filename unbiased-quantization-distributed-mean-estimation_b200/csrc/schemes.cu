@@ -1,0 +1,325 @@
+// schemes.cu -- the comparison quantizers of the reference: DRIVE (AS:707-752), EDEN (AS:323-426), the QUIC-FL
+// receiver (AS:526-535) and the scalar stochastic quantizer (AS:755-790).  Rotations come from hadamard.cu.
+// Reductions whose fp32 order ATen leaves unspecified (norms, dot products, abs-sums) accumulate in fp64 in a
+// fixed order and round once, like the oracle.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace dme {
+
+int fwht_rows(const float *src, int64_t src_d, int64_t src_ld, float *dst, int64_t d, int64_t dst_ld, int64_t n,
+              const float *diag, uint64_t seed, int pre_diag, int post_diag, cudaStream_t st);   // hadamard.cu
+
+__device__ __forceinline__ float sgn0(float v) { return (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f); }
+
+// ------------------------------------------------------------------ DRIVE: one CTA per 2048-chunk
+__global__ void __launch_bounds__(256)
+drive_kernel(const float *__restrict__ X, int64_t d, int64_t ld, float *__restrict__ out, int64_t ld_out, uint64_t seed,
+             const float *__restrict__ dsign, int64_t dsign_row, int compat) {
+    __shared__ float buf[2048];
+    __shared__ float Dg[2048];
+    __shared__ double s_red[kWarps];
+    const int64_t c = blockIdx.y, chunk = blockIdx.x;
+    const int64_t s0 = chunk * 2048;
+    const int len = (int)((d - s0 < 2048) ? (d - s0) : 2048);
+    int np2 = 1, lg = 0;
+    while (np2 < len) { np2 <<= 1; ++lg; }
+    const float *row = X + c * ld;
+    double n2 = 0.0;
+    for (int j = threadIdx.x; j < np2; j += 256) {
+        const float xv = j < len ? row[s0 + j] : 0.0f;
+        const float Dv = dsign ? dsign[c * dsign_row + s0 + j]
+                               : philox_sign(seed, (uint64_t)(s0 + j), kStreamDrive, (uint32_t)c);       // AS:735
+        Dg[j] = Dv;
+        buf[j] = __fmul_rn(Dv, xv);                                                                    // AS:737
+        n2 += (double)xv * (double)xv;
+    }
+    n2 = block_sum_f64(n2, s_red);
+    __syncthreads();
+    auto transform = [&]() {
+        if (compat == 0) {
+            // AS:37-59 as executed: lg stages on every adjacent pair
+            for (int j = threadIdx.x; 2 * j + 1 < np2; j += 256) {
+                float a = buf[2 * j], b = buf[2 * j + 1];
+                for (int s = 0; s < lg; ++s) { const float t = __fadd_rn(a, b); b = __fsub_rn(t, b); a = t; }
+                buf[2 * j] = a; buf[2 * j + 1] = b;
+            }
+            __syncthreads();
+        } else {
+            for (int h = 1; h < np2; h <<= 1) {
+                for (int j = threadIdx.x; j < np2 / 2; j += 256) {
+                    const int i = ((j / h) * 2 * h) + (j % h);
+                    const float a = buf[i], b = buf[i + h];
+                    buf[i] = __fadd_rn(a, b); buf[i + h] = __fsub_rn(a, b);
+                }
+                __syncthreads();
+            }
+        }
+    };
+    transform();                                                                                       // AS:738
+    double l1 = 0.0;
+    for (int j = threadIdx.x; j < np2; j += 256) l1 += (double)fabsf(buf[j]);
+    l1 = block_sum_f64(l1, s_red);
+    const float nrm = (float)sqrt(n2);
+    const float S = __fdiv_rn(__fmul_rn(nrm, nrm), __fadd_rn((float)l1, 1e-12f));                      // AS:741
+    __syncthreads();
+    for (int j = threadIdx.x; j < np2; j += 256) buf[j] = __fmul_rn(S, sgn0(buf[j]));                  // AS:743
+    __syncthreads();
+    transform();                                                                                       // AS:746
+    for (int j = threadIdx.x; j < len; j += 256) out[c * ld_out + s0 + j] = __fmul_rn(buf[j], Dg[j]);  // AS:747-750
+}
+
+// ------------------------------------------------------------------ row reductions (fp64, fixed order)
+// partial[c * nb + b] = sum over the b-th slice of row c of f(v).  kind 0: v^2, 1: centroid[bin]*v (EDEN dot)
+struct EdenTab { float cent[4]; float bnd[3]; int nc; };
+
+__global__ void __launch_bounds__(256)
+row_sumsq_kernel(const float *__restrict__ V, int64_t dpad, int64_t ld, int nb, double *__restrict__ partial) {
+    __shared__ double s_red[kWarps];
+    const int64_t c = blockIdx.y;
+    const int64_t per = (dpad + nb - 1) / nb, lo = blockIdx.x * per, hi = min(dpad, lo + per);
+    double s = 0.0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += 256) { const double v = V[c * ld + i]; s += v * v; }
+    s = block_sum_f64(s, s_red);
+    if (threadIdx.x == 0) partial[c * nb + blockIdx.x] = s;
+}
+__global__ void norm_finalize_kernel(const double *__restrict__ partial, int nb, int64_t n, const float *__restrict__ inject,
+                                     float *__restrict__ nrm) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double s = 0.0;
+    for (int b = 0; b < nb; ++b) s += partial[c * nb + b];
+    nrm[c] = inject ? inject[c] : (float)sqrt(s);                                 // torch.norm(vec, 2)
+}
+__global__ void __launch_bounds__(256)
+eden_bucket_kernel(const float *__restrict__ V, int64_t dpad, int64_t ld, int nb, const float *__restrict__ nrm, float sq, EdenTab tab,
+                   uint8_t *__restrict__ bins, double *__restrict__ partial) {
+    __shared__ double s_red[kWarps];
+    const int64_t c = blockIdx.y;
+    const int64_t per = (dpad + nb - 1) / nb, lo = blockIdx.x * per, hi = min(dpad, lo + per);
+    const float nr = nrm[c];
+    double s = 0.0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
+        const float v = V[c * ld + i];
+        const float z = __fdiv_rn(__fmul_rn(v, sq), nr);                           // AS:343
+        int b = 0;
+        while (b < tab.nc - 1 && tab.bnd[b] < z) ++b;                              // torch.bucketize, right=False
+        bins[c * dpad + i] = (uint8_t)b;
+        s += (double)tab.cent[b] * (double)v;
+    }
+    s = block_sum_f64(s, s_red);
+    if (threadIdx.x == 0) partial[c * nb + blockIdx.x] = s;
+}
+__global__ void eden_scale_kernel(const double *__restrict__ partial, int nb, int64_t n, const float *__restrict__ nrm, float *__restrict__ scale) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double s = 0.0;
+    for (int b = 0; b < nb; ++b) s += partial[c * nb + b];
+    scale[c] = __fdiv_rn(__fmul_rn(nrm[c], nrm[c]), (float)s);                     // AS:348
+}
+__global__ void eden_lookup_kernel(const uint8_t *__restrict__ bins, int64_t total, EdenTab tab, float *__restrict__ work) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) work[i] = tab.cent[bins[i] & 3];                                // AS:400
+}
+__global__ void scale_rows_kernel(const float *__restrict__ work, int64_t dpad, const float *__restrict__ scale, int64_t n, int64_t d,
+                                  float *__restrict__ out, int64_t ld_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * d) return;
+    const int64_t c = i / d, j = i - c * d;
+    out[c * ld_out + j] = scale ? __fmul_rn(scale[c], work[c * dpad + j]) : work[c * dpad + j];   // AS:426 / AS:535
+}
+
+static EdenTab eden_tab(int nbits) {
+    EdenTab t{};
+    if (nbits == 1) {
+        t.nc = 2; t.cent[0] = -(float)0.7978845608028654; t.cent[1] = (float)0.7978845608028654;   // AS:303
+        t.bnd[0] = (t.cent[0] + t.cent[1]) / 2.0f;
+    } else {
+        t.nc = 4;
+        t.cent[0] = -(float)1.5104176087114887; t.cent[1] = -(float)0.4527800398860679;            // AS:304
+        t.cent[2] = (float)0.4527800398860679; t.cent[3] = (float)1.5104176087114887;
+        for (int i = 0; i < 3; ++i) t.bnd[i] = (t.cent[i] + t.cent[i + 1]) / 2.0f;                 // AS:311-312
+    }
+    return t;
+}
+
+// ------------------------------------------------------------------ QUIC-FL receiver: one CTA per row
+__global__ void __launch_bounds__(256)
+quicfl_gather_kernel(const int32_t *__restrict__ Xq, const int32_t *__restrict__ h, int64_t dpad, int h_len,
+                     const float *__restrict__ table, int table_len, const uint8_t *__restrict__ mask, const float *__restrict__ exact_vals,
+                     const int64_t *__restrict__ exact_off, const float *__restrict__ scale, float *__restrict__ work) {
+    __shared__ uint32_t s_w[kWarps];
+    __shared__ uint32_t s_carry;
+    const int64_t c = blockIdx.x;
+    const float sc = scale[c];
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < dpad; base += 256) {
+        const int64_t i = base + threadIdx.x;
+        const bool live = i < dpad;
+        const uint32_t mk = (live && mask) ? (mask[c * dpad + i] != 0) : 0u;
+        uint32_t inc = mk;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((threadIdx.x & 31) >= o) inc += up;
+        }
+        if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += s_w[w];
+        const uint32_t carry = s_carry;
+        if (live) {
+            int64_t idx = (int64_t)Xq[c * dpad + i] * h_len + h[c * dpad + i];
+            idx = idx < 0 ? 0 : (idx >= table_len ? table_len - 1 : idx);
+            float val = table[idx];                                                               // AS:530
+            if (mk) val = exact_vals[exact_off[c] + carry + wbase + inc - 1];                      // AS:531
+            work[c * dpad + i] = __fdiv_rn(val, sc);                                               // AS:532
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) s_carry = carry + wbase + inc;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ scalar stochastic quantizer
+__global__ void __launch_bounds__(256)
+row_minmax_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int nb, float *__restrict__ pmin, float *__restrict__ pmax) {
+    __shared__ float s_mn[kWarps], s_mx[kWarps];
+    const int64_t c = blockIdx.y;
+    const int64_t per = (d + nb - 1) / nb, lo = blockIdx.x * per, hi = min(d, lo + per);
+    float mn = INFINITY, mx = -INFINITY;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += 256) { const float v = X[c * ld + i]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kWarps; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
+        pmin[c * nb + blockIdx.x] = mn; pmax[c * nb + blockIdx.x] = mx;
+    }
+}
+__global__ void __launch_bounds__(256)
+scalar_kernel(const float *__restrict__ X, int64_t n, int64_t d, int64_t ld, int nb, const float *__restrict__ pmin,
+              const float *__restrict__ pmax, float nlevels, uint64_t seed, uint64_t client0, const float *__restrict__ u_inject,
+              float *__restrict__ out, int64_t ld_out) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n * d) return;
+    const int64_t c = gid / d, i = gid - c * d;
+    float mn = INFINITY, mx = -INFINITY;
+    for (int b = 0; b < nb; ++b) { mn = fminf(mn, pmin[c * nb + b]); mx = fmaxf(mx, pmax[c * nb + b]); }
+    const float x = X[c * ld + i];
+    const float denom = __fsub_rn(mx, mn);
+    if (denom == 0.0f || nlevels < 1.0f) { out[c * ld_out + i] = x; return; }                       // AS:763-765, AS:772-773
+    float q = __fdiv_rn(__fsub_rn(x, mn), denom);                                                    // AS:768
+    q = fminf(fmaxf(q, 0.0f), 1.0f);                                                                 // AS:776
+    const float t = __fmul_rn(q, nlevels);
+    const float bf = floorf(t);                                                                      // AS:779
+    const float fr = __fsub_rn(t, bf);
+    float u;
+    if (u_inject) u = u_inject[c * d + i];
+    else {
+        const uint64_t cl = client0 + (uint64_t)c;
+        u = u24_to_unit(philox4x32_10(seed ^ (cl * 0x9E3779B97F4A7C15ull), (uint32_t)i, (uint32_t)((uint64_t)i >> 32), (uint32_t)cl, kStreamScalar).x);
+    }
+    const float bi = __fadd_rn(bf, (u < fr) ? 1.0f : 0.0f);                                          // AS:783-784
+    q = __fdiv_rn(bi, nlevels);                                                                      // AS:787
+    out[c * ld_out + i] = __fadd_rn(__fmul_rn(q, __fsub_rn(mx, mn)), mn);                            // AS:788
+}
+
+static int pow2_ceil(int64_t v) { int64_t p = 1; while (p < v) p <<= 1; return (int)p; }
+static int slices(int64_t d) { int64_t nb = (d + 16383) / 16384; return (int)(nb < 1 ? 1 : (nb > 64 ? 64 : nb)); }
+
+}  // namespace dme
+
+using namespace dme;
+
+extern "C" int dme_drive(const float *X, int64_t n, int64_t d, int64_t ld, float *out, int64_t ld_out, uint64_t seed,
+                         const float *dsign_inject, int compat, dme_stream_t stream) {
+    DME_REQUIRE(X && out && n >= 1 && n <= 65535 && d >= 1 && ld >= d && ld_out >= d, "bad argument");
+    DME_REQUIRE(compat == 0 || compat == 1, "compat must be 0 (reference transform) or 1 (true WHT)");
+    const int64_t chunks = (d + 2047) / 2048;
+    const int64_t tail = d - (chunks - 1) * 2048;
+    const int64_t row_pad = (chunks - 1) * 2048 + pow2_ceil(tail);
+    dim3 grid((unsigned)chunks, (unsigned)n);
+    drive_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, d, ld, out, ld_out, seed, dsign_inject, row_pad, compat);
+    DME_LAUNCH_CHECK("drive_kernel");
+    return DME_OK;
+}
+
+extern "C" int dme_eden_encode(const float *X, int64_t n, int64_t d, int64_t ld, int64_t dpad, int nbits, uint64_t seed,
+                               const float *diag_inject, const float *norm_inject, float *rot, uint8_t *bins, float *scale,
+                               dme_stream_t stream) {
+    DME_REQUIRE(X && rot && bins && scale && n >= 1 && n <= 65535, "bad argument");
+    DME_REQUIRE(nbits == 1 || nbits == 2, "EDEN centroids exist for 1 and 2 bits only (AS:301-320)");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = fwht_rows(X, d, ld, rot, dpad, dpad, n, diag_inject, seed, 1, 0, st);                   // AS:378-380
+    if (rc) return rc;
+    const int nb = slices(dpad);
+    double *partial = nullptr;
+    DME_CUDA(cudaMallocAsync(&partial, sizeof(double) * (size_t)(n * nb), st));
+    float *nrm = nullptr;
+    DME_CUDA(cudaMallocAsync(&nrm, sizeof(float) * (size_t)n, st));
+    dim3 grid((unsigned)nb, (unsigned)n);
+    row_sumsq_kernel<<<grid, 256, 0, st>>>(rot, dpad, dpad, nb, partial);
+    DME_LAUNCH_CHECK("row_sumsq_kernel");
+    norm_finalize_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(partial, nb, n, norm_inject, nrm);
+    DME_LAUNCH_CHECK("norm_finalize_kernel");
+    const float sq = (float)std::pow((double)dpad, 0.5);                                             // vec.numel() ** 0.5
+    eden_bucket_kernel<<<grid, 256, 0, st>>>(rot, dpad, dpad, nb, nrm, sq, eden_tab(nbits), bins, partial);
+    DME_LAUNCH_CHECK("eden_bucket_kernel");
+    eden_scale_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(partial, nb, n, nrm, scale);
+    DME_LAUNCH_CHECK("eden_scale_kernel");
+    DME_CUDA(cudaFreeAsync(partial, st));
+    DME_CUDA(cudaFreeAsync(nrm, st));
+    return DME_OK;
+}
+
+extern "C" int dme_eden_decode(const uint8_t *bins, const float *scale, int64_t n, int64_t d, int64_t dpad, int nbits, uint64_t seed,
+                               const float *diag_inject, float *work, float *out, int64_t ld_out, dme_stream_t stream) {
+    DME_REQUIRE(bins && scale && work && out && n >= 1 && d >= 1 && dpad >= d && ld_out >= d, "bad argument");
+    DME_REQUIRE(nbits == 1 || nbits == 2, "EDEN centroids exist for 1 and 2 bits only (AS:301-320)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total = n * dpad;
+    eden_lookup_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(bins, total, eden_tab(nbits), work);
+    DME_LAUNCH_CHECK("eden_lookup_kernel");
+    int rc = fwht_rows(work, dpad, dpad, work, dpad, dpad, n, diag_inject, seed, 0, 1, st);          // AS:425
+    if (rc) return rc;
+    scale_rows_kernel<<<(unsigned)((n * d + 255) / 256), 256, 0, st>>>(work, dpad, scale, n, d, out, ld_out);
+    DME_LAUNCH_CHECK("scale_rows_kernel");
+    return DME_OK;
+}
+
+extern "C" int dme_quicfl_decode(const int32_t *Xq, const int32_t *h, int64_t n, int64_t d, int64_t dpad, int h_len,
+                                 const float *recv_table, int table_len, const uint8_t *exact_mask, const float *exact_vals,
+                                 const int64_t *exact_off, const float *scale, uint64_t rotation_seed, const float *diag_inject,
+                                 float *work, float *out, int64_t ld_out, dme_stream_t stream) {
+    DME_REQUIRE(Xq && h && recv_table && scale && work && out, "null pointer argument");
+    DME_REQUIRE(n >= 1 && d >= 1 && dpad >= d && h_len >= 1 && table_len >= h_len && ld_out >= d, "bad geometry");
+    DME_REQUIRE(!exact_mask || (exact_vals && exact_off), "exact_mask needs exact_vals and exact_off");
+    cudaStream_t st = (cudaStream_t)stream;
+    quicfl_gather_kernel<<<(unsigned)n, 256, 0, st>>>(Xq, h, dpad, h_len, recv_table, table_len, exact_mask, exact_vals, exact_off, scale, work);
+    DME_LAUNCH_CHECK("quicfl_gather_kernel");
+    int rc = fwht_rows(work, dpad, dpad, work, dpad, dpad, n, diag_inject, rotation_seed, 0, 1, st);  // AS:534
+    if (rc) return rc;
+    scale_rows_kernel<<<(unsigned)((n * d + 255) / 256), 256, 0, st>>>(work, dpad, nullptr, n, d, out, ld_out);
+    DME_LAUNCH_CHECK("scale_rows_kernel");
+    return DME_OK;
+}
+
+extern "C" int dme_scalar_quantize(const float *X, int64_t n, int64_t d, int64_t ld, float nlevels, uint64_t seed, uint64_t client0,
+                                   const float *u_inject, float *out, int64_t ld_out, dme_stream_t stream) {
+    DME_REQUIRE(X && out && n >= 1 && n <= 65535 && d >= 1 && ld >= d && ld_out >= d, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = slices(d);
+    float *pm = nullptr;
+    DME_CUDA(cudaMallocAsync(&pm, sizeof(float) * (size_t)(2 * n * nb), st));
+    dim3 grid((unsigned)nb, (unsigned)n);
+    row_minmax_kernel<<<grid, 256, 0, st>>>(X, d, ld, nb, pm, pm + n * nb);
+    DME_LAUNCH_CHECK("row_minmax_kernel");
+    scalar_kernel<<<(unsigned)((n * d + 255) / 256), 256, 0, st>>>(X, n, d, ld, nb, pm, pm + n * nb, nlevels, seed, client0, u_inject, out, ld_out);
+    DME_LAUNCH_CHECK("scalar_kernel");
+    DME_CUDA(cudaFreeAsync(pm, st));
+    return DME_OK;
+}

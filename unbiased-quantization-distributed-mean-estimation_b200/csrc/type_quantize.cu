@@ -190,23 +190,6 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
 }
 
-// Pack 16 (magnitude, sign) pairs of one thread with field width W into W/2 words.
-template <int W>
-__device__ __forceinline__ void pack_store(const uint32_t (&k)[kEpt], const uint32_t (&sg)[kEpt], uint32_t *tile_words) {
-    constexpr int kPerWord = 32 / W;
-#pragma unroll
-    for (int q = 0; q < W / 2; ++q) {
-        uint32_t word = 0;
-#pragma unroll
-        for (int e = 0; e < kPerWord; ++e) {
-            const int j = q * kPerWord + e;
-            const uint32_t field = (W == 32) ? ((sg[j] << 31) | k[j]) : ((sg[j] << (W - 1)) | k[j]);
-            word |= field << ((W * e) & 31);
-        }
-        tile_words[q * kThreads + threadIdx.x] = word;
-    }
-}
-
 // AS:625-631 for one coordinate.  EXACT: IEEE division + floorf.  Fast: x/D by Markstein's correction of x*rcp
 // (correctly rounded for D in [2^-20, 2^100], 1/D correctly rounded, quotient normal) and floor by adding 2^23
 // toward zero (exact for 0 <= mp < 2^23).
@@ -236,8 +219,7 @@ struct TileScratch {
     double P;
     long long Pq;
     int alast[kWarps];
-    uint32_t u32[kWarps];
-    unsigned long long off16;
+    PackScratch pack;
     uint32_t flag;
 };
 
@@ -441,48 +423,15 @@ __device__ __forceinline__ void pass_b_tile(const StreamArgs &a, const RowConst 
         }
         if (ovf) atomicOr(&a.hdr->status, 1u);
     } else {
-        uint32_t k[kEpt], sg[kEpt], kmax = 0;
+        uint32_t k[kEpt], sg[kEpt];
         bool ovf = false;
 #pragma unroll
         for (int j = 0; j < kEpt; ++j) {
             if (kf[j] >= 2147483648.0f) { ovf = true; k[j] = 0x7fffffffu; } else k[j] = (uint32_t)kf[j];
             sg[j] = __float_as_uint(x[j]) >> 31;
-            kmax = max(kmax, k[j]);
         }
-        if (ovf) atomicOr(&a.hdr->status, 1u);
-        kmax = __reduce_max_sync(0xffffffffu, kmax);
-        if (lane == 0) sc.u32[warp] = kmax;
-        __syncthreads();
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) kmax = max(kmax, sc.u32[w]);
-        int W = 2;
-        while (W < 32 && kmax >= (1u << (W - 1))) W <<= 1;
-        // Tiles no wider than the expected width W0 live in their fixed primary slot; wider ones take overflow space.
-        unsigned long long off16;
-        if (W <= a.W0) {
-            off16 = (unsigned long long)(c * a.T + t) * (32ull * a.W0);
-            if (threadIdx.x == 0) a.dir[c * a.T + t] = (off16 << 8) | (unsigned long long)W;
-        } else {
-            if (threadIdx.x == 0) {
-                const unsigned long long units = 32ull * W;                  // 512*W bytes / 16
-                unsigned long long off = a.arena_base16 + atomicAdd(&a.hdr->arena_top, units);
-                if ((long long)((off + units) * 16ull) > a.codes_bytes) { atomicOr(&a.hdr->status, 2u); off = ~0ull; }
-                sc.off16 = off;
-                a.dir[c * a.T + t] = (off == ~0ull) ? 0ull : ((off << 8) | (unsigned long long)W);
-            }
-            __syncthreads();
-            off16 = sc.off16;
-        }
-        if (off16 != ~0ull) {
-            uint32_t *tw = a.codes + off16 * 4ull;
-            switch (W) {
-                case 2: pack_store<2>(k, sg, tw); break;
-                case 4: pack_store<4>(k, sg, tw); break;
-                case 8: pack_store<8>(k, sg, tw); break;
-                case 16: pack_store<16>(k, sg, tw); break;
-                default: pack_store<32>(k, sg, tw); break;
-            }
-        }
+        PackTarget pt{a.codes, a.codes_bytes, a.dir, a.hdr, a.W0, a.arena_base16};
+        emit_packed_tile(pt, c * a.T + t, k, sg, ovf, sc.pack);
     }
 }
 

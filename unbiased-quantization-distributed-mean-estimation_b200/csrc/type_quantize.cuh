@@ -91,4 +91,71 @@ inline WsLayout ws_layout(int64_t n, int64_t d) {
     return L;
 }
 
+#ifdef __CUDACC__
+// ------------------------------------------------------------------ packed-code emit shared by both quantizer modes
+struct PackTarget { uint32_t *codes; int64_t codes_bytes; uint64_t *dir; WsHeader *hdr; int W0; unsigned long long arena_base16; };
+struct PackScratch { uint32_t u32[kWarps]; unsigned long long off16; };
+
+// Pack 16 (magnitude, sign) pairs of one thread with field width W into W/2 words.
+template <int W>
+__device__ __forceinline__ void pack_store(const uint32_t (&k)[kEpt], const uint32_t (&sg)[kEpt], uint32_t *tile_words) {
+    constexpr int kPerWord = 32 / W;
+#pragma unroll
+    for (int q = 0; q < W / 2; ++q) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int e = 0; e < kPerWord; ++e) {
+            const int j = q * kPerWord + e;
+            const uint32_t field = (W == 32) ? ((sg[j] << 31) | k[j]) : ((sg[j] << (W - 1)) | k[j]);
+            word |= field << ((W * e) & 31);
+        }
+        tile_words[q * kThreads + threadIdx.x] = word;
+    }
+}
+
+// Whole CTA: choose the tile's minimal field width, place it (fixed primary slot when W <= W0, bump-allocated
+// overflow space otherwise), write the directory entry and the words.  slot = client * T + tile.
+__device__ __forceinline__ void emit_packed_tile(const PackTarget &p, int64_t slot, const uint32_t (&k)[kEpt],
+                                                 const uint32_t (&sg)[kEpt], bool ovf, PackScratch &ps) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t kmax = 0;
+#pragma unroll
+    for (int j = 0; j < kEpt; ++j) kmax = max(kmax, k[j]);
+    if (ovf) atomicOr(&p.hdr->status, 1u);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (lane == 0) ps.u32[warp] = kmax;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) kmax = max(kmax, ps.u32[w]);
+    int W = 2;
+    while (W < 32 && kmax >= (1u << (W - 1))) W <<= 1;
+    unsigned long long off16;
+    if (W <= p.W0) {
+        off16 = (unsigned long long)slot * (32ull * p.W0);
+        if (threadIdx.x == 0) p.dir[slot] = (off16 << 8) | (unsigned long long)W;
+    } else {
+        if (threadIdx.x == 0) {
+            const unsigned long long units = 32ull * W;                  // 512*W bytes / 16
+            unsigned long long off = p.arena_base16 + atomicAdd(&p.hdr->arena_top, units);
+            if ((long long)((off + units) * 16ull) > p.codes_bytes) { atomicOr(&p.hdr->status, 2u); off = ~0ull; }
+            ps.off16 = off;
+            p.dir[slot] = (off == ~0ull) ? 0ull : ((off << 8) | (unsigned long long)W);
+        }
+        __syncthreads();
+        off16 = ps.off16;
+    }
+    if (off16 != ~0ull) {
+        uint32_t *tw = p.codes + off16 * 4ull;
+        switch (W) {
+            case 2: pack_store<2>(k, sg, tw); break;
+            case 4: pack_store<4>(k, sg, tw); break;
+            case 8: pack_store<8>(k, sg, tw); break;
+            case 16: pack_store<16>(k, sg, tw); break;
+            default: pack_store<32>(k, sg, tw); break;
+        }
+    }
+    __syncthreads();        // ps is reused by the caller's next tile
+}
+#endif  // __CUDACC__
+
 }  // namespace dme

@@ -121,11 +121,13 @@ DME_API int dme_mean_accumulate(const float *Q, int64_t n, int64_t d, int64_t ld
 /* ---- rotations ---- */
 /* In-place normalised natural-order Walsh-Hadamard transform of n rows of dpad (power of two) floats. */
 DME_API int dme_hadamard(float *V, int64_t n, int64_t dpad, int64_t ld, dme_stream_t stream);
-/* out[c][0..dpad) = H(diag * pad(x[c])).  diag: Philox(seed, coordinate) sign, or diag_inject (dpad floats, +-1). */
+/* out[c][0..dpad) = H(diag_c * pad(x[c])).  diag_c: Philox(seed + c * seed_stride, coordinate) signs (seed_stride 0 =
+ * one diagonal shared by all rows, as when one rotation_seed is used; 1 = a fresh rotation per client, as the
+ * reference's per-call EDEN seed AS:800), or diag_inject (dpad floats, +-1, shared). */
 DME_API int dme_rht(const float *X, int64_t n, int64_t d, int64_t ld, float *out, int64_t dpad, int64_t ld_out,
-            uint64_t seed, const float *diag_inject, dme_stream_t stream);
-DME_API int dme_irht(float *V, int64_t n, int64_t dpad, int64_t ld, uint64_t seed, const float *diag_inject,
-             dme_stream_t stream);
+            uint64_t seed, uint64_t seed_stride, const float *diag_inject, dme_stream_t stream);
+DME_API int dme_irht(float *V, int64_t n, int64_t dpad, int64_t ld, uint64_t seed, uint64_t seed_stride,
+             const float *diag_inject, dme_stream_t stream);
 DME_API int dme_rademacher(float *diag, int64_t dpad, uint64_t seed, dme_stream_t stream);
 /* The reference's `fast_walsh_hadamard_transform` as it executes: log2(len) stages on adjacent pairs. */
 DME_API int dme_pair_transform(float *V, int64_t n, int64_t len, int64_t ld, dme_stream_t stream);
@@ -137,10 +139,10 @@ DME_API int dme_drive(const float *X, int64_t n, int64_t d, int64_t ld, float *o
               const float *dsign_inject, int compat, dme_stream_t stream);
 /* rot: n x dpad scratch/out (rotated vectors); bins: uint8 n x dpad; scale: n floats. nbits in {1,2}. */
 DME_API int dme_eden_encode(const float *X, int64_t n, int64_t d, int64_t ld, int64_t dpad, int nbits, uint64_t seed,
-                    const float *diag_inject, const float *norm_inject, float *rot, uint8_t *bins, float *scale,
+                    uint64_t seed_stride, const float *diag_inject, const float *norm_inject, float *rot, uint8_t *bins, float *scale,
                     dme_stream_t stream);
 DME_API int dme_eden_decode(const uint8_t *bins, const float *scale, int64_t n, int64_t d, int64_t dpad, int nbits,
-                    uint64_t seed, const float *diag_inject, float *work, float *out, int64_t ld_out,
+                    uint64_t seed, uint64_t seed_stride, const float *diag_inject, float *work, float *out, int64_t ld_out,
                     dme_stream_t stream);
 /* Xq: int32 n x dpad table rows; h: int32 n x dpad shared randomness; recv_table: (2^nbits) x h_len floats;
  * exact_mask (uint8, nullable) / exact_vals (per row: exact_off[c] .. exact_off[c+1]). */

@@ -147,10 +147,10 @@ def test_eden_golden(dme, golden_dir):
 def test_eden_batched_quality(dme):
     rng = np.random.default_rng(4)
     X = rng.standard_normal((8, 50000)).astype(np.float32)
-    diag = dme.rademacher(1 << 16, seed=11).cpu().numpy()
     for nb in (1, 2):
         Y = dme.eden(X, nb, seed=11).cpu().numpy()
         for c in range(X.shape[0]):
+            diag = dme.rademacher(1 << 16, seed=11 + c).cpu().numpy()           # row c is rotated with seed + c (AS:800)
             o = orc.eden(X[c], diag, nb)                                         # same Philox diagonal, oracle arithmetic
             assert np.max(np.abs(Y[c] - o)) <= 4e-6 * np.max(np.abs(o)), (nb, c)
         err = np.sum((Y - X) ** 2, axis=1) / np.sum(X ** 2, axis=1)

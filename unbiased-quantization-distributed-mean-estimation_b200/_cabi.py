@@ -28,13 +28,13 @@ SIGNATURES = {
     "dme_quantize_mean": (ci, [vp, i64, i64, i64, i64, ci, vp, u64, u64, i64, vp, ci, vp, i64, vp, vp, vp, i64, vp]),
     "dme_mean_accumulate": (ci, [vp, i64, i64, i64, i64, vp, ci, vp]),
     "dme_hadamard": (ci, [vp, i64, i64, i64, vp]),
-    "dme_rht": (ci, [vp, i64, i64, i64, vp, i64, i64, u64, vp, vp]),
-    "dme_irht": (ci, [vp, i64, i64, i64, u64, vp, vp]),
+    "dme_rht": (ci, [vp, i64, i64, i64, vp, i64, i64, u64, u64, vp, vp]),
+    "dme_irht": (ci, [vp, i64, i64, i64, u64, u64, vp, vp]),
     "dme_rademacher": (ci, [vp, i64, u64, vp]),
     "dme_pair_transform": (ci, [vp, i64, i64, i64, vp]),
     "dme_drive": (ci, [vp, i64, i64, i64, vp, i64, u64, vp, ci, vp]),
-    "dme_eden_encode": (ci, [vp, i64, i64, i64, i64, ci, u64, vp, vp, vp, vp, vp, vp]),
-    "dme_eden_decode": (ci, [vp, vp, i64, i64, i64, ci, u64, vp, vp, vp, i64, vp]),
+    "dme_eden_encode": (ci, [vp, i64, i64, i64, i64, ci, u64, u64, vp, vp, vp, vp, vp, vp]),
+    "dme_eden_decode": (ci, [vp, vp, i64, i64, i64, ci, u64, u64, vp, vp, vp, i64, vp]),
     "dme_quicfl_decode": (ci, [vp, vp, i64, i64, i64, ci, vp, ci, vp, vp, vp, vp, u64, vp, vp, vp, i64, vp]),
     "dme_scalar_quantize": (ci, [vp, i64, i64, i64, cf, u64, u64, vp, vp, i64, vp]),
 }

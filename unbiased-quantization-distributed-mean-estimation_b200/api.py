@@ -350,24 +350,24 @@ def rademacher(dpad: int, seed: int):
     return out
 
 
-def rht(x, seed=0, *, diag_inject=None):
+def rht(x, seed=0, *, diag_inject=None, per_row_seed=False):
     """HadamardSender.randomized_hadamard_transform (AS:127-144): pad to a power of two, H(D x)/sqrt(dpad)."""
     X, n, d, was_1d = _rows(x)
     dpad = _pow2_ceil(d)
     out = torch.empty((n, dpad), dtype=torch.float32, device=X.device)
     dg = _diag(diag_inject, dpad, X.device)
-    _check(_cabi.lib().dme_rht(_ptr(X), n, d, _ld(X), _ptr(out), dpad, dpad, seed, _ptr(dg), C.c_void_p(_stream())))
+    _check(_cabi.lib().dme_rht(_ptr(X), n, d, _ld(X), _ptr(out), dpad, dpad, seed, int(bool(per_row_seed)), _ptr(dg), C.c_void_p(_stream())))
     return out[0] if was_1d else out
 
 
-def irht(v, seed=0, *, diag_inject=None):
+def irht(v, seed=0, *, diag_inject=None, per_row_seed=False):
     """HadamardReceiver.randomized_inverse_hadamard_transform (AS:151-156); returns a new tensor."""
     V, n, d, was_1d = _rows(v)
     if d & (d - 1):
         raise Exception("input numel must be a power of 2")
     V = V.clone().contiguous()
     dg = _diag(diag_inject, d, V.device)
-    _check(_cabi.lib().dme_irht(_ptr(V), n, d, _ld(V), seed, _ptr(dg), C.c_void_p(_stream())))
+    _check(_cabi.lib().dme_irht(_ptr(V), n, d, _ld(V), seed, int(bool(per_row_seed)), _ptr(dg), C.c_void_p(_stream())))
     return V[0] if was_1d else V
 
 
@@ -407,7 +407,9 @@ def drive(x, *, seed=0, dsign_inject=None, compat="reference"):
 
 
 def eden_encode(x, nbits=1, *, seed=0, diag_inject=None, norm_inject=None):
-    """EdenSender.compress (AS:370-390, integer nbits in {1,2}) -> dict(bins uint8 [n,dpad], scale [n], rot [n,dpad])."""
+    """EdenSender.compress (AS:370-390, integer nbits in {1,2}) -> dict(bins uint8 [n,dpad], scale [n], rot [n,dpad]).
+    Row c is rotated with the diagonal of seed + c (the reference draws a fresh seed per call, AS:800) unless a
+    diagonal is injected."""
     if nbits not in (1, 2):
         raise KeyError(nbits)           # AS:301-320 defines centroids for 1 and 2 bits only (SURVEY F8)
     X, n, d, was_1d = _rows(x)
@@ -418,7 +420,7 @@ def eden_encode(x, nbits=1, *, seed=0, diag_inject=None, norm_inject=None):
     scale = torch.empty(n, dtype=torch.float32, device=dev)
     dg = _diag(diag_inject, dpad, dev)
     ni = _opt_vec(norm_inject, n, dev)
-    _check(_cabi.lib().dme_eden_encode(_ptr(X), n, d, _ld(X), dpad, nbits, seed, _ptr(dg), _ptr(ni), _ptr(rot), _ptr(bins), _ptr(scale),
+    _check(_cabi.lib().dme_eden_encode(_ptr(X), n, d, _ld(X), dpad, nbits, seed, 1, _ptr(dg), _ptr(ni), _ptr(rot), _ptr(bins), _ptr(scale),
                                        C.c_void_p(_stream())))
     return {"bins": bins, "scale": scale, "rot": rot, "d": d, "dpad": dpad, "nbits": nbits, "seed": seed, "was_1d": was_1d}
 
@@ -432,7 +434,7 @@ def eden_decode(enc, *, diag_inject=None):
     work = torch.empty((n, dpad), dtype=torch.float32, device=dev)
     out = torch.empty((n, (d + 3) // 4 * 4), dtype=torch.float32, device=dev)
     dg = _diag(diag_inject, dpad, dev)
-    _check(_cabi.lib().dme_eden_decode(_ptr(bins), _ptr(scale), n, d, dpad, enc["nbits"], enc["seed"], _ptr(dg), _ptr(work), _ptr(out),
+    _check(_cabi.lib().dme_eden_decode(_ptr(bins), _ptr(scale), n, d, dpad, enc["nbits"], enc["seed"], 1, _ptr(dg), _ptr(work), _ptr(out),
                                        out.stride(0), C.c_void_p(_stream())))
     out = out[:, :d]
     return out[0] if enc.get("was_1d") else out

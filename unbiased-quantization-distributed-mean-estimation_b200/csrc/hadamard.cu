@@ -37,14 +37,14 @@ struct FwhtIo {
     const float *src; int64_t src_d, src_ld;   // source rows (length src_d <= d, zero padded)
     float *dst; int64_t d, dst_ld;             // destination rows (length d = power of two)
     const float *diag;                         // injected +-1 diagonal (d entries) or null
-    uint64_t seed; int use_philox;             // Philox diagonal when diag == null and use_philox
+    uint64_t seed, seed_stride; int use_philox; // Philox diagonal of row r is keyed by seed + r * seed_stride
     int pre_diag, post_diag;                   // multiply by the diagonal before the first stage / after the scaling
     int finalize; float sq;                    // divide by sq = float(sqrt(d)) after the last stage
 };
 
-__device__ __forceinline__ float diag_at(const FwhtIo &io, int64_t col) {
+__device__ __forceinline__ float diag_at(const FwhtIo &io, int64_t col, int64_t row) {
     if (io.diag) return io.diag[col];
-    return philox_sign(io.seed, (uint64_t)col, kStreamDiag);
+    return philox_sign(io.seed + (uint64_t)row * io.seed_stride, (uint64_t)col, kStreamDiag);
 }
 
 constexpr int kPad = 4096 + 4096 / 32;   // +1 float every 32: transposes are conflict-free
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) fwht_contig_kernel(FwhtIo io, int64_t n, 
         }
         if (io.pre_diag && live) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], diag_at(io, col + j));
+            for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], diag_at(io, col + j, row));
         }
     } else {
 #pragma unroll
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) fwht_contig_kernel(FwhtIo io, int64_t n, 
             const int64_t g = g0 + j;
             const int64_t row = g / io.d, col = g - row * io.d;
             float x = (g < total && col < io.src_d) ? io.src[row * io.src_ld + col] : 0.0f;
-            if (io.pre_diag && g < total) x = __fmul_rn(x, diag_at(io, col));
+            if (io.pre_diag && g < total) x = __fmul_rn(x, diag_at(io, col, row));
             v[j] = x;
         }
     }
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) fwht_contig_kernel(FwhtIo io, int64_t n, 
         float y = v[j];
         if (io.finalize) {
             y = __fdiv_rn(y, io.sq);                                        // AS:113
-            if (io.post_diag) y = __fmul_rn(y, diag_at(io, col));           // AS:154
+            if (io.post_diag) y = __fmul_rn(y, diag_at(io, col, row));      // AS:154
         }
         io.dst[row * io.dst_ld + col] = y;
     }
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) fwht_strided_kernel(FwhtIo io, int64_t n,
             float y = v[r];
             if (io.finalize) {
                 y = __fdiv_rn(y, io.sq);
-                if (io.post_diag) y = __fmul_rn(y, diag_at(io, (hi << (s + p)) + ((int64_t)r << s) + col));
+                if (io.post_diag) y = __fmul_rn(y, diag_at(io, (hi << (s + p)) + ((int64_t)r << s) + col, row));
             }
             base[(int64_t)r << s] = y;
         }
@@ -185,14 +185,14 @@ static int ilog2(int64_t v) { int l = 0; while (((int64_t)1 << l) < v) ++l; retu
 
 // Full transform of n rows: src (length src_d, stride src_ld) -> dst (length d = 2^k, stride dst_ld).
 int fwht_rows(const float *src, int64_t src_d, int64_t src_ld, float *dst, int64_t d, int64_t dst_ld, int64_t n,
-              const float *diag, uint64_t seed, int pre_diag, int post_diag, cudaStream_t st) {
+              const float *diag, uint64_t seed, uint64_t seed_stride, int pre_diag, int post_diag, cudaStream_t st) {
     DME_REQUIRE(d >= 1 && (d & (d - 1)) == 0, "input numel must be a power of 2");
     DME_REQUIRE(src && dst && n >= 1 && src_d >= 1 && src_d <= d && src_ld >= src_d && dst_ld >= d, "bad row geometry");
     DME_REQUIRE(n * d < ((int64_t)1 << 40), "problem too large");
     const int logd = ilog2(d);
     FwhtIo io;
     io.src = src; io.src_d = src_d; io.src_ld = src_ld; io.dst = dst; io.d = d; io.dst_ld = dst_ld;
-    io.diag = diag; io.seed = seed; io.use_philox = diag == nullptr; io.pre_diag = pre_diag; io.post_diag = post_diag;
+    io.diag = diag; io.seed = seed; io.seed_stride = seed_stride; io.use_philox = diag == nullptr; io.pre_diag = pre_diag; io.post_diag = post_diag;
     io.sq = (float)std::sqrt((double)d);
     const int logL = logd < 12 ? logd : 12;
     io.finalize = (logd <= 12);
@@ -216,17 +216,18 @@ using namespace dme;
 
 extern "C" int dme_hadamard(float *V, int64_t n, int64_t dpad, int64_t ld, dme_stream_t stream) {
     DME_REQUIRE(V != nullptr, "V is null");
-    return fwht_rows(V, dpad, ld, V, dpad, ld, n, nullptr, 0, 0, 0, (cudaStream_t)stream);
+    return fwht_rows(V, dpad, ld, V, dpad, ld, n, nullptr, 0, 0, 0, 0, (cudaStream_t)stream);
 }
 extern "C" int dme_rht(const float *X, int64_t n, int64_t d, int64_t ld, float *out, int64_t dpad, int64_t ld_out, uint64_t seed,
-                       const float *diag_inject, dme_stream_t stream) {
+                       uint64_t seed_stride, const float *diag_inject, dme_stream_t stream) {
     DME_REQUIRE(X && out, "null pointer argument");
     DME_REQUIRE(dpad >= d, "dpad < d");
-    return fwht_rows(X, d, ld, out, dpad, ld_out, n, diag_inject, seed, 1, 0, (cudaStream_t)stream);
+    return fwht_rows(X, d, ld, out, dpad, ld_out, n, diag_inject, seed, seed_stride, 1, 0, (cudaStream_t)stream);
 }
-extern "C" int dme_irht(float *V, int64_t n, int64_t dpad, int64_t ld, uint64_t seed, const float *diag_inject, dme_stream_t stream) {
+extern "C" int dme_irht(float *V, int64_t n, int64_t dpad, int64_t ld, uint64_t seed, uint64_t seed_stride, const float *diag_inject,
+                        dme_stream_t stream) {
     DME_REQUIRE(V != nullptr, "V is null");
-    return fwht_rows(V, dpad, ld, V, dpad, ld, n, diag_inject, seed, 0, 1, (cudaStream_t)stream);
+    return fwht_rows(V, dpad, ld, V, dpad, ld, n, diag_inject, seed, seed_stride, 0, 1, (cudaStream_t)stream);
 }
 extern "C" int dme_rademacher(float *diag, int64_t dpad, uint64_t seed, dme_stream_t stream) {
     DME_REQUIRE(diag && dpad >= 1, "bad argument");

@@ -9,7 +9,7 @@
 namespace dme {
 
 int fwht_rows(const float *src, int64_t src_d, int64_t src_ld, float *dst, int64_t d, int64_t dst_ld, int64_t n,
-              const float *diag, uint64_t seed, int pre_diag, int post_diag, cudaStream_t st);   // hadamard.cu
+              const float *diag, uint64_t seed, uint64_t seed_stride, int pre_diag, int post_diag, cudaStream_t st);   // hadamard.cu
 
 __device__ __forceinline__ float sgn0(float v) { return (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f); }
 
@@ -249,12 +249,12 @@ extern "C" int dme_drive(const float *X, int64_t n, int64_t d, int64_t ld, float
 }
 
 extern "C" int dme_eden_encode(const float *X, int64_t n, int64_t d, int64_t ld, int64_t dpad, int nbits, uint64_t seed,
-                               const float *diag_inject, const float *norm_inject, float *rot, uint8_t *bins, float *scale,
+                               uint64_t seed_stride, const float *diag_inject, const float *norm_inject, float *rot, uint8_t *bins, float *scale,
                                dme_stream_t stream) {
     DME_REQUIRE(X && rot && bins && scale && n >= 1 && n <= 65535, "bad argument");
     DME_REQUIRE(nbits == 1 || nbits == 2, "EDEN centroids exist for 1 and 2 bits only (AS:301-320)");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = fwht_rows(X, d, ld, rot, dpad, dpad, n, diag_inject, seed, 1, 0, st);                   // AS:378-380
+    int rc = fwht_rows(X, d, ld, rot, dpad, dpad, n, diag_inject, seed, seed_stride, 1, 0, st);                   // AS:378-380
     if (rc) return rc;
     const int nb = slices(dpad);
     double *partial = nullptr;
@@ -277,14 +277,14 @@ extern "C" int dme_eden_encode(const float *X, int64_t n, int64_t d, int64_t ld,
 }
 
 extern "C" int dme_eden_decode(const uint8_t *bins, const float *scale, int64_t n, int64_t d, int64_t dpad, int nbits, uint64_t seed,
-                               const float *diag_inject, float *work, float *out, int64_t ld_out, dme_stream_t stream) {
+                               uint64_t seed_stride, const float *diag_inject, float *work, float *out, int64_t ld_out, dme_stream_t stream) {
     DME_REQUIRE(bins && scale && work && out && n >= 1 && d >= 1 && dpad >= d && ld_out >= d, "bad argument");
     DME_REQUIRE(nbits == 1 || nbits == 2, "EDEN centroids exist for 1 and 2 bits only (AS:301-320)");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t total = n * dpad;
     eden_lookup_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(bins, total, eden_tab(nbits), work);
     DME_LAUNCH_CHECK("eden_lookup_kernel");
-    int rc = fwht_rows(work, dpad, dpad, work, dpad, dpad, n, diag_inject, seed, 0, 1, st);          // AS:425
+    int rc = fwht_rows(work, dpad, dpad, work, dpad, dpad, n, diag_inject, seed, seed_stride, 0, 1, st);   // AS:425
     if (rc) return rc;
     scale_rows_kernel<<<(unsigned)((n * d + 255) / 256), 256, 0, st>>>(work, dpad, scale, n, d, out, ld_out);
     DME_LAUNCH_CHECK("scale_rows_kernel");
@@ -301,7 +301,7 @@ extern "C" int dme_quicfl_decode(const int32_t *Xq, const int32_t *h, int64_t n,
     cudaStream_t st = (cudaStream_t)stream;
     quicfl_gather_kernel<<<(unsigned)n, 256, 0, st>>>(Xq, h, dpad, h_len, recv_table, table_len, exact_mask, exact_vals, exact_off, scale, work);
     DME_LAUNCH_CHECK("quicfl_gather_kernel");
-    int rc = fwht_rows(work, dpad, dpad, work, dpad, dpad, n, diag_inject, rotation_seed, 0, 1, st);  // AS:534
+    int rc = fwht_rows(work, dpad, dpad, work, dpad, dpad, n, diag_inject, rotation_seed, 0, 0, 1, st);  // AS:534
     if (rc) return rc;
     scale_rows_kernel<<<(unsigned)((n * d + 255) / 256), 256, 0, st>>>(work, dpad, nullptr, n, d, out, ld_out);
     DME_LAUNCH_CHECK("scale_rows_kernel");

@@ -32,7 +32,7 @@ for n, d in shapes:
         ws = dme.Workspace.get(X.device).buf
         off = (-ws.data_ptr()) % 256
         hdr = ws[off: off + 256].cpu().numpy().view("uint64")
-        names = ["row_ready wait", "tma wait", "publish agg", "lookback", "publish incl", "A item total", "B item total"]
-        tot = 2 * n * ((d + 4095) // 4096)
-        print("   per-item ns (thread 0):", {nm: round(float(hdr[3 + q]) / (tot / 2), 1) for q, nm in enumerate(names)})
+        names = ["tma wait", "pass A", "stage 1", "stage 2", "poll fallback ns", "poll fallbacks", "cta lifetime"]
+        pairs = n * ((d + 4095) // 4096)
+        print("   per tile pair, ns of thread 0 (summed over CTAs / pairs):", {nm: round(float(hdr[3 + q]) / pairs, 2) for q, nm in enumerate(names)})
     del X

@@ -1,0 +1,585 @@
+// stream.cu -- the persistent quantize kernel of the unbiased type quantizer (AS:609-641):
+// per-client L1 norm, scale to m, floor + systematic-sampling allocation of the fractional mass, sign/magnitude
+// packing (or the dequantised output of the drop-in API), for all clients of one GPU in ONE launch.
+//
+// Schedule.  Work items are enumerated in one global order and dealt round-robin to G co-resident CTAs
+// (cooperative launch, G odd).  Even items are pass-A tiles (stream a 16 KB tile of a row from HBM with an L2
+// evict_last hint, add |x| in fp64), odd items are pass-B tiles of the row `lag` tiles behind (re-read the tile
+// from L2 with evict_first, run AS:625-637, emit).  The A item at position (p+1)T + goff also reduces row p's tile
+// sums and publishes the row constants, so that row p's pass B, which starts `lag - T - goff` tiles later, never
+// waits for them.  Every wait is on an item with a smaller index, every CTA is resident: no deadlock.
+//
+// Inside a CTA.  Tiles arrive through a 4-deep ring of 1-D bulk async copies (TMA, SASS UBLKCP) issued two items
+// ahead.  A pass-B tile is split in two stages: stage 1 (division, floor, fractional parts, block scan, publish the
+// tile aggregate) and stage 2 (decoupled look-back, prefix -> floor(c - X), type vector, emit).  Stage 2 of a tile
+// runs after stage 1 of the CTA's NEXT pass-B tile, so the look-back finds its predecessors already published; the
+// parked state (floor, fraction, signs: 33 registers per thread) lives in registers.
+//
+// Cross-CTA messages are 16-byte records {value, flag} written and read with single 128-bit accesses, so no
+// fences are needed; tile aggregates travel as int64 fixed point, which makes the look-back result independent of
+// timing (integer addition is associative).
+#include <cooperative_groups.h>
+#include <cstdlib>
+
+#include "type_quantize.cuh"
+
+namespace dme {
+
+constexpr int kRing = 4;        // TMA ring depth
+constexpr int kAhead = 2;       // items prefetched ahead
+
+struct __align__(16) Rec { unsigned long long v; uint32_t flag; uint32_t pad; };
+typedef Rec TileRec;      // per tile: flag 1 = v is the tile aggregate, 2 = v is the inclusive prefix (fixed point)
+
+__device__ __forceinline__ void rec_store(Rec *p, unsigned long long v, uint32_t flag) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((uint32_t)v), "r"((uint32_t)(v >> 32)), "r"(flag), "r"(0u)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t rec_load(const Rec *p, unsigned long long &v) {
+    uint32_t a, b, f, z;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(f), "=r"(z) : "l"(p) : "memory");
+    v = ((unsigned long long)b << 32) | a;
+    return f;
+}
+
+// ---- async-copy / mbarrier primitives (TMA 1-D bulk copy)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TIC(a, k) do { if (((a).dbg & 32) && threadIdx.x == 0) sc.tacc[k] -= gtime(); } while (0)
+#define TOC(a, k) do { if (((a).dbg & 32) && threadIdx.x == 0) sc.tacc[k] += gtime(); } while (0)
+
+struct StreamArgs {
+    const float *X; int64_t d, ld, T, n, m;
+    RowConst *consts; TileRec *desc; WsHeader *hdr; Rec *partial; uint32_t *row_ready;
+    const float *x_inject; const float *l1_inject; uint64_t seed, client0; float *l1_out;
+    int64_t lag, goff, total_items, G;
+    int32_t *k_out; uint8_t *sgn_out; float *deq_out; int64_t ld_out;     // array outputs
+    PackTarget pack; int packed;                                        // packed output
+    int dbg;                                                            // development: bit 5 = phase timers
+};
+
+struct Item { int valid; int is_b; int64_t pos, c, t; int copied; const float *src; int64_t fin_row; };
+__device__ __forceinline__ Item decode_item(const StreamArgs &a, int64_t i) {
+    Item it; it.valid = 0; it.is_b = (int)(i & 1); it.pos = 0; it.c = 0; it.t = 0; it.copied = 0; it.src = nullptr; it.fin_row = -1;
+    if (i >= a.total_items) return it;
+    const int64_t s = it.is_b ? ((i >> 1) - a.lag) : (i >> 1);
+    it.pos = s;
+    if (!it.is_b && s >= a.T + a.goff) {                       // finaliser duty of this A position
+        const int64_t u = s - a.goff;
+        const int64_t p = u / a.T;
+        if (u - p * a.T == 0 && p - 1 < a.n) it.fin_row = p - 1;
+    }
+    if (s < 0 || s >= a.n * a.T) return it;
+    it.valid = 1;
+    it.c = s / a.T; it.t = s - it.c * a.T;
+    const int64_t rem = a.d - it.t * kTile;
+    it.copied = rem >= kTile ? kTile : (int)(rem & ~(int64_t)3);
+    it.src = a.X + it.c * a.ld + it.t * kTile;
+    return it;
+}
+
+struct Scratch {
+    double wtot[kWarps];
+    double red[kWarps];
+    double P[2];
+    long long Pq[2];
+    RowConst rc[2];
+    long long rc_row[2];
+    PackScratch pack;
+    Rec lb[kThreads];          // prefetched look-back window
+    long long lb_sum[kWarps];
+    int lb_f[kWarps];
+    unsigned long long tacc[8];  // phase timers (dbg)
+};
+
+// value of tile-local coordinate e from the staged tile; beyond `copied` floats fall back to global / zero
+__device__ __forceinline__ float staged(const float *buf, int e, int copied, const float *row, int64_t tile0, int64_t d) {
+    if (e < copied) return buf[e];
+    const int64_t i = tile0 + e;
+    return i < d ? row[i] : 0.0f;
+}
+
+__device__ __forceinline__ void make_row_const(const StreamArgs &a, int64_t c, double l1sum) {
+    RowConst rc;
+    rc.L1f = a.l1_inject ? a.l1_inject[c] : (float)l1sum;           // AS:624
+    rc.D = __fadd_rn(rc.L1f, 1e-12f);                               // AS:625
+    rc.mf = (float)a.m;
+    rc.X = a.x_inject ? a.x_inject[c] : philox_client_uniform(a.seed, a.client0 + (uint64_t)c);   // AS:634
+    rc.rcpD = __frcp_rn(rc.D);
+    uint32_t fl = 0;
+    // The fast chain (Markstein division, magic-number floor) is proven for these operand ranges only;
+    // anything else takes the IEEE-div / floorf instantiation.  See DESIGN.md "Exactness of the fast chain".
+    if (!(rc.D >= 9.5367431640625e-07f && rc.D <= 1.2676506e30f)) fl |= kRowExact;            // 2^-20 .. 2^100
+    if ((__float_as_uint(rc.D) & 0x7fffffu) == 0x7fffffu) fl |= kRowExact;                      // 1/D rounding exception
+    if (!(rc.X == 0.0f || (rc.X >= 5.9604644775390625e-08f && rc.X < 1.0f))) fl |= kRowExact;  // X on torch.rand's grid
+    if (!(rc.mf <= 4194304.0f) || a.l1_inject) fl |= kRowGuardFloor;                            // m*p may reach 2^23
+    rc.flags = fl;
+    int lg = 0;
+    while (((int64_t)1 << lg) < a.d) ++lg;
+    rc.qshift = min(50, 62 - lg);
+    rc.pad0 = 0;
+    rc.q_up = scalbn(1.0, rc.qshift);
+    rc.q_dn = scalbn(1.0, -rc.qshift);
+    rc.pad1[0] = rc.pad1[1] = 0.0;
+    a.consts[c] = rc;
+    if (a.l1_out) a.l1_out[c] = rc.L1f;
+}
+
+// ---- pass A of one tile (+ the finaliser duty attached to this stream position)
+__device__ __forceinline__ void pass_a(const StreamArgs &a, const Item &it, const float *buf, Scratch &sc) {
+    if (it.valid) {
+        const float *row = a.X + it.c * a.ld;
+        const int64_t tile0 = it.t * kTile;
+        double s = 0.0;
+        if (it.copied == kTile) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 v = *reinterpret_cast<const float4 *>(buf + q * 1024 + 4 * threadIdx.x);
+                s += (double)fabsf(v.x); s += (double)fabsf(v.y); s += (double)fabsf(v.z); s += (double)fabsf(v.w);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) s += (double)fabsf(staged(buf, q * 1024 + 4 * threadIdx.x + e, it.copied, row, tile0, a.d));
+        }
+        s = block_sum_f64(s, sc.red);                     // fixed association; ends with every thread past a barrier
+        if (threadIdx.x == 0) rec_store(&a.partial[it.c * a.T + it.t], (unsigned long long)__double_as_longlong(s), 1u);
+    }
+    if (it.fin_row >= 0) {
+        // reduce row fin_row's tile sums in a fixed order (thread-strided, then the block tree) and publish the row
+        const Rec *pp = a.partial + it.fin_row * a.T;
+        double acc = 0.0;
+        for (int64_t i = threadIdx.x; i < a.T; i += kThreads) {
+            unsigned long long v;
+            while (rec_load(pp + i, v) == 0u) __nanosleep(64);
+            acc += __longlong_as_double((long long)v);
+        }
+        acc = block_sum_f64(acc, sc.red);
+        if (threadIdx.x == 0) {
+            make_row_const(a, it.fin_row, acc);
+            __threadfence();
+            st_release_u32(&a.row_ready[it.fin_row], 1u);
+        }
+    }
+    __syncthreads();
+}
+
+// AS:625-631 for one coordinate.  EXACT: IEEE division + floorf.  Fast: x/D by Markstein's correction of x*rcp
+// (correctly rounded for D in [2^-20, 2^100], 1/D correctly rounded, quotient normal) and floor by adding 2^23
+// toward zero (exact for 0 <= mp < 2^23).
+template <bool EXACT>
+__device__ __forceinline__ void chain(float x, const RowConst &rc, float &flf, float &fr) {
+    float mp;
+    if (EXACT) {
+        const float v = __fdiv_rn(x, rc.D);
+        mp = __fmul_rn(rc.mf, fabsf(v));
+        flf = floorf(mp);
+    } else {
+        const float ax = fabsf(x);
+        const float q0 = __fmul_rn(ax, rc.rcpD);
+        const float rem = __fmaf_rn(-q0, rc.D, ax);
+        const float p = __fmaf_rn(rem, rc.rcpD, q0);
+        mp = __fmul_rn(rc.mf, p);
+        flf = __fsub_rn(__fadd_rz(mp, 8388608.0f), 8388608.0f);
+    }
+    fr = __fsub_rn(mp, flf);
+}
+
+// State of a pass-B tile between its two stages (registers).
+struct BState {
+    float fl[kEpt];
+    float fr[kEpt];
+    uint32_t sign;          // bit j = IEEE sign of coordinate j
+    double base;            // in-tile exclusive prefix of this thread's first coordinate
+    double end;             // in-tile inclusive prefix of this thread's last coordinate (scan value)
+    long long Aq;           // tile aggregate, fixed point
+    int64_t c, t;
+    int live;
+};
+
+// ---- stage 1: everything that does not need the prefix of earlier tiles
+__device__ __forceinline__ void stage1(const StreamArgs &a, const Item &it, const float *buf, Scratch &sc, int slot, BState &st) {
+    st.live = it.valid;
+    if (!it.valid) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    st.c = it.c; st.t = it.t;
+    // row constants: cached in shared memory; a new row waits for the finaliser (an earlier A item)
+    if (sc.rc_row[slot] != it.c) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            while (ld_acquire_u32(&a.row_ready[it.c]) == 0u) __nanosleep(64);
+            const uint4 *src = reinterpret_cast<const uint4 *>(&a.consts[it.c]);
+            uint4 *dst = reinterpret_cast<uint4 *>(&sc.rc[slot]);
+#pragma unroll
+            for (int q = 0; q < (int)(sizeof(RowConst) / 16); ++q) dst[q] = __ldcg(src + q);
+            sc.rc_row[slot] = it.c;
+        }
+        __syncthreads();
+    }
+    const RowConst &rc = sc.rc[slot];
+    const float *row = a.X + it.c * a.ld;
+    const int64_t tile0 = it.t * kTile;
+    float x[kEpt];
+    if (it.copied == kTile) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4 *>(buf + kEpt * threadIdx.x + 4 * q);
+            x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) x[j] = staged(buf, kEpt * threadIdx.x + j, it.copied, row, tile0, a.d);
+    }
+    const bool exact = rc.flags & kRowExact;
+    bool big = false;
+    if (!exact && (rc.flags & kRowGuardFloor)) {
+        // m*p can reach 2^23 in this row: threads that actually see such a value use floorf
+        float mx = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) mx = fmaxf(mx, fabsf(x[j]));
+        big = !(__fmul_rn(rc.mf, __fmul_rn(mx, rc.rcpD)) < 4194304.0f);
+    }
+    double S = 0.0;
+    uint32_t sg = 0;
+    if (exact || big) {
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) {
+            chain<true>(x[j], rc, st.fl[j], st.fr[j]);
+            S += (double)st.fr[j];
+            sg |= (__float_as_uint(x[j]) >> 31) << j;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) {
+            chain<false>(x[j], rc, st.fl[j], st.fr[j]);
+            S += (double)st.fr[j];
+            sg |= (__float_as_uint(x[j]) >> 31) << j;
+        }
+    }
+    st.sign = sg;
+    // block scan of the thread sums (Kogge-Stone inside a warp, warps in order): fixed association
+    double incl = S;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 0.0;
+    if (lane == 31) sc.wtot[warp] = incl;
+    __syncthreads();
+    double wbase = 0.0, A = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        if (w == warp) wbase = A;
+        A += sc.wtot[w];
+    }
+    st.base = wbase + excl;
+    st.end = wbase + incl;
+    st.Aq = __double2ll_rn(A * rc.q_up);                 // fixed point, 2^-qshift resolution
+    if (threadIdx.x == 0) rec_store(a.desc + it.c * a.T + it.t, (unsigned long long)st.Aq, it.t == 0 ? 2u : 1u);
+    __syncthreads();                                     // wtot and the tile buffer may be reused
+}
+
+// Decoupled look-back over the 16-byte records (warp 0): polling fallback of the prefetched look-back below.
+__device__ __forceinline__ long long lookback_poll(const TileRec *rowdesc, int64_t t, int lane) {
+    long long P = 0;
+    int64_t top = t - 1;
+    while (top >= 0) {
+        const int64_t idx = top - lane;
+        while (true) {
+            unsigned long long v = 0;
+            const uint32_t fl = idx >= 0 ? rec_load(&rowdesc[idx], v) : 2u;      // virtual tiles < 0: inclusive prefix 0
+            const unsigned incl = __ballot_sync(0xffffffffu, fl == 2u);
+            const unsigned none = __ballot_sync(0xffffffffu, fl == 0u);
+            const int f = incl ? (__ffs(incl) - 1) : 32;
+            const unsigned need = (f >= 31) ? 0xffffffffu : ((1u << (f + 1)) - 1u);
+            if ((none & need) == 0u) {
+                long long x = (lane <= f) ? (long long)v : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                P += x;
+                if (f < 32) return P;
+                break;
+            }
+            __nanosleep(32);
+        }
+        top -= 32;
+    }
+    return P;
+}
+
+// Prefetch the records of the 256 tiles before tile t of the row into shared memory (cp.async, 16 bytes per
+// thread, L2 only), so that the look-back of stage 2 costs no round trip.
+__device__ __forceinline__ void lookback_prefetch(const TileRec *rowdesc, int64_t t, Rec *lb) {
+    const int64_t idx = t - 1 - (int64_t)threadIdx.x;
+    if (idx >= 0)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(lb + threadIdx.x)), "l"(rowdesc + idx) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// ---- stage 2: look-back, prefix -> floor(c - X) (AS:635-637), type vector, emit
+template <int EMIT>
+__device__ __forceinline__ void stage2(const StreamArgs &a, Scratch &sc, int slot, BState &st) {
+    if (!st.live) return;
+    st.live = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const RowConst &rc = sc.rc[slot];
+    const TileRec *rowdesc = a.desc + st.c * a.T;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    {
+        // thread i looks at tile t-1-i; tiles before the row start count as an inclusive prefix of 0
+        const int64_t idx = st.t - 1 - (int64_t)threadIdx.x;
+        const Rec r = sc.lb[threadIdx.x];
+        const uint32_t fl = idx >= 0 ? r.flag : 2u;
+        const long long val = idx >= 0 ? (long long)r.v : 0;
+        const unsigned incl = __ballot_sync(0xffffffffu, fl == 2u);
+        const unsigned none = __ballot_sync(0xffffffffu, fl == 0u);
+        const int f = incl ? (__ffs(incl) - 1) : 32;
+        const unsigned need = (f >= 31) ? 0xffffffffu : ((1u << (f + 1)) - 1u);
+        long long x = (lane <= f) ? val : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) { sc.lb_sum[warp] = x; sc.lb_f[warp] = (none & need) ? -1 : f; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        long long P = 0;
+        bool done = st.t == 0;
+        if (!done) {
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                const int f = sc.lb_f[w];
+                if (f < 0) break;                       // a nearer tile has not published yet: poll instead
+                P += sc.lb_sum[w];
+                if (f < 32) { done = true; break; }
+            }
+            if (!done) { if ((a.dbg & 32) && lane == 0) sc.tacc[5] += 1; TIC(a, 4); P = lookback_poll(rowdesc, st.t, lane); TOC(a, 4); }
+            if (lane == 0) rec_store(a.desc + st.c * a.T + st.t, (unsigned long long)(P + st.Aq), 2u);
+        }
+        if (lane == 0) { sc.Pq[slot] = P; sc.P[slot] = __ll2double_rn(P) * rc.q_dn; }
+    }
+    __syncthreads();
+    const double Pd = sc.P[slot];
+    // The prefix at the LAST coordinate of a warp is defined from the scan values (and at the last coordinate of the
+    // tile from the fixed-point inclusive prefix), so the next warp / tile derives the same floor(c - X) for its
+    // predecessor from its own exclusive prefix: no hand-off is needed.
+    double C = Pd + st.base;
+    int aprev = __float2int_rd(__fsub_rn(__double2float_rn(C), rc.X));       // floor(c_{first-1} - X); c_0 = 0 (AS:635)
+    int av[kEpt];
+#pragma unroll
+    for (int j = 0; j < kEpt; ++j) {
+        C += (double)st.fr[j];
+        if (j == kEpt - 1 && lane == 31) C = Pd + st.end;
+        if (j == kEpt - 1 && threadIdx.x == kThreads - 1) C = __ll2double_rn(sc.Pq[slot] + st.Aq) * rc.q_dn;
+        av[j] = __float2int_rd(__fsub_rn(__double2float_rn(C), rc.X));       // AS:636
+    }
+    // predecessor's floor: from the previous lane; lane 0 uses its own exclusive prefix (computed above), which is
+    // bit-identical to the previous warp's last prefix only if that one is defined the same way:
+    const int from_prev = __shfl_up_sync(0xffffffffu, av[kEpt - 1], 1);
+    if (lane != 0) aprev = from_prev;
+    float kf[kEpt];
+#pragma unroll
+    for (int j = 0; j < kEpt; ++j) {
+        const int r = (av[j] - aprev == 1) ? 1 : 0;                           // AS:636-637
+        aprev = av[j];
+        kf[j] = __fadd_rn(st.fl[j], (float)r);
+    }
+    const int64_t i0 = st.t * kTile + (int64_t)threadIdx.x * kEpt;
+    if (EMIT == 0) {
+        bool ovf = false;
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) {
+            const int64_t i = i0 + j;
+            if (i >= a.d) break;
+            const uint32_t sbit = (st.sign >> j) & 1u;
+            if (a.deq_out) {
+                // sign(v) of AS:640: v = x / D is zero exactly when m * |v| is (floor and fraction both zero, m > 0)
+                const float sgf = (st.fl[j] == 0.0f && st.fr[j] == 0.0f) ? 0.0f : (sbit ? -1.0f : 1.0f);
+                a.deq_out[st.c * a.ld_out + i] = __fdiv_rn(__fmul_rn(__fmul_rn(rc.L1f, sgf), kf[j]), rc.mf);
+            }
+            if (a.k_out) {
+                if (kf[j] >= 2147483648.0f) { ovf = true; a.k_out[st.c * a.ld_out + i] = 0x7fffffff; }
+                else a.k_out[st.c * a.ld_out + i] = (int32_t)kf[j];
+            }
+            if (a.sgn_out) a.sgn_out[st.c * a.ld_out + i] = (uint8_t)sbit;
+        }
+        if (ovf) atomicOr(&a.hdr->status, 1u);
+        __syncthreads();
+    } else {
+        uint32_t k[kEpt], sg[kEpt];
+        bool ovf = false;
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) {
+            if (kf[j] >= 2147483648.0f) { ovf = true; k[j] = 0x7fffffffu; } else k[j] = (uint32_t)kf[j];
+            sg[j] = (st.sign >> j) & 1u;
+        }
+        emit_packed_tile(a.pack, st.c * a.T + st.t, k, sg, ovf, sc.pack);
+    }
+}
+
+template <int EMIT>
+__global__ void __launch_bounds__(kThreads, 2)
+quantize_stream_kernel(StreamArgs a) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    __shared__ uint64_t mbar[kRing];
+    __shared__ Scratch sc;
+
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < kRing; ++b) mbar_init(&mbar[b], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sc.rc_row[0] = sc.rc_row[1] = -1;
+        for (int q = 0; q < 8; ++q) sc.tacc[q] = 0;
+        if (a.dbg & 32) sc.tacc[6] -= gtime();
+    }
+    __syncthreads();
+    const uint64_t pol_a = policy_evict_last(), pol_b = policy_evict_first();
+    const int64_t g = blockIdx.x;
+    int64_t jn = 0;                      // local index of the next item to fetch
+    uint32_t parity_bits = 0;            // phase parity of each ring slot
+
+    auto issue = [&](int64_t j) {        // thread 0: start the bulk copy of local item j (if it has data)
+        const Item it = decode_item(a, g + j * a.G);
+        if (it.valid && it.copied > 0) {
+            const int b = (int)(j % kRing);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&mbar[b], (uint32_t)it.copied * 4u);
+            bulk_g2s(dyn_smem + (size_t)b * kTile * 4, it.src, (uint32_t)it.copied * 4u, &mbar[b], it.is_b ? pol_b : pol_a);
+        }
+    };
+    if (threadIdx.x == 0) {
+        for (int64_t j = 0; j < kAhead; ++j) issue(j);
+    }
+    // fetch(): next item of this CTA, its staged tile ready in shared memory
+    auto fetch = [&](Item &it, const float *&buf) -> bool {
+        const int64_t j = jn++;
+        const int64_t i = g + j * a.G;
+        if (i >= a.total_items) return false;
+        if (threadIdx.x == 0) issue(j + kAhead);
+        it = decode_item(a, i);
+        const int b = (int)(j % kRing);
+        buf = reinterpret_cast<const float *>(dyn_smem + (size_t)b * kTile * 4);
+        if (it.valid && it.copied > 0) {
+            TIC(a, 0);
+            mbar_wait(&mbar[b], (parity_bits >> b) & 1u);
+            parity_bits ^= 1u << b;
+            TOC(a, 0);
+        }
+        return true;
+    };
+
+    BState s0, s1;
+    s0.live = 0; s1.live = 0;
+    Item it; const float *buf = nullptr;
+    while (true) {
+        // ---- pass-B tile into state 0 (an A item may come first)
+        if (!fetch(it, buf)) break;
+        if (!it.is_b) { TIC(a, 1); pass_a(a, it, buf, sc); TOC(a, 1); if (!fetch(it, buf)) break; }
+        if (s1.live) lookback_prefetch(a.desc + s1.c * a.T, s1.t, sc.lb);
+        TIC(a, 2); stage1(a, it, buf, sc, 0, s0); TOC(a, 2);
+        TIC(a, 3); stage2<EMIT>(a, sc, 1, s1); TOC(a, 3);
+        // ---- pass-B tile into state 1
+        if (!fetch(it, buf)) break;
+        if (!it.is_b) { TIC(a, 1); pass_a(a, it, buf, sc); TOC(a, 1); if (!fetch(it, buf)) break; }
+        if (s0.live) lookback_prefetch(a.desc + s0.c * a.T, s0.t, sc.lb);
+        TIC(a, 2); stage1(a, it, buf, sc, 1, s1); TOC(a, 2);
+        TIC(a, 3); stage2<EMIT>(a, sc, 0, s0); TOC(a, 3);
+    }
+    // drain: the last parked tiles (their look-back falls back to polling when nothing was prefetched)
+    if (s0.live) lookback_prefetch(a.desc + s0.c * a.T, s0.t, sc.lb);
+    stage2<EMIT>(a, sc, 0, s0);
+    if (s1.live) lookback_prefetch(a.desc + s1.c * a.T, s1.t, sc.lb);
+    stage2<EMIT>(a, sc, 1, s1);
+    if ((a.dbg & 32) && threadIdx.x == 0) {
+        sc.tacc[6] += gtime();
+        for (int q = 0; q < 8; ++q) atomicAdd(reinterpret_cast<unsigned long long *>(a.hdr->pad + 1) + q, sc.tacc[q]);
+    }
+}
+
+static int g_sms = 0, g_occ[2] = {0, 0};
+
+int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
+                  const float *x_inject, const float *l1_inject, uint64_t seed, uint64_t client0,
+                  int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
+                  uint32_t *codes, int64_t codes_bytes, uint64_t *dir, float *l1_out, cudaStream_t st, bool packed) {
+    char *base = (char *)ws;
+    StreamArgs a;
+    a.X = X; a.d = d; a.ld = ld; a.T = L.T; a.n = n; a.m = m;
+    a.consts = (RowConst *)(base + L.off_consts);
+    a.desc = (TileRec *)(base + L.off_desc);
+    a.hdr = (WsHeader *)base;
+    a.partial = (Rec *)(base + L.off_partial);
+    a.row_ready = (uint32_t *)(base + L.off_ready);
+    a.x_inject = x_inject; a.l1_inject = l1_inject; a.seed = seed; a.client0 = client0; a.l1_out = l1_out;
+    a.k_out = k_out; a.sgn_out = sgn_out; a.deq_out = deq_out; a.ld_out = ld_out;
+    a.packed = packed ? 1 : 0;
+    a.pack.codes = codes; a.pack.codes_bytes = codes_bytes; a.pack.dir = dir; a.pack.hdr = a.hdr;
+    a.pack.W0 = expected_width(m > 0 ? m : 1, d);
+    const int64_t nT = n * L.T;
+    a.pack.arena_base16 = (unsigned long long)nT * 32ull * (unsigned long long)a.pack.W0;
+    if (packed && (long long)(a.pack.arena_base16 * 16ull) > codes_bytes) {
+        set_error("code arena too small for the primary slots: %lld < %llu bytes", (long long)codes_bytes, a.pack.arena_base16 * 16ull);
+        return DME_EWORKSPACE;
+    }
+    const size_t dyn = (size_t)kRing * kTile * sizeof(float);
+    if (g_sms == 0) {
+        int dev = 0;
+        DME_CUDA(cudaGetDevice(&dev));
+        DME_CUDA(cudaFuncSetAttribute(quantize_stream_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        DME_CUDA(cudaFuncSetAttribute(quantize_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_occ[0], quantize_stream_kernel<0>, kThreads, dyn));
+        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_occ[1], quantize_stream_kernel<1>, kThreads, dyn));
+        DME_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int occ = g_occ[packed ? 1 : 0];
+    if (occ < 1) { set_error("quantize_stream_kernel does not fit on an SM"); return DME_ECUDA; }
+    int64_t G = (int64_t)g_sms * occ;
+    if (const char *e = getenv("DME_DBG_G")) G = atoll(e);
+    if ((G & 1) == 0) --G;                       // odd: every CTA alternates pass-A and pass-B items
+    if (G < 1) G = 1;
+    a.goff = G / 2 + 16;
+    a.lag = L.T + a.goff + G + 16;
+    if (const char *e = getenv("DME_DBG_LAG")) a.lag = L.T + a.goff + atoll(e);
+    const int64_t lenA = nT + a.goff + 1, lenB = nT + a.lag;
+    a.total_items = 2 * (lenA > lenB ? lenA : lenB);
+    a.G = G;
+    a.dbg = 0;
+    if (const char *e = getenv("DME_DBG")) a.dbg = atoi(e);
+    void *args[] = {&a};
+    const void *fn = packed ? (const void *)quantize_stream_kernel<1> : (const void *)quantize_stream_kernel<0>;
+    DME_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)G), dim3(kThreads), args, dyn, st));
+    count_launch();
+    return DME_OK;
+}
+
+}  // namespace dme

@@ -84,7 +84,7 @@ inline WsLayout ws_layout(int64_t n, int64_t d) {
     L.off_ready = o; o = align_up(o + 4 * n, 256);
     L.zero_bytes = o;
     L.off_consts = o; o = align_up(o + (int64_t)sizeof(RowConst) * n, 256);
-    L.off_partial = o; o = align_up(o + 8 * n * L.T, 256);
+    L.off_partial = o; o = align_up(o + 16 * n * L.T, 256);     // 16-byte {sum, flag} records
     L.off_desc = o; o = align_up(o + (int64_t)sizeof(TileDesc) * n * L.T, 256);
     L.off_sel = o; o = align_up(o + (int64_t)sizeof(RowSelect) * n, 256);
     L.total = o;

@@ -20,6 +20,7 @@
 // timing (integer addition is associative).
 #include <cooperative_groups.h>
 #include <cstdlib>
+#include <type_traits>
 
 #include "type_quantize.cuh"
 
@@ -73,8 +74,13 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
 }
 
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#ifdef DME_TIMERS
 #define TIC(a, k) do { if (((a).dbg & 32) && threadIdx.x == 0) sc.tacc[k] -= gtime(); } while (0)
 #define TOC(a, k) do { if (((a).dbg & 32) && threadIdx.x == 0) sc.tacc[k] += gtime(); } while (0)
+#else
+#define TIC(a, k) do { } while (0)
+#define TOC(a, k) do { } while (0)
+#endif
 
 struct StreamArgs {
     const float *X; int64_t d, ld, T, n, m;
@@ -86,23 +92,24 @@ struct StreamArgs {
     int dbg;                                                            // development: bit 5 = phase timers
 };
 
-struct Item { int valid; int is_b; int64_t pos, c, t; int copied; const float *src; int64_t fin_row; };
+// One work item, decoded once by thread 0 when it issues the tile's bulk copy and shared through a ring.
+struct __align__(16) Item { int c, t; int copied; int fin_row; int valid, is_b; int pad0, pad1; };
 __device__ __forceinline__ Item decode_item(const StreamArgs &a, int64_t i) {
-    Item it; it.valid = 0; it.is_b = (int)(i & 1); it.pos = 0; it.c = 0; it.t = 0; it.copied = 0; it.src = nullptr; it.fin_row = -1;
+    Item it; it.valid = 0; it.is_b = (int)(i & 1); it.c = 0; it.t = 0; it.copied = 0; it.fin_row = -1; it.pad0 = it.pad1 = 0;
     if (i >= a.total_items) return it;
     const int64_t s = it.is_b ? ((i >> 1) - a.lag) : (i >> 1);
-    it.pos = s;
+    const uint32_t T32 = (uint32_t)a.T;                        // positions fit 32 bits (n * T < 2^30, host check)
     if (!it.is_b && s >= a.T + a.goff) {                       // finaliser duty of this A position
-        const int64_t u = s - a.goff;
-        const int64_t p = u / a.T;
-        if (u - p * a.T == 0 && p - 1 < a.n) it.fin_row = p - 1;
+        const uint32_t u = (uint32_t)(s - a.goff);
+        const uint32_t p = u / T32;
+        if (u - p * T32 == 0 && (int64_t)p - 1 < a.n) it.fin_row = (int)p - 1;
     }
     if (s < 0 || s >= a.n * a.T) return it;
     it.valid = 1;
-    it.c = s / a.T; it.t = s - it.c * a.T;
-    const int64_t rem = a.d - it.t * kTile;
+    const uint32_t c32 = (uint32_t)s / T32;
+    it.c = (int)c32; it.t = (int)((uint32_t)s - c32 * T32);
+    const int64_t rem = a.d - (int64_t)it.t * kTile;
     it.copied = rem >= kTile ? kTile : (int)(rem & ~(int64_t)3);
-    it.src = a.X + it.c * a.ld + it.t * kTile;
     return it;
 }
 
@@ -114,6 +121,7 @@ struct Scratch {
     RowConst rc[2];
     long long rc_row[2];
     PackScratch pack;
+    Item items[kRing];
     Rec lb[kThreads];          // prefetched look-back window
     long long lb_sum[kWarps];
     int lb_f[kWarps];
@@ -156,8 +164,8 @@ __device__ __forceinline__ void make_row_const(const StreamArgs &a, int64_t c, d
 // ---- pass A of one tile (+ the finaliser duty attached to this stream position)
 __device__ __forceinline__ void pass_a(const StreamArgs &a, const Item &it, const float *buf, Scratch &sc) {
     if (it.valid) {
-        const float *row = a.X + it.c * a.ld;
-        const int64_t tile0 = it.t * kTile;
+        const float *row = a.X + (int64_t)it.c * a.ld;
+        const int64_t tile0 = (int64_t)it.t * kTile;
         double s = 0.0;
         if (it.copied == kTile) {
 #pragma unroll
@@ -172,11 +180,11 @@ __device__ __forceinline__ void pass_a(const StreamArgs &a, const Item &it, cons
                 for (int e = 0; e < 4; ++e) s += (double)fabsf(staged(buf, q * 1024 + 4 * threadIdx.x + e, it.copied, row, tile0, a.d));
         }
         s = block_sum_f64(s, sc.red);                     // fixed association; ends with every thread past a barrier
-        if (threadIdx.x == 0) rec_store(&a.partial[it.c * a.T + it.t], (unsigned long long)__double_as_longlong(s), 1u);
+        if (threadIdx.x == 0) rec_store(&a.partial[(int64_t)it.c * a.T + it.t], (unsigned long long)__double_as_longlong(s), 1u);
     }
     if (it.fin_row >= 0) {
         // reduce row fin_row's tile sums in a fixed order (thread-strided, then the block tree) and publish the row
-        const Rec *pp = a.partial + it.fin_row * a.T;
+        const Rec *pp = a.partial + (int64_t)it.fin_row * a.T;
         double acc = 0.0;
         for (int64_t i = threadIdx.x; i < a.T; i += kThreads) {
             unsigned long long v;
@@ -215,19 +223,22 @@ __device__ __forceinline__ void chain(float x, const RowConst &rc, float &flf, f
 }
 
 // State of a pass-B tile between its two stages (registers).
+template <int EMIT>
 struct BState {
-    float fl[kEpt];
+    // floor(m p): integer for the packed output (magnitudes >= 2^31 raise DME_EOVERFLOW), float for the array output
+    typename std::conditional<EMIT == 1, int, float>::type fl[kEpt];
     float fr[kEpt];
     uint32_t sign;          // bit j = IEEE sign of coordinate j
     double base;            // in-tile exclusive prefix of this thread's first coordinate
     double end;             // in-tile inclusive prefix of this thread's last coordinate (scan value)
     long long Aq;           // tile aggregate, fixed point
-    int64_t c, t;
+    int c, t;
     int live;
 };
 
 // ---- stage 1: everything that does not need the prefix of earlier tiles
-__device__ __forceinline__ void stage1(const StreamArgs &a, const Item &it, const float *buf, Scratch &sc, int slot, BState &st) {
+template <int EMIT>
+__device__ __forceinline__ void stage1(const StreamArgs &a, const Item &it, const float *buf, Scratch &sc, int slot, BState<EMIT> &st) {
     st.live = it.valid;
     if (!it.valid) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -246,8 +257,8 @@ __device__ __forceinline__ void stage1(const StreamArgs &a, const Item &it, cons
         __syncthreads();
     }
     const RowConst &rc = sc.rc[slot];
-    const float *row = a.X + it.c * a.ld;
-    const int64_t tile0 = it.t * kTile;
+    const float *row = a.X + (int64_t)it.c * a.ld;
+    const int64_t tile0 = (int64_t)it.t * kTile;
     float x[kEpt];
     if (it.copied == kTile) {
 #pragma unroll
@@ -268,24 +279,50 @@ __device__ __forceinline__ void stage1(const StreamArgs &a, const Item &it, cons
         for (int j = 0; j < kEpt; ++j) mx = fmaxf(mx, fabsf(x[j]));
         big = !(__fmul_rn(rc.mf, __fmul_rn(mx, rc.rcpD)) < 4194304.0f);
     }
-    double S = 0.0;
     uint32_t sg = 0;
+#pragma unroll
+    for (int j = kEpt - 1; j >= 0; --j) sg = __funnelshift_l(__float_as_uint(x[j]), sg, 1);     // bit j = sign of x[j]
+    st.sign = sg;
     if (exact || big) {
+        bool ovf = false;
 #pragma unroll
         for (int j = 0; j < kEpt; ++j) {
-            chain<true>(x[j], rc, st.fl[j], st.fr[j]);
-            S += (double)st.fr[j];
-            sg |= (__float_as_uint(x[j]) >> 31) << j;
+            float flf;
+            chain<true>(x[j], rc, flf, st.fr[j]);
+            if (EMIT == 1) {
+                if (flf >= 2147483520.0f) { ovf = true; st.fl[j] = 0x7ffffffe; } else st.fl[j] = (int)flf;
+            } else st.fl[j] = flf;
         }
+        if (ovf) atomicOr(&a.hdr->status, 1u);
     } else {
 #pragma unroll
         for (int j = 0; j < kEpt; ++j) {
-            chain<false>(x[j], rc, st.fl[j], st.fr[j]);
-            S += (double)st.fr[j];
-            sg |= (__float_as_uint(x[j]) >> 31) << j;
+            // fast chain: x/D by Markstein's correction of x * rcp, floor by the 2^23 trick (see chain<false>)
+            const float ax = fabsf(x[j]);
+            const float q0 = __fmul_rn(ax, rc.rcpD);
+            const float rem = __fmaf_rn(-q0, rc.D, ax);
+            const float pq = __fmaf_rn(rem, rc.rcpD, q0);
+            const float mp = __fmul_rn(rc.mf, pq);
+            const float tt = __fadd_rz(mp, 8388608.0f);
+            const float flf = __fsub_rn(tt, 8388608.0f);
+            st.fr[j] = __fsub_rn(mp, flf);
+            if (EMIT == 1) st.fl[j] = __float_as_int(tt) - 0x4b000000;       // the integer sits in the mantissa of tt
+            else st.fl[j] = flf;
         }
     }
-    st.sign = sg;
+    // thread sum: four groups of four, each summed left to right, then combined left to right -- the same
+    // association stage 2 uses for the running prefix, so the thread total equals its last prefix bit for bit
+    double S;
+    {
+        double g4[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            g4[g] = (double)st.fr[4 * g];
+#pragma unroll
+            for (int e = 1; e < 4; ++e) g4[g] += (double)st.fr[4 * g + e];
+        }
+        S = ((g4[0] + g4[1]) + g4[2]) + g4[3];
+    }
     // block scan of the thread sums (Kogge-Stone inside a warp, warps in order): fixed association
     double incl = S;
 #pragma unroll
@@ -306,7 +343,7 @@ __device__ __forceinline__ void stage1(const StreamArgs &a, const Item &it, cons
     st.base = wbase + excl;
     st.end = wbase + incl;
     st.Aq = __double2ll_rn(A * rc.q_up);                 // fixed point, 2^-qshift resolution
-    if (threadIdx.x == 0) rec_store(a.desc + it.c * a.T + it.t, (unsigned long long)st.Aq, it.t == 0 ? 2u : 1u);
+    if (threadIdx.x == 0) rec_store(a.desc + (int64_t)it.c * a.T + it.t, (unsigned long long)st.Aq, it.t == 0 ? 2u : 1u);
     __syncthreads();                                     // wtot and the tile buffer may be reused
 }
 
@@ -349,12 +386,12 @@ __device__ __forceinline__ void lookback_prefetch(const TileRec *rowdesc, int64_
 
 // ---- stage 2: look-back, prefix -> floor(c - X) (AS:635-637), type vector, emit
 template <int EMIT>
-__device__ __forceinline__ void stage2(const StreamArgs &a, Scratch &sc, int slot, BState &st) {
+__device__ __forceinline__ void stage2(const StreamArgs &a, Scratch &sc, int slot, BState<EMIT> &st) {
     if (!st.live) return;
     st.live = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const RowConst &rc = sc.rc[slot];
-    const TileRec *rowdesc = a.desc + st.c * a.T;
+    const TileRec *rowdesc = a.desc + (int64_t)st.c * a.T;
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     {
@@ -384,8 +421,8 @@ __device__ __forceinline__ void stage2(const StreamArgs &a, Scratch &sc, int slo
                 P += sc.lb_sum[w];
                 if (f < 32) { done = true; break; }
             }
-            if (!done) { if ((a.dbg & 32) && lane == 0) sc.tacc[5] += 1; TIC(a, 4); P = lookback_poll(rowdesc, st.t, lane); TOC(a, 4); }
-            if (lane == 0) rec_store(a.desc + st.c * a.T + st.t, (unsigned long long)(P + st.Aq), 2u);
+            if (!done) { TIC(a, 4); P = lookback_poll(rowdesc, st.t, lane); TOC(a, 4); }
+            if (lane == 0) rec_store(a.desc + (int64_t)st.c * a.T + st.t, (unsigned long long)(P + st.Aq), 2u);
         }
         if (lane == 0) { sc.Pq[slot] = P; sc.P[slot] = __ll2double_rn(P) * rc.q_dn; }
     }
@@ -394,57 +431,116 @@ __device__ __forceinline__ void stage2(const StreamArgs &a, Scratch &sc, int slo
     // The prefix at the LAST coordinate of a warp is defined from the scan values (and at the last coordinate of the
     // tile from the fixed-point inclusive prefix), so the next warp / tile derives the same floor(c - X) for its
     // predecessor from its own exclusive prefix: no hand-off is needed.
-    double C = Pd + st.base;
-    int aprev = __float2int_rd(__fsub_rn(__double2float_rn(C), rc.X));       // floor(c_{first-1} - X); c_0 = 0 (AS:635)
+    const double E = Pd + st.base;
+    int aprev = __float2int_rd(__fsub_rn(__double2float_rn(E), rc.X));       // floor(c_{first-1} - X); c_0 = 0 (AS:635)
     int av[kEpt];
+    {
+        // local prefixes in four independent groups of four (instruction-level parallelism), then the group offsets
+        double lp[kEpt];
 #pragma unroll
-    for (int j = 0; j < kEpt; ++j) {
-        C += (double)st.fr[j];
-        if (j == kEpt - 1 && lane == 31) C = Pd + st.end;
-        if (j == kEpt - 1 && threadIdx.x == kThreads - 1) C = __ll2double_rn(sc.Pq[slot] + st.Aq) * rc.q_dn;
-        av[j] = __float2int_rd(__fsub_rn(__double2float_rn(C), rc.X));       // AS:636
+        for (int g = 0; g < 4; ++g) {
+            lp[4 * g] = (double)st.fr[4 * g];
+#pragma unroll
+            for (int e = 1; e < 4; ++e) lp[4 * g + e] = lp[4 * g + e - 1] + (double)st.fr[4 * g + e];
+        }
+        double off[4];
+        off[0] = 0.0; off[1] = lp[3]; off[2] = lp[3] + lp[7]; off[3] = (lp[3] + lp[7]) + lp[11];
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) {
+            double C = (j < 4) ? (E + lp[j]) : (E + (off[j >> 2] + lp[j]));
+            if (j == kEpt - 1 && lane == 31) C = Pd + st.end;
+            if (j == kEpt - 1 && threadIdx.x == kThreads - 1) C = __ll2double_rn(sc.Pq[slot] + st.Aq) * rc.q_dn;
+            av[j] = __float2int_rd(__fsub_rn(__double2float_rn(C), rc.X));   // AS:636
+        }
     }
-    // predecessor's floor: from the previous lane; lane 0 uses its own exclusive prefix (computed above), which is
-    // bit-identical to the previous warp's last prefix only if that one is defined the same way:
+    // predecessor's floor: from the previous lane; lane 0 uses its own exclusive prefix (computed above)
     const int from_prev = __shfl_up_sync(0xffffffffu, av[kEpt - 1], 1);
     if (lane != 0) aprev = from_prev;
-    float kf[kEpt];
-#pragma unroll
-    for (int j = 0; j < kEpt; ++j) {
-        const int r = (av[j] - aprev == 1) ? 1 : 0;                           // AS:636-637
-        aprev = av[j];
-        kf[j] = __fadd_rn(st.fl[j], (float)r);
-    }
-    const int64_t i0 = st.t * kTile + (int64_t)threadIdx.x * kEpt;
+    const int64_t i0 = (int64_t)st.t * kTile + (int64_t)threadIdx.x * kEpt;
     if (EMIT == 0) {
         bool ovf = false;
 #pragma unroll
         for (int j = 0; j < kEpt; ++j) {
+            const int r = (av[j] - aprev == 1) ? 1 : 0;                       // AS:636-637
+            aprev = av[j];
+            const float kf = __fadd_rn((float)st.fl[j], (float)r);
             const int64_t i = i0 + j;
-            if (i >= a.d) break;
+            if (i >= a.d) continue;
             const uint32_t sbit = (st.sign >> j) & 1u;
             if (a.deq_out) {
                 // sign(v) of AS:640: v = x / D is zero exactly when m * |v| is (floor and fraction both zero, m > 0)
-                const float sgf = (st.fl[j] == 0.0f && st.fr[j] == 0.0f) ? 0.0f : (sbit ? -1.0f : 1.0f);
-                a.deq_out[st.c * a.ld_out + i] = __fdiv_rn(__fmul_rn(__fmul_rn(rc.L1f, sgf), kf[j]), rc.mf);
+                const float sgf = ((float)st.fl[j] == 0.0f && st.fr[j] == 0.0f) ? 0.0f : (sbit ? -1.0f : 1.0f);
+                a.deq_out[(int64_t)st.c * a.ld_out + i] = __fdiv_rn(__fmul_rn(__fmul_rn(rc.L1f, sgf), kf), rc.mf);
             }
             if (a.k_out) {
-                if (kf[j] >= 2147483648.0f) { ovf = true; a.k_out[st.c * a.ld_out + i] = 0x7fffffff; }
-                else a.k_out[st.c * a.ld_out + i] = (int32_t)kf[j];
+                if (kf >= 2147483648.0f) { ovf = true; a.k_out[(int64_t)st.c * a.ld_out + i] = 0x7fffffff; }
+                else a.k_out[(int64_t)st.c * a.ld_out + i] = (int32_t)kf;
             }
-            if (a.sgn_out) a.sgn_out[st.c * a.ld_out + i] = (uint8_t)sbit;
+            if (a.sgn_out) a.sgn_out[(int64_t)st.c * a.ld_out + i] = (uint8_t)sbit;
         }
         if (ovf) atomicOr(&a.hdr->status, 1u);
         __syncthreads();
     } else {
-        uint32_t k[kEpt], sg[kEpt];
-        bool ovf = false;
+        // type vector in place of av: k_j = floor + [floor(c_j - X) - floor(c_{j-1} - X) == 1]
+        int kmax = 0;
+        uint32_t kbits = 0;
 #pragma unroll
         for (int j = 0; j < kEpt; ++j) {
-            if (kf[j] >= 2147483648.0f) { ovf = true; k[j] = 0x7fffffffu; } else k[j] = (uint32_t)kf[j];
-            sg[j] = (st.sign >> j) & 1u;
+            const int cur = av[j];
+            const int k = (int)st.fl[j] + ((cur - aprev == 1) ? 1 : 0);
+            aprev = cur;
+            av[j] = k;
+            kmax = max(kmax, k);
+            kbits |= (uint32_t)(k & 1) << j;
         }
-        emit_packed_tile(a.pack, st.c * a.T + st.t, k, sg, ovf, sc.pack);
+        // tile-wide minimal field width
+        kmax = __reduce_max_sync(0xffffffffu, kmax);
+        if (lane == 0) sc.pack.u32[warp] = (uint32_t)kmax;
+        __syncthreads();
+        uint32_t km = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) km = max(km, sc.pack.u32[w]);
+        int W = 2;
+        while (W < 32 && km >= (1u << (W - 1))) W <<= 1;
+        const int64_t slot_id = (int64_t)st.c * a.T + st.t;
+        unsigned long long off16;
+        if (W <= a.pack.W0) {
+            off16 = (unsigned long long)slot_id * (32ull * a.pack.W0);
+            if (threadIdx.x == 0) a.pack.dir[slot_id] = (off16 << 8) | (unsigned long long)W;
+        } else {
+            if (threadIdx.x == 0) {
+                const unsigned long long units = 32ull * W;
+                unsigned long long off = a.pack.arena_base16 + atomicAdd(&a.hdr->arena_top, units);
+                if ((long long)((off + units) * 16ull) > a.pack.codes_bytes) { atomicOr(&a.hdr->status, 2u); off = ~0ull; }
+                sc.pack.off16 = off;
+                a.pack.dir[slot_id] = (off == ~0ull) ? 0ull : ((off << 8) | (unsigned long long)W);
+            }
+            __syncthreads();
+            off16 = sc.pack.off16;
+        }
+        if (off16 != ~0ull) {
+            uint32_t *tw = a.pack.codes + off16 * 4ull;
+            if (W == 2) {
+                // fields [sign | magnitude bit]: interleave the two 16-bit masks
+                uint32_t lo = kbits, hi = st.sign;
+                lo = (lo | (lo << 8)) & 0x00ff00ffu; hi = (hi | (hi << 8)) & 0x00ff00ffu;
+                lo = (lo | (lo << 4)) & 0x0f0f0f0fu; hi = (hi | (hi << 4)) & 0x0f0f0f0fu;
+                lo = (lo | (lo << 2)) & 0x33333333u; hi = (hi | (hi << 2)) & 0x33333333u;
+                lo = (lo | (lo << 1)) & 0x55555555u; hi = (hi | (hi << 1)) & 0x55555555u;
+                tw[threadIdx.x] = lo | (hi << 1);
+            } else {
+                uint32_t k[kEpt], sg[kEpt];
+#pragma unroll
+                for (int j = 0; j < kEpt; ++j) { k[j] = (uint32_t)av[j]; sg[j] = (st.sign >> j) & 1u; }
+                switch (W) {
+                    case 4: pack_store<4>(k, sg, tw); break;
+                    case 8: pack_store<8>(k, sg, tw); break;
+                    case 16: pack_store<16>(k, sg, tw); break;
+                    default: pack_store<32>(k, sg, tw); break;
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -468,26 +564,28 @@ quantize_stream_kernel(StreamArgs a) {
     int64_t jn = 0;                      // local index of the next item to fetch
     uint32_t parity_bits = 0;            // phase parity of each ring slot
 
-    auto issue = [&](int64_t j) {        // thread 0: start the bulk copy of local item j (if it has data)
+    auto issue = [&](int64_t j) {        // thread 0: decode local item j, start its bulk copy (if it has data)
         const Item it = decode_item(a, g + j * a.G);
+        const int b = (int)(j & (kRing - 1));
+        sc.items[b] = it;
         if (it.valid && it.copied > 0) {
-            const int b = (int)(j % kRing);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(&mbar[b], (uint32_t)it.copied * 4u);
-            bulk_g2s(dyn_smem + (size_t)b * kTile * 4, it.src, (uint32_t)it.copied * 4u, &mbar[b], it.is_b ? pol_b : pol_a);
+            bulk_g2s(dyn_smem + (size_t)b * kTile * 4, a.X + (int64_t)it.c * a.ld + (int64_t)it.t * kTile, (uint32_t)it.copied * 4u, &mbar[b],
+                     it.is_b ? pol_b : pol_a);
         }
     };
     if (threadIdx.x == 0) {
         for (int64_t j = 0; j < kAhead; ++j) issue(j);
     }
+    __syncthreads();
     // fetch(): next item of this CTA, its staged tile ready in shared memory
     auto fetch = [&](Item &it, const float *&buf) -> bool {
         const int64_t j = jn++;
-        const int64_t i = g + j * a.G;
-        if (i >= a.total_items) return false;
+        if (g + j * a.G >= a.total_items) return false;
         if (threadIdx.x == 0) issue(j + kAhead);
-        it = decode_item(a, i);
-        const int b = (int)(j % kRing);
+        const int b = (int)(j & (kRing - 1));
+        it = sc.items[b];
         buf = reinterpret_cast<const float *>(dyn_smem + (size_t)b * kTile * 4);
         if (it.valid && it.copied > 0) {
             TIC(a, 0);
@@ -498,27 +596,27 @@ quantize_stream_kernel(StreamArgs a) {
         return true;
     };
 
-    BState s0, s1;
+    BState<EMIT> s0, s1;
     s0.live = 0; s1.live = 0;
     Item it; const float *buf = nullptr;
     while (true) {
         // ---- pass-B tile into state 0 (an A item may come first)
         if (!fetch(it, buf)) break;
         if (!it.is_b) { TIC(a, 1); pass_a(a, it, buf, sc); TOC(a, 1); if (!fetch(it, buf)) break; }
-        if (s1.live) lookback_prefetch(a.desc + s1.c * a.T, s1.t, sc.lb);
-        TIC(a, 2); stage1(a, it, buf, sc, 0, s0); TOC(a, 2);
+        if (s1.live) lookback_prefetch(a.desc + (int64_t)s1.c * a.T, s1.t, sc.lb);
+        TIC(a, 2); stage1<EMIT>(a, it, buf, sc, 0, s0); TOC(a, 2);
         TIC(a, 3); stage2<EMIT>(a, sc, 1, s1); TOC(a, 3);
         // ---- pass-B tile into state 1
         if (!fetch(it, buf)) break;
         if (!it.is_b) { TIC(a, 1); pass_a(a, it, buf, sc); TOC(a, 1); if (!fetch(it, buf)) break; }
-        if (s0.live) lookback_prefetch(a.desc + s0.c * a.T, s0.t, sc.lb);
-        TIC(a, 2); stage1(a, it, buf, sc, 1, s1); TOC(a, 2);
+        if (s0.live) lookback_prefetch(a.desc + (int64_t)s0.c * a.T, s0.t, sc.lb);
+        TIC(a, 2); stage1<EMIT>(a, it, buf, sc, 1, s1); TOC(a, 2);
         TIC(a, 3); stage2<EMIT>(a, sc, 0, s0); TOC(a, 3);
     }
     // drain: the last parked tiles (their look-back falls back to polling when nothing was prefetched)
-    if (s0.live) lookback_prefetch(a.desc + s0.c * a.T, s0.t, sc.lb);
+    if (s0.live) lookback_prefetch(a.desc + (int64_t)s0.c * a.T, s0.t, sc.lb);
     stage2<EMIT>(a, sc, 0, s0);
-    if (s1.live) lookback_prefetch(a.desc + s1.c * a.T, s1.t, sc.lb);
+    if (s1.live) lookback_prefetch(a.desc + (int64_t)s1.c * a.T, s1.t, sc.lb);
     stage2<EMIT>(a, sc, 1, s1);
     if ((a.dbg & 32) && threadIdx.x == 0) {
         sc.tacc[6] += gtime();

@@ -121,14 +121,6 @@ __device__ __forceinline__ float deq_over_n(float L1f, float kf, float mf, float
     const float q = biased ? __fmul_rn(L1f, __fdiv_rn(kf, mf)) : __fdiv_rn(__fmul_rn(L1f, kf), mf);
     return __fdiv_rn(q, nf);                                                                       // ND:137
 }
-__global__ void decode_lut_kernel(const float *__restrict__ l1, int64_t n, float mf, float nf, int biased, float *__restrict__ lut) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * kLut) return;
-    const int64_t c = i / kLut;
-    const int k = (int)(i - c * kLut);
-    lut[i] = k == 0 ? 0.0f : deq_over_n(l1[c], (float)k, mf, nf, biased);
-}
-
 // Add one client's chunk with field width W (words already in registers).
 template <int W>
 __device__ __forceinline__ void add_fields(const uint32_t (&words)[W / 2], const float *__restrict__ lutc, const float (&lv)[kLut], float L1f,
@@ -145,7 +137,7 @@ __device__ __forceinline__ void add_fields(const uint32_t (&words)[W / 2], const
             float v;
             if (W == 2) v = mag ? lv[1] : 0.0f;
             else if (W == 4) v = lv[mag];
-            else v = mag < (uint32_t)kLut ? __ldg(lutc + mag) : deq_over_n(L1f, (float)mag, mf, nf, biased);
+            else v = mag < (uint32_t)kLut ? lutc[mag] : deq_over_n(L1f, (float)mag, mf, nf, biased);
             acc[j] = __fadd_rn(acc[j], __uint_as_float(__float_as_uint(v) ^ (mag ? sgn : 0u)));   // zero magnitudes add +0
         }
     }
@@ -158,7 +150,7 @@ __device__ __forceinline__ void decode_generic(const uint32_t *__restrict__ tw, 
     for (int q = 0; q < W / 2; ++q) words[q] = __ldg(tw + q * kThreads + chunk);
     float lv[kLut];
 #pragma unroll
-    for (int k = 0; k < kLut; ++k) lv[k] = (W <= 4) ? __ldg(lutc + k) : 0.0f;
+    for (int k = 0; k < kLut; ++k) lv[k] = (W <= 4) ? lutc[k] : 0.0f;
     add_fields<W>(words, lutc, lv, L1f, mf, nf, biased, acc);
 }
 
@@ -166,18 +158,29 @@ __device__ __forceinline__ void decode_generic(const uint32_t *__restrict__ tw, 
 // 64-thread CTAs, 4 per tile, so that short rows still fill the GPU.  Clients are taken in batches of 8 whose
 // directory entries and code words are loaded together (8 independent loads in flight per thread).
 constexpr int kBatch = 8;
+constexpr int kLutClients = 256;     // clients whose tables are staged in shared memory at a time (8 KB)
 __global__ void __launch_bounds__(64)
 decode_mean_kernel(const uint32_t *__restrict__ codes, const uint64_t *__restrict__ dir, const float *__restrict__ l1,
-                   const float *__restrict__ lut, int64_t n, int64_t d, int64_t T, float mf, float nf, int biased,
-                   float *__restrict__ mean, int accumulate) {
+                   int64_t n, int64_t d, int64_t T, float mf, float nf, int biased, float *__restrict__ mean, int accumulate) {
+    __shared__ float lut[kLutClients * kLut];
     const int64_t t = blockIdx.x >> 2;
     const int chunk = (int)(blockIdx.x & 3) * 64 + threadIdx.x;
     const int64_t i0 = t * kTile + (int64_t)chunk * kEpt;
-    if (i0 >= d) return;
+    const bool live = i0 < d;
     float acc[kEpt];
 #pragma unroll
     for (int j = 0; j < kEpt; ++j) acc[j] = (accumulate && i0 + j < d) ? mean[i0 + j] : 0.0f;
-    for (int64_t c0 = 0; c0 < n; c0 += kBatch) {
+    for (int64_t cb = 0; cb < n; cb += kLutClients) {
+    const int64_t ce = (cb + kLutClients < n) ? cb + kLutClients : n;
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)(ce - cb) * kLut; i += 64) {
+        const int k = i & (kLut - 1);
+        lut[i] = k == 0 ? 0.0f : deq_over_n(__ldg(l1 + cb + (i >> 3)), (float)k, mf, nf, biased);
+    }
+    __syncthreads();
+    if (live)
+    for (int64_t c0 = cb; c0 < ce; c0 += kBatch) {
+        const int64_t n = ce;                      // batch bound inside this block of clients
         uint64_t e[kBatch];
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) e[u] = (c0 + u < n) ? __ldg(dir + (c0 + u) * T + t) : 0ull;
@@ -189,7 +192,7 @@ decode_mean_kernel(const uint32_t *__restrict__ codes, const uint64_t *__restric
             const int W = (int)(e[u] & 0xffu);
             all2 = all2 && (W == 2 || W == 0);
             w0[u] = (W == 2) ? __ldg(codes + (e[u] >> 8) * 4ull + chunk) : 0u;
-            v1[u] = (c0 + u < n) ? __ldg(lut + (c0 + u) * kLut + 1) : 0.0f;
+            v1[u] = (c0 + u < n) ? lut[(c0 + u - cb) * kLut + 1] : 0.0f;
         }
         if (all2) {
             // common case at low rates: sign/magnitude pairs of 2 bits, value +-lut[1]
@@ -207,7 +210,7 @@ decode_mean_kernel(const uint32_t *__restrict__ codes, const uint64_t *__restric
                 if (c0 + u >= n) break;
                 const int W = (int)(e[u] & 0xffu);
                 const uint32_t *tw = codes + (e[u] >> 8) * 4ull;
-                const float *lutc = lut + (c0 + u) * kLut;
+                const float *lutc = lut + (c0 + u - cb) * kLut;
                 if (W == 2) decode_generic<2>(tw, chunk, lutc, 0.0f, mf, nf, biased, acc);
                 else if (W == 4) decode_generic<4>(tw, chunk, lutc, 0.0f, mf, nf, biased, acc);
                 else if (W == 8) decode_generic<8>(tw, chunk, lutc, __ldg(l1 + c0 + u), mf, nf, biased, acc);
@@ -217,6 +220,8 @@ decode_mean_kernel(const uint32_t *__restrict__ codes, const uint64_t *__restric
             }
         }
     }
+    }
+    if (!live) return;
     if (i0 + kEpt <= d) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -368,14 +373,9 @@ extern "C" int dme_decode_mean(const void *codes, const uint64_t *dir, const flo
     DME_REQUIRE(((uintptr_t)mean & 15u) == 0 && ((uintptr_t)codes & 15u) == 0, "mean and codes must be 16-byte aligned");
     const int64_t T = (d + kTile - 1) / kTile;
     cudaStream_t st = (cudaStream_t)stream;
-    float *lut = nullptr;                                   // internal, stream-ordered scratch (32 bytes per client)
-    DME_CUDA(cudaMallocAsync(&lut, sizeof(float) * (size_t)(n * kLut), st));
-    decode_lut_kernel<<<(unsigned)((n * kLut + 127) / 128), 128, 0, st>>>(l1, n, (float)m, (float)n_total, mode == DME_MODE_BIASED, lut);
-    DME_LAUNCH_CHECK("decode_lut_kernel");
-    decode_mean_kernel<<<(unsigned)(4 * T), 64, 0, st>>>((const uint32_t *)codes, dir, l1, lut, n, d, T, (float)m, (float)n_total,
+    decode_mean_kernel<<<(unsigned)(4 * T), 64, 0, st>>>((const uint32_t *)codes, dir, l1, n, d, T, (float)m, (float)n_total,
                                                          mode == DME_MODE_BIASED, mean, accumulate);
     DME_LAUNCH_CHECK("decode_mean_kernel");
-    DME_CUDA(cudaFreeAsync(lut, st));
     prof_mark((cudaStream_t)stream);
     return DME_OK;
 }

@@ -21,7 +21,7 @@ FLAGS = [
     "-fmad=false",                      # every fp32 op of the reference chain rounds once; FMAs are explicit
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2", "-cudart", "static", "-shared",
     "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-]
+] + (["-DDME_TIMERS"] if os.environ.get("DME_TIMERS") else []) + os.environ.get("DME_NVCC_EXTRA", "").split()
 
 
 def sources():

@@ -9,11 +9,13 @@
 // sums and publishes the row constants, so that row p's pass B, which starts `lag - T - goff` tiles later, never
 // waits for them.  Every wait is on an item with a smaller index, every CTA is resident: no deadlock.
 //
-// Inside a CTA.  Tiles arrive through a 4-deep ring of 1-D bulk async copies (TMA, SASS UBLKCP) issued two items
-// ahead.  A pass-B tile is split in two stages: stage 1 (division, floor, fractional parts, block scan, publish the
-// tile aggregate) and stage 2 (decoupled look-back, prefix -> floor(c - X), type vector, emit).  Stage 2 of a tile
-// runs after stage 1 of the CTA's NEXT pass-B tile, so the look-back finds its predecessors already published; the
-// parked state (floor, fraction, signs: 33 registers per thread) lives in registers.
+// Inside a CTA.  Tiles arrive through a ring of 1-D bulk async copies (TMA, SASS UBLKCP) issued one item ahead.
+// A pass-B tile is split in two stages: stage 1 (division, floor, fractional parts, block scan, publish the tile
+// aggregate) and stage 2 (decoupled look-back, prefix -> floor(c - X), type vector, emit).  The pass-A item that
+// follows every pass-B tile runs BETWEEN the two stages, which gives the look-back a head start while the tile's
+// state (floor, fraction, signs: 33 registers) waits in registers; 64 registers per thread keep 4 CTAs (32 warps)
+// resident per SM, which hides the rest.  (A fully pipelined variant with two tile states is kept behind
+// DME_STREAM_PIPELINED=1; it needs 128 registers and measured slower.)
 //
 // Cross-CTA messages are 16-byte records {value, flag} written and read with single 128-bit accesses, so no
 // fences are needed; tile aggregates travel as int64 fixed point, which makes the look-back result independent of
@@ -26,8 +28,16 @@
 
 namespace dme {
 
-constexpr int kRing = 4;        // TMA ring depth
-constexpr int kAhead = 2;       // items prefetched ahead
+#ifndef DME_STREAM_RING
+#define DME_STREAM_RING 2
+#endif
+#ifndef DME_STREAM_AHEAD
+#define DME_STREAM_AHEAD (DME_STREAM_RING - 1)
+#endif
+constexpr int kRing = DME_STREAM_RING;   // TMA ring depth
+constexpr int kAhead = DME_STREAM_AHEAD; // items prefetched ahead (<= kRing - 1: a slot is refilled only after the
+                                         // barrier inside the item that consumed it)
+static_assert(kAhead >= 1 && kAhead <= kRing - 1, "ring too shallow");
 
 struct __align__(16) Rec { unsigned long long v; uint32_t flag; uint32_t pad; };
 typedef Rec TileRec;      // per tile: flag 1 = v is the tile aggregate, 2 = v is the inclusive prefix (fixed point)
@@ -116,15 +126,14 @@ __device__ __forceinline__ Item decode_item(const StreamArgs &a, int64_t i) {
 struct Scratch {
     double wtot[kWarps];
     double red[kWarps];
+    double redA[kWarps];
     double P[2];
     long long Pq[2];
     RowConst rc[2];
     long long rc_row[2];
     PackScratch pack;
     Item items[kRing];
-    Rec lb[kThreads];          // prefetched look-back window
-    long long lb_sum[kWarps];
-    int lb_f[kWarps];
+    Rec lb[32 * 4];            // prefetched look-back windows (warp 0)
     unsigned long long tacc[8];  // phase timers (dbg)
 };
 
@@ -161,6 +170,23 @@ __device__ __forceinline__ void make_row_const(const StreamArgs &a, int64_t c, d
     if (a.l1_out) a.l1_out[c] = rc.L1f;
 }
 
+// Cold path: reduce row `row`'s tile sums in a fixed order (thread-strided, then the block tree), publish the row.
+__device__ void finalize_row(const StreamArgs &a, int row, Scratch &sc) {
+    const Rec *pp = a.partial + (int64_t)row * a.T;
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < a.T; i += kThreads) {
+        unsigned long long v;
+        while (rec_load(pp + i, v) == 0u) __nanosleep(64);
+        acc += __longlong_as_double((long long)v);
+    }
+    acc = block_sum_f64(acc, sc.red);
+    if (threadIdx.x == 0) {
+        make_row_const(a, row, acc);
+        __threadfence();
+        st_release_u32(&a.row_ready[row], 1u);
+    }
+}
+
 // ---- pass A of one tile (+ the finaliser duty attached to this stream position)
 __device__ __forceinline__ void pass_a(const StreamArgs &a, const Item &it, const float *buf, Scratch &sc) {
     if (it.valid) {
@@ -179,26 +205,18 @@ __device__ __forceinline__ void pass_a(const StreamArgs &a, const Item &it, cons
 #pragma unroll
                 for (int e = 0; e < 4; ++e) s += (double)fabsf(staged(buf, q * 1024 + 4 * threadIdx.x + e, it.copied, row, tile0, a.d));
         }
-        s = block_sum_f64(s, sc.red);                     // fixed association; ends with every thread past a barrier
-        if (threadIdx.x == 0) rec_store(&a.partial[(int64_t)it.c * a.T + it.t], (unsigned long long)__double_as_longlong(s), 1u);
-    }
-    if (it.fin_row >= 0) {
-        // reduce row fin_row's tile sums in a fixed order (thread-strided, then the block tree) and publish the row
-        const Rec *pp = a.partial + (int64_t)it.fin_row * a.T;
-        double acc = 0.0;
-        for (int64_t i = threadIdx.x; i < a.T; i += kThreads) {
-            unsigned long long v;
-            while (rec_load(pp + i, v) == 0u) __nanosleep(64);
-            acc += __longlong_as_double((long long)v);
-        }
-        acc = block_sum_f64(acc, sc.red);
+        // fixed association: xor butterfly inside a warp, warps in index order (same tree as block_sum_f64)
+        s = warp_sum_f64(s);
+        if ((threadIdx.x & 31) == 0) sc.redA[threadIdx.x >> 5] = s;
+        __syncthreads();
         if (threadIdx.x == 0) {
-            make_row_const(a, it.fin_row, acc);
-            __threadfence();
-            st_release_u32(&a.row_ready[it.fin_row], 1u);
+            double tot = sc.redA[0];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) tot += sc.redA[w];
+            rec_store(&a.partial[(int64_t)it.c * a.T + it.t], (unsigned long long)__double_as_longlong(tot), 1u);
         }
     }
-    __syncthreads();
+    if (it.fin_row >= 0) finalize_row(a, it.fin_row, sc);
 }
 
 // AS:625-631 for one coordinate.  EXACT: IEEE division + floorf.  Fast: x/D by Markstein's correction of x*rcp
@@ -344,11 +362,11 @@ __device__ __forceinline__ void stage1(const StreamArgs &a, const Item &it, cons
     st.end = wbase + incl;
     st.Aq = __double2ll_rn(A * rc.q_up);                 // fixed point, 2^-qshift resolution
     if (threadIdx.x == 0) rec_store(a.desc + (int64_t)it.c * a.T + it.t, (unsigned long long)st.Aq, it.t == 0 ? 2u : 1u);
-    __syncthreads();                                     // wtot and the tile buffer may be reused
+    // no trailing barrier: wtot and this ring slot are next written after the barriers of the following stage 2
 }
 
 // Decoupled look-back over the 16-byte records (warp 0): polling fallback of the prefetched look-back below.
-__device__ __forceinline__ long long lookback_poll(const TileRec *rowdesc, int64_t t, int lane) {
+__device__ __noinline__ long long lookback_poll(const TileRec *rowdesc, int64_t t, int lane) {
     long long P = 0;
     int64_t top = t - 1;
     while (top >= 0) {
@@ -375,13 +393,51 @@ __device__ __forceinline__ long long lookback_poll(const TileRec *rowdesc, int64
     return P;
 }
 
-// Prefetch the records of the 256 tiles before tile t of the row into shared memory (cp.async, 16 bytes per
-// thread, L2 only), so that the look-back of stage 2 costs no round trip.
+constexpr int kLbWin = 4;       // prefetched look-back windows of 32 tiles
+// Warp 0 prefetches the records of the 128 tiles before tile t into shared memory (cp.async, 16 bytes each, L2
+// only) while the CTA runs stage 1 of its next tile, so that the look-back of stage 2 costs no round trip.
 __device__ __forceinline__ void lookback_prefetch(const TileRec *rowdesc, int64_t t, Rec *lb) {
-    const int64_t idx = t - 1 - (int64_t)threadIdx.x;
-    if (idx >= 0)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(lb + threadIdx.x)), "l"(rowdesc + idx) : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (threadIdx.x < 32) {
+#pragma unroll
+        for (int q = 0; q < kLbWin; ++q) {
+            const int64_t idx = t - 1 - (32 * q + (int)threadIdx.x);
+            if (idx >= 0)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(lb + 32 * q + threadIdx.x)), "l"(rowdesc + idx) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+}
+// Warp 0: exclusive fixed-point prefix of tile t from the prefetched windows (all windows examined at once for
+// instruction-level parallelism), polling if they do not resolve it.
+__device__ __forceinline__ long long lookback_resolve(const TileRec *rowdesc, int64_t t, const Rec *lb, int lane) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    unsigned incl[kLbWin], none[kLbWin];
+    long long val[kLbWin];
+#pragma unroll
+    for (int q = 0; q < kLbWin; ++q) {
+        const int64_t idx = t - 1 - (32 * q + lane);
+        const Rec r = lb[32 * q + lane];
+        const uint32_t fl = idx >= 0 ? r.flag : 2u;                 // tiles before the row start: inclusive prefix 0
+        val[q] = idx >= 0 ? (long long)r.v : 0;
+        incl[q] = __ballot_sync(0xffffffffu, fl == 2u);
+        none[q] = __ballot_sync(0xffffffffu, fl == 0u);
+    }
+    long long x = 0;
+    bool found = false, ok = true;
+#pragma unroll
+    for (int q = 0; q < kLbWin; ++q) {
+        if (!found && ok) {
+            const int f = incl[q] ? (__ffs(incl[q]) - 1) : 32;
+            const unsigned need = (f >= 31) ? 0xffffffffu : ((1u << (f + 1)) - 1u);
+            if (none[q] & need) ok = false;                         // a nearer tile had not published yet
+            else { if (lane <= f) x += val[q]; found = f < 32; }
+        }
+    }
+    if (!(found && ok)) return lookback_poll(rowdesc, t, lane);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
 }
 
 // ---- stage 2: look-back, prefix -> floor(c - X) (AS:635-637), type vector, emit
@@ -392,36 +448,10 @@ __device__ __forceinline__ void stage2(const StreamArgs &a, Scratch &sc, int slo
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const RowConst &rc = sc.rc[slot];
     const TileRec *rowdesc = a.desc + (int64_t)st.c * a.T;
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();
-    {
-        // thread i looks at tile t-1-i; tiles before the row start count as an inclusive prefix of 0
-        const int64_t idx = st.t - 1 - (int64_t)threadIdx.x;
-        const Rec r = sc.lb[threadIdx.x];
-        const uint32_t fl = idx >= 0 ? r.flag : 2u;
-        const long long val = idx >= 0 ? (long long)r.v : 0;
-        const unsigned incl = __ballot_sync(0xffffffffu, fl == 2u);
-        const unsigned none = __ballot_sync(0xffffffffu, fl == 0u);
-        const int f = incl ? (__ffs(incl) - 1) : 32;
-        const unsigned need = (f >= 31) ? 0xffffffffu : ((1u << (f + 1)) - 1u);
-        long long x = (lane <= f) ? val : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0) { sc.lb_sum[warp] = x; sc.lb_f[warp] = (none & need) ? -1 : f; }
-    }
-    __syncthreads();
     if (warp == 0) {
         long long P = 0;
-        bool done = st.t == 0;
-        if (!done) {
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w) {
-                const int f = sc.lb_f[w];
-                if (f < 0) break;                       // a nearer tile has not published yet: poll instead
-                P += sc.lb_sum[w];
-                if (f < 32) { done = true; break; }
-            }
-            if (!done) { TIC(a, 4); P = lookback_poll(rowdesc, st.t, lane); TOC(a, 4); }
+        if (st.t > 0) {
+            P = lookback_resolve(rowdesc, st.t, sc.lb, lane);
             if (lane == 0) rec_store(a.desc + (int64_t)st.c * a.T + st.t, (unsigned long long)(P + st.Aq), 2u);
         }
         if (lane == 0) { sc.Pq[slot] = P; sc.P[slot] = __ll2double_rn(P) * rc.q_dn; }
@@ -479,7 +509,6 @@ __device__ __forceinline__ void stage2(const StreamArgs &a, Scratch &sc, int slo
             if (a.sgn_out) a.sgn_out[(int64_t)st.c * a.ld_out + i] = (uint8_t)sbit;
         }
         if (ovf) atomicOr(&a.hdr->status, 1u);
-        __syncthreads();
     } else {
         // type vector in place of av: k_j = floor + [floor(c_j - X) - floor(c_{j-1} - X) == 1]
         int kmax = 0;
@@ -540,12 +569,20 @@ __device__ __forceinline__ void stage2(const StreamArgs &a, Scratch &sc, int slo
                 }
             }
         }
-        __syncthreads();
+        // no trailing barrier: the scratch used here is next written after the first barrier of the next stage 2
     }
 }
 
+// Measured on B200 (d=2^24, n=128): fully pipelined (2 tile states, 128 regs, 2 CTAs/SM) 9.8 ms; no pipelining
+// 3 CTAs 9.0 ms, 4 CTAs 8.0 ms; half-pipelined (below) 4 CTAs/SM, ring 2: 7.2 ms; ring 3: 7.6 ms.
+#ifndef DME_STREAM_CTAS
+#define DME_STREAM_CTAS 4
+#endif
+#ifndef DME_STREAM_PIPELINED
+#define DME_STREAM_PIPELINED 0
+#endif
 template <int EMIT>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, DME_STREAM_CTAS)
 quantize_stream_kernel(StreamArgs a) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ uint64_t mbar[kRing];
@@ -566,7 +603,7 @@ quantize_stream_kernel(StreamArgs a) {
 
     auto issue = [&](int64_t j) {        // thread 0: decode local item j, start its bulk copy (if it has data)
         const Item it = decode_item(a, g + j * a.G);
-        const int b = (int)(j & (kRing - 1));
+        const int b = (int)(j % kRing);
         sc.items[b] = it;
         if (it.valid && it.copied > 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -584,7 +621,7 @@ quantize_stream_kernel(StreamArgs a) {
         const int64_t j = jn++;
         if (g + j * a.G >= a.total_items) return false;
         if (threadIdx.x == 0) issue(j + kAhead);
-        const int b = (int)(j & (kRing - 1));
+        const int b = (int)(j % kRing);
         it = sc.items[b];
         buf = reinterpret_cast<const float *>(dyn_smem + (size_t)b * kTile * 4);
         if (it.valid && it.copied > 0) {
@@ -593,9 +630,14 @@ quantize_stream_kernel(StreamArgs a) {
             parity_bits ^= 1u << b;
             TOC(a, 0);
         }
+        // Every item must contain at least one CTA barrier: thread 0 runs the item ring and the TMA ring two items
+        // ahead, and a slot may only be overwritten after all threads have passed a barrier since they read it.
+        // Valid items have theirs inside pass A / stage 1; empty items (stream head and tail) get one here.
+        if (!it.valid) __syncthreads();
         return true;
     };
 
+#if DME_STREAM_PIPELINED
     BState<EMIT> s0, s1;
     s0.live = 0; s1.live = 0;
     Item it; const float *buf = nullptr;
@@ -618,6 +660,27 @@ quantize_stream_kernel(StreamArgs a) {
     stage2<EMIT>(a, sc, 0, s0);
     if (s1.live) lookback_prefetch(a.desc + (int64_t)s1.c * a.T, s1.t, sc.lb);
     stage2<EMIT>(a, sc, 1, s1);
+#else
+    // half-pipelined variant: one tile state in registers; the pass-A item that follows a pass-B tile (items
+    // alternate because G is odd) runs between the tile's two stages and gives its look-back a head start
+    BState<EMIT> s0;
+    s0.live = 0;
+    Item it; const float *buf = nullptr;
+    while (true) {
+        if (!fetch(it, buf)) break;
+        if (!it.is_b) { TIC(a, 1); pass_a(a, it, buf, sc); TOC(a, 1); continue; }
+        TIC(a, 2); stage1<EMIT>(a, it, buf, sc, 0, s0); TOC(a, 2);
+        if (s0.live) lookback_prefetch(a.desc + (int64_t)s0.c * a.T, s0.t, sc.lb);
+        const bool more = fetch(it, buf);
+        if (more && !it.is_b) { TIC(a, 1); pass_a(a, it, buf, sc); TOC(a, 1); }
+        TIC(a, 3); stage2<EMIT>(a, sc, 0, s0); TOC(a, 3);
+        if (!more) break;
+        if (it.is_b) {                    // cannot happen while G is odd; kept so that no item is ever dropped
+            stage1<EMIT>(a, it, buf, sc, 0, s0);
+            stage2<EMIT>(a, sc, 0, s0);
+        }
+    }
+#endif
     if ((a.dbg & 32) && threadIdx.x == 0) {
         sc.tacc[6] += gtime();
         for (int q = 0; q < 8; ++q) atomicAdd(reinterpret_cast<unsigned long long *>(a.hdr->pad + 1) + q, sc.tacc[q]);

@@ -32,7 +32,7 @@ for n, d in shapes:
         ws = dme.Workspace.get(X.device).buf
         off = (-ws.data_ptr()) % 256
         hdr = ws[off: off + 256].cpu().numpy().view("uint64")
-        names = ["tma wait", "pass A", "stage 1", "stage 2", "poll fallback ns", "poll fallbacks", "cta lifetime"]
+        names = ["tma wait", "pass A", "stage 1", "stage 2", "resolve (in stage 2)", "polls", "cta lifetime"]
         pairs = n * ((d + 4095) // 4096)
         print("   per tile pair, ns of thread 0 (summed over CTAs / pairs):", {nm: round(float(hdr[3 + q]) / pairs, 2) for q, nm in enumerate(names)})
     del X

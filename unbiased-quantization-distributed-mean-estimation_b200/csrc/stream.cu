@@ -94,7 +94,7 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 
 struct StreamArgs {
     const float *X; int64_t d, ld, T, n, m;
-    RowConst *consts; TileRec *desc; WsHeader *hdr; Rec *partial; uint32_t *row_ready;
+    RowConst *consts; TileRec *desc; Rec *blocks; int64_t TB; WsHeader *hdr; Rec *partial; uint32_t *row_ready;
     const float *x_inject; const float *l1_inject; uint64_t seed, client0; float *l1_out;
     int64_t lag, goff, total_items, G;
     int32_t *k_out; uint8_t *sgn_out; float *deq_out; int64_t ld_out;     // array outputs
@@ -104,21 +104,45 @@ struct StreamArgs {
 
 // One work item, decoded once by thread 0 when it issues the tile's bulk copy and shared through a ring.
 struct __align__(16) Item { int c, t; int copied; int fin_row; int valid, is_b; int pad0, pad1; };
-__device__ __forceinline__ Item decode_item(const StreamArgs &a, int64_t i) {
-    Item it; it.valid = 0; it.is_b = (int)(i & 1); it.c = 0; it.t = 0; it.copied = 0; it.fin_row = -1; it.pad0 = it.pad1 = 0;
-    if (i >= a.total_items) return it;
-    const int64_t s = it.is_b ? ((i >> 1) - a.lag) : (i >> 1);
-    const uint32_t T32 = (uint32_t)a.T;                        // positions fit 32 bits (n * T < 2^30, host check)
-    if (!it.is_b && s >= a.T + a.goff) {                       // finaliser duty of this A position
-        const uint32_t u = (uint32_t)(s - a.goff);
-        const uint32_t p = u / T32;
-        if (u - p * T32 == 0 && (int64_t)p - 1 < a.n) it.fin_row = (int)p - 1;
+// Incremental item decoder (owned by the producer thread): the CTA's items advance by G in the global order, i.e. by
+// G positions in the A stream and in the B stream alternately, so (client, tile) pairs are updated without divisions.
+struct Decoder { long long i; int cA, tA, cB, tB, cF, tF; int pad; };
+constexpr int kProducer = 32;     // warp 1 lane 0 decodes items and issues the bulk copies
+constexpr int kSummer = 64;       // warp 2 lane 0 finishes the pass-A tile sum
+__device__ __forceinline__ void floor_divmod(long long s, long long T, int &c, int &t) {
+    long long q = s >= 0 ? s / T : -((-s + T - 1) / T);
+    c = (int)q; t = (int)(s - q * T);
+}
+__device__ __forceinline__ void advance(int &c, int &t, int step, int T) {
+    t += step;
+    if (t >= T) { const int q = t / T; c += q; t -= q * T; }
+}
+__device__ __forceinline__ void decoder_init(Decoder &d, const StreamArgs &a, long long g) {
+    d.i = g;
+    const long long firstA = (g & 1) ? g + a.G : g, firstB = (g & 1) ? g : g + a.G;
+    floor_divmod(firstA >> 1, a.T, d.cA, d.tA);
+    floor_divmod((firstA >> 1) - a.goff, a.T, d.cF, d.tF);
+    floor_divmod((firstB >> 1) - a.lag, a.T, d.cB, d.tB);
+    d.pad = 0;
+}
+// Next item of the CTA (items alternate between the two streams because G is odd).
+__device__ __forceinline__ Item decoder_next(Decoder &d, const StreamArgs &a) {
+    Item it; it.valid = 0; it.is_b = (int)(d.i & 1); it.c = 0; it.t = 0; it.copied = 0; it.fin_row = -1; it.pad0 = it.pad1 = 0;
+    const bool live = d.i < a.total_items;
+    d.i += a.G;
+    int c, t;
+    if (!it.is_b) {
+        c = d.cA; t = d.tA;
+        if (live && d.tF == 0 && d.cF >= 1 && d.cF - 1 < a.n) it.fin_row = d.cF - 1;     // finaliser duty of this position
+        advance(d.cA, d.tA, (int)a.G, (int)a.T);
+        advance(d.cF, d.tF, (int)a.G, (int)a.T);
+    } else {
+        c = d.cB; t = d.tB;
+        advance(d.cB, d.tB, (int)a.G, (int)a.T);
     }
-    if (s < 0 || s >= a.n * a.T) return it;
-    it.valid = 1;
-    const uint32_t c32 = (uint32_t)s / T32;
-    it.c = (int)c32; it.t = (int)((uint32_t)s - c32 * T32);
-    const int64_t rem = a.d - (int64_t)it.t * kTile;
+    if (!live || c < 0 || c >= a.n) return it;
+    it.valid = 1; it.c = c; it.t = t;
+    const int64_t rem = a.d - (int64_t)t * kTile;
     it.copied = rem >= kTile ? kTile : (int)(rem & ~(int64_t)3);
     return it;
 }
@@ -133,7 +157,8 @@ struct Scratch {
     long long rc_row[2];
     PackScratch pack;
     Item items[kRing];
-    Rec lb[32 * 4];            // prefetched look-back windows (warp 0)
+    Decoder dec;
+    Rec lb[64];                // prefetched look-back windows: 32 tile records + 32 block records (warp 0)
     unsigned long long tacc[8];  // phase timers (dbg)
 };
 
@@ -209,7 +234,7 @@ __device__ __forceinline__ void pass_a(const StreamArgs &a, const Item &it, cons
         s = warp_sum_f64(s);
         if ((threadIdx.x & 31) == 0) sc.redA[threadIdx.x >> 5] = s;
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == kSummer) {
             double tot = sc.redA[0];
 #pragma unroll
             for (int w = 1; w < kWarps; ++w) tot += sc.redA[w];
@@ -361,83 +386,72 @@ __device__ __forceinline__ void stage1(const StreamArgs &a, const Item &it, cons
     st.base = wbase + excl;
     st.end = wbase + incl;
     st.Aq = __double2ll_rn(A * rc.q_up);                 // fixed point, 2^-qshift resolution
-    if (threadIdx.x == 0) rec_store(a.desc + (int64_t)it.c * a.T + it.t, (unsigned long long)st.Aq, it.t == 0 ? 2u : 1u);
+    if (threadIdx.x == 0) rec_store(a.desc + (int64_t)it.c * a.T + it.t, (unsigned long long)st.Aq, 1u);
     // no trailing barrier: wtot and this ring slot are next written after the barriers of the following stage 2
 }
 
-// Decoupled look-back over the 16-byte records (warp 0): polling fallback of the prefetched look-back below.
-__device__ __noinline__ long long lookback_poll(const TileRec *rowdesc, int64_t t, int lane) {
-    long long P = 0;
-    int64_t top = t - 1;
-    while (top >= 0) {
-        const int64_t idx = top - lane;
-        while (true) {
-            unsigned long long v = 0;
-            const uint32_t fl = idx >= 0 ? rec_load(&rowdesc[idx], v) : 2u;      // virtual tiles < 0: inclusive prefix 0
-            const unsigned incl = __ballot_sync(0xffffffffu, fl == 2u);
-            const unsigned none = __ballot_sync(0xffffffffu, fl == 0u);
-            const int f = incl ? (__ffs(incl) - 1) : 32;
-            const unsigned need = (f >= 31) ? 0xffffffffu : ((1u << (f + 1)) - 1u);
-            if ((none & need) == 0u) {
-                long long x = (lane <= f) ? (long long)v : 0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-                P += x;
-                if (f < 32) return P;
-                break;
-            }
-            __nanosleep(32);
-        }
-        top -= 32;
-    }
-    return P;
-}
-
-constexpr int kLbWin = 4;       // prefetched look-back windows of 32 tiles
-// Warp 0 prefetches the records of the 128 tiles before tile t into shared memory (cp.async, 16 bytes each, L2
-// only) while the CTA runs stage 1 of its next tile, so that the look-back of stage 2 costs no round trip.
-__device__ __forceinline__ void lookback_prefetch(const TileRec *rowdesc, int64_t t, Rec *lb) {
+// ------------------------------------------------------------------ two-level decoupled look-back (warp 0)
+// With ~300 pass-B tiles in flight a flat look-back has to walk ~10 windows of 32 records, and that latency in turn
+// keeps more tiles in flight.  Two levels bound it: tiles publish their aggregate {flag 1}; the LAST tile of every
+// block of 32 tiles publishes the block aggregate {flag 1} as soon as its 31 predecessors' aggregates are in and the
+// block's inclusive prefix {flag 2} once it knows its own.  A tile's exclusive prefix = aggregates of the earlier
+// tiles of its block (one window) + block aggregates back to the nearest block-inclusive record (one window): two
+// independent 16-byte loads per lane per poll.  All values are int64 fixed point, so any mixture gives the same sum.
+#ifdef DME_TIMERS
+__device__ unsigned long long g_polls;
+#endif
+struct LookArgs { const Rec *tiles; Rec *blocks; int t; };   // records of the tile's row
+__device__ __forceinline__ void lookback_prefetch(const LookArgs &k, Rec *lb) {
     if (threadIdx.x < 32) {
-#pragma unroll
-        for (int q = 0; q < kLbWin; ++q) {
-            const int64_t idx = t - 1 - (32 * q + (int)threadIdx.x);
-            if (idx >= 0)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(lb + 32 * q + threadIdx.x)), "l"(rowdesc + idx) : "memory");
-        }
+        const int lane = threadIdx.x, b = k.t >> 5, pos = k.t & 31;
+        if (lane < pos)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(lb + lane)), "l"(k.tiles + (k.t - 1 - lane)) : "memory");
+        if (b - 1 - lane >= 0)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(lb + 32 + lane)), "l"(k.blocks + (b - 1 - lane)) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
 }
-// Warp 0: exclusive fixed-point prefix of tile t from the prefetched windows (all windows examined at once for
-// instruction-level parallelism), polling if they do not resolve it.
-__device__ __forceinline__ long long lookback_resolve(const TileRec *rowdesc, int64_t t, const Rec *lb, int lane) {
+// Returns the exclusive fixed-point prefix P of tile k.t; Aq = the tile's own aggregate (for the block records).
+__device__ __forceinline__ long long lookback_resolve(const LookArgs &k, long long Aq, const Rec *lb, int lane) {
+    const int b = k.t >> 5, pos = k.t & 31;
+    const bool has_t = lane < pos, has_b = (b - 1 - lane) >= 0;
+    const bool block_last = pos == 31;
+    bool ba_done = false;
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
-    unsigned incl[kLbWin], none[kLbWin];
-    long long val[kLbWin];
+    Rec rt = lb[lane], rb = lb[32 + lane];                         // first attempt: the prefetched copies
+    while (true) {
+        const uint32_t ft = has_t ? rt.flag : 1u;
+        const uint32_t fb = has_b ? rb.flag : 2u;                  // blocks before the row start: inclusive prefix 0
+        const unsigned t_none = __ballot_sync(0xffffffffu, ft == 0u);
+        const unsigned b_incl = __ballot_sync(0xffffffffu, fb == 2u);
+        const unsigned b_none = __ballot_sync(0xffffffffu, fb == 0u);
+        const int f = b_incl ? (__ffs(b_incl) - 1) : 32;
+        const unsigned need = (f >= 31) ? 0xffffffffu : ((1u << (f + 1)) - 1u);
+        if (t_none == 0u) {
+            long long xt = has_t ? (long long)rt.v : 0;
+            if (block_last && !ba_done) {                           // block aggregate: unblocks later blocks early
+                long long s = xt;
 #pragma unroll
-    for (int q = 0; q < kLbWin; ++q) {
-        const int64_t idx = t - 1 - (32 * q + lane);
-        const Rec r = lb[32 * q + lane];
-        const uint32_t fl = idx >= 0 ? r.flag : 2u;                 // tiles before the row start: inclusive prefix 0
-        val[q] = idx >= 0 ? (long long)r.v : 0;
-        incl[q] = __ballot_sync(0xffffffffu, fl == 2u);
-        none[q] = __ballot_sync(0xffffffffu, fl == 0u);
-    }
-    long long x = 0;
-    bool found = false, ok = true;
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) rec_store(k.blocks + b, (unsigned long long)(s + Aq), 1u);
+                ba_done = true;
+            }
+            if (f < 32 && (b_none & need) == 0u) {
+                long long x = xt + ((has_b && lane <= f) ? (long long)rb.v : 0);
 #pragma unroll
-    for (int q = 0; q < kLbWin; ++q) {
-        if (!found && ok) {
-            const int f = incl[q] ? (__ffs(incl[q]) - 1) : 32;
-            const unsigned need = (f >= 31) ? 0xffffffffu : ((1u << (f + 1)) - 1u);
-            if (none[q] & need) ok = false;                         // a nearer tile had not published yet
-            else { if (lane <= f) x += val[q]; found = f < 32; }
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                if (block_last && lane == 0) rec_store(k.blocks + b, (unsigned long long)(x + Aq), 2u);
+                return x;
+            }
         }
+#ifdef DME_TIMERS
+        if (lane == 0) atomicAdd(&g_polls, 1ull);
+#endif
+        __nanosleep(32);
+        if (has_t) rt.flag = rec_load(k.tiles + (k.t - 1 - lane), rt.v);
+        if (has_b) rb.flag = rec_load(k.blocks + (b - 1 - lane), rb.v);
     }
-    if (!(found && ok)) return lookback_poll(rowdesc, t, lane);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    return x;
 }
 
 // ---- stage 2: look-back, prefix -> floor(c - X) (AS:635-637), type vector, emit
@@ -449,11 +463,10 @@ __device__ __forceinline__ void stage2(const StreamArgs &a, Scratch &sc, int slo
     const RowConst &rc = sc.rc[slot];
     const TileRec *rowdesc = a.desc + (int64_t)st.c * a.T;
     if (warp == 0) {
-        long long P = 0;
-        if (st.t > 0) {
-            P = lookback_resolve(rowdesc, st.t, sc.lb, lane);
-            if (lane == 0) rec_store(a.desc + (int64_t)st.c * a.T + st.t, (unsigned long long)(P + st.Aq), 2u);
-        }
+        const LookArgs la{rowdesc, a.blocks + (int64_t)st.c * a.TB, st.t};
+        TIC(a, 4);
+        const long long P = lookback_resolve(la, st.Aq, sc.lb, lane);
+        TOC(a, 4);
         if (lane == 0) { sc.Pq[slot] = P; sc.P[slot] = __ll2double_rn(P) * rc.q_dn; }
     }
     __syncthreads();
@@ -601,8 +614,8 @@ quantize_stream_kernel(StreamArgs a) {
     int64_t jn = 0;                      // local index of the next item to fetch
     uint32_t parity_bits = 0;            // phase parity of each ring slot
 
-    auto issue = [&](int64_t j) {        // thread 0: decode local item j, start its bulk copy (if it has data)
-        const Item it = decode_item(a, g + j * a.G);
+    auto issue = [&](int64_t j) {        // producer thread: decode local item j, start its bulk copy (if it has data)
+        const Item it = decoder_next(sc.dec, a);
         const int b = (int)(j % kRing);
         sc.items[b] = it;
         if (it.valid && it.copied > 0) {
@@ -612,7 +625,8 @@ quantize_stream_kernel(StreamArgs a) {
                      it.is_b ? pol_b : pol_a);
         }
     };
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == kProducer) {
+        decoder_init(sc.dec, a, g);
         for (int64_t j = 0; j < kAhead; ++j) issue(j);
     }
     __syncthreads();
@@ -620,7 +634,7 @@ quantize_stream_kernel(StreamArgs a) {
     auto fetch = [&](Item &it, const float *&buf) -> bool {
         const int64_t j = jn++;
         if (g + j * a.G >= a.total_items) return false;
-        if (threadIdx.x == 0) issue(j + kAhead);
+        if (threadIdx.x == kProducer) issue(j + kAhead);
         const int b = (int)(j % kRing);
         it = sc.items[b];
         buf = reinterpret_cast<const float *>(dyn_smem + (size_t)b * kTile * 4);
@@ -645,20 +659,20 @@ quantize_stream_kernel(StreamArgs a) {
         // ---- pass-B tile into state 0 (an A item may come first)
         if (!fetch(it, buf)) break;
         if (!it.is_b) { TIC(a, 1); pass_a(a, it, buf, sc); TOC(a, 1); if (!fetch(it, buf)) break; }
-        if (s1.live) lookback_prefetch(a.desc + (int64_t)s1.c * a.T, s1.t, sc.lb);
+        if (s1.live) lookback_prefetch(LookArgs{a.desc + (int64_t)s1.c * a.T, a.blocks + (int64_t)s1.c * a.TB, s1.t}, sc.lb);
         TIC(a, 2); stage1<EMIT>(a, it, buf, sc, 0, s0); TOC(a, 2);
         TIC(a, 3); stage2<EMIT>(a, sc, 1, s1); TOC(a, 3);
         // ---- pass-B tile into state 1
         if (!fetch(it, buf)) break;
         if (!it.is_b) { TIC(a, 1); pass_a(a, it, buf, sc); TOC(a, 1); if (!fetch(it, buf)) break; }
-        if (s0.live) lookback_prefetch(a.desc + (int64_t)s0.c * a.T, s0.t, sc.lb);
+        if (s0.live) lookback_prefetch(LookArgs{a.desc + (int64_t)s0.c * a.T, a.blocks + (int64_t)s0.c * a.TB, s0.t}, sc.lb);
         TIC(a, 2); stage1<EMIT>(a, it, buf, sc, 1, s1); TOC(a, 2);
         TIC(a, 3); stage2<EMIT>(a, sc, 0, s0); TOC(a, 3);
     }
     // drain: the last parked tiles (their look-back falls back to polling when nothing was prefetched)
-    if (s0.live) lookback_prefetch(a.desc + (int64_t)s0.c * a.T, s0.t, sc.lb);
+    if (s0.live) lookback_prefetch(LookArgs{a.desc + (int64_t)s0.c * a.T, a.blocks + (int64_t)s0.c * a.TB, s0.t}, sc.lb);
     stage2<EMIT>(a, sc, 0, s0);
-    if (s1.live) lookback_prefetch(a.desc + (int64_t)s1.c * a.T, s1.t, sc.lb);
+    if (s1.live) lookback_prefetch(LookArgs{a.desc + (int64_t)s1.c * a.T, a.blocks + (int64_t)s1.c * a.TB, s1.t}, sc.lb);
     stage2<EMIT>(a, sc, 1, s1);
 #else
     // half-pipelined variant: one tile state in registers; the pass-A item that follows a pass-B tile (items
@@ -670,7 +684,7 @@ quantize_stream_kernel(StreamArgs a) {
         if (!fetch(it, buf)) break;
         if (!it.is_b) { TIC(a, 1); pass_a(a, it, buf, sc); TOC(a, 1); continue; }
         TIC(a, 2); stage1<EMIT>(a, it, buf, sc, 0, s0); TOC(a, 2);
-        if (s0.live) lookback_prefetch(a.desc + (int64_t)s0.c * a.T, s0.t, sc.lb);
+        if (s0.live) lookback_prefetch(LookArgs{a.desc + (int64_t)s0.c * a.T, a.blocks + (int64_t)s0.c * a.TB, s0.t}, sc.lb);
         const bool more = fetch(it, buf);
         if (more && !it.is_b) { TIC(a, 1); pass_a(a, it, buf, sc); TOC(a, 1); }
         TIC(a, 3); stage2<EMIT>(a, sc, 0, s0); TOC(a, 3);
@@ -683,6 +697,9 @@ quantize_stream_kernel(StreamArgs a) {
 #endif
     if ((a.dbg & 32) && threadIdx.x == 0) {
         sc.tacc[6] += gtime();
+#ifdef DME_TIMERS
+        if (blockIdx.x == 0) { sc.tacc[5] = g_polls; g_polls = 0; }
+#endif
         for (int q = 0; q < 8; ++q) atomicAdd(reinterpret_cast<unsigned long long *>(a.hdr->pad + 1) + q, sc.tacc[q]);
     }
 }
@@ -697,7 +714,9 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
     StreamArgs a;
     a.X = X; a.d = d; a.ld = ld; a.T = L.T; a.n = n; a.m = m;
     a.consts = (RowConst *)(base + L.off_consts);
-    a.desc = (TileRec *)(base + L.off_desc);
+    a.desc = (TileRec *)(base + L.off_desc);                       // tile records: first 16 bytes per tile of the region
+    a.TB = (L.T + 31) / 32;                                        // blocks of 32 tiles per row
+    a.blocks = (Rec *)(base + L.off_desc + 16 * n * L.T);         // block records: in the second half of the region
     a.hdr = (WsHeader *)base;
     a.partial = (Rec *)(base + L.off_partial);
     a.row_ready = (uint32_t *)(base + L.off_ready);

@@ -478,19 +478,14 @@ __device__ __forceinline__ void stage2(const StreamArgs &a, Scratch &sc, int slo
     int aprev = __float2int_rd(__fsub_rn(__double2float_rn(E), rc.X));       // floor(c_{first-1} - X); c_0 = 0 (AS:635)
     int av[kEpt];
     {
-        // local prefixes in four independent groups of four (instruction-level parallelism), then the group offsets
-        double lp[kEpt];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            lp[4 * g] = (double)st.fr[4 * g];
-#pragma unroll
-            for (int e = 1; e < 4; ++e) lp[4 * g + e] = lp[4 * g + e - 1] + (double)st.fr[4 * g + e];
-        }
-        double off[4];
-        off[0] = 0.0; off[1] = lp[3]; off[2] = lp[3] + lp[7]; off[3] = (lp[3] + lp[7]) + lp[11];
+        // running prefix, left to right inside the thread's four groups of four exactly as stage 1 summed them:
+        // C_j = E + (group offset + in-group prefix), so the thread's last prefix equals E + S bit for bit
+        double off = 0.0, grp = 0.0;
 #pragma unroll
         for (int j = 0; j < kEpt; ++j) {
-            double C = (j < 4) ? (E + lp[j]) : (E + (off[j >> 2] + lp[j]));
+            grp = (j & 3) ? grp + (double)st.fr[j] : (double)st.fr[j];
+            double C = (j < 4) ? (E + grp) : (E + (off + grp));
+            if ((j & 3) == 3) off = (j == 3) ? grp : off + grp;
             if (j == kEpt - 1 && lane == 31) C = Pd + st.end;
             if (j == kEpt - 1 && threadIdx.x == kThreads - 1) C = __ll2double_rn(sc.Pq[slot] + st.Aq) * rc.q_dn;
             av[j] = __float2int_rd(__fsub_rn(__double2float_rn(C), rc.X));   // AS:636
@@ -525,15 +520,14 @@ __device__ __forceinline__ void stage2(const StreamArgs &a, Scratch &sc, int slo
     } else {
         // type vector in place of av: k_j = floor + [floor(c_j - X) - floor(c_{j-1} - X) == 1]
         int kmax = 0;
-        uint32_t kbits = 0;
+        uint32_t kbits = 0;                 // bit j = k_j when every k_j <= 1 (the only case the 2-bit path is taken)
 #pragma unroll
-        for (int j = 0; j < kEpt; ++j) {
-            const int cur = av[j];
-            const int k = (int)st.fl[j] + ((cur - aprev == 1) ? 1 : 0);
-            aprev = cur;
-            av[j] = k;
+        for (int j = kEpt - 1; j >= 0; --j) {
+            const int prev = (j == 0) ? aprev : av[j - 1];
+            const int k = (int)st.fl[j] + ((av[j] - prev == 1) ? 1 : 0);
+            av[j] = k;                      // av[j-1] is still the floor value when it is read in the next iteration
             kmax = max(kmax, k);
-            kbits |= (uint32_t)(k & 1) << j;
+            kbits = kbits * 2u + (uint32_t)k;
         }
         // tile-wide minimal field width
         kmax = __reduce_max_sync(0xffffffffu, kmax);

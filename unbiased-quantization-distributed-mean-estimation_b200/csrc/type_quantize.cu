@@ -274,7 +274,7 @@ int ws_prepare(void *ws, int64_t ws_bytes, int64_t n, int64_t d, cudaStream_t st
     char *base = (char *)ws;
     DME_CUDA(cudaMemsetAsync(base, 0, (size_t)L.zero_bytes, st));
     if (need_desc) {
-        DME_CUDA(cudaMemsetAsync(base + L.off_desc, 0, 32 * (size_t)(n * L.T), st));
+        DME_CUDA(cudaMemsetAsync(base + L.off_desc, 0, (size_t)L.desc_bytes, st));
         DME_CUDA(cudaMemsetAsync(base + L.off_partial, 0, 16 * (size_t)(n * L.T), st));
     }
     if (need_sel) DME_CUDA(cudaMemsetAsync(base + L.off_sel, 0, sizeof(RowSelect) * (size_t)n, st));

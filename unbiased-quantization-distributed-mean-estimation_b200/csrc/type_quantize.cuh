@@ -40,14 +40,21 @@ struct __align__(256) WsHeader {
     uint32_t pad[59];
 };
 
+// Closed form of AS:636 inside one binade of the fp32 prefix (stream.cu): for c32 in [2^e + 1, 2^(e+1)),
+// floor(RN32(RN32(c) - X)) = floor(c - Xp) when sigma = +1, ceil(c - Xp) - 1 when sigma = -1; sigma = 0: no closed form.
+struct __align__(16) BinadeEntry { double Xp; double sigma; };
+constexpr int kBinades = 24;
+
 struct WsLayout {
     int64_t T;            // tiles per row
     int64_t off_done;     // uint32 a_done[n]
     int64_t off_ready;    // uint32 row_ready[n]
     int64_t off_consts;   // RowConst consts[n]
     int64_t off_partial;  // double partial[n*T]
-    int64_t off_desc;     // TileDesc desc[n*T]
+    int64_t off_desc;     // look-back records: 16 bytes per tile, per block of 32 tiles, per super-block of 1024 tiles
+    int64_t desc_bytes;
     int64_t off_sel;      // RowSelect sel[n] (biased mode)
+    int64_t off_tab;      // BinadeEntry tab[n][kBinades] (unbiased stream kernel: closed-form floor(c - X) per binade)
     int64_t zero_bytes;   // prefix that must be zeroed before each call (header + a_done)
     int64_t total;
 };
@@ -85,8 +92,13 @@ inline WsLayout ws_layout(int64_t n, int64_t d) {
     L.zero_bytes = o;
     L.off_consts = o; o = align_up(o + (int64_t)sizeof(RowConst) * n, 256);
     L.off_partial = o; o = align_up(o + 16 * n * L.T, 256);     // 16-byte {sum, flag} records
-    L.off_desc = o; o = align_up(o + (int64_t)sizeof(TileDesc) * n * L.T, 256);
+    {
+        const int64_t TB = (L.T + 31) / 32, TS = (TB + 31) / 32;
+        L.desc_bytes = 16 * n * (L.T + TB + TS);
+    }
+    L.off_desc = o; o = align_up(o + L.desc_bytes, 256);
     L.off_sel = o; o = align_up(o + (int64_t)sizeof(RowSelect) * n, 256);
+    L.off_tab = o; o = align_up(o + (int64_t)sizeof(BinadeEntry) * kBinades * n, 256);
     L.total = o;
     return L;
 }

@@ -32,7 +32,8 @@ for n, d in shapes:
         ws = dme.Workspace.get(X.device).buf
         off = (-ws.data_ptr()) % 256
         hdr = ws[off: off + 256].cpu().numpy().view("uint64")
-        names = ["tma wait", "pass A", "stage 1", "stage 2", "resolve (in stage 2)", "polls", "cta lifetime"]
+        names = ["c:tma wait", "c:pass A", "c:stage 1", "c:stage 2", "c:READY wait (in stage 2)", "-", "cta lifetime", "polls",
+                 "s:B1 wait", "s:sums+publish", "s:finish try", "s:scan", "s:issue B", "s:PA wait", "s:finish block", "-"]
         pairs = n * ((d + 4095) // 4096)
-        print("   per tile pair, ns of thread 0 (summed over CTAs / pairs):", {nm: round(float(hdr[3 + q]) / pairs, 2) for q, nm in enumerate(names)})
+        print("   per tile pair, ns:", {nm: round(float(hdr[3 + q]) / pairs, 1) for q, nm in enumerate(names) if nm != "-"})
     del X

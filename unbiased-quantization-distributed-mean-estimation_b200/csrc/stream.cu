@@ -43,7 +43,8 @@
 
 namespace dme {
 
-constexpr int kRing = 2;                 // TMA ring depth (item j uses slot j & 1; refilled after the barrier of item j)
+constexpr int kRing = 3;                 // TMA ring depth (item j uses slot j % 3; refilled after the barrier of item j)
+constexpr int kParkBytes = kThreads * 16;   // parked floors of a pass-B tile: one byte per coordinate
 constexpr int kBlock = kThreads + 32;    // 8 compute warps + 1 service warp
 
 struct __align__(16) Rec { unsigned long long v; uint32_t flag; uint32_t pad; };
@@ -82,6 +83,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -136,9 +147,14 @@ __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
 
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #ifdef DME_TIMERS
-#define TIC(k) do { if ((a.dbg & 32) && threadIdx.x == (k >= 4 ? kThreads : 0)) sc.tacc[k] -= gtime(); } while (0)
-#define TOC(k) do { if ((a.dbg & 32) && threadIdx.x == (k >= 4 ? kThreads : 0)) sc.tacc[k] += gtime(); } while (0)
+__device__ unsigned long long g_trace[8192];      // development: event timeline of one CTA (DME_DBG bit 6)
+__device__ unsigned int g_trace_n;
+#define TRACE(code, val) do { if ((((a.dbg & 64) && blockIdx.x == 100) || ((a.dbg & 128) && (code == 11 || code == 12 || code == 3) && blockIdx.x >= 96 && blockIdx.x < 160)) && (threadIdx.x == 0 || threadIdx.x == kThreads)) { \
+        const unsigned int _i = atomicAdd(&g_trace_n, 1u); if (_i < 4096) { g_trace[2 * _i] = gtime(); g_trace[2 * _i + 1] = ((unsigned long long)(code) << 32) | ((unsigned long long)(blockIdx.x & 0xfff) << 20) | ((unsigned int)(val) & 0xfffff); } } } while (0)
+#define TIC(k) do { if ((a.dbg & 32) && threadIdx.x == (k >= 8 ? kThreads : 0)) sc.tacc[k] -= gtime(); } while (0)
+#define TOC(k) do { if ((a.dbg & 32) && threadIdx.x == (k >= 8 ? kThreads : 0)) sc.tacc[k] += gtime(); } while (0)
 #else
+#define TRACE(code, val) do { } while (0)
 #define TIC(k) do { } while (0)
 #define TOC(k) do { } while (0)
 #endif
@@ -150,6 +166,7 @@ struct StreamArgs {
     const float *x_inject; const float *l1_inject; uint64_t seed, client0; float *l1_out;
     int64_t lag, goff, total_items, G;
     int step_c, step_t;                    // G = step_c * T + step_t: per-item advance of (client, tile) without a division
+    int total_items32, tiles_tma, has_tail;
     int32_t *k_out; uint8_t *sgn_out; float *deq_out; int64_t ld_out;     // array outputs
     PackTarget pack; int packed;                                        // packed output
     int dbg;                                                            // development: bit 5 = phase timers
@@ -166,56 +183,61 @@ __device__ __forceinline__ void floor_divmod(long long s, long long T, int &c, i
 // Item decoder (service warp, lane-uniform): the CTA's items advance by G in the global order, i.e. by G positions in
 // the A stream and in the B stream alternately, so (client, tile) pairs are updated without divisions.
 struct Decoder {
-    long long i; int cA, tA, cB, tB, cF, tF;
+    int i; int cA, tA, cB, tB, cF, tF;
     __device__ __forceinline__ void init(const StreamArgs &a, long long g) {
-        i = g;
+        i = (int)g;
         const long long firstA = (g & 1) ? g + a.G : g, firstB = (g & 1) ? g : g + a.G;
         floor_divmod(firstA >> 1, a.T, cA, tA);
         floor_divmod((firstA >> 1) - a.goff, a.T, cF, tF);
         floor_divmod((firstB >> 1) - a.lag, a.T, cB, tB);
     }
-    __device__ __forceinline__ static void advance(int &c, int &t, const StreamArgs &a) {
-        c += a.step_c; t += a.step_t;
-        if (t >= (int)a.T) { t -= (int)a.T; ++c; }
+    __device__ __forceinline__ static void advance(int &c, int &t, int sc_, int st_, int T) {
+        c += sc_; t += st_;
+        if (t >= T) { t -= T; ++c; }
     }
     __device__ __forceinline__ Item next(const StreamArgs &a) {
+        const int T = (int)a.T, n = (int)a.n;
         Item it; it.c = 0; it.t = 0; it.fin_row = -1;
         const bool is_b = (i & 1) != 0;
         it.flags = is_b ? kItB : 0u;
-        if (i >= a.total_items) { it.flags |= kItEnd; return it; }
-        i += a.G;
+        if (i >= a.total_items32) { it.flags |= kItEnd; return it; }
+        i += (int)a.G;
         int c, t;
         if (!is_b) {
             c = cA; t = tA;
-            if (tF == 0 && cF >= 1 && cF - 1 < a.n) it.fin_row = cF - 1;     // finaliser duty of this position
-            advance(cA, tA, a);
-            advance(cF, tF, a);
+            if (tF == 0 && cF >= 1 && cF <= n) it.fin_row = cF - 1;           // finaliser duty of this position
+            advance(cA, tA, a.step_c, a.step_t, T);
+            advance(cF, tF, a.step_c, a.step_t, T);
         } else {
             c = cB; t = tB;
-            advance(cB, tB, a);
+            advance(cB, tB, a.step_c, a.step_t, T);
         }
-        if (c < 0 || c >= a.n) return it;
+        if ((unsigned)c >= (unsigned)n) return it;
         it.c = c; it.t = t;
-        it.flags |= kItValid;
-        if ((int64_t)t * (kTile / 32) < a.rows32) it.flags |= kItTma;             // at least one full row in this tile
-        if (t == a.T - 1 && (a.d & 31)) it.flags |= kItTail;                      // d % 32 coordinates come straight from global
+        uint32_t f = it.flags | kItValid;
+        if (t < a.tiles_tma) f |= kItTma;                                     // at least one full 128-byte row in this tile
+        if (t == T - 1 && a.has_tail) f |= kItTail;                           // d % 32 coordinates come straight from global
+        it.flags = f;
         return it;
     }
 };
 
-constexpr int kScanPad = kThreads + kThreads / 8 + 8;     // index t + (t >> 3): conflict-free for lane-strided-by-8 access
-__device__ __forceinline__ int spad(int t) { return t + (t >> 3); }
 struct TileInfo {            // what stage 2 needs about a pass-B tile (written by the service warp), by tile parity
     double P;                // exclusive prefix of the tile
     double EnLast;           // inclusive prefix at the last coordinate of the tile (from the fixed-point values)
     float flmax;             // largest floor in the tile
     int rcslot;
+    int Wlo, Whi;            // field width needed for the largest floor / the largest floor + 1
+    int pad[2];
 };
 // Thread sums (stage 1 of a pass-B tile, pass A) travel to the service warp through the tile's own ring slot: every
 // thread overwrites 8 of the 64 bytes only it has read, and the slot is refilled by the service warp after it has
 // consumed them.
 struct Scratch {
-    double scanE[2][kScanPad];     // in-tile exclusive prefixes (entry kThreads = tile total), by tile parity
+    double scanI[2][kThreads];     // inclusive prefix of the thread sums inside each warp (thread-private entries), by tile parity
+    double wtot[2][kWarps];        // warp totals of a pass-B tile (stage 1 -> service warp), by tile parity
+    double wbase[2][kWarps + 1];   // in-tile exclusive prefixes of the warps (+ tile total) (service warp -> stage 2)
+    double wsumA[2][kWarps];       // warp sums of a pass-A tile, by parity
     double red[kWarps];            // finalize_row
     uint32_t flmaxw[2][kWarps];    // per-warp max floor (float bits), by tile parity
     TileInfo info[2];
@@ -224,8 +246,9 @@ struct Scratch {
     int rc_row[4];
     unsigned long long off16;      // arena offset of a wide tile (compute warps)
     Item items[kRing];
-    uint64_t mbar[kRing];
-    unsigned long long tacc[8];    // phase timers (dbg)
+    uint64_t mbar[kRing];          // ring slots: copy complete + row constants present
+    uint64_t b1bar[2];             // stage-1 data of a pass-B tile complete (256 arrivals), by tile parity
+    unsigned long long tacc[16];   // phase timers (dbg): 0-7 compute thread 0, 8-15 service lane 0
 };
 
 // Row constants + the binade table of AS:636's closed form (cold: once per client row).
@@ -332,6 +355,11 @@ __device__ __forceinline__ uint32_t blocked_off_of(uint32_t tid) {
 }
 __device__ __forceinline__ uint32_t blocked_off() { return blocked_off_of(threadIdx.x); }
 
+// |x| of the row's coordinate rows32 * 32 + tid when it exists (the d % 32 coordinates the tensor map does not cover)
+__device__ __noinline__ double row_tail_abs(const StreamArgs &a, int c) {
+    if (threadIdx.x >= (uint32_t)(a.d & 31)) return 0.0;
+    return (double)fabsf(a.X[(int64_t)c * a.ld + a.rows32 * 32 + threadIdx.x]);
+}
 // ---- pass A of one tile: the thread sums go to shared memory, the service warp finishes them
 __device__ __forceinline__ void pass_a(const StreamArgs &a, const Item &it, uint32_t buf, Scratch &sc, int parity) {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -343,42 +371,18 @@ __device__ __forceinline__ void pass_a(const StreamArgs &a, const Item &it, uint
             s0 += (double)fabsf(v.x); s1 += (double)fabsf(v.y); s2 += (double)fabsf(v.z); s3 += (double)fabsf(v.w);
         }
     }
-    if ((it.flags & kItTail) && threadIdx.x < 32) {
-        const int64_t i = a.rows32 * 32 + threadIdx.x;
-        if (i < a.d) s0 += (double)fabsf(a.X[(int64_t)it.c * a.ld + i]);
-    }
-    sts64(buf + threadIdx.x * 16u, (s0 + s1) + (s2 + s3));      // over the thread's own first chunk
+    if (it.flags & kItTail) s0 += row_tail_abs(a, it.c);
+    const double ws = warp_sum_f64((s0 + s1) + (s2 + s3));      // fixed association
+    if ((threadIdx.x & 31) == 0) sc.wsumA[parity][threadIdx.x >> 5] = ws;
     bar_arrive(kBarPA + parity, kBlock);
+    TRACE(4, it.t);
     if (it.fin_row >= 0) finalize_row(a, it.fin_row, sc);
 }
 
-// ---- stage 1: everything that does not need the prefix of earlier tiles
-template <int EMIT>
-__device__ __forceinline__ void stage1(const StreamArgs &a, const Item &it, uint32_t buf, uint32_t park, const RowConst &rc, Scratch &sc, BState &st,
-                                       int parity) {
-    st.flags = it.flags; st.c = it.c; st.t = it.t;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t off = blocked_off();
-    float x[kEpt];
-    if (it.flags & kItTma) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 v = lds128((buf + off) ^ (uint32_t)(q << 4));
-            x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < kEpt; ++j) x[j] = 0.0f;
-    }
-    if (it.flags & kItTail) {          // the last d % 32 coordinates of the row are not covered by the tensor map
-        const int64_t i0 = (int64_t)it.t * kTile + (int64_t)threadIdx.x * kEpt, lo = a.rows32 * 32;
-        const float *row = a.X + (int64_t)it.c * a.ld;
-        if (i0 + kEpt > lo && i0 < a.d) {
-#pragma unroll
-            for (int j = 0; j < kEpt; ++j)
-                if (i0 + j >= lo && i0 + j < a.d) x[j] = row[i0 + j];
-        }
-    }
+// AS:625-631 for the thread's 16 coordinates: floors and fractional parts of m |x| / D.  The fast chain (pairs of |x|:
+// x/D by Markstein's correction of x * rcp, floor by adding 2^23 toward zero) and the literal one (rows / threads outside
+// the proven operand range) give the same values.  `big` is decided per thread from its largest |x|.
+__device__ __forceinline__ void floors_and_fracs(const float (&x)[kEpt], const RowConst &rc, float (&flf)[kEpt], float (&fr)[kEpt]) {
     const bool exact = rc.flags & kRowExact;
     bool big = false;
     if (!exact && (rc.flags & kRowGuardFloor)) {
@@ -388,17 +392,11 @@ __device__ __forceinline__ void stage1(const StreamArgs &a, const Item &it, uint
         for (int j = 0; j < kEpt; ++j) mx = fmaxf(mx, fabsf(x[j]));
         big = !(__fmul_rn(rc.mf, __fmul_rn(mx, rc.rcpD)) < 4194304.0f);
     }
-    uint32_t sg = 0;
-#pragma unroll
-    for (int j = kEpt - 1; j >= 0; --j) sg = __funnelshift_l(__float_as_uint(x[j]), sg, 2);     // bit 2j+1 = sign of x[j]
-    st.sgw = sg;
-    float flf[kEpt];
     if (exact || big) {
 #pragma unroll
-        for (int j = 0; j < kEpt; ++j) chain_exact(x[j], rc, flf[j], st.fr[j]);
+        for (int j = 0; j < kEpt; ++j) chain_exact(x[j], rc, flf[j], fr[j]);
     } else {
 #if DME_X2
-        // fast chain on pairs of |x|: x/D by Markstein's correction of x * rcp, floor by adding 2^23 toward zero
         const f2 R2 = f2_pack(rc.rcpD, rc.rcpD), ND = f2_pack(-rc.D, -rc.D), M2 = f2_pack(rc.mf, rc.mf), C2 = f2_pack(8388608.0f, 8388608.0f);
 #pragma unroll
         for (int j = 0; j < kEpt; j += 2) {
@@ -411,7 +409,7 @@ __device__ __forceinline__ void stage1(const StreamArgs &a, const Item &it, uint
             const f2 fl2 = f2_sub(tt, C2);
             const f2 fr2 = f2_sub(mp, fl2);
             f2_unpack(fl2, flf[j], flf[j + 1]);
-            f2_unpack(fr2, st.fr[j], st.fr[j + 1]);
+            f2_unpack(fr2, fr[j], fr[j + 1]);
         }
 #else
 #pragma unroll
@@ -423,13 +421,61 @@ __device__ __forceinline__ void stage1(const StreamArgs &a, const Item &it, uint
             const float mp = __fmul_rn(rc.mf, pq);
             const float tt = __fadd_rz(mp, 8388608.0f);
             flf[j] = __fsub_rn(tt, 8388608.0f);
-            st.fr[j] = __fsub_rn(mp, flf[j]);
+            fr[j] = __fsub_rn(mp, flf[j]);
         }
 #endif
     }
-    // park the floors (thread-private 64 bytes of the park buffer)
+}
+// the tile's coordinates owned by this thread, from the staged tile (+ the row tail straight from global)
+__device__ __forceinline__ void load_x(const StreamArgs &a, uint32_t flags, int c, int t, uint32_t buf, float (&x)[kEpt]) {
+    const uint32_t off = blocked_off();
+    if (flags & kItTma) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) sts128((park + off) ^ (uint32_t)(q << 4), make_float4(flf[4 * q], flf[4 * q + 1], flf[4 * q + 2], flf[4 * q + 3]));
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = lds128((buf + off) ^ (uint32_t)(q << 4));
+            x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) x[j] = 0.0f;
+    }
+    if (flags & kItTail) {          // the last d % 32 coordinates of the row are not covered by the tensor map
+        const int64_t i0 = (int64_t)t * kTile + (int64_t)threadIdx.x * kEpt, lo = a.rows32 * 32;
+        const float *row = a.X + (int64_t)c * a.ld;
+        if (i0 + kEpt > lo && i0 < a.d) {
+#pragma unroll
+            for (int j = 0; j < kEpt; ++j)
+                if (i0 + j >= lo && i0 + j < a.d) x[j] = row[i0 + j];
+        }
+    }
+}
+
+// ---- stage 1: everything that does not need the prefix of earlier tiles
+template <int EMIT>
+__device__ __forceinline__ void stage1(const StreamArgs &a, const Item &it, uint32_t buf, uint32_t park, const RowConst &rc, Scratch &sc, BState &st,
+                                       int parity) {
+    st.flags = it.flags; st.c = it.c; st.t = it.t;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float x[kEpt];
+    load_x(a, it.flags, it.c, it.t, buf, x);
+    uint32_t sg = 0;
+#pragma unroll
+    for (int j = kEpt - 1; j >= 0; --j) sg = __funnelshift_l(__float_as_uint(x[j]), sg, 2);     // bit 2j+1 = sign of x[j]
+    st.sgw = sg;
+    float flf[kEpt];
+    floors_and_fracs(x, rc, flf, st.fr);
+    // park the floors as bytes (only meaningful while the tile's largest floor is below 256: wider tiles recompute
+    // them in stage 2); floor + 2^23 carries the integer in its low mantissa bits
+    {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t b0 = __float_as_uint(__fadd_rn(flf[4 * q], 8388608.0f)), b1 = __float_as_uint(__fadd_rn(flf[4 * q + 1], 8388608.0f));
+            const uint32_t b2 = __float_as_uint(__fadd_rn(flf[4 * q + 2], 8388608.0f)), b3 = __float_as_uint(__fadd_rn(flf[4 * q + 3], 8388608.0f));
+            w[q] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+        }
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(park + threadIdx.x * 16u), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+    }
     if (EMIT == 0) {
         uint32_t z = 0;
 #pragma unroll
@@ -444,10 +490,19 @@ __device__ __forceinline__ void stage1(const StreamArgs &a, const Item &it, uint
     double run = (double)st.fr[0];
 #pragma unroll
     for (int j = 1; j < kEpt; ++j) run += (double)st.fr[j];
-    sts64((buf + off) ^ (((threadIdx.x >> 4) & 3u) << 4), run);                      // over one of the thread's own chunks
+    // inclusive scan of the thread sums inside the warp (Kogge-Stone, fixed association); warp total to the service warp
+    double incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    sc.scanI[parity][threadIdx.x] = incl;
+    if (lane == 31) sc.wtot[parity][warp] = incl;
     const uint32_t wmx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));     // floors are >= 0: bit order = value order
     if (lane == 0) sc.flmaxw[parity][warp] = wmx;
-    bar_arrive(kBarB1 + parity, kBlock);
+    mbar_arrive(&sc.b1bar[parity]);
+    TRACE(3, it.t);
 }
 
 // AS:636 literally, for one prefix value
@@ -487,33 +542,6 @@ __device__ __forceinline__ Geo make_geo(const BinadeEntry *tab, double E, double
     return g;
 }
 
-// r_j = [floor(c_j - X) - floor(c_{j-1} - X) == 1] (AS:636-637) for the thread's 16 coordinates, as a bit mask
-__device__ __forceinline__ uint32_t rbits_generic(const Geo &g, const BState &st, float X) {
-    uint32_t rb = 0;
-    if (g.fast) {
-        const int sgi = g.sig > 0.0 ? 1 : -1;
-        double u = g.sE;
-        int Lp = floor_lo(u);
-#pragma unroll
-        for (int j = 0; j < kEpt; ++j) {
-            u = (j < kEpt - 1) ? fma(frac_to_double(st.fr[j]), g.sig, u) : g.sEn;
-            const int L = floor_lo(u);
-            rb |= (((L - Lp) * sgi == 1) ? 1u : 0u) << j;
-            Lp = L;
-        }
-    } else {
-        double c = g.E;
-        int tp = floor_ref(c, X);
-#pragma unroll
-        for (int j = 0; j < kEpt; ++j) {
-            c = (j < kEpt - 1) ? c + (double)st.fr[j] : g.En;
-            const int t = floor_ref(c, X);
-            rb |= ((t - tp == 1) ? 1u : 0u) << j;
-            tp = t;
-        }
-    }
-    return rb;
-}
 __device__ __forceinline__ uint32_t spread16(uint32_t v) {       // bit j -> bit 2j
     v = (v | (v << 8)) & 0x00ff00ffu;
     v = (v | (v << 4)) & 0x0f0f0f0fu;
@@ -521,7 +549,8 @@ __device__ __forceinline__ uint32_t spread16(uint32_t v) {       // bit j -> bit
     v = (v | (v << 1)) & 0x55555555u;
     return v;
 }
-// the same as 2-bit interleaved fields (bit 2j = r_j): the differences telescope into one IMAD per coordinate
+// r_j = [floor(c_j - X) - floor(c_{j-1} - X) == 1] (AS:636-637) for the thread's 16 coordinates as 2-bit interleaved
+// fields (bit 2j = r_j).  Closed form: the 0/1 differences telescope into one IMAD per coordinate.
 __device__ __forceinline__ uint32_t rbits_interleaved(const Geo &g, const BState &st, float X) {
     if (g.fast) {
         const int sgi = g.sig > 0.0 ? 1 : -1;
@@ -543,21 +572,84 @@ __device__ __forceinline__ uint32_t rbits_interleaved(const Geo &g, const BState
         if ((L15 - L14) * sgi == 1) acc |= 1u << 30;
         return acc;
     }
-    return spread16(rbits_generic(g, st, X));
+    uint32_t rb = 0;
+    double c = g.E;
+    int tp = floor_ref(c, X);
+#pragma unroll
+    for (int j = 0; j < kEpt; ++j) {
+        c = (j < kEpt - 1) ? c + (double)st.fr[j] : g.En;
+        const int t = floor_ref(c, X);
+        rb |= ((t - tp == 1) ? 1u : 0u) << j;
+        tp = t;
+    }
+    return spread16(rb);
 }
 
-// smallest field width whose magnitude part holds k
-__device__ __forceinline__ int width_for(float kmax) {
-    int W = 2;
-    while (W < 32 && kmax >= (float)(1u << (W - 1))) W <<= 1;
-    return W;
+// floors of the thread's coordinates in stage 2: the parked bytes, or -- tiles whose largest floor does not fit a
+// byte (heavy tails) -- recomputed from the row (same function of the same inputs as in stage 1)
+__device__ __noinline__ void reload_floors(const StreamArgs &a, int c, int t, const RowConst &rc, float (&fl)[kEpt]) {
+    float x[kEpt], fr[kEpt];
+    const int64_t i0 = (int64_t)t * kTile + (int64_t)threadIdx.x * kEpt;
+    const float *row = a.X + (int64_t)c * a.ld;
+#pragma unroll
+    for (int j = 0; j < kEpt; ++j) x[j] = (i0 + j < a.d) ? __ldcg(row + i0 + j) : 0.0f;
+    floors_and_fracs(x, rc, fl, fr);
+}
+__device__ __forceinline__ void load_floors(const StreamArgs &a, int c, int t, const RowConst &rc, uint32_t park, float fm, float (&fl)[kEpt]) {
+    if (fm < 256.0f) {
+        uint32_t w[4];
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(park + threadIdx.x * 16u));
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) fl[j] = (float)((w[j >> 2] >> (8 * (j & 3))) & 0xffu);
+    } else {
+        reload_floors(a, c, t, rc, fl);
+    }
+}
+// cold helpers of the packed emit (rare threads / wide tiles): kept out of line to keep the hot loop small
+// any coordinate whose floor equals the tile maximum and that received a unit?
+__device__ __noinline__ bool floors_hit(const StreamArgs &a, int c, int t, const RowConst &rc, uint32_t park, float fm, uint32_t kw) {
+    float fl[kEpt];
+    load_floors(a, c, t, rc, park, fm, fl);
+    bool hit = false;
+#pragma unroll
+    for (int j = 0; j < kEpt; ++j) hit |= (fl[j] == fm) && ((kw >> (2 * j)) & 1u);
+    return hit;
+}
+// bit 2j = floor_j != 0
+__device__ __noinline__ uint32_t floors_nonzero(const StreamArgs &a, int c, int t, const RowConst &rc, uint32_t park, float fm) {
+    float fl[kEpt];
+    load_floors(a, c, t, rc, park, fm, fl);
+    uint32_t kb = 0;
+#pragma unroll
+    for (int j = 0; j < kEpt; ++j) kb |= ((fl[j] != 0.0f) ? 1u : 0u) << (2 * j);
+    return kb;
+}
+// fields of 4 / 8 / 16 / 32 bits
+__device__ __noinline__ void emit_wide(const StreamArgs &a, int c, int t, uint32_t sgw, const RowConst &rc, uint32_t park, float fm, uint32_t kw, int W, uint32_t *tw) {
+    float fl[kEpt];
+    load_floors(a, c, t, rc, park, fm, fl);
+    uint32_t k[kEpt], sg[kEpt];
+#pragma unroll
+    for (int j = 0; j < kEpt; ++j) {
+        const float ff = fminf(fl[j], 2147483520.0f);       // overflow already reported
+        k[j] = (uint32_t)ff + ((kw >> (2 * j)) & 1u);
+        sg[j] = (sgw >> (2 * j + 1)) & 1u;
+    }
+    switch (W) {
+        case 4: pack_store<4>(k, sg, tw); break;
+        case 8: pack_store<8>(k, sg, tw); break;
+        case 16: pack_store<16>(k, sg, tw); break;
+        default: pack_store<32>(k, sg, tw); break;
+    }
 }
 
 // ---- stage 2: prefix -> floor(c - X) (AS:635-637), type vector, emit
 template <int EMIT>
 __device__ __forceinline__ void stage2(const StreamArgs &a, Scratch &sc, uint32_t park, BState &st, int parity) {
+    TRACE(5, st.t);
     bar_sync(kBarReady + parity, kBlock);                 // the service warp has resolved this tile's prefix
     if (!(st.flags & kItValid)) return;
+    TRACE(6, (int)sc.info[parity].flmax);
     st.flags = 0;
     const TileInfo &ti = sc.info[parity];
     const RowConst &rc = sc.rc[ti.rcslot];
@@ -565,25 +657,26 @@ __device__ __forceinline__ void stage2(const StreamArgs &a, Scratch &sc, uint32_
     // The prefix at a thread's LAST coordinate is defined from the scan values (at the last coordinate of the tile
     // from the fixed-point inclusive prefix), so the next thread / tile starts from exactly the same value and
     // derives the same floor(c - X) for its predecessor: no hand-off is needed.
-    const double E = Pd + sc.scanE[parity][spad(threadIdx.x)];
-    double En = Pd + sc.scanE[parity][spad(threadIdx.x + 1)];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double incl = sc.scanI[parity][threadIdx.x];
+    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 0.0;
+    const double Pw = Pd + sc.wbase[parity][warp];
+    const double E = Pw + excl;
+    double En = Pw + incl;
+    if (lane == 31) En = Pd + sc.wbase[parity][warp + 1];        // = the next warp's first prefix, bit for bit
     if (threadIdx.x == kThreads - 1) En = ti.EnLast;
     const Geo g = make_geo(sc.tab[ti.rcslot], E, En);
     const float fm = ti.flmax;
-    const uint32_t off = blocked_off();
-    const int64_t i0 = (int64_t)st.t * kTile + (int64_t)threadIdx.x * kEpt;
+    const uint32_t kw = rbits_interleaved(g, st, rc.X);
     if (EMIT == 0) {
-        const uint32_t rb = rbits_generic(g, st, rc.X);
+        const int64_t i0 = (int64_t)st.t * kTile + (int64_t)threadIdx.x * kEpt;
         float fl[kEpt];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 v = lds128((park + off) ^ (uint32_t)(q << 4));
-            fl[4 * q] = v.x; fl[4 * q + 1] = v.y; fl[4 * q + 2] = v.z; fl[4 * q + 3] = v.w;
-        }
+        load_floors(a, st.c, st.t, rc, park, fm, fl);
         bool ovf = false;
 #pragma unroll
         for (int j = 0; j < kEpt; ++j) {
-            const float kf = __fadd_rn(fl[j], (float)((rb >> j) & 1u));
+            const float kf = __fadd_rn(fl[j], (float)((kw >> (2 * j)) & 1u));
             const int64_t i = i0 + j;
             if (i >= a.d) continue;
             const uint32_t sbit = (st.sgw >> (2 * j + 1)) & 1u;
@@ -602,24 +695,12 @@ __device__ __forceinline__ void stage2(const StreamArgs &a, Scratch &sc, uint32_
     } else {
         // tile-wide minimal field width: from the largest floor; only when the largest floor sits right below a
         // width boundary does it matter whether one of those coordinates also received a unit
-        const int Wlo = width_for(fm), Whi = width_for(__fadd_rn(fm, 1.0f));
-        int W = Wlo;
-        uint32_t rb16 = 0;
-        const bool certain2 = (Whi == 2);
-        if (!certain2) {
-            rb16 = rbits_generic(g, st, rc.X);
-            if (Wlo != Whi) {
-                bool hit = false;
-                if (st.flmax_t == fm) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 v = lds128((park + off) ^ (uint32_t)(q << 4));
-                        hit |= (v.x == fm && ((rb16 >> (4 * q)) & 1u)) | (v.y == fm && ((rb16 >> (4 * q + 1)) & 1u)) |
-                               (v.z == fm && ((rb16 >> (4 * q + 2)) & 1u)) | (v.w == fm && ((rb16 >> (4 * q + 3)) & 1u));
-                    }
-                }
-                W = bar_or(kBarOr, kThreads, hit) ? Whi : Wlo;
-            }
+        int W = ti.Wlo;
+        const bool plain = (ti.Whi == 2);               // every floor is 0: k = r
+        if (!plain && ti.Wlo != ti.Whi) {
+            bool hit = false;
+            if (st.flmax_t == fm) hit = floors_hit(a, st.c, st.t, rc, park, fm, kw);
+            W = bar_or(kBarOr, kThreads, hit) ? ti.Whi : ti.Wlo;
         }
         if (fm >= 2147483520.0f && threadIdx.x == 0) atomicOr(&a.hdr->status, 1u);
         const int64_t slot_id = (int64_t)st.c * a.T + st.t;
@@ -643,42 +724,12 @@ __device__ __forceinline__ void stage2(const StreamArgs &a, Scratch &sc, uint32_
             uint32_t *tw = a.pack.codes + off16 * 4ull;
             if (W == 2) {
                 // fields [sign | magnitude bit]
-                uint32_t kw;
-                if (certain2) kw = rbits_interleaved(g, st, rc.X);
-                else {
-                    // largest floor is 1 and no such coordinate received a unit: k = floor + r is still <= 1
-                    uint32_t kb = rb16;
-                    if (st.flmax_t != 0.0f) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 v = lds128((park + off) ^ (uint32_t)(q << 4));
-                            kb |= ((v.x != 0.0f) ? 1u : 0u) << (4 * q) | ((v.y != 0.0f) ? 1u : 0u) << (4 * q + 1) |
-                                  ((v.z != 0.0f) ? 1u : 0u) << (4 * q + 2) | ((v.w != 0.0f) ? 1u : 0u) << (4 * q + 3);
-                        }
-                    }
-                    kw = spread16(kb);
-                }
-                tw[threadIdx.x] = kw | (st.sgw & 0xaaaaaaaau);
+                uint32_t kb = kw;
+                // largest floor is 1 and no such coordinate received a unit: k = floor + r is still <= 1
+                if (!plain && st.flmax_t != 0.0f) kb |= floors_nonzero(a, st.c, st.t, rc, park, fm);
+                tw[threadIdx.x] = kb | (st.sgw & 0xaaaaaaaau);
             } else {
-                uint32_t k[kEpt], sg[kEpt];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 v = lds128((park + off) ^ (uint32_t)(q << 4));
-                    const float f4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int j = 4 * q + e;
-                        const float ff = fminf(f4[e], 2147483520.0f);       // overflow already reported
-                        k[j] = (uint32_t)ff + ((rb16 >> j) & 1u);
-                        sg[j] = (st.sgw >> (2 * j + 1)) & 1u;
-                    }
-                }
-                switch (W) {
-                    case 4: pack_store<4>(k, sg, tw); break;
-                    case 8: pack_store<8>(k, sg, tw); break;
-                    case 16: pack_store<16>(k, sg, tw); break;
-                    default: pack_store<32>(k, sg, tw); break;
-                }
+                emit_wide(a, st.c, st.t, st.sgw, rc, park, fm, kw, W, tw);
             }
         }
     }
@@ -689,67 +740,127 @@ __device__ __forceinline__ void stage2(const StreamArgs &a, Scratch &sc, uint32_
 __device__ unsigned long long g_polls;
 #endif
 // Exclusive fixed-point prefix of tile t of a row: earlier tiles of its block + earlier blocks of its super-block +
-// earlier super-blocks (see the header).  All lanes return the result.
-__device__ __forceinline__ long long lookback_resolve(const TileRec *tiles, const Rec2 *blocks, const Rec2 *supers, int t, int lane) {
+// earlier super-blocks (see the header).  The records are loaded in one round (lookback_load) and evaluated later
+// (lookback_eval), so that the warp can do something else while the loads are in flight; a round that finds an
+// incomplete record is repeated.
+struct LookRegs { unsigned long long tv, blo, bhi, slo, shi; uint32_t tf; };
+__device__ __forceinline__ void lookback_load(const TileRec *tiles, const Rec2 *blocks, const Rec2 *supers, int t, int lane, LookRegs &r) {
     const int b = t >> 5, pos = t & 31, sb = b >> 5, bpos = b & 31;
-    const bool has_t = lane < pos, has_b = lane < bpos;
-    while (true) {
-        bool ok = true;
-        long long x = 0;
-        if (has_t) {
-            unsigned long long v;
-            ok = rec_load(tiles + (t - 1 - lane), v) != 0u;
-            x = (long long)v;
-        }
-        if (has_b) {
-            unsigned long long lo, hi;
-            rec2_load(blocks + (sb * 32 + lane), lo, hi);
-            ok = ok && (lo >> kCntShift) == 32ull && (hi >> kCntShift) == 32ull;
-            x += (long long)(((hi & kSumMask) << 31) + (lo & kSumMask));
-        }
-        for (int s = lane; s < sb; s += 32) {
-            unsigned long long lo, hi;
-            rec2_load(supers + s, lo, hi);
-            ok = ok && (lo >> kCntShift) == 1024ull && (hi >> kCntShift) == 1024ull;
-            x += (long long)(((hi & kSumMask) << 31) + (lo & kSumMask));
-        }
-        if (__all_sync(0xffffffffu, ok)) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            return x;
-        }
-#ifdef DME_TIMERS
-        if (lane == 0) atomicAdd(&g_polls, 1ull);
-#endif
-        __nanosleep(64);
+    r.tv = 0; r.tf = 1u; r.blo = r.bhi = 32ull << kCntShift; r.slo = r.shi = 1024ull << kCntShift;
+    if (lane < pos) r.tf = rec_load(tiles + (t - 1 - lane), r.tv);
+    if (lane < bpos) rec2_load(blocks + (sb * 32 + lane), r.blo, r.bhi);
+    if (lane < sb) rec2_load(supers + lane, r.slo, r.shi);
+}
+__device__ __forceinline__ bool lookback_eval(const Rec2 *supers, int t, int lane, const LookRegs &r, long long &P) {
+    const int sb = t >> 10;
+    bool ok = r.tf != 0u && (r.blo >> kCntShift) == 32ull && (r.bhi >> kCntShift) == 32ull && (r.slo >> kCntShift) == 1024ull &&
+              (r.shi >> kCntShift) == 1024ull;
+    long long x = (long long)r.tv + (long long)((((r.bhi & kSumMask) + (r.shi & kSumMask)) << 31) + (r.blo & kSumMask) + (r.slo & kSumMask));
+    for (int s = lane + 32; s < sb; s += 32) {          // rows longer than 2^27 coordinates
+        unsigned long long lo, hi;
+        rec2_load(supers + s, lo, hi);
+        ok = ok && (lo >> kCntShift) == 1024ull && (hi >> kCntShift) == 1024ull;
+        x += (long long)(((hi & kSumMask) << 31) + (lo & kSumMask));
     }
+    if (!__all_sync(0xffffffffu, ok)) return false;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    P = x;
+    return true;
 }
 
+// the look-back of the last pass-B tile, resolved while the compute warps work on the next one
+struct Pending {
+    int owed, valid;     // a READY arrival is owed / the tile has a prefix to resolve
+    int c, t, par, rs;
+    long long Aq;
+    uint32_t fm;
+    LookRegs regs;
+};
+// row constants that a pass-B item already in flight still needs (its row was not final when the copy was issued)
+struct RcWait { int n; int c0, rs0, slot0, c1, rs1, slot1; };
 struct Service {
     Decoder dec;
-    int nb;              // pass-B items seen so far (tile parity = nb & 1, row-constant slot = nb & 3)
+    int nb;              // pass-B items issued so far (row-constant slot = nb & 3)
+    Pending pd;
+    RcWait rq;
 };
 
-// decode the next item into ring slot `slot`, make its row constants available, start its copy
+__device__ __forceinline__ int width_of(float kmax) {
+    return kmax < 2.0f ? 2 : kmax < 8.0f ? 4 : kmax < 128.0f ? 8 : kmax < 32768.0f ? 16 : 32;
+}
+// post the resolved prefix of the pending tile for stage 2 and release the compute warps
+__device__ __forceinline__ void service_post(Scratch &sc, Pending &pd, long long P, int lane) {
+    if (pd.valid) {
+        if (lane == 0) {
+            const RowConst &rc = sc.rc[pd.rs];
+            TileInfo ti;
+            ti.P = __ll2double_rn(P) * rc.q_dn;
+            ti.EnLast = __ll2double_rn(P + pd.Aq) * rc.q_dn;
+            const float fm = __uint_as_float(pd.fm);
+            ti.flmax = fm;
+            ti.rcslot = pd.rs;
+            ti.Wlo = width_of(fm); ti.Whi = width_of(__fadd_rn(fm, 1.0f));
+            ti.pad[0] = ti.pad[1] = 0;
+            sc.info[pd.par] = ti;
+        }
+        __syncwarp();
+    }
+    bar_arrive(kBarReady + pd.par, kBlock);
+    pd.owed = 0;
+}
+
+// copy the constants of row c into slot rs and complete the item's barrier phase (its second arrival)
+__device__ __forceinline__ void service_rc_copy(const StreamArgs &a, Scratch &sc, int c, int rs, int slot, int lane) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(&a.consts[c]);
+    uint4 *dst = reinterpret_cast<uint4 *>(&sc.rc[rs]);
+    if (lane < (int)(sizeof(RowConst) / 16)) dst[lane] = __ldcg(src + lane);
+    const uint4 *ts = reinterpret_cast<const uint4 *>(a.tabs + (int64_t)c * kBinades);
+    uint4 *td = reinterpret_cast<uint4 *>(sc.tab[rs]);
+    if (lane < kBinades) td[lane] = __ldcg(ts + lane);
+    if (lane == 0) sc.rc_row[rs] = c;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sc.mbar[slot]);
+}
+// One round of background work: look-back of the pending tile, row constants of items in flight.  Loads first, a few
+// looks at `bar` while they fly, then the evaluation.  Returns true when `bar` (phase `parity`) has completed.
+__device__ __forceinline__ bool service_background(const StreamArgs &a, Scratch &sc, Service &sv, int lane, uint32_t bar, uint32_t parity) {
+    Pending &pd = sv.pd;
+    const bool lb = pd.owed && pd.valid;
+    const bool rw = sv.rq.n > 0;
+    const TileRec *tiles = a.desc + (int64_t)pd.c * a.T;
+    const Rec2 *blocks = a.blocks + (int64_t)pd.c * a.TB, *supers = a.supers + (int64_t)pd.c * a.TS;
+    uint32_t rr = 0;
+    if (lb) lookback_load(tiles, blocks, supers, pd.t, lane, pd.regs);
+    if (rw) rr = ld_acquire_u32(&a.row_ready[sv.rq.c0]);
+    bool arrived = false;
+    if (bar) {
+#pragma unroll 1
+        for (int i = 0; i < 12 && !arrived; ++i) arrived = mbar_test(bar, parity);
+    }
+    if (lb) {
+        long long P;
+        if (lookback_eval(supers, pd.t, lane, pd.regs, P)) service_post(sc, pd, P, lane);
+#ifdef DME_TIMERS
+        else if (lane == 0) atomicAdd(&g_polls, 1ull);
+#endif
+    } else if (pd.owed && !pd.valid) {
+        service_post(sc, pd, 0, lane);
+    }
+    if (rw && rr != 0u) {
+        service_rc_copy(a, sc, sv.rq.c0, sv.rq.rs0, sv.rq.slot0, lane);
+        sv.rq.c0 = sv.rq.c1; sv.rq.rs0 = sv.rq.rs1; sv.rq.slot0 = sv.rq.slot1;
+        --sv.rq.n;
+    }
+    if (!lb && !rw && !arrived && bar) __nanosleep(20);
+    return arrived;
+}
+
+// decode the next item into ring slot `slot` and start its copy.  The barrier of a ring slot takes two arrivals per
+// phase: the copy (with its byte count) and "row constants in shared memory", which may come later.
 __device__ __forceinline__ void service_issue(const StreamArgs &a, const CUtensorMap *tmap, Scratch &sc, Service &sv, int slot, uint32_t ring0, int lane,
                                               uint64_t pol_a, uint64_t pol_b) {
     const Item it = sv.dec.next(a);
-    if ((it.flags & kItB) && (it.flags & kItValid)) {
-        const int rs = sv.nb & 3;
-        if (sc.rc_row[rs] != it.c) {
-            if (lane == 0) while (ld_acquire_u32(&a.row_ready[it.c]) == 0u) __nanosleep(64);
-            __syncwarp();
-            const uint4 *src = reinterpret_cast<const uint4 *>(&a.consts[it.c]);
-            uint4 *dst = reinterpret_cast<uint4 *>(&sc.rc[rs]);
-            if (lane < (int)(sizeof(RowConst) / 16)) dst[lane] = __ldcg(src + lane);
-            const uint4 *ts = reinterpret_cast<const uint4 *>(a.tabs + (int64_t)it.c * kBinades);
-            uint4 *td = reinterpret_cast<uint4 *>(sc.tab[rs]);
-            if (lane < kBinades) td[lane] = __ldcg(ts + lane);
-            if (lane == 0) sc.rc_row[rs] = it.c;
-            __syncwarp();
-        }
-    }
-    if (it.flags & kItB) ++sv.nb;
     __syncwarp();                                 // every lane has finished reading the slot
     if (lane == 0) {
         sc.items[slot] = it;
@@ -758,10 +869,36 @@ __device__ __forceinline__ void service_issue(const StreamArgs &a, const CUtenso
             mbar_expect_tx(&sc.mbar[slot], (uint32_t)kTile * 4u);
             tma_tile_g2s(ring0 + (uint32_t)slot * kTile * 4u, tmap, it.t * (kTile / 32), it.c, &sc.mbar[slot], (it.flags & kItB) ? pol_b : pol_a);
         } else {
-            mbar_arrive(&sc.mbar[slot]);          // nothing to copy: the phase completes at once (releases the item record)
+            mbar_arrive(&sc.mbar[slot]);          // nothing to copy
         }
     }
+    bool later = false;
+    if ((it.flags & kItB) && (it.flags & kItValid)) {
+        const int rs = sv.nb & 3;
+        if (sc.rc_row[rs] != it.c) {
+            later = true;
+            if (sv.rq.n == 0) { sv.rq.c0 = it.c; sv.rq.rs0 = rs; sv.rq.slot0 = slot; }
+            else { sv.rq.c1 = it.c; sv.rq.rs1 = rs; sv.rq.slot1 = slot; }
+            ++sv.rq.n;
+        }
+    }
+    if (it.flags & kItB) ++sv.nb;
+    if (!later && lane == 0) mbar_arrive(&sc.mbar[slot]);
     __syncwarp();
+}
+// pass-A duty: finish the tile sum from the 256 thread sums left in the ring slot, then refill the slot
+__device__ __forceinline__ void service_pass_a(const StreamArgs &a, const CUtensorMap *tmap, Scratch &sc, Service &sv, const Item &it, int slot,
+                                               uint32_t ring0, int lane, int parity, uint64_t pol_a, uint64_t pol_b) {
+    TIC(13);
+    bar_sync(kBarPA + parity, kBlock);
+    TOC(13);
+    TRACE(15, it.t);
+    double tot = lane < kWarps ? sc.wsumA[parity][lane] : 0.0;
+#pragma unroll
+    for (int o = kWarps / 2; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0 && (it.flags & kItValid)) rec_store(&a.partial[(int64_t)it.c * a.T + it.t], (unsigned long long)__double_as_longlong(tot), 1u);
+    service_issue(a, tmap, sc, sv, slot, ring0, lane, pol_a, pol_b);
+    TRACE(16, it.t);
 }
 
 #ifndef DME_STREAM_CTAS
@@ -771,13 +908,14 @@ template <int EMIT>
 __global__ void __launch_bounds__(kBlock, DME_STREAM_CTAS)
 quantize_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char dyn_smem[];      // ring slots, two park buffers, Scratch
-    Scratch &sc = *reinterpret_cast<Scratch *>(dyn_smem + (size_t)(kRing + 2) * kTile * sizeof(float));
+    Scratch &sc = *reinterpret_cast<Scratch *>(dyn_smem + (size_t)kRing * kTile * sizeof(float) + 2 * kParkBytes);
 
     if (threadIdx.x == 0) {
-        for (int b = 0; b < kRing; ++b) mbar_init(&sc.mbar[b], 1);
+        for (int b = 0; b < kRing; ++b) mbar_init(&sc.mbar[b], 2);
+        for (int b = 0; b < 2; ++b) mbar_init(&sc.b1bar[b], kThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int q = 0; q < 4; ++q) sc.rc_row[q] = -1;
-        for (int q = 0; q < 8; ++q) sc.tacc[q] = 0;
+        for (int q = 0; q < 16; ++q) sc.tacc[q] = 0;
         if (a.dbg & 32) sc.tacc[6] -= gtime();
     }
     __syncthreads();
@@ -790,39 +928,42 @@ quantize_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_consta
         // ================================================================== service warp
         const int lane = threadIdx.x & 31;
         const uint64_t pol_a = policy_evict_last(), pol_b = policy_evict_first();
+        const uint32_t b1bar0 = smem_u32(&sc.b1bar[0]);
         Service sv;
         sv.dec.init(a, g);
         sv.nb = 0;
+        sv.pd.owed = 0; sv.pd.valid = 0; sv.pd.c = 0; sv.pd.t = 0;
+        sv.rq.n = 0; sv.rq.c0 = sv.rq.rs0 = sv.rq.slot0 = sv.rq.c1 = sv.rq.rs1 = sv.rq.slot1 = 0;
         for (int j = 0; j < kRing; ++j) service_issue(a, &tmap, sc, sv, j, ring0, lane, pol_a, pol_b);
         int nbd = 0, nad = 0;                   // pass-B / pass-A items completed by this warp
-        for (int64_t j = 0;; ++j) {
-            const int slot = (int)(j & 1);
+        uint32_t b1phase = 0;                   // phase parity of the two stage-1 barriers
+        int slot = 0;
+        while (true) {
             const Item it = sc.items[slot];     // written by this warp
             if (it.flags & kItEnd) break;
             if (it.flags & kItB) {
-                const int par = nbd & 1;
-                bar_sync(kBarB1 + par, kBlock);                                   // thread sums + floor maxima are in
-                TIC(4);
-                const int rs = nbd & 3;
-                // scan of the 256 thread sums: lane l owns threads 8l .. 8l+7 (fixed association)
-                double v[8];
-                double tot = 0.0;
+                const int par = nbd & 1, rs = nbd & 3;
+                // wait for the stage-1 data of this tile; meanwhile resolve the previous tile's look-back and fetch
+                // row constants (the compute warps cannot get here before the constants of this tile are in)
+                TIC(8);
+                while (!service_background(a, sc, sv, lane, b1bar0 + 8u * par, (b1phase >> par) & 1u)) { }
+                b1phase ^= 1u << par;
+                TOC(8);
+                TRACE(10, it.t);
+                TIC(9);
+                // the tile aggregate from the 8 warp totals (inclusive scan over lanes 0..7, fixed association)
+                double incl = lane < kWarps ? sc.wtot[par][lane] : 0.0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const uint32_t u = 8u * lane + i;
-                    v[i] = lds64((ring0 + (uint32_t)slot * kTile * 4u + blocked_off_of(u)) ^ (((u >> 4) & 3u) << 4));
-                    tot += v[i];
-                }
-                uint32_t fm = lane < kWarps ? sc.flmaxw[par][lane] : 0u;
-                double incl = tot;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
+                for (int o = 1; o < kWarps; o <<= 1) {
                     const double up = __shfl_up_sync(0xffffffffu, incl, o);
                     if (lane >= o) incl += up;
                 }
-                const double A = __shfl_sync(0xffffffffu, incl, 31);
+                if (lane < kWarps) sc.wbase[par][lane + 1] = incl;
+                if (lane == 0) sc.wbase[par][0] = 0.0;
+                // publish it first: the look-backs of the later tiles wait for nothing else
                 long long Aq = 0;
                 if (it.flags & kItValid) {
+                    const double A = __shfl_sync(0xffffffffu, incl, kWarps - 1);
                     const RowConst &rc = sc.rc[rs];
                     Aq = __double2ll_rn(A * rc.q_up);                             // fixed point, 2^-qshift resolution
                     if (lane == 0) {
@@ -834,76 +975,57 @@ quantize_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_consta
                         red_add_u64(&sr->lo, lo); red_add_u64(&sr->hi, hi);
                     }
                 }
-                double ex = __shfl_up_sync(0xffffffffu, incl, 1);
-                if (lane == 0) ex = 0.0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { sc.scanE[par][9 * lane + i] = ex; ex += v[i]; }
-                if (lane == 31) sc.scanE[par][spad(kThreads)] = incl;
+                uint32_t fm = lane < kWarps ? sc.flmaxw[par][lane] : 0u;
                 fm = __reduce_max_sync(0xffffffffu, fm);
-                TOC(4);
-                service_issue(a, &tmap, sc, sv, slot, ring0, lane, pol_a, pol_b);  // the slot is free: next item of this parity
-                // the A item that follows gives the predecessors time to publish; resolve after it
-                const int slotA = slot ^ 1;
-                const Item ia = sc.items[slotA];
+                TOC(9);
+                TRACE(11, it.t);
+                // the previous tile's stage 2 comes right after the pass-A item: its prefix must be out now
+                TIC(10);
+                while (sv.pd.owed) service_background(a, sc, sv, lane, 0u, 0u);
+                TOC(10);
+                TRACE(12, it.t);
+                TIC(12);
+                service_issue(a, &tmap, sc, sv, slot, ring0, lane, pol_a, pol_b);  // the slot is free: refill it
+                TOC(12);
+                TRACE(14, it.t);
+                slot = slot == kRing - 1 ? 0 : slot + 1;
+                // the A item that follows
+                const Item ia = sc.items[slot];
                 if (!(ia.flags & kItEnd) && !(ia.flags & kItB)) {
-                    const int pa = nad & 1;
-                    bar_sync(kBarPA + pa, kBlock);
-                    const uint32_t bufA = ring0 + (uint32_t)slotA * kTile * 4u;
-                    double tot2 = lds64(bufA + lane * 16u);
-#pragma unroll
-                    for (int i = 1; i < kThreads / 32; ++i) tot2 += lds64(bufA + (lane + 32 * i) * 16u);
-                    tot2 = warp_sum_f64(tot2);
-                    if (lane == 0 && (ia.flags & kItValid))
-                        rec_store(&a.partial[(int64_t)ia.c * a.T + ia.t], (unsigned long long)__double_as_longlong(tot2), 1u);
-                    service_issue(a, &tmap, sc, sv, slotA, ring0, lane, pol_a, pol_b);
-                    ++nad; ++j;
+                    service_pass_a(a, &tmap, sc, sv, ia, slot, ring0, lane, nad & 1, pol_a, pol_b);
+                    ++nad;
+                    slot = slot == kRing - 1 ? 0 : slot + 1;
                 }
-                if (it.flags & kItValid) {
-                    TIC(5);
-                    const long long P = lookback_resolve(a.desc + (int64_t)it.c * a.T, a.blocks + (int64_t)it.c * a.TB, a.supers + (int64_t)it.c * a.TS,
-                                                         it.t, lane);
-                    TOC(5);
-                    if (lane == 0) {
-                        const RowConst &rc = sc.rc[rs];
-                        TileInfo ti;
-                        ti.P = __ll2double_rn(P) * rc.q_dn;
-                        ti.EnLast = __ll2double_rn(P + Aq) * rc.q_dn;
-                        ti.flmax = __uint_as_float(fm);
-                        ti.rcslot = rs;
-                        sc.info[par] = ti;
-                    }
-                }
-                __syncwarp();
-                bar_arrive(kBarReady + par, kBlock);
+                // this tile's look-back is resolved in the background of the next wait
+                sv.pd.owed = 1; sv.pd.valid = (it.flags & kItValid) ? 1 : 0;
+                sv.pd.c = it.c; sv.pd.t = it.t; sv.pd.par = par; sv.pd.rs = rs; sv.pd.Aq = Aq; sv.pd.fm = fm;
                 ++nbd;
             } else {
-                const int pa = nad & 1;
-                bar_sync(kBarPA + pa, kBlock);
-                const uint32_t bufA = ring0 + (uint32_t)slot * kTile * 4u;
-                double tot2 = lds64(bufA + lane * 16u);
-#pragma unroll
-                for (int i = 1; i < kThreads / 32; ++i) tot2 += lds64(bufA + (lane + 32 * i) * 16u);
-                tot2 = warp_sum_f64(tot2);
-                if (lane == 0 && (it.flags & kItValid))
-                    rec_store(&a.partial[(int64_t)it.c * a.T + it.t], (unsigned long long)__double_as_longlong(tot2), 1u);
-                service_issue(a, &tmap, sc, sv, slot, ring0, lane, pol_a, pol_b);
+                service_pass_a(a, &tmap, sc, sv, it, slot, ring0, lane, nad & 1, pol_a, pol_b);
                 ++nad;
+                slot = slot == kRing - 1 ? 0 : slot + 1;
             }
         }
+        while (sv.pd.owed) service_background(a, sc, sv, lane, 0u, 0u);
     } else {
         // ================================================================== compute warps
         // software pipeline of depth 2 over the pass-B tiles: stage 1 of tile i+1, the pass-A item between, stage 2 of tile i
         BState s0, s1;
         s0.flags = 0; s1.flags = 0;
-        int64_t j = 0;                      // local item index
+        int slot = 0;
+        uint32_t phases = 0;                // phase parity of every ring slot
         int nb = 0, na = 0;                 // pass-B / pass-A items started
         int pend0 = 0, pend1 = 0;           // a stage 2 is owed for state 0 / 1 (its READY barrier must be consumed)
         auto fetch = [&](Item &it, uint32_t &buf) -> bool {
-            const int slot = (int)(j & 1);
-            mbar_wait(mbar0 + 8u * slot, (uint32_t)((j >> 1) & 1));
+            TIC(0);
+            TRACE(1, slot);
+            mbar_wait(mbar0 + 8u * slot, (phases >> slot) & 1u);
+            TRACE(2, slot);
+            TOC(0);
+            phases ^= 1u << slot;
             it = sc.items[slot];
             buf = ring0 + (uint32_t)slot * kTile * 4u;
-            ++j;
+            slot = slot == kRing - 1 ? 0 : slot + 1;
             return !(it.flags & kItEnd);
         };
         auto run_a = [&](const Item &it, uint32_t buf) { TIC(1); pass_a(a, it, buf, sc, na & 1); TOC(1); ++na; };
@@ -915,43 +1037,42 @@ quantize_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_consta
             {
                 const int par = nb & 1, rs = nb & 3;
                 TIC(2);
-                if (it.flags & kItValid) stage1<EMIT>(a, it, buf, park0 + (uint32_t)par * kTile * 4u, sc.rc[rs], sc, s0, par);
-                else { s0.flags = 0; bar_arrive(kBarB1 + par, kBlock); }
+                if (it.flags & kItValid) stage1<EMIT>(a, it, buf, park0 + (uint32_t)par * kParkBytes, sc.rc[rs], sc, s0, par);
+                else { s0.flags = 0; mbar_arrive(&sc.b1bar[par]); }
                 TOC(2);
                 pend0 = 1; ++nb;
             }
             more = fetch(it, buf);
             if (more && !(it.flags & kItB)) { run_a(it, buf); more = fetch(it, buf); }
-            if (pend1) { TIC(3); stage2<EMIT>(a, sc, park0 + (uint32_t)kTile * 4u, s1, 1); TOC(3); pend1 = 0; }
+            if (pend1) { TIC(3); stage2<EMIT>(a, sc, park0 + (uint32_t)kParkBytes, s1, 1); TOC(3); pend1 = 0; TRACE(7, 1); }
             if (!more) break;
             // ---- B item -> state 1
             {
                 const int par = nb & 1, rs = nb & 3;
                 TIC(2);
-                if (it.flags & kItValid) stage1<EMIT>(a, it, buf, park0 + (uint32_t)par * kTile * 4u, sc.rc[rs], sc, s1, par);
-                else { s1.flags = 0; bar_arrive(kBarB1 + par, kBlock); }
+                if (it.flags & kItValid) stage1<EMIT>(a, it, buf, park0 + (uint32_t)par * kParkBytes, sc.rc[rs], sc, s1, par);
+                else { s1.flags = 0; mbar_arrive(&sc.b1bar[par]); }
                 TOC(2);
                 pend1 = 1; ++nb;
             }
             more = fetch(it, buf);
             if (more && !(it.flags & kItB)) { run_a(it, buf); more = fetch(it, buf); }
-            if (pend0) { TIC(3); stage2<EMIT>(a, sc, park0, s0, 0); TOC(3); pend0 = 0; }
+            if (pend0) { TIC(3); stage2<EMIT>(a, sc, park0, s0, 0); TOC(3); pend0 = 0; TRACE(7, 0); }
         }
         // drain in tile order
         if (pend0 && pend1) {
-            if (nb & 1) { stage2<EMIT>(a, sc, park0 + (uint32_t)kTile * 4u, s1, 1); stage2<EMIT>(a, sc, park0, s0, 0); }
-            else { stage2<EMIT>(a, sc, park0, s0, 0); stage2<EMIT>(a, sc, park0 + (uint32_t)kTile * 4u, s1, 1); }
+            if (nb & 1) { stage2<EMIT>(a, sc, park0 + (uint32_t)kParkBytes, s1, 1); stage2<EMIT>(a, sc, park0, s0, 0); }
+            else { stage2<EMIT>(a, sc, park0, s0, 0); stage2<EMIT>(a, sc, park0 + (uint32_t)kParkBytes, s1, 1); }
         } else if (pend0) stage2<EMIT>(a, sc, park0, s0, 0);
-        else if (pend1) stage2<EMIT>(a, sc, park0 + (uint32_t)kTile * 4u, s1, 1);
+        else if (pend1) stage2<EMIT>(a, sc, park0 + (uint32_t)kParkBytes, s1, 1);
     }
     if ((a.dbg & 32) && (threadIdx.x == 0 || threadIdx.x == kThreads)) {
         if (threadIdx.x == 0) sc.tacc[6] += gtime();
 #ifdef DME_TIMERS
         if (blockIdx.x == 0 && threadIdx.x == 0) { sc.tacc[7] = g_polls; g_polls = 0; }
 #endif
-        for (int q = (threadIdx.x == 0 ? 0 : 4); q < (threadIdx.x == 0 ? 4 : 6); ++q)
-            atomicAdd(reinterpret_cast<unsigned long long *>(a.hdr->pad + 1) + q, sc.tacc[q]);
-        if (threadIdx.x == 0) for (int q = 6; q < 8; ++q) atomicAdd(reinterpret_cast<unsigned long long *>(a.hdr->pad + 1) + q, sc.tacc[q]);
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(a.hdr->pad + 1);
+        for (int q = (threadIdx.x == 0 ? 0 : 8); q < (threadIdx.x == 0 ? 8 : 16); ++q) atomicAdd(dst + q, sc.tacc[q]);
     }
 }
 
@@ -990,7 +1111,7 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
         set_error("code arena too small for the primary slots: %lld < %llu bytes", (long long)codes_bytes, a.pack.arena_base16 * 16ull);
         return DME_EWORKSPACE;
     }
-    const size_t dyn = (size_t)(kRing + 2) * kTile * sizeof(float) + sizeof(Scratch);
+    const size_t dyn = (size_t)kRing * kTile * sizeof(float) + 2 * kParkBytes + sizeof(Scratch);
     if (g_sms == 0) {
         int dev = 0;
         DME_CUDA(cudaGetDevice(&dev));
@@ -1030,6 +1151,10 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
     a.total_items = 2 * (lenA > lenB ? lenA : lenB);
     a.G = G;
     a.step_c = (int)(G / L.T); a.step_t = (int)(G % L.T);
+    if (a.total_items + G >= ((int64_t)1 << 31)) { set_error("n * tiles too large for the stream kernel"); return DME_EINVAL; }
+    a.total_items32 = (int)a.total_items;
+    a.tiles_tma = (int)((a.rows32 + kTile / 32 - 1) / (kTile / 32));
+    a.has_tail = (d & 31) ? 1 : 0;
     a.dbg = 0;
     if (const char *e = getenv("DME_DBG")) a.dbg = atoi(e);
     void *args[] = {&a, &tmap};
@@ -1040,3 +1165,16 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
 }
 
 }  // namespace dme
+
+#ifdef DME_TIMERS
+extern "C" __attribute__((visibility("default"))) int dme_debug_trace(unsigned long long *out, int cap) {
+    unsigned int n = 0;
+    cudaMemcpyFromSymbol(&n, dme::g_trace_n, sizeof(n));
+    if ((int)n > cap) n = cap;
+    if (n > 4096) n = 4096;
+    cudaMemcpyFromSymbol(out, dme::g_trace, (size_t)n * 16);
+    unsigned int z = 0;
+    cudaMemcpyToSymbol(dme::g_trace_n, &z, sizeof(z));
+    return (int)n;
+}
+#endif

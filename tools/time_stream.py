@@ -32,8 +32,8 @@ for n, d in shapes:
         ws = dme.Workspace.get(X.device).buf
         off = (-ws.data_ptr()) % 256
         hdr = ws[off: off + 256].cpu().numpy().view("uint64")
-        names = ["c:tma wait", "c:pass A", "c:stage 1", "c:stage 2", "c:READY wait (in stage 2)", "-", "cta lifetime", "polls",
-                 "s:B1 wait", "s:sums+publish", "s:finish try", "s:scan", "s:issue B", "s:PA wait", "s:finish block", "-"]
+        names = ["c:copy wait A", "c:pass A", "c:B-phase", "c:C-phase", "c:READY wait", "c:copy wait B", "cta lifetime", "c:look-back finish (warp 0)",
+                 "-", "-", "s:cdone wait", "s:count x1000", "s:issue B", "s:adone wait", "s:issue A", "s:raw B copy latency (sum)"]
         pairs = n * ((d + 4095) // 4096)
         print("   per tile pair, ns:", {nm: round(float(hdr[3 + q]) / pairs, 1) for q, nm in enumerate(names) if nm != "-"})
     del X

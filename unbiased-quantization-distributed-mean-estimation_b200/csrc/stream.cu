@@ -9,18 +9,20 @@
 // sums and publishes the row constants, so that row p's pass B, which starts `lag - T - goff` tiles later, never
 // waits for them.  Every wait is on an item with a smaller index, every CTA is resident: no deadlock.
 //
-// Inside a CTA: 8 compute warps + 1 service warp.
-//   service warp : decodes the CTA's items, waits for the row constants, issues the TMA tensor copies (3-D map
-//                  {32 floats, rows of 128 B, client}, SWIZZLE_128B: the blocked read "thread t owns coordinates
-//                  [16t, 16t+16)" is free of bank conflicts, rows past the end of a client vector arrive as zeros),
-//                  scans the 256 thread sums of a pass-B tile, publishes the tile aggregate, finishes the pass-A
-//                  tile sums and resolves the decoupled look-back -- all the serial work, off the compute warps.
-//   compute warps: pass A; pass B in two stages that are one tile apart (software pipeline of depth 2):
-//                  stage 1 (tile i+1): division, floor, fractional parts (kept in registers as floats), thread sum;
-//                  stage 2 (tile i)  : running fp64 prefix -> floor(c_j - X) for every coordinate, emit.
-//                  The look-back of tile i has a whole tile pair of time to resolve.
+// Inside a CTA: 8 compute warps + 1 service warp, and six 16 KB tile slots in shared memory (2 for pass A, 4 for
+// pass B) filled by TMA tensor copies (3-D map {32 floats, rows of 128 B, client}, SWIZZLE_128B: the blocked read
+// "thread t owns coordinates [16t, 16t+16)" is free of bank conflicts, rows past the end of a client vector arrive
+// as zeros).
+//   A pass-B tile goes through two phases that are TWO tiles apart while it stays in its slot:
+//     B-phase (tile j)  : division, floor, fractional parts -> thread sums -> warp scan -> warp totals;
+//     C-phase (tile j-2): the same chain again (cheaper than keeping 20 values per coordinate alive), running fp64
+//                         prefix -> floor(c - X) for every coordinate, emit.
+//   Between them the service warp publishes the tile aggregate and resolves the decoupled look-back; two tile
+//   periods of slack absorb the jitter between CTAs (every tile needs the aggregates of ALL earlier tiles of its row).
+//   service warp : decodes the CTA's items, issues the copies, fetches row constants, finishes the pass-A tile sums,
+//                  publishes aggregates, polls the look-back records -- all the serial work, never blocking.
 //
-// Stage 2 in closed form.  AS:636 evaluates t = floor(RN32(RN32(c) - X)) with c the fp64 prefix.  While c32 stays
+// C-phase in closed form.  AS:636 evaluates t = floor(RN32(RN32(c) - X)) with c the fp64 prefix.  While c32 stays
 // inside one binade [2^e + 1, 2^(e+1)), 2 <= e <= 22 (fp32 grid g = 2^(e-23)), this equals floor(c - Xp) when
 // a = ceil(X/g - 1/2) is even and ceil(c - Xp) - 1 when a is odd, with Xp = g (a - 1/2) (proof in DESIGN.md
 // section 3.1; ties of both roundings included).  So per coordinate: one DFMA (running sigma (c - Xp)) and one
@@ -31,7 +33,7 @@
 // Look-back.  Every tile publishes its aggregate (int64 fixed point) as a 16-byte record and adds it, split in two
 // 31-bit halves that each carry a contribution count, to the record of its block (32 tiles) and of its super-block
 // (1024 tiles) with fire-and-forget 64-bit reductions.  A record is complete when both counts are full, so the
-// exclusive prefix of a tile needs nothing but the stage 1 of the earlier tiles of its row: one round of independent
+// exclusive prefix of a tile needs nothing but the B-phase of the earlier tiles of its row: one round of independent
 // 16-byte loads (tiles of its block, blocks of its super-block, earlier super-blocks).  Integer addition is
 // associative: the result does not depend on timing.
 #include <cuda.h>
@@ -43,8 +45,7 @@
 
 namespace dme {
 
-constexpr int kRing = 3;                 // TMA ring depth (item j uses slot j % 3; refilled after the barrier of item j)
-constexpr int kParkBytes = kThreads * 16;   // parked floors of a pass-B tile: one byte per coordinate
+constexpr int kSlotsA = 2, kSlotsB = 4;  // tile slots in shared memory
 constexpr int kBlock = kThreads + 32;    // 8 compute warps + 1 service warp
 
 struct __align__(16) Rec { unsigned long long v; uint32_t flag; uint32_t pad; };
@@ -118,9 +119,8 @@ __device__ __forceinline__ bool bar_or(int id, int n, bool pred) {
         "}\n" : "=r"(r) : "r"(id), "r"(n), "r"((uint32_t)pred) : "memory");
     return r != 0;
 }
-// named barriers: 1,2 = stage-1 data of a pass-B tile (by tile parity), 3,4 = pass-A thread sums (by parity),
-// 5,6 = prefix of a pass-B tile resolved (by tile parity), 7 = compute warps only, 8 = compute warps, OR-reduce
-constexpr int kBarB1 = 1, kBarPA = 3, kBarReady = 5, kBarCompute = 7, kBarOr = 8;
+// named barriers: 3,4 = pass-A warp sums are in (by parity), 7 = compute warps only, 8 = compute warps, OR-reduce
+constexpr int kBarPA = 3, kBarCompute = 7, kBarOr = 8;
 
 // one 16 KB box {32 floats, 128 rows, 1 client} at (0, row0, client) of the 3-D tensor map
 __device__ __forceinline__ void tma_tile_g2s(uint32_t dst, const CUtensorMap *map, int row0, int client, uint64_t *bar, uint64_t policy) {
@@ -130,6 +130,9 @@ __device__ __forceinline__ void tma_tile_g2s(uint32_t dst, const CUtensorMap *ma
 }
 __device__ __forceinline__ uint64_t policy_evict_last() {
     uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); return p;
 }
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
@@ -172,21 +175,22 @@ struct StreamArgs {
     int dbg;                                                            // development: bit 5 = phase timers
 };
 
-// One work item, decoded by the service warp when it issues the tile's copy and shared through a ring.
+// One work item, decoded by the service warp when it issues the tile's copy.
 struct __align__(16) Item { int c, t; uint32_t flags; int fin_row; };
-constexpr uint32_t kItValid = 1u, kItB = 2u, kItTma = 4u, kItTail = 8u, kItEnd = 16u;
+constexpr uint32_t kItValid = 1u, kItTma = 4u, kItTail = 8u, kItEnd = 16u;
 
 __device__ __forceinline__ void floor_divmod(long long s, long long T, int &c, int &t) {
     long long q = s >= 0 ? s / T : -((-s + T - 1) / T);
     c = (int)q; t = (int)(s - q * T);
 }
-// Item decoder (service warp, lane-uniform): the CTA's items advance by G in the global order, i.e. by G positions in
-// the A stream and in the B stream alternately, so (client, tile) pairs are updated without divisions.
+// Item decoder (service warp, lane-uniform): the CTA's items advance by G in the global order, i.e. its pass-A items
+// and its pass-B items each advance by G positions in their stream, so (client, tile) pairs are updated without
+// divisions.  The two streams are decoded independently (their copies are issued at different times).
 struct Decoder {
-    int i; int cA, tA, cB, tB, cF, tF;
+    int iA, iB; int cA, tA, cB, tB, cF, tF;
     __device__ __forceinline__ void init(const StreamArgs &a, long long g) {
-        i = (int)g;
         const long long firstA = (g & 1) ? g + a.G : g, firstB = (g & 1) ? g : g + a.G;
+        iA = (int)firstA; iB = (int)firstB;
         floor_divmod(firstA >> 1, a.T, cA, tA);
         floor_divmod((firstA >> 1) - a.goff, a.T, cF, tF);
         floor_divmod((firstB >> 1) - a.lag, a.T, cB, tB);
@@ -195,60 +199,68 @@ struct Decoder {
         c += sc_; t += st_;
         if (t >= T) { t -= T; ++c; }
     }
-    __device__ __forceinline__ Item next(const StreamArgs &a) {
-        const int T = (int)a.T, n = (int)a.n;
-        Item it; it.c = 0; it.t = 0; it.fin_row = -1;
-        const bool is_b = (i & 1) != 0;
-        it.flags = is_b ? kItB : 0u;
-        if (i >= a.total_items32) { it.flags |= kItEnd; return it; }
-        i += (int)a.G;
-        int c, t;
-        if (!is_b) {
-            c = cA; t = tA;
-            if (tF == 0 && cF >= 1 && cF <= n) it.fin_row = cF - 1;           // finaliser duty of this position
-            advance(cA, tA, a.step_c, a.step_t, T);
-            advance(cF, tF, a.step_c, a.step_t, T);
-        } else {
-            c = cB; t = tB;
-            advance(cB, tB, a.step_c, a.step_t, T);
-        }
-        if ((unsigned)c >= (unsigned)n) return it;
+    __device__ __forceinline__ static void classify(const StreamArgs &a, Item &it, int c, int t) {
+        const int T = (int)a.T;
+        if ((unsigned)c >= (unsigned)a.n) return;
         it.c = c; it.t = t;
         uint32_t f = it.flags | kItValid;
         if (t < a.tiles_tma) f |= kItTma;                                     // at least one full 128-byte row in this tile
         if (t == T - 1 && a.has_tail) f |= kItTail;                           // d % 32 coordinates come straight from global
         it.flags = f;
+    }
+    __device__ __forceinline__ Item next_a(const StreamArgs &a) {
+        Item it; it.c = 0; it.t = 0; it.fin_row = -1; it.flags = 0;
+        if (iA >= a.total_items32) { it.flags = kItEnd; return it; }
+        iA += 2 * (int)a.G;
+        if (tF == 0 && cF >= 1 && cF <= (int)a.n) it.fin_row = cF - 1;        // finaliser duty of this position
+        classify(a, it, cA, tA);
+        advance(cA, tA, a.step_c, a.step_t, (int)a.T);
+        advance(cF, tF, a.step_c, a.step_t, (int)a.T);
+        return it;
+    }
+    __device__ __forceinline__ Item next_b(const StreamArgs &a) {
+        Item it; it.c = 0; it.t = 0; it.fin_row = -1; it.flags = 0;
+        if (iB >= a.total_items32) { it.flags = kItEnd; return it; }
+        iB += 2 * (int)a.G;
+        classify(a, it, cB, tB);
+        advance(cB, tB, a.step_c, a.step_t, (int)a.T);
         return it;
     }
 };
 
-struct TileInfo {            // what stage 2 needs about a pass-B tile (written by the service warp), by tile parity
+struct TileInfo {            // what the C-phase needs about a pass-B tile (written by the service warp), by slot
     double P;                // exclusive prefix of the tile
     double EnLast;           // inclusive prefix at the last coordinate of the tile (from the fixed-point values)
     float flmax;             // largest floor in the tile
-    int rcslot;
     int Wlo, Whi;            // field width needed for the largest floor / the largest floor + 1
-    int pad[2];
+    int pad;
 };
-// Thread sums (stage 1 of a pass-B tile, pass A) travel to the service warp through the tile's own ring slot: every
-// thread overwrites 8 of the 64 bytes only it has read, and the slot is refilled by the service warp after it has
-// consumed them.
+// what the warp that finished a tile's B-phase last leaves for the look-back of that tile
+struct __align__(16) PubInfo { long long Aq; uint32_t fm; int valid; };
 struct Scratch {
-    double scanI[2][kThreads];     // inclusive prefix of the thread sums inside each warp (thread-private entries), by tile parity
-    double wtot[2][kWarps];        // warp totals of a pass-B tile (stage 1 -> service warp), by tile parity
-    double wbase[2][kWarps + 1];   // in-tile exclusive prefixes of the warps (+ tile total) (service warp -> stage 2)
-    double wsumA[2][kWarps];       // warp sums of a pass-A tile, by parity
-    double red[kWarps];            // finalize_row
-    uint32_t flmaxw[2][kWarps];    // per-warp max floor (float bits), by tile parity
-    TileInfo info[2];
-    RowConst rc[4];                // row constants of the pass-B tiles in flight (slot = tile count & 3)
-    BinadeEntry tab[4][kBinades];
-    int rc_row[4];
-    unsigned long long off16;      // arena offset of a wide tile (compute warps)
-    Item items[kRing];
-    uint64_t mbar[kRing];          // ring slots: copy complete + row constants present
-    uint64_t b1bar[2];             // stage-1 data of a pass-B tile complete (256 arrivals), by tile parity
-    unsigned long long tacc[16];   // phase timers (dbg): 0-7 compute thread 0, 8-15 service lane 0
+    double scanI[kSlotsB][kThreads];     // inclusive prefix of the thread sums inside each warp (thread-private entries)
+    double wtot[kSlotsB][kWarps];        // warp totals of a pass-B tile (B-phase -> service warp)
+    double wbase[kSlotsB][kWarps + 1];   // in-tile exclusive prefixes of the warps (+ tile total) (service warp -> C-phase)
+    double wsumA[2][kWarps];             // warp sums of a pass-A tile, by parity
+    double red[kWarps];                  // finalize_row
+    uint32_t flmaxw[kSlotsB][kWarps];    // per-warp max floor (float bits)
+    TileInfo info[kSlotsB];
+    PubInfo pubinfo[kSlotsB];
+    unsigned int cntB[kSlotsB];          // warps that have finished the slot's B-phase
+    unsigned int cntA[2];                // warps that have finished the pass-A tile, by parity
+    RowConst rc[kSlotsB];                // cache of row constants (entry e holds row rc_row[e]); a slot uses entry rc_of[slot]
+    BinadeEntry tab[kSlotsB][kBinades];
+    int rc_row[kSlotsB];
+    int rc_of[kSlotsB];
+    unsigned long long off16;            // arena offset of a wide tile (compute warps)
+    Item itemsA[kSlotsA], itemsB[kSlotsB];
+    uint64_t mbarA[kSlotsA];             // pass-A slot: copy complete (1 arrival + bytes)
+    uint64_t mbarB[kSlotsB];             // pass-B slot: copy complete + row constants present (2 arrivals + bytes)
+    uint64_t pub[kSlotsB];               // the slot's tile aggregate is published, warp bases are in (1 arrival: last warp)
+    uint64_t adone[kSlotsA];             // pass-A slot consumed: may be refilled (1 arrival: last warp)
+    uint64_t cdone[kSlotsB];             // C-phase of the slot's tile complete: the slot may be refilled (256 arrivals)
+    uint64_t ready[kSlotsB];             // prefix of the slot's tile resolved (1 arrival, service warp)
+    unsigned long long tacc[16];         // phase timers (dbg): 0-7 compute thread 0, 8-15 service lane 0
 };
 
 // Row constants + the binade table of AS:636's closed form (cold: once per client row).
@@ -337,16 +349,6 @@ __device__ __forceinline__ f2 f2_sub(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %
 #define DME_X2 1
 #endif
 
-// State of a pass-B tile between its two stages (registers of the compute warps).
-struct BState {
-    float fr[kEpt];         // fractional parts m p - floor(m p)
-    uint32_t sgw;           // bits 2j+1 = IEEE sign of coordinate j (even bits: junk)
-    uint32_t zmask;         // array output only: bit j = m * |v_j| is exactly zero (sign(v) = 0 in AS:640)
-    float flmax_t;          // the thread's largest floor
-    int c, t;
-    uint32_t flags;         // item flags (0 = nothing parked)
-};
-
 // swizzled shared-memory offset of the 16-byte chunk q (0..3) of thread tid's 16 coordinates inside a 16 KB tile
 // (SWIZZLE_128B: chunk index within the 128-byte row is XORed with row & 7); q enters as an XOR of (q << 4)
 __device__ __forceinline__ uint32_t blocked_off_of(uint32_t tid) {
@@ -360,8 +362,8 @@ __device__ __noinline__ double row_tail_abs(const StreamArgs &a, int c) {
     if (threadIdx.x >= (uint32_t)(a.d & 31)) return 0.0;
     return (double)fabsf(a.X[(int64_t)c * a.ld + a.rows32 * 32 + threadIdx.x]);
 }
-// ---- pass A of one tile: the thread sums go to shared memory, the service warp finishes them
-__device__ __forceinline__ void pass_a(const StreamArgs &a, const Item &it, uint32_t buf, Scratch &sc, int parity) {
+// ---- pass A of one tile: warp sums to shared memory, the service warp finishes them
+__device__ __forceinline__ void pass_a(const StreamArgs &a, const Item &it, uint32_t buf, Scratch &sc, int parity, int slotA) {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     if (it.flags & kItTma) {
         // any order will do: physical 16-byte chunks q*256 + tid (conflict-free), fixed association
@@ -373,9 +375,26 @@ __device__ __forceinline__ void pass_a(const StreamArgs &a, const Item &it, uint
     }
     if (it.flags & kItTail) s0 += row_tail_abs(a, it.c);
     const double ws = warp_sum_f64((s0 + s1) + (s2 + s3));      // fixed association
-    if ((threadIdx.x & 31) == 0) sc.wsumA[parity][threadIdx.x >> 5] = ws;
-    bar_arrive(kBarPA + parity, kBlock);
-    TRACE(4, it.t);
+    const int lane = threadIdx.x & 31;
+    unsigned int old = 0;
+    if (lane == 0) {
+        sc.wsumA[parity][threadIdx.x >> 5] = ws;
+        __threadfence_block();
+        old = atomicAdd(&sc.cntA[parity], 1u);
+    }
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old == kWarps - 1) {
+        // the warp that finishes last adds the 8 warp sums (fixed order), publishes the tile sum and frees the slot
+        __threadfence_block();
+        double tot = lane < kWarps ? sc.wsumA[parity][lane] : 0.0;
+#pragma unroll
+        for (int o = kWarps / 2; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (lane == 0) {
+            if (it.flags & kItValid) rec_store(&a.partial[(int64_t)it.c * a.T + it.t], (unsigned long long)__double_as_longlong(tot), 1u);
+            sc.cntA[parity] = 0;
+            mbar_arrive(&sc.adone[slotA]);
+        }
+    }
     if (it.fin_row >= 0) finalize_row(a, it.fin_row, sc);
 }
 
@@ -450,59 +469,72 @@ __device__ __forceinline__ void load_x(const StreamArgs &a, uint32_t flags, int 
     }
 }
 
-// ---- stage 1: everything that does not need the prefix of earlier tiles
-template <int EMIT>
-__device__ __forceinline__ void stage1(const StreamArgs &a, const Item &it, uint32_t buf, uint32_t park, const RowConst &rc, Scratch &sc, BState &st,
-                                       int parity) {
-    st.flags = it.flags; st.c = it.c; st.t = it.t;
+// ---- B-phase: thread sums of the fractional parts, their scan inside each warp, warp totals, largest floor
+__device__ __forceinline__ void phase_b(const StreamArgs &a, const Item &it, uint32_t buf, Scratch &sc, int slot) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float x[kEpt];
-    load_x(a, it.flags, it.c, it.t, buf, x);
-    uint32_t sg = 0;
+    if (it.flags & kItValid) {
+        const RowConst &rc = sc.rc[sc.rc_of[slot]];
+        float x[kEpt], flf[kEpt], fr[kEpt];
+        load_x(a, it.flags, it.c, it.t, buf, x);
+        floors_and_fracs(x, rc, flf, fr);
+        float mxf = flf[0];
 #pragma unroll
-    for (int j = kEpt - 1; j >= 0; --j) sg = __funnelshift_l(__float_as_uint(x[j]), sg, 2);     // bit 2j+1 = sign of x[j]
-    st.sgw = sg;
-    float flf[kEpt];
-    floors_and_fracs(x, rc, flf, st.fr);
-    // park the floors as bytes (only meaningful while the tile's largest floor is below 256: wider tiles recompute
-    // them in stage 2); floor + 2^23 carries the integer in its low mantissa bits
-    {
-        uint32_t w[4];
+        for (int j = 1; j < kEpt; ++j) mxf = fmaxf(mxf, flf[j]);
+        // thread sum, left to right
+        double run = (double)fr[0];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t b0 = __float_as_uint(__fadd_rn(flf[4 * q], 8388608.0f)), b1 = __float_as_uint(__fadd_rn(flf[4 * q + 1], 8388608.0f));
-            const uint32_t b2 = __float_as_uint(__fadd_rn(flf[4 * q + 2], 8388608.0f)), b3 = __float_as_uint(__fadd_rn(flf[4 * q + 3], 8388608.0f));
-            w[q] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+        for (int j = 1; j < kEpt; ++j) run += (double)fr[j];
+        // inclusive scan of the thread sums inside the warp (Kogge-Stone, fixed association)
+        double incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
         }
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(park + threadIdx.x * 16u), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+        sc.scanI[slot][threadIdx.x] = incl;
+        if (lane == 31) sc.wtot[slot][warp] = incl;
+        const uint32_t wmx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));     // floors are >= 0: bit order = value order
+        if (lane == 0) sc.flmaxw[slot][warp] = wmx;
     }
-    if (EMIT == 0) {
-        uint32_t z = 0;
-#pragma unroll
-        for (int j = 0; j < kEpt; ++j) z |= ((flf[j] == 0.0f && st.fr[j] == 0.0f) ? 1u : 0u) << j;
-        st.zmask = z;
+    __syncwarp();
+    unsigned int old = 0;
+    if (lane == 0) {
+        __threadfence_block();
+        old = atomicAdd(&sc.cntB[slot], 1u);
     }
-    float mxf = flf[0];
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old == kWarps - 1) {
+        // the warp that finishes last: in-tile exclusive prefixes of the warps (inclusive scan over lanes 0..7, fixed
+        // association), then the tile aggregate goes out at once -- the look-backs of the later tiles wait for nothing else
+        __threadfence_block();
+        double incl = lane < kWarps ? sc.wtot[slot][lane] : 0.0;
 #pragma unroll
-    for (int j = 1; j < kEpt; ++j) mxf = fmaxf(mxf, flf[j]);
-    st.flmax_t = mxf;
-    // thread sum, left to right
-    double run = (double)st.fr[0];
-#pragma unroll
-    for (int j = 1; j < kEpt; ++j) run += (double)st.fr[j];
-    // inclusive scan of the thread sums inside the warp (Kogge-Stone, fixed association); warp total to the service warp
-    double incl = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double up = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += up;
+        for (int o = 1; o < kWarps; o <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane < kWarps) sc.wbase[slot][lane + 1] = incl;
+        uint32_t fm = lane < kWarps ? sc.flmaxw[slot][lane] : 0u;
+        fm = __reduce_max_sync(0xffffffffu, fm);
+        const double A = __shfl_sync(0xffffffffu, incl, kWarps - 1);
+        if (lane == 0) {
+            sc.wbase[slot][0] = 0.0;
+            PubInfo pi; pi.Aq = 0; pi.fm = fm; pi.valid = (it.flags & kItValid) ? 1 : 0;
+            if (it.flags & kItValid) {
+                const long long Aq = __double2ll_rn(A * sc.rc[sc.rc_of[slot]].q_up);  // fixed point, 2^-qshift resolution
+                pi.Aq = Aq;
+                rec_store(a.desc + (int64_t)it.c * a.T + it.t, (unsigned long long)Aq, 1u);
+                const unsigned long long lo = ((unsigned long long)Aq & 0x7fffffffull) + (1ull << kCntShift);
+                const unsigned long long hi = ((unsigned long long)Aq >> 31) + (1ull << kCntShift);
+                Rec2 *br = a.blocks + (int64_t)it.c * a.TB + (it.t >> 5), *sr = a.supers + (int64_t)it.c * a.TS + (it.t >> 10);
+                red_add_u64(&br->lo, lo); red_add_u64(&br->hi, hi);
+                red_add_u64(&sr->lo, lo); red_add_u64(&sr->hi, hi);
+            }
+            sc.pubinfo[slot] = pi;
+            sc.cntB[slot] = 0;
+            mbar_arrive(&sc.pub[slot]);
+        }
     }
-    sc.scanI[parity][threadIdx.x] = incl;
-    if (lane == 31) sc.wtot[parity][warp] = incl;
-    const uint32_t wmx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));     // floors are >= 0: bit order = value order
-    if (lane == 0) sc.flmaxw[parity][warp] = wmx;
-    mbar_arrive(&sc.b1bar[parity]);
-    TRACE(3, it.t);
 }
 
 // AS:636 literally, for one prefix value
@@ -551,7 +583,7 @@ __device__ __forceinline__ uint32_t spread16(uint32_t v) {       // bit j -> bit
 }
 // r_j = [floor(c_j - X) - floor(c_{j-1} - X) == 1] (AS:636-637) for the thread's 16 coordinates as 2-bit interleaved
 // fields (bit 2j = r_j).  Closed form: the 0/1 differences telescope into one IMAD per coordinate.
-__device__ __forceinline__ uint32_t rbits_interleaved(const Geo &g, const BState &st, float X) {
+__device__ __forceinline__ uint32_t rbits_interleaved(const Geo &g, const float (&fr)[kEpt], float X) {
     if (g.fast) {
         const int sgi = g.sig > 0.0 ? 1 : -1;
         double u = g.sE;
@@ -559,7 +591,7 @@ __device__ __forceinline__ uint32_t rbits_interleaved(const Geo &g, const BState
         int L14 = 0;
 #pragma unroll
         for (int j = 0; j < kEpt - 1; ++j) {
-            u = fma(frac_to_double(st.fr[j]), g.sig, u);
+            u = fma(frac_to_double(fr[j]), g.sig, u);
             const int L = floor_lo(u);
             // sum_j (L_j - L_{j-1}) 4^j  =  -L_{-1} - sum_{j<14} 3 * 4^j L_j + 4^14 L_14
             if (j < kEpt - 2) acc += (uint32_t)L * (0u - (3u << (2 * j)));
@@ -577,7 +609,7 @@ __device__ __forceinline__ uint32_t rbits_interleaved(const Geo &g, const BState
     int tp = floor_ref(c, X);
 #pragma unroll
     for (int j = 0; j < kEpt; ++j) {
-        c = (j < kEpt - 1) ? c + (double)st.fr[j] : g.En;
+        c = (j < kEpt - 1) ? c + (double)fr[j] : g.En;
         const int t = floor_ref(c, X);
         rb |= ((t - tp == 1) ? 1u : 0u) << j;
         tp = t;
@@ -585,49 +617,12 @@ __device__ __forceinline__ uint32_t rbits_interleaved(const Geo &g, const BState
     return spread16(rb);
 }
 
-// floors of the thread's coordinates in stage 2: the parked bytes, or -- tiles whose largest floor does not fit a
-// byte (heavy tails) -- recomputed from the row (same function of the same inputs as in stage 1)
-__device__ __noinline__ void reload_floors(const StreamArgs &a, int c, int t, const RowConst &rc, float (&fl)[kEpt]) {
-    float x[kEpt], fr[kEpt];
-    const int64_t i0 = (int64_t)t * kTile + (int64_t)threadIdx.x * kEpt;
-    const float *row = a.X + (int64_t)c * a.ld;
-#pragma unroll
-    for (int j = 0; j < kEpt; ++j) x[j] = (i0 + j < a.d) ? __ldcg(row + i0 + j) : 0.0f;
+// fields of 4 / 8 / 16 / 32 bits (cold: kept out of line)
+__device__ __noinline__ void emit_wide(const StreamArgs &a, uint32_t flags, int c, int t, uint32_t buf, const RowConst &rc, uint32_t kw, uint32_t sgw, int W,
+                                       uint32_t *tw) {
+    float x[kEpt], fl[kEpt], fr[kEpt];
+    load_x(a, flags, c, t, buf, x);                        // the floors again: same function of the same inputs
     floors_and_fracs(x, rc, fl, fr);
-}
-__device__ __forceinline__ void load_floors(const StreamArgs &a, int c, int t, const RowConst &rc, uint32_t park, float fm, float (&fl)[kEpt]) {
-    if (fm < 256.0f) {
-        uint32_t w[4];
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(park + threadIdx.x * 16u));
-#pragma unroll
-        for (int j = 0; j < kEpt; ++j) fl[j] = (float)((w[j >> 2] >> (8 * (j & 3))) & 0xffu);
-    } else {
-        reload_floors(a, c, t, rc, fl);
-    }
-}
-// cold helpers of the packed emit (rare threads / wide tiles): kept out of line to keep the hot loop small
-// any coordinate whose floor equals the tile maximum and that received a unit?
-__device__ __noinline__ bool floors_hit(const StreamArgs &a, int c, int t, const RowConst &rc, uint32_t park, float fm, uint32_t kw) {
-    float fl[kEpt];
-    load_floors(a, c, t, rc, park, fm, fl);
-    bool hit = false;
-#pragma unroll
-    for (int j = 0; j < kEpt; ++j) hit |= (fl[j] == fm) && ((kw >> (2 * j)) & 1u);
-    return hit;
-}
-// bit 2j = floor_j != 0
-__device__ __noinline__ uint32_t floors_nonzero(const StreamArgs &a, int c, int t, const RowConst &rc, uint32_t park, float fm) {
-    float fl[kEpt];
-    load_floors(a, c, t, rc, park, fm, fl);
-    uint32_t kb = 0;
-#pragma unroll
-    for (int j = 0; j < kEpt; ++j) kb |= ((fl[j] != 0.0f) ? 1u : 0u) << (2 * j);
-    return kb;
-}
-// fields of 4 / 8 / 16 / 32 bits
-__device__ __noinline__ void emit_wide(const StreamArgs &a, int c, int t, uint32_t sgw, const RowConst &rc, uint32_t park, float fm, uint32_t kw, int W, uint32_t *tw) {
-    float fl[kEpt];
-    load_floors(a, c, t, rc, park, fm, fl);
     uint32_t k[kEpt], sg[kEpt];
 #pragma unroll
     for (int j = 0; j < kEpt; ++j) {
@@ -643,106 +638,113 @@ __device__ __noinline__ void emit_wide(const StreamArgs &a, int c, int t, uint32
     }
 }
 
-// ---- stage 2: prefix -> floor(c - X) (AS:635-637), type vector, emit
+// ---- C-phase: prefix -> floor(c - X) (AS:635-637), type vector, emit
 template <int EMIT>
-__device__ __forceinline__ void stage2(const StreamArgs &a, Scratch &sc, uint32_t park, BState &st, int parity) {
-    TRACE(5, st.t);
-    bar_sync(kBarReady + parity, kBlock);                 // the service warp has resolved this tile's prefix
-    if (!(st.flags & kItValid)) return;
-    TRACE(6, (int)sc.info[parity].flmax);
-    st.flags = 0;
-    const TileInfo &ti = sc.info[parity];
-    const RowConst &rc = sc.rc[ti.rcslot];
-    const double Pd = ti.P;
-    // The prefix at a thread's LAST coordinate is defined from the scan values (at the last coordinate of the tile
-    // from the fixed-point inclusive prefix), so the next thread / tile starts from exactly the same value and
-    // derives the same floor(c - X) for its predecessor: no hand-off is needed.
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double incl = sc.scanI[parity][threadIdx.x];
-    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane == 0) excl = 0.0;
-    const double Pw = Pd + sc.wbase[parity][warp];
-    const double E = Pw + excl;
-    double En = Pw + incl;
-    if (lane == 31) En = Pd + sc.wbase[parity][warp + 1];        // = the next warp's first prefix, bit for bit
-    if (threadIdx.x == kThreads - 1) En = ti.EnLast;
-    const Geo g = make_geo(sc.tab[ti.rcslot], E, En);
-    const float fm = ti.flmax;
-    const uint32_t kw = rbits_interleaved(g, st, rc.X);
-    if (EMIT == 0) {
-        const int64_t i0 = (int64_t)st.t * kTile + (int64_t)threadIdx.x * kEpt;
-        float fl[kEpt];
-        load_floors(a, st.c, st.t, rc, park, fm, fl);
-        bool ovf = false;
+__device__ __forceinline__ void phase_c(const StreamArgs &a, Scratch &sc, const Item &it, uint32_t buf, int slot) {
+    if (it.flags & kItValid) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int re = sc.rc_of[slot];
+        const RowConst &rc = sc.rc[re];
+        const TileInfo &ti = sc.info[slot];
+        float x[kEpt], fl[kEpt], fr[kEpt];
+        load_x(a, it.flags, it.c, it.t, buf, x);
+        uint32_t sgw = 0;
 #pragma unroll
-        for (int j = 0; j < kEpt; ++j) {
-            const float kf = __fadd_rn(fl[j], (float)((kw >> (2 * j)) & 1u));
-            const int64_t i = i0 + j;
-            if (i >= a.d) continue;
-            const uint32_t sbit = (st.sgw >> (2 * j + 1)) & 1u;
-            if (a.deq_out) {
-                // sign(v) of AS:640: v = x / D is zero exactly when m * |v| is (floor and fraction both zero, m > 0)
-                const float sgf = ((st.zmask >> j) & 1u) ? 0.0f : (sbit ? -1.0f : 1.0f);
-                a.deq_out[(int64_t)st.c * a.ld_out + i] = __fdiv_rn(__fmul_rn(__fmul_rn(rc.L1f, sgf), kf), rc.mf);
+        for (int j = kEpt - 1; j >= 0; --j) sgw = __funnelshift_l(__float_as_uint(x[j]), sgw, 2);     // bit 2j+1 = sign of x[j]
+        floors_and_fracs(x, rc, fl, fr);
+        const double Pd = ti.P;
+        // The prefix at a thread's LAST coordinate is defined from the scan values (at the last coordinate of the tile
+        // from the fixed-point inclusive prefix), so the next thread / tile starts from exactly the same value and
+        // derives the same floor(c - X) for its predecessor: no hand-off is needed.
+        const double incl = sc.scanI[slot][threadIdx.x];
+        double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 0.0;
+        const double Pw = Pd + sc.wbase[slot][warp];
+        const double E = Pw + excl;
+        double En = Pw + incl;
+        if (lane == 31) En = Pd + sc.wbase[slot][warp + 1];        // = the next warp's first prefix, bit for bit
+        if (threadIdx.x == kThreads - 1) En = ti.EnLast;
+        const Geo g = make_geo(sc.tab[re], E, En);
+        const float fm = ti.flmax;
+        const uint32_t kw = rbits_interleaved(g, fr, rc.X);
+        if (EMIT == 0) {
+            const int64_t i0 = (int64_t)it.t * kTile + (int64_t)threadIdx.x * kEpt;
+            bool ovf = false;
+#pragma unroll
+            for (int j = 0; j < kEpt; ++j) {
+                const float kf = __fadd_rn(fl[j], (float)((kw >> (2 * j)) & 1u));
+                const int64_t i = i0 + j;
+                if (i >= a.d) continue;
+                const uint32_t sbit = (sgw >> (2 * j + 1)) & 1u;
+                if (a.deq_out) {
+                    // sign(v) of AS:640: v = x / D is zero exactly when m * |v| is (floor and fraction both zero, m > 0)
+                    const float sgf = (fl[j] == 0.0f && fr[j] == 0.0f) ? 0.0f : (sbit ? -1.0f : 1.0f);
+                    a.deq_out[(int64_t)it.c * a.ld_out + i] = __fdiv_rn(__fmul_rn(__fmul_rn(rc.L1f, sgf), kf), rc.mf);
+                }
+                if (a.k_out) {
+                    if (kf >= 2147483648.0f) { ovf = true; a.k_out[(int64_t)it.c * a.ld_out + i] = 0x7fffffff; }
+                    else a.k_out[(int64_t)it.c * a.ld_out + i] = (int32_t)kf;
+                }
+                if (a.sgn_out) a.sgn_out[(int64_t)it.c * a.ld_out + i] = (uint8_t)sbit;
             }
-            if (a.k_out) {
-                if (kf >= 2147483648.0f) { ovf = true; a.k_out[(int64_t)st.c * a.ld_out + i] = 0x7fffffff; }
-                else a.k_out[(int64_t)st.c * a.ld_out + i] = (int32_t)kf;
-            }
-            if (a.sgn_out) a.sgn_out[(int64_t)st.c * a.ld_out + i] = (uint8_t)sbit;
-        }
-        if (ovf) atomicOr(&a.hdr->status, 1u);
-    } else {
-        // tile-wide minimal field width: from the largest floor; only when the largest floor sits right below a
-        // width boundary does it matter whether one of those coordinates also received a unit
-        int W = ti.Wlo;
-        const bool plain = (ti.Whi == 2);               // every floor is 0: k = r
-        if (!plain && ti.Wlo != ti.Whi) {
-            bool hit = false;
-            if (st.flmax_t == fm) hit = floors_hit(a, st.c, st.t, rc, park, fm, kw);
-            W = bar_or(kBarOr, kThreads, hit) ? ti.Whi : ti.Wlo;
-        }
-        if (fm >= 2147483520.0f && threadIdx.x == 0) atomicOr(&a.hdr->status, 1u);
-        const int64_t slot_id = (int64_t)st.c * a.T + st.t;
-        unsigned long long off16;
-        if (W <= a.pack.W0) {
-            off16 = (unsigned long long)slot_id * (32ull * a.pack.W0);
-            if (threadIdx.x == 0) a.pack.dir[slot_id] = (off16 << 8) | (unsigned long long)W;
+            if (ovf) atomicOr(&a.hdr->status, 1u);
         } else {
-            if (threadIdx.x == 0) {
-                const unsigned long long units = 32ull * W;
-                unsigned long long o = a.pack.arena_base16 + atomicAdd(&a.hdr->arena_top, units);
-                if ((long long)((o + units) * 16ull) > a.pack.codes_bytes) { atomicOr(&a.hdr->status, 2u); o = ~0ull; }
-                sc.off16 = o;
-                a.pack.dir[slot_id] = (o == ~0ull) ? 0ull : ((o << 8) | (unsigned long long)W);
+            // tile-wide minimal field width: from the largest floor; only when the largest floor sits right below a
+            // width boundary does it matter whether one of those coordinates also received a unit
+            int W = ti.Wlo;
+            const bool plain = (ti.Whi == 2);               // every floor is 0: k = r
+            if (!plain && ti.Wlo != ti.Whi) {
+                bool hit = false;
+#pragma unroll
+                for (int j = 0; j < kEpt; ++j) hit |= (fl[j] == fm) && ((kw >> (2 * j)) & 1u);
+                W = bar_or(kBarOr, kThreads, hit) ? ti.Whi : ti.Wlo;
             }
-            bar_sync(kBarCompute, kThreads);
-            off16 = sc.off16;
-            bar_sync(kBarCompute, kThreads);        // off16 may be rewritten by the next wide tile
-        }
-        if (off16 != ~0ull) {
-            uint32_t *tw = a.pack.codes + off16 * 4ull;
-            if (W == 2) {
-                // fields [sign | magnitude bit]
-                uint32_t kb = kw;
-                // largest floor is 1 and no such coordinate received a unit: k = floor + r is still <= 1
-                if (!plain && st.flmax_t != 0.0f) kb |= floors_nonzero(a, st.c, st.t, rc, park, fm);
-                tw[threadIdx.x] = kb | (st.sgw & 0xaaaaaaaau);
+            if (fm >= 2147483520.0f && threadIdx.x == 0) atomicOr(&a.hdr->status, 1u);
+            const int64_t slot_id = (int64_t)it.c * a.T + it.t;
+            unsigned long long off16;
+            if (W <= a.pack.W0) {
+                off16 = (unsigned long long)slot_id * (32ull * a.pack.W0);
+                if (threadIdx.x == 0) a.pack.dir[slot_id] = (off16 << 8) | (unsigned long long)W;
             } else {
-                emit_wide(a, st.c, st.t, st.sgw, rc, park, fm, kw, W, tw);
+                if (threadIdx.x == 0) {
+                    const unsigned long long units = 32ull * W;
+                    unsigned long long o = a.pack.arena_base16 + atomicAdd(&a.hdr->arena_top, units);
+                    if ((long long)((o + units) * 16ull) > a.pack.codes_bytes) { atomicOr(&a.hdr->status, 2u); o = ~0ull; }
+                    sc.off16 = o;
+                    a.pack.dir[slot_id] = (o == ~0ull) ? 0ull : ((o << 8) | (unsigned long long)W);
+                }
+                bar_sync(kBarCompute, kThreads);
+                off16 = sc.off16;
+                bar_sync(kBarCompute, kThreads);        // off16 may be rewritten by the next wide tile
+            }
+            if (off16 != ~0ull) {
+                uint32_t *tw = a.pack.codes + off16 * 4ull;
+                if (W == 2) {
+                    // fields [sign | magnitude bit]
+                    uint32_t kb = kw;
+                    if (!plain) {
+                        // largest floor is 1 and no such coordinate received a unit: k = floor + r is still <= 1
+#pragma unroll
+                        for (int j = 0; j < kEpt; ++j) kb |= ((fl[j] != 0.0f) ? 1u : 0u) << (2 * j);
+                    }
+                    tw[threadIdx.x] = kb | (sgw & 0xaaaaaaaau);
+                } else {
+                    emit_wide(a, it.flags, it.c, it.t, buf, rc, kw, sgw, W, tw);
+                }
             }
         }
     }
+    mbar_arrive(&sc.cdone[slot]);
 }
 
-// ------------------------------------------------------------------ service warp
+// ------------------------------------------------------------------ look-back (compute warp 0)
 #ifdef DME_TIMERS
 __device__ unsigned long long g_polls;
 #endif
 // Exclusive fixed-point prefix of tile t of a row: earlier tiles of its block + earlier blocks of its super-block +
 // earlier super-blocks (see the header).  The records are loaded in one round (lookback_load) and evaluated later
-// (lookback_eval), so that the warp can do something else while the loads are in flight; a round that finds an
-// incomplete record is repeated.
+// (lookback_eval), so that the warp can work while the loads are in flight; a round that finds an incomplete record
+// is repeated.
 struct LookRegs { unsigned long long tv, blo, bhi, slo, shi; uint32_t tf; };
 __device__ __forceinline__ void lookback_load(const TileRec *tiles, const Rec2 *blocks, const Rec2 *supers, int t, int lane, LookRegs &r) {
     const int b = t >> 5, pos = t & 31, sb = b >> 5, bpos = b & 31;
@@ -768,309 +770,276 @@ __device__ __forceinline__ bool lookback_eval(const Rec2 *supers, int t, int lan
     P = x;
     return true;
 }
-
-// the look-back of the last pass-B tile, resolved while the compute warps work on the next one
-struct Pending {
-    int owed, valid;     // a READY arrival is owed / the tile has a prefix to resolve
-    int c, t, par, rs;
-    long long Aq;
-    uint32_t fm;
-    LookRegs regs;
-};
-// row constants that a pass-B item already in flight still needs (its row was not final when the copy was issued)
-struct RcWait { int n; int c0, rs0, slot0, c1, rs1, slot1; };
-struct Service {
-    Decoder dec;
-    int nb;              // pass-B items issued so far (row-constant slot = nb & 3)
-    Pending pd;
-    RcWait rq;
-};
-
 __device__ __forceinline__ int width_of(float kmax) {
     return kmax < 2.0f ? 2 : kmax < 8.0f ? 4 : kmax < 128.0f ? 8 : kmax < 32768.0f ? 16 : 32;
 }
-// post the resolved prefix of the pending tile for stage 2 and release the compute warps
-__device__ __forceinline__ void service_post(Scratch &sc, Pending &pd, long long P, int lane) {
-    if (pd.valid) {
-        if (lane == 0) {
-            const RowConst &rc = sc.rc[pd.rs];
-            TileInfo ti;
-            ti.P = __ll2double_rn(P) * rc.q_dn;
-            ti.EnLast = __ll2double_rn(P + pd.Aq) * rc.q_dn;
-            const float fm = __uint_as_float(pd.fm);
-            ti.flmax = fm;
-            ti.rcslot = pd.rs;
-            ti.Wlo = width_of(fm); ti.Whi = width_of(__fadd_rn(fm, 1.0f));
-            ti.pad[0] = ti.pad[1] = 0;
-            sc.info[pd.par] = ti;
-        }
-        __syncwarp();
-    }
-    bar_arrive(kBarReady + pd.par, kBlock);
-    pd.owed = 0;
-}
-
-// copy the constants of row c into slot rs and complete the item's barrier phase (its second arrival)
-__device__ __forceinline__ void service_rc_copy(const StreamArgs &a, Scratch &sc, int c, int rs, int slot, int lane) {
+// ------------------------------------------------------------------ service warp: copies, row constants, look-backs
+struct Service {
+    Decoder dec;
+    int nbi;             // pass-B items issued
+    int rcb;             // oldest issued pass-B item whose row constants may still be missing
+    uint32_t rc_pending; // bit slot: the slot's row constants are not in shared memory yet
+    uint32_t rc_loaded;  // bit e: cache entry e holds the constants of row rc_row[e]
+    int hb;              // oldest pass-B tile whose look-back is unresolved (slot hb & 3)
+    int nbe;             // pass-B items the compute warps have been allowed to reach (bounds hb)
+    LookRegs regs;
+};
+// copy the constants of row c into cache entry e and complete the slot's barrier phase (its second arrival)
+__device__ __forceinline__ void service_rc_copy(const StreamArgs &a, Scratch &sc, int c, int e, int slot, int lane) {
     const uint4 *src = reinterpret_cast<const uint4 *>(&a.consts[c]);
-    uint4 *dst = reinterpret_cast<uint4 *>(&sc.rc[rs]);
+    uint4 *dst = reinterpret_cast<uint4 *>(&sc.rc[e]);
     if (lane < (int)(sizeof(RowConst) / 16)) dst[lane] = __ldcg(src + lane);
     const uint4 *ts = reinterpret_cast<const uint4 *>(a.tabs + (int64_t)c * kBinades);
-    uint4 *td = reinterpret_cast<uint4 *>(sc.tab[rs]);
+    uint4 *td = reinterpret_cast<uint4 *>(sc.tab[e]);
     if (lane < kBinades) td[lane] = __ldcg(ts + lane);
-    if (lane == 0) sc.rc_row[rs] = c;
     __syncwarp();
-    if (lane == 0) mbar_arrive(&sc.mbar[slot]);
+    if (lane == 0) mbar_arrive(&sc.mbarB[slot]);
 }
-// One round of background work: look-back of the pending tile, row constants of items in flight.  Loads first, a few
-// looks at `bar` while they fly, then the evaluation.  Returns true when `bar` (phase `parity`) has completed.
+// One round of background work: look-back of the oldest unresolved published tile, row constants of the oldest item
+// that still misses them.  Loads first, a few looks at `bar` while they fly, then the evaluation.  Returns true when
+// `bar` (phase `parity`) has completed (bar == 0: nothing to watch).
 __device__ __forceinline__ bool service_background(const StreamArgs &a, Scratch &sc, Service &sv, int lane, uint32_t bar, uint32_t parity) {
-    Pending &pd = sv.pd;
-    const bool lb = pd.owed && pd.valid;
-    const bool rw = sv.rq.n > 0;
-    const TileRec *tiles = a.desc + (int64_t)pd.c * a.T;
-    const Rec2 *blocks = a.blocks + (int64_t)pd.c * a.TB, *supers = a.supers + (int64_t)pd.c * a.TS;
+    // look-back: tile hb, once it is published
+    const int lslot = sv.hb & (kSlotsB - 1);
+    bool lb = sv.hb < sv.nbe && mbar_test(smem_u32(&sc.pub[lslot]), (uint32_t)((sv.hb >> 2) & 1));
+    Item lit; lit.c = 0; lit.t = 0; lit.flags = 0; lit.fin_row = -1;
+    PubInfo pi; pi.Aq = 0; pi.fm = 0; pi.valid = 0;
+    if (lb) { lit = sc.itemsB[lslot]; pi = sc.pubinfo[lslot]; }
+    const TileRec *tiles = a.desc + (int64_t)lit.c * a.T;
+    const Rec2 *blocks = a.blocks + (int64_t)lit.c * a.TB, *supers = a.supers + (int64_t)lit.c * a.TS;
+    if (lb && pi.valid) lookback_load(tiles, blocks, supers, lit.t, lane, sv.regs);
+    // row constants: skip items that have them already
+    while (sv.rcb < sv.nbi && !((sv.rc_pending >> (sv.rcb & (kSlotsB - 1))) & 1u)) ++sv.rcb;
+    const bool rw = sv.rcb < sv.nbi;
+    const int rslot = sv.rcb & (kSlotsB - 1);
+    int rrow = 0;
     uint32_t rr = 0;
-    if (lb) lookback_load(tiles, blocks, supers, pd.t, lane, pd.regs);
-    if (rw) rr = ld_acquire_u32(&a.row_ready[sv.rq.c0]);
+    const int rent = sc.rc_of[rslot];
+    const bool rhave = rw && ((sv.rc_loaded >> rent) & 1u);           // an earlier item of the same row fetched them meanwhile
+    if (rw && !rhave) { rrow = sc.itemsB[rslot].c; rr = ld_acquire_u32(&a.row_ready[rrow]); }
     bool arrived = false;
     if (bar) {
 #pragma unroll 1
-        for (int i = 0; i < 12 && !arrived; ++i) arrived = mbar_test(bar, parity);
+        for (int i = 0; i < 8 && !arrived; ++i) arrived = mbar_test(bar, parity);
     }
     if (lb) {
-        long long P;
-        if (lookback_eval(supers, pd.t, lane, pd.regs, P)) service_post(sc, pd, P, lane);
-#ifdef DME_TIMERS
-        else if (lane == 0) atomicAdd(&g_polls, 1ull);
-#endif
-    } else if (pd.owed && !pd.valid) {
-        service_post(sc, pd, 0, lane);
+        long long P = 0;
+        if (!pi.valid || lookback_eval(supers, lit.t, lane, sv.regs, P)) {
+            if (lane == 0) {
+                if (pi.valid) {
+                    const RowConst &rc = sc.rc[sc.rc_of[lslot]];
+                    TileInfo ti;
+                    ti.P = __ll2double_rn(P) * rc.q_dn;
+                    ti.EnLast = __ll2double_rn(P + pi.Aq) * rc.q_dn;
+                    const float fm = __uint_as_float(pi.fm);
+                    ti.flmax = fm;
+                    ti.Wlo = width_of(fm); ti.Whi = width_of(__fadd_rn(fm, 1.0f));
+                    ti.pad = 0;
+                    sc.info[lslot] = ti;
+                }
+                mbar_arrive(&sc.ready[lslot]);
+            }
+            __syncwarp();
+            ++sv.hb;
+        }
     }
-    if (rw && rr != 0u) {
-        service_rc_copy(a, sc, sv.rq.c0, sv.rq.rs0, sv.rq.slot0, lane);
-        sv.rq.c0 = sv.rq.c1; sv.rq.rs0 = sv.rq.rs1; sv.rq.slot0 = sv.rq.slot1;
-        --sv.rq.n;
+    if (rhave) {
+        if (lane == 0) mbar_arrive(&sc.mbarB[rslot]);
+        sv.rc_pending &= ~(1u << rslot);
+        ++sv.rcb;
+    } else if (rw && rr != 0u) {
+        service_rc_copy(a, sc, rrow, rent, rslot, lane);
+        sv.rc_loaded |= 1u << rent;
+        sv.rc_pending &= ~(1u << rslot);
+        ++sv.rcb;
     }
     if (!lb && !rw && !arrived && bar) __nanosleep(20);
     return arrived;
 }
 
-// decode the next item into ring slot `slot` and start its copy.  The barrier of a ring slot takes two arrivals per
-// phase: the copy (with its byte count) and "row constants in shared memory", which may come later.
-__device__ __forceinline__ void service_issue(const StreamArgs &a, const CUtensorMap *tmap, Scratch &sc, Service &sv, int slot, uint32_t ring0, int lane,
-                                              uint64_t pol_a, uint64_t pol_b) {
-    const Item it = sv.dec.next(a);
-    __syncwarp();                                 // every lane has finished reading the slot
-    if (lane == 0) {
-        sc.items[slot] = it;
+// decode the next pass-A item into its slot and start its copy
+__device__ __forceinline__ void service_issue_a(const StreamArgs &a, const CUtensorMap *tmap, Scratch &sc, Service &sv, int slot, uint32_t bufA0, int lane,
+                                                uint64_t pol) {
+    const Item it = sv.dec.next_a(a);
+    __syncwarp();
+    if (lane == 0 && !(it.flags & kItEnd)) {
+        sc.itemsA[slot] = it;
         if ((it.flags & kItValid) && (it.flags & kItTma)) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&sc.mbar[slot], (uint32_t)kTile * 4u);
-            tma_tile_g2s(ring0 + (uint32_t)slot * kTile * 4u, tmap, it.t * (kTile / 32), it.c, &sc.mbar[slot], (it.flags & kItB) ? pol_b : pol_a);
+            mbar_expect_tx(&sc.mbarA[slot], (uint32_t)kTile * 4u);
+            tma_tile_g2s(bufA0 + (uint32_t)slot * kTile * 4u, tmap, it.t * (kTile / 32), it.c, &sc.mbarA[slot], pol);
         } else {
-            mbar_arrive(&sc.mbar[slot]);          // nothing to copy
+            mbar_arrive(&sc.mbarA[slot]);         // nothing to copy
         }
     }
-    bool later = false;
-    if ((it.flags & kItB) && (it.flags & kItValid)) {
-        const int rs = sv.nb & 3;
-        if (sc.rc_row[rs] != it.c) {
-            later = true;
-            if (sv.rq.n == 0) { sv.rq.c0 = it.c; sv.rq.rs0 = rs; sv.rq.slot0 = slot; }
-            else { sv.rq.c1 = it.c; sv.rq.rs1 = rs; sv.rq.slot1 = slot; }
-            ++sv.rq.n;
-        }
-    }
-    if (it.flags & kItB) ++sv.nb;
-    if (!later && lane == 0) mbar_arrive(&sc.mbar[slot]);
     __syncwarp();
 }
-// pass-A duty: finish the tile sum from the 256 thread sums left in the ring slot, then refill the slot
-__device__ __forceinline__ void service_pass_a(const StreamArgs &a, const CUtensorMap *tmap, Scratch &sc, Service &sv, const Item &it, int slot,
-                                               uint32_t ring0, int lane, int parity, uint64_t pol_a, uint64_t pol_b) {
-    TIC(13);
-    bar_sync(kBarPA + parity, kBlock);
-    TOC(13);
-    TRACE(15, it.t);
-    double tot = lane < kWarps ? sc.wsumA[parity][lane] : 0.0;
+// decode the next pass-B item into its slot and start its copy.  The barrier of a pass-B slot takes two arrivals per
+// phase: the copy (with its byte count) and "row constants in shared memory", which may come later.
+__device__ __forceinline__ void service_issue_b(const StreamArgs &a, const CUtensorMap *tmap, Scratch &sc, Service &sv, int slot, uint32_t bufB0, int lane,
+                                                uint64_t pol) {
+    const Item it = sv.dec.next_b(a);
+    __syncwarp();
+    if (it.flags & kItEnd) return;
+    // row constants: cache keyed by row; a miss takes an entry that no other slot in flight refers to
+    bool later = false;
+    if (it.flags & kItValid) {
+        int e = -1;
 #pragma unroll
-    for (int o = kWarps / 2; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if (lane == 0 && (it.flags & kItValid)) rec_store(&a.partial[(int64_t)it.c * a.T + it.t], (unsigned long long)__double_as_longlong(tot), 1u);
-    service_issue(a, tmap, sc, sv, slot, ring0, lane, pol_a, pol_b);
-    TRACE(16, it.t);
+        for (int q = 0; q < kSlotsB; ++q) if (sc.rc_row[q] == it.c) e = q;
+        if (e < 0) {
+            uint32_t used = 0;
+#pragma unroll
+            for (int q = 0; q < kSlotsB; ++q) if (q != slot) used |= 1u << sc.rc_of[q];
+            e = __ffs(~used) - 1;
+            sv.rc_loaded &= ~(1u << e);
+            __syncwarp();
+            if (lane == 0) sc.rc_row[e] = it.c;
+        }
+        later = !((sv.rc_loaded >> e) & 1u);
+        __syncwarp();
+        if (lane == 0) sc.rc_of[slot] = e;
+    }
+    if (lane == 0) {
+        sc.itemsB[slot] = it;
+        if ((it.flags & kItValid) && (it.flags & kItTma)) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&sc.mbarB[slot], (uint32_t)kTile * 4u);
+            tma_tile_g2s(bufB0 + (uint32_t)slot * kTile * 4u, tmap, it.t * (kTile / 32), it.c, &sc.mbarB[slot], pol);
+        } else {
+            mbar_arrive(&sc.mbarB[slot]);         // nothing to copy
+        }
+        if (!later) mbar_arrive(&sc.mbarB[slot]);
+    }
+    if (later) sv.rc_pending |= 1u << slot;
+#ifdef DME_TIMERS
+    if ((a.dbg & 256) && !later && (it.flags & kItValid) && (it.flags & kItTma)) {      // experiment: raw latency of the copy
+        TIC(15);
+        const uint32_t par = (uint32_t)((sv.nbi >> 2) & 1);
+        while (!mbar_test(smem_u32(&sc.mbarB[slot]), par)) { }
+        TOC(15);
+        if (lane == 0) sc.tacc[11] += 1000;
+    }
+#endif
+    ++sv.nbi;
+    __syncwarp();
 }
 
 #ifndef DME_STREAM_CTAS
-#define DME_STREAM_CTAS 3
+#define DME_STREAM_CTAS 2
 #endif
 template <int EMIT>
 __global__ void __launch_bounds__(kBlock, DME_STREAM_CTAS)
 quantize_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ CUtensorMap tmap) {
-    extern __shared__ __align__(1024) unsigned char dyn_smem[];      // ring slots, two park buffers, Scratch
-    Scratch &sc = *reinterpret_cast<Scratch *>(dyn_smem + (size_t)kRing * kTile * sizeof(float) + 2 * kParkBytes);
+    extern __shared__ __align__(1024) unsigned char dyn_smem[];      // tile slots (A, then B), Scratch
+    Scratch &sc = *reinterpret_cast<Scratch *>(dyn_smem + (size_t)(kSlotsA + kSlotsB) * kTile * sizeof(float));
 
     if (threadIdx.x == 0) {
-        for (int b = 0; b < kRing; ++b) mbar_init(&sc.mbar[b], 2);
-        for (int b = 0; b < 2; ++b) mbar_init(&sc.b1bar[b], kThreads);
+        for (int b = 0; b < kSlotsA; ++b) { mbar_init(&sc.mbarA[b], 1); mbar_init(&sc.adone[b], 1); }
+        for (int b = 0; b < kSlotsB; ++b) {
+            mbar_init(&sc.mbarB[b], 2);
+            mbar_init(&sc.pub[b], 1);
+            mbar_init(&sc.cdone[b], kThreads);
+            mbar_init(&sc.ready[b], 1);
+            sc.rc_row[b] = -1;
+            sc.rc_of[b] = b;
+            sc.cntB[b] = 0;
+        }
+        sc.cntA[0] = sc.cntA[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int q = 0; q < 4; ++q) sc.rc_row[q] = -1;
         for (int q = 0; q < 16; ++q) sc.tacc[q] = 0;
         if (a.dbg & 32) sc.tacc[6] -= gtime();
     }
     __syncthreads();
-    const int64_t g = blockIdx.x;
-    const uint32_t ring0 = smem_u32(dyn_smem);                         // SWIZZLE_128B wants 1024-byte aligned boxes
-    const uint32_t park0 = ring0 + (uint32_t)kRing * kTile * 4u;       // two park buffers (floors of the tiles in flight)
-    const uint32_t mbar0 = smem_u32(&sc.mbar[0]);
+    const int g = (int)blockIdx.x, G = (int)a.G;
+    const uint32_t bufA0 = smem_u32(dyn_smem);                          // SWIZZLE_128B wants 1024-byte aligned boxes
+    const uint32_t bufB0 = bufA0 + (uint32_t)kSlotsA * kTile * 4u;
 
     if (threadIdx.x >= kThreads) {
         // ================================================================== service warp
         const int lane = threadIdx.x & 31;
-        const uint64_t pol_a = policy_evict_last(), pol_b = policy_evict_first();
-        const uint32_t b1bar0 = smem_u32(&sc.b1bar[0]);
+        uint64_t pol_a = policy_evict_last(), pol_b = policy_evict_first();
+        const uint32_t adone0 = smem_u32(&sc.adone[0]), cdone0 = smem_u32(&sc.cdone[0]);
         Service sv;
         sv.dec.init(a, g);
-        sv.nb = 0;
-        sv.pd.owed = 0; sv.pd.valid = 0; sv.pd.c = 0; sv.pd.t = 0;
-        sv.rq.n = 0; sv.rq.c0 = sv.rq.rs0 = sv.rq.slot0 = sv.rq.c1 = sv.rq.rs1 = sv.rq.slot1 = 0;
-        for (int j = 0; j < kRing; ++j) service_issue(a, &tmap, sc, sv, j, ring0, lane, pol_a, pol_b);
-        int nbd = 0, nad = 0;                   // pass-B / pass-A items completed by this warp
-        uint32_t b1phase = 0;                   // phase parity of the two stage-1 barriers
-        int slot = 0;
-        while (true) {
-            const Item it = sc.items[slot];     // written by this warp
-            if (it.flags & kItEnd) break;
-            if (it.flags & kItB) {
-                const int par = nbd & 1, rs = nbd & 3;
-                // wait for the stage-1 data of this tile; meanwhile resolve the previous tile's look-back and fetch
-                // row constants (the compute warps cannot get here before the constants of this tile are in)
-                TIC(8);
-                while (!service_background(a, sc, sv, lane, b1bar0 + 8u * par, (b1phase >> par) & 1u)) { }
-                b1phase ^= 1u << par;
-                TOC(8);
-                TRACE(10, it.t);
-                TIC(9);
-                // the tile aggregate from the 8 warp totals (inclusive scan over lanes 0..7, fixed association)
-                double incl = lane < kWarps ? sc.wtot[par][lane] : 0.0;
-#pragma unroll
-                for (int o = 1; o < kWarps; o <<= 1) {
-                    const double up = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += up;
-                }
-                if (lane < kWarps) sc.wbase[par][lane + 1] = incl;
-                if (lane == 0) sc.wbase[par][0] = 0.0;
-                // publish it first: the look-backs of the later tiles wait for nothing else
-                long long Aq = 0;
-                if (it.flags & kItValid) {
-                    const double A = __shfl_sync(0xffffffffu, incl, kWarps - 1);
-                    const RowConst &rc = sc.rc[rs];
-                    Aq = __double2ll_rn(A * rc.q_up);                             // fixed point, 2^-qshift resolution
-                    if (lane == 0) {
-                        rec_store(a.desc + (int64_t)it.c * a.T + it.t, (unsigned long long)Aq, 1u);
-                        const unsigned long long lo = ((unsigned long long)Aq & 0x7fffffffull) + (1ull << kCntShift);
-                        const unsigned long long hi = ((unsigned long long)Aq >> 31) + (1ull << kCntShift);
-                        Rec2 *br = a.blocks + (int64_t)it.c * a.TB + (it.t >> 5), *sr = a.supers + (int64_t)it.c * a.TS + (it.t >> 10);
-                        red_add_u64(&br->lo, lo); red_add_u64(&br->hi, hi);
-                        red_add_u64(&sr->lo, lo); red_add_u64(&sr->hi, hi);
-                    }
-                }
-                uint32_t fm = lane < kWarps ? sc.flmaxw[par][lane] : 0u;
-                fm = __reduce_max_sync(0xffffffffu, fm);
-                TOC(9);
-                TRACE(11, it.t);
-                // the previous tile's stage 2 comes right after the pass-A item: its prefix must be out now
-                TIC(10);
-                while (sv.pd.owed) service_background(a, sc, sv, lane, 0u, 0u);
-                TOC(10);
-                TRACE(12, it.t);
-                TIC(12);
-                service_issue(a, &tmap, sc, sv, slot, ring0, lane, pol_a, pol_b);  // the slot is free: refill it
-                TOC(12);
-                TRACE(14, it.t);
-                slot = slot == kRing - 1 ? 0 : slot + 1;
-                // the A item that follows
-                const Item ia = sc.items[slot];
-                if (!(ia.flags & kItEnd) && !(ia.flags & kItB)) {
-                    service_pass_a(a, &tmap, sc, sv, ia, slot, ring0, lane, nad & 1, pol_a, pol_b);
-                    ++nad;
-                    slot = slot == kRing - 1 ? 0 : slot + 1;
-                }
-                // this tile's look-back is resolved in the background of the next wait
-                sv.pd.owed = 1; sv.pd.valid = (it.flags & kItValid) ? 1 : 0;
-                sv.pd.c = it.c; sv.pd.t = it.t; sv.pd.par = par; sv.pd.rs = rs; sv.pd.Aq = Aq; sv.pd.fm = fm;
-                ++nbd;
-            } else {
-                service_pass_a(a, &tmap, sc, sv, it, slot, ring0, lane, nad & 1, pol_a, pol_b);
+        sv.nbi = 0; sv.rcb = 0; sv.rc_pending = 0; sv.rc_loaded = 0; sv.hb = 0; sv.nbe = 0;
+        for (int j = 0; j < kSlotsA; ++j) service_issue_a(a, &tmap, sc, sv, j, bufA0, lane, pol_a);
+        for (int j = 0; j < kSlotsB; ++j) service_issue_b(a, &tmap, sc, sv, j, bufB0, lane, pol_b);
+        int nad = 0, nbd = 0;                   // pass-A / pass-B items followed so far
+        for (int I = g; I < a.total_items32; I += G) {
+            if (!(I & 1)) {
+                // the pass-A slot is free once the tile sum is out: refill it
+                const int sa = nad & (kSlotsA - 1);
+                TIC(13);
+                while (!service_background(a, sc, sv, lane, adone0 + 8u * sa, (uint32_t)((nad >> 1) & 1))) { }
+                TOC(13);
+                TIC(14);
+                service_issue_a(a, &tmap, sc, sv, sa, bufA0, lane, pol_a);
+                TOC(14);
                 ++nad;
-                slot = slot == kRing - 1 ? 0 : slot + 1;
+            } else {
+                // the slot of the tile two back is free once its C-phase is complete: refill it
+                const int b = nbd;
+                sv.nbe = b + 1;                 // tile b is on its way: its look-back may be attempted once it is published
+                if (b >= 2) {
+                    const int sC = (b - 2) & (kSlotsB - 1);
+                    TIC(10);
+                    while (!service_background(a, sc, sv, lane, cdone0 + 8u * sC, (uint32_t)(((b - 2) >> 2) & 1))) { }
+                    TOC(10);
+                    TIC(12);
+                    service_issue_b(a, &tmap, sc, sv, sC, bufB0, lane, pol_b);
+                    TOC(12);
+                }
+                ++nbd;
             }
         }
-        while (sv.pd.owed) service_background(a, sc, sv, lane, 0u, 0u);
+        while (sv.hb < sv.nbe || sv.rcb < sv.nbi) {                 // the last tiles' look-backs
+            service_background(a, sc, sv, lane, 0u, 0u);
+            while (sv.rcb < sv.nbi && !((sv.rc_pending >> (sv.rcb & (kSlotsB - 1))) & 1u)) ++sv.rcb;
+        }
     } else {
         // ================================================================== compute warps
-        // software pipeline of depth 2 over the pass-B tiles: stage 1 of tile i+1, the pass-A item between, stage 2 of tile i
-        BState s0, s1;
-        s0.flags = 0; s1.flags = 0;
-        int slot = 0;
-        uint32_t phases = 0;                // phase parity of every ring slot
+        const uint32_t mbarA0 = smem_u32(&sc.mbarA[0]), mbarB0 = smem_u32(&sc.mbarB[0]), ready0 = smem_u32(&sc.ready[0]);
         int nb = 0, na = 0;                 // pass-B / pass-A items started
-        int pend0 = 0, pend1 = 0;           // a stage 2 is owed for state 0 / 1 (its READY barrier must be consumed)
-        auto fetch = [&](Item &it, uint32_t &buf) -> bool {
-            TIC(0);
-            TRACE(1, slot);
-            mbar_wait(mbar0 + 8u * slot, (phases >> slot) & 1u);
-            TRACE(2, slot);
-            TOC(0);
-            phases ^= 1u << slot;
-            it = sc.items[slot];
-            buf = ring0 + (uint32_t)slot * kTile * 4u;
-            slot = slot == kRing - 1 ? 0 : slot + 1;
-            return !(it.flags & kItEnd);
-        };
-        auto run_a = [&](const Item &it, uint32_t buf) { TIC(1); pass_a(a, it, buf, sc, na & 1); TOC(1); ++na; };
-        Item it; uint32_t buf = 0;
-        bool more = fetch(it, buf);
-        if (more && !(it.flags & kItB)) { run_a(it, buf); more = fetch(it, buf); }
-        while (more) {
-            // ---- B item -> state 0
-            {
-                const int par = nb & 1, rs = nb & 3;
+        for (int I = g; I < a.total_items32; I += G) {
+            if (!(I & 1)) {
+                const int sa = na & (kSlotsA - 1);
+                TIC(0);
+                mbar_wait(mbarA0 + 8u * sa, (uint32_t)((na >> 1) & 1));
+                TOC(0);
+                const Item it = sc.itemsA[sa];
+                TIC(1);
+                pass_a(a, it, bufA0 + (uint32_t)sa * kTile * 4u, sc, na & 1, sa);
+                TOC(1);
+                ++na;
+            } else {
+                const int slot = nb & (kSlotsB - 1);
+                TIC(5);
+                mbar_wait(mbarB0 + 8u * slot, (uint32_t)((nb >> 2) & 1));
+                TOC(5);
                 TIC(2);
-                if (it.flags & kItValid) stage1<EMIT>(a, it, buf, park0 + (uint32_t)par * kParkBytes, sc.rc[rs], sc, s0, par);
-                else { s0.flags = 0; mbar_arrive(&sc.b1bar[par]); }
+                phase_b(a, sc.itemsB[slot], bufB0 + (uint32_t)slot * kTile * 4u, sc, slot);
                 TOC(2);
-                pend0 = 1; ++nb;
+                if (nb >= 2) {
+                    const int sC = (nb - 2) & (kSlotsB - 1);
+                    TIC(4);
+                    mbar_wait(ready0 + 8u * sC, (uint32_t)(((nb - 2) >> 2) & 1));
+                    TOC(4);
+                    TIC(3);
+                    phase_c<EMIT>(a, sc, sc.itemsB[sC], bufB0 + (uint32_t)sC * kTile * 4u, sC);
+                    TOC(3);
+                }
+                ++nb;
             }
-            more = fetch(it, buf);
-            if (more && !(it.flags & kItB)) { run_a(it, buf); more = fetch(it, buf); }
-            if (pend1) { TIC(3); stage2<EMIT>(a, sc, park0 + (uint32_t)kParkBytes, s1, 1); TOC(3); pend1 = 0; TRACE(7, 1); }
-            if (!more) break;
-            // ---- B item -> state 1
-            {
-                const int par = nb & 1, rs = nb & 3;
-                TIC(2);
-                if (it.flags & kItValid) stage1<EMIT>(a, it, buf, park0 + (uint32_t)par * kParkBytes, sc.rc[rs], sc, s1, par);
-                else { s1.flags = 0; mbar_arrive(&sc.b1bar[par]); }
-                TOC(2);
-                pend1 = 1; ++nb;
-            }
-            more = fetch(it, buf);
-            if (more && !(it.flags & kItB)) { run_a(it, buf); more = fetch(it, buf); }
-            if (pend0) { TIC(3); stage2<EMIT>(a, sc, park0, s0, 0); TOC(3); pend0 = 0; TRACE(7, 0); }
         }
-        // drain in tile order
-        if (pend0 && pend1) {
-            if (nb & 1) { stage2<EMIT>(a, sc, park0 + (uint32_t)kParkBytes, s1, 1); stage2<EMIT>(a, sc, park0, s0, 0); }
-            else { stage2<EMIT>(a, sc, park0, s0, 0); stage2<EMIT>(a, sc, park0 + (uint32_t)kParkBytes, s1, 1); }
-        } else if (pend0) stage2<EMIT>(a, sc, park0, s0, 0);
-        else if (pend1) stage2<EMIT>(a, sc, park0 + (uint32_t)kParkBytes, s1, 1);
+        for (int b = nb >= 2 ? nb - 2 : 0; b < nb; ++b) {      // drain
+            const int sC = b & (kSlotsB - 1);
+            mbar_wait(ready0 + 8u * sC, (uint32_t)((b >> 2) & 1));
+            phase_c<EMIT>(a, sc, sc.itemsB[sC], bufB0 + (uint32_t)sC * kTile * 4u, sC);
+        }
     }
     if ((a.dbg & 32) && (threadIdx.x == 0 || threadIdx.x == kThreads)) {
         if (threadIdx.x == 0) sc.tacc[6] += gtime();
-#ifdef DME_TIMERS
-        if (blockIdx.x == 0 && threadIdx.x == 0) { sc.tacc[7] = g_polls; g_polls = 0; }
-#endif
         unsigned long long *dst = reinterpret_cast<unsigned long long *>(a.hdr->pad + 1);
         for (int q = (threadIdx.x == 0 ? 0 : 8); q < (threadIdx.x == 0 ? 8 : 16); ++q) atomicAdd(dst + q, sc.tacc[q]);
     }
@@ -1111,7 +1080,7 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
         set_error("code arena too small for the primary slots: %lld < %llu bytes", (long long)codes_bytes, a.pack.arena_base16 * 16ull);
         return DME_EWORKSPACE;
     }
-    const size_t dyn = (size_t)kRing * kTile * sizeof(float) + 2 * kParkBytes + sizeof(Scratch);
+    const size_t dyn = (size_t)(kSlotsA + kSlotsB) * kTile * sizeof(float) + sizeof(Scratch);
     if (g_sms == 0) {
         int dev = 0;
         DME_CUDA(cudaGetDevice(&dev));
@@ -1145,7 +1114,9 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
     if ((G & 1) == 0) --G;                       // odd: every CTA alternates pass-A and pass-B items
     if (G < 1) G = 1;
     a.goff = G / 2 + 16;
-    a.lag = L.T + a.goff + G + 16;
+    // pass B of a row starts 3 steps after the row's finaliser position: the copies of a pass-B tile are issued two
+    // tiles (steps) ahead, and the row constants should be there by then (measured: G+16 -> 3G+16 is 10 % faster)
+    a.lag = L.T + a.goff + 3 * G + 16;
     if (const char *e = getenv("DME_DBG_LAG")) a.lag = L.T + a.goff + atoll(e);
     const int64_t lenA = nT + a.goff + 1, lenB = nT + a.lag;
     a.total_items = 2 * (lenA > lenB ? lenA : lenB);

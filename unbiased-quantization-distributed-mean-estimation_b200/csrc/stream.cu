@@ -693,10 +693,18 @@ __device__ __forceinline__ void phase_c(const StreamArgs &a, Scratch &sc, const 
             // width boundary does it matter whether one of those coordinates also received a unit
             int W = ti.Wlo;
             const bool plain = (ti.Whi == 2);               // every floor is 0: k = r
+            float mxf = 0.0f;                               // the thread's largest floor: most threads have none at all
+            if (!plain) {
+                mxf = fl[0];
+#pragma unroll
+                for (int j = 1; j < kEpt; ++j) mxf = fmaxf(mxf, fl[j]);
+            }
             if (!plain && ti.Wlo != ti.Whi) {
                 bool hit = false;
+                if (mxf == fm) {
 #pragma unroll
-                for (int j = 0; j < kEpt; ++j) hit |= (fl[j] == fm) && ((kw >> (2 * j)) & 1u);
+                    for (int j = 0; j < kEpt; ++j) hit |= (fl[j] == fm) && ((kw >> (2 * j)) & 1u);
+                }
                 W = bar_or(kBarOr, kThreads, hit) ? ti.Whi : ti.Wlo;
             }
             if (fm >= 2147483520.0f && threadIdx.x == 0) atomicOr(&a.hdr->status, 1u);
@@ -722,7 +730,7 @@ __device__ __forceinline__ void phase_c(const StreamArgs &a, Scratch &sc, const 
                 if (W == 2) {
                     // fields [sign | magnitude bit]
                     uint32_t kb = kw;
-                    if (!plain) {
+                    if (mxf != 0.0f) {
                         // largest floor is 1 and no such coordinate received a unit: k = floor + r is still <= 1
 #pragma unroll
                         for (int j = 0; j < kEpt; ++j) kb |= ((fl[j] != 0.0f) ? 1u : 0u) << (2 * j);

@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(64)
 decode_mean_kernel(const uint32_t *__restrict__ codes, const uint64_t *__restrict__ dir, const float *__restrict__ l1,
                    int64_t n, int64_t d, int64_t T, float mf, float nf, int biased, float *__restrict__ mean, int accumulate) {
     __shared__ float lut[kLutClients * kLut];
+    __shared__ uint64_t sdir[kLutClients];      // the tile's directory entries of the staged clients
     const int64_t t = blockIdx.x >> 2;
     const int chunk = (int)(blockIdx.x & 3) * 64 + threadIdx.x;
     const int64_t i0 = t * kTile + (int64_t)chunk * kEpt;
@@ -177,13 +178,14 @@ decode_mean_kernel(const uint32_t *__restrict__ codes, const uint64_t *__restric
         const int k = i & (kLut - 1);
         lut[i] = k == 0 ? 0.0f : deq_over_n(__ldg(l1 + cb + (i >> 3)), (float)k, mf, nf, biased);
     }
+    for (int i = threadIdx.x; i < (int)(ce - cb); i += 64) sdir[i] = __ldg(dir + (cb + i) * T + t);
     __syncthreads();
     if (live)
     for (int64_t c0 = cb; c0 < ce; c0 += kBatch) {
         const int64_t n = ce;                      // batch bound inside this block of clients
         uint64_t e[kBatch];
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u) e[u] = (c0 + u < n) ? __ldg(dir + (c0 + u) * T + t) : 0ull;
+        for (int u = 0; u < kBatch; ++u) e[u] = (c0 + u < n) ? sdir[c0 + u - cb] : 0ull;
         uint32_t w0[kBatch];
         float v1[kBatch];
         bool all2 = true;

@@ -177,3 +177,39 @@ def test_full_size_row_properties(dme):
     bad = int((k[0].cpu().numpy() != o["k"]).sum())
     print(f"d=2^24: {bad} type-vector mismatches vs the sequential-fp64 oracle ({bad / d:.2e} of coordinates)")
     assert bad <= d // 4096                                  # informational bound at this size
+
+
+@pytest.mark.parametrize("X", [0.0, 2.0 ** -24, 0.25, 0.5, 0.75, 1 - 2.0 ** -24, 0.3333333432674408])
+def test_ties_and_binade_crossings_bit_exact(dme, X):
+    """Dyadic rows (every prefix is exact, so the fp32 roundings of AS:636 tie all the time) long enough to cross
+    many binades of the prefix: the closed-form floor of the stream kernel against the literal oracle."""
+    rng = np.random.default_rng(17)
+    d = 3 * 4096 + 777
+    for R in (1, 3, 6):
+        m = dme.m_for_rate(R, d)
+        # |x| multiples of L1/(64 m): m*p is a multiple of 1/64 -> fractions are multiples of 2^-6, prefixes exact
+        q = rng.integers(0, 160, d)
+        q[rng.random(d) < 0.3] = 0
+        x = (q * rng.choice([-1.0, 1.0], d)).astype(np.float32)
+        L1 = np.float32(np.abs(x).astype(np.float64).sum())
+        out = dme.type_quantize(x, R, x_inject=[X], l1_inject=[L1], want=("k", "sgn", "deq"))
+        o = orc.type_unbiased(x, out["m"], X, l1_inject=L1)
+        assert np.array_equal(out["k"].cpu().numpy(), o["k"].astype(np.int32)), (X, R)
+        assert np.array_equal(_u32(out["deq"].cpu().numpy()), _u32(o["deq"])), (X, R)
+        pc = dme.type_encode(x, R, x_inject=[X], l1_inject=[L1])
+        ref = orc.mean_of([o["deq"]])
+        assert np.array_equal(_u32(dme.decode_mean(pc).cpu().numpy()), _u32(ref)), (X, R)
+
+
+@pytest.mark.parametrize("n,d", [(300, 31), (64, 32), (40, 4096 + 33), (700, 4096), (9, 2 * 4096 + 4095)])
+def test_many_short_rows_packed_path(dme, n, d):
+    """Rows shorter than / not aligned to the 128-byte rows of the tensor map, more rows than tile slots in flight:
+    the packed (north-star) path end to end against the oracle."""
+    rng = np.random.default_rng(n * 7 + d)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    for R in (1, 2):
+        m = dme.m_for_rate(R, d)
+        Xs = dme.client_uniforms(seed=11, client0=0, n=n)
+        got = dme.quantize_mean(torch.from_numpy(X).cuda(), R, seed=11).cpu().numpy()
+        ref = orc.mean_of([orc.type_unbiased(X[c], m, float(Xs[c]))["deq"] for c in range(n)])
+        assert np.array_equal(_u32(got), _u32(ref)), (n, d, R)

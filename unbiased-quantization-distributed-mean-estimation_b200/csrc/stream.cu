@@ -46,7 +46,9 @@
 namespace dme {
 
 constexpr int kSlotsA = 2, kSlotsB = 4;  // tile slots in shared memory
-constexpr int kBlock = kThreads + 32;    // 8 compute warps + 1 service warp
+constexpr int kThreadsA = 128;           // pass-A warps (threads kThreads .. kThreads + kThreadsA - 1)
+constexpr int kService = kThreads + kThreadsA;     // first thread of the service warp
+constexpr int kBlock = kService + 32;    // 8 pass-B warps + 4 pass-A warps + 1 service warp
 
 struct __align__(16) Rec { unsigned long long v; uint32_t flag; uint32_t pad; };
 struct __align__(16) Rec2 { unsigned long long lo, hi; };
@@ -100,11 +102,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"      // suspend-time hint: sleep in hardware, do not spin
         "@p bra LAB_DONE;\n"
         "bra LAB_WAIT;\n"
         "LAB_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
+        "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -119,8 +121,8 @@ __device__ __forceinline__ bool bar_or(int id, int n, bool pred) {
         "}\n" : "=r"(r) : "r"(id), "r"(n), "r"((uint32_t)pred) : "memory");
     return r != 0;
 }
-// named barriers: 3,4 = pass-A warp sums are in (by parity), 7 = compute warps only, 8 = compute warps, OR-reduce
-constexpr int kBarPA = 3, kBarCompute = 7, kBarOr = 8;
+// named barriers: 6 = pass-A warps, 7 = pass-B warps, 8 = pass-B warps with OR-reduce
+constexpr int kBarA = 6, kBarCompute = 7, kBarOr = 8;
 
 // one 16 KB box {32 floats, 128 rows, 1 client} at (0, row0, client) of the 3-D tensor map
 __device__ __forceinline__ void tma_tile_g2s(uint32_t dst, const CUtensorMap *map, int row0, int client, uint64_t *bar, uint64_t policy) {
@@ -154,8 +156,8 @@ __device__ unsigned long long g_trace[8192];      // development: event timeline
 __device__ unsigned int g_trace_n;
 #define TRACE(code, val) do { if ((((a.dbg & 64) && blockIdx.x == 100) || ((a.dbg & 128) && (code == 11 || code == 12 || code == 3) && blockIdx.x >= 96 && blockIdx.x < 160)) && (threadIdx.x == 0 || threadIdx.x == kThreads)) { \
         const unsigned int _i = atomicAdd(&g_trace_n, 1u); if (_i < 4096) { g_trace[2 * _i] = gtime(); g_trace[2 * _i + 1] = ((unsigned long long)(code) << 32) | ((unsigned long long)(blockIdx.x & 0xfff) << 20) | ((unsigned int)(val) & 0xfffff); } } } while (0)
-#define TIC(k) do { if ((a.dbg & 32) && threadIdx.x == (k >= 8 ? kThreads : 0)) sc.tacc[k] -= gtime(); } while (0)
-#define TOC(k) do { if ((a.dbg & 32) && threadIdx.x == (k >= 8 ? kThreads : 0)) sc.tacc[k] += gtime(); } while (0)
+#define TIC(k) do { if ((a.dbg & 32) && threadIdx.x == (k >= 8 ? kService : k <= 1 ? kThreads : 0)) sc.tacc[k] -= gtime(); } while (0)
+#define TOC(k) do { if ((a.dbg & 32) && threadIdx.x == (k >= 8 ? kService : k <= 1 ? kThreads : 0)) sc.tacc[k] += gtime(); } while (0)
 #else
 #define TRACE(code, val) do { } while (0)
 #define TIC(k) do { } while (0)
@@ -303,29 +305,30 @@ __device__ __forceinline__ void make_row_const(const StreamArgs &a, int64_t c, d
     if (a.l1_out) a.l1_out[c] = rc.L1f;
 }
 
-// Cold path (compute warps): reduce row `row`'s tile sums in a fixed order (thread-strided, then warp trees in
-// index order), publish the row.
+// Cold path (pass-A warps): reduce row `row`'s tile sums in a fixed order (thread-strided, then warp trees in index
+// order), publish the row.
 __device__ __noinline__ void finalize_row(const StreamArgs &a, int row, Scratch &sc) {
+    const int ta = threadIdx.x - kThreads;
     const Rec *pp = a.partial + (int64_t)row * a.T;
     double acc = 0.0;
-    for (int64_t i = threadIdx.x; i < a.T; i += kThreads) {
+    for (int64_t i = ta; i < a.T; i += kThreadsA) {
         unsigned long long v;
         while (rec_load(pp + i, v) == 0u) __nanosleep(64);
         acc += __longlong_as_double((long long)v);
     }
     acc = warp_sum_f64(acc);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = ta & 31, warp = ta >> 5;
     if (lane == 0) sc.red[warp] = acc;
-    bar_sync(kBarCompute, kThreads);
-    if (threadIdx.x == 0) {
+    bar_sync(kBarA, kThreadsA);
+    if (ta == 0) {
         double t = sc.red[0];
 #pragma unroll
-        for (int w = 1; w < kWarps; ++w) t += sc.red[w];
+        for (int w = 1; w < kThreadsA / 32; ++w) t += sc.red[w];
         make_row_const(a, row, t);
         __threadfence();
         st_release_u32(&a.row_ready[row], 1u);
     }
-    bar_sync(kBarCompute, kThreads);
+    bar_sync(kBarA, kThreadsA);
 }
 
 // AS:625-631 for one coordinate, literal: IEEE division + floorf.
@@ -357,38 +360,38 @@ __device__ __forceinline__ uint32_t blocked_off_of(uint32_t tid) {
 }
 __device__ __forceinline__ uint32_t blocked_off() { return blocked_off_of(threadIdx.x); }
 
-// |x| of the row's coordinate rows32 * 32 + tid when it exists (the d % 32 coordinates the tensor map does not cover)
-__device__ __noinline__ double row_tail_abs(const StreamArgs &a, int c) {
-    if (threadIdx.x >= (uint32_t)(a.d & 31)) return 0.0;
-    return (double)fabsf(a.X[(int64_t)c * a.ld + a.rows32 * 32 + threadIdx.x]);
+// |x| of the row's coordinate rows32 * 32 + ta when it exists (the d % 32 coordinates the tensor map does not cover)
+__device__ __noinline__ double row_tail_abs(const StreamArgs &a, int c, int ta) {
+    if (ta >= (int)(a.d & 31)) return 0.0;
+    return (double)fabsf(a.X[(int64_t)c * a.ld + a.rows32 * 32 + ta]);
 }
-// ---- pass A of one tile: warp sums to shared memory, the service warp finishes them
+// ---- pass A of one tile (the 4 pass-A warps): warp sums to shared memory; the warp that finishes last adds them
+// (fixed order), publishes the tile sum and frees the slot
 __device__ __forceinline__ void pass_a(const StreamArgs &a, const Item &it, uint32_t buf, Scratch &sc, int parity, int slotA) {
+    const int ta = threadIdx.x - kThreads, lane = ta & 31;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     if (it.flags & kItTma) {
-        // any order will do: physical 16-byte chunks q*256 + tid (conflict-free), fixed association
+        // any order will do: physical 16-byte chunks q*128 + ta (conflict-free), fixed association
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 v = lds128(buf + (uint32_t)(q * kThreads + threadIdx.x) * 16u);
+        for (int q = 0; q < kTile / 4 / kThreadsA; ++q) {
+            const float4 v = lds128(buf + (uint32_t)(q * kThreadsA + ta) * 16u);
             s0 += (double)fabsf(v.x); s1 += (double)fabsf(v.y); s2 += (double)fabsf(v.z); s3 += (double)fabsf(v.w);
         }
     }
-    if (it.flags & kItTail) s0 += row_tail_abs(a, it.c);
+    if (it.flags & kItTail) s0 += row_tail_abs(a, it.c, ta);
     const double ws = warp_sum_f64((s0 + s1) + (s2 + s3));      // fixed association
-    const int lane = threadIdx.x & 31;
     unsigned int old = 0;
     if (lane == 0) {
-        sc.wsumA[parity][threadIdx.x >> 5] = ws;
+        sc.wsumA[parity][ta >> 5] = ws;
         __threadfence_block();
         old = atomicAdd(&sc.cntA[parity], 1u);
     }
     old = __shfl_sync(0xffffffffu, old, 0);
-    if (old == kWarps - 1) {
-        // the warp that finishes last adds the 8 warp sums (fixed order), publishes the tile sum and frees the slot
+    if (old == kThreadsA / 32 - 1) {
         __threadfence_block();
-        double tot = lane < kWarps ? sc.wsumA[parity][lane] : 0.0;
+        double tot = lane < kThreadsA / 32 ? sc.wsumA[parity][lane] : 0.0;
 #pragma unroll
-        for (int o = kWarps / 2; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        for (int o = kThreadsA / 64; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
         if (lane == 0) {
             if (it.flags & kItValid) rec_store(&a.partial[(int64_t)it.c * a.T + it.t], (unsigned long long)__double_as_longlong(tot), 1u);
             sc.cntA[parity] = 0;
@@ -809,7 +812,7 @@ __device__ __forceinline__ void service_rc_copy(const StreamArgs &a, Scratch &sc
 __device__ __forceinline__ bool service_background(const StreamArgs &a, Scratch &sc, Service &sv, int lane, uint32_t bar, uint32_t parity) {
     // look-back: tile hb, once it is published
     const int lslot = sv.hb & (kSlotsB - 1);
-    bool lb = sv.hb < sv.nbe && mbar_test(smem_u32(&sc.pub[lslot]), (uint32_t)((sv.hb >> 2) & 1));
+    bool lb = sv.hb < sv.nbe && mbar_test(smem_u32(&sc.pub[lslot]), (uint32_t)((sv.hb >> 2) & 1));      // nbe = all pass-B items of the CTA
     Item lit; lit.c = 0; lit.t = 0; lit.flags = 0; lit.fin_row = -1;
     PubInfo pi; pi.Aq = 0; pi.fm = 0; pi.valid = 0;
     if (lb) { lit = sc.itemsB[lslot]; pi = sc.pubinfo[lslot]; }
@@ -963,7 +966,7 @@ quantize_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_consta
     const uint32_t bufA0 = smem_u32(dyn_smem);                          // SWIZZLE_128B wants 1024-byte aligned boxes
     const uint32_t bufB0 = bufA0 + (uint32_t)kSlotsA * kTile * 4u;
 
-    if (threadIdx.x >= kThreads) {
+    if (threadIdx.x >= kService) {
         // ================================================================== service warp
         const int lane = threadIdx.x & 31;
         uint64_t pol_a = policy_evict_last(), pol_b = policy_evict_first();
@@ -973,72 +976,75 @@ quantize_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_consta
         sv.nbi = 0; sv.rcb = 0; sv.rc_pending = 0; sv.rc_loaded = 0; sv.hb = 0; sv.nbe = 0;
         for (int j = 0; j < kSlotsA; ++j) service_issue_a(a, &tmap, sc, sv, j, bufA0, lane, pol_a);
         for (int j = 0; j < kSlotsB; ++j) service_issue_b(a, &tmap, sc, sv, j, bufB0, lane, pol_b);
-        int nad = 0, nbd = 0;                   // pass-A / pass-B items followed so far
-        for (int I = g; I < a.total_items32; I += G) {
-            if (!(I & 1)) {
-                // the pass-A slot is free once the tile sum is out: refill it
-                const int sa = nad & (kSlotsA - 1);
-                TIC(13);
-                while (!service_background(a, sc, sv, lane, adone0 + 8u * sa, (uint32_t)((nad >> 1) & 1))) { }
-                TOC(13);
+        // event loop: whichever group frees a slot first gets it refilled first; look-backs and row constants in between
+        int nA = 0, nB = 0;                     // items of each kind this CTA owns
+        for (int I = g; I < a.total_items32; I += G) { if (I & 1) ++nB; else ++nA; }
+        sv.nbe = nB;
+        int ia = 0, ib = 0;                     // pass-A items whose slot has been refilled / pass-B items followed
+        while (ia < nA || ib < nB || sv.hb < nB || sv.rcb < sv.nbi) {
+            if (ia < nA && mbar_test(adone0 + 8u * (ia & (kSlotsA - 1)), (uint32_t)((ia >> 1) & 1))) {
                 TIC(14);
-                service_issue_a(a, &tmap, sc, sv, sa, bufA0, lane, pol_a);
+                service_issue_a(a, &tmap, sc, sv, ia & (kSlotsA - 1), bufA0, lane, pol_a);
                 TOC(14);
-                ++nad;
-            } else {
-                // the slot of the tile two back is free once its C-phase is complete: refill it
-                const int b = nbd;
-                sv.nbe = b + 1;                 // tile b is on its way: its look-back may be attempted once it is published
-                if (b >= 2) {
-                    const int sC = (b - 2) & (kSlotsB - 1);
-                    TIC(10);
-                    while (!service_background(a, sc, sv, lane, cdone0 + 8u * sC, (uint32_t)(((b - 2) >> 2) & 1))) { }
-                    TOC(10);
-                    TIC(12);
-                    service_issue_b(a, &tmap, sc, sv, sC, bufB0, lane, pol_b);
-                    TOC(12);
-                }
-                ++nbd;
+                ++ia;
             }
-        }
-        while (sv.hb < sv.nbe || sv.rcb < sv.nbi) {                 // the last tiles' look-backs
+            if (ib < nB) {
+                if (ib < 2) ++ib;               // the first two tiles have nothing behind them to wait for
+                else {
+                    const int sC = (ib - 2) & (kSlotsB - 1);
+                    if (mbar_test(cdone0 + 8u * sC, (uint32_t)(((ib - 2) >> 2) & 1))) {
+                        // the slot of the tile two back is free once its C-phase is complete: refill it
+                        TIC(12);
+                        service_issue_b(a, &tmap, sc, sv, sC, bufB0, lane, pol_b);
+                        TOC(12);
+                        ++ib;
+                    }
+                }
+            }
+            TIC(10);
             service_background(a, sc, sv, lane, 0u, 0u);
+            TOC(10);
             while (sv.rcb < sv.nbi && !((sv.rc_pending >> (sv.rcb & (kSlotsB - 1))) & 1u)) ++sv.rcb;
         }
-    } else {
-        // ================================================================== compute warps
-        const uint32_t mbarA0 = smem_u32(&sc.mbarA[0]), mbarB0 = smem_u32(&sc.mbarB[0]), ready0 = smem_u32(&sc.ready[0]);
-        int nb = 0, na = 0;                 // pass-B / pass-A items started
+    } else if (threadIdx.x >= kThreads) {
+        // ================================================================== pass-A warps
+        const uint32_t mbarA0 = smem_u32(&sc.mbarA[0]);
+        int na = 0;
         for (int I = g; I < a.total_items32; I += G) {
-            if (!(I & 1)) {
-                const int sa = na & (kSlotsA - 1);
-                TIC(0);
-                mbar_wait(mbarA0 + 8u * sa, (uint32_t)((na >> 1) & 1));
-                TOC(0);
-                const Item it = sc.itemsA[sa];
-                TIC(1);
-                pass_a(a, it, bufA0 + (uint32_t)sa * kTile * 4u, sc, na & 1, sa);
-                TOC(1);
-                ++na;
-            } else {
-                const int slot = nb & (kSlotsB - 1);
-                TIC(5);
-                mbar_wait(mbarB0 + 8u * slot, (uint32_t)((nb >> 2) & 1));
-                TOC(5);
-                TIC(2);
-                phase_b(a, sc.itemsB[slot], bufB0 + (uint32_t)slot * kTile * 4u, sc, slot);
-                TOC(2);
-                if (nb >= 2) {
-                    const int sC = (nb - 2) & (kSlotsB - 1);
-                    TIC(4);
-                    mbar_wait(ready0 + 8u * sC, (uint32_t)(((nb - 2) >> 2) & 1));
-                    TOC(4);
-                    TIC(3);
-                    phase_c<EMIT>(a, sc, sc.itemsB[sC], bufB0 + (uint32_t)sC * kTile * 4u, sC);
-                    TOC(3);
-                }
-                ++nb;
+            if (I & 1) continue;
+            const int sa = na & (kSlotsA - 1);
+            TIC(0);
+            mbar_wait(mbarA0 + 8u * sa, (uint32_t)((na >> 1) & 1));
+            TOC(0);
+            const Item it = sc.itemsA[sa];
+            TIC(1);
+            pass_a(a, it, bufA0 + (uint32_t)sa * kTile * 4u, sc, na & 1, sa);
+            TOC(1);
+            ++na;
+        }
+    } else {
+        // ================================================================== pass-B warps
+        const uint32_t mbarB0 = smem_u32(&sc.mbarB[0]), ready0 = smem_u32(&sc.ready[0]);
+        int nb = 0;                         // pass-B items started
+        for (int I = g; I < a.total_items32; I += G) {
+            if (!(I & 1)) continue;
+            const int slot = nb & (kSlotsB - 1);
+            TIC(5);
+            mbar_wait(mbarB0 + 8u * slot, (uint32_t)((nb >> 2) & 1));
+            TOC(5);
+            TIC(2);
+            phase_b(a, sc.itemsB[slot], bufB0 + (uint32_t)slot * kTile * 4u, sc, slot);
+            TOC(2);
+            if (nb >= 2) {
+                const int sC = (nb - 2) & (kSlotsB - 1);
+                TIC(4);
+                mbar_wait(ready0 + 8u * sC, (uint32_t)(((nb - 2) >> 2) & 1));
+                TOC(4);
+                TIC(3);
+                phase_c<EMIT>(a, sc, sc.itemsB[sC], bufB0 + (uint32_t)sC * kTile * 4u, sC);
+                TOC(3);
             }
+            ++nb;
         }
         for (int b = nb >= 2 ? nb - 2 : 0; b < nb; ++b) {      // drain
             const int sC = b & (kSlotsB - 1);
@@ -1046,10 +1052,11 @@ quantize_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_consta
             phase_c<EMIT>(a, sc, sc.itemsB[sC], bufB0 + (uint32_t)sC * kTile * 4u, sC);
         }
     }
-    if ((a.dbg & 32) && (threadIdx.x == 0 || threadIdx.x == kThreads)) {
+    if ((a.dbg & 32) && (threadIdx.x == 0 || threadIdx.x == kThreads || threadIdx.x == kService)) {
         if (threadIdx.x == 0) sc.tacc[6] += gtime();
         unsigned long long *dst = reinterpret_cast<unsigned long long *>(a.hdr->pad + 1);
-        for (int q = (threadIdx.x == 0 ? 0 : 8); q < (threadIdx.x == 0 ? 8 : 16); ++q) atomicAdd(dst + q, sc.tacc[q]);
+        const int q0 = threadIdx.x == 0 ? 2 : threadIdx.x == kThreads ? 0 : 8, q1 = threadIdx.x == 0 ? 8 : threadIdx.x == kThreads ? 2 : 16;
+        for (int q = q0; q < q1; ++q) atomicAdd(dst + q, sc.tacc[q]);
     }
 }
 

@@ -24,7 +24,10 @@ for n, d in shapes:
         k = L.dme_profile_read(buf, 8)
         res.append([round(buf[j], 3) for j in range(k)])
     L.dme_profile_enable(0)
-    dme.Workspace.get(X.device).status()
+    try:
+        dme.Workspace.get(X.device).status()
+    except Exception as ex:
+        print('status:', type(ex).__name__)
     balg = 4.0 * n * d + 4.0 * d
     t = sum(res[-1])
     print(f"n={n} d={d} env={os.environ.get('DME_DBG','')}/{os.environ.get('DME_DBG_LAG','')}/{os.environ.get('DME_DBG_G','')}: kernels ms {res[1:]}  -> {balg / t * 1e-6:.0f} GB/s alg", flush=True)

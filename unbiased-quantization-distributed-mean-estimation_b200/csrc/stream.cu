@@ -133,9 +133,6 @@ __device__ __forceinline__ void tma_tile_g2s(uint32_t dst, const CUtensorMap *ma
 __device__ __forceinline__ uint64_t policy_evict_last() {
     uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
 }
-__device__ __forceinline__ uint64_t policy_evict_normal() {
-    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); return p;
-}
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
 }
@@ -172,6 +169,7 @@ struct StreamArgs {
     int64_t lag, goff, total_items, G;
     int step_c, step_t;                    // G = step_c * T + step_t: per-item advance of (client, tile) without a division
     int total_items32, tiles_tma, has_tail;
+    int ahead;                             // how many items pass A may lead pass B inside a CTA (see the service loop)
     int32_t *k_out; uint8_t *sgn_out; float *deq_out; int64_t ld_out;     // array outputs
     PackTarget pack; int packed;                                        // packed output
     int dbg;                                                            // development: bit 5 = phase timers
@@ -923,15 +921,6 @@ __device__ __forceinline__ void service_issue_b(const StreamArgs &a, const CUten
         if (!later) mbar_arrive(&sc.mbarB[slot]);
     }
     if (later) sv.rc_pending |= 1u << slot;
-#ifdef DME_TIMERS
-    if ((a.dbg & 256) && !later && (it.flags & kItValid) && (it.flags & kItTma)) {      // experiment: raw latency of the copy
-        TIC(15);
-        const uint32_t par = (uint32_t)((sv.nbi >> 2) & 1);
-        while (!mbar_test(smem_u32(&sc.mbarB[slot]), par)) { }
-        TOC(15);
-        if (lane == 0) sc.tacc[11] += 1000;
-    }
-#endif
     ++sv.nbi;
     __syncwarp();
 }
@@ -969,7 +958,7 @@ quantize_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_consta
     if (threadIdx.x >= kService) {
         // ================================================================== service warp
         const int lane = threadIdx.x & 31;
-        uint64_t pol_a = policy_evict_last(), pol_b = policy_evict_first();
+        const uint64_t pol_a = policy_evict_last(), pol_b = policy_evict_first();
         const uint32_t adone0 = smem_u32(&sc.adone[0]), cdone0 = smem_u32(&sc.cdone[0]);
         Service sv;
         sv.dec.init(a, g);
@@ -981,8 +970,12 @@ quantize_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_consta
         for (int I = g; I < a.total_items32; I += G) { if (I & 1) ++nB; else ++nA; }
         sv.nbe = nB;
         int ia = 0, ib = 0;                     // pass-A items whose slot has been refilled / pass-B items followed
+        const int kAhead = a.ahead;
         while (ia < nA || ib < nB || sv.hb < nB || sv.rcb < sv.nbi) {
-            if (ia < nA && mbar_test(adone0 + 8u * (ia & (kSlotsA - 1)), (uint32_t)((ia >> 1) & 1))) {
+            // rows that fit in L2 together with the lag window: pass A must not run ahead of pass B by more than the
+            // designed lag (+ the slots in flight), so that pass B re-reads the row from L2 (measured: DRAM reads 1.0x
+            // the input at d = 2^20).  Longer rows do not fit anyway; there the two passes run free (faster).
+            if (ia < nA && (ia <= ib + kAhead || ib >= nB) && mbar_test(adone0 + 8u * (ia & (kSlotsA - 1)), (uint32_t)((ia >> 1) & 1))) {
                 TIC(14);
                 service_issue_a(a, &tmap, sc, sv, ia & (kSlotsA - 1), bufA0, lane, pol_a);
                 TOC(14);
@@ -1129,9 +1122,9 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
     if ((G & 1) == 0) --G;                       // odd: every CTA alternates pass-A and pass-B items
     if (G < 1) G = 1;
     a.goff = G / 2 + 16;
-    // pass B of a row starts 3 steps after the row's finaliser position: the copies of a pass-B tile are issued two
-    // tiles (steps) ahead, and the row constants should be there by then (measured: G+16 -> 3G+16 is 10 % faster)
-    a.lag = L.T + a.goff + 3 * G + 16;
+    a.lag = L.T + a.goff + G + 16;
+    a.ahead = (d <= ((int64_t)1 << 22)) ? 1 : (1 << 20);
+    if (const char *e = getenv("DME_DBG_AHEAD")) a.ahead = atoi(e);
     if (const char *e = getenv("DME_DBG_LAG")) a.lag = L.T + a.goff + atoll(e);
     const int64_t lenA = nT + a.goff + 1, lenB = nT + a.lag;
     a.total_items = 2 * (lenA > lenB ? lenA : lenB);

@@ -263,44 +263,11 @@ struct Scratch {
     unsigned long long tacc[16];         // phase timers (dbg): 0-7 compute thread 0, 8-15 service lane 0
 };
 
-// Row constants + the binade table of AS:636's closed form (cold: once per client row).
 __device__ __forceinline__ void make_row_const(const StreamArgs &a, int64_t c, double l1sum) {
-    RowConst rc;
-    rc.L1f = a.l1_inject ? a.l1_inject[c] : (float)l1sum;           // AS:624
-    rc.D = __fadd_rn(rc.L1f, 1e-12f);                               // AS:625
-    rc.mf = (float)a.m;
-    rc.X = a.x_inject ? a.x_inject[c] : philox_client_uniform(a.seed, a.client0 + (uint64_t)c);   // AS:634
-    rc.rcpD = __frcp_rn(rc.D);
-    uint32_t fl = 0;
-    // The fast chain (Markstein division, magic-number floor) is proven for these operand ranges only;
-    // anything else takes the IEEE-div / floorf instantiation.  See DESIGN.md "Exactness of the fast chain".
-    if (!(rc.D >= 9.5367431640625e-07f && rc.D <= 1.2676506e30f)) fl |= kRowExact;            // 2^-20 .. 2^100
-    if ((__float_as_uint(rc.D) & 0x7fffffu) == 0x7fffffu) fl |= kRowExact;                      // 1/D rounding exception
-    if (!(rc.X == 0.0f || (rc.X >= 5.9604644775390625e-08f && rc.X < 1.0f))) fl |= kRowExact;  // X on torch.rand's range
-    if (!(rc.mf <= 4194304.0f) || a.l1_inject) fl |= kRowGuardFloor;                            // m*p may reach 2^23
-    rc.flags = fl;
-    int lg = 0;
-    while (((int64_t)1 << lg) < a.d) ++lg;
-    rc.qshift = min(50, 62 - lg);
-    rc.pad0 = 0;
-    rc.q_up = __longlong_as_double((long long)(1023 + rc.qshift) << 52);
-    rc.q_dn = __longlong_as_double((long long)(1023 - rc.qshift) << 52);
-    rc.pad1[0] = rc.pad1[1] = 0.0;
-    a.consts[c] = rc;
-    BinadeEntry *tab = a.tabs + c * kBinades;
-    const double Xd = (double)rc.X;
-#pragma unroll 1
-    for (int e = 0; e < kBinades; ++e) {
-        BinadeEntry b; b.Xp = 0.0; b.sigma = 0.0;
-        if (!(fl & kRowExact) && e >= 2 && e <= 22) {
-            const double g = __longlong_as_double((long long)(1023 + e - 23) << 52), ginv = __longlong_as_double((long long)(1023 + 23 - e) << 52);
-            const double av = ceil(Xd * ginv - 0.5);                 // exact: X has 24 bits, X >= 2^-24 or X == 0
-            b.sigma = (((long long)av) & 1) ? -1.0 : 1.0;
-            b.Xp = -b.sigma * (g * (av - 0.5));                      // stored as -sigma * Xp: sigma (c - Xp) = fma(c, sigma, b.Xp)
-        }
-        tab[e] = b;
-    }
-    if (a.l1_out) a.l1_out[c] = rc.L1f;
+    RowConstIn in;
+    in.m = a.m; in.d = a.d; in.x_inject = a.x_inject; in.l1_inject = a.l1_inject; in.seed = a.seed; in.client0 = a.client0;
+    in.consts = a.consts; in.tabs = a.tabs; in.l1_out = a.l1_out;
+    make_row_const(in, c, l1sum);
 }
 
 // Cold path (pass-A warps): reduce row `row`'s tile sums in a fixed order (thread-strided, then warp trees in index
@@ -348,6 +315,9 @@ __device__ __forceinline__ f2 f2_sub(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %
 
 #ifndef DME_X2
 #define DME_X2 1
+#endif
+#ifndef DME_C_F2F
+#define DME_C_F2F 0       // 1: fp32 -> fp64 conversions of the C-phase on the conversion unit instead of integer moves
 #endif
 
 // swizzled shared-memory offset of the 16-byte chunk q (0..3) of thread tid's 16 coordinates inside a 16 KB tile
@@ -447,8 +417,8 @@ __device__ __forceinline__ void floors_and_fracs(const float (&x)[kEpt], const R
     }
 }
 // the tile's coordinates owned by this thread, from the staged tile (+ the row tail straight from global)
-__device__ __forceinline__ void load_x(const StreamArgs &a, uint32_t flags, int c, int t, uint32_t buf, float (&x)[kEpt]) {
-    const uint32_t off = blocked_off();
+__device__ __forceinline__ void load_x(const StreamArgs &a, uint32_t flags, int c, int t, uint32_t buf, float (&x)[kEpt], int chunk) {
+    const uint32_t off = blocked_off_of((uint32_t)chunk);
     if (flags & kItTma) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -460,7 +430,7 @@ __device__ __forceinline__ void load_x(const StreamArgs &a, uint32_t flags, int 
         for (int j = 0; j < kEpt; ++j) x[j] = 0.0f;
     }
     if (flags & kItTail) {          // the last d % 32 coordinates of the row are not covered by the tensor map
-        const int64_t i0 = (int64_t)t * kTile + (int64_t)threadIdx.x * kEpt, lo = a.rows32 * 32;
+        const int64_t i0 = (int64_t)t * kTile + (int64_t)chunk * kEpt, lo = a.rows32 * 32;
         const float *row = a.X + (int64_t)c * a.ld;
         if (i0 + kEpt > lo && i0 < a.d) {
 #pragma unroll
@@ -468,6 +438,9 @@ __device__ __forceinline__ void load_x(const StreamArgs &a, uint32_t flags, int 
                 if (i0 + j >= lo && i0 + j < a.d) x[j] = row[i0 + j];
         }
     }
+}
+__device__ __forceinline__ void load_x(const StreamArgs &a, uint32_t flags, int c, int t, uint32_t buf, float (&x)[kEpt]) {
+    load_x(a, flags, c, t, buf, x, (int)threadIdx.x);          // one chunk per thread
 }
 
 // ---- B-phase: thread sums of the fractional parts, their scan inside each warp, warp totals, largest floor
@@ -592,7 +565,11 @@ __device__ __forceinline__ uint32_t rbits_interleaved(const Geo &g, const float 
         int L14 = 0;
 #pragma unroll
         for (int j = 0; j < kEpt - 1; ++j) {
+#if DME_C_F2F
+            u = fma((double)fr[j], g.sig, u);
+#else
             u = fma(frac_to_double(fr[j]), g.sig, u);
+#endif
             const int L = floor_lo(u);
             // sum_j (L_j - L_{j-1}) 4^j  =  -L_{-1} - sum_{j<14} 3 * 4^j L_j + 4^14 L_14
             if (j < kEpt - 2) acc += (uint32_t)L * (0u - (3u << (2 * j)));
@@ -619,11 +596,9 @@ __device__ __forceinline__ uint32_t rbits_interleaved(const Geo &g, const float 
 }
 
 // fields of 4 / 8 / 16 / 32 bits (cold: kept out of line)
-__device__ __noinline__ void emit_wide(const StreamArgs &a, uint32_t flags, int c, int t, uint32_t buf, const RowConst &rc, uint32_t kw, uint32_t sgw, int W,
-                                       uint32_t *tw) {
-    float x[kEpt], fl[kEpt], fr[kEpt];
-    load_x(a, flags, c, t, buf, x);                        // the floors again: same function of the same inputs
-    floors_and_fracs(x, rc, fl, fr);
+__device__ __noinline__ void emit_wide_x(const float (&x)[kEpt], const RowConst &rc, uint32_t kw, uint32_t sgw, int W, uint32_t *tw, int chunk) {
+    float fl[kEpt], fr[kEpt];
+    floors_and_fracs(x, rc, fl, fr);                       // the floors again: same function of the same inputs
     uint32_t k[kEpt], sg[kEpt];
 #pragma unroll
     for (int j = 0; j < kEpt; ++j) {
@@ -632,10 +607,31 @@ __device__ __noinline__ void emit_wide(const StreamArgs &a, uint32_t flags, int 
         sg[j] = (sgw >> (2 * j + 1)) & 1u;
     }
     switch (W) {
-        case 4: pack_store<4>(k, sg, tw); break;
-        case 8: pack_store<8>(k, sg, tw); break;
-        case 16: pack_store<16>(k, sg, tw); break;
-        default: pack_store<32>(k, sg, tw); break;
+        case 4: pack_store<4>(k, sg, tw, chunk); break;
+        case 8: pack_store<8>(k, sg, tw, chunk); break;
+        case 16: pack_store<16>(k, sg, tw, chunk); break;
+        default: pack_store<32>(k, sg, tw, chunk); break;
+    }
+}
+__device__ __forceinline__ void emit_wide(const StreamArgs &a, uint32_t flags, int c, int t, uint32_t buf, const RowConst &rc, uint32_t kw, uint32_t sgw, int W,
+                                          uint32_t *tw) {
+    float x[kEpt];
+    load_x(a, flags, c, t, buf, x);
+    emit_wide_x(x, rc, kw, sgw, W, tw, (int)threadIdx.x);
+}
+// the thread's 16 coordinates of tile t of client c straight from global memory (cold paths of the tiles kernel)
+__device__ __noinline__ void load_x_global(const StreamArgs &a, int c, int t, float (&x)[kEpt], int chunk) {
+    const int64_t i0 = (int64_t)t * kTile + (int64_t)chunk * kEpt;
+    const float *row = a.X + (int64_t)c * a.ld;
+    if (i0 + kEpt <= a.d) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4 *>(row + i0 + 4 * q);
+            x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) x[j] = (i0 + j < a.d) ? row[i0 + j] : 0.0f;
     }
 }
 
@@ -1053,11 +1049,343 @@ quantize_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_consta
     }
 }
 
-static int g_sms = 0, g_occ[2] = {0, 0};
+// ====================================================================================================================
+// Two-kernel path: l1_kernel (type_quantize.cu) has published every row's constants; this kernel makes ONE pass over the
+// tiles in ticket order (client-major) with the same decoupled look-back records as above.  Per CTA and iteration:
+//   B-phase of tile i   : floors, fractional parts (parked in place of x in the tile buffer), thread sums, scans;
+//   warp 0              : publish tile i's aggregate, resolve the look-back of tile i-1 (published one iteration ago:
+//                         normally nothing to wait for);
+//   C-phase of tile i-1 : prefix -> floor(c - X) -> type vector, emit;
+//   then the next ticket is taken and its tile copied into the buffer just freed (ring of three).
+// No aggregate ever waits for a look-back, so the tiles of a row flow without convoys.  Every wait is on a smaller
+// ticket held by a resident CTA that does not wait on a larger one: no deadlock.
+struct __align__(16) TItem { int c, t; uint32_t flags; uint32_t ticket; };
+struct TScratch {
+    Rec win[2][96];              // look-back window of the C tile (tile / block / super-block records), by iteration parity
+    double wtot[2][kWarps];      // warp totals of the B tile, by iteration parity
+    uint32_t flmaxw[2][kWarps];
+    TItem item[3];
+    uint64_t mbar[3];
+    unsigned int hit[2];
+    int rc_row[2];
+    unsigned long long off16;
+    long long pfb;               // look-back result of the fallback path
+    RowConst rc[2];
+    BinadeEntry tab[2][kBinades];
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// thread 0: take the next ticket, decode it into item slot `slot` and start the tile's copy into buffer `slot`
+__device__ __forceinline__ void tiles_take(const StreamArgs &a, const CUtensorMap *tmap, TScratch &sc, int slot, uint32_t buf0, uint64_t pol, bool take) {
+    TItem it; it.c = 0; it.t = 0; it.flags = 0; it.ticket = 0xffffffffu;
+    if (take) {
+        const unsigned int tk = atomicAdd(&a.hdr->ticket, 1u);
+        if ((long long)tk < a.n * a.T) {
+            it.ticket = tk;
+            it.c = (int)(tk / (unsigned int)a.T); it.t = (int)(tk - (unsigned int)it.c * (unsigned int)a.T);
+            it.flags = kItValid;
+            if (it.t < a.tiles_tma) it.flags |= kItTma;
+            if (it.t == (int)a.T - 1 && a.has_tail) it.flags |= kItTail;
+            if (it.flags & kItTma) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&sc.mbar[slot], (uint32_t)kTile * 4u);
+                tma_tile_g2s(buf0 + (uint32_t)slot * kTile * 4u, tmap, it.t * (kTile / 32), it.c, &sc.mbar[slot], pol);
+            } else {
+                mbar_arrive(&sc.mbar[slot]);
+            }
+        }
+    }
+    sc.item[slot] = it;
+}
+
+// warp 0: start the copies of tile t's look-back window (earlier tiles of its block, earlier blocks of its super-block,
+// earlier super-blocks) into shared memory; entries that do not exist are filled with complete neutral records
+__device__ __forceinline__ void window_prefetch(const StreamArgs &a, Rec *win, int c, int t, int lane) {
+    const TileRec *tiles = a.desc + (int64_t)c * a.T;
+    const Rec2 *blocks = a.blocks + (int64_t)c * a.TB, *supers = a.supers + (int64_t)c * a.TS;
+    const int b = t >> 5, pos = t & 31, sb = b >> 5, bpos = b & 31;
+    if (lane < pos) cp_async16(smem_u32(&win[lane]), tiles + (t - 1 - lane));
+    else { Rec r; r.v = 0; r.flag = 1u; r.pad = 0; win[lane] = r; }
+    Rec2 *w2 = reinterpret_cast<Rec2 *>(win);
+    if (lane < bpos) cp_async16(smem_u32(&w2[32 + lane]), blocks + (sb * 32 + lane));
+    else { Rec2 r; r.lo = r.hi = 32ull << kCntShift; w2[32 + lane] = r; }
+    if (lane < sb) cp_async16(smem_u32(&w2[64 + lane]), supers + lane);
+    else { Rec2 r; r.lo = r.hi = 1024ull << kCntShift; w2[64 + lane] = r; }
+}
+// any warp: exclusive fixed-point prefix of tile t from the window; false when a record was not complete yet
+__device__ __forceinline__ bool window_eval(const Rec *win, int lane, long long &P) {
+    const uint4 tr = *reinterpret_cast<const uint4 *>(&win[lane]);
+    const Rec2 *w2 = reinterpret_cast<const Rec2 *>(win);
+    const Rec2 br = w2[32 + lane], sr = w2[64 + lane];
+    const bool ok = tr.z != 0u && (br.lo >> kCntShift) == 32ull && (br.hi >> kCntShift) == 32ull && (sr.lo >> kCntShift) == 1024ull &&
+                    (sr.hi >> kCntShift) == 1024ull;
+    long long x = (long long)(((unsigned long long)tr.y << 32) | tr.x) +
+                  (long long)((((br.hi & kSumMask) + (sr.hi & kSumMask)) << 31) + (br.lo & kSumMask) + (sr.lo & kSumMask));
+    if (!__all_sync(0xffffffffu, ok)) return false;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    P = x;
+    return true;
+}
+
+#ifndef DME_TILES_CTAS
+#define DME_TILES_CTAS 4
+#endif
+template <int EMIT>
+__global__ void __launch_bounds__(kThreads, DME_TILES_CTAS)
+quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) unsigned char dyn_smem[];      // three tile buffers, TScratch
+    TScratch &sc = *reinterpret_cast<TScratch *>(dyn_smem + (size_t)3 * kTile * sizeof(float));
+    const uint32_t buf0 = smem_u32(dyn_smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t pol = policy_evict_first();
+    const uint32_t boff = blocked_off();
+    const bool window_ok = a.TS <= 32;           // rows beyond 2^27 coordinates resolve their look-back from global memory
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < 3; ++q) mbar_init(&sc.mbar[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tiles_take(a, &tmap, sc, 0, buf0, pol, true);
+        tiles_take(a, &tmap, sc, 1, buf0, pol, true);
+        tiles_take(a, &tmap, sc, 2, buf0, pol, false);
+        sc.rc_row[0] = sc.rc_row[1] = -1;
+        sc.hit[0] = sc.hit[1] = 0;
+    }
+    __syncthreads();
+    // state of the tile whose C-phase is pending (one iteration behind its B-phase)
+    uint32_t sgwP = 0, flmP = 0;
+    float mxfP = 0.0f;
+    double inclP = 0.0;
+    double wbaseP = 0.0, wnextP = 0.0;   // in-tile exclusive prefix of this warp / of the next warp (tile total for the last warp)
+    uint32_t fmP = 0;                    // largest floor of that tile (float bits)
+    long long AqP = 0;                   // its aggregate (fixed point)
+    int sB = 0, sC = 2, useB = 0;        // ring positions of the B tile / the C tile, how often buffer sB has been filled before
+    for (int it = 0;; ++it) {
+        const TItem iB = sc.item[sB];
+        TItem iC = sc.item[sC];
+        if (it == 0) iC.flags = 0;
+        const bool validB = iB.flags & kItValid, validC = iC.flags & kItValid;
+        if (!validB && !validC) break;
+        const int e = it & 1;
+        // ---------------------------------------------------------------- B-phase of tile iB
+        uint32_t sgw = 0, flm = 0;
+        float mxf = 0.0f;
+        double incl = 0.0;
+        if (validB) {
+            if (sc.rc_row[e] != iB.c) {          // CTA-uniform: the row's constants and binade table into shared memory
+                __syncthreads();                // (everybody has read rc_row)
+                if (threadIdx.x < (int)(sizeof(RowConst) / 16))
+                    reinterpret_cast<uint4 *>(&sc.rc[e])[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(&a.consts[iB.c]) + threadIdx.x);
+                else if (threadIdx.x >= 32 && threadIdx.x < 32 + kBinades)
+                    reinterpret_cast<uint4 *>(sc.tab[e])[threadIdx.x - 32] =
+                        __ldg(reinterpret_cast<const uint4 *>(a.tabs + (int64_t)iB.c * kBinades) + (threadIdx.x - 32));
+                if (threadIdx.x == 64) sc.rc_row[e] = iB.c;
+                __syncthreads();
+            }
+            const RowConst &rc = sc.rc[e];
+            const uint32_t buf = buf0 + (uint32_t)sB * kTile * 4u;
+            mbar_wait(smem_u32(&sc.mbar[sB]), (uint32_t)(useB & 1));
+            // the look-back window of tile C as late as its latency allows (the records are fresher), behind the B-phase math
+            if (warp == 0 && validC && window_ok) window_prefetch(a, sc.win[e], iC.c, iC.t, lane);
+            float x[kEpt], flf[kEpt], fr[kEpt];
+            load_x(a, iB.flags, iB.c, iB.t, buf, x);
+#pragma unroll
+            for (int j = kEpt - 1; j >= 0; --j) sgw = __funnelshift_l(__float_as_uint(x[j]), sgw, 2);     // bit 2j+1 = sign of x[j]
+            floors_and_fracs(x, rc, flf, fr);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)            // park the fractional parts in place of x
+                sts128((buf + boff) ^ (uint32_t)(q << 4), make_float4(fr[4 * q], fr[4 * q + 1], fr[4 * q + 2], fr[4 * q + 3]));
+            mxf = flf[0];
+#pragma unroll
+            for (int j = 1; j < kEpt; ++j) mxf = fmaxf(mxf, flf[j]);
+            if (mxf != 0.0f) {
+#pragma unroll
+                for (int j = 0; j < kEpt; ++j) flm |= ((flf[j] != 0.0f) ? 1u : 0u) << (2 * j);
+            }
+            double run = (double)fr[0];
+#pragma unroll
+            for (int j = 1; j < kEpt; ++j) run += (double)fr[j];
+            incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            if (lane == 31) sc.wtot[e][warp] = incl;
+            const uint32_t wmx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));     // floors are >= 0: bit order = value order
+            if (lane == 0) sc.flmaxw[e][warp] = wmx;
+        }
+        if (warp == 0) {
+            if (!validB && validC && window_ok) window_prefetch(a, sc.win[e], iC.c, iC.t, lane);
+            cp_async_wait_all();
+        }
+        __syncthreads();
+        // ---------------------------------------------------------------- every warp: warp bases of tile B (fixed order), its aggregate
+        double wbase = 0.0, wnext = 0.0;
+        uint32_t fm = 0;
+        long long Aq = 0;
+        if (validB) {
+            double wi = lane < kWarps ? sc.wtot[e][lane] : 0.0;
+#pragma unroll
+            for (int o = 1; o < kWarps; o <<= 1) {
+                const double up = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += up;
+            }
+            wnext = __shfl_sync(0xffffffffu, wi, warp);
+            wbase = __shfl_sync(0xffffffffu, wi, warp > 0 ? warp - 1 : 0);
+            if (warp == 0) wbase = 0.0;
+            const double A = __shfl_sync(0xffffffffu, wi, kWarps - 1);
+            fm = __reduce_max_sync(0xffffffffu, lane < kWarps ? sc.flmaxw[e][lane] : 0u);
+            Aq = __double2ll_rn(A * sc.rc[e].q_up);          // fixed point, 2^-qshift resolution
+            if (threadIdx.x == 0) {
+                rec_store(a.desc + (int64_t)iB.c * a.T + iB.t, (unsigned long long)Aq, 1u);
+                const unsigned long long lo = ((unsigned long long)Aq & 0x7fffffffull) + (1ull << kCntShift);
+                const unsigned long long hi = ((unsigned long long)Aq >> 31) + (1ull << kCntShift);
+                Rec2 *br = a.blocks + (int64_t)iB.c * a.TB + (iB.t >> 5), *sr = a.supers + (int64_t)iB.c * a.TS + (iB.t >> 10);
+                red_add_u64(&br->lo, lo); red_add_u64(&br->hi, hi);
+                red_add_u64(&sr->lo, lo); red_add_u64(&sr->hi, hi);
+            }
+        }
+        if (threadIdx.x == 0) sc.hit[e ^ 1] = 0;
+        // ---------------------------------------------------------------- C-phase of tile iC: AS:635-637
+        uint32_t kw = 0;
+        if (validC) {
+            const RowConst &rc = sc.rc[e ^ 1];
+            const uint32_t buf = buf0 + (uint32_t)sC * kTile * 4u;
+            long long P = 0;
+            if (iC.t > 0 && !(window_ok && window_eval(sc.win[e], lane, P))) {
+                // a record of the window was not complete when it was copied (every warp sees the same window, so the
+                // whole CTA is here): warp 0 polls global memory, the others wait
+                if (warp == 0) {
+                    const TileRec *tiles = a.desc + (int64_t)iC.c * a.T;
+                    const Rec2 *blocks = a.blocks + (int64_t)iC.c * a.TB, *supers = a.supers + (int64_t)iC.c * a.TS;
+                    LookRegs r;
+                    for (;;) {
+                        lookback_load(tiles, blocks, supers, iC.t, lane, r);
+                        if (lookback_eval(supers, iC.t, lane, r, P)) break;
+                        __nanosleep(200);
+                    }
+                    if (lane == 0) sc.pfb = P;
+                }
+                __syncthreads();
+                P = sc.pfb;
+            }
+            const double Pd = __ll2double_rn(P) * rc.q_dn;
+            float fr[kEpt];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 v = lds128((buf + boff) ^ (uint32_t)(q << 4));
+                fr[4 * q] = v.x; fr[4 * q + 1] = v.y; fr[4 * q + 2] = v.z; fr[4 * q + 3] = v.w;
+            }
+            double excl = __shfl_up_sync(0xffffffffu, inclP, 1);
+            if (lane == 0) excl = 0.0;
+            const double Pw = Pd + wbaseP;
+            const double E = Pw + excl;
+            double En = Pw + inclP;
+            if (lane == 31) En = Pd + wnextP;                    // = the next warp's first prefix, bit for bit
+            if (threadIdx.x == kThreads - 1) En = __ll2double_rn(P + AqP) * rc.q_dn;      // = the next tile's first prefix
+            const Geo g = make_geo(sc.tab[e ^ 1], E, En);
+            kw = rbits_interleaved(g, fr, rc.X);
+            const float fmf = __uint_as_float(fmP);
+            if (EMIT == 1 && width_of(fmf) != width_of(__fadd_rn(fmf, 1.0f)) && mxfP == fmf) {
+                // the largest floor sits right below a width boundary: did one of those coordinates also receive a unit?
+                bool hit;
+                if (fmf == 1.0f) hit = (flmP & kw) != 0u;
+                else {
+                    float x[kEpt], fl[kEpt], fr2[kEpt];
+                    load_x_global(a, iC.c, iC.t, x, (int)threadIdx.x);
+                    floors_and_fracs(x, rc, fl, fr2);
+                    hit = false;
+#pragma unroll
+                    for (int j = 0; j < kEpt; ++j) hit |= (fl[j] == fmf) && ((kw >> (2 * j)) & 1u);
+                }
+                if (hit) atomicOr(&sc.hit[e], 1u);
+            }
+        }
+        __syncthreads();                         // buffer sC is free, sc.hit is complete, the scratch of this iteration is consumed
+        if (threadIdx.x == 0) tiles_take(a, &tmap, sc, sC, buf0, pol, validB);       // next ticket; its tile goes where tile C was
+        // ---------------------------------------------------------------- emit tile iC
+        if (validC) {
+            const RowConst &rc = sc.rc[e ^ 1];
+            const float fm_c = __uint_as_float(fmP);
+            if (EMIT == 0) {
+                float x[kEpt], fl[kEpt], fr2[kEpt];
+                load_x_global(a, iC.c, iC.t, x, (int)threadIdx.x);
+                floors_and_fracs(x, rc, fl, fr2);
+                const int64_t i0 = (int64_t)iC.t * kTile + (int64_t)threadIdx.x * kEpt;
+                bool ovf = false;
+#pragma unroll
+                for (int j = 0; j < kEpt; ++j) {
+                    const float kf = __fadd_rn(fl[j], (float)((kw >> (2 * j)) & 1u));
+                    const int64_t i = i0 + j;
+                    if (i >= a.d) continue;
+                    const uint32_t sbit = (sgwP >> (2 * j + 1)) & 1u;
+                    if (a.deq_out) {
+                        // sign(v) of AS:640: v = x / D is zero exactly when m * |v| is (floor and fraction both zero, m > 0)
+                        const float sgf = (fl[j] == 0.0f && fr2[j] == 0.0f) ? 0.0f : (sbit ? -1.0f : 1.0f);
+                        a.deq_out[(int64_t)iC.c * a.ld_out + i] = __fdiv_rn(__fmul_rn(__fmul_rn(rc.L1f, sgf), kf), rc.mf);
+                    }
+                    if (a.k_out) {
+                        if (kf >= 2147483648.0f) { ovf = true; a.k_out[(int64_t)iC.c * a.ld_out + i] = 0x7fffffff; }
+                        else a.k_out[(int64_t)iC.c * a.ld_out + i] = (int32_t)kf;
+                    }
+                    if (a.sgn_out) a.sgn_out[(int64_t)iC.c * a.ld_out + i] = (uint8_t)sbit;
+                }
+                if (ovf) atomicOr(&a.hdr->status, 1u);
+            } else {
+                // tile-wide minimal field width: from the largest floor, one step wider when such a coordinate received a unit
+                const int W = sc.hit[e] ? width_of(__fadd_rn(fm_c, 1.0f)) : width_of(fm_c);
+                if (fm_c >= 2147483520.0f && threadIdx.x == 0) atomicOr(&a.hdr->status, 1u);
+                const int64_t slot_id = (int64_t)iC.c * a.T + iC.t;
+                unsigned long long off16;
+                if (W <= a.pack.W0) {
+                    off16 = (unsigned long long)slot_id * (32ull * a.pack.W0);
+                    if (threadIdx.x == 0) a.pack.dir[slot_id] = (off16 << 8) | (unsigned long long)W;
+                } else {
+                    if (threadIdx.x == 0) {
+                        const unsigned long long units = 32ull * W;
+                        unsigned long long o = a.pack.arena_base16 + atomicAdd(&a.hdr->arena_top, units);
+                        if ((long long)((o + units) * 16ull) > a.pack.codes_bytes) { atomicOr(&a.hdr->status, 2u); o = ~0ull; }
+                        sc.off16 = o;
+                        a.pack.dir[slot_id] = (o == ~0ull) ? 0ull : ((o << 8) | (unsigned long long)W);
+                    }
+                    __syncthreads();
+                    off16 = sc.off16;
+                }
+                if (off16 != ~0ull) {
+                    uint32_t *tw = a.pack.codes + off16 * 4ull;
+                    if (W == 2) tw[threadIdx.x] = kw | flmP | (sgwP & 0xaaaaaaaau);     // fields [sign | magnitude bit]: k = floor + r <= 1
+                    else {
+                        float x[kEpt];
+                        load_x_global(a, iC.c, iC.t, x, (int)threadIdx.x);
+                        emit_wide_x(x, rc, kw, sgwP, W, tw, (int)threadIdx.x);
+                    }
+                }
+            }
+        }
+        sgwP = sgw; flmP = flm; mxfP = mxf; inclP = incl; wbaseP = wbase; wnextP = wnext; fmP = fm; AqP = Aq;
+        // rotate the ring: the B tile becomes the C tile, the buffer after it holds the next B tile, the freed buffer
+        // receives the prefetch
+        const int nB = sB == 2 ? 0 : sB + 1;
+        sC = sB; sB = nB;
+        if (sB == 0) ++useB;
+    }
+}
+
+static int g_sms = 0, g_occ[2] = {0, 0}, g_occ_tiles[2] = {0, 0};
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
+
+// Which path quantises: 1 = l1_kernel + quantize_tiles_kernel (default), 0 = the fused persistent kernel.
+bool use_tiles_path() {
+    if (const char *e = getenv("DME_PATH")) return !(e[0] == 's');
+    return true;
+}
 
 int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
                   const float *x_inject, const float *l1_inject, uint64_t seed, uint64_t client0,
@@ -1089,6 +1417,7 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
         return DME_EWORKSPACE;
     }
     const size_t dyn = (size_t)(kSlotsA + kSlotsB) * kTile * sizeof(float) + sizeof(Scratch);
+    const size_t dyn_tiles = (size_t)3 * kTile * sizeof(float) + sizeof(TScratch);
     if (g_sms == 0) {
         int dev = 0;
         DME_CUDA(cudaGetDevice(&dev));
@@ -1096,6 +1425,10 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
         DME_CUDA(cudaFuncSetAttribute(quantize_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_occ[0], quantize_stream_kernel<0>, kBlock, dyn));
         DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_occ[1], quantize_stream_kernel<1>, kBlock, dyn));
+        DME_CUDA(cudaFuncSetAttribute(quantize_tiles_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_tiles));
+        DME_CUDA(cudaFuncSetAttribute(quantize_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_tiles));
+        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_occ_tiles[0], quantize_tiles_kernel<0>, kThreads, dyn_tiles));
+        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_occ_tiles[1], quantize_tiles_kernel<1>, kThreads, dyn_tiles));
         cudaDriverEntryPointQueryResult qres;
         void *fn = nullptr;
         DME_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -1114,6 +1447,22 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
         const CUresult r = g_encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)X, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for n=%lld d=%lld ld=%lld", (int)r, (long long)n, (long long)d, (long long)ld); return DME_ECUDA; }
+    }
+    a.tiles_tma = (int)((a.rows32 + kTile / 32 - 1) / (kTile / 32));
+    a.has_tail = (d & 31) ? 1 : 0;
+    a.dbg = 0;
+    if (use_tiles_path()) {
+        // the row constants are there already (l1_kernel, launched by the caller on the same stream)
+        const int occ_t = g_occ_tiles[packed ? 1 : 0];
+        if (occ_t < 1) { set_error("quantize_tiles_kernel does not fit on an SM"); return DME_ECUDA; }
+        int64_t Gt = (int64_t)g_sms * occ_t;
+        if (const char *e = getenv("DME_DBG_G")) Gt = atoll(e);
+        if (Gt > nT) Gt = nT;
+        a.lag = a.goff = a.total_items = 0; a.G = Gt; a.step_c = a.step_t = a.total_items32 = a.ahead = 0;
+        if (packed) quantize_tiles_kernel<1><<<(unsigned)Gt, kThreads, dyn_tiles, st>>>(a, tmap);
+        else quantize_tiles_kernel<0><<<(unsigned)Gt, kThreads, dyn_tiles, st>>>(a, tmap);
+        DME_LAUNCH_CHECK("quantize_tiles_kernel");
+        return DME_OK;
     }
     const int occ = g_occ[packed ? 1 : 0];
     if (occ < 1) { set_error("quantize_stream_kernel does not fit on an SM"); return DME_ECUDA; }

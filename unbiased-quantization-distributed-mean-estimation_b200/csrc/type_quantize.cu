@@ -59,7 +59,7 @@ __device__ __forceinline__ void load_tile_striped(const float *__restrict__ row,
 // grid (T, n).  partial[c*T + t] = sum over the tile of |x| in fp64 (fixed association).
 __global__ void __launch_bounds__(kThreads)
 l1_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t m, int64_t T,
-          double *__restrict__ partial, uint32_t *__restrict__ a_done, RowConst *__restrict__ consts,
+          double *__restrict__ partial, uint32_t *__restrict__ a_done, RowConst *__restrict__ consts, BinadeEntry *__restrict__ tabs,
           const float *__restrict__ x_inject, const float *__restrict__ l1_inject, uint64_t seed,
           uint64_t client0, float *__restrict__ l1_out) {
     __shared__ double s_red[kWarps];
@@ -86,29 +86,10 @@ l1_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t m, int64_t
     for (int64_t i = threadIdx.x; i < T; i += kThreads) acc += pp[i];
     acc = block_sum_f64(acc, s_red);
     if (threadIdx.x == 0) {
-        RowConst rc;
-        rc.L1f = l1_inject ? l1_inject[c] : (float)acc;               // AS:624
-        rc.D = __fadd_rn(rc.L1f, 1e-12f);                             // AS:625
-        rc.mf = (float)m;
-        rc.X = x_inject ? x_inject[c] : philox_client_uniform(seed, client0 + (uint64_t)c);   // AS:634
-        rc.rcpD = __frcp_rn(rc.D);
-        uint32_t fl = 0;
-        // The fast chain (Markstein division, magic-number floor) is proven for these operand ranges only;
-        // anything else takes the IEEE-div / floorf instantiation.  See DESIGN.md "Exactness of the fast chain".
-        if (!(rc.D >= 9.5367431640625e-07f && rc.D <= 1.2676506e30f)) fl |= kRowExact;            // 2^-20 .. 2^100
-        if ((__float_as_uint(rc.D) & 0x7fffffu) == 0x7fffffu) fl |= kRowExact;                      // 1/D rounding exception
-        if (!(rc.X == 0.0f || (rc.X >= 5.9604644775390625e-08f && rc.X < 1.0f))) fl |= kRowExact;  // X on torch.rand's grid
-        if (!(rc.mf <= 4194304.0f) || l1_inject) fl |= kRowGuardFloor;                              // m*p may reach 2^23
-        rc.flags = fl;
-        int lg = 0;
-        while (((int64_t)1 << lg) < d) ++lg;
-        rc.qshift = min(50, 62 - lg);
-        rc.pad0 = 0;
-        rc.q_up = scalbn(1.0, rc.qshift);
-        rc.q_dn = scalbn(1.0, -rc.qshift);
-        rc.pad1[0] = rc.pad1[1] = 0.0;
-        consts[c] = rc;
-        if (l1_out) l1_out[c] = rc.L1f;
+        RowConstIn in;
+        in.m = m; in.d = d; in.x_inject = x_inject; in.l1_inject = l1_inject; in.seed = seed; in.client0 = client0;
+        in.consts = consts; in.tabs = tabs; in.l1_out = l1_out;
+        make_row_const(in, c, acc);
     }
 }
 
@@ -200,11 +181,13 @@ decode_mean_kernel(const uint32_t *__restrict__ codes, const uint64_t *__restric
             // common case at low rates: sign/magnitude pairs of 2 bits, value +-lut[1]
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
+                // per coordinate: sign bit of the field onto +-lut[1] (shift + one 3-input logic op), then an add
+                // predicated on the magnitude bit.  Skipping the add of a zero is exact: acc is never -0.
+                const uint32_t w = w0[u], pv = __float_as_uint(v1[u]);
 #pragma unroll
                 for (int j = 0; j < kEpt; ++j) {
-                    const uint32_t f = (w0[u] >> (2 * j)) & 3u;
-                    const float v = (f & 1u) ? __uint_as_float(__float_as_uint(v1[u]) ^ ((f >> 1) << 31)) : 0.0f;
-                    acc[j] = __fadd_rn(acc[j], v);
+                    const uint32_t val = ((w << (30 - 2 * j)) & 0x80000000u) ^ pv;
+                    if (w & (1u << (2 * j))) acc[j] = __fadd_rn(acc[j], __uint_as_float(val));
                 }
             }
         } else {
@@ -289,7 +272,7 @@ int launch_l1(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const
     char *base = (char *)ws;
     dim3 grid((unsigned)L.T, (unsigned)n);
     l1_kernel<<<grid, kThreads, 0, st>>>(X, d, ld, m, L.T, (double *)(base + L.off_partial), (uint32_t *)(base + L.off_done),
-                                         (RowConst *)(base + L.off_consts), x_inject, l1_inject, seed, client0, l1_out);
+                                         (RowConst *)(base + L.off_consts), (BinadeEntry *)(base + L.off_tab), x_inject, l1_inject, seed, client0, l1_out);
     DME_LAUNCH_CHECK("l1_kernel");
     return DME_OK;
 }
@@ -301,6 +284,7 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
                   const float *x_inject, const float *l1_inject, uint64_t seed, uint64_t client0,
                   int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
                   uint32_t *codes, int64_t codes_bytes, uint64_t *dir, float *l1_out, cudaStream_t st, bool packed);   // stream.cu
+bool use_tiles_path();   // stream.cu
 
 }  // namespace dme
 
@@ -339,10 +323,10 @@ static int quantize_common(const float *X, int64_t n, int64_t d, int64_t ld, int
     if (rc) return rc;
     prof_reset();
     prof_mark(st);
-    char *base = (char *)ws;
-    if (mode == DME_MODE_BIASED) {
+    if (mode == DME_MODE_BIASED || use_tiles_path()) {
         rc = launch_l1(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, l1_out, st);
         if (rc) return rc;
+        if (mode != DME_MODE_BIASED) prof_mark(st);
     }
     if (mode == DME_MODE_BIASED)
         return biased_quantize(X, n, d, ld, m, L, ws, k_out, sgn_out, deq_out, ld_out, codes, codes_bytes, dir, st);

@@ -104,13 +104,54 @@ inline WsLayout ws_layout(int64_t n, int64_t d) {
 }
 
 #ifdef __CUDACC__
+// Row constants + the binade table of AS:636's closed form (cold: once per client row).
+struct RowConstIn { int64_t m, d; const float *x_inject, *l1_inject; uint64_t seed, client0; RowConst *consts; BinadeEntry *tabs; float *l1_out; };
+__device__ inline void make_row_const(const RowConstIn &a, int64_t c, double l1sum) {
+    RowConst rc;
+    rc.L1f = a.l1_inject ? a.l1_inject[c] : (float)l1sum;           // AS:624
+    rc.D = __fadd_rn(rc.L1f, 1e-12f);                               // AS:625
+    rc.mf = (float)a.m;
+    rc.X = a.x_inject ? a.x_inject[c] : philox_client_uniform(a.seed, a.client0 + (uint64_t)c);   // AS:634
+    rc.rcpD = __frcp_rn(rc.D);
+    uint32_t fl = 0;
+    // The fast chain (Markstein division, magic-number floor) is proven for these operand ranges only;
+    // anything else takes the IEEE-div / floorf instantiation.  See DESIGN.md "Exactness of the fast chain".
+    if (!(rc.D >= 9.5367431640625e-07f && rc.D <= 1.2676506e30f)) fl |= kRowExact;            // 2^-20 .. 2^100
+    if ((__float_as_uint(rc.D) & 0x7fffffu) == 0x7fffffu) fl |= kRowExact;                      // 1/D rounding exception
+    if (!(rc.X == 0.0f || (rc.X >= 5.9604644775390625e-08f && rc.X < 1.0f))) fl |= kRowExact;  // X on torch.rand's range
+    if (!(rc.mf <= 4194304.0f) || a.l1_inject) fl |= kRowGuardFloor;                            // m*p may reach 2^23
+    rc.flags = fl;
+    int lg = 0;
+    while (((int64_t)1 << lg) < a.d) ++lg;
+    rc.qshift = min(50, 62 - lg);
+    rc.pad0 = 0;
+    rc.q_up = __longlong_as_double((long long)(1023 + rc.qshift) << 52);
+    rc.q_dn = __longlong_as_double((long long)(1023 - rc.qshift) << 52);
+    rc.pad1[0] = rc.pad1[1] = 0.0;
+    a.consts[c] = rc;
+    BinadeEntry *tab = a.tabs + c * kBinades;
+    const double Xd = (double)rc.X;
+#pragma unroll 1
+    for (int e = 0; e < kBinades; ++e) {
+        BinadeEntry b; b.Xp = 0.0; b.sigma = 0.0;
+        if (!(fl & kRowExact) && e >= 2 && e <= 22) {
+            const double g = __longlong_as_double((long long)(1023 + e - 23) << 52), ginv = __longlong_as_double((long long)(1023 + 23 - e) << 52);
+            const double av = ceil(Xd * ginv - 0.5);                 // exact: X has 24 bits, X >= 2^-24 or X == 0
+            b.sigma = (((long long)av) & 1) ? -1.0 : 1.0;
+            b.Xp = -b.sigma * (g * (av - 0.5));                      // stored as -sigma * Xp: sigma (c - Xp) = fma(c, sigma, b.Xp)
+        }
+        tab[e] = b;
+    }
+    if (a.l1_out) a.l1_out[c] = rc.L1f;
+}
+
 // ------------------------------------------------------------------ packed-code emit shared by both quantizer modes
 struct PackTarget { uint32_t *codes; int64_t codes_bytes; uint64_t *dir; WsHeader *hdr; int W0; unsigned long long arena_base16; };
 struct PackScratch { uint32_t u32[kWarps]; unsigned long long off16; };
 
 // Pack 16 (magnitude, sign) pairs of one thread with field width W into W/2 words.
 template <int W>
-__device__ __forceinline__ void pack_store(const uint32_t (&k)[kEpt], const uint32_t (&sg)[kEpt], uint32_t *tile_words) {
+__device__ __forceinline__ void pack_store(const uint32_t (&k)[kEpt], const uint32_t (&sg)[kEpt], uint32_t *tile_words, int chunk) {
     constexpr int kPerWord = 32 / W;
 #pragma unroll
     for (int q = 0; q < W / 2; ++q) {
@@ -121,8 +162,12 @@ __device__ __forceinline__ void pack_store(const uint32_t (&k)[kEpt], const uint
             const uint32_t field = (W == 32) ? ((sg[j] << 31) | k[j]) : ((sg[j] << (W - 1)) | k[j]);
             word |= field << ((W * e) & 31);
         }
-        tile_words[q * kThreads + threadIdx.x] = word;
+        tile_words[q * kThreads + chunk] = word;
     }
+}
+template <int W>
+__device__ __forceinline__ void pack_store(const uint32_t (&k)[kEpt], const uint32_t (&sg)[kEpt], uint32_t *tile_words) {
+    pack_store<W>(k, sg, tile_words, (int)threadIdx.x);       // one chunk per thread
 }
 
 // Whole CTA: choose the tile's minimal field width, place it (fixed primary slot when W <= W0, bump-allocated

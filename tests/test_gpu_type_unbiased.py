@@ -19,6 +19,14 @@ def dme():
     return dme_b200
 
 
+@pytest.fixture(autouse=True, params=["tiles", "stream"])
+def quantize_path(request, monkeypatch):
+    """Every test of this file runs on both quantize paths (the library picks by row length otherwise):
+    l1_kernel + quantize_tiles_kernel, and the fused persistent quantize_stream_kernel."""
+    monkeypatch.setenv("DME_PATH", request.param)
+    yield request.param
+
+
 def _R(v):
     v = float(v)
     return int(v) if v == int(v) else v

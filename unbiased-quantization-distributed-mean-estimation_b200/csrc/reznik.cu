@@ -286,7 +286,7 @@ int biased_quantize(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m,
     RzEmit e;
     e.k_out = k_out; e.sgn_out = sgn_out; e.deq_out = deq_out; e.ld_out = ld_out;
     e.packed = codes != nullptr;
-    e.pack.codes = codes; e.pack.codes_bytes = codes_bytes; e.pack.dir = dir; e.pack.hdr = (WsHeader *)base;
+    e.pack.codes = codes; e.pack.codes_bytes = codes_bytes; e.pack.dir = dir; e.pack.hdr = (WsHeader *)base; e.pack.n = n; e.pack.T = L.T;
     e.pack.W0 = expected_width(m, d);
     e.pack.arena_base16 = (unsigned long long)(n * L.T) * 32ull * (unsigned long long)e.pack.W0;
     if (e.packed && (long long)(e.pack.arena_base16 * 16ull) > codes_bytes) {

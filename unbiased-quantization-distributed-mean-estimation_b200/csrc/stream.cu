@@ -122,7 +122,7 @@ __device__ __forceinline__ bool bar_or(int id, int n, bool pred) {
     return r != 0;
 }
 // named barriers: 6 = pass-A warps, 7 = pass-B warps, 8 = pass-B warps with OR-reduce
-constexpr int kBarA = 6, kBarCompute = 7, kBarOr = 8;
+constexpr int kBarA = 6, kBarCompute = 7, kBarOr = 8, kBarFree = 1;
 
 // one 16 KB box {32 floats, 128 rows, 1 client} at (0, row0, client) of the 3-D tensor map
 __device__ __forceinline__ void tma_tile_g2s(uint32_t dst, const CUtensorMap *map, int row0, int client, uint64_t *bar, uint64_t policy) {
@@ -708,7 +708,7 @@ __device__ __forceinline__ void phase_c(const StreamArgs &a, Scratch &sc, const 
             const int64_t slot_id = (int64_t)it.c * a.T + it.t;
             unsigned long long off16;
             if (W <= a.pack.W0) {
-                off16 = (unsigned long long)slot_id * (32ull * a.pack.W0);
+                off16 = primary_off16(a.pack, it.c, it.t);
                 if (threadIdx.x == 0) a.pack.dir[slot_id] = (off16 << 8) | (unsigned long long)W;
             } else {
                 if (threadIdx.x == 0) {
@@ -1079,24 +1079,23 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// thread 0: take the next ticket, decode it into item slot `slot` and start the tile's copy into buffer `slot`
-__device__ __forceinline__ void tiles_take(const StreamArgs &a, const CUtensorMap *tmap, TScratch &sc, int slot, uint32_t buf0, uint64_t pol, bool take) {
+// thread 0: decode ticket tk (0xffffffff: none) into item slot `slot` and start the tile's copy into buffer `slot`.
+// (Drawing the ticket one iteration early to hide the atomic's round trip was measured: no gain, slightly slower.)
+__device__ __forceinline__ unsigned int tiles_ticket(const StreamArgs &a) { return atomicAdd(&a.hdr->ticket, 1u); }
+__device__ __forceinline__ void tiles_take(const StreamArgs &a, const CUtensorMap *tmap, TScratch &sc, int slot, uint32_t buf0, uint64_t pol, unsigned int tk) {
     TItem it; it.c = 0; it.t = 0; it.flags = 0; it.ticket = 0xffffffffu;
-    if (take) {
-        const unsigned int tk = atomicAdd(&a.hdr->ticket, 1u);
-        if ((long long)tk < a.n * a.T) {
-            it.ticket = tk;
-            it.c = (int)(tk / (unsigned int)a.T); it.t = (int)(tk - (unsigned int)it.c * (unsigned int)a.T);
-            it.flags = kItValid;
-            if (it.t < a.tiles_tma) it.flags |= kItTma;
-            if (it.t == (int)a.T - 1 && a.has_tail) it.flags |= kItTail;
-            if (it.flags & kItTma) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(&sc.mbar[slot], (uint32_t)kTile * 4u);
-                tma_tile_g2s(buf0 + (uint32_t)slot * kTile * 4u, tmap, it.t * (kTile / 32), it.c, &sc.mbar[slot], pol);
-            } else {
-                mbar_arrive(&sc.mbar[slot]);
-            }
+    if (tk != 0xffffffffu && (long long)tk < a.n * a.T) {
+        it.ticket = tk;
+        it.c = (int)(tk / (unsigned int)a.T); it.t = (int)(tk - (unsigned int)it.c * (unsigned int)a.T);
+        it.flags = kItValid;
+        if (it.t < a.tiles_tma) it.flags |= kItTma;
+        if (it.t == (int)a.T - 1 && a.has_tail) it.flags |= kItTail;
+        if (it.flags & kItTma) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&sc.mbar[slot], (uint32_t)kTile * 4u);
+            tma_tile_g2s(buf0 + (uint32_t)slot * kTile * 4u, tmap, it.t * (kTile / 32), it.c, &sc.mbar[slot], pol);
+        } else {
+            mbar_arrive(&sc.mbar[slot]);
         }
     }
     sc.item[slot] = it;
@@ -1132,11 +1131,8 @@ __device__ __forceinline__ bool window_eval(const Rec *win, int lane, long long 
     return true;
 }
 
-#ifndef DME_TILES_CTAS
-#define DME_TILES_CTAS 4
-#endif
-template <int EMIT>
-__global__ void __launch_bounds__(kThreads, DME_TILES_CTAS)
+template <int EMIT, int CTAS>
+__global__ void __launch_bounds__(kThreads, CTAS)
 quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char dyn_smem[];      // three tile buffers, TScratch
     TScratch &sc = *reinterpret_cast<TScratch *>(dyn_smem + (size_t)3 * kTile * sizeof(float));
@@ -1148,9 +1144,10 @@ quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constan
     if (threadIdx.x == 0) {
         for (int q = 0; q < 3; ++q) mbar_init(&sc.mbar[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        tiles_take(a, &tmap, sc, 0, buf0, pol, true);
-        tiles_take(a, &tmap, sc, 1, buf0, pol, true);
-        tiles_take(a, &tmap, sc, 2, buf0, pol, false);
+        const unsigned int t0 = tiles_ticket(a), t1 = tiles_ticket(a);
+        tiles_take(a, &tmap, sc, 0, buf0, pol, t0);
+        tiles_take(a, &tmap, sc, 1, buf0, pol, t1);
+        tiles_take(a, &tmap, sc, 2, buf0, pol, 0xffffffffu);
         sc.rc_row[0] = sc.rc_row[1] = -1;
         sc.hit[0] = sc.hit[1] = 0;
     }
@@ -1305,8 +1302,17 @@ quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constan
                 if (hit) atomicOr(&sc.hit[e], 1u);
             }
         }
-        __syncthreads();                         // buffer sC is free, sc.hit is complete, the scratch of this iteration is consumed
-        if (threadIdx.x == 0) tiles_take(a, &tmap, sc, sC, buf0, pol, validB);       // next ticket; its tile goes where tile C was
+        // Buffer sC is free once every warp has read its fractional parts: only warp 0 (which issues the next copy into
+        // it) has to wait for that; the other warps just signal.  When the tile's width depends on sc.hit, everybody waits.
+        {
+            const float fmf = __uint_as_float(fmP);
+            const bool need_hit = validC && EMIT == 1 && width_of(fmf) != width_of(__fadd_rn(fmf, 1.0f));      // CTA-uniform
+            if (warp == 0 || need_hit) bar_sync(kBarFree, kThreads);
+            else bar_arrive(kBarFree, kThreads);
+        }
+        if (threadIdx.x == 0) {                  // next ticket; its tile goes where tile C was
+            tiles_take(a, &tmap, sc, sC, buf0, pol, validB ? tiles_ticket(a) : 0xffffffffu);
+        }
         // ---------------------------------------------------------------- emit tile iC
         if (validC) {
             const RowConst &rc = sc.rc[e ^ 1];
@@ -1342,7 +1348,7 @@ quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constan
                 const int64_t slot_id = (int64_t)iC.c * a.T + iC.t;
                 unsigned long long off16;
                 if (W <= a.pack.W0) {
-                    off16 = (unsigned long long)slot_id * (32ull * a.pack.W0);
+                    off16 = primary_off16(a.pack, iC.c, iC.t);
                     if (threadIdx.x == 0) a.pack.dir[slot_id] = (off16 << 8) | (unsigned long long)W;
                 } else {
                     if (threadIdx.x == 0) {
@@ -1380,11 +1386,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
+static int g_tiles_ctas = 3;
+static const void *g_tiles_fn[2] = {nullptr, nullptr};
 
-// Which path quantises: 1 = l1_kernel + quantize_tiles_kernel (default), 0 = the fused persistent kernel.
-bool use_tiles_path() {
+// Which path quantises a row of d coordinates: the fused persistent kernel for rows of 32 MiB and more (no L2 reuse
+// either way; it overlaps the L1 pass with the quantize pass: 5.5 ms vs 1.3 + 4.6 ms at d = 2^24, n = 128), l1_kernel +
+// quantize_tiles_kernel below that (0.41 ms vs 0.55 ms at d = 2^20, n = 128).  DME_PATH=stream|tiles overrides.
+bool use_tiles_path(int64_t d) {
     if (const char *e = getenv("DME_PATH")) return !(e[0] == 's');
-    return true;
+    return d < ((int64_t)1 << 23);
 }
 
 int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
@@ -1408,7 +1418,7 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
     a.x_inject = x_inject; a.l1_inject = l1_inject; a.seed = seed; a.client0 = client0; a.l1_out = l1_out;
     a.k_out = k_out; a.sgn_out = sgn_out; a.deq_out = deq_out; a.ld_out = ld_out;
     a.packed = packed ? 1 : 0;
-    a.pack.codes = codes; a.pack.codes_bytes = codes_bytes; a.pack.dir = dir; a.pack.hdr = a.hdr;
+    a.pack.codes = codes; a.pack.codes_bytes = codes_bytes; a.pack.dir = dir; a.pack.hdr = a.hdr; a.pack.n = n; a.pack.T = L.T;
     a.pack.W0 = expected_width(m > 0 ? m : 1, d);
     const int64_t nT = n * L.T;
     a.pack.arena_base16 = (unsigned long long)nT * 32ull * (unsigned long long)a.pack.W0;
@@ -1425,10 +1435,15 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
         DME_CUDA(cudaFuncSetAttribute(quantize_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_occ[0], quantize_stream_kernel<0>, kBlock, dyn));
         DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_occ[1], quantize_stream_kernel<1>, kBlock, dyn));
-        DME_CUDA(cudaFuncSetAttribute(quantize_tiles_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_tiles));
-        DME_CUDA(cudaFuncSetAttribute(quantize_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_tiles));
-        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_occ_tiles[0], quantize_tiles_kernel<0>, kThreads, dyn_tiles));
-        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_occ_tiles[1], quantize_tiles_kernel<1>, kThreads, dyn_tiles));
+        g_tiles_ctas = 3;           // 80 registers, no spills: 4.63 ms vs 5.16 ms with 4 CTAs of 64 registers (d = 2^24, n = 128)
+        if (const char *e = getenv("DME_TILES_CTAS")) g_tiles_ctas = atoi(e) == 4 ? 4 : 3;
+        g_tiles_fn[0] = g_tiles_ctas == 3 ? (const void *)quantize_tiles_kernel<0, 3> : (const void *)quantize_tiles_kernel<0, 4>;
+        g_tiles_fn[1] = g_tiles_ctas == 3 ? (const void *)quantize_tiles_kernel<1, 3> : (const void *)quantize_tiles_kernel<1, 4>;
+        for (int q = 0; q < 2; ++q) {
+            DME_CUDA(cudaFuncSetAttribute(g_tiles_fn[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_tiles));
+            DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_occ_tiles[q], g_tiles_fn[q], kThreads, dyn_tiles));
+            if (g_occ_tiles[q] > g_tiles_ctas) g_occ_tiles[q] = g_tiles_ctas;
+        }
         cudaDriverEntryPointQueryResult qres;
         void *fn = nullptr;
         DME_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -1451,7 +1466,8 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
     a.tiles_tma = (int)((a.rows32 + kTile / 32 - 1) / (kTile / 32));
     a.has_tail = (d & 31) ? 1 : 0;
     a.dbg = 0;
-    if (use_tiles_path()) {
+    if (const char *e = getenv("DME_DBG")) a.dbg = atoi(e);
+    if (use_tiles_path(d)) {
         // the row constants are there already (l1_kernel, launched by the caller on the same stream)
         const int occ_t = g_occ_tiles[packed ? 1 : 0];
         if (occ_t < 1) { set_error("quantize_tiles_kernel does not fit on an SM"); return DME_ECUDA; }
@@ -1459,8 +1475,8 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
         if (const char *e = getenv("DME_DBG_G")) Gt = atoll(e);
         if (Gt > nT) Gt = nT;
         a.lag = a.goff = a.total_items = 0; a.G = Gt; a.step_c = a.step_t = a.total_items32 = a.ahead = 0;
-        if (packed) quantize_tiles_kernel<1><<<(unsigned)Gt, kThreads, dyn_tiles, st>>>(a, tmap);
-        else quantize_tiles_kernel<0><<<(unsigned)Gt, kThreads, dyn_tiles, st>>>(a, tmap);
+        void *targs[] = {&a, &tmap};
+        DME_CUDA(cudaLaunchKernel(g_tiles_fn[packed ? 1 : 0], dim3((unsigned)Gt), dim3(kThreads), targs, dyn_tiles, st));
         DME_LAUNCH_CHECK("quantize_tiles_kernel");
         return DME_OK;
     }

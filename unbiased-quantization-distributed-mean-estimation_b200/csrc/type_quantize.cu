@@ -136,77 +136,155 @@ __device__ __forceinline__ void decode_generic(const uint32_t *__restrict__ tw, 
 }
 
 // One thread = one 16-coordinate chunk of a tile, all clients in order (est += q / n, ND:133-147), fp32.
-// 64-thread CTAs, 4 per tile, so that short rows still fill the GPU.  Clients are taken in batches of 8 whose
-// directory entries and code words are loaded together (8 independent loads in flight per thread).
+// 64-thread CTAs, 4 per tile, so that short rows still fill the GPU.  Clients are taken in batches of 8 whose code words
+// are loaded together, one batch ahead of the adds.
 constexpr int kBatch = 8;
-constexpr int kLutClients = 256;     // clients whose tables are staged in shared memory at a time (8 KB)
-__global__ void __launch_bounds__(64)
+constexpr int kLutClients = 128;     // clients whose tables are staged in shared memory at a time
+constexpr int kSignLutBytes = 8192;  // dynamic shared memory: a 4 KB table at a 4 KB-aligned address
+
+// packed f32x2 (sm_100: one FFMA2 for two coordinates)
+typedef unsigned long long pf2;
+__device__ __forceinline__ pf2 pf2_pack(float lo, float hi) { pf2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void pf2_unpack(pf2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ pf2 pf2_fma(pf2 a, pf2 b, pf2 c) { pf2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ pf2 pf2_lds(uint32_t addr) { pf2 v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ float f32_lds(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+
+// Fast paths (a tile's field width is the same for the whole CTA, so the choice does not diverge):
+//  * W = 2, fields [sign | magnitude bit]: a coordinate adds 0 or +-v, v = q(1) / n.  Four bits of the code word (two
+//    coordinates) index a table of sign pairs (s0, s1), s in {0, +1, -1}; one FFMA2 does acc += s * v for both -- exact:
+//    s * v is exact and the sum rounds once, like the FADD of ND:137 (0 * v = +0 leaves acc unchanged; acc is never -0).
+//    The table has one copy per lane (entry i of lane l at i * 256 + l * 8 bytes): a warp's 64-bit loads never conflict
+//    whatever the code bits are, and the 4 KB alignment lets one LOP3 form the address.  Needs a finite v.
+//  * W = 4, fields [sign | 3-bit magnitude]: the field indexes the client's 16 signed values q(k) / n directly (64 bytes
+//    per client: 16 entries in 16 banks, equal entries broadcast -- conflict-free), one FADD per coordinate.
+//  * anything else (wide fields of heavy-tailed rows, m = 0): the batch is decoded field by field (decode_generic).
+constexpr uint32_t kWSlow = 255u;     // staged width code of a client whose tile needs decode_generic
+struct DecBatch { uint32_t wa[kBatch], wb[kBatch], wc[kBatch]; };
+// Start the loads of one batch: word 0 of 2- and 4-bit tiles, word 1 of 4-bit tiles (sinfo = {offset / 16, width code}).
+__device__ __forceinline__ void dec_fetch(DecBatch &b, const uint2 *sinfo, const uint32_t *__restrict__ cptr) {
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+        const uint2 inf = sinfo[u];
+        const uint32_t *tw = cptr + (unsigned long long)inf.x * 4ull;
+        b.wc[u] = inf.y;
+        b.wa[u] = (inf.y == 2u || inf.y == 4u) ? __ldg(tw) : 0u;
+        b.wb[u] = (inf.y == 4u) ? __ldg(tw + kThreads) : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(64, 8)
 decode_mean_kernel(const uint32_t *__restrict__ codes, const uint64_t *__restrict__ dir, const float *__restrict__ l1,
                    int64_t n, int64_t d, int64_t T, float mf, float nf, int biased, float *__restrict__ mean, int accumulate) {
-    __shared__ float lut[kLutClients * kLut];
-    __shared__ uint64_t sdir[kLutClients];      // the tile's directory entries of the staged clients
+    __shared__ __align__(64) float lut16[kLutClients * 16];    // [client][sign << 3 | k] = +-q(k) / n for k < 8
+    __shared__ __align__(8) uint2 sinfo[kLutClients + kBatch]; // per staged client: {code offset / 16, width code}
+    __shared__ uint32_t sslow[kLutClients / kBatch];           // per batch: some client needs decode_generic
+    extern __shared__ unsigned char dec_dyn[];
+    const uint32_t slut = ((uint32_t)__cvta_generic_to_shared(dec_dyn) + 4095u) & ~4095u;
+    for (int i = threadIdx.x; i < 512; i += 64) {
+        const int idx = i >> 5, f0 = idx & 3, f1 = idx >> 2;
+        const float s0 = (f0 & 1) ? ((f0 & 2) ? -1.0f : 1.0f) : 0.0f, s1 = (f1 & 1) ? ((f1 & 2) ? -1.0f : 1.0f) : 0.0f;
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(slut + (uint32_t)i * 8u), "f"(s0), "f"(s1) : "memory");
+    }
+    const uint32_t lanebase = slut | ((threadIdx.x & 31u) << 3);
+    const uint32_t lut16_base = (uint32_t)__cvta_generic_to_shared(lut16);
     const int64_t t = blockIdx.x >> 2;
     const int chunk = (int)(blockIdx.x & 3) * 64 + threadIdx.x;
+    const uint32_t *cptr = codes + chunk;
     const int64_t i0 = t * kTile + (int64_t)chunk * kEpt;
     const bool live = i0 < d;
-    float acc[kEpt];
+    pf2 acc2[kEpt / 2];
 #pragma unroll
-    for (int j = 0; j < kEpt; ++j) acc[j] = (accumulate && i0 + j < d) ? mean[i0 + j] : 0.0f;
+    for (int p = 0; p < kEpt / 2; ++p)
+        acc2[p] = pf2_pack((accumulate && i0 + 2 * p < d) ? mean[i0 + 2 * p] : 0.0f, (accumulate && i0 + 2 * p + 1 < d) ? mean[i0 + 2 * p + 1] : 0.0f);
     for (int64_t cb = 0; cb < n; cb += kLutClients) {
-    const int64_t ce = (cb + kLutClients < n) ? cb + kLutClients : n;
-    __syncthreads();
-    for (int i = threadIdx.x; i < (int)(ce - cb) * kLut; i += 64) {
-        const int k = i & (kLut - 1);
-        lut[i] = k == 0 ? 0.0f : deq_over_n(__ldg(l1 + cb + (i >> 3)), (float)k, mf, nf, biased);
-    }
-    for (int i = threadIdx.x; i < (int)(ce - cb); i += 64) sdir[i] = __ldg(dir + (cb + i) * T + t);
-    __syncthreads();
-    if (live)
-    for (int64_t c0 = cb; c0 < ce; c0 += kBatch) {
-        const int64_t n = ce;                      // batch bound inside this block of clients
-        uint64_t e[kBatch];
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) e[u] = (c0 + u < n) ? sdir[c0 + u - cb] : 0ull;
-        uint32_t w0[kBatch];
-        float v1[kBatch];
-        bool all2 = true;
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-            const int W = (int)(e[u] & 0xffu);
-            all2 = all2 && (W == 2 || W == 0);
-            w0[u] = (W == 2) ? __ldg(codes + (e[u] >> 8) * 4ull + chunk) : 0u;
-            v1[u] = (c0 + u < n) ? lut[(c0 + u - cb) * kLut + 1] : 0.0f;
+        const int nc = (int)((cb + kLutClients < n) ? kLutClients : n - cb);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nc * kLut; i += 64) {
+            const int k = i & (kLut - 1), c = i >> 3;
+            const float v = k == 0 ? 0.0f : deq_over_n(__ldg(l1 + cb + c), (float)k, mf, nf, biased);
+            lut16[c * 16 + k] = v;
+            lut16[c * 16 + 8 + k] = k == 0 ? 0.0f : __uint_as_float(__float_as_uint(v) ^ 0x80000000u);
         }
-        if (all2) {
-            // common case at low rates: sign/magnitude pairs of 2 bits, value +-lut[1]
+        for (int i = threadIdx.x; i < kLutClients / kBatch; i += 64) sslow[i] = 0u;
+        __syncthreads();
+        for (int i = threadIdx.x; i < kLutClients + kBatch; i += 64) {
+            uint2 inf = make_uint2(0u, 0u);
+            if (i < nc) {
+                const uint64_t e = __ldg(dir + (cb + i) * T + t);
+                uint32_t W = (uint32_t)(e & 0xffu);
+                // the sign-table path multiplies: it needs a finite q(1) / n (m = 0 gives 0/0: decode_generic adds it as is);
+                // offsets that do not fit 32 bits take the generic path too
+                if (W > 4u || (e >> 40) != 0ull || (W == 2u && !(fabsf(lut16[i * 16 + 1]) <= 3.0e38f))) { W = kWSlow; atomicOr(&sslow[i / kBatch], 1u); }
+                inf = make_uint2((uint32_t)(e >> 8), W);
+            }
+            sinfo[i] = inf;
+        }
+        __syncthreads();
+        if (!live) continue;
+        // software pipeline over batches of kBatch clients: the code words of the next batch are in flight while this
+        // batch is added (one round trip to L2 / HBM per batch would otherwise sit on every thread's critical path)
+        DecBatch nx;
+        dec_fetch(nx, sinfo, cptr);
+        for (int c0 = 0; c0 < nc; c0 += kBatch) {
+            const DecBatch cur = nx;
+            dec_fetch(nx, sinfo + c0 + kBatch, cptr);          // past the last client: {0, 0} entries, no loads
+            if (sslow[c0 / kBatch] == 0u) {
 #pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                // per coordinate: sign bit of the field onto +-lut[1] (shift + one 3-input logic op), then an add
-                // predicated on the magnitude bit.  Skipping the add of a zero is exact: acc is never -0.
-                const uint32_t w = w0[u], pv = __float_as_uint(v1[u]);
+                for (int u = 0; u < kBatch; ++u) {
+                    const uint32_t cbase = lut16_base + (uint32_t)(c0 + u) * 64u;
+                    if (cur.wc[u] == 2u) {
+                        const uint32_t w = cur.wa[u];
+                        const float v = f32_lds(cbase + 4u);
+                        const pf2 vv = pf2_pack(v, v);
 #pragma unroll
-                for (int j = 0; j < kEpt; ++j) {
-                    const uint32_t val = ((w << (30 - 2 * j)) & 0x80000000u) ^ pv;
-                    if (w & (1u << (2 * j))) acc[j] = __fadd_rn(acc[j], __uint_as_float(val));
+                        for (int p = 0; p < kEpt / 2; ++p) {
+                            const uint32_t sh = (p < 2) ? (w << (8 - 4 * p)) : (w >> (4 * p - 8));
+                            acc2[p] = pf2_fma(pf2_lds((sh & 0xf00u) | lanebase), vv, acc2[p]);
+                        }
+                    } else if (cur.wc[u] == 4u) {
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const uint32_t w = q ? cur.wb[u] : cur.wa[u];
+#pragma unroll
+                            for (int p = 0; p < 4; ++p) {
+                                float lo, hi;
+                                pf2_unpack(acc2[4 * q + p], lo, hi);
+                                const uint32_t s0 = (p == 0) ? (w << 2) : (w >> (8 * p - 2)), s1 = w >> (8 * p + 2);
+                                lo = __fadd_rn(lo, f32_lds((s0 & 0x3cu) | cbase));
+                                hi = __fadd_rn(hi, f32_lds((s1 & 0x3cu) | cbase));
+                                acc2[4 * q + p] = pf2_pack(lo, hi);
+                            }
+                        }
+                    }
                 }
-            }
-        } else {
-            for (int u = 0; u < kBatch; ++u) {
-                if (c0 + u >= n) break;
-                const int W = (int)(e[u] & 0xffu);
-                const uint32_t *tw = codes + (e[u] >> 8) * 4ull;
-                const float *lutc = lut + (c0 + u - cb) * kLut;
-                if (W == 2) decode_generic<2>(tw, chunk, lutc, 0.0f, mf, nf, biased, acc);
-                else if (W == 4) decode_generic<4>(tw, chunk, lutc, 0.0f, mf, nf, biased, acc);
-                else if (W == 8) decode_generic<8>(tw, chunk, lutc, __ldg(l1 + c0 + u), mf, nf, biased, acc);
-                else if (W == 16) decode_generic<16>(tw, chunk, lutc, __ldg(l1 + c0 + u), mf, nf, biased, acc);
-                else if (W == 32) decode_generic<32>(tw, chunk, lutc, __ldg(l1 + c0 + u), mf, nf, biased, acc);
-                // W == 0: the tile was dropped (arena exhausted; status bit 2 is set)
+            } else {
+                float acc[kEpt];
+#pragma unroll
+                for (int p = 0; p < kEpt / 2; ++p) pf2_unpack(acc2[p], acc[2 * p], acc[2 * p + 1]);
+                for (int u = 0; u < kBatch; ++u) {
+                    if (c0 + u >= nc) break;
+                    const uint64_t e = __ldg(dir + (cb + c0 + u) * T + t);
+                    const int W = (int)(e & 0xffu);
+                    const uint32_t *tw = codes + (e >> 8) * 4ull;
+                    const float *lutc = lut16 + (c0 + u) * 16;
+                    const float L1c = __ldg(l1 + cb + c0 + u);
+                    if (W == 2) decode_generic<2>(tw, chunk, lutc, 0.0f, mf, nf, biased, acc);
+                    else if (W == 4) decode_generic<4>(tw, chunk, lutc, 0.0f, mf, nf, biased, acc);
+                    else if (W == 8) decode_generic<8>(tw, chunk, lutc, L1c, mf, nf, biased, acc);
+                    else if (W == 16) decode_generic<16>(tw, chunk, lutc, L1c, mf, nf, biased, acc);
+                    else if (W == 32) decode_generic<32>(tw, chunk, lutc, L1c, mf, nf, biased, acc);
+                    // W == 0: the tile was dropped (arena exhausted; status bit 2 is set)
+                }
+#pragma unroll
+                for (int p = 0; p < kEpt / 2; ++p) acc2[p] = pf2_pack(acc[2 * p], acc[2 * p + 1]);
             }
         }
-    }
     }
     if (!live) return;
+    float acc[kEpt];
+#pragma unroll
+    for (int p = 0; p < kEpt / 2; ++p) pf2_unpack(acc2[p], acc[2 * p], acc[2 * p + 1]);
     if (i0 + kEpt <= d) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -284,7 +362,7 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
                   const float *x_inject, const float *l1_inject, uint64_t seed, uint64_t client0,
                   int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
                   uint32_t *codes, int64_t codes_bytes, uint64_t *dir, float *l1_out, cudaStream_t st, bool packed);   // stream.cu
-bool use_tiles_path();   // stream.cu
+bool use_tiles_path(int64_t d);   // stream.cu
 
 }  // namespace dme
 
@@ -323,7 +401,7 @@ static int quantize_common(const float *X, int64_t n, int64_t d, int64_t ld, int
     if (rc) return rc;
     prof_reset();
     prof_mark(st);
-    if (mode == DME_MODE_BIASED || use_tiles_path()) {
+    if (mode == DME_MODE_BIASED || use_tiles_path(d)) {
         rc = launch_l1(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, l1_out, st);
         if (rc) return rc;
         if (mode != DME_MODE_BIASED) prof_mark(st);
@@ -359,7 +437,7 @@ extern "C" int dme_decode_mean(const void *codes, const uint64_t *dir, const flo
     DME_REQUIRE(((uintptr_t)mean & 15u) == 0 && ((uintptr_t)codes & 15u) == 0, "mean and codes must be 16-byte aligned");
     const int64_t T = (d + kTile - 1) / kTile;
     cudaStream_t st = (cudaStream_t)stream;
-    decode_mean_kernel<<<(unsigned)(4 * T), 64, 0, st>>>((const uint32_t *)codes, dir, l1, n, d, T, (float)m, (float)n_total,
+    decode_mean_kernel<<<(unsigned)(4 * T), 64, kSignLutBytes, st>>>((const uint32_t *)codes, dir, l1, n, d, T, (float)m, (float)n_total,
                                                          mode == DME_MODE_BIASED, mean, accumulate);
     DME_LAUNCH_CHECK("decode_mean_kernel");
     prof_mark((cudaStream_t)stream);

@@ -146,7 +146,12 @@ __device__ inline void make_row_const(const RowConstIn &a, int64_t c, double l1s
 }
 
 // ------------------------------------------------------------------ packed-code emit shared by both quantizer modes
-struct PackTarget { uint32_t *codes; int64_t codes_bytes; uint64_t *dir; WsHeader *hdr; int W0; unsigned long long arena_base16; };
+struct PackTarget { uint32_t *codes; int64_t codes_bytes; uint64_t *dir; WsHeader *hdr; int W0; unsigned long long arena_base16; int64_t n, T; };
+// Primary slots are laid out TILE-major (tile t of all n clients is one contiguous run of n * 512 * W0 bytes): the
+// decoder walks a tile's clients in order, so its reads are long sequential runs instead of 1 KB pieces 4 MB apart.
+__device__ __forceinline__ unsigned long long primary_off16(const PackTarget &p, int64_t c, int64_t t) {
+    return (unsigned long long)(t * p.n + c) * (32ull * (unsigned long long)p.W0);
+}
 struct PackScratch { uint32_t u32[kWarps]; unsigned long long off16; };
 
 // Pack 16 (magnitude, sign) pairs of one thread with field width W into W/2 words.
@@ -188,7 +193,7 @@ __device__ __forceinline__ void emit_packed_tile(const PackTarget &p, int64_t sl
     while (W < 32 && kmax >= (1u << (W - 1))) W <<= 1;
     unsigned long long off16;
     if (W <= p.W0) {
-        off16 = (unsigned long long)slot * (32ull * p.W0);
+        off16 = primary_off16(p, slot / p.T, slot % p.T);
         if (threadIdx.x == 0) p.dir[slot] = (off16 << 8) | (unsigned long long)W;
     } else {
         if (threadIdx.x == 0) {

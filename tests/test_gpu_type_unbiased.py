@@ -130,6 +130,9 @@ def test_fused_quantize_mean_and_determinism(dme):
     assert np.allclose((h1 + h2).cpu().numpy(), a, rtol=0, atol=4e-7 * np.abs(X).max())
     host = dme.quantize_mean_host(torch.from_numpy(X).pin_memory(), 1, seed=3).numpy()
     assert np.array_equal(_u32(host), _u32(a))
+    # chunked host pipeline (ragged last chunk): clients are still added in order -> the same bits
+    host5 = dme.quantize_mean_host(torch.from_numpy(X).pin_memory(), 1, seed=3, chunk_clients=5).numpy()
+    assert np.array_equal(_u32(host5), _u32(a))
 
 
 def test_arena_growth_on_heavy_tails(dme):

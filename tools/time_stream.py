@@ -14,7 +14,7 @@ shapes = [(16, 1 << 24), (128, 1 << 20), (1000, 1 << 16), (4, 1 << 24)]
 if len(sys.argv) > 1:
     shapes = [tuple(int(v) for v in s.split("x")) for s in sys.argv[1:]]
 for n, d in shapes:
-    X = torch.randn((n, d), device="cuda")
+    X = (torch.rand((n, d), device="cuda") * 2 - 1) if os.environ.get("UNIF") else torch.randn((n, d), device="cuda")
     out = torch.empty(d, device="cuda")
     L.dme_profile_enable(1)
     res = []

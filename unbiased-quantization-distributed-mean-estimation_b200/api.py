@@ -265,7 +265,7 @@ class _MeanPlan:
 
 
 def quantize_mean(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, client0=0, n_total=None, x_inject=None,
-                  out=None, accumulate=False, check=True):
+                  out=None, accumulate=False, check=True, plan_rows=None):
     """The north-star path: quantize all rows, pack, decode and average -> mean[d] (fp32, CUDA).
 
     n_total: divisor of the mean (defaults to the number of rows; pass the global client count when the rows are
@@ -275,7 +275,8 @@ def quantize_mean(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, c
     dev = X.device
     L = _cabi.lib()
     ws, wsb = Workspace.get(dev).ensure(n, d)
-    plan = _MeanPlan.get(n, d, mm, dev)
+    pn = n if plan_rows is None else max(n, int(plan_rows))      # buffers sized for pn rows serve any n <= pn
+    plan = _MeanPlan.get(pn, d, mm, dev)
     if out is None:
         out = torch.empty(d, dtype=torch.float32, device=dev)
         accumulate = False
@@ -290,21 +291,96 @@ def quantize_mean(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, c
                 Workspace.get(dev).status()
             return out
         except MemoryError:
-            if accumulate or plan.cb >= int(L.dme_codes_bytes(n, d, mm, 0)):
+            if accumulate or plan.cb >= int(L.dme_codes_bytes(pn, d, mm, 0)):
                 raise
-            plan.grow_worst_case(n, d, mm, dev)
+            plan.grow_worst_case(pn, d, mm, dev)
 
 
-def quantize_mean_host(x_host, bits_per_dimension=1, *, out_host=None, **kw):
-    """End-to-end call with HOST buffers: H2D copy of the client rows, fused path, D2H copy of the mean."""
+class _HostPipe:
+    """Two device staging buffers + a copy stream for quantize_mean_host (kept per device and row length)."""
+    _cache: dict = {}
+
+    def __init__(self, rows, d, dev):
+        self.bufs = [torch.empty((rows, d), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.freed = [torch.cuda.Event(), torch.cuda.Event()]     # recorded when the compute stream is done with buffer b
+        self.mean = torch.empty(d, dtype=torch.float32, device=dev)
+
+    @classmethod
+    def get(cls, rows, d, dev):
+        key = (dev.index, rows, d)
+        pipe = cls._cache.get(key)
+        if pipe is None:
+            cls._cache.clear()                                    # one plan at a time: the buffers can be GiBs
+            pipe = cls._cache[key] = cls(rows, d, dev)
+        return pipe
+
+
+def quantize_mean_host(x_host, bits_per_dimension=1, *, out_host=None, chunk_clients=16, reduce_fn=None, **kw):
+    """End-to-end call with HOST buffers: H2D copy of the client rows, fused path, D2H copy of the mean.
+
+    The rows go to the GPU in chunks of `chunk_clients` on a copy stream, double-buffered, while the previous chunk is
+    quantized, decoded and ADDED to the running mean on the caller's stream (decode_mean's accumulate mode adds the
+    clients in order, so the result is bit-identical to one call over all rows).  Pin x_host for full PCIe speed.
+    reduce_fn(mean_device), if given, runs before the D2H copy (the all-reduce of a sharded run)."""
     dev = _device()
     xh = x_host if isinstance(x_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x_host, dtype=np.float32))
-    xd = xh.to(dev, non_blocking=True)
-    mean = quantize_mean(xd, bits_per_dimension, **kw)
+    if xh.dim() == 1:
+        xh = xh.reshape(1, -1)
+    if xh.dtype != torch.float32 or not xh.is_contiguous():
+        xh = xh.to(torch.float32).contiguous()
+    n, d = xh.shape
+    g = max(1, min(int(chunk_clients), n))
+    pipe = _HostPipe.get(g, d, dev)
+    main = torch.cuda.current_stream()
+    client0 = int(kw.pop("client0", 0))
+    n_total = kw.pop("n_total", None)
+    n_total = n if n_total is None else int(n_total)
+    x_inject = kw.pop("x_inject", None)
+    kw.pop("out", None); kw.pop("accumulate", None); kw.pop("plan_rows", None)
+    check = kw.pop("check", True)
+    starts = list(range(0, n, g))
+
+    def stage(i):                       # H2D copy of chunk i into staging buffer i & 1, on the copy stream
+        c0 = starts[i]
+        k = min(g, n - c0)
+        with torch.cuda.stream(pipe.copy_stream):
+            if i >= 2:
+                pipe.copy_stream.wait_event(pipe.freed[i & 1])
+            pipe.bufs[i & 1][:k].copy_(xh[c0:c0 + k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(pipe.copy_stream)
+        return ev
+
+    for attempt in range(2):
+        pipe.copy_stream.wait_stream(main)
+        copied = stage(0)
+        try:
+            for i, c0 in enumerate(starts):
+                k = min(g, n - c0)
+                nxt = stage(i + 1) if i + 1 < len(starts) else None      # in flight while chunk i is quantized
+                main.wait_event(copied)
+                xi = None if x_inject is None else x_inject[c0:c0 + k]
+                # a status read is a sync point of the caller's stream only: the copy stream keeps running
+                quantize_mean(pipe.bufs[i & 1][:k], bits_per_dimension, client0=client0 + c0, n_total=n_total, x_inject=xi,
+                              out=pipe.mean, accumulate=(i > 0), check=check, plan_rows=g, **kw)
+                pipe.freed[i & 1].record(main)
+                copied = nxt
+            break
+        except MemoryError:
+            # a later chunk overflowed the code arena after earlier ones were already added: start over with the
+            # worst-case arena (heavy-tailed rows only)
+            main.synchronize(); pipe.copy_stream.synchronize()
+            if attempt == 1:
+                raise
+            mm = _resolve_m(d, bits_per_dimension, kw.get("m"))
+            _MeanPlan.get(g, d, mm, dev).grow_worst_case(g, d, mm, dev)
+    if reduce_fn is not None:
+        reduce_fn(pipe.mean)
     if out_host is None:
-        out_host = torch.empty(mean.shape, dtype=torch.float32, pin_memory=True)
-    out_host.copy_(mean, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
+        out_host = torch.empty(d, dtype=torch.float32, pin_memory=True)
+    out_host.copy_(pipe.mean, non_blocking=True)
+    main.synchronize()
     return out_host
 
 

@@ -1256,6 +1256,9 @@ quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constan
             if (iC.t > 0 && !(window_ok && window_eval(sc.win[e], lane, P))) {
                 // a record of the window was not complete when it was copied (every warp sees the same window, so the
                 // whole CTA is here): warp 0 polls global memory, the others wait
+#ifdef DME_COUNT_FALLBACK
+                if (threadIdx.x == 0) atomicAdd(&a.hdr->pad[0], 1u);      // tools/fallback_count.py
+#endif
                 if (warp == 0) {
                     const TileRec *tiles = a.desc + (int64_t)iC.c * a.T;
                     const Rec2 *blocks = a.blocks + (int64_t)iC.c * a.TB, *supers = a.supers + (int64_t)iC.c * a.TS;

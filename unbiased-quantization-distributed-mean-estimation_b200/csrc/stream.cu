@@ -1131,6 +1131,14 @@ __device__ __forceinline__ bool window_eval(const Rec *win, int lane, long long 
     return true;
 }
 
+// eight 2-bit pairs [s | r] (low 16 bits of v) -> eight nibbles [s 0 0 r]
+__device__ __forceinline__ uint32_t spread_pairs_to_nibbles(uint32_t v) {
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    return (v & 0x11111111u) | ((v & 0x22222222u) << 2);
+}
+
 template <int EMIT, int CTAS>
 __global__ void __launch_bounds__(kThreads, CTAS)
 quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ CUtensorMap tmap) {
@@ -1153,7 +1161,7 @@ quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constan
     }
     __syncthreads();
     // state of the tile whose C-phase is pending (one iteration behind its B-phase)
-    uint32_t sgwP = 0, flmP = 0;
+    uint32_t sgwP = 0, flmP = 0, fl4aP = 0, fl4bP = 0;   // fl4: the thread's floors as nibbles (coordinates 0-7 / 8-15), for 4-bit tiles
     float mxfP = 0.0f;
     double inclP = 0.0;
     double wbaseP = 0.0, wnextP = 0.0;   // in-tile exclusive prefix of this warp / of the next warp (tile total for the last warp)
@@ -1168,7 +1176,7 @@ quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constan
         if (!validB && !validC) break;
         const int e = it & 1;
         // ---------------------------------------------------------------- B-phase of tile iB
-        uint32_t sgw = 0, flm = 0;
+        uint32_t sgw = 0, flm = 0, fl4a = 0, fl4b = 0;
         float mxf = 0.0f;
         double incl = 0.0;
         if (validB) {
@@ -1198,9 +1206,14 @@ quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constan
             mxf = flf[0];
 #pragma unroll
             for (int j = 1; j < kEpt; ++j) mxf = fmaxf(mxf, flf[j]);
-            if (mxf != 0.0f) {
+            if (mxf != 0.0f) {            // rare (light tails): 2-bit mask "floor != 0" and the floors themselves, saturated at 15
 #pragma unroll
                 for (int j = 0; j < kEpt; ++j) flm |= ((flf[j] != 0.0f) ? 1u : 0u) << (2 * j);
+#pragma unroll
+                for (int j = 0; j < kEpt / 2; ++j) {
+                    fl4a |= (uint32_t)fminf(flf[j], 15.0f) << (4 * j);
+                    fl4b |= (uint32_t)fminf(flf[j + kEpt / 2], 15.0f) << (4 * j);
+                }
             }
             double run = (double)fr[0];
 #pragma unroll
@@ -1367,7 +1380,13 @@ quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constan
                 if (off16 != ~0ull) {
                     uint32_t *tw = a.pack.codes + off16 * 4ull;
                     if (W == 2) tw[threadIdx.x] = kw | flmP | (sgwP & 0xaaaaaaaau);     // fields [sign | magnitude bit]: k = floor + r <= 1
-                    else {
+                    else if (W == 4) {
+                        // fields [sign | 3-bit k], k = floor + r <= 7, from registers: the 2-bit pairs [sign | r] are spread
+                        // to nibbles [sign 0 0 r], the parked floors are added nibble-wise (no carry reaches the sign bit)
+                        const uint32_t c = (kw & 0x55555555u) | (sgwP & 0xaaaaaaaau);
+                        tw[threadIdx.x] = spread_pairs_to_nibbles(c & 0xffffu) + fl4aP;
+                        tw[kThreads + threadIdx.x] = spread_pairs_to_nibbles(c >> 16) + fl4bP;
+                    } else {
                         float x[kEpt];
                         load_x_global(a, iC.c, iC.t, x, (int)threadIdx.x);
                         emit_wide_x(x, rc, kw, sgwP, W, tw, (int)threadIdx.x);
@@ -1375,7 +1394,7 @@ quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constan
                 }
             }
         }
-        sgwP = sgw; flmP = flm; mxfP = mxf; inclP = incl; wbaseP = wbase; wnextP = wnext; fmP = fm; AqP = Aq;
+        sgwP = sgw; flmP = flm; fl4aP = fl4a; fl4bP = fl4b; mxfP = mxf; inclP = incl; wbaseP = wbase; wnextP = wnext; fmP = fm; AqP = Aq;
         // rotate the ring: the B tile becomes the C tile, the buffer after it holds the next B tile, the freed buffer
         // receives the prefetch
         const int nB = sB == 2 ? 0 : sB + 1;

@@ -1066,6 +1066,7 @@ struct TScratch {
     uint32_t flmaxw[2][kWarps];
     TItem item[3];
     uint64_t mbar[3];
+    uint64_t winbar[2];          // completion of the look-back window copies (32 arrivals: the lanes of warp 0), by iteration parity
     unsigned int hit[2];
     int rc_row[2];
     unsigned long long off16;
@@ -1139,18 +1140,67 @@ __device__ __forceinline__ uint32_t spread_pairs_to_nibbles(uint32_t v) {
     return (v & 0x11111111u) | ((v & 0x22222222u) << 2);
 }
 
-template <int EMIT, int CTAS>
-__global__ void __launch_bounds__(kThreads, CTAS)
+// ====================================================================================================================
+// 128 threads per tile, TWO chunks per thread: thread t owns coordinates [32t, 32t + 32) = one 128-byte swizzle row of the
+// staged tile (its eight 16-byte pieces fall into distinct banks for the eight lanes of a quarter warp).  The per-thread
+// work that does not depend on the number of coordinates (warp scans, prefix geometry, look-back evaluation, control) is
+// paid once per 32 coordinates, and a CTA-wide barrier joins 4 warps.  The prefix after a thread's first chunk is DEFINED
+// as E + (sum of the first 16 fractional parts, left to right); the second chunk starts from that very value.
+// (A 256-thread variant with one chunk per thread was measured: 4.26 ms vs 4.05 ms at d = 2^24, n = 128 with the same
+// look-back timing.)
+constexpr int kThreads2 = kThreads / 2, kWarps2 = kThreads2 / 32;
+// B-phase of one chunk: signs, floors / fractions (parked in place of x), floor masks, running fp64 sum of the fractions
+__device__ __forceinline__ void tiles_chunk_b(const StreamArgs &a, const TItem &iB, uint32_t buf, uint32_t boff, int ch, const RowConst &rc,
+                                               uint32_t &sgw, uint32_t &flm, uint32_t &fl4a, uint32_t &fl4b, float &mx, double &run, bool first) {
+    float x[kEpt], flf[kEpt], fr[kEpt];
+    load_x(a, iB.flags, iB.c, iB.t, buf, x, ch);
+#pragma unroll
+    for (int j = kEpt - 1; j >= 0; --j) sgw = __funnelshift_l(__float_as_uint(x[j]), sgw, 2);
+    floors_and_fracs(x, rc, flf, fr);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        sts128((buf + boff) ^ (uint32_t)(q << 4), make_float4(fr[4 * q], fr[4 * q + 1], fr[4 * q + 2], fr[4 * q + 3]));
+    mx = flf[0];
+#pragma unroll
+    for (int j = 1; j < kEpt; ++j) mx = fmaxf(mx, flf[j]);
+    if (mx != 0.0f) {
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) flm |= ((flf[j] != 0.0f) ? 1u : 0u) << (2 * j);
+#pragma unroll
+        for (int j = 0; j < kEpt / 2; ++j) {
+            fl4a |= (uint32_t)fminf(flf[j], 15.0f) << (4 * j);
+            fl4b |= (uint32_t)fminf(flf[j + kEpt / 2], 15.0f) << (4 * j);
+        }
+    }
+    if (first) run = (double)fr[0];
+    else run += (double)fr[0];
+#pragma unroll
+    for (int j = 1; j < kEpt; ++j) run += (double)fr[j];
+}
+__device__ __forceinline__ uint32_t tiles_chunk_c(const BinadeEntry *tab, uint32_t buf, uint32_t boff, double E, double En, float X) {
+    float fr[kEpt];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 v = lds128((buf + boff) ^ (uint32_t)(q << 4));
+        fr[4 * q] = v.x; fr[4 * q + 1] = v.y; fr[4 * q + 2] = v.z; fr[4 * q + 3] = v.w;
+    }
+    const Geo g = make_geo(tab, E, En);
+    return rbits_interleaved(g, fr, X);
+}
+template <int EMIT>
+__global__ void __launch_bounds__(kThreads2, 4)
 quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char dyn_smem[];      // three tile buffers, TScratch
     TScratch &sc = *reinterpret_cast<TScratch *>(dyn_smem + (size_t)3 * kTile * sizeof(float));
     const uint32_t buf0 = smem_u32(dyn_smem);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ch0 = 2 * tid, ch1 = 2 * tid + 1;
     const uint64_t pol = policy_evict_first();
-    const uint32_t boff = blocked_off();
-    const bool window_ok = a.TS <= 32;           // rows beyond 2^27 coordinates resolve their look-back from global memory
-    if (threadIdx.x == 0) {
+    const uint32_t boff0 = blocked_off_of((uint32_t)ch0), boff1 = blocked_off_of((uint32_t)ch1);
+    const bool window_ok = a.TS <= 32;
+    if (tid == 0) {
         for (int q = 0; q < 3; ++q) mbar_init(&sc.mbar[q], 1);
+        mbar_init(&sc.winbar[0], 32); mbar_init(&sc.winbar[1], 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const unsigned int t0 = tiles_ticket(a), t1 = tiles_ticket(a);
         tiles_take(a, &tmap, sc, 0, buf0, pol, t0);
@@ -1160,14 +1210,14 @@ quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constan
         sc.hit[0] = sc.hit[1] = 0;
     }
     __syncthreads();
-    // state of the tile whose C-phase is pending (one iteration behind its B-phase)
-    uint32_t sgwP = 0, flmP = 0, fl4aP = 0, fl4bP = 0;   // fl4: the thread's floors as nibbles (coordinates 0-7 / 8-15), for 4-bit tiles
+    // state of the tile whose C-phase is pending (one iteration behind its B-phase); index 0 / 1 = the thread's chunks
+    uint32_t sgw0P = 0, sgw1P = 0, flm0P = 0, flm1P = 0, f4a0P = 0, f4b0P = 0, f4a1P = 0, f4b1P = 0;
     float mxfP = 0.0f;
-    double inclP = 0.0;
-    double wbaseP = 0.0, wnextP = 0.0;   // in-tile exclusive prefix of this warp / of the next warp (tile total for the last warp)
-    uint32_t fmP = 0;                    // largest floor of that tile (float bits)
-    long long AqP = 0;                   // its aggregate (fixed point)
-    int sB = 0, sC = 2, useB = 0;        // ring positions of the B tile / the C tile, how often buffer sB has been filled before
+    double inclP = 0.0, run0P = 0.0;
+    double wbaseP = 0.0, wnextP = 0.0;
+    uint32_t fmP = 0;
+    long long AqP = 0;
+    int sB = 0, sC = 2, useB = 0;
     for (int it = 0;; ++it) {
         const TItem iB = sc.item[sB];
         TItem iC = sc.item[sC];
@@ -1176,48 +1226,28 @@ quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constan
         if (!validB && !validC) break;
         const int e = it & 1;
         // ---------------------------------------------------------------- B-phase of tile iB
-        uint32_t sgw = 0, flm = 0, fl4a = 0, fl4b = 0;
+        uint32_t sgw0 = 0, sgw1 = 0, flm0 = 0, flm1 = 0, f4a0 = 0, f4b0 = 0, f4a1 = 0, f4b1 = 0;
         float mxf = 0.0f;
-        double incl = 0.0;
+        double incl = 0.0, run0 = 0.0;
         if (validB) {
             if (sc.rc_row[e] != iB.c) {          // CTA-uniform: the row's constants and binade table into shared memory
-                __syncthreads();                // (everybody has read rc_row)
-                if (threadIdx.x < (int)(sizeof(RowConst) / 16))
-                    reinterpret_cast<uint4 *>(&sc.rc[e])[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(&a.consts[iB.c]) + threadIdx.x);
-                else if (threadIdx.x >= 32 && threadIdx.x < 32 + kBinades)
-                    reinterpret_cast<uint4 *>(sc.tab[e])[threadIdx.x - 32] =
-                        __ldg(reinterpret_cast<const uint4 *>(a.tabs + (int64_t)iB.c * kBinades) + (threadIdx.x - 32));
-                if (threadIdx.x == 64) sc.rc_row[e] = iB.c;
+                __syncthreads();
+                if (tid < (int)(sizeof(RowConst) / 16))
+                    reinterpret_cast<uint4 *>(&sc.rc[e])[tid] = __ldg(reinterpret_cast<const uint4 *>(&a.consts[iB.c]) + tid);
+                else if (tid >= 32 && tid < 32 + kBinades)
+                    reinterpret_cast<uint4 *>(sc.tab[e])[tid - 32] = __ldg(reinterpret_cast<const uint4 *>(a.tabs + (int64_t)iB.c * kBinades) + (tid - 32));
+                if (tid == 64) sc.rc_row[e] = iB.c;
                 __syncthreads();
             }
             const RowConst &rc = sc.rc[e];
             const uint32_t buf = buf0 + (uint32_t)sB * kTile * 4u;
             mbar_wait(smem_u32(&sc.mbar[sB]), (uint32_t)(useB & 1));
-            // the look-back window of tile C as late as its latency allows (the records are fresher), behind the B-phase math
-            if (warp == 0 && validC && window_ok) window_prefetch(a, sc.win[e], iC.c, iC.t, lane);
-            float x[kEpt], flf[kEpt], fr[kEpt];
-            load_x(a, iB.flags, iB.c, iB.t, buf, x);
-#pragma unroll
-            for (int j = kEpt - 1; j >= 0; --j) sgw = __funnelshift_l(__float_as_uint(x[j]), sgw, 2);     // bit 2j+1 = sign of x[j]
-            floors_and_fracs(x, rc, flf, fr);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)            // park the fractional parts in place of x
-                sts128((buf + boff) ^ (uint32_t)(q << 4), make_float4(fr[4 * q], fr[4 * q + 1], fr[4 * q + 2], fr[4 * q + 3]));
-            mxf = flf[0];
-#pragma unroll
-            for (int j = 1; j < kEpt; ++j) mxf = fmaxf(mxf, flf[j]);
-            if (mxf != 0.0f) {            // rare (light tails): 2-bit mask "floor != 0" and the floors themselves, saturated at 15
-#pragma unroll
-                for (int j = 0; j < kEpt; ++j) flm |= ((flf[j] != 0.0f) ? 1u : 0u) << (2 * j);
-#pragma unroll
-                for (int j = 0; j < kEpt / 2; ++j) {
-                    fl4a |= (uint32_t)fminf(flf[j], 15.0f) << (4 * j);
-                    fl4b |= (uint32_t)fminf(flf[j + kEpt / 2], 15.0f) << (4 * j);
-                }
-            }
-            double run = (double)fr[0];
-#pragma unroll
-            for (int j = 1; j < kEpt; ++j) run += (double)fr[j];
+            float mx0, mx1;
+            double run;
+            tiles_chunk_b(a, iB, buf, boff0, ch0, rc, sgw0, flm0, f4a0, f4b0, mx0, run, true);
+            run0 = run;
+            tiles_chunk_b(a, iB, buf, boff1, ch1, rc, sgw1, flm1, f4a1, f4b1, mx1, run, false);
+            mxf = fmaxf(mx0, mx1);
             incl = run;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -1225,12 +1255,15 @@ quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constan
                 if (lane >= o) incl += up;
             }
             if (lane == 31) sc.wtot[e][warp] = incl;
-            const uint32_t wmx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));     // floors are >= 0: bit order = value order
+            const uint32_t wmx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));
             if (lane == 0) sc.flmaxw[e][warp] = wmx;
         }
         if (warp == 0) {
-            if (!validB && validC && window_ok) window_prefetch(a, sc.win[e], iC.c, iC.t, lane);
-            cp_async_wait_all();
+            // The look-back window of tile C is copied as LATE as possible -- the later, the more of the earlier tiles'
+            // aggregates are there (issued at the start of the B-phase a third of the tiles found it incomplete and had to
+            // poll) -- and nobody waits for the copies here: they signal winbar[e], which the C-phase checks.
+            if (validC && window_ok) window_prefetch(a, sc.win[e], iC.c, iC.t, lane);
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&sc.winbar[e])) : "memory");
         }
         __syncthreads();
         // ---------------------------------------------------------------- every warp: warp bases of tile B (fixed order), its aggregate
@@ -1238,19 +1271,19 @@ quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constan
         uint32_t fm = 0;
         long long Aq = 0;
         if (validB) {
-            double wi = lane < kWarps ? sc.wtot[e][lane] : 0.0;
+            double wi = lane < kWarps2 ? sc.wtot[e][lane] : 0.0;
 #pragma unroll
-            for (int o = 1; o < kWarps; o <<= 1) {
+            for (int o = 1; o < kWarps2; o <<= 1) {
                 const double up = __shfl_up_sync(0xffffffffu, wi, o);
                 if (lane >= o) wi += up;
             }
             wnext = __shfl_sync(0xffffffffu, wi, warp);
             wbase = __shfl_sync(0xffffffffu, wi, warp > 0 ? warp - 1 : 0);
             if (warp == 0) wbase = 0.0;
-            const double A = __shfl_sync(0xffffffffu, wi, kWarps - 1);
-            fm = __reduce_max_sync(0xffffffffu, lane < kWarps ? sc.flmaxw[e][lane] : 0u);
+            const double A = __shfl_sync(0xffffffffu, wi, kWarps2 - 1);
+            fm = __reduce_max_sync(0xffffffffu, lane < kWarps2 ? sc.flmaxw[e][lane] : 0u);
             Aq = __double2ll_rn(A * sc.rc[e].q_up);          // fixed point, 2^-qshift resolution
-            if (threadIdx.x == 0) {
+            if (tid == 0) {
                 rec_store(a.desc + (int64_t)iB.c * a.T + iB.t, (unsigned long long)Aq, 1u);
                 const unsigned long long lo = ((unsigned long long)Aq & 0x7fffffffull) + (1ull << kCntShift);
                 const unsigned long long hi = ((unsigned long long)Aq >> 31) + (1ull << kCntShift);
@@ -1259,18 +1292,19 @@ quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constan
                 red_add_u64(&sr->lo, lo); red_add_u64(&sr->hi, hi);
             }
         }
-        if (threadIdx.x == 0) sc.hit[e ^ 1] = 0;
+        if (tid == 0) sc.hit[e ^ 1] = 0;
         // ---------------------------------------------------------------- C-phase of tile iC: AS:635-637
-        uint32_t kw = 0;
+        uint32_t kw0 = 0, kw1 = 0;
+        const float fmf = __uint_as_float(fmP);
+        const bool need_hit = validC && EMIT == 1 && width_of(fmf) != width_of(__fadd_rn(fmf, 1.0f));      // CTA-uniform
         if (validC) {
             const RowConst &rc = sc.rc[e ^ 1];
             const uint32_t buf = buf0 + (uint32_t)sC * kTile * 4u;
             long long P = 0;
+            mbar_wait(smem_u32(&sc.winbar[e]), (uint32_t)((it >> 1) & 1));          // the window copies have landed
             if (iC.t > 0 && !(window_ok && window_eval(sc.win[e], lane, P))) {
-                // a record of the window was not complete when it was copied (every warp sees the same window, so the
-                // whole CTA is here): warp 0 polls global memory, the others wait
 #ifdef DME_COUNT_FALLBACK
-                if (threadIdx.x == 0) atomicAdd(&a.hdr->pad[0], 1u);      // tools/fallback_count.py
+                if (tid == 0) atomicAdd(&a.hdr->pad[0], 1u);
 #endif
                 if (warp == 0) {
                     const TileRec *tiles = a.desc + (int64_t)iC.c * a.T;
@@ -1287,87 +1321,81 @@ quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constan
                 P = sc.pfb;
             }
             const double Pd = __ll2double_rn(P) * rc.q_dn;
-            float fr[kEpt];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 v = lds128((buf + boff) ^ (uint32_t)(q << 4));
-                fr[4 * q] = v.x; fr[4 * q + 1] = v.y; fr[4 * q + 2] = v.z; fr[4 * q + 3] = v.w;
-            }
             double excl = __shfl_up_sync(0xffffffffu, inclP, 1);
             if (lane == 0) excl = 0.0;
             const double Pw = Pd + wbaseP;
             const double E = Pw + excl;
             double En = Pw + inclP;
             if (lane == 31) En = Pd + wnextP;                    // = the next warp's first prefix, bit for bit
-            if (threadIdx.x == kThreads - 1) En = __ll2double_rn(P + AqP) * rc.q_dn;      // = the next tile's first prefix
-            const Geo g = make_geo(sc.tab[e ^ 1], E, En);
-            kw = rbits_interleaved(g, fr, rc.X);
-            const float fmf = __uint_as_float(fmP);
-            if (EMIT == 1 && width_of(fmf) != width_of(__fadd_rn(fmf, 1.0f)) && mxfP == fmf) {
+            if (tid == kThreads2 - 1) En = __ll2double_rn(P + AqP) * rc.q_dn;      // = the next tile's first prefix
+            const double Em = E + run0P;                         // prefix after the first chunk
+            kw0 = tiles_chunk_c(sc.tab[e ^ 1], buf, boff0, E, Em, rc.X);
+            kw1 = tiles_chunk_c(sc.tab[e ^ 1], buf, boff1, Em, En, rc.X);
+            if (need_hit && mxfP == fmf) {
                 // the largest floor sits right below a width boundary: did one of those coordinates also receive a unit?
                 bool hit;
-                if (fmf == 1.0f) hit = (flmP & kw) != 0u;
+                if (fmf == 1.0f) hit = ((flm0P & kw0) | (flm1P & kw1)) != 0u;
                 else {
-                    float x[kEpt], fl[kEpt], fr2[kEpt];
-                    load_x_global(a, iC.c, iC.t, x, (int)threadIdx.x);
-                    floors_and_fracs(x, rc, fl, fr2);
                     hit = false;
+#pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {
+                        float x[kEpt], fl[kEpt], fr2[kEpt];
+                        load_x_global(a, iC.c, iC.t, x, h ? ch1 : ch0);
+                        floors_and_fracs(x, rc, fl, fr2);
+                        const uint32_t kw = h ? kw1 : kw0;
 #pragma unroll
-                    for (int j = 0; j < kEpt; ++j) hit |= (fl[j] == fmf) && ((kw >> (2 * j)) & 1u);
+                        for (int j = 0; j < kEpt; ++j) hit |= (fl[j] == fmf) && ((kw >> (2 * j)) & 1u);
+                    }
                 }
                 if (hit) atomicOr(&sc.hit[e], 1u);
             }
         }
-        // Buffer sC is free once every warp has read its fractional parts: only warp 0 (which issues the next copy into
-        // it) has to wait for that; the other warps just signal.  When the tile's width depends on sc.hit, everybody waits.
-        {
-            const float fmf = __uint_as_float(fmP);
-            const bool need_hit = validC && EMIT == 1 && width_of(fmf) != width_of(__fadd_rn(fmf, 1.0f));      // CTA-uniform
-            if (warp == 0 || need_hit) bar_sync(kBarFree, kThreads);
-            else bar_arrive(kBarFree, kThreads);
-        }
-        if (threadIdx.x == 0) {                  // next ticket; its tile goes where tile C was
-            tiles_take(a, &tmap, sc, sC, buf0, pol, validB ? tiles_ticket(a) : 0xffffffffu);
-        }
+        if (warp == 0 || need_hit) bar_sync(kBarFree, kThreads2);        // buffer sC is free (see quantize_tiles_kernel)
+        else bar_arrive(kBarFree, kThreads2);
+        if (tid == 0) tiles_take(a, &tmap, sc, sC, buf0, pol, validB ? tiles_ticket(a) : 0xffffffffu);
         // ---------------------------------------------------------------- emit tile iC
         if (validC) {
             const RowConst &rc = sc.rc[e ^ 1];
-            const float fm_c = __uint_as_float(fmP);
+            const float fm_c = fmf;
             if (EMIT == 0) {
-                float x[kEpt], fl[kEpt], fr2[kEpt];
-                load_x_global(a, iC.c, iC.t, x, (int)threadIdx.x);
-                floors_and_fracs(x, rc, fl, fr2);
-                const int64_t i0 = (int64_t)iC.t * kTile + (int64_t)threadIdx.x * kEpt;
                 bool ovf = false;
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    float x[kEpt], fl[kEpt], fr2[kEpt];
+                    const int ch = h ? ch1 : ch0;
+                    const uint32_t kw = h ? kw1 : kw0, sgwP = h ? sgw1P : sgw0P;
+                    load_x_global(a, iC.c, iC.t, x, ch);
+                    floors_and_fracs(x, rc, fl, fr2);
+                    const int64_t i0 = (int64_t)iC.t * kTile + (int64_t)ch * kEpt;
 #pragma unroll
-                for (int j = 0; j < kEpt; ++j) {
-                    const float kf = __fadd_rn(fl[j], (float)((kw >> (2 * j)) & 1u));
-                    const int64_t i = i0 + j;
-                    if (i >= a.d) continue;
-                    const uint32_t sbit = (sgwP >> (2 * j + 1)) & 1u;
-                    if (a.deq_out) {
-                        // sign(v) of AS:640: v = x / D is zero exactly when m * |v| is (floor and fraction both zero, m > 0)
-                        const float sgf = (fl[j] == 0.0f && fr2[j] == 0.0f) ? 0.0f : (sbit ? -1.0f : 1.0f);
-                        a.deq_out[(int64_t)iC.c * a.ld_out + i] = __fdiv_rn(__fmul_rn(__fmul_rn(rc.L1f, sgf), kf), rc.mf);
+                    for (int j = 0; j < kEpt; ++j) {
+                        const float kf = __fadd_rn(fl[j], (float)((kw >> (2 * j)) & 1u));
+                        const int64_t i = i0 + j;
+                        if (i >= a.d) continue;
+                        const uint32_t sbit = (sgwP >> (2 * j + 1)) & 1u;
+                        if (a.deq_out) {
+                            // sign(v) of AS:640: v = x / D is zero exactly when m * |v| is (floor and fraction both zero, m > 0)
+                            const float sgf = (fl[j] == 0.0f && fr2[j] == 0.0f) ? 0.0f : (sbit ? -1.0f : 1.0f);
+                            a.deq_out[(int64_t)iC.c * a.ld_out + i] = __fdiv_rn(__fmul_rn(__fmul_rn(rc.L1f, sgf), kf), rc.mf);
+                        }
+                        if (a.k_out) {
+                            if (kf >= 2147483648.0f) { ovf = true; a.k_out[(int64_t)iC.c * a.ld_out + i] = 0x7fffffff; }
+                            else a.k_out[(int64_t)iC.c * a.ld_out + i] = (int32_t)kf;
+                        }
+                        if (a.sgn_out) a.sgn_out[(int64_t)iC.c * a.ld_out + i] = (uint8_t)sbit;
                     }
-                    if (a.k_out) {
-                        if (kf >= 2147483648.0f) { ovf = true; a.k_out[(int64_t)iC.c * a.ld_out + i] = 0x7fffffff; }
-                        else a.k_out[(int64_t)iC.c * a.ld_out + i] = (int32_t)kf;
-                    }
-                    if (a.sgn_out) a.sgn_out[(int64_t)iC.c * a.ld_out + i] = (uint8_t)sbit;
                 }
                 if (ovf) atomicOr(&a.hdr->status, 1u);
             } else {
-                // tile-wide minimal field width: from the largest floor, one step wider when such a coordinate received a unit
                 const int W = sc.hit[e] ? width_of(__fadd_rn(fm_c, 1.0f)) : width_of(fm_c);
-                if (fm_c >= 2147483520.0f && threadIdx.x == 0) atomicOr(&a.hdr->status, 1u);
+                if (fm_c >= 2147483520.0f && tid == 0) atomicOr(&a.hdr->status, 1u);
                 const int64_t slot_id = (int64_t)iC.c * a.T + iC.t;
                 unsigned long long off16;
                 if (W <= a.pack.W0) {
                     off16 = primary_off16(a.pack, iC.c, iC.t);
-                    if (threadIdx.x == 0) a.pack.dir[slot_id] = (off16 << 8) | (unsigned long long)W;
+                    if (tid == 0) a.pack.dir[slot_id] = (off16 << 8) | (unsigned long long)W;
                 } else {
-                    if (threadIdx.x == 0) {
+                    if (tid == 0) {
                         const unsigned long long units = 32ull * W;
                         unsigned long long o = a.pack.arena_base16 + atomicAdd(&a.hdr->arena_top, units);
                         if ((long long)((o + units) * 16ull) > a.pack.codes_bytes) { atomicOr(&a.hdr->status, 2u); o = ~0ull; }
@@ -1379,24 +1407,32 @@ quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constan
                 }
                 if (off16 != ~0ull) {
                     uint32_t *tw = a.pack.codes + off16 * 4ull;
-                    if (W == 2) tw[threadIdx.x] = kw | flmP | (sgwP & 0xaaaaaaaau);     // fields [sign | magnitude bit]: k = floor + r <= 1
-                    else if (W == 4) {
-                        // fields [sign | 3-bit k], k = floor + r <= 7, from registers: the 2-bit pairs [sign | r] are spread
-                        // to nibbles [sign 0 0 r], the parked floors are added nibble-wise (no carry reaches the sign bit)
-                        const uint32_t c = (kw & 0x55555555u) | (sgwP & 0xaaaaaaaau);
-                        tw[threadIdx.x] = spread_pairs_to_nibbles(c & 0xffffu) + fl4aP;
-                        tw[kThreads + threadIdx.x] = spread_pairs_to_nibbles(c >> 16) + fl4bP;
+                    if (W == 2) {
+                        // fields [sign | magnitude bit]: k = floor + r <= 1; the thread's two words are adjacent
+                        uint2 w2;
+                        w2.x = kw0 | flm0P | (sgw0P & 0xaaaaaaaau);
+                        w2.y = kw1 | flm1P | (sgw1P & 0xaaaaaaaau);
+                        *reinterpret_cast<uint2 *>(tw + ch0) = w2;
+                    } else if (W == 4) {
+                        const uint32_t c0 = (kw0 & 0x55555555u) | (sgw0P & 0xaaaaaaaau), c1 = (kw1 & 0x55555555u) | (sgw1P & 0xaaaaaaaau);
+                        uint2 lo, hi;
+                        lo.x = spread_pairs_to_nibbles(c0 & 0xffffu) + f4a0P; lo.y = spread_pairs_to_nibbles(c1 & 0xffffu) + f4a1P;
+                        hi.x = spread_pairs_to_nibbles(c0 >> 16) + f4b0P;     hi.y = spread_pairs_to_nibbles(c1 >> 16) + f4b1P;
+                        *reinterpret_cast<uint2 *>(tw + ch0) = lo;
+                        *reinterpret_cast<uint2 *>(tw + kThreads + ch0) = hi;
                     } else {
-                        float x[kEpt];
-                        load_x_global(a, iC.c, iC.t, x, (int)threadIdx.x);
-                        emit_wide_x(x, rc, kw, sgwP, W, tw, (int)threadIdx.x);
+#pragma unroll 1
+                        for (int h = 0; h < 2; ++h) {
+                            float x[kEpt];
+                            load_x_global(a, iC.c, iC.t, x, h ? ch1 : ch0);
+                            emit_wide_x(x, rc, h ? kw1 : kw0, h ? sgw1P : sgw0P, W, tw, h ? ch1 : ch0);
+                        }
                     }
                 }
             }
         }
-        sgwP = sgw; flmP = flm; fl4aP = fl4a; fl4bP = fl4b; mxfP = mxf; inclP = incl; wbaseP = wbase; wnextP = wnext; fmP = fm; AqP = Aq;
-        // rotate the ring: the B tile becomes the C tile, the buffer after it holds the next B tile, the freed buffer
-        // receives the prefetch
+        sgw0P = sgw0; sgw1P = sgw1; flm0P = flm0; flm1P = flm1; f4a0P = f4a0; f4b0P = f4b0; f4a1P = f4a1; f4b1P = f4b1;
+        mxfP = mxf; inclP = incl; run0P = run0; wbaseP = wbase; wnextP = wnext; fmP = fm; AqP = Aq;
         const int nB = sB == 2 ? 0 : sB + 1;
         sC = sB; sB = nB;
         if (sB == 0) ++useB;
@@ -1408,15 +1444,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
-static int g_tiles_ctas = 3;
-static const void *g_tiles_fn[2] = {nullptr, nullptr};
 
-// Which path quantises a row of d coordinates: the fused persistent kernel for rows of 32 MiB and more (no L2 reuse
-// either way; it overlaps the L1 pass with the quantize pass: 5.5 ms vs 1.3 + 4.6 ms at d = 2^24, n = 128), l1_kernel +
-// quantize_tiles_kernel below that (0.41 ms vs 0.55 ms at d = 2^20, n = 128).  DME_PATH=stream|tiles overrides.
+// Which path quantises: l1_kernel + quantize_tiles_kernel (default: 1.32 + 3.27 ms at d = 2^24, n = 128; 0.10 + 0.22 ms at
+// d = 2^20) or the fused persistent quantize_stream_kernel (5.55 ms / 0.55 ms), kept as the alternative that touches DRAM
+// once for rows that fit L2.  DME_PATH=stream|tiles selects; the GPU tests run both.
 bool use_tiles_path(int64_t d) {
+    (void)d;
     if (const char *e = getenv("DME_PATH")) return !(e[0] == 's');
-    return d < ((int64_t)1 << 23);
+    return true;
 }
 
 int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
@@ -1457,15 +1492,10 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
         DME_CUDA(cudaFuncSetAttribute(quantize_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_occ[0], quantize_stream_kernel<0>, kBlock, dyn));
         DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_occ[1], quantize_stream_kernel<1>, kBlock, dyn));
-        g_tiles_ctas = 3;           // 80 registers, no spills: 4.63 ms vs 5.16 ms with 4 CTAs of 64 registers (d = 2^24, n = 128)
-        if (const char *e = getenv("DME_TILES_CTAS")) g_tiles_ctas = atoi(e) == 4 ? 4 : 3;
-        g_tiles_fn[0] = g_tiles_ctas == 3 ? (const void *)quantize_tiles_kernel<0, 3> : (const void *)quantize_tiles_kernel<0, 4>;
-        g_tiles_fn[1] = g_tiles_ctas == 3 ? (const void *)quantize_tiles_kernel<1, 3> : (const void *)quantize_tiles_kernel<1, 4>;
-        for (int q = 0; q < 2; ++q) {
-            DME_CUDA(cudaFuncSetAttribute(g_tiles_fn[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_tiles));
-            DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_occ_tiles[q], g_tiles_fn[q], kThreads, dyn_tiles));
-            if (g_occ_tiles[q] > g_tiles_ctas) g_occ_tiles[q] = g_tiles_ctas;
-        }
+        DME_CUDA(cudaFuncSetAttribute(quantize_tiles_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_tiles));
+        DME_CUDA(cudaFuncSetAttribute(quantize_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_tiles));
+        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_occ_tiles[0], quantize_tiles_kernel<0>, kThreads2, dyn_tiles));
+        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_occ_tiles[1], quantize_tiles_kernel<1>, kThreads2, dyn_tiles));
         cudaDriverEntryPointQueryResult qres;
         void *fn = nullptr;
         DME_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -1497,8 +1527,8 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
         if (const char *e = getenv("DME_DBG_G")) Gt = atoll(e);
         if (Gt > nT) Gt = nT;
         a.lag = a.goff = a.total_items = 0; a.G = Gt; a.step_c = a.step_t = a.total_items32 = a.ahead = 0;
-        void *targs[] = {&a, &tmap};
-        DME_CUDA(cudaLaunchKernel(g_tiles_fn[packed ? 1 : 0], dim3((unsigned)Gt), dim3(kThreads), targs, dyn_tiles, st));
+        if (packed) quantize_tiles_kernel<1><<<(unsigned)Gt, kThreads2, dyn_tiles, st>>>(a, tmap);
+        else quantize_tiles_kernel<0><<<(unsigned)Gt, kThreads2, dyn_tiles, st>>>(a, tmap);
         DME_LAUNCH_CHECK("quantize_tiles_kernel");
         return DME_OK;
     }

@@ -177,10 +177,14 @@ def run_ours(a):
     mean = torch.empty(d, dtype=torch.float32, device=dev)
     L = _cabi.lib()
 
+    from dme_b200 import distributed as dmed
+
     def step(i):
-        dme.quantize_mean(X, R, mode=a.mode, seed=1234 + i, client0=client0, n_total=n_total, out=mean, check=False)
-        if world > 1:
-            dist.all_reduce(mean, op=dist.ReduceOp.SUM)          # the path's one exchange step
+        # N > 1: every rank quantizes + decodes its own clients with the global divisor, then ONE all-reduce.
+        # (dmed.quantize_mean_overlapped, which all-reduces finished slices of the mean while later ones are decoded, was
+        # measured at N = 2: 5.24-5.30 ms vs 5.22 ms -- the 0.4 ms decode is too short to hide anything behind.)
+        dmed.quantize_mean_sharded(X, R, n_total=n_total, client0=client0, seed=1234 + i, mode=a.mode, out=mean,
+                                   local_fn=lambda x, r, **kw: dme.quantize_mean(x, r, check=False, **kw))
 
     def sync():
         if world > 1:
@@ -225,9 +229,10 @@ def run_ours(a):
     L.dme_profile_enable(0)
     per = np.array(per[1:])
     kern_ms = per.mean(axis=0) if per.size else np.array([ms_step])
-    if len(kern_ms) >= 3:      # rows below 32 MiB (or DME_PATH=tiles): l1_kernel -> quantize_tiles_kernel -> decode_mean_kernel
+    if len(kern_ms) >= 3:      # default path: l1_kernel -> quantize_tiles_kernel -> decode_mean_kernel (one launch per slice when N > 1)
         names = ["l1_kernel", "quantize_tiles_kernel", "decode_mean_kernel"]
-    else:                      # the fused persistent kernel (L1 pass + quantize pass in one launch)
+        kern_ms = np.array([kern_ms[0], kern_ms[1], kern_ms[2:].sum()])
+    else:                      # DME_PATH=stream: the fused persistent kernel (L1 pass + quantize pass in one launch)
         names = ["quantize_stream_kernel", "decode_mean_kernel"][: len(kern_ms)]
     dom = int(np.argmax(kern_ms))
     # algorithmic bytes of one step (every input coordinate read once, the mean written once) over the

@@ -15,6 +15,7 @@
  *                           (deq) and/or the integer type vector + signs it only implies
  *   dme_type_encode         same arithmetic, emits the packed code "DMEP1" (no reference counterpart)
  *   dme_decode_mean         AS:640 / AS:687 dequantise + ND:133-147 `est += q / n`
+ *   dme_decode_mean_tiles   the same for a range of tiles (slices of the mean, for overlap with the all-reduce)
  *   dme_quantize_mean       fused: the whole server loop ND:133-147 for the type quantizers
  *   dme_hadamard            AS:100-115   Hadamard.hadamard
  *   dme_rht / dme_irht      AS:127-144 / AS:151-156 (diagonal AS:117-120: Philox or injected)
@@ -107,6 +108,13 @@ DME_API int dme_type_encode(const float *X, int64_t n, int64_t d, int64_t ld, in
 /* mean[i] (+)= sum_c deq(c, i) / n_total, clients in order, fp32.  accumulate=0 overwrites. */
 DME_API int dme_decode_mean(const void *codes, const uint64_t *dir, const float *l1, int64_t n, int64_t d,
                     int64_t m, int mode, int64_t n_total, float *mean, int accumulate, dme_stream_t stream);
+
+/* The same for tiles [tile0, tile0 + tiles) only, i.e. coordinates [tile0 * DME_TILE, (tile0 + tiles) * DME_TILE) of the
+ * mean: the decoder is tile-major, so a sharded run can all-reduce finished slices of the mean while later slices are
+ * still being decoded (ND:133-147 + the exchange step of SURVEY 8e). */
+DME_API int dme_decode_mean_tiles(const void *codes, const uint64_t *dir, const float *l1, int64_t n, int64_t d,
+                    int64_t m, int mode, int64_t n_total, float *mean, int accumulate, int64_t tile0, int64_t tiles,
+                    dme_stream_t stream);
 
 /* quantize -> pack -> decode -> mean in one call (the north-star path).  `codes`/`dir` are scratch here. */
 DME_API int dme_quantize_mean(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, int mode,

@@ -130,6 +130,10 @@ def test_fused_quantize_mean_and_determinism(dme):
     assert np.allclose((h1 + h2).cpu().numpy(), a, rtol=0, atol=4e-7 * np.abs(X).max())
     host = dme.quantize_mean_host(torch.from_numpy(X).pin_memory(), 1, seed=3).numpy()
     assert np.array_equal(_u32(host), _u32(a))
+    # decode in slices of tiles (what a sharded run overlaps with its all-reduce): the same bits
+    seen = []
+    sl = dme.quantize_mean_sliced(Xd, 1, seed=3, slices=4, on_slice=lambda v: seen.append(v.numel())).cpu().numpy()
+    assert np.array_equal(_u32(sl), _u32(a)) and sum(seen) == d and len(seen) == 4
     # chunked host pipeline (ragged last chunk): clients are still added in order -> the same bits
     host5 = dme.quantize_mean_host(torch.from_numpy(X).pin_memory(), 1, seed=3, chunk_clients=5).numpy()
     assert np.array_equal(_u32(host5), _u32(a))

@@ -25,6 +25,7 @@ SIGNATURES = {
     "dme_type_quantize": (ci, [vp, i64, i64, i64, i64, ci, vp, vp, u64, u64, vp, vp, vp, i64, vp, vp, i64, vp]),
     "dme_type_encode": (ci, [vp, i64, i64, i64, i64, ci, vp, vp, u64, u64, vp, i64, vp, vp, vp, i64, vp]),
     "dme_decode_mean": (ci, [vp, vp, vp, i64, i64, i64, ci, i64, vp, ci, vp]),
+    "dme_decode_mean_tiles": (ci, [vp, vp, vp, i64, i64, i64, ci, i64, vp, ci, i64, i64, vp]),
     "dme_quantize_mean": (ci, [vp, i64, i64, i64, i64, ci, vp, u64, u64, i64, vp, ci, vp, i64, vp, vp, vp, i64, vp]),
     "dme_mean_accumulate": (ci, [vp, i64, i64, i64, i64, vp, ci, vp]),
     "dme_hadamard": (ci, [vp, i64, i64, i64, vp]),

@@ -228,15 +228,58 @@ def type_encode(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, cli
     return PackedCodes(codes, dr, l1, n, d, mm, MODE[mode])
 
 
-def decode_mean(pc: PackedCodes, *, n_total=None, out=None, accumulate=False):
-    """Server side: dequantise (AS:640 / AS:687) and average, `est += q / n` in client order (ND:133-147)."""
+def decode_mean(pc: PackedCodes, *, n_total=None, out=None, accumulate=False, tiles=None):
+    """Server side: dequantise (AS:640 / AS:687) and average, `est += q / n` in client order (ND:133-147).
+
+    tiles=(tile0, count) decodes only coordinates [tile0 * 4096, (tile0 + count) * 4096) of `out` (slices of the mean
+    complete in order, so a sharded run can all-reduce one slice while the next is decoded)."""
     dev = pc.codes.device
     if out is None:
         out = torch.empty(pc.d, dtype=torch.float32, device=dev)
         accumulate = False
     nt = pc.n if n_total is None else int(n_total)
-    _check(_cabi.lib().dme_decode_mean(_ptr(pc.codes), _ptr(pc.dir), _ptr(pc.l1), pc.n, pc.d, pc.m, pc.mode, nt, _ptr(out),
-                                       int(bool(accumulate)), C.c_void_p(_stream())))
+    T = (pc.d + TILE - 1) // TILE
+    t0, cnt = (0, T) if tiles is None else (int(tiles[0]), int(tiles[1]))
+    _check(_cabi.lib().dme_decode_mean_tiles(_ptr(pc.codes), _ptr(pc.dir), _ptr(pc.l1), pc.n, pc.d, pc.m, pc.mode, nt, _ptr(out),
+                                             int(bool(accumulate)), t0, cnt, C.c_void_p(_stream())))
+    return out
+
+
+def quantize_mean_sliced(x, bits_per_dimension=1, *, slices=4, on_slice=None, mode="unbiased", m=None, seed=0, client0=0,
+                         n_total=None, x_inject=None, out=None, check=True):
+    """quantize_mean with the decode split into `slices` runs of tiles; on_slice(out[lo:hi]) is called right after the
+    decode of each slice has been enqueued (the caller's hook for a per-slice all-reduce on another stream).
+    Same bits as quantize_mean: every coordinate still sees its clients in order."""
+    X, n, d, _ = _rows(x)
+    mm = _resolve_m(d, bits_per_dimension, m)
+    dev = X.device
+    L = _cabi.lib()
+    ws, wsb = Workspace.get(dev).ensure(n, d)
+    plan = _MeanPlan.get(n, d, mm, dev)
+    if out is None:
+        out = torch.empty(d, dtype=torch.float32, device=dev)
+    xi = _opt_vec(x_inject, n, dev)
+    nt = n if n_total is None else int(n_total)
+    while True:
+        try:
+            _check(L.dme_type_encode(_ptr(X), n, d, _ld(X), mm, MODE[mode], _ptr(xi), None, seed, client0, _ptr(plan.codes), plan.cb,
+                                     _ptr(plan.dir), _ptr(plan.l1), ws, wsb, C.c_void_p(_stream())))
+            if check:
+                Workspace.get(dev).status()
+            break
+        except MemoryError:
+            if plan.cb >= int(L.dme_codes_bytes(n, d, mm, 0)):
+                raise
+            plan.grow_worst_case(n, d, mm, dev)
+    T = (d + TILE - 1) // TILE
+    S = max(1, min(int(slices), T))
+    per = (T + S - 1) // S
+    for t0 in range(0, T, per):
+        cnt = min(per, T - t0)
+        _check(L.dme_decode_mean_tiles(_ptr(plan.codes), _ptr(plan.dir), _ptr(plan.l1), n, d, mm, MODE[mode], nt, _ptr(out), 0, t0, cnt,
+                                       C.c_void_p(_stream())))
+        if on_slice is not None:
+            on_slice(out[t0 * TILE: min(d, (t0 + cnt) * TILE)])
     return out
 
 

@@ -175,7 +175,8 @@ __device__ __forceinline__ void dec_fetch(DecBatch &b, const uint2 *sinfo, const
 
 __global__ void __launch_bounds__(64, 8)
 decode_mean_kernel(const uint32_t *__restrict__ codes, const uint64_t *__restrict__ dir, const float *__restrict__ l1,
-                   int64_t n, int64_t d, int64_t T, float mf, float nf, int biased, float *__restrict__ mean, int accumulate) {
+                   int64_t n, int64_t d, int64_t T, float mf, float nf, int biased, float *__restrict__ mean, int accumulate,
+                   int64_t tile0) {
     __shared__ __align__(64) float lut16[kLutClients * 16];    // [client][sign << 3 | k] = +-q(k) / n for k < 8
     __shared__ __align__(8) uint2 sinfo[kLutClients + kBatch]; // per staged client: {code offset / 16, width code}
     __shared__ uint32_t sslow[kLutClients / kBatch];           // per batch: some client needs decode_generic
@@ -188,7 +189,7 @@ decode_mean_kernel(const uint32_t *__restrict__ codes, const uint64_t *__restric
     }
     const uint32_t lanebase = slut | ((threadIdx.x & 31u) << 3);
     const uint32_t lut16_base = (uint32_t)__cvta_generic_to_shared(lut16);
-    const int64_t t = blockIdx.x >> 2;
+    const int64_t t = tile0 + (blockIdx.x >> 2);
     const int chunk = (int)(blockIdx.x & 3) * 64 + threadIdx.x;
     const uint32_t *cptr = codes + chunk;
     const int64_t i0 = t * kTile + (int64_t)chunk * kEpt;
@@ -430,18 +431,26 @@ extern "C" int dme_type_encode(const float *X, int64_t n, int64_t d, int64_t ld,
                            (uint32_t *)codes, codes_bytes, dir, l1_out, ws, ws_bytes, (cudaStream_t)stream, true);
 }
 
-extern "C" int dme_decode_mean(const void *codes, const uint64_t *dir, const float *l1, int64_t n, int64_t d, int64_t m, int mode,
-                               int64_t n_total, float *mean, int accumulate, dme_stream_t stream) {
+extern "C" int dme_decode_mean_tiles(const void *codes, const uint64_t *dir, const float *l1, int64_t n, int64_t d, int64_t m, int mode,
+                                     int64_t n_total, float *mean, int accumulate, int64_t tile0, int64_t tiles, dme_stream_t stream) {
     DME_REQUIRE(codes && dir && l1 && mean, "null pointer argument");
     DME_REQUIRE(n >= 1 && d >= 1 && m >= 1 && n_total >= 1, "n, d, m, n_total must be >= 1");
     DME_REQUIRE(((uintptr_t)mean & 15u) == 0 && ((uintptr_t)codes & 15u) == 0, "mean and codes must be 16-byte aligned");
     const int64_t T = (d + kTile - 1) / kTile;
-    cudaStream_t st = (cudaStream_t)stream;
-    decode_mean_kernel<<<(unsigned)(4 * T), 64, kSignLutBytes, st>>>((const uint32_t *)codes, dir, l1, n, d, T, (float)m, (float)n_total,
-                                                         mode == DME_MODE_BIASED, mean, accumulate);
-    DME_LAUNCH_CHECK("decode_mean_kernel");
+    DME_REQUIRE(tile0 >= 0 && tiles >= 0 && tile0 + tiles <= T, "tile range [%lld, %lld) outside [0, %lld)", (long long)tile0,
+                (long long)(tile0 + tiles), (long long)T);
+    if (tiles > 0) {
+        decode_mean_kernel<<<(unsigned)(4 * tiles), 64, kSignLutBytes, (cudaStream_t)stream>>>(
+            (const uint32_t *)codes, dir, l1, n, d, T, (float)m, (float)n_total, mode == DME_MODE_BIASED, mean, accumulate, tile0);
+        DME_LAUNCH_CHECK("decode_mean_kernel");
+    }
     prof_mark((cudaStream_t)stream);
     return DME_OK;
+}
+
+extern "C" int dme_decode_mean(const void *codes, const uint64_t *dir, const float *l1, int64_t n, int64_t d, int64_t m, int mode,
+                               int64_t n_total, float *mean, int accumulate, dme_stream_t stream) {
+    return dme_decode_mean_tiles(codes, dir, l1, n, d, m, mode, n_total, mean, accumulate, 0, d >= 1 ? (d + kTile - 1) / kTile : 0, stream);
 }
 
 extern "C" int dme_profile_enable(int on) { g_prof.on = on != 0; prof_reset(); return DME_OK; }

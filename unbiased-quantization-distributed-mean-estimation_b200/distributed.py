@@ -36,3 +36,42 @@ def quantize_mean_sharded(x_local, bits_per_dimension=1, *, n_total: int, client
         local_fn = api.quantize_mean
     partial = local_fn(x_local, bits_per_dimension, mode=mode, seed=seed, client0=client0, n_total=n_total, out=out)
     return allreduce_partial_mean(partial, group)
+
+
+class _Comm:
+    """Side stream on which the per-slice all-reduces of quantize_mean_overlapped are enqueued (one per device)."""
+    _streams: dict = {}
+
+    @classmethod
+    def stream(cls, dev):
+        if dev.index not in cls._streams:
+            cls._streams[dev.index] = torch.cuda.Stream(device=dev)
+        return cls._streams[dev.index]
+
+
+def quantize_mean_overlapped(x_local, bits_per_dimension=1, *, n_total: int, client0: int, seed: int = 0, mode="unbiased",
+                             out=None, group=None, slices: int = 4, check=True):
+    """quantize_mean_sharded with the exchange step overlapped: the decoder is tile-major, so the mean is produced in
+    `slices` runs of tiles and each finished slice is all-reduced (NCCL, on a side stream) while the next one is decoded.
+    Same result as quantize_mean_sharded (the all-reduce of a slice does not depend on how the vector was cut).
+    Measured on 2 B200s at d = 2^24, n = 128 per GPU: 5.24 ms (2 slices) .. 5.30 ms (8) vs 5.22 ms un-overlapped -- the
+    0.4 ms decode is too short to hide a 0.2 ms all-reduce behind once NCCL's kernels share the SMs; bench.py uses the
+    plain call.  Kept for shapes where the decode dominates (many clients per GPU)."""
+    from . import api
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return api.quantize_mean(x_local, bits_per_dimension, mode=mode, seed=seed, client0=client0, n_total=n_total, out=out, check=check)
+    dev = x_local.device
+    main = torch.cuda.current_stream()
+    comm = _Comm.stream(dev)
+
+    def reduce_slice(view):
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(comm):
+            comm.wait_event(ev)
+            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group)
+
+    res = api.quantize_mean_sliced(x_local, bits_per_dimension, slices=slices, on_slice=reduce_slice, mode=mode, seed=seed,
+                                   client0=client0, n_total=n_total, out=out, check=check)
+    main.wait_stream(comm)
+    return res

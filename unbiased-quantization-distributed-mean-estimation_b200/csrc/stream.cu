@@ -1523,6 +1523,7 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
         // the row constants are there already (l1_kernel, launched by the caller on the same stream)
         const int occ_t = g_occ_tiles[packed ? 1 : 0];
         if (occ_t < 1) { set_error("quantize_tiles_kernel does not fit on an SM"); return DME_ECUDA; }
+        if (nT >= ((int64_t)1 << 32) - 65536) { set_error("n * tiles = %lld does not fit the 32-bit ticket counter", (long long)nT); return DME_EINVAL; }
         int64_t Gt = (int64_t)g_sms * occ_t;
         if (const char *e = getenv("DME_DBG_G")) Gt = atoll(e);
         if (Gt > nT) Gt = nT;

@@ -1258,7 +1258,10 @@ quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constan
             const uint32_t wmx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));
             if (lane == 0) sc.flmaxw[e][warp] = wmx;
         }
-        if (warp == 0) {
+        // The serial jobs of an iteration are spread over the four warps (window copies: warp 1, publish: warp 2, next ticket and
+        // copy: warp 3, directory / arena: warp 0): warp w of every CTA runs on scheduler w, so giving them all to warp 0
+        // overloads one scheduler while the other three wait at the barrier.
+        if (warp == 1) {
             // The look-back window of tile C is copied as LATE as possible -- the later, the more of the earlier tiles'
             // aggregates are there (issued at the start of the B-phase a third of the tiles found it incomplete and had to
             // poll) -- and nobody waits for the copies here: they signal winbar[e], which the C-phase checks.
@@ -1283,7 +1286,7 @@ quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constan
             const double A = __shfl_sync(0xffffffffu, wi, kWarps2 - 1);
             fm = __reduce_max_sync(0xffffffffu, lane < kWarps2 ? sc.flmaxw[e][lane] : 0u);
             Aq = __double2ll_rn(A * sc.rc[e].q_up);          // fixed point, 2^-qshift resolution
-            if (tid == 0) {
+            if (tid == 64) {
                 rec_store(a.desc + (int64_t)iB.c * a.T + iB.t, (unsigned long long)Aq, 1u);
                 const unsigned long long lo = ((unsigned long long)Aq & 0x7fffffffull) + (1ull << kCntShift);
                 const unsigned long long hi = ((unsigned long long)Aq >> 31) + (1ull << kCntShift);
@@ -1350,9 +1353,11 @@ quantize_tiles_kernel(const __grid_constant__ StreamArgs a, const __grid_constan
                 if (hit) atomicOr(&sc.hit[e], 1u);
             }
         }
-        if (warp == 0 || need_hit) bar_sync(kBarFree, kThreads2);        // buffer sC is free (see quantize_tiles_kernel)
+        // Buffer sC is free once every warp has read its fractional parts: only the warp that issues the next copy into it has
+        // to wait for that, the others just signal.  When the tile's width depends on sc.hit, everybody waits.
+        if (warp == 3 || need_hit) bar_sync(kBarFree, kThreads2);
         else bar_arrive(kBarFree, kThreads2);
-        if (tid == 0) tiles_take(a, &tmap, sc, sC, buf0, pol, validB ? tiles_ticket(a) : 0xffffffffu);
+        if (tid == 96) tiles_take(a, &tmap, sc, sC, buf0, pol, validB ? tiles_ticket(a) : 0xffffffffu);
         // ---------------------------------------------------------------- emit tile iC
         if (validC) {
             const RowConst &rc = sc.rc[e ^ 1];

@@ -1,3 +1,5 @@
+"""Development helper: how many tiles of quantize_tiles_kernel found their look-back window incomplete and had to poll.
+Build the library with DME_NVCC_EXTRA=-DDME_COUNT_FALLBACK first; UNIF=1 uses uniform inputs (only 2-bit tiles)."""
 import os, sys, torch
 sys.path.insert(0, os.getcwd())
 import dme_b200 as dme

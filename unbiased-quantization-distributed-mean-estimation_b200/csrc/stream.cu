@@ -1050,15 +1050,18 @@ quantize_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_consta
 }
 
 // ====================================================================================================================
-// Two-kernel path: l1_kernel (type_quantize.cu) has published every row's constants; this kernel makes ONE pass over the
-// tiles in ticket order (client-major) with the same decoupled look-back records as above.  Per CTA and iteration:
+// Two-kernel path (the default): l1_kernel (type_quantize.cu) has published every row's constants; quantize_tiles_kernel
+// makes ONE pass over the tiles in ticket order (client-major) with the same decoupled look-back records as above.
+// Per CTA (128 threads, a thread owns 32 coordinates) and iteration:
 //   B-phase of tile i   : floors, fractional parts (parked in place of x in the tile buffer), thread sums, scans;
-//   warp 0              : publish tile i's aggregate, resolve the look-back of tile i-1 (published one iteration ago:
-//                         normally nothing to wait for);
-//   C-phase of tile i-1 : prefix -> floor(c - X) -> type vector, emit;
+//   one warp            : copies the look-back window of tile i-1 into shared memory (cp.async, completion on an mbarrier)
+//                         as late as possible, i.e. right before the barrier that ends the B-phase;
+//   every warp          : warp bases and aggregate of tile i; one thread publishes the aggregate;
+//   C-phase of tile i-1 : window -> exclusive prefix -> floor(c - X) -> type vector, emit;
 //   then the next ticket is taken and its tile copied into the buffer just freed (ring of three).
-// No aggregate ever waits for a look-back, so the tiles of a row flow without convoys.  Every wait is on a smaller
-// ticket held by a resident CTA that does not wait on a larger one: no deadlock.
+// No aggregate ever waits for a look-back.  Every wait is on a smaller ticket held by a resident CTA that does not wait
+// on a larger one: no deadlock.  The fallback (a window record not complete yet: 0.3 % of the tiles at d = 2^24, n = 128)
+// polls global memory.
 struct __align__(16) TItem { int c, t; uint32_t flags; uint32_t ticket; };
 struct TScratch {
     Rec win[2][96];              // look-back window of the C tile (tile / block / super-block records), by iteration parity

@@ -190,7 +190,17 @@ row_minmax_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int nb, fl
     const int64_t c = blockIdx.y;
     const int64_t per = (d + nb - 1) / nb, lo = blockIdx.x * per, hi = min(d, lo + per);
     float mn = INFINITY, mx = -INFINITY;
-    for (int64_t i = lo + threadIdx.x; i < hi; i += 256) { const float v = X[c * ld + i]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+    const float *xr = X + c * ld;
+    int64_t i = lo + threadIdx.x;
+    if (((uintptr_t)(xr + lo) & 15u) == 0) {          // 128-bit loads over the aligned body of the slice
+        const int64_t nv = (hi - lo) / 4;
+        for (int64_t q = threadIdx.x; q < nv; q += 256) {
+            const float4 v = ldg_stream_f4(xr + lo + 4 * q);
+            mn = fminf(fminf(mn, fminf(v.x, v.y)), fminf(v.z, v.w)); mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+        }
+        i = lo + 4 * nv + threadIdx.x;
+    }
+    for (; i < hi; i += 256) { const float v = xr[i]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
     if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
@@ -200,36 +210,68 @@ row_minmax_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int nb, fl
         pmin[c * nb + blockIdx.x] = mn; pmax[c * nb + blockIdx.x] = mx;
     }
 }
-__global__ void __launch_bounds__(256)
-scalar_kernel(const float *__restrict__ X, int64_t n, int64_t d, int64_t ld, int nb, const float *__restrict__ pmin,
-              const float *__restrict__ pmax, float nlevels, uint64_t seed, uint64_t client0, const float *__restrict__ u_inject,
-              float *__restrict__ out, int64_t ld_out) {
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= n * d) return;
-    const int64_t c = gid / d, i = gid - c * d;
-    float mn = INFINITY, mx = -INFINITY;
-    for (int b = 0; b < nb; ++b) { mn = fminf(mn, pmin[c * nb + b]); mx = fmaxf(mx, pmax[c * nb + b]); }
-    const float x = X[c * ld + i];
-    const float denom = __fsub_rn(mx, mn);
-    if (denom == 0.0f || nlevels < 1.0f) { out[c * ld_out + i] = x; return; }                       // AS:763-765, AS:772-773
+// One coordinate of AS:768-788 (u: the uniform of AS:783).
+__device__ __forceinline__ float scalar_one(float x, float mn, float mx, float denom, float nlevels, float u) {
     float q = __fdiv_rn(__fsub_rn(x, mn), denom);                                                    // AS:768
     q = fminf(fmaxf(q, 0.0f), 1.0f);                                                                 // AS:776
     const float t = __fmul_rn(q, nlevels);
     const float bf = floorf(t);                                                                      // AS:779
     const float fr = __fsub_rn(t, bf);
-    float u;
-    if (u_inject) u = u_inject[c * d + i];
-    else {
-        const uint64_t cl = client0 + (uint64_t)c;
-        u = u24_to_unit(philox4x32_10(seed ^ (cl * 0x9E3779B97F4A7C15ull), (uint32_t)i, (uint32_t)((uint64_t)i >> 32), (uint32_t)cl, kStreamScalar).x);
-    }
     const float bi = __fadd_rn(bf, (u < fr) ? 1.0f : 0.0f);                                          // AS:783-784
     q = __fdiv_rn(bi, nlevels);                                                                      // AS:787
-    out[c * ld_out + i] = __fadd_rn(__fmul_rn(q, __fsub_rn(mx, mn)), mn);                            // AS:788
+    return __fadd_rn(__fmul_rn(q, __fsub_rn(mx, mn)), mn);                                           // AS:788
+}
+// grid (blocks along the row, client).  The CTA first folds the row's partial minima / maxima (fminf / fmaxf: any order
+// gives the same value), then every thread takes groups of 4 consecutive coordinates: one 128-bit load and store and ONE
+// Philox block per group (coordinate i uses component i & 3 of block i >> 2 of the client's stream).
+constexpr int kScalarGroups = 4;      // groups of 4 coordinates per thread
+__global__ void __launch_bounds__(256)
+scalar_kernel(const float *__restrict__ X, int64_t n, int64_t d, int64_t ld, int nb, const float *__restrict__ pmin,
+              const float *__restrict__ pmax, float nlevels, uint64_t seed, uint64_t client0, const float *__restrict__ u_inject,
+              float *__restrict__ out, int64_t ld_out, int vec_ok) {
+    __shared__ float s_mn[kWarps], s_mx[kWarps];
+    const int64_t c = blockIdx.y;
+    float mn = INFINITY, mx = -INFINITY;
+    for (int b = threadIdx.x; b < nb; b += 256) { mn = fminf(mn, pmin[c * nb + b]); mx = fmaxf(mx, pmax[c * nb + b]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    mn = s_mn[0]; mx = s_mx[0];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
+    const float denom = __fsub_rn(mx, mn);
+    const bool copy = (denom == 0.0f || nlevels < 1.0f);                                            // AS:763-765, AS:772-773
+    const uint64_t cl = client0 + (uint64_t)c;
+    const uint64_t key = seed ^ (cl * 0x9E3779B97F4A7C15ull);
+    const float *xr = X + c * ld;
+    float *orow = out + c * ld_out;
+    const int64_t g0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * kScalarGroups;       // first group of this thread
+#pragma unroll
+    for (int k = 0; k < kScalarGroups; ++k) {
+        const int64_t g = g0 + k, i0 = g * 4;
+        if (i0 >= d) break;
+        float x[4], u[4];
+        const bool full = vec_ok && i0 + 4 <= d;
+        if (full) { const float4 v = *reinterpret_cast<const float4 *>(xr + i0); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+        else { for (int j = 0; j < 4; ++j) x[j] = (i0 + j < d) ? xr[i0 + j] : 0.0f; }
+        if (!copy) {
+            if (u_inject) { for (int j = 0; j < 4; ++j) u[j] = (i0 + j < d) ? u_inject[c * d + i0 + j] : 0.0f; }
+            else {
+                const Philox4 p = philox4x32_10(key, (uint32_t)g, (uint32_t)((uint64_t)g >> 32), (uint32_t)cl, kStreamScalar);
+                u[0] = u24_to_unit(p.x); u[1] = u24_to_unit(p.y); u[2] = u24_to_unit(p.z); u[3] = u24_to_unit(p.w);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = scalar_one(x[j], mn, mx, denom, nlevels, u[j]);
+        }
+        if (full) *reinterpret_cast<float4 *>(orow + i0) = make_float4(x[0], x[1], x[2], x[3]);
+        else { for (int j = 0; j < 4; ++j) if (i0 + j < d) orow[i0 + j] = x[j]; }
+    }
 }
 
 static int pow2_ceil(int64_t v) { int64_t p = 1; while (p < v) p <<= 1; return (int)p; }
 static int slices(int64_t d) { int64_t nb = (d + 16383) / 16384; return (int)(nb < 1 ? 1 : (nb > 64 ? 64 : nb)); }
+static int slices_minmax(int64_t d) { int64_t nb = (d + 16383) / 16384; return (int)(nb < 1 ? 1 : (nb > 256 ? 256 : nb)); }   // min / max: any grouping gives the same value
 
 }  // namespace dme
 
@@ -312,13 +354,16 @@ extern "C" int dme_scalar_quantize(const float *X, int64_t n, int64_t d, int64_t
                                    const float *u_inject, float *out, int64_t ld_out, dme_stream_t stream) {
     DME_REQUIRE(X && out && n >= 1 && n <= 65535 && d >= 1 && ld >= d && ld_out >= d, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    const int nb = slices(d);
+    const int nb = slices_minmax(d);
     float *pm = nullptr;
     DME_CUDA(cudaMallocAsync(&pm, sizeof(float) * (size_t)(2 * n * nb), st));
     dim3 grid((unsigned)nb, (unsigned)n);
     row_minmax_kernel<<<grid, 256, 0, st>>>(X, d, ld, nb, pm, pm + n * nb);
     DME_LAUNCH_CHECK("row_minmax_kernel");
-    scalar_kernel<<<(unsigned)((n * d + 255) / 256), 256, 0, st>>>(X, n, d, ld, nb, pm, pm + n * nb, nlevels, seed, client0, u_inject, out, ld_out);
+    const int vec_ok = (ld % 4 == 0) && (ld_out % 4 == 0) && (((uintptr_t)X | (uintptr_t)out) & 15u) == 0;
+    const int64_t per_cta = 256 * kScalarGroups * 4;
+    dim3 grid2((unsigned)((d + per_cta - 1) / per_cta), (unsigned)n);
+    scalar_kernel<<<grid2, 256, 0, st>>>(X, n, d, ld, nb, pm, pm + n * nb, nlevels, seed, client0, u_inject, out, ld_out, vec_ok);
     DME_LAUNCH_CHECK("scalar_kernel");
     DME_CUDA(cudaFreeAsync(pm, st));
     return DME_OK;

@@ -26,11 +26,20 @@ drive_kernel(const float *__restrict__ X, int64_t d, int64_t ld, float *__restri
     int np2 = 1, lg = 0;
     while (np2 < len) { np2 <<= 1; ++lg; }
     const float *row = X + c * ld;
+    // the chunk's 2048 sign bits = 16 Philox blocks of 128 bits (philox_sign's mapping: coordinate i is bit i & 31 of word
+    // (i >> 5) & 3 of block i >> 7): computed once per chunk by 16 threads instead of once per coordinate
+    __shared__ uint32_t s_bits[64];
+    if (!dsign && threadIdx.x < 16) {
+        const uint64_t blk = (uint64_t)(s0 >> 7) + threadIdx.x;
+        const Philox4 p = philox4x32_10(seed, (uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)c, kStreamDrive);
+        s_bits[4 * threadIdx.x] = p.x; s_bits[4 * threadIdx.x + 1] = p.y; s_bits[4 * threadIdx.x + 2] = p.z; s_bits[4 * threadIdx.x + 3] = p.w;
+    }
+    __syncthreads();
     double n2 = 0.0;
     for (int j = threadIdx.x; j < np2; j += 256) {
         const float xv = j < len ? row[s0 + j] : 0.0f;
         const float Dv = dsign ? dsign[c * dsign_row + s0 + j]
-                               : philox_sign(seed, (uint64_t)(s0 + j), kStreamDrive, (uint32_t)c);       // AS:735
+                               : (((s_bits[j >> 5] >> (j & 31)) & 1u) ? 1.0f : -1.0f);                   // AS:735
         Dg[j] = Dv;
         buf[j] = __fmul_rn(Dv, xv);                                                                    // AS:737
         n2 += (double)xv * (double)xv;

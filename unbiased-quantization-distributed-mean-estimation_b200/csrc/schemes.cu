@@ -127,16 +127,33 @@ __global__ void eden_scale_kernel(const double *__restrict__ partial, int nb, in
     for (int b = 0; b < nb; ++b) s += partial[c * nb + b];
     scale[c] = __fdiv_rn(__fmul_rn(nrm[c], nrm[c]), (float)s);                     // AS:348
 }
+// four bins -> four centroids per thread (total is a multiple of 4: rows are padded to a power of two >= 4 or handled by the tail)
 __global__ void eden_lookup_kernel(const uint8_t *__restrict__ bins, int64_t total, EdenTab tab, float *__restrict__ work) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < total) work[i] = tab.cent[bins[i] & 3];                                // AS:400
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, i = 4 * q;
+    if (i + 4 <= total && ((reinterpret_cast<uintptr_t>(bins) & 3u) == 0) && ((reinterpret_cast<uintptr_t>(work) & 15u) == 0)) {
+        const uchar4 b = *reinterpret_cast<const uchar4 *>(bins + i);
+        *reinterpret_cast<float4 *>(work + i) = make_float4(tab.cent[b.x & 3], tab.cent[b.y & 3], tab.cent[b.z & 3], tab.cent[b.w & 3]);   // AS:400
+    } else {
+        for (int64_t k = i; k < total && k < i + 4; ++k) work[k] = tab.cent[bins[k] & 3];
+    }
 }
+// grid (blocks along the row, client): out[c][j] = scale[c] * work[c][j] for j < d, four coordinates per thread
 __global__ void scale_rows_kernel(const float *__restrict__ work, int64_t dpad, const float *__restrict__ scale, int64_t n, int64_t d,
                                   float *__restrict__ out, int64_t ld_out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * d) return;
-    const int64_t c = i / d, j = i - c * d;
-    out[c * ld_out + j] = scale ? __fmul_rn(scale[c], work[c * dpad + j]) : work[c * dpad + j];   // AS:426 / AS:535
+    const int64_t c = blockIdx.y;
+    const int64_t j = 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (j >= d) return;
+    const float sc = scale ? scale[c] : 1.0f;
+    const float *w = work + c * dpad;
+    float *o = out + c * ld_out;
+    const bool vec = j + 4 <= d && ((dpad & 3) == 0) && ((ld_out & 3) == 0) && (((reinterpret_cast<uintptr_t>(work) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0);
+    if (vec) {
+        float4 v = *reinterpret_cast<const float4 *>(w + j);
+        if (scale) { v.x = __fmul_rn(sc, v.x); v.y = __fmul_rn(sc, v.y); v.z = __fmul_rn(sc, v.z); v.w = __fmul_rn(sc, v.w); }   // AS:426 / AS:535
+        *reinterpret_cast<float4 *>(o + j) = v;
+    } else {
+        for (int64_t k = j; k < d && k < j + 4; ++k) o[k] = scale ? __fmul_rn(sc, w[k]) : w[k];
+    }
 }
 
 static EdenTab eden_tab(int nbits) {
@@ -333,11 +350,11 @@ extern "C" int dme_eden_decode(const uint8_t *bins, const float *scale, int64_t 
     DME_REQUIRE(nbits == 1 || nbits == 2, "EDEN centroids exist for 1 and 2 bits only (AS:301-320)");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t total = n * dpad;
-    eden_lookup_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(bins, total, eden_tab(nbits), work);
+    eden_lookup_kernel<<<(unsigned)((total + 1023) / 1024), 256, 0, st>>>(bins, total, eden_tab(nbits), work);
     DME_LAUNCH_CHECK("eden_lookup_kernel");
     int rc = fwht_rows(work, dpad, dpad, work, dpad, dpad, n, diag_inject, seed, seed_stride, 0, 1, st);   // AS:425
     if (rc) return rc;
-    scale_rows_kernel<<<(unsigned)((n * d + 255) / 256), 256, 0, st>>>(work, dpad, scale, n, d, out, ld_out);
+    scale_rows_kernel<<<dim3((unsigned)((d + 1023) / 1024), (unsigned)n), 256, 0, st>>>(work, dpad, scale, n, d, out, ld_out);
     DME_LAUNCH_CHECK("scale_rows_kernel");
     return DME_OK;
 }
@@ -354,7 +371,7 @@ extern "C" int dme_quicfl_decode(const int32_t *Xq, const int32_t *h, int64_t n,
     DME_LAUNCH_CHECK("quicfl_gather_kernel");
     int rc = fwht_rows(work, dpad, dpad, work, dpad, dpad, n, diag_inject, rotation_seed, 0, 0, 1, st);  // AS:534
     if (rc) return rc;
-    scale_rows_kernel<<<(unsigned)((n * d + 255) / 256), 256, 0, st>>>(work, dpad, nullptr, n, d, out, ld_out);
+    scale_rows_kernel<<<dim3((unsigned)((d + 1023) / 1024), (unsigned)n), 256, 0, st>>>(work, dpad, nullptr, n, d, out, ld_out);
     DME_LAUNCH_CHECK("scale_rows_kernel");
     return DME_OK;
 }

@@ -47,6 +47,23 @@ __device__ __forceinline__ float diag_at(const FwhtIo &io, int64_t col, int64_t 
     return philox_sign(io.seed + (uint64_t)row * io.seed_stride, (uint64_t)col, kStreamDiag);
 }
 
+// Signs of 16 consecutive columns col .. col+15 (col a multiple of 16) of one row as a bit mask (bit j set: +1).  With the
+// Philox diagonal they are 16 bits of ONE 32-bit word of one block (philox_sign's mapping: column i = bit i & 31 of word
+// (i >> 5) & 3 of block i >> 7), so one Philox evaluation serves the thread's whole chunk.
+__device__ __forceinline__ uint32_t diag_bits16(const FwhtIo &io, int64_t col, int64_t row) {
+    if (io.diag) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) m |= (io.diag[col + j] > 0.0f ? 1u : 0u) << j;
+        return m;
+    }
+    const uint64_t blk = (uint64_t)col >> 7;
+    const Philox4 p = philox4x32_10(io.seed + (uint64_t)row * io.seed_stride, (uint32_t)blk, (uint32_t)(blk >> 32), 0u, kStreamDiag);
+    const int wi = (int)((col >> 5) & 3);
+    const uint32_t word = wi == 0 ? p.x : wi == 1 ? p.y : wi == 2 ? p.z : p.w;
+    return (word >> (col & 31)) & 0xffffu;
+}
+
 constexpr int kPad = 4096 + 4096 / 32;   // +1 float every 32: transposes are conflict-free
 __device__ __forceinline__ int padded(int e) { return e + (e >> 5); }
 
@@ -74,8 +91,9 @@ __global__ void __launch_bounds__(256) fwht_contig_kernel(FwhtIo io, int64_t n, 
             }
         }
         if (io.pre_diag && live) {
+            const uint32_t sb = diag_bits16(io, col, row);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], diag_at(io, col + j, row));
+            for (int j = 0; j < 16; ++j) v[j] = __fmul_rn(v[j], ((sb >> j) & 1u) ? 1.0f : -1.0f);
         }
     } else {
 #pragma unroll
@@ -120,6 +138,30 @@ __global__ void __launch_bounds__(256) fwht_contig_kernel(FwhtIo io, int64_t n, 
         for (int j = 0; j < 16; ++j) v[j] = sm[padded(16 * t + j)];
     }
     // ---- store (+ scaling, + diagonal)
+    if (io.d >= 16) {
+        // the thread's 16 elements are consecutive columns of one row: one row / column computation, one sign word, and
+        // 128-bit stores when the destination allows
+        if (g0 >= total) return;
+        const int64_t row = g0 / io.d, col = g0 - row * io.d;
+        uint32_t sb = 0xffffu;
+        if (io.finalize && io.post_diag) sb = diag_bits16(io, col, row);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (io.finalize) {
+                v[j] = __fdiv_rn(v[j], io.sq);                                                          // AS:113
+                if (io.post_diag) v[j] = __fmul_rn(v[j], ((sb >> j) & 1u) ? 1.0f : -1.0f);                // AS:154
+            }
+        }
+        float *drow = io.dst + row * io.dst_ld + col;
+        if (((io.dst_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(io.dst) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<float4 *>(drow + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) drow[j] = v[j];
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const int64_t g = g0 + j;

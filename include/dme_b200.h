@@ -67,6 +67,9 @@ DME_API int64_t dme_launch_count(void);
  * keep it off inside timed regions).  dme_profile_read returns the number of intervals written: for
  * dme_quantize_mean they are {L1 reduce, scan/quantize/pack, decode+mean} in milliseconds. */
 DME_API int dme_profile_enable(int on);
+/* Test hook: which implementation runs the unbiased mode.  0 (default) = the fused fixed-point kernel, with the literal kernel for
+ * the rows outside its proven operand range; 1 = the literal kernel (AS:625-637 as written) for every row. */
+DME_API int dme_set_unbiased_path(int path);
 DME_API int dme_profile_read(float *ms, int cap);
 
 /* X_c, the single uniform of client c (AS:634): Philox4x32-10, key = seed, counter = (client, 0, 0, 0x584D44),

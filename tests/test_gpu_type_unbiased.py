@@ -19,12 +19,14 @@ def dme():
     return dme_b200
 
 
-@pytest.fixture(autouse=True, params=["tiles", "stream"])
-def quantize_path(request, monkeypatch):
-    """Every test of this file runs on both quantize paths (the library picks by row length otherwise):
-    l1_kernel + quantize_tiles_kernel, and the fused persistent quantize_stream_kernel."""
-    monkeypatch.setenv("DME_PATH", request.param)
+@pytest.fixture(autouse=True, params=["fx", "literal"])
+def quantize_path(request, dme):
+    """Every test of this file runs on both implementations of the unbiased quantizer: the fused fixed-point kernel
+    (quantize_fx.cu, the product path) and the literal kernel (quantize_literal.cu: AS:625-637 as written, which also serves
+    the rows outside the fast kernel's proven operand range)."""
+    dme.set_unbiased_path(request.param)
     yield request.param
+    dme.set_unbiased_path("fx")
 
 
 def _R(v):

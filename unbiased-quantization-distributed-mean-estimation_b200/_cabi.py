@@ -16,6 +16,7 @@ SIGNATURES = {
     "dme_launch_count": (i64, []),
     "dme_profile_enable": (ci, [ci]),
     "dme_profile_read": (ci, [vp, ci]),
+    "dme_set_unbiased_path": (ci, [ci]),
     "dme_uniform_x": (cf, [u64, u64]),
     "dme_workspace_bytes": (i64, [i64, i64]),
     "dme_codes_bytes": (i64, [i64, i64, i64, ci]),

@@ -118,6 +118,15 @@ class Workspace:
         _check(_cabi.lib().dme_status(C.c_void_p(self.buf.data_ptr() + off), C.c_void_p(_stream())))
 
 
+UNBIASED_PATHS = {"fx": 0, "literal": 1, "tiles": 2, "stream": 3}
+
+
+def set_unbiased_path(path) -> None:
+    """Test hook (dme_set_unbiased_path): "fx" = the fused fixed-point kernel (default), "literal" = AS:625-637 as
+    written, for every row (slow; an independent implementation the GPU tests check against the same oracle)."""
+    _check(_cabi.lib().dme_set_unbiased_path(UNBIASED_PATHS.get(path, path)))
+
+
 def client_uniforms(seed: int, client0: int, n: int) -> np.ndarray:
     """X_c for clients client0 .. client0+n-1: the same Philox draw the kernels make (AS:634)."""
     L = _cabi.lib()

@@ -1527,7 +1527,7 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
     a.has_tail = (d & 31) ? 1 : 0;
     a.dbg = 0;
     if (const char *e = getenv("DME_DBG")) a.dbg = atoi(e);
-    if (use_tiles_path(d)) {
+    if (L.T >= 0 && !getenv("DME_OLD_STREAM")) {
         // the row constants are there already (l1_kernel, launched by the caller on the same stream)
         const int occ_t = g_occ_tiles[packed ? 1 : 0];
         if (occ_t < 1) { set_error("quantize_tiles_kernel does not fit on an SM"); return DME_ECUDA; }

@@ -328,7 +328,7 @@ static int check_rows(const void *X, int64_t n, int64_t d, int64_t ld) {
     return DME_OK;
 }
 
-int ws_prepare(void *ws, int64_t ws_bytes, int64_t n, int64_t d, cudaStream_t st, WsLayout *out, bool need_desc, bool need_sel) {
+int ws_prepare(void *ws, int64_t ws_bytes, int64_t n, int64_t d, cudaStream_t st, WsLayout *out, bool need_desc, bool need_sel, bool need_partial = true) {
     const WsLayout L = ws_layout(n, d);
     DME_REQUIRE(ws != nullptr && ((uintptr_t)ws & 255u) == 0, "workspace must be non-null and 256-byte aligned");
     if (ws_bytes < L.total) {
@@ -339,7 +339,7 @@ int ws_prepare(void *ws, int64_t ws_bytes, int64_t n, int64_t d, cudaStream_t st
     DME_CUDA(cudaMemsetAsync(base, 0, (size_t)L.zero_bytes, st));
     if (need_desc) {
         DME_CUDA(cudaMemsetAsync(base + L.off_desc, 0, (size_t)L.desc_bytes, st));
-        DME_CUDA(cudaMemsetAsync(base + L.off_partial, 0, 16 * (size_t)(n * L.T), st));
+        if (need_partial) DME_CUDA(cudaMemsetAsync(base + L.off_partial, 0, 16 * (size_t)(n * L.T), st));
     }
     if (need_sel) DME_CUDA(cudaMemsetAsync(base + L.off_sel, 0, sizeof(RowSelect) * (size_t)n, st));
     *out = L;
@@ -364,6 +364,17 @@ int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, c
                   int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
                   uint32_t *codes, int64_t codes_bytes, uint64_t *dir, float *l1_out, cudaStream_t st, bool packed);   // stream.cu
 bool use_tiles_path(int64_t d);   // stream.cu
+int launch_quantize_fx(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
+                       const float *x_inject, const float *l1_inject, uint64_t seed, uint64_t client0,
+                       int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
+                       uint32_t *codes, int64_t codes_bytes, uint64_t *dir, float *l1_out, cudaStream_t st, bool packed);   // quantize_fx.cu
+int launch_literal_rows(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
+                        const float *x_inject, const float *l1_inject, uint64_t seed, uint64_t client0,
+                        int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
+                        uint32_t *codes, int64_t codes_bytes, uint64_t *dir, float *l1_out, cudaStream_t st, bool packed, bool all_rows);   // quantize_literal.cu
+// Which implementation quantises the unbiased mode: 0 = quantize_fx_kernel (+ literal_rows_kernel for the rows it leaves out),
+// 1 = literal_rows_kernel for every row (tests), 2 / 3 = the round-1 fp64 kernels (development).  dme_set_unbiased_path.
+static int g_unbiased_path = 0;
 
 }  // namespace dme
 
@@ -398,11 +409,22 @@ static int quantize_common(const float *X, int64_t n, int64_t d, int64_t ld, int
         DME_REQUIRE(ld_out >= d, "ld_out=%lld < d", (long long)ld_out);
     }
     WsLayout L;
-    rc = ws_prepare(ws, ws_bytes, n, d, st, &L, true, mode == DME_MODE_BIASED);
+    const int path = g_unbiased_path;
+    const bool old_path = mode == DME_MODE_BIASED || path >= 2;
+    rc = ws_prepare(ws, ws_bytes, n, d, st, &L, path != 1 || mode == DME_MODE_BIASED, mode == DME_MODE_BIASED, old_path);
     if (rc) return rc;
     prof_reset();
     prof_mark(st);
-    if (mode == DME_MODE_BIASED || use_tiles_path(d)) {
+    if (!old_path) {
+        if (path == 0) rc = launch_quantize_fx(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, k_out, sgn_out, deq_out, ld_out, codes,
+                                               codes_bytes, dir, l1_out, st, packed);
+        else rc = launch_literal_rows(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, k_out, sgn_out, deq_out, ld_out, codes,
+                                      codes_bytes, dir, l1_out, st, packed, true);
+        if (rc) return rc;
+        prof_mark(st);
+        return DME_OK;
+    }
+    if (mode == DME_MODE_BIASED || path == 2) {
         rc = launch_l1(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, l1_out, st);
         if (rc) return rc;
         if (mode != DME_MODE_BIASED) prof_mark(st);
@@ -451,6 +473,12 @@ extern "C" int dme_decode_mean_tiles(const void *codes, const uint64_t *dir, con
 extern "C" int dme_decode_mean(const void *codes, const uint64_t *dir, const float *l1, int64_t n, int64_t d, int64_t m, int mode,
                                int64_t n_total, float *mean, int accumulate, dme_stream_t stream) {
     return dme_decode_mean_tiles(codes, dir, l1, n, d, m, mode, n_total, mean, accumulate, 0, d >= 1 ? (d + kTile - 1) / kTile : 0, stream);
+}
+
+extern "C" int dme_set_unbiased_path(int path) {
+    DME_REQUIRE(path >= 0 && path <= 3, "path=%d unknown", path);
+    g_unbiased_path = path;
+    return DME_OK;
 }
 
 extern "C" int dme_profile_enable(int on) { g_prof.on = on != 0; prof_reset(); return DME_OK; }

@@ -14,12 +14,14 @@ struct __align__(64) RowConst {
     float rcpD;  // RN(1 / D) for the Markstein division  x/D = fma(fma(-q0, D, x), rcp, q0), q0 = x*rcp
     uint32_t flags;      // kRowExact: use IEEE div / floorf (operands outside the proven range of the fast chain)
                          // kRowGuardFloor: mp may reach 2^23 -> per-thread check before the magic floor
-    int32_t qshift;      // tile aggregates are exchanged as int64 fixed point with 2^-qshift resolution
-    uint32_t pad0;
+    int32_t qshift;      // (fp64 kernels) tile aggregates are exchanged as int64 fixed point with 2^-qshift resolution
+    uint32_t Xi;         // X * 2^32 (quantize_fx.cu: the uniform on the fixed-point grid)
     double q_up, q_dn;   // 2^qshift, 2^-qshift
-    double pad1[2];
+    float mfs;           // float(m) * 2^32 (quantize_fx.cu: m |x| / D comes out scaled for the 64-bit conversion)
+    float pad2[3];
 };
 constexpr uint32_t kRowExact = 1u, kRowGuardFloor = 2u;
+constexpr uint32_t kRowExotic = 4u;    // outside the proven range of quantize_fx_kernel: left to literal_rows_kernel
 
 // Decoupled look-back record of one (client, tile).  state: 0 = nothing, 1 = aggregate valid,
 // 2 = aggregate + inclusive valid.  a_state: 1 = a_last valid.
@@ -55,6 +57,7 @@ struct WsLayout {
     int64_t desc_bytes;
     int64_t off_sel;      // RowSelect sel[n] (biased mode)
     int64_t off_tab;      // BinadeEntry tab[n][kBinades] (unbiased stream kernel: closed-form floor(c - X) per binade)
+    int64_t off_exotic;   // int32 exotic_rows[n]: rows left to literal_rows_kernel (their count is WsHeader::pad[1])
     int64_t zero_bytes;   // prefix that must be zeroed before each call (header + a_done)
     int64_t total;
 };
@@ -99,6 +102,7 @@ inline WsLayout ws_layout(int64_t n, int64_t d) {
     L.off_desc = o; o = align_up(o + L.desc_bytes, 256);
     L.off_sel = o; o = align_up(o + (int64_t)sizeof(RowSelect) * n, 256);
     L.off_tab = o; o = align_up(o + (int64_t)sizeof(BinadeEntry) * kBinades * n, 256);
+    L.off_exotic = o; o = align_up(o + 4 * n, 256);
     L.total = o;
     return L;
 }
@@ -124,10 +128,10 @@ __device__ inline void make_row_const(const RowConstIn &a, int64_t c, double l1s
     int lg = 0;
     while (((int64_t)1 << lg) < a.d) ++lg;
     rc.qshift = min(50, 62 - lg);
-    rc.pad0 = 0;
+    rc.Xi = 0;
     rc.q_up = __longlong_as_double((long long)(1023 + rc.qshift) << 52);
     rc.q_dn = __longlong_as_double((long long)(1023 - rc.qshift) << 52);
-    rc.pad1[0] = rc.pad1[1] = 0.0;
+    rc.mfs = 0.0f; rc.pad2[0] = rc.pad2[1] = rc.pad2[2] = 0.0f;
     a.consts[c] = rc;
     BinadeEntry *tab = a.tabs + c * kBinades;
     const double Xd = (double)rc.X;

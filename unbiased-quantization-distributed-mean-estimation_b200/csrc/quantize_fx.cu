@@ -2,17 +2,22 @@
 // the input ONCE from HBM: per-client L1 norm (pass A), scale to m, floor + systematic-sampling allocation of the fractional
 // mass (pass B), sign/magnitude packing (or the dequantised output of the drop-in API).
 //
-// Schedule.  Tiles (4096 coordinates = 16 KB) of all client rows are numbered row-major; CTA b of G co-resident CTAs
-// (cooperative launch) owns the positions b, b + G, b + 2G, ...  At position p it runs pass A of tile p (first touch, from HBM)
-// and pass B of tile p - Lg.  Lg = T + lead is a multiple of G, so THE SAME CTA runs both passes of a tile: on B200 the two
-// halves of L2 each cache what their own SMs touch, and a tile re-read by the SM that streamed it is an L2 hit where a re-read
-// by an arbitrary SM is not (tools/ubench3.cu: 8 GiB of 64 MiB rows in 1.46 ms with this mapping, 1.69 ms with tickets,
-// 2.47 ms for two passes over HBM).  Every wait is on a smaller position and every CTA is resident: no deadlock.
+// Schedule.  Tiles (4096 coordinates = 16 KB) of all client rows are numbered row-major.  One CTA per SM (cooperative launch);
+// SM b owns the positions b, b + S, b + 2S, ... (S = number of SMs) and its four 128-thread GROUPS draw them in order from a
+// ticket in shared memory.  At position p a group runs pass A of tile p (first touch, from HBM) and pass B of tile p - Lg.
+// Lg = T + lead is a multiple of S, so THE SAME SM runs both passes of a tile: on B200 the two halves of L2 each cache what
+// their own SMs touch, and a tile re-read by the SM that streamed it is an L2 hit where a re-read by an arbitrary SM is not
+// (tools/ubench3.cu: 8 GiB of 64 MiB rows in 1.46 ms with this mapping, 1.69 ms with global tickets, 2.47 ms for two passes
+// over HBM).  Inside an SM the assignment is dynamic: a group that waits for a look-back does not hold up the SM's next
+// position -- with a static assignment per CTA every wait delayed the waiter's next aggregate, which delayed its successors
+// (measured: 44 % of the tiles polled, 8.7 ms; profiles/r02_fx_history.md).  Every wait is on a smaller position and all CTAs
+// are resident: no deadlock.
 //
 // Pass A.  Coalesced 128-bit loads, |x| widened to fp64 by ONE integer multiply-add (the fp32 bit pattern times 2^29 is
-// the fp64 pattern up to the exponent bias; the conversion unit is kept for pass B), thread-private fp64 sums carried over
-// the CTA's tiles of a row, one partial per (row, CTA); the CTA that publishes last adds the partials in slot order and
-// writes the row constants.  Fixed association: run-to-run deterministic.
+// the fp64 pattern up to the exponent bias; the conversion unit is kept for pass B), one fp64 sum per tile (fixed association).
+// Tile sums are added into a per-row superaccumulator of twelve 64-bit bins (32 bits of payload each) with integer atomics:
+// integer addition is associative, so the row's norm does not depend on which group streamed which tile or when.  Every group
+// derives a row's constants from the bins when it first needs them (same arithmetic, same bits everywhere).
 //
 // Pass B, in integers.  y = m|x|/D (AS:625-629: Markstein division x*rcp corrected by two FMAs = the IEEE quotient, in packed
 // f32x2) is converted ONCE to 64-bit fixed point with 2^-32 resolution, F = RN(y 2^32): the high word is floor(y) (AS:630),
@@ -87,7 +92,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-constexpr int kBarFree = 1;
 
 // one 16 KB box {32 floats, 128 rows, 1 client} at (0, row0, client) of the 3-D tensor map
 __device__ __forceinline__ void tma_tile_g2s(uint32_t dst, const CUtensorMap *map, int row0, int client, uint64_t *bar, uint64_t policy) {
@@ -126,25 +130,55 @@ __device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %
 __device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ u64 f2u64_abs(float v) { u64 r; asm("cvt.rni.u64.f32 %0, %1;" : "=l"(r) : "f"(fabsf(v))); return r; }
 
+
+#ifndef FX_GROUPS
+#define FX_GROUPS 4
+#define FX_AWARPS 4
+#define FX_CTAS 1
+#endif
+constexpr int kFxGroups = FX_GROUPS;      // independent 128-thread groups per CTA
+constexpr int kFxAWarps = FX_AWARPS;        // pass-A warps per CTA (they only stream and add)
+constexpr int kFxCtas = FX_CTAS;            // CTAs per SM
+constexpr int kFxBlock = kFxGroups * kFxThreads + kFxAWarps * 32;
+constexpr int kBins = 12;                 // 64-bit bins of a row's |x| superaccumulator (bin q weighs 2^(32 q - 224))
+constexpr int kBinBias = 224;
+
+#ifdef DME_TIMERS
+__device__ unsigned long long g_fx_trace[1 << 16];      // development: {globaltimer, code << 56 | tile position}
+__device__ unsigned int g_fx_trace_n;
+__device__ __forceinline__ void fx_trace(int code, long long pos) {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned int i = atomicAdd(&g_fx_trace_n, 1u);
+    if (i < (1u << 15)) { g_fx_trace[2 * i] = t; g_fx_trace[2 * i + 1] = ((unsigned long long)code << 56) | (unsigned long long)pos; }
+}
+#define FXTR(code, c, t) do { if (gtid == 0 && (c) == 40) fx_trace(code, (long long)(t)); } while (0)
+#define FXW(code) do { if (lane == 0 && g == 0 && blockIdx.x == 5 && it >= 200 && it < 232) fx_trace(code, (long long)it * 8 + warp); } while (0)
+#define FXT(k) do { if (gtid == 0) { const long long _t = clock64(); tacc[k] += _t - tlast; tlast = _t; } } while (0)
+#else
+#define FXT(k) do { } while (0)
+#define FXTR(code, c, t) do { } while (0)
+#define FXW(code) do { } while (0)
+#endif
 struct FxArgs {
     const float *X; int64_t d, ld, T, n, m;
     int64_t rows32;                        // full 128-byte rows per client vector (the part the tensor map covers)
     RowConst *consts; Rec *desc; Rec2 *blocks; Rec2 *supers; int64_t TB, TS; WsHeader *hdr;
-    double *rowpart; uint32_t *pub_count; uint32_t *row_ready; int32_t *exotic_rows;
+    u64 *bins; uint32_t *pub_count; uint32_t *row_ready; int32_t *exotic_rows;
     const float *x_inject; const float *l1_inject; uint64_t seed, client0; float *l1_out;
-    int64_t nT, Lg;                        // tiles in all rows; pass B runs Lg positions behind pass A (a multiple of G)
-    int G, slots;                          // co-resident CTAs; partial slots per row = min(G, T)
-    int step_c, step_t;                    // G = step_c * T + step_t: per-iteration advance of (client, tile)
+    int64_t nT, Lg;                        // tiles in all rows; pass B runs Lg positions behind pass A (a multiple of S)
+    int S;                                 // CTAs = SMs: SM b owns positions b, b + S, ...
     int tiles_tma, has_tail;
     int32_t *k_out; uint8_t *sgn_out; float *deq_out; int64_t ld_out;     // array outputs
     PackTarget pack;                                                    // packed output
+    int hack;
     uint32_t one;                          // = 1, as a register operand: keeps the 64-bit accumulate one IMAD.WIDE
 };
 
+// one drawn position: pass-B tile (c, t) and pass-A tile (ca, ta)
 struct __align__(16) FxItem { int c, t; uint32_t flags; uint32_t pad; };
-constexpr uint32_t kItValid = 1u, kItTma = 4u, kItTail = 8u;
+constexpr uint32_t kItValid = 1u, kItTma = 4u, kItTail = 8u, kItEnd = 16u;
 
-struct FxScratch {
+struct FxScratch {               // per group
     Rec win[2][96];              // look-back window of the C tile (tile / block / super-block records), by iteration parity
     u64 wtot[2][kFxWarps];       // warp totals of the B tile, by iteration parity
     uint32_t fmw[2][kFxWarps];   // per-warp largest floor
@@ -157,9 +191,8 @@ struct FxScratch {
     long long pfb;               // look-back result of the fallback path
     RowConst rc[2];
     u64 tab[2][kBinades];        // U_e of the closed form, per binade
-    double redA[kFxWarps];       // pass A: warp sums of a row partial
-    unsigned int flagA;          // pass A: this CTA published the last partial of the row
 };
+constexpr size_t kGroupBytes = (size_t)3 * kTile * sizeof(float) + ((sizeof(FxScratch) + 1023) / 1024) * 1024;
 
 // swizzled shared-memory offset of the 16-byte piece q (0..3) of 16-coordinate chunk `ch` inside a 16 KB tile
 // (SWIZZLE_128B: piece index within the 128-byte row is XORed with row & 7); q enters as an XOR of (q << 4)
@@ -168,12 +201,13 @@ __device__ __forceinline__ uint32_t blocked_off_of(uint32_t ch) {
     return row * 128u + ((((ch & 1u) << 2) ^ (row & 7u)) << 4);
 }
 
-// ------------------------------------------------------------------ row constants (cold: once per client row)
+// ------------------------------------------------------------------ row constants (cold: once per group and client row)
 // U_e of the closed form in 2^-32 units: a = ceil(X / g - 1/2), g = 2^(e-23); U = g (a - 1/2) + [a odd]
 __device__ __forceinline__ u64 binade_offset(uint32_t Xi, int e) {
     const u64 a = ((u64)Xi + (1ull << (e + 8)) - 1ull) >> (e + 9);
     return (a << (e + 9)) - (1ull << (e + 8)) + (a & 1ull);
 }
+// The constants of a row, written once by the pass-A lane that counted the row's last tile.
 __device__ void make_row_const_fx(const FxArgs &a, int64_t c, double l1sum) {
     RowConst rc;
     bool exotic = false;
@@ -197,11 +231,7 @@ __device__ void make_row_const_fx(const FxArgs &a, int64_t c, double l1sum) {
     rc.flags = exotic ? kRowExotic : 0u;
     rc.Xi = exotic ? 0u : (uint32_t)xs;
     rc.mfs = __fmul_rn(rc.mf, 4294967296.0f);
-    int lg = 0;
-    while (((int64_t)1 << lg) < a.d) ++lg;
-    rc.qshift = min(50, 62 - lg);
-    rc.q_up = __longlong_as_double((long long)(1023 + rc.qshift) << 52);
-    rc.q_dn = __longlong_as_double((long long)(1023 - rc.qshift) << 52);
+    rc.qshift = 0; rc.q_up = rc.q_dn = 0.0;
     rc.pad2[0] = rc.pad2[1] = rc.pad2[2] = 0.0f;
     a.consts[c] = rc;
     if (exotic) a.exotic_rows[atomicAdd(&a.hdr->pad[1], 1u)] = (int32_t)c;
@@ -218,36 +248,57 @@ __device__ __forceinline__ double abs_to_double(uint32_t bits) {
 __device__ __forceinline__ void acc_abs4(const uint4 v, double (&s)[4]) {
     s[0] += abs_to_double(v.x); s[1] += abs_to_double(v.y); s[2] += abs_to_double(v.z); s[3] += abs_to_double(v.w);
 }
-// Publish the CTA's partial of row c (slot = the first tile of its run in the row); the CTA that publishes last reduces
-// the partials in slot order and writes the row constants.  Whole CTA; called after a __syncthreads that made redA visible.
-__device__ __noinline__ void publish_row(const FxArgs &a, FxScratch &sc, int c, int slot) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cnt = a.slots;
-    if (tid == 0) {
-        double tot = sc.redA[0];
-#pragma unroll
-        for (int w = 1; w < kFxWarps; ++w) tot += sc.redA[w];
-        __stcg(a.rowpart + (int64_t)c * cnt + slot, tot);
-        __threadfence();
-        sc.flagA = (atomicAdd(&a.pub_count[c], 1u) == (unsigned int)(cnt - 1)) ? 1u : 0u;
+// Add a tile's fp64 sum (>= 0, finite) to the row's superaccumulator.  One thread; fire and forget.
+// v = mant * 2^ex: mant << ((ex + bias) % 32) is spread over three 32-bit limbs that go to consecutive bins.
+__device__ __forceinline__ void publish_tile_sum(const FxArgs &a, int c, double v) {
+    u64 *bins = a.bins + (int64_t)c * kBins;
+    const u64 bits = (u64)__double_as_longlong(v);
+    const int be = (int)(bits >> 52) & 0x7ff;
+    if (be != 0) {                                       // tile sums are 0 or >= 2^-127: never fp64-subnormal
+        const u64 mant = (bits & 0xfffffffffffffull) | (1ull << 52);
+        const int sh = be - 1075 + kBinBias;             // v = mant * 2^(sh - kBinBias), sh >= 22
+        const int q = sh >> 5, r = sh & 31;
+        const u64 lo = mant << r;                        // low 64 bits of the 85-bit value
+        const u64 hi = r ? (mant >> (64 - r)) : 0ull;
+        const u64 l0 = lo & 0xffffffffull, l1 = lo >> 32, l2 = hi;
+        if (l0) red_add_u64(bins + q, l0);
+        if (l1) red_add_u64(bins + q + 1, l1);
+        if (l2) red_add_u64(bins + q + 2, l2);
     }
-    __syncthreads();
-    if (!sc.flagA) return;
-    __threadfence();
-    const double *pp = a.rowpart + (int64_t)c * cnt;
-    double acc = 0.0;
-    for (int i = tid; i < cnt; i += kFxThreads) acc += __ldcg(pp + i);
-    acc = warp_sum_f64(acc);
-    if (lane == 0) sc.redA[warp] = acc;
-    __syncthreads();
-    if (tid == 0) {
-        double t = sc.redA[0];
+}
+// Count the tile whose sum went to the bins earlier in the iteration (release: the bins first).  Called a C-phase later, when
+// the thread's reductions have long been acknowledged and the fence costs next to nothing.
+__device__ __forceinline__ void publish_tile_count(const FxArgs &a, int c) {
+    uint32_t old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(a.pub_count + c) : "memory");
+    if (old == (uint32_t)a.T - 1u) {           // the row's last tile: evaluate the bins from the top (fixed order) and publish the constants
+        const u64 *bins = a.bins + (int64_t)c * kBins;
+        double t = 0.0;
 #pragma unroll
-        for (int w = 1; w < kFxWarps; ++w) t += sc.redA[w];
-        make_row_const_fx(a, c, t);
+        for (int q = kBins - 1; q >= 0; --q) t = t * 4294967296.0 + (double)__ldcg(bins + q);
+        make_row_const_fx(a, c, t * 3.7092061506874214e-68);      // 2^-224
         __threadfence();
         st_release_u32(&a.row_ready[c], 1u);
     }
+}
+__device__ __forceinline__ void grp_sync(int g) { bar_sync(1 + g, kFxThreads); }
+// The constants of row c into cache entry e (+ the binade offsets).  Whole group.
+__device__ __noinline__ void load_row(const FxArgs &a, FxScratch &sc, int g, int c, int e) {
+    const int gtid = threadIdx.x & (kFxThreads - 1);
+    grp_sync(g);                           // the previous users of rc[e] / tab[e] are done
+    if (gtid < 32) {
+        if (a.hack & 2) { if (gtid == 0) { make_row_const_fx(a, c, 1.3387e7); __threadfence(); } __syncwarp(); }
+        else while (ld_acquire_u32(&a.row_ready[c]) == 0u) __nanosleep(100);
+        uint4 part = make_uint4(0u, 0u, 0u, 0u);
+        if (gtid < (int)(sizeof(RowConst) / 16)) {
+            part = __ldcg(reinterpret_cast<const uint4 *>(&a.consts[c]) + gtid);
+            reinterpret_cast<uint4 *>(&sc.rc[e])[gtid] = part;
+        }
+        const uint32_t Xi = __shfl_sync(0xffffffffu, part.w, 1);       // RowConst::Xi is word 7
+        if (gtid < kBinades) sc.tab[e][gtid] = (gtid >= 2 && gtid <= 22) ? binade_offset(Xi, gtid) : 0ull;
+        if (gtid == 0) sc.rc_row[e] = c;
+    }
+    grp_sync(g);
 }
 
 // ------------------------------------------------------------------ pass B
@@ -403,8 +454,8 @@ __device__ __forceinline__ uint32_t spread_pairs_to_nibbles(uint32_t v) {
 __device__ __forceinline__ int width_of_u(uint32_t kmax) { return kmax < 2u ? 2 : kmax < 8u ? 4 : kmax < 128u ? 8 : kmax < 32768u ? 16 : 32; }
 
 // ------------------------------------------------------------------ look-back
-// warp 1: start the copies of tile t's look-back window (earlier tiles of its block, earlier blocks of its super-block,
-// earlier super-blocks) into shared memory; entries that do not exist are filled with complete neutral records
+// warp 1 of a group: start the copies of tile t's look-back window (earlier tiles of its block, earlier blocks of its
+// super-block, earlier super-blocks) into shared memory; entries that do not exist are filled with complete neutral records
 __device__ __forceinline__ void window_prefetch(const FxArgs &a, Rec *win, int c, int t, int lane) {
     const Rec *tiles = a.desc + (int64_t)c * a.T;
     const Rec2 *blocks = a.blocks + (int64_t)c * a.TB, *supers = a.supers + (int64_t)c * a.TS;
@@ -454,105 +505,157 @@ __device__ __noinline__ u64 lookback_poll(const FxArgs &a, int c, int t, int lan
             for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
             return x;
         }
-        __nanosleep(200);
+        __nanosleep(100);
     }
 }
 
-// thread 96: decode position `pos` of pass B into item slot `slot` and start the tile's copy into buffer `slot`
-__device__ __forceinline__ void fx_take(const FxArgs &a, const CUtensorMap *tmap, FxScratch &sc, int slot, uint32_t buf0, uint64_t pol, long long pos) {
-    FxItem it; it.c = 0; it.t = 0; it.flags = 0; it.pad = 0;
-    if (pos >= 0 && pos < a.nT) {
-        it.c = (int)((unsigned int)pos / (unsigned int)a.T); it.t = (int)((unsigned int)pos - (unsigned int)it.c * (unsigned int)a.T);
-        it.flags = kItValid;
-        if (it.t < a.tiles_tma) it.flags |= kItTma;
-        if (it.t == (int)a.T - 1 && a.has_tail) it.flags |= kItTail;
-        if (it.flags & kItTma) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&sc.mbar[slot], (uint32_t)kTile * 4u);
-            tma_tile_g2s(buf0 + (uint32_t)slot * kTile * 4u, tmap, it.t * (kTile / 32), it.c, &sc.mbar[slot], pol);
-        } else {
-            mbar_arrive(&sc.mbar[slot]);
+// one thread of a group: draw the SM's next position, decode its pass-B tile into item slot `slot` and start the tile's copy
+__device__ __forceinline__ void fx_take(const FxArgs &a, const CUtensorMap *tmap, FxScratch &sc, unsigned int *ticket, int slot, uint32_t buf0, uint64_t pol,
+                                        bool draw) {
+    FxItem it; it.c = 0; it.t = 0; it.flags = kItEnd; it.pad = 0;
+    if (draw) {
+        long long pb;
+        if (a.hack & 4) { pb = sc.pfb; sc.pfb += (long long)kFxGroups * gridDim.x; }
+        else pb = (long long)atomicAdd(ticket, 1u);
+        it.flags = 0;
+        if (pb >= a.nT) it.flags = kItEnd;
+        else if (pb >= 0) {
+            it.c = (int)((unsigned int)pb / (unsigned int)a.T); it.t = (int)((unsigned int)pb - (unsigned int)it.c * (unsigned int)a.T);
+            it.flags = kItValid;
+            if (it.t < a.tiles_tma) it.flags |= kItTma;
+            if (it.t == (int)a.T - 1 && a.has_tail) it.flags |= kItTail;
+            if (it.flags & kItTma) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&sc.mbar[slot], (uint32_t)kTile * 4u);
+                tma_tile_g2s(buf0 + (uint32_t)slot * kTile * 4u, tmap, it.t * (kTile / 32), it.c, &sc.mbar[slot], pol);
+            } else {
+                mbar_arrive(&sc.mbar[slot]);
+            }
         }
     }
     sc.item[slot] = it;
 }
 
+// ------------------------------------------------------------------ pass A (its own warps: they stream, add and publish; nobody waits for them inside the CTA)
+__device__ __forceinline__ unsigned int ldg_volatile_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ void pass_a_warp(const FxArgs &a, unsigned int *ticketA, const unsigned int *ticketB, int lane) {
+    const uint64_t polA = policy_evict_last();
+    for (;;) {
+        unsigned int kA = 0;
+        if (lane == 0) kA = atomicAdd(ticketA, 1u);
+        kA = __shfl_sync(0xffffffffu, kA, 0);
+        const long long pos = (long long)kA;
+        if (pos >= a.nT) break;
+        // stay within Lg tiles of the pass-B draws: what pass A streams has to survive in L2 until pass B comes for it
+        while ((long long)ldg_volatile_u32(ticketB) + a.Lg < pos) __nanosleep(2000);
+        const int c = (int)((unsigned int)pos / (unsigned int)a.T), t = (int)((unsigned int)pos - (unsigned int)c * (unsigned int)a.T);
+        const float *pa = a.X + (int64_t)c * a.ld + (int64_t)t * kTile;
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        if ((int64_t)(t + 1) * kTile <= a.d) {
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                uint4 v[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = ldg_keep_u4(pa + ((h * 16 + q) * 32 + lane) * 4, polA);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) acc_abs4(v[q], s);
+            }
+        } else {
+            const int64_t i0 = (int64_t)t * kTile;
+            for (int i = lane; i < kTile && i0 + i < a.d; i += 32) s[0] += abs_to_double(__float_as_uint(pa[i]));
+        }
+        const double ws = warp_sum_f64((s[0] + s[1]) + (s[2] + s[3]));      // fixed association
+        if (lane == 0) {
+            publish_tile_sum(a, c, ws);
+            publish_tile_count(a, c);
+        }
+    }
+}
+
 template <int EMIT>
-__global__ void __launch_bounds__(kFxThreads, 4)
+__global__ void __launch_bounds__(kFxBlock, kFxCtas)
 quantize_fx_kernel(const __grid_constant__ FxArgs a, const __grid_constant__ CUtensorMap tmap) {
-    extern __shared__ __align__(1024) unsigned char dyn_smem[];      // three tile buffers, FxScratch
-    FxScratch &sc = *reinterpret_cast<FxScratch *>(dyn_smem + (size_t)3 * kTile * sizeof(float));
-    const uint32_t buf0 = smem_u32(dyn_smem);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ch0 = 2 * tid, ch1 = 2 * tid + 1;
-    const uint64_t polB = policy_evict_first(), polA = policy_evict_last();
+    extern __shared__ __align__(1024) unsigned char dyn_smem[];      // per group: three tile buffers + FxScratch; then the ticket
+    const int g = threadIdx.x / kFxThreads, gtid = threadIdx.x & (kFxThreads - 1), lane = gtid & 31, warp = gtid >> 5;
+    unsigned int *ticket = &a.hdr->ticket;             // pass-B draws (pass A: ticket2); zeroed by the host before the launch
+    if (kFxAWarps > 0 && g == kFxGroups) {                  // the pass-A warps
+        __syncthreads();
+        pass_a_warp(a, &a.hdr->ticket2, ticket, lane);
+        return;
+    }
+    unsigned char *gbase = dyn_smem + (size_t)g * kGroupBytes;
+    FxScratch &sc = *reinterpret_cast<FxScratch *>(gbase + (size_t)3 * kTile * sizeof(float));
+    const uint32_t buf0 = smem_u32(gbase);
+    const int ch0 = 2 * gtid, ch1 = 2 * gtid + 1;
+    const uint64_t polB = policy_evict_first();
     const uint32_t boff0 = blocked_off_of((uint32_t)ch0), boff1 = blocked_off_of((uint32_t)ch1);
     const bool window_ok = a.TS <= 32;
-    const int T = (int)a.T;
-    long long posA = blockIdx.x;
-    if (tid == 0) {
+    const int kBarFree = 1 + kFxGroups + g;
+    if (gtid == 0) {
         for (int q = 0; q < 3; ++q) mbar_init(&sc.mbar[q], 1);
         mbar_init(&sc.winbar[0], 32); mbar_init(&sc.winbar[1], 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        fx_take(a, &tmap, sc, 0, buf0, polB, posA - a.Lg);
-        fx_take(a, &tmap, sc, 1, buf0, polB, posA - a.Lg + a.G);
-        fx_take(a, &tmap, sc, 2, buf0, polB, -1);
         sc.rc_row[0] = sc.rc_row[1] = -1;
         sc.hit[0] = sc.hit[1] = 0;
+        sc.pfb = (long long)blockIdx.x * kFxGroups + g;
     }
-    // pass-A state: (client, tile) of this position, the row whose partial is being accumulated and the slot it goes to
-    int cA = (int)(posA / T), tA = (int)(posA - (long long)cA * T);
-    int slotA = tA;
-    double sA[4] = {0.0, 0.0, 0.0, 0.0};
     __syncthreads();
+    if (gtid == 0) {
+        fx_take(a, &tmap, sc, ticket, 0, buf0, polB, true);
+        fx_take(a, &tmap, sc, ticket, 1, buf0, polB, !(sc.item[0].flags & kItEnd));
+        fx_take(a, &tmap, sc, ticket, 2, buf0, polB, false);
+    }
+    grp_sync(g);
     // state of the tile whose C-phase is pending (one iteration behind its B-phase); index 0 / 1 = the thread's chunks
     uint32_t sgw0P = 0, sgw1P = 0, flm0P = 0, flm1P = 0, f4a0P = 0, f4b0P = 0, f4a1P = 0, f4b1P = 0, mxhP = 0, fmP = 0;
     u64 exclP = 0, runP = 0, wbaseP = 0;
+    uint32_t run0P = 0;              // low word of the first chunk's sum
     bool liveC = false;
+    FxItem iC; iC.c = 0; iC.t = 0; iC.flags = 0;
     int sB = 0, sC = 2;
     uint32_t phase = 0;             // bit s: parity of the next completion of mbar[s]
+#ifdef DME_TIMERS
+    long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#endif
     for (int it = 0;; ++it) {
-        const long long posB = posA - a.Lg;
         const FxItem iB = sc.item[sB];
-        const FxItem iC = sc.item[sC];
-        if (posB >= a.nT && !liveC) break;
-        const bool validA = posA < a.nT, validB = iB.flags & kItValid;
+        if ((iB.flags & kItEnd) && !liveC) break;
+        const bool validB = iB.flags & kItValid;
         const int e = it & 1;
-        // ---------------------------------------------------------------- pass A, first half of tile posA: loads in flight during the B-phase
-        const float *pa = a.X + (int64_t)cA * a.ld + (int64_t)tA * kTile;
-        const bool fullA = validA && ((int64_t)(tA + 1) * kTile <= a.d);
-        uint4 va[4];
-        if (fullA) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) va[q] = ldg_keep_u4(pa + (q * kFxThreads + tid) * 4, polA);
+        FXW(20);
+        // The look-back window of tile C: its copies take an L2 round trip (well over a microsecond under load), so they start
+        // here and land during the B-phase; records that are not complete yet are polled for later.
+        if (warp == 1) {
+            if (liveC && window_ok) window_prefetch(a, sc.win[e], iC.c, iC.t, lane);
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&sc.winbar[e])) : "memory");
         }
         // ---------------------------------------------------------------- B-phase of tile iB
         uint32_t sgw0 = 0, sgw1 = 0, flm0 = 0, flm1 = 0, f4a0 = 0, f4b0 = 0, f4a1 = 0, f4b1 = 0, mxh = 0;
         u64 run = 0, incl = 0;
+        uint32_t run0 = 0;
         bool liveB = false;
         if (validB) {
-            if (sc.rc_row[e] != iB.c) {          // CTA-uniform: the row's constants and binade offsets into shared memory
-                __syncthreads();
-                if (warp == 0) {
-                    while (ld_acquire_u32(&a.row_ready[iB.c]) == 0u) __nanosleep(100);
-                    uint4 part = make_uint4(0u, 0u, 0u, 0u);
-                    if (lane < (int)(sizeof(RowConst) / 16)) {
-                        part = __ldcg(reinterpret_cast<const uint4 *>(&a.consts[iB.c]) + lane);
-                        reinterpret_cast<uint4 *>(&sc.rc[e])[lane] = part;
-                    }
-                    const uint32_t Xi = __shfl_sync(0xffffffffu, part.w, 1);       // RowConst::Xi is word 7
-                    if (lane < kBinades) sc.tab[e][lane] = (lane >= 2 && lane <= 22) ? binade_offset(Xi, lane) : 0ull;
-                    if (lane == 0) sc.rc_row[e] = iB.c;
-                }
-                __syncthreads();
+            if (sc.rc_row[e] != iB.c) {          // group-uniform: the row's constants and binade offsets into shared memory
+                FXT(0);
+                load_row(a, sc, g, iB.c, e);
+                FXT(10);
             }
             const RowConst &rc = sc.rc[e];
             const uint32_t buf = buf0 + (uint32_t)sB * kTile * 4u;
+            FXT(0);
             mbar_wait(smem_u32(&sc.mbar[sB]), (phase >> sB) & 1u);
             phase ^= 1u << sB;
+            FXT(1);
             liveB = !(rc.flags & kRowExotic);
+            FXW(21);
+            FXTR(1, iB.c, iB.t);
             if (liveB) {
                 fx_chunk_b(a, iB, buf, boff0, ch0, rc, sgw0, flm0, f4a0, f4b0, mxh, run);
+                run0 = (uint32_t)run;
                 fx_chunk_b(a, iB, buf, boff1, ch1, rc, sgw1, flm1, f4a1, f4b1, mxh, run);
                 incl = run;
 #pragma unroll
@@ -565,40 +668,17 @@ quantize_fx_kernel(const __grid_constant__ FxArgs a, const __grid_constant__ CUt
                 if (lane == 0) sc.fmw[e][warp] = wmx;
             }
         }
-        // ---------------------------------------------------------------- pass A: consume the first half, second half
-        int cN = cA + a.step_c, tN = tA + a.step_t;
-        if (tN >= T) { tN -= T; ++cN; }
-        const bool rowEndA = validA && (posA + a.G >= a.nT || cN != cA);
-        if (validA) {
-            if (fullA) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) acc_abs4(va[q], sA);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) va[q] = ldg_keep_u4(pa + ((q + 4) * kFxThreads + tid) * 4, polA);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) acc_abs4(va[q], sA);
-            } else {
-                const int64_t i0 = (int64_t)tA * kTile;
-                for (int i = tid; i < kTile && i0 + i < a.d; i += kFxThreads) sA[0] += abs_to_double(__float_as_uint(pa[i]));
-            }
-            if (rowEndA) {
-                const double ws = warp_sum_f64((sA[0] + sA[1]) + (sA[2] + sA[3]));      // fixed association
-                if (lane == 0) sc.redA[warp] = ws;
-            }
-        }
-        // The serial jobs of an iteration are spread over the warps (window copies: warp 1, publish: warp 2, next copy: warp 3):
-        // warp w of every CTA runs on scheduler w.  The look-back window of tile C is copied as LATE as possible -- the later,
-        // the more of the earlier tiles' aggregates are there -- and nobody waits for the copies here: they signal winbar[e].
-        if (warp == 1) {
-            if (liveC && window_ok) window_prefetch(a, sc.win[e], iC.c, iC.t, lane);
-            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&sc.winbar[e])) : "memory");
-        }
-        __syncthreads();
-        if (rowEndA) {
-            publish_row(a, sc, cA, slotA);
-            sA[0] = sA[1] = sA[2] = sA[3] = 0.0;
-            slotA = tN;
-        }
+        FXT(2);
+        // The serial jobs of an iteration are spread over the warps (window copies: warp 1, aggregate: warp 2,
+        // next draw + copy: warp 3): warp w of every group runs on scheduler w.  The look-back window of tile C is copied as
+        // LATE as possible -- the later, the more of the earlier tiles' aggregates are there -- and nobody waits for the copies
+        // here: they signal winbar[e].
+        FXW(22);
+        FXW(23);
+        grp_sync(g);
+        FXW(24);
+        FXT(4);
+        FXT(5);
         // ---------------------------------------------------------------- every warp: warp base of tile B, its aggregate
         u64 wbase = 0;
         uint32_t fm = 0;
@@ -611,7 +691,8 @@ quantize_fx_kernel(const __grid_constant__ FxArgs a, const __grid_constant__ CUt
                 Aq += v;
                 fm = max(fm, sc.fmw[e][w]);
             }
-            if (tid == 64) {
+            FXTR(2, iB.c, iB.t);
+            if (gtid == 64) {
                 rec_store(a.desc + (int64_t)iB.c * a.T + iB.t, Aq, 1u);
                 const u64 lo = (Aq & 0x7fffffffull) + (1ull << kCntShift), hi = (Aq >> 31) + (1ull << kCntShift);
                 Rec2 *br = a.blocks + (int64_t)iB.c * a.TB + (iB.t >> 5), *sr = a.supers + (int64_t)iB.c * a.TS + (iB.t >> 10);
@@ -619,32 +700,42 @@ quantize_fx_kernel(const __grid_constant__ FxArgs a, const __grid_constant__ CUt
                 red_add_u64(&sr->lo, lo); red_add_u64(&sr->hi, hi);
             }
         }
-        if (tid == 0) sc.hit[e ^ 1] = 0;
+        if (gtid == 0) sc.hit[e ^ 1] = 0;
         // ---------------------------------------------------------------- C-phase of tile iC: AS:635-637
         uint32_t kw0 = 0, kw1 = 0;
-        const bool need_hit = liveC && EMIT == 1 && fmP < 0x7fffffffu && width_of_u(fmP) != width_of_u(fmP + 1u);      // CTA-uniform
+        const bool need_hit = liveC && EMIT == 1 && fmP < 0x7fffffffu && width_of_u(fmP) != width_of_u(fmP + 1u);      // group-uniform
         if (liveC) {
             const RowConst &rc = sc.rc[e ^ 1];
             const uint32_t buf = buf0 + (uint32_t)sC * kTile * 4u;
             u64 P = 0;
+            FXT(6);
+            FXTR(3, iC.c, iC.t);
             mbar_wait(smem_u32(&sc.winbar[e]), (uint32_t)((it >> 1) & 1));          // the window copies have landed
-            if (iC.t > 0 && !(window_ok && window_eval(sc.win[e], lane, P))) {
+            FXT(7);
+            if (a.hack & 1) P = (u64)iC.t * (877ull << 32);
+            if (!(a.hack & 1) && iC.t > 0 && !(window_ok && window_eval(sc.win[e], lane, P))) {
+#ifdef DME_TIMERS
+                if (gtid == 0) tacc[11] += 1;
+#endif
                 if (warp == 0) {
-                    const u64 p = lookback_poll(a, iC.c, iC.t, lane);
-                    if (lane == 0) sc.pfb = (long long)p;
+                    const u64 pp = lookback_poll(a, iC.c, iC.t, lane);
+                    if (lane == 0) sc.pfb = (long long)pp;
                 }
-                __syncthreads();
+                grp_sync(g);
                 P = (u64)sc.pfb;
             }
+            FXT(8);
+            FXW(25);
+            FXTR(4, iC.c, iC.t);
             const u64 E = P + wbaseP + exclP, En = E + runP;
             const int eb = 31 - __clzll((long long)(E | 1ull));                     // E in [2^eb, 2^(eb+1))
             // every prefix of the thread, and their fp32 roundings, stay inside [2^eb + 1, 2^(eb+1))
             const bool fast = eb >= 2 && eb <= 22 && ((E - (3ull << 31)) >> (eb + 32)) == 1ull && ((En + (1ull << 32)) >> (eb + 32)) == 1ull;
             uint32_t rb0, rb1;
             if (fast) {
-                uint32_t acc = (uint32_t)(E - sc.tab[e ^ 1][eb]);
-                rb0 = walk_carry(buf + boff0, acc);
-                rb1 = walk_carry(buf + boff1, acc);
+                uint32_t acc0 = (uint32_t)(E - sc.tab[e ^ 1][eb]), acc1 = acc0 + run0P;      // the second chunk starts from the first chunk's sum: two independent carry chains
+                rb0 = walk_carry(buf + boff0, acc0);
+                rb1 = walk_carry(buf + boff1, acc1);
             } else {
                 u64 c = E;
                 long long tp = t_literal(c, rc.Xi);
@@ -676,9 +767,11 @@ quantize_fx_kernel(const __grid_constant__ FxArgs a, const __grid_constant__ CUt
         }
         // Buffer sC is free once every warp has read its low words: only the warp that issues the next copy into it has
         // to wait for that, the others just signal.  When the tile's width depends on sc.hit, everybody waits.
+        FXT(9);
+        FXW(26);
         if (warp == 3 || need_hit) bar_sync(kBarFree, kFxThreads);
         else bar_arrive(kBarFree, kFxThreads);
-        if (tid == 96) fx_take(a, &tmap, sc, sC, buf0, polB, posB + 2ll * a.G);
+        if (gtid == 96) fx_take(a, &tmap, sc, ticket, sC, buf0, polB, !(iB.flags & kItEnd));
         // ---------------------------------------------------------------- emit tile iC
         if (liveC) {
             const RowConst &rc = sc.rc[e ^ 1];
@@ -714,21 +807,21 @@ quantize_fx_kernel(const __grid_constant__ FxArgs a, const __grid_constant__ CUt
                 if (ovf) atomicOr(&a.hdr->status, 1u);
             } else {
                 const int W = sc.hit[e] ? width_of_u(fmP + 1u) : width_of_u(fmP);
-                if (fmP >= 0x7fffffffu && tid == 0) atomicOr(&a.hdr->status, 1u);
+                if (fmP >= 0x7fffffffu && gtid == 0) atomicOr(&a.hdr->status, 1u);
                 const int64_t slot_id = (int64_t)iC.c * a.T + iC.t;
                 u64 off16;
                 if (W <= a.pack.W0) {
                     off16 = primary_off16(a.pack, iC.c, iC.t);
-                    if (tid == 0) a.pack.dir[slot_id] = (off16 << 8) | (u64)W;
+                    if (gtid == 0) a.pack.dir[slot_id] = (off16 << 8) | (u64)W;
                 } else {
-                    if (tid == 0) {
+                    if (gtid == 0) {
                         const u64 units = 32ull * W;
                         u64 o = a.pack.arena_base16 + atomicAdd(&a.hdr->arena_top, units);
                         if ((long long)((o + units) * 16ull) > a.pack.codes_bytes) { atomicOr(&a.hdr->status, 2u); o = ~0ull; }
                         sc.off16 = o;
                         a.pack.dir[slot_id] = (o == ~0ull) ? 0ull : ((o << 8) | (u64)W);
                     }
-                    __syncthreads();
+                    grp_sync(g);
                     off16 = sc.off16;
                 }
                 if (off16 != ~0ull) {
@@ -772,15 +865,21 @@ quantize_fx_kernel(const __grid_constant__ FxArgs a, const __grid_constant__ CUt
             }
         }
         sgw0P = sgw0; sgw1P = sgw1; flm0P = flm0; flm1P = flm1; f4a0P = f4a0; f4b0P = f4b0; f4a1P = f4a1; f4b1P = f4b1;
-        mxhP = mxh; exclP = incl - run; runP = run; wbaseP = wbase; fmP = fm; liveC = liveB;
+        mxhP = mxh; exclP = incl - run; runP = run; run0P = run0; wbaseP = wbase; fmP = fm; liveC = liveB; iC = iB;
+        FXW(27);
+        if (liveC) FXTR(5, iC.c, iC.t);
         const int nB = sB == 2 ? 0 : sB + 1;
         sC = sB; sB = nB;
-        posA += a.G; cA = cN; tA = tN;
+        FXT(10);
     }
+#ifdef DME_TIMERS
+    if (gtid == 0)
+        for (int q = 0; q < 12; ++q) atomicAdd(reinterpret_cast<unsigned long long *>(&a.hdr->pad[5]) + q, (unsigned long long)tacc[q]);
+#endif
 }
 
 // ------------------------------------------------------------------ host side
-struct FxDevice { bool ready = false; int sms = 0; int occ[2] = {0, 0}; };
+struct FxDevice { bool ready = false; int sms = 0; };
 static FxDevice g_fx_dev[64];
 static std::mutex g_fx_mu;
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -788,6 +887,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_fx_encode = nullptr;
 static int g_fx_lead = -1;       // DME_FX_LEAD (development): minimum distance, in tiles, between the end of a row's pass A and the start of its pass B
+constexpr size_t kFxDynSmem = (size_t)kFxGroups * kGroupBytes + 16;
 
 static int fx_device(FxDevice **out) {
     int dev = 0;
@@ -796,12 +896,12 @@ static int fx_device(FxDevice **out) {
     std::lock_guard<std::mutex> lock(g_fx_mu);
     FxDevice &D = g_fx_dev[dev];
     if (!D.ready) {
-        // function attributes and occupancy are per device: set / queried once for each device the library is used on
-        const size_t dyn = (size_t)3 * kTile * sizeof(float) + sizeof(FxScratch);
-        DME_CUDA(cudaFuncSetAttribute(quantize_fx_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        DME_CUDA(cudaFuncSetAttribute(quantize_fx_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.occ[0], quantize_fx_kernel<0>, kFxThreads, dyn));
-        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.occ[1], quantize_fx_kernel<1>, kFxThreads, dyn));
+        // function attributes are per device: set once for each device the library is used on
+        DME_CUDA(cudaFuncSetAttribute(quantize_fx_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFxDynSmem));
+        DME_CUDA(cudaFuncSetAttribute(quantize_fx_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFxDynSmem));
+        int occ = 0;
+        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quantize_fx_kernel<1>, kFxBlock, kFxDynSmem));
+        if (occ < 1) { set_error("quantize_fx_kernel does not fit on an SM of device %d", dev); return DME_ECUDA; }
         DME_CUDA(cudaDeviceGetAttribute(&D.sms, cudaDevAttrMultiProcessorCount, dev));
         if (g_fx_encode == nullptr) {
             cudaDriverEntryPointQueryResult qres;
@@ -840,7 +940,7 @@ int launch_quantize_fx(const float *X, int64_t n, int64_t d, int64_t ld, int64_t
     a.blocks = (Rec2 *)(base + L.off_desc + 16 * n * L.T);
     a.supers = (Rec2 *)(base + L.off_desc + 16 * n * (L.T + a.TB));
     a.hdr = (WsHeader *)base;
-    a.rowpart = (double *)(base + L.off_partial);
+    a.bins = (u64 *)(base + L.off_bins);
     a.pub_count = (uint32_t *)(base + L.off_done);
     a.row_ready = (uint32_t *)(base + L.off_ready);
     a.exotic_rows = (int32_t *)(base + L.off_exotic);
@@ -854,21 +954,18 @@ int launch_quantize_fx(const float *X, int64_t n, int64_t d, int64_t ld, int64_t
         set_error("code arena too small for the primary slots: %lld < %llu bytes", (long long)codes_bytes, a.pack.arena_base16 * 16ull);
         return DME_EWORKSPACE;
     }
-    const int occ = D->occ[packed ? 1 : 0];
-    if (occ < 1) { set_error("quantize_fx_kernel does not fit on an SM"); return DME_ECUDA; }
-    int64_t G = (int64_t)D->sms * occ;
-    if (G > kFxMaxG) G = kFxMaxG;
-    if (G > a.nT) G = a.nT;
-    // pass B of a tile runs Lg = T + lead positions after its pass A, on the same CTA (Lg a multiple of G); `lead` covers
-    // the time it takes to finish a row's norm after its last tile has been streamed
-    int64_t lead_min = g_fx_lead >= 0 ? g_fx_lead : G;
-    int64_t Lg = (L.T + lead_min + G - 1) / G * G;
-    a.G = (int)G; a.Lg = Lg;
-    a.slots = (int)(G < L.T ? G : L.T);
-    a.step_c = (int)(G / L.T); a.step_t = (int)(G % L.T);
+    int64_t S = (int64_t)D->sms * kFxCtas;
+    if (const char *e = getenv("DME_FX_G")) S = atoll(e);        // development
+    if (S > a.nT) S = a.nT;
+    // pass B of a tile runs Lg = T + lead positions after its pass A, on the same SM (Lg a multiple of S); `lead` covers
+    // the time it takes until a row's norm is known after its last tile has been streamed
+    const int64_t lead = g_fx_lead >= 0 ? g_fx_lead : 512;
+    a.S = (int)S;
+    a.Lg = L.T + lead;
     a.tiles_tma = (int)((a.rows32 + kTile / 32 - 1) / (kTile / 32));
     a.has_tail = (d & 31) ? 1 : 0;
     a.one = 1u;
+    a.hack = getenv("DME_FX_HACK") ? atoi(getenv("DME_FX_HACK")) : 0;
     // 3-D view of the client rows: {32 floats, full 128-byte rows of a client, clients}; the last d % 32 coordinates
     // of every row are read directly by the kernel
     CUtensorMap tmap;
@@ -881,10 +978,9 @@ int launch_quantize_fx(const float *X, int64_t n, int64_t d, int64_t ld, int64_t
                                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for n=%lld d=%lld ld=%lld", (int)r, (long long)n, (long long)d, (long long)ld); return DME_ECUDA; }
     }
-    const size_t dyn = (size_t)3 * kTile * sizeof(float) + sizeof(FxScratch);
     void *args[] = {&a, &tmap};
     const void *fn = packed ? (const void *)quantize_fx_kernel<1> : (const void *)quantize_fx_kernel<0>;
-    DME_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)G), dim3(kFxThreads), args, dyn, st));
+    DME_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)S), dim3(kFxBlock), args, kFxDynSmem, st));
     count_launch();
     // rows outside the proven range of the fast chain (none on ordinary inputs: the kernel exits at once)
     return launch_literal_rows(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, k_out, sgn_out, deq_out, ld_out, codes, codes_bytes, dir,
@@ -892,3 +988,16 @@ int launch_quantize_fx(const float *X, int64_t n, int64_t d, int64_t ld, int64_t
 }
 
 }  // namespace dme
+
+#ifdef DME_TIMERS
+extern "C" __attribute__((visibility("default"))) int dme_debug_fx_trace(unsigned long long *out, int cap) {
+    unsigned int n = 0;
+    cudaMemcpyFromSymbol(&n, dme::g_fx_trace_n, sizeof(n));
+    if ((int)n > cap) n = cap;
+    if (n > (1u << 15)) n = 1u << 15;
+    cudaMemcpyFromSymbol(out, dme::g_fx_trace, (size_t)n * 16);
+    unsigned int z = 0;
+    cudaMemcpyToSymbol(dme::g_fx_trace_n, &z, sizeof(z));
+    return (int)n;
+}
+#endif

@@ -51,6 +51,7 @@ struct WsLayout {
     int64_t T;            // tiles per row
     int64_t off_done;     // uint32 a_done[n]
     int64_t off_ready;    // uint32 row_ready[n]
+    int64_t off_bins;     // uint64 bins[n][12]: per-row superaccumulator of |x| (quantize_fx.cu)
     int64_t off_consts;   // RowConst consts[n]
     int64_t off_partial;  // double partial[n*T]
     int64_t off_desc;     // look-back records: 16 bytes per tile, per block of 32 tiles, per super-block of 1024 tiles
@@ -92,6 +93,7 @@ inline WsLayout ws_layout(int64_t n, int64_t d) {
     int64_t o = (int64_t)sizeof(WsHeader);
     L.off_done = o; o = align_up(o + 4 * n, 256);
     L.off_ready = o; o = align_up(o + 4 * n, 256);
+    L.off_bins = o; o = align_up(o + 96 * n, 256);
     L.zero_bytes = o;
     L.off_consts = o; o = align_up(o + (int64_t)sizeof(RowConst) * n, 256);
     L.off_partial = o; o = align_up(o + 16 * n * L.T, 256);     // 16-byte {sum, flag} records

@@ -232,8 +232,8 @@ def run_ours(a):
     if len(kern_ms) >= 3:      # default path: l1_kernel -> quantize_tiles_kernel -> decode_mean_kernel (one launch per slice when N > 1)
         names = ["l1_kernel", "quantize_tiles_kernel", "decode_mean_kernel"]
         kern_ms = np.array([kern_ms[0], kern_ms[1], kern_ms[2:].sum()])
-    else:                      # DME_PATH=stream: the fused persistent kernel (L1 pass + quantize pass in one launch)
-        names = ["quantize_stream_kernel", "decode_mean_kernel"][: len(kern_ms)]
+    else:
+        names = ["quantize", "decode_mean_kernel"][: len(kern_ms)]
     dom = int(np.argmax(kern_ms))
     # algorithmic bytes of one step (every input coordinate read once, the mean written once) over the
     # duration of the dominant kernel's launch; the whole step against the same bytes is step_achieved

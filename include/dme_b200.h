@@ -67,8 +67,8 @@ DME_API int64_t dme_launch_count(void);
  * keep it off inside timed regions).  dme_profile_read returns the number of intervals written: for
  * dme_quantize_mean they are {L1 reduce, scan/quantize/pack, decode+mean} in milliseconds. */
 DME_API int dme_profile_enable(int on);
-/* Test hook: which implementation runs the unbiased mode.  0 (default) = the fused fixed-point kernel, with the literal kernel for
- * the rows outside its proven operand range; 1 = the literal kernel (AS:625-637 as written) for every row. */
+/* Test hook: which implementation runs the unbiased mode.  0 (default) = l1_kernel + quantize_tiles_kernel (the product path);
+ * 1 = literal_rows_kernel (AS:625-637 as written, one CTA per row: an independent implementation for the parity tests). */
 DME_API int dme_set_unbiased_path(int path);
 DME_API int dme_profile_read(float *ms, int cap);
 

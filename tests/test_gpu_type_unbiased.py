@@ -19,14 +19,14 @@ def dme():
     return dme_b200
 
 
-@pytest.fixture(autouse=True, params=["fx", "literal"])
+@pytest.fixture(autouse=True, params=["tiles", "literal"])
 def quantize_path(request, dme):
-    """Every test of this file runs on both implementations of the unbiased quantizer: the fused fixed-point kernel
-    (quantize_fx.cu, the product path) and the literal kernel (quantize_literal.cu: AS:625-637 as written, which also serves
-    the rows outside the fast kernel's proven operand range)."""
+    """Every test of this file runs on both implementations of the unbiased quantizer: the product path (l1_kernel +
+    quantize_tiles_kernel, csrc/quantize_tiles.cu) and the literal kernel (csrc/quantize_literal.cu: AS:625-637 as written,
+    one CTA per row), an independent second implementation checked against the same oracle and goldens."""
     dme.set_unbiased_path(request.param)
     yield request.param
-    dme.set_unbiased_path("fx")
+    dme.set_unbiased_path("tiles")
 
 
 def _R(v):
@@ -199,7 +199,7 @@ def test_full_size_row_properties(dme):
 @pytest.mark.parametrize("X", [0.0, 2.0 ** -24, 0.25, 0.5, 0.75, 1 - 2.0 ** -24, 0.3333333432674408])
 def test_ties_and_binade_crossings_bit_exact(dme, X):
     """Dyadic rows (every prefix is exact, so the fp32 roundings of AS:636 tie all the time) long enough to cross
-    many binades of the prefix: the closed-form floor of the stream kernel against the literal oracle."""
+    many binades of the prefix: the closed-form floor of quantize_tiles_kernel against the literal oracle."""
     rng = np.random.default_rng(17)
     d = 3 * 4096 + 777
     for R in (1, 3, 6):

@@ -118,12 +118,13 @@ class Workspace:
         _check(_cabi.lib().dme_status(C.c_void_p(self.buf.data_ptr() + off), C.c_void_p(_stream())))
 
 
-UNBIASED_PATHS = {"fx": 0, "literal": 1, "tiles": 2, "stream": 3}
+UNBIASED_PATHS = {"tiles": 0, "literal": 1}
 
 
 def set_unbiased_path(path) -> None:
-    """Test hook (dme_set_unbiased_path): "fx" = the fused fixed-point kernel (default), "literal" = AS:625-637 as
-    written, for every row (slow; an independent implementation the GPU tests check against the same oracle)."""
+    """Test hook (dme_set_unbiased_path): "tiles" = l1_kernel + quantize_tiles_kernel (the product path, default),
+    "literal" = AS:625-637 as written, one CTA per row (slow; an independent implementation the GPU tests check
+    against the same oracle)."""
     _check(_cabi.lib().dme_set_unbiased_path(UNBIASED_PATHS.get(path, path)))
 
 

@@ -1,15 +1,14 @@
 // quantize_literal.cu -- the unbiased type quantizer (AS:609-641) evaluated LITERALLY: IEEE division, floorf, fp64 prefix,
-// AS:636 as written.  One CTA per client row, tiles in order.  It serves the rows quantize_fx_kernel (quantize_fx.cu) leaves
-// out -- norms outside [2^-20, 2^100] or with an all-ones mantissa, a uniform X off the 2^-32 grid -- and, with
-// DME_PATH=literal, every row: an independent second implementation the GPU tests run against the same oracle.
-// Slow by construction (a 2^24-coordinate row takes milliseconds); ordinary inputs never reach it.
+// AS:636 as written.  One CTA per client row, tiles in order, no look-back, no closed forms.  It is NOT the product path
+// (quantize_tiles.cu is): dme_set_unbiased_path(1) selects it so that the GPU tests can run an independent second
+// implementation against the same oracle and the same goldens.  Slow by construction (a 2^24-coordinate row takes milliseconds).
 #include "type_quantize.cuh"
 
 namespace dme {
 
 struct LitArgs {
     const float *X; int64_t d, ld, T, n, m;
-    WsHeader *hdr; const int32_t *rows; int all_rows;
+    WsHeader *hdr;
     const float *x_inject; const float *l1_inject; uint64_t seed, client0; float *l1_out;
     int32_t *k_out; uint8_t *sgn_out; float *deq_out; int64_t ld_out;
     PackTarget pack; int packed;
@@ -25,9 +24,7 @@ literal_rows_kernel(const LitArgs a) {
     __shared__ double s_wtot[kWarps];
     __shared__ PackScratch s_ps;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned int count = a.all_rows ? (unsigned int)a.n : *reinterpret_cast<volatile unsigned int *>(&a.hdr->pad[1]);
-    for (unsigned int j = blockIdx.x; j < count; j += gridDim.x) {
-        const int64_t c = a.all_rows ? (int64_t)j : (int64_t)a.rows[j];
+    for (int64_t c = blockIdx.x; c < a.n; c += gridDim.x) {
         const float *row = a.X + c * a.ld;
         // ---- AS:624: L1 in fp64, fixed association (thread-strided, then the block tree)
         double s = 0.0;
@@ -105,11 +102,11 @@ literal_rows_kernel(const LitArgs a) {
 int launch_literal_rows(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
                         const float *x_inject, const float *l1_inject, uint64_t seed, uint64_t client0,
                         int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
-                        uint32_t *codes, int64_t codes_bytes, uint64_t *dir, float *l1_out, cudaStream_t st, bool packed, bool all_rows) {
+                        uint32_t *codes, int64_t codes_bytes, uint64_t *dir, float *l1_out, cudaStream_t st, bool packed) {
     char *base = (char *)ws;
     LitArgs a;
     a.X = X; a.d = d; a.ld = ld; a.T = L.T; a.n = n; a.m = m;
-    a.hdr = (WsHeader *)base; a.rows = (const int32_t *)(base + L.off_exotic); a.all_rows = all_rows ? 1 : 0;
+    a.hdr = (WsHeader *)base;
     a.x_inject = x_inject; a.l1_inject = l1_inject; a.seed = seed; a.client0 = client0; a.l1_out = l1_out;
     a.k_out = k_out; a.sgn_out = sgn_out; a.deq_out = deq_out; a.ld_out = ld_out;
     a.pack.codes = codes; a.pack.codes_bytes = codes_bytes; a.pack.dir = dir; a.pack.hdr = a.hdr; a.pack.n = n; a.pack.T = L.T;

@@ -9,11 +9,7 @@
 // coordinates so that the in-thread part of the prefix is a plain sequential sum):
 //   l1_kernel      : per-tile fp64 partial sums; the LAST tile of a row to finish reduces the partials in
 //                    index order and publishes the row constants (deterministic, no float atomics).
-//   scan_kernel<E> : single pass over the row in ticket order with a decoupled look-back across tiles.
-//                    The exclusive prefix of a tile is the canonical left-to-right sum of tile aggregates
-//                    (start at the nearest published inclusive prefix, add the aggregates after it in
-//                    order), so the result does not depend on timing.  floor(c - X) of a tile's last
-//                    coordinate is handed to the next tile through the descriptor (each a_i is computed once).
+//   quantize_tiles_kernel (quantize_tiles.cu): single pass over the rows in ticket order with a decoupled look-back.
 //   decode_mean_kernel : tile-major over d, clients in order in registers, one write of the mean.
 #include <cstdlib>
 
@@ -328,7 +324,7 @@ static int check_rows(const void *X, int64_t n, int64_t d, int64_t ld) {
     return DME_OK;
 }
 
-int ws_prepare(void *ws, int64_t ws_bytes, int64_t n, int64_t d, cudaStream_t st, WsLayout *out, bool need_desc, bool need_sel, bool need_partial = true) {
+int ws_prepare(void *ws, int64_t ws_bytes, int64_t n, int64_t d, cudaStream_t st, WsLayout *out, bool need_desc, bool need_sel) {
     const WsLayout L = ws_layout(n, d);
     DME_REQUIRE(ws != nullptr && ((uintptr_t)ws & 255u) == 0, "workspace must be non-null and 256-byte aligned");
     if (ws_bytes < L.total) {
@@ -339,7 +335,6 @@ int ws_prepare(void *ws, int64_t ws_bytes, int64_t n, int64_t d, cudaStream_t st
     DME_CUDA(cudaMemsetAsync(base, 0, (size_t)L.zero_bytes, st));
     if (need_desc) {
         DME_CUDA(cudaMemsetAsync(base + L.off_desc, 0, (size_t)L.desc_bytes, st));
-        if (need_partial) DME_CUDA(cudaMemsetAsync(base + L.off_partial, 0, 16 * (size_t)(n * L.T), st));
     }
     if (need_sel) DME_CUDA(cudaMemsetAsync(base + L.off_sel, 0, sizeof(RowSelect) * (size_t)n, st));
     *out = L;
@@ -359,21 +354,15 @@ int launch_l1(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const
 int biased_quantize(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
                     int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
                     uint32_t *codes, int64_t codes_bytes, uint64_t *dir, cudaStream_t st);   // reznik.cu
-int launch_stream(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
-                  const float *x_inject, const float *l1_inject, uint64_t seed, uint64_t client0,
-                  int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
-                  uint32_t *codes, int64_t codes_bytes, uint64_t *dir, float *l1_out, cudaStream_t st, bool packed);   // stream.cu
-bool use_tiles_path(int64_t d);   // stream.cu
-int launch_quantize_fx(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
-                       const float *x_inject, const float *l1_inject, uint64_t seed, uint64_t client0,
-                       int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
-                       uint32_t *codes, int64_t codes_bytes, uint64_t *dir, float *l1_out, cudaStream_t st, bool packed);   // quantize_fx.cu
+int launch_quantize_tiles(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
+                          int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
+                          uint32_t *codes, int64_t codes_bytes, uint64_t *dir, cudaStream_t st, bool packed);   // quantize_tiles.cu
 int launch_literal_rows(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
                         const float *x_inject, const float *l1_inject, uint64_t seed, uint64_t client0,
                         int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
-                        uint32_t *codes, int64_t codes_bytes, uint64_t *dir, float *l1_out, cudaStream_t st, bool packed, bool all_rows);   // quantize_literal.cu
-// Which implementation quantises the unbiased mode: 0 = quantize_fx_kernel (+ literal_rows_kernel for the rows it leaves out),
-// 1 = literal_rows_kernel for every row (tests), 2 / 3 = the round-1 fp64 kernels (development).  dme_set_unbiased_path.
+                        uint32_t *codes, int64_t codes_bytes, uint64_t *dir, float *l1_out, cudaStream_t st, bool packed);   // quantize_literal.cu
+// Which implementation quantises the unbiased mode: 0 = l1_kernel + quantize_tiles_kernel (the product path),
+// 1 = literal_rows_kernel (tests: an independent implementation).  dme_set_unbiased_path.
 static int g_unbiased_path = 0;
 
 }  // namespace dme
@@ -409,30 +398,24 @@ static int quantize_common(const float *X, int64_t n, int64_t d, int64_t ld, int
         DME_REQUIRE(ld_out >= d, "ld_out=%lld < d", (long long)ld_out);
     }
     WsLayout L;
-    const int path = g_unbiased_path;
-    const bool old_path = mode == DME_MODE_BIASED || path >= 2;
-    rc = ws_prepare(ws, ws_bytes, n, d, st, &L, path != 1 || mode == DME_MODE_BIASED, mode == DME_MODE_BIASED, old_path);
+    const bool literal = mode == DME_MODE_UNBIASED && g_unbiased_path == 1;
+    rc = ws_prepare(ws, ws_bytes, n, d, st, &L, !literal, mode == DME_MODE_BIASED);
     if (rc) return rc;
     prof_reset();
     prof_mark(st);
-    if (!old_path) {
-        if (path == 0) rc = launch_quantize_fx(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, k_out, sgn_out, deq_out, ld_out, codes,
-                                               codes_bytes, dir, l1_out, st, packed);
-        else rc = launch_literal_rows(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, k_out, sgn_out, deq_out, ld_out, codes,
-                                      codes_bytes, dir, l1_out, st, packed, true);
+    if (literal) {
+        rc = launch_literal_rows(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, k_out, sgn_out, deq_out, ld_out, codes, codes_bytes,
+                                 dir, l1_out, st, packed);
         if (rc) return rc;
         prof_mark(st);
         return DME_OK;
     }
-    if (mode == DME_MODE_BIASED || path == 2) {
-        rc = launch_l1(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, l1_out, st);
-        if (rc) return rc;
-        if (mode != DME_MODE_BIASED) prof_mark(st);
-    }
+    rc = launch_l1(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, l1_out, st);
+    if (rc) return rc;
     if (mode == DME_MODE_BIASED)
         return biased_quantize(X, n, d, ld, m, L, ws, k_out, sgn_out, deq_out, ld_out, codes, codes_bytes, dir, st);
-    rc = launch_stream(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, k_out, sgn_out, deq_out, ld_out, codes, codes_bytes,
-                       dir, l1_out, st, packed);
+    prof_mark(st);
+    rc = launch_quantize_tiles(X, n, d, ld, m, L, ws, k_out, sgn_out, deq_out, ld_out, codes, codes_bytes, dir, st, packed);
     if (rc) return rc;
     prof_mark(st);
     return DME_OK;
@@ -476,7 +459,7 @@ extern "C" int dme_decode_mean(const void *codes, const uint64_t *dir, const flo
 }
 
 extern "C" int dme_set_unbiased_path(int path) {
-    DME_REQUIRE(path >= 0 && path <= 3, "path=%d unknown", path);
+    DME_REQUIRE(path == 0 || path == 1, "path=%d unknown", path);
     g_unbiased_path = path;
     return DME_OK;
 }

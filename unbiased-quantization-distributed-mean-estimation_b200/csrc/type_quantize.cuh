@@ -14,14 +14,12 @@ struct __align__(64) RowConst {
     float rcpD;  // RN(1 / D) for the Markstein division  x/D = fma(fma(-q0, D, x), rcp, q0), q0 = x*rcp
     uint32_t flags;      // kRowExact: use IEEE div / floorf (operands outside the proven range of the fast chain)
                          // kRowGuardFloor: mp may reach 2^23 -> per-thread check before the magic floor
-    int32_t qshift;      // (fp64 kernels) tile aggregates are exchanged as int64 fixed point with 2^-qshift resolution
-    uint32_t Xi;         // X * 2^32 (quantize_fx.cu: the uniform on the fixed-point grid)
+    int32_t qshift;      // tile aggregates are exchanged as int64 fixed point with 2^-qshift resolution
+    uint32_t pad0;
     double q_up, q_dn;   // 2^qshift, 2^-qshift
-    float mfs;           // float(m) * 2^32 (quantize_fx.cu: m |x| / D comes out scaled for the 64-bit conversion)
-    float pad2[3];
+    double pad1[2];
 };
 constexpr uint32_t kRowExact = 1u, kRowGuardFloor = 2u;
-constexpr uint32_t kRowExotic = 4u;    // outside the proven range of quantize_fx_kernel: left to literal_rows_kernel
 
 // Decoupled look-back record of one (client, tile).  state: 0 = nothing, 1 = aggregate valid,
 // 2 = aggregate + inclusive valid.  a_state: 1 = a_last valid.
@@ -42,7 +40,7 @@ struct __align__(256) WsHeader {
     uint32_t pad[59];
 };
 
-// Closed form of AS:636 inside one binade of the fp32 prefix (stream.cu): for c32 in [2^e + 1, 2^(e+1)),
+// Closed form of AS:636 inside one binade of the fp32 prefix (quantize_tiles.cu): for c32 in [2^e + 1, 2^(e+1)),
 // floor(RN32(RN32(c) - X)) = floor(c - Xp) when sigma = +1, ceil(c - Xp) - 1 when sigma = -1; sigma = 0: no closed form.
 struct __align__(16) BinadeEntry { double Xp; double sigma; };
 constexpr int kBinades = 24;
@@ -51,14 +49,12 @@ struct WsLayout {
     int64_t T;            // tiles per row
     int64_t off_done;     // uint32 a_done[n]
     int64_t off_ready;    // uint32 row_ready[n]
-    int64_t off_bins;     // uint64 bins[n][12]: per-row superaccumulator of |x| (quantize_fx.cu)
     int64_t off_consts;   // RowConst consts[n]
     int64_t off_partial;  // double partial[n*T]
     int64_t off_desc;     // look-back records: 16 bytes per tile, per block of 32 tiles, per super-block of 1024 tiles
     int64_t desc_bytes;
     int64_t off_sel;      // RowSelect sel[n] (biased mode)
-    int64_t off_tab;      // BinadeEntry tab[n][kBinades] (unbiased stream kernel: closed-form floor(c - X) per binade)
-    int64_t off_exotic;   // int32 exotic_rows[n]: rows left to literal_rows_kernel (their count is WsHeader::pad[1])
+    int64_t off_tab;      // BinadeEntry tab[n][kBinades] (quantize_tiles_kernel: closed-form floor(c - X) per binade)
     int64_t zero_bytes;   // prefix that must be zeroed before each call (header + a_done)
     int64_t total;
 };
@@ -93,10 +89,9 @@ inline WsLayout ws_layout(int64_t n, int64_t d) {
     int64_t o = (int64_t)sizeof(WsHeader);
     L.off_done = o; o = align_up(o + 4 * n, 256);
     L.off_ready = o; o = align_up(o + 4 * n, 256);
-    L.off_bins = o; o = align_up(o + 96 * n, 256);
     L.zero_bytes = o;
     L.off_consts = o; o = align_up(o + (int64_t)sizeof(RowConst) * n, 256);
-    L.off_partial = o; o = align_up(o + 16 * n * L.T, 256);     // 16-byte {sum, flag} records
+    L.off_partial = o; o = align_up(o + 8 * n * L.T, 256);
     {
         const int64_t TB = (L.T + 31) / 32, TS = (TB + 31) / 32;
         L.desc_bytes = 16 * n * (L.T + TB + TS);
@@ -104,7 +99,6 @@ inline WsLayout ws_layout(int64_t n, int64_t d) {
     L.off_desc = o; o = align_up(o + L.desc_bytes, 256);
     L.off_sel = o; o = align_up(o + (int64_t)sizeof(RowSelect) * n, 256);
     L.off_tab = o; o = align_up(o + (int64_t)sizeof(BinadeEntry) * kBinades * n, 256);
-    L.off_exotic = o; o = align_up(o + 4 * n, 256);
     L.total = o;
     return L;
 }
@@ -130,10 +124,10 @@ __device__ inline void make_row_const(const RowConstIn &a, int64_t c, double l1s
     int lg = 0;
     while (((int64_t)1 << lg) < a.d) ++lg;
     rc.qshift = min(50, 62 - lg);
-    rc.Xi = 0;
+    rc.pad0 = 0;
     rc.q_up = __longlong_as_double((long long)(1023 + rc.qshift) << 52);
     rc.q_dn = __longlong_as_double((long long)(1023 - rc.qshift) << 52);
-    rc.mfs = 0.0f; rc.pad2[0] = rc.pad2[1] = rc.pad2[2] = 0.0f;
+    rc.pad1[0] = rc.pad1[1] = 0.0;
     a.consts[c] = rc;
     BinadeEntry *tab = a.tabs + c * kBinades;
     const double Xd = (double)rc.X;

@@ -500,6 +500,45 @@ def irht(v, seed=0, *, diag_inject=None, per_row_seed=False):
     return V[0] if was_1d else V
 
 
+def rotated_type_quantize(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, client0=0, rotation_seed=123, x_inject=None,
+                          diag_inject=None):
+    """The rotated type quantizer of BASELINE config 3, per vector.  The reference has no such function: it is
+    the composition of its pieces, randomized_hadamard_transform (AS:127-144, one shared rotation_seed as AS:802) ->
+    Type_{un}biased_quantize on the dpad rotated coordinates (AS:609-641 / AS:669-687, m = int(table[R] * dpad)) ->
+    randomized_inverse_hadamard_transform (AS:151-156) -> [:d].  Returns the dequantised rows (n, d)."""
+    X, n, d, was_1d = _rows(x)
+    rot = rht(X, rotation_seed, diag_inject=diag_inject)
+    if rot.dim() == 1:
+        rot = rot.unsqueeze(0)
+    q = type_quantize(rot, bits_per_dimension, mode=mode, m=m, seed=seed, client0=client0, x_inject=x_inject, want=("deq",))["deq"]
+    if q.dim() == 1:
+        q = q.unsqueeze(0)
+    back = irht(q, rotation_seed, diag_inject=diag_inject)
+    if back.dim() == 1:
+        back = back.unsqueeze(0)
+    back = back[:, :d]
+    return back[0] if was_1d else back
+
+
+def rotated_quantize_mean(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, client0=0, n_total=None, rotation_seed=123,
+                          x_inject=None, diag_inject=None, out=None, check=True):
+    """Config 3 as a server would run it: every client rotates with the shared diagonal and sends its packed type code; the
+    server decodes and averages IN THE ROTATED DOMAIN and rotates the mean back once (the inverse rotation is linear, so this
+    is the mean of the per-client compositions up to the fp32 rounding of the last transform: one inverse transform instead of
+    n).  -> mean[d] (fp32, CUDA).  With rows sharded over GPUs, all-reduce the rotated mean before the inverse transform
+    (`rotated=True` returns it)."""
+    X, n, d, _ = _rows(x)
+    rot = rht(X, rotation_seed, diag_inject=diag_inject)
+    if rot.dim() == 1:
+        rot = rot.unsqueeze(0)
+    mean_rot = quantize_mean(rot, bits_per_dimension, mode=mode, m=m, seed=seed, client0=client0, n_total=n_total, x_inject=x_inject, check=check)
+    back = irht(mean_rot, rotation_seed, diag_inject=diag_inject)[:d]
+    if out is not None:
+        out.copy_(back)
+        return out
+    return back.contiguous()
+
+
 def pair_transform(v):
     """`fast_walsh_hadamard_transform` as the reference executes it (AS:37-59)."""
     V, n, d, was_1d = _rows(v)

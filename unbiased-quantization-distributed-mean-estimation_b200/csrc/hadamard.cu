@@ -7,8 +7,9 @@
 // keeps the stage ORDER and these two operations reproduces the reference bit for bit:
 //   fwht_contig_kernel : stages with distance 1 .. 2048 on contiguous 4096-blocks, radix-16 in registers, two
 //                        shared-memory transposes (padded, conflict-free)
-//   fwht_strided_kernel: 4 further stages per pass (distance 2^s .. 2^(s+3)), 16 strided elements per thread,
-//                        warp-coalesced columns
+//   fwht_strided_wide_kernel: 5 to 8 further stages per pass (distance 2^s .. 2^(s+P-1)) on tiles of 2^P strided rows x
+//                        4096 / 2^P contiguous columns, one shared-memory transpose
+//   fwht_strided_kernel: up to 4 further stages (what is left when fewer than 5 remain), 16 strided elements per thread
 // The +-1 diagonal, the zero padding and the final 1/sqrt(d) are fused into the first load / last store.
 #include <cmath>
 
@@ -202,6 +203,74 @@ __global__ void __launch_bounds__(256) fwht_strided_kernel(FwhtIo io, int64_t n,
     }
 }
 
+// P = 5..8 stages with distance 2^s .. 2^(s+P-1), s >= 12, in place on dst: one CTA = a tile of 2^P strided rows x C = 4096 / 2^P
+// consecutive columns (C * 4 >= 64 contiguous bytes per row: coalesced), 16 elements per thread: the first four stages in
+// registers, one shared-memory transpose, the remaining P - 4 stages in registers again.  Same stage order and butterfly as
+// AS:105-112: bit-exact.  With this pass the transform of d = 2^20 takes 2 passes over memory and d = 2^24 takes 3.
+template <int P>
+__global__ void __launch_bounds__(256) fwht_strided_wide_kernel(FwhtIo io, int64_t n, int s) {
+    constexpr int R = 1 << P, C = 4096 / R, J = R / 16, K = 16 / J;
+    constexpr int kStride = C + (C == 16 ? 1 : 0);          // C = 16: two rows per warp land in different bank halves
+    __shared__ float sm[R * kStride];
+    const int t = threadIdx.x, col_l = t % C, q = t / C;
+    const int64_t tiles_per_row = io.d >> 12;
+    const int64_t row = blockIdx.x / tiles_per_row, w = blockIdx.x - row * tiles_per_row;
+    const int64_t cblocks = ((int64_t)1 << s) / C;          // column blocks inside one 2^s run
+    const int64_t hi = w / cblocks, col0 = (w - hi * cblocks) * C;
+    float *base = io.dst + row * io.dst_ld + (hi << (s + P)) + col0 + col_l;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = base[(int64_t)(q * 16 + j) << s];
+    reg_stages<4>(v, 4);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sm[(q * 16 + j) * kStride + col_l] = v[j];
+    __syncthreads();
+    // v[k * J + j2] = element r = j2 * 16 + (q * K + k)
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int j2 = 0; j2 < J; ++j2) v[k * J + j2] = sm[(j2 * 16 + q * K + k) * kStride + col_l];
+#pragma unroll
+    for (int b = 0; b < P - 4; ++b)
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (!((i % J) & (1 << b))) bfly(v[i], v[i | (1 << b)]);
+    if (io.finalize) {
+        // Philox diagonal: the columns of a warp's row segment share one 32-bit word of one block, so lane e computes the word
+        // of element e once and the warp passes it around
+        uint32_t myword = 0;
+        const bool philox = io.post_diag && io.diag == nullptr;
+        if (philox) {
+            const int e = (t & 15), k = e / J, j2 = e % J;
+            const int64_t col = (hi << (s + P)) + ((int64_t)(j2 * 16 + q * K + k) << s) + col0 + col_l;
+            const uint64_t blk = (uint64_t)col >> 7;
+            const Philox4 ph = philox4x32_10(io.seed + (uint64_t)row * io.seed_stride, (uint32_t)blk, (uint32_t)(blk >> 32), 0u, kStreamDiag);
+            const int wi = (int)((col >> 5) & 3);
+            myword = wi == 0 ? ph.x : wi == 1 ? ph.y : wi == 2 ? ph.z : ph.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int k = i / J, j2 = i % J;
+            const int64_t col = (hi << (s + P)) + ((int64_t)(j2 * 16 + q * K + k) << s) + col0 + col_l;
+            float y = __fdiv_rn(v[i], io.sq);                                        // AS:113
+            if (io.post_diag) {                                                      // AS:154
+                float sg;
+                if (philox) {
+                    const uint32_t word = __shfl_sync(0xffffffffu, myword, (t & 16) | i);
+                    sg = ((word >> (col & 31)) & 1u) ? 1.0f : -1.0f;
+                } else sg = io.diag[col];
+                y = __fmul_rn(y, sg);
+            }
+            v[i] = y;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int k = i / J, j2 = i % J;
+        base[(int64_t)(j2 * 16 + q * K + k) << s] = v[i];
+    }
+}
+
 __global__ void rademacher_kernel(float *out, int64_t d, uint64_t seed) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < d) out[i] = philox_sign(seed, (uint64_t)i, kStreamDiag);
@@ -242,12 +311,28 @@ int fwht_rows(const float *src, int64_t src_d, int64_t src_ld, float *dst, int64
     fwht_contig_kernel<<<(unsigned)blocks, 256, 0, st>>>(io, n, logL);
     DME_LAUNCH_CHECK("fwht_contig_kernel");
     io.src = dst; io.src_d = d; io.src_ld = dst_ld; io.pre_diag = 0;
-    for (int s = 12; s < logd; s += 4) {
-        const int p = (logd - s) < 4 ? (logd - s) : 4;
+    // the remaining logd - 12 stages: one pass of up to 8 stages (two for more than 8), so d <= 2^20 takes 2 passes over
+    // memory and d <= 2^28 takes 3
+    int s = 12;
+    while (s < logd) {
+        const int rem = logd - s;
+        const int p = rem <= 8 ? rem : (rem <= 16 ? (rem + 1) / 2 : 8);
         io.finalize = (s + p >= logd);
-        const int64_t threads = n * (d >> p);
-        fwht_strided_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(io, n, s, p);
-        DME_LAUNCH_CHECK("fwht_strided_kernel");
+        if (p >= 5) {
+            const unsigned grid = (unsigned)(n * (d >> 12));
+            switch (p) {
+                case 5: fwht_strided_wide_kernel<5><<<grid, 256, 0, st>>>(io, n, s); break;
+                case 6: fwht_strided_wide_kernel<6><<<grid, 256, 0, st>>>(io, n, s); break;
+                case 7: fwht_strided_wide_kernel<7><<<grid, 256, 0, st>>>(io, n, s); break;
+                default: fwht_strided_wide_kernel<8><<<grid, 256, 0, st>>>(io, n, s); break;
+            }
+            DME_LAUNCH_CHECK("fwht_strided_wide_kernel");
+        } else {
+            const int64_t threads = n * (d >> p);
+            fwht_strided_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(io, n, s, p);
+            DME_LAUNCH_CHECK("fwht_strided_kernel");
+        }
+        s += p;
     }
     return DME_OK;
 }

@@ -1,17 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- the reference's headline metric on B200: fused quantize -> decode -> mean throughput (coords/s)
-of the unbiased type quantizer at d = 2^24, n = 128 clients per GPU (BASELINE.json `metric`).
+of the type quantizer (BASELINE.json `metric`), on the named workloads of BASELINE.json `configs`.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--d D] [--n N] [--rate R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload metric|cfg2|cfg3|cfg4|biased]
+                    [--d D] [--n N] [--rate R] [--mode unbiased|biased]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
+  --workload metric (default): d = 2^24, n = 128 clients per GPU, R = 1, unbiased -- the shape BASELINE.json's metric is quoted on
+             cfg2 : d = 2^16, n = 1000 (the largest point of the NMSE sweep)
+             cfg3 : rotated variant, d = 2^20, n = 128: randomized Hadamard -> type quantizer -> mean in the rotated domain -> inverse
+             cfg4 : Flower hook shape, d = 122 626 (the reference's CIFAR-10 CNN, TU:40-49), n = 100 client deltas
+             biased: the metric shape with the biased (Reznik) quantizer
 One "step" = one pass of the hot path over one batch of synthetic client vectors resident in HBM
 (N(0,1) i.i.d., torch.Generator seed 42 + rank).  Rank 0 prints ONE JSON line.
   value     : whole-job coords/s = N_gpus * n * d * K / (max-over-ranks device time), inputs in HBM
   e2e       : same metric through the public host-buffer call (pinned host rows -> H2D -> fused path -> D2H of the mean)
-  roofline  : dominant kernel (persistent L1+scan+quantize+pack), algorithmic bytes 4*n*d + 4*d per launch / its CUDA-event time,
-              against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline : oracle port (oracle/dme_oracle.c, pthreads over clients) on the box's host cores, bounded sample
+  roofline  : dominant kernel by per-kernel CUDA events (dme_profile_*), algorithmic bytes 4*n*d + 4*d of the step / its time,
+              against MEASURED_PEAKS.json hbm_gbs; kernel_ms lists every kernel of the step
+  cpu_baseline : oracle port (oracle/dme_oracle.c) on the box's host cores, bounded sample
 --impl reference times that CPU port alone (the reference is pure Python/torch and cannot travel to the GPU box).
 """
 from __future__ import annotations
@@ -21,7 +27,6 @@ import json
 import os
 import subprocess
 import sys
-import tempfile
 import threading
 import time
 
@@ -30,8 +35,15 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-METRIC = "quantize+decode+mean coords/s (unbiased type quantizer, R=1)"
 UNIT = "coords/s"
+L2_BYTES = 256 << 20          # inputs smaller than this are rotated over several copies so that no step re-reads a cached input
+WORKLOADS = {
+    "metric": dict(d=1 << 24, n=128, rate=1, mode="unbiased", kind="type"),
+    "cfg2": dict(d=1 << 16, n=1000, rate=1, mode="unbiased", kind="type"),
+    "cfg3": dict(d=1 << 20, n=128, rate=1, mode="unbiased", kind="rotated"),
+    "cfg4": dict(d=122626, n=100, rate=1, mode="unbiased", kind="type"),
+    "biased": dict(d=1 << 24, n=128, rate=1, mode="biased", kind="type"),
+}
 
 
 def parse():
@@ -40,19 +52,32 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--d", type=int, default=1 << 24)
-    ap.add_argument("--n", type=int, default=128, help="clients per GPU")
-    ap.add_argument("--rate", type=float, default=1)
-    ap.add_argument("--mode", default="unbiased", choices=["unbiased", "biased"])
+    ap.add_argument("--workload", default="metric", choices=sorted(WORKLOADS))
+    ap.add_argument("--d", type=int, default=None)
+    ap.add_argument("--n", type=int, default=None, help="clients per GPU")
+    ap.add_argument("--rate", type=float, default=None)
+    ap.add_argument("--mode", default=None, choices=["unbiased", "biased"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    return ap.parse_args()
+    a = ap.parse_args()
+    w = WORKLOADS[a.workload]
+    a.kind = w["kind"]
+    for k in ("d", "n", "rate", "mode"):
+        if getattr(a, k) is None:
+            setattr(a, k, w[k])
+    return a
+
+
+def metric_name(a):
+    q = "rotated type quantizer" if a.kind == "rotated" else f"{a.mode} type quantizer"
+    return f"quantize+decode+mean coords/s ({q}, R={a.rate:g})"
 
 
 def workload_name(a):
-    return f"type_{a.mode} R={a.rate:g} d={a.d} n={a.n}/gpu N(0,1) synthetic"
+    rot = "rotated (RHT -> type -> mean -> inverse) " if a.kind == "rotated" else ""
+    return f"{a.workload}: {rot}type_{a.mode} R={a.rate:g} d={a.d} n={a.n}/gpu N(0,1) synthetic"
 
 
 def rate_key(r):
@@ -61,29 +86,49 @@ def rate_key(r):
 
 # ------------------------------------------------------------------ CPU arm (oracle port; the checker, timed)
 def cpu_arm(a, steps, warmup, budget_s):
-    """Times the oracle's quantize->dequantize->mean loop (ND:133-147 with Type_unbiased_quantize) on host cores.
-    Sample: `cores` clients (at most a.n) of the full length d per step."""
+    """Times the oracle's quantize->dequantize->mean loop (ND:133-147) on host cores.  Unbiased type quantizer: the C port with one
+    pthread per core, `cores` clients of the full length d per step.  Rotated / biased: the port's single-threaded pieces driven
+    from Python, a few clients per step."""
     from oracle import oracle as orc
     cores = os.cpu_count() or 1
     d = a.d
-    ns = max(1, min(a.n, cores))
     rng = np.random.default_rng(42)
-    X = rng.standard_normal((ns, d), dtype=np.float32)
-    Xs = rng.random(ns, dtype=np.float32)
-    m = orc.m_for(rate_key(a.rate), d)
+    R = rate_key(a.rate)
+    if a.kind == "type" and a.mode == "unbiased":
+        ns = max(1, min(a.n, cores))
+        X = rng.standard_normal((ns, d), dtype=np.float32)
+        Xs = rng.random(ns, dtype=np.float32)
+        m = orc.m_for(R, d)
+        fn = lambda: orc.quantize_mean_unbiased(X, m, Xs, threads=cores)
+        used, what = cores, f"oracle/dme_oracle.c with {cores} pthreads"
+    else:
+        ns = max(1, min(a.n, 2 if d >= (1 << 22) else 4))
+        X = rng.standard_normal((ns, d), dtype=np.float32)
+        Xs = rng.random(ns, dtype=np.float32)
+        dpad = orc.pad_pow2(d)
+        diag = np.where(rng.random(dpad) < 0.5, -1.0, 1.0).astype(np.float32)
+        if a.kind == "rotated":
+            m = orc.m_for(R, dpad)
+            def fn():
+                qs = [orc.type_unbiased(orc.rht(X[c], diag), m, float(Xs[c]))["deq"] for c in range(ns)]
+                return orc.irht(orc.mean_of(qs), diag)[:d]
+        else:
+            m = orc.m_for(R, d)
+            fn = lambda: orc.mean_of([orc.type_biased(X[c], m)["deq"] for c in range(ns)])
+        used, what = 1, "oracle/dme_oracle.c pieces driven from Python, 1 thread"
     times = []
     t_start = time.perf_counter()
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        orc.quantize_mean_unbiased(X, m, Xs, threads=cores)
+        fn()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
         if budget_s and time.perf_counter() - t_start > budget_s and len(times) >= 1:
             break
     t = float(np.mean(times))
-    return {"value": ns * d / t, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{ns} clients x d={d} per step, {len(times)} timed steps, oracle/dme_oracle.c with {cores} pthreads",
+    return {"value": ns * d / t, "unit": UNIT, "cores": used, "kind": "port",
+            "sample": f"{ns} clients x d={d} per step, {len(times)} timed steps, {what}",
             "ms_per_step": t * 1e3, "steps": len(times)}
 
 
@@ -93,7 +138,7 @@ def run_reference(a):
         return
     steps, warmup = max(1, min(a.steps, 5)), max(1, min(a.warmup, 1))
     cb = cpu_arm(a, steps, warmup, budget_s=150.0)
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": cb["steps"],
+    line = {"impl": "reference", "metric": metric_name(a), "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": cb["steps"],
             "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32+f64acc", "data": "synthetic", "config": {"workload": workload_name(a), "sample": cb["sample"]},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -171,20 +216,30 @@ def run_ours(a):
     n_total = n * world
     client0 = rank * n
     gen = torch.Generator(device=dev).manual_seed(42 + rank)
-    X = torch.empty((n, d), dtype=torch.float32, device=dev)
-    for c in range(n):                                   # row by row: keeps the generator's scratch small
-        X[c].normal_(generator=gen)
+    copies = max(1, -(-L2_BYTES // (4 * n * d)))          # small inputs: rotate over enough copies to defeat L2
+    Xs = []
+    for k in range(copies):
+        X = torch.empty((n, d), dtype=torch.float32, device=dev)
+        for c in range(n):                                   # row by row: keeps the generator's scratch small
+            X[c].normal_(generator=gen)
+        Xs.append(X)
     mean = torch.empty(d, dtype=torch.float32, device=dev)
     L = _cabi.lib()
 
     from dme_b200 import distributed as dmed
 
+    def local_type(x, r, **kw):
+        return dme.quantize_mean(x, r, check=False, **kw)
+
     def step(i):
-        # N > 1: every rank quantizes + decodes its own clients with the global divisor, then ONE all-reduce.
-        # (dmed.quantize_mean_overlapped, which all-reduces finished slices of the mean while later ones are decoded, was
-        # measured at N = 2: 5.24-5.30 ms vs 5.22 ms -- the 0.4 ms decode is too short to hide anything behind.)
-        dmed.quantize_mean_sharded(X, R, n_total=n_total, client0=client0, seed=1234 + i, mode=a.mode, out=mean,
-                                   local_fn=lambda x, r, **kw: dme.quantize_mean(x, r, check=False, **kw))
+        X = Xs[i % copies]
+        if a.kind == "rotated":
+            # every rank rotates its clients, averages them in the rotated domain with the global divisor, ONE all-reduce of the
+            # rotated partial mean, then the single inverse rotation (linear) on every rank
+            dmed.rotated_quantize_mean_sharded(X, R, n_total=n_total, client0=client0, seed=1234 + i, mode=a.mode, out=mean)
+        else:
+            # N > 1: every rank quantizes + decodes its own clients with the global divisor, then ONE all-reduce
+            dmed.quantize_mean_sharded(X, R, n_total=n_total, client0=client0, seed=1234 + i, mode=a.mode, out=mean, local_fn=local_type)
 
     def sync():
         if world > 1:
@@ -219,33 +274,24 @@ def run_ours(a):
     # ---- roofline leg: per-kernel CUDA-event times (events on the launching stream), outside the timed region
     peak, peak_src = peaks()
     B_alg = 4.0 * n * d + 4.0 * d
-    L.dme_profile_enable(1)
-    per = []
-    for i in range(5):
-        step(1000 + i)
-        buf = (C.c_float * 8)()
-        k = L.dme_profile_read(buf, 8)
-        per.append([buf[j] for j in range(k)])
-    L.dme_profile_enable(0)
-    per = np.array(per[1:])
-    kern_ms = per.mean(axis=0) if per.size else np.array([ms_step])
-    if len(kern_ms) >= 3:      # default path: l1_kernel -> quantize_tiles_kernel -> decode_mean_kernel (one launch per slice when N > 1)
-        names = ["l1_kernel", "quantize_tiles_kernel", "decode_mean_kernel"]
-        kern_ms = np.array([kern_ms[0], kern_ms[1], kern_ms[2:].sum()])
-    else:
-        names = ["quantize", "decode_mean_kernel"][: len(kern_ms)]
-    dom = int(np.argmax(kern_ms))
+    runs = [dme.profile_kernels(lambda: step(1000 + j), warm=0) for j in range(4)][1:]
+    kern_ms = {}
+    for run in runs:
+        for name, t_ms in run:
+            kern_ms[name] = kern_ms.get(name, 0.0) + t_ms / len(runs)
+    dom = max(kern_ms, key=kern_ms.get) if kern_ms else "step"
+    dom_ms = kern_ms.get(dom, ms_step)
     # algorithmic bytes of one step (every input coordinate read once, the mean written once) over the
-    # duration of the dominant kernel's launch; the whole step against the same bytes is step_achieved
-    ach = B_alg / (kern_ms[dom] * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    # time the dominant kernel takes per step; the whole step against the same bytes is step_achieved
+    ach = B_alg / (dom_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": B_alg,
-            "kernel_ms": {nm: float(v) for nm, v in zip(names, kern_ms)},
+            "kernel_ms": {nm: float(v) for nm, v in sorted(kern_ms.items(), key=lambda kv: -kv[1])},
             "step_achieved": B_alg / (ms_step * 1e-3) / 1e9, "step_frac": B_alg / (ms_step * 1e-3) / 1e9 / peak}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            roof["traffic"] = json.load(open(tr)).get(names[dom])
+            roof["traffic"] = json.load(open(tr)).get(a.workload, {}).get(dom)
         except Exception:
             pass
 
@@ -254,14 +300,25 @@ def run_ours(a):
     if not a.no_e2e:
         try:
             Xh = torch.empty((n, d), dtype=torch.float32, pin_memory=True)
-            Xh.copy_(X)
+            Xh.copy_(Xs[0])
             outh = torch.empty(d, dtype=torch.float32, pin_memory=True)
             red = (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)) if world > 1 else None
-            def e2e_step(i):
-                # the public host-buffer API: chunked H2D on a copy stream overlapped with quantize + decode of the previous
-                # chunk, the all-reduce of the partial mean (N > 1), D2H of the mean, stream synchronize
-                dme.quantize_mean_host(Xh, R, out_host=outh, mode=a.mode, seed=77 + i, client0=client0, n_total=n_total,
-                                       check=False, reduce_fn=red)
+            if a.kind == "rotated":
+                stage = torch.empty((n, d), dtype=torch.float32, device=dev)
+                def e2e_step(i):
+                    # pinned host rows -> device, the rotated fused path, all-reduce (N > 1), D2H of the mean, stream synchronize
+                    stage.copy_(Xh, non_blocking=True)
+                    dmed.rotated_quantize_mean_sharded(stage, R, n_total=n_total, client0=client0, seed=77 + i, mode=a.mode, out=mean)
+                    outh.copy_(mean, non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+                api_name = "dme_b200.distributed.rotated_quantize_mean_sharded on rows copied from pinned host memory, D2H of the mean"
+            else:
+                def e2e_step(i):
+                    # the public host-buffer API: chunked H2D on a copy stream overlapped with quantize + decode of the previous
+                    # chunk, the all-reduce of the partial mean (N > 1), D2H of the mean, stream synchronize
+                    dme.quantize_mean_host(Xh, R, out_host=outh, mode=a.mode, seed=77 + i, client0=client0, n_total=n_total,
+                                           check=False, reduce_fn=red)
+                api_name = "dme_b200.quantize_mean_host on pinned host rows (chunked H2D overlapped with the fused path, D2H of the mean)"
             e2e_step(0)
             sync()
             t0 = time.perf_counter()
@@ -277,7 +334,7 @@ def run_ours(a):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 ems = float(t.item())
             e2e = {"value": n_total * d / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(4 * n * d), "d2h_bytes_per_step": int(4 * d),
-                   "ms_per_step": ems, "steps": a.e2e_steps, "api": "dme_b200.quantize_mean_host on pinned host rows (chunked H2D overlapped with the fused path, D2H of the mean)"}
+                   "ms_per_step": ems, "steps": a.e2e_steps, "api": api_name}
             del Xh
         except Exception as ex:  # pinned allocation can fail on a small host
             e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
@@ -288,10 +345,13 @@ def run_ours(a):
         cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step,
+        hyg = (f"inputs ({4 * n * d / 2**30:.2f} GiB/GPU) larger than L2; no flush needed" if copies == 1 else
+               f"inputs ({4 * n * d / 2**20:.0f} MiB/GPU) rotated over {copies} copies ({copies * 4 * n * d / 2**20:.0f} MiB > L2)")
+        mm = dme.m_for_rate(R, (1 << (d - 1).bit_length()) if a.kind == "rotated" else d)
+        line = {"metric": metric_name(a), "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 accumulate)", "data": "synthetic",
-                "config": {"workload": workload_name(a), "clients_total": n_total, "m": dme.m_for_rate(R, d), "parallelism": f"clients sharded x{world}",
-                           "l2_hygiene": f"inputs ({4 * n * d / 2**30:.1f} GiB/GPU) larger than L2; no flush needed"},
+                "config": {"workload": workload_name(a), "clients_total": n_total, "m": mm, "parallelism": f"clients sharded x{world}",
+                           "l2_hygiene": hyg},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "e2e": e2e, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

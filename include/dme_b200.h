@@ -63,14 +63,16 @@ DME_API int dme_version(void);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 DME_API int64_t dme_launch_count(void);
 
-/* Per-kernel timing of the type-quantizer path with CUDA events on the caller's stream (bench.py's roofline leg;
- * keep it off inside timed regions).  dme_profile_read returns the number of intervals written: for
- * dme_quantize_mean they are {L1 reduce, scan/quantize/pack, decode+mean} in milliseconds. */
-DME_API int dme_profile_enable(int on);
+/* Per-kernel timing (bench.py's roofline leg; keep it off inside timed regions; one caller thread).  While enabled, the
+ * library records a CUDA event on `stream` after every kernel it launches; dme_profile_read returns, for the calls made
+ * since dme_profile_enable(1, stream), the duration of each kernel in launch order (milliseconds) and dme_profile_name(i)
+ * the kernel's name. */
+DME_API int dme_profile_enable(int on, dme_stream_t stream);
+DME_API int dme_profile_read(float *ms, int cap);
+DME_API const char *dme_profile_name(int i);
 /* Test hook: which implementation runs the unbiased mode.  0 (default) = l1_kernel + quantize_tiles_kernel (the product path);
  * 1 = literal_rows_kernel (AS:625-637 as written, one CTA per row: an independent implementation for the parity tests). */
 DME_API int dme_set_unbiased_path(int path);
-DME_API int dme_profile_read(float *ms, int cap);
 
 /* X_c, the single uniform of client c (AS:634): Philox4x32-10, key = seed, counter = (client, 0, 0, 0x584D44),
  * top 24 bits -> [0,1).  Host-side helper so callers/tests can reproduce the draws. */

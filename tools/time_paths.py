@@ -15,12 +15,5 @@ X = torch.randn((n, d), device="cuda")
 out = torch.empty(d, device="cuda")
 for path in sys.argv[2:] or ["fx", "tiles"]:
     dme.set_unbiased_path(path)
-    res = []
-    for i in range(4):
-        L.dme_profile_enable(1)
-        dme.quantize_mean(X, 1, seed=i, out=out, check=False)
-        buf = (C.c_float * 8)()
-        k = L.dme_profile_read(buf, 8)
-        L.dme_profile_enable(0)
-        res.append([round(buf[j], 3) for j in range(k)])
-    print(path, n, d, res[1:], flush=True)
+    res = [dme.profile_kernels(lambda: dme.quantize_mean(X, 1, seed=i, out=out, check=False), warm=0) for i in range(4)]
+    print(path, n, d, [[(nm, round(t, 3)) for nm, t in r] for r in res[2:]], flush=True)

@@ -14,8 +14,9 @@ SIGNATURES = {
     "dme_last_error": (C.c_char_p, []),
     "dme_version": (ci, []),
     "dme_launch_count": (i64, []),
-    "dme_profile_enable": (ci, [ci]),
+    "dme_profile_enable": (ci, [ci, vp]),
     "dme_profile_read": (ci, [vp, ci]),
+    "dme_profile_name": (C.c_char_p, [ci]),
     "dme_set_unbiased_path": (ci, [ci]),
     "dme_uniform_x": (cf, [u64, u64]),
     "dme_workspace_bytes": (i64, [i64, i64]),

@@ -128,6 +128,22 @@ def set_unbiased_path(path) -> None:
     _check(_cabi.lib().dme_set_unbiased_path(UNBIASED_PATHS.get(path, path)))
 
 
+def profile_kernels(fn, *, warm=1):
+    """Run fn() with per-kernel CUDA events on the current stream -> [(kernel name, ms), ...] in launch order
+    (dme_profile_enable / dme_profile_read; bench.py's roofline leg -- not for use inside a timed region)."""
+    L = _cabi.lib()
+    for _ in range(warm):
+        fn()
+    _check(L.dme_profile_enable(1, C.c_void_p(_stream())))
+    try:
+        fn()
+        buf = (C.c_float * 96)()
+        k = L.dme_profile_read(buf, 96)
+        return [((L.dme_profile_name(i) or b"").decode(), float(buf[i])) for i in range(k)]
+    finally:
+        L.dme_profile_enable(0, None)
+
+
 def client_uniforms(seed: int, client0: int, n: int) -> np.ndarray:
     """X_c for clients client0 .. client0+n-1: the same Philox draw the kernels make (AS:634)."""
     L = _cabi.lib()

@@ -22,6 +22,18 @@ int cuda_fail(cudaError_t e, const char *what) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Optional per-kernel timing (bench.py's roofline leg): while enabled, a CUDA event is recorded on the profiled stream after
+// every kernel launch of the library (DME_LAUNCH_CHECK); interval i is kernel i of the calls made since dme_profile_enable.
+// Off by default; never enabled inside a timed region; one caller thread.
+constexpr int kProfMax = 96;
+struct Profile { bool on = false; bool have = false; cudaStream_t st = nullptr; int marks = 0; cudaEvent_t ev[kProfMax + 1]; const char *name[kProfMax]; };
+static Profile g_prof;
+void prof_launch(const char *name) {
+    if (!g_prof.on || g_prof.marks >= kProfMax) return;
+    g_prof.name[g_prof.marks] = name;
+    cudaEventRecord(g_prof.ev[++g_prof.marks], g_prof.st);
+}
+
 }  // namespace dme
 
 using namespace dme;
@@ -48,3 +60,23 @@ extern "C" int64_t dme_codes_bytes(int64_t n, int64_t d, int64_t m, int expect) 
     const int64_t overflow = expect ? (n * T * 512 * (w0 < 32 ? 2 * w0 : 0)) / 4 + 65536 : n * T * 512 * 32;
     return primary + overflow + 4096;
 }
+
+extern "C" int dme_profile_enable(int on, dme_stream_t stream) {
+    if (on && !g_prof.have) {
+        for (auto &e : g_prof.ev) DME_CUDA(cudaEventCreate(&e));
+        g_prof.have = true;
+    }
+    g_prof.on = on != 0; g_prof.st = (cudaStream_t)stream; g_prof.marks = 0;
+    if (on) DME_CUDA(cudaEventRecord(g_prof.ev[0], g_prof.st));
+    return DME_OK;
+}
+extern "C" int dme_profile_read(float *ms, int cap) {
+    DME_REQUIRE(ms != nullptr && cap >= 1, "bad argument");
+    int k = 0;
+    for (; k < g_prof.marks && k < cap; ++k) {
+        DME_CUDA(cudaEventSynchronize(g_prof.ev[k + 1]));
+        DME_CUDA(cudaEventElapsedTime(&ms[k], g_prof.ev[k], g_prof.ev[k + 1]));
+    }
+    return k;
+}
+extern "C" const char *dme_profile_name(int i) { return (i >= 0 && i < g_prof.marks) ? g_prof.name[i] : ""; }

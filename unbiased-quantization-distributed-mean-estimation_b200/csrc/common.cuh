@@ -16,6 +16,7 @@ constexpr int kWarps = kThreads / 32;
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
 void count_launch(int n = 1);
+void prof_launch(const char *name);      // cabi.cu: per-kernel CUDA events while dme_profile_enable is on
 #define DME_CUDA(expr)                                             \
     do {                                                           \
         cudaError_t _e = (expr);                                   \
@@ -31,6 +32,7 @@ void count_launch(int n = 1);
 #define DME_LAUNCH_CHECK(name)                                          \
     do {                                                                \
         ::dme::count_launch();                                          \
+        ::dme::prof_launch(name);                                       \
         cudaError_t _e = cudaGetLastError();                            \
         if (_e != cudaSuccess) return ::dme::cuda_fail(_e, "launch " name); \
     } while (0)

@@ -81,12 +81,12 @@ l1_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t m, int64_t
     double acc = 0.0;
     for (int64_t i = threadIdx.x; i < T; i += kThreads) acc += pp[i];
     acc = block_sum_f64(acc, s_red);
-    if (threadIdx.x == 0) {
-        RowConstIn in;
-        in.m = m; in.d = d; in.x_inject = x_inject; in.l1_inject = l1_inject; in.seed = seed; in.client0 = client0;
-        in.consts = consts; in.tabs = tabs; in.l1_out = l1_out;
-        make_row_const(in, c, acc);
-    }
+    RowConstIn in;
+    in.m = m; in.d = d; in.x_inject = x_inject; in.l1_inject = l1_inject; in.seed = seed; in.client0 = client0;
+    in.consts = consts; in.tabs = tabs; in.l1_out = l1_out;
+    if (threadIdx.x == 0) make_row_const(in, c, acc);
+    __syncthreads();
+    if (threadIdx.x < kBinades) make_binade_entry(in, c, (int)threadIdx.x);      // the table in parallel: short rows are bound by this tail
 }
 
 // ------------------------------------------------------------------ K7: decode + mean (tile-major)
@@ -304,17 +304,6 @@ __global__ void mean_accumulate_kernel(const float *__restrict__ Q, int64_t n, i
 }
 
 // ------------------------------------------------------------------ host side
-// Optional per-kernel timing (bench.py's roofline leg): CUDA events recorded on the caller's stream around each
-// kernel of the type-quantizer path.  Off by default; never enabled inside a timed region.
-struct Profile { bool on = false; cudaEvent_t ev[8]; bool have = false; int marks = 0; };
-static Profile g_prof;
-static void prof_mark(cudaStream_t st) {
-    if (!g_prof.on) return;
-    if (!g_prof.have) { for (auto &e : g_prof.ev) cudaEventCreate(&e); g_prof.have = true; }
-    if (g_prof.marks < 8) cudaEventRecord(g_prof.ev[g_prof.marks++], st);
-}
-static void prof_reset() { g_prof.marks = 0; }
-
 static int check_rows(const void *X, int64_t n, int64_t d, int64_t ld) {
     DME_REQUIRE(X != nullptr, "X is null");
     DME_REQUIRE(n >= 1 && n <= 65535, "n=%lld out of range [1, 65535]", (long long)n);
@@ -401,23 +390,18 @@ static int quantize_common(const float *X, int64_t n, int64_t d, int64_t ld, int
     const bool literal = mode == DME_MODE_UNBIASED && g_unbiased_path == 1;
     rc = ws_prepare(ws, ws_bytes, n, d, st, &L, !literal, mode == DME_MODE_BIASED);
     if (rc) return rc;
-    prof_reset();
-    prof_mark(st);
     if (literal) {
         rc = launch_literal_rows(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, k_out, sgn_out, deq_out, ld_out, codes, codes_bytes,
                                  dir, l1_out, st, packed);
         if (rc) return rc;
-        prof_mark(st);
-        return DME_OK;
+            return DME_OK;
     }
     rc = launch_l1(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, l1_out, st);
     if (rc) return rc;
     if (mode == DME_MODE_BIASED)
         return biased_quantize(X, n, d, ld, m, L, ws, k_out, sgn_out, deq_out, ld_out, codes, codes_bytes, dir, st);
-    prof_mark(st);
     rc = launch_quantize_tiles(X, n, d, ld, m, L, ws, k_out, sgn_out, deq_out, ld_out, codes, codes_bytes, dir, st, packed);
     if (rc) return rc;
-    prof_mark(st);
     return DME_OK;
 }
 
@@ -449,7 +433,6 @@ extern "C" int dme_decode_mean_tiles(const void *codes, const uint64_t *dir, con
             (const uint32_t *)codes, dir, l1, n, d, T, (float)m, (float)n_total, mode == DME_MODE_BIASED, mean, accumulate, tile0);
         DME_LAUNCH_CHECK("decode_mean_kernel");
     }
-    prof_mark((cudaStream_t)stream);
     return DME_OK;
 }
 
@@ -462,18 +445,6 @@ extern "C" int dme_set_unbiased_path(int path) {
     DME_REQUIRE(path == 0 || path == 1, "path=%d unknown", path);
     g_unbiased_path = path;
     return DME_OK;
-}
-
-extern "C" int dme_profile_enable(int on) { g_prof.on = on != 0; prof_reset(); return DME_OK; }
-// ms[i] = time between mark i and mark i+1 of the last profiled call (l1, scan, decode for dme_quantize_mean).
-extern "C" int dme_profile_read(float *ms, int cap) {
-    DME_REQUIRE(ms != nullptr && cap >= 1, "bad argument");
-    int k = 0;
-    for (; k + 1 < g_prof.marks && k < cap; ++k) {
-        DME_CUDA(cudaEventSynchronize(g_prof.ev[k + 1]));
-        DME_CUDA(cudaEventElapsedTime(&ms[k], g_prof.ev[k], g_prof.ev[k + 1]));
-    }
-    return k;
 }
 
 extern "C" int dme_quantize_mean(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, int mode, const float *x_inject,

@@ -129,20 +129,20 @@ __device__ inline void make_row_const(const RowConstIn &a, int64_t c, double l1s
     rc.q_dn = __longlong_as_double((long long)(1023 - rc.qshift) << 52);
     rc.pad1[0] = rc.pad1[1] = 0.0;
     a.consts[c] = rc;
-    BinadeEntry *tab = a.tabs + c * kBinades;
-    const double Xd = (double)rc.X;
-#pragma unroll 1
-    for (int e = 0; e < kBinades; ++e) {
-        BinadeEntry b; b.Xp = 0.0; b.sigma = 0.0;
-        if (!(fl & kRowExact) && e >= 2 && e <= 22) {
-            const double g = __longlong_as_double((long long)(1023 + e - 23) << 52), ginv = __longlong_as_double((long long)(1023 + 23 - e) << 52);
-            const double av = ceil(Xd * ginv - 0.5);                 // exact: X has 24 bits, X >= 2^-24 or X == 0
-            b.sigma = (((long long)av) & 1) ? -1.0 : 1.0;
-            b.Xp = -b.sigma * (g * (av - 0.5));                      // stored as -sigma * Xp: sigma (c - Xp) = fma(c, sigma, b.Xp)
-        }
-        tab[e] = b;
-    }
     if (a.l1_out) a.l1_out[c] = rc.L1f;
+}
+// Entry e of the row's binade table (closed form of AS:636): threads 0 .. kBinades-1 of the finishing CTA, one entry each.
+__device__ inline void make_binade_entry(const RowConstIn &a, int64_t c, int e) {
+    const RowConst &rc = a.consts[c];
+    BinadeEntry b; b.Xp = 0.0; b.sigma = 0.0;
+    if (!(rc.flags & kRowExact) && e >= 2 && e <= 22) {
+        const double Xd = (double)rc.X;
+        const double g = __longlong_as_double((long long)(1023 + e - 23) << 52), ginv = __longlong_as_double((long long)(1023 + 23 - e) << 52);
+        const double av = ceil(Xd * ginv - 0.5);                 // exact: X has 24 bits, X >= 2^-24 or X == 0
+        b.sigma = (((long long)av) & 1) ? -1.0 : 1.0;
+        b.Xp = -b.sigma * (g * (av - 0.5));                      // stored as -sigma * Xp: sigma (c - Xp) = fma(c, sigma, b.Xp)
+    }
+    a.tabs[c * kBinades + e] = b;
 }
 
 // ------------------------------------------------------------------ packed-code emit shared by both quantizer modes

@@ -38,6 +38,25 @@ def quantize_mean_sharded(x_local, bits_per_dimension=1, *, n_total: int, client
     return allreduce_partial_mean(partial, group)
 
 
+def rotated_quantize_mean_sharded(x_local, bits_per_dimension=1, *, n_total: int, client0: int, seed: int = 0, mode="unbiased",
+                                  rotation_seed: int = 123, out=None, group=None, check=False):
+    """Config 3 across ranks: every rank rotates its clients with the SHARED diagonal (AS:127-144), quantizes and averages them
+    in the rotated domain with the global divisor, ONE all-reduce adds the rotated partial means (dpad floats), and every rank
+    applies the single inverse rotation (AS:151-156; linear, so it commutes with the sum)."""
+    from . import api
+    X, n, d, _ = api._rows(x_local)
+    rot = api.rht(X, rotation_seed)
+    if rot.dim() == 1:
+        rot = rot.unsqueeze(0)
+    partial = api.quantize_mean(rot, bits_per_dimension, mode=mode, seed=seed, client0=client0, n_total=n_total, check=check)
+    allreduce_partial_mean(partial, group)
+    back = api.irht(partial, rotation_seed)[:d]
+    if out is not None:
+        out.copy_(back)
+        return out
+    return back.contiguous()
+
+
 class _Comm:
     """Side stream on which the per-slice all-reduces of quantize_mean_overlapped are enqueued (one per device)."""
     _streams: dict = {}

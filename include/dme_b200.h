@@ -48,7 +48,7 @@ extern "C" {
 #define DME_MODE_UNBIASED 0
 #define DME_MODE_BIASED 1
 
-#define DME_TILE 4096      /* coordinates per tile of the packed code and of every row kernel */
+#define DME_TILE 1024      /* coordinates per tile of the packed code (one directory entry, one field width) */
 
 typedef void *dme_stream_t; /* cudaStream_t */
 
@@ -70,7 +70,7 @@ DME_API int64_t dme_launch_count(void);
 DME_API int dme_profile_enable(int on, dme_stream_t stream);
 DME_API int dme_profile_read(float *ms, int cap);
 DME_API const char *dme_profile_name(int i);
-/* Test hook: which implementation runs the unbiased mode.  0 (default) = l1_kernel + quantize_tiles_kernel (the product path);
+/* Test hook: which implementation runs the unbiased mode.  0 (default) = l1_kernel + quantize_warp_kernel (the product path);
  * 1 = literal_rows_kernel (AS:625-637 as written, one CTA per row: an independent implementation for the parity tests). */
 DME_API int dme_set_unbiased_path(int path);
 
@@ -103,8 +103,9 @@ DME_API int dme_type_quantize(const float *X, int64_t n, int64_t d, int64_t ld, 
                       void *ws, int64_t ws_bytes, dme_stream_t stream);
 
 /* Packed code DMEP1.  dir[c * T + t] = (byte offset of the tile in `codes` / 16) << 8 | field width,
- * T = ceil(d / DME_TILE); a tile of width w holds 128*w uint32 words: word q of 16-coordinate chunk j at
- * [q * 256 + j], field i of the chunk at bits [w*i, w*i + w) = sign << (w-1) | magnitude. */
+ * T = ceil(d / DME_TILE); a tile of width w (the smallest of 2, 4, 8, 16, 32 with max |k| < 2^(w-1)) holds 32*w uint32
+ * words: word q of 16-coordinate chunk j (0..63) at [q * 64 + j], field i of the chunk at bits [w*i, w*i + w) =
+ * sign << (w-1) | magnitude. */
 DME_API int dme_type_encode(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, int mode,
                     const float *x_inject, const float *l1_inject, uint64_t seed, uint64_t client0,
                     void *codes, int64_t codes_bytes, uint64_t *dir, float *l1_out,

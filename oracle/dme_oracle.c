@@ -311,13 +311,13 @@ ORC_API int orc_tile_width(const int64_t *k, int64_t cnt) {
 }
 ORC_API void orc_pack_tile(const int64_t *k, const uint8_t *sgn, int64_t cnt, int w, uint32_t *words) {
     int wpc = w / 2;                                  /* words per chunk = 16*w/32 */
-    memset(words, 0, sizeof(uint32_t) * (size_t)(256 * wpc));
+    memset(words, 0, sizeof(uint32_t) * (size_t)(64 * wpc));   /* a code tile = 1024 coordinates = 64 chunks */
     for (int64_t i = 0; i < cnt; ++i) {
         int64_t c = i >> 4, j = i & 15;
         uint64_t field = ((uint64_t)(sgn[i] & 1) << (w - 1)) | (uint64_t)k[i];
         int64_t bit = (int64_t)w * j;
         int q = (int)(bit >> 5), sh = (int)(bit & 31);
-        words[q * 256 + c] |= (uint32_t)(field << sh);   /* w divides 32: a field never straddles */
+        words[q * 64 + c] |= (uint32_t)(field << sh);   /* w divides 32: a field never straddles */
     }
 }
 ORC_API void orc_unpack_tile(const uint32_t *words, int w, int64_t cnt, int64_t *k, uint8_t *sgn) {
@@ -325,7 +325,7 @@ ORC_API void orc_unpack_tile(const uint32_t *words, int w, int64_t cnt, int64_t 
         int64_t c = i >> 4, j = i & 15;
         int64_t bit = (int64_t)w * j;
         int q = (int)(bit >> 5), sh = (int)(bit & 31);
-        uint64_t field = (words[q * 256 + c] >> sh);
+        uint64_t field = (words[q * 64 + c] >> sh);
         if (w < 32) field &= (((uint64_t)1 << w) - 1);
         sgn[i] = (uint8_t)((field >> (w - 1)) & 1);
         k[i] = (int64_t)(field & (((uint64_t)1 << (w - 1)) - 1));

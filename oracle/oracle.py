@@ -21,7 +21,7 @@ RATE_TABLE = {
     4: 2.91504, 4.5: 4.14217, 5: 5.87195, 5.5: 8.31416, 6: 11.76507, 6.5: 16.64332, 7: 23.54075,
     7.5: 33.29414, 8: 47.0868, 8.5: 66.59204, 9: 94.17625, 9.5: 133.18596, 10: 188.35383,
 }
-TILE = 4096
+TILE = 1024
 
 
 def m_for(bits_per_dimension, d: int) -> int:
@@ -224,7 +224,7 @@ def mean_of(qs):
 
 
 def pack_row(k, sgn):
-    """-> list of (width, uint32 words[128*width]) per 4096-coordinate tile (format DMEP1)."""
+    """-> list of (width, uint32 words[32*width]) per 1024-coordinate code tile (format DMEP1)."""
     k = np.ascontiguousarray(k, np.int64); sgn = np.ascontiguousarray(sgn, np.uint8)
     tiles = []
     for t0 in range(0, k.size, TILE):
@@ -232,7 +232,7 @@ def pack_row(k, sgn):
         w = lib().orc_tile_width(kk, kk.size)
         if w < 0:
             raise OverflowError("magnitude >= 2^31 cannot be packed")
-        words = np.empty(128 * w, np.uint32)
+        words = np.empty(32 * w, np.uint32)
         lib().orc_pack_tile(kk, ss, kk.size, w, words)
         tiles.append((w, words))
     return tiles

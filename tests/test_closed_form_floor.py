@@ -1,4 +1,4 @@
-"""CPU: the identity the C-phase of quantize_tiles_kernel relies on (csrc/quantize_tiles.cu).
+"""CPU: the identity the C-phase of quantize_warp_kernel relies on (csrc/quantize_warp.cu).
 
 AS:636 evaluates t = floor(RN32(RN32(c) - X)) with c the fp64 prefix of the fractional parts.  Inside one binade of the
 fp32 prefix, c32 in [2^e + 1, 2^(e+1)), 2 <= e <= 22, with g = 2^(e-23) and a = ceil(X/g - 1/2):

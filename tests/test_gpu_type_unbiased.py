@@ -22,7 +22,7 @@ def dme():
 @pytest.fixture(autouse=True, params=["tiles", "literal"])
 def quantize_path(request, dme):
     """Every test of this file runs on both implementations of the unbiased quantizer: the product path (l1_kernel +
-    quantize_tiles_kernel, csrc/quantize_tiles.cu) and the literal kernel (csrc/quantize_literal.cu: AS:625-637 as written,
+    quantize_warp_kernel, csrc/quantize_warp.cu) and the literal kernel (csrc/quantize_literal.cu: AS:625-637 as written,
     one CTA per row), an independent second implementation checked against the same oracle and goldens."""
     dme.set_unbiased_path(request.param)
     yield request.param
@@ -90,7 +90,8 @@ def test_packed_code_matches_oracle_and_roundtrips(dme):
     Xs = [0.1, 0.5, 0.9, 0.25]
     for R in (1, 2, 5):
         pc = dme.type_encode(X, R, x_inject=Xs)
-        T = (d + 4095) // 4096
+        TILE = orc.TILE
+        T = (d + TILE - 1) // TILE
         for c in range(n):
             o = orc.type_unbiased(X[c], pc.m, Xs[c])
             tiles = orc.pack_row(o["k"], o["sgn"])
@@ -98,9 +99,9 @@ def test_packed_code_matches_oracle_and_roundtrips(dme):
                 w, words = pc.tile(c, t)
                 assert w == tiles[t][0], (R, c, t)
                 assert np.array_equal(words, tiles[t][1]), (R, c, t)       # packed code bit-exact vs the oracle
-                cnt = min(4096, d - 4096 * t)
+                cnt = min(TILE, d - TILE * t)
                 kk, ss = orc.unpack_tile(words, w, cnt)
-                assert np.array_equal(kk, o["k"][4096 * t: 4096 * t + cnt])
+                assert np.array_equal(kk, o["k"][TILE * t: TILE * t + cnt])
         mean = dme.decode_mean(pc).cpu().numpy()
         ref = orc.mean_of([orc.type_unbiased(X[c], pc.m, Xs[c])["deq"] for c in range(n)])
         assert np.array_equal(_u32(mean), _u32(ref)), R
@@ -199,7 +200,7 @@ def test_full_size_row_properties(dme):
 @pytest.mark.parametrize("X", [0.0, 2.0 ** -24, 0.25, 0.5, 0.75, 1 - 2.0 ** -24, 0.3333333432674408])
 def test_ties_and_binade_crossings_bit_exact(dme, X):
     """Dyadic rows (every prefix is exact, so the fp32 roundings of AS:636 tie all the time) long enough to cross
-    many binades of the prefix: the closed-form floor of quantize_tiles_kernel against the literal oracle."""
+    many binades of the prefix: the closed-form floor of quantize_warp_kernel against the literal oracle."""
     rng = np.random.default_rng(17)
     d = 3 * 4096 + 777
     for R in (1, 3, 6):

@@ -40,7 +40,7 @@ def test_host_only_entry_points():
     assert len(set(a)) > 990 and L.dme_uniform_x(8, 0) != a[0]
     assert all(abs(v * 2 ** 24 - round(v * 2 ** 24)) == 0 for v in a)            # on torch.rand's 2^-24 grid
     assert L.dme_workspace_bytes(128, 1 << 24) > 128 * 4096 * 24     # 8-byte L1 partial + 16-byte look-back record per tile
-    assert L.dme_dir_entries(3, 4097) == 6
+    assert L.dme_dir_entries(3, 4097) == 3 * 5                      # one entry per 1024-coordinate code tile
     assert L.dme_codes_bytes(128, 1 << 24, 3590827, 1) < L.dme_codes_bytes(128, 1 << 24, 3590827, 0)
     assert L.dme_codes_bytes(128, 1 << 24, 3590827, 0) >= 128 * (1 << 24) * 4
 

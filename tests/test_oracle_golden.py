@@ -167,15 +167,16 @@ def test_pack_roundtrip_and_layout():
         k = rng.integers(0, kmax + 1, d).astype(np.int64)
         s = rng.integers(0, 2, d).astype(np.uint8)
         tiles = orc.pack_row(k, s)
-        assert len(tiles) == (d + 4095) // 4096
+        TILE = orc.TILE
+        assert len(tiles) == (d + TILE - 1) // TILE
         for t, (w, words) in enumerate(tiles):
-            cnt = min(4096, d - t * 4096)
+            cnt = min(TILE, d - t * TILE)
             kk, ss = orc.unpack_tile(words, w, cnt)
-            assert np.array_equal(kk, k[t * 4096: t * 4096 + cnt]) and np.array_equal(ss, s[t * 4096: t * 4096 + cnt])
+            assert np.array_equal(kk, k[t * TILE: t * TILE + cnt]) and np.array_equal(ss, s[t * TILE: t * TILE + cnt])
             assert w in (2, 4, 8, 16, 32) and kk.max(initial=0) < 2 ** (w - 1)
             assert w == 2 or kk.max() >= 2 ** (w // 2 - 1)            # minimal width
     # layout: width 2, coordinate 17 = chunk 1 field 1 -> word index 1, bits [3:2] = sign<<1 | mag
-    k = np.zeros(4096, np.int64); s = np.zeros(4096, np.uint8); k[17] = 1; s[17] = 1
+    k = np.zeros(orc.TILE, np.int64); s = np.zeros(orc.TILE, np.uint8); k[17] = 1; s[17] = 1
     (w, words), = orc.pack_row(k, s)
     assert w == 2 and words[1] == 0b1100 and words.sum() == 0b1100
     with pytest.raises(OverflowError):

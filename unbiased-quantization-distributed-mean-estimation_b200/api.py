@@ -14,7 +14,7 @@ import torch
 
 from . import _cabi
 
-TILE = 4096
+TILE = 1024          # coordinates per tile of the packed code (DME_TILE)
 MODE = {"unbiased": 0, "biased": 1, 0: 0, 1: 1}
 
 # AS:614-620 (the API of the reference: R -> m/d; kept verbatim because it IS the interface)
@@ -122,7 +122,7 @@ UNBIASED_PATHS = {"tiles": 0, "literal": 1}
 
 
 def set_unbiased_path(path) -> None:
-    """Test hook (dme_set_unbiased_path): "tiles" = l1_kernel + quantize_tiles_kernel (the product path, default),
+    """Test hook (dme_set_unbiased_path): "tiles" = l1_kernel + quantize_warp_kernel (the product path, default),
     "literal" = AS:625-637 as written, one CTA per row (slow; an independent implementation the GPU tests check
     against the same oracle)."""
     _check(_cabi.lib().dme_set_unbiased_path(UNBIASED_PATHS.get(path, path)))
@@ -218,12 +218,12 @@ class PackedCodes:
         T = (self.d + TILE - 1) // TILE
         e = int(self.dir[c * T + t].item()) & 0xFFFFFFFFFFFFFFFF
         w, off = e & 0xFF, (e >> 8) * 16
-        words = self.codes[off: off + 512 * w].cpu().numpy().view(np.uint32)
+        words = self.codes[off: off + 128 * w].cpu().numpy().view(np.uint32)
         return w, words
 
     def payload_bytes(self) -> int:
         w = (self.dir & 0xFF).sum().item()
-        return int(w) * 512
+        return int(w) * 128
 
 
 def type_encode(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, client0=0, x_inject=None, l1_inject=None,
@@ -257,7 +257,7 @@ def type_encode(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, cli
 def decode_mean(pc: PackedCodes, *, n_total=None, out=None, accumulate=False, tiles=None):
     """Server side: dequantise (AS:640 / AS:687) and average, `est += q / n` in client order (ND:133-147).
 
-    tiles=(tile0, count) decodes only coordinates [tile0 * 4096, (tile0 + count) * 4096) of `out` (slices of the mean
+    tiles=(tile0, count) decodes only coordinates [tile0 * TILE, (tile0 + count) * TILE) of `out` (slices of the mean
     complete in order, so a sharded run can all-reduce one slice while the next is decoded)."""
     dev = pc.codes.device
     if out is None:

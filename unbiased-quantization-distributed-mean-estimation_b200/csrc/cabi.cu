@@ -49,15 +49,15 @@ extern "C" int64_t dme_workspace_bytes(int64_t n, int64_t d) {
 }
 extern "C" int64_t dme_dir_entries(int64_t n, int64_t d) {
     if (n < 1 || d < 1) return 0;
-    return n * ((d + kTile - 1) / kTile);
+    return n * ((d + kCodeTile - 1) / kCodeTile);
 }
 extern "C" int64_t dme_codes_bytes(int64_t n, int64_t d, int64_t m, int expect) {
     if (n < 1 || d < 1 || m < 1) return 0;
-    const int64_t T = (d + kTile - 1) / kTile;
-    // primary slots (expected width) + overflow space for wider tiles
+    const int64_t T = (d + kCodeTile - 1) / kCodeTile;
+    // primary slots (expected width, 128 * w0 bytes per code tile) + overflow space for wider tiles
     const int w0 = expected_width(m, d);
-    const int64_t primary = n * T * 512 * w0;
-    const int64_t overflow = expect ? (n * T * 512 * (w0 < 32 ? 2 * w0 : 0)) / 4 + 65536 : n * T * 512 * 32;
+    const int64_t primary = n * T * 128 * w0;
+    const int64_t overflow = expect ? (n * T * 128 * (w0 < 32 ? 2 * w0 : 0)) / 4 + 65536 : n * T * 128 * 32;
     return primary + overflow + 4096;
 }
 

@@ -7,7 +7,9 @@
 
 namespace dme {
 
-constexpr int kTile = DME_TILE;      // coordinates per tile
+constexpr int kTile = 4096;           // coordinates per CTA tile of the row kernels (l1, Reznik passes, literal rows, FWHT blocks)
+constexpr int kCodeTile = DME_TILE;   // coordinates per tile of the packed code: one directory entry, one field width
+constexpr int kCodeChunks = kCodeTile / 16;   // 16-coordinate chunks per code tile (word q of chunk j at [q * kCodeChunks + j])
 constexpr int kThreads = 256;        // threads per tile CTA
 constexpr int kEpt = 16;             // coordinates per thread (blocked: thread t owns [16t, 16t+16))
 constexpr int kWarps = kThreads / 32;

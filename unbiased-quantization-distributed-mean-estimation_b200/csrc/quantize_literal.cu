@@ -1,6 +1,6 @@
 // quantize_literal.cu -- the unbiased type quantizer (AS:609-641) evaluated LITERALLY: IEEE division, floorf, fp64 prefix,
 // AS:636 as written.  One CTA per client row, tiles in order, no look-back, no closed forms.  It is NOT the product path
-// (quantize_tiles.cu is): dme_set_unbiased_path(1) selects it so that the GPU tests can run an independent second
+// (quantize_warp.cu is): dme_set_unbiased_path(1) selects it so that the GPU tests can run an independent second
 // implementation against the same oracle and the same goldens.  Slow by construction (a 2^24-coordinate row takes milliseconds).
 #include "type_quantize.cuh"
 
@@ -93,7 +93,7 @@ literal_rows_kernel(const LitArgs a) {
                     if (a.sgn_out) a.sgn_out[o] = (uint8_t)sg[q];
                 }
             }
-            if (a.packed) emit_packed_tile(a.pack, c * a.T + t, k, sg, ovf, s_ps);
+            if (a.packed) emit_packed_tile(a.pack, c, t, k, sg, ovf, s_ps);
             else if (ovf) atomicOr(&a.hdr->status, 1u);
         }
     }
@@ -109,9 +109,7 @@ int launch_literal_rows(const float *X, int64_t n, int64_t d, int64_t ld, int64_
     a.hdr = (WsHeader *)base;
     a.x_inject = x_inject; a.l1_inject = l1_inject; a.seed = seed; a.client0 = client0; a.l1_out = l1_out;
     a.k_out = k_out; a.sgn_out = sgn_out; a.deq_out = deq_out; a.ld_out = ld_out;
-    a.pack.codes = codes; a.pack.codes_bytes = codes_bytes; a.pack.dir = dir; a.pack.hdr = a.hdr; a.pack.n = n; a.pack.T = L.T;
-    a.pack.W0 = expected_width(m > 0 ? m : 1, d);
-    a.pack.arena_base16 = (unsigned long long)(n * L.T) * 32ull * (unsigned long long)a.pack.W0;
+    init_pack_target(a.pack, codes, codes_bytes, dir, a.hdr, n, d, m);
     a.packed = packed ? 1 : 0;
     if (packed && (long long)(a.pack.arena_base16 * 16ull) > codes_bytes) {
         set_error("code arena too small for the primary slots: %lld < %llu bytes", (long long)codes_bytes, a.pack.arena_base16 * 16ull);

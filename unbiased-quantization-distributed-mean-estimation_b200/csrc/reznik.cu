@@ -256,7 +256,7 @@ rz_apply_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T, c
             if (kk >= 2147483648.0f) { ovf = true; k[j] = 0x7fffffffu; } else k[j] = (uint32_t)kk;
             sg[j] = __float_as_uint(x[j]) >> 31;
         }
-        emit_packed_tile(e.pack, c * T + t, k, sg, ovf, s_pack);
+        emit_packed_tile(e.pack, c, t, k, sg, ovf, s_pack);
     }
 }
 
@@ -286,9 +286,7 @@ int biased_quantize(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m,
     RzEmit e;
     e.k_out = k_out; e.sgn_out = sgn_out; e.deq_out = deq_out; e.ld_out = ld_out;
     e.packed = codes != nullptr;
-    e.pack.codes = codes; e.pack.codes_bytes = codes_bytes; e.pack.dir = dir; e.pack.hdr = (WsHeader *)base; e.pack.n = n; e.pack.T = L.T;
-    e.pack.W0 = expected_width(m, d);
-    e.pack.arena_base16 = (unsigned long long)(n * L.T) * 32ull * (unsigned long long)e.pack.W0;
+    init_pack_target(e.pack, codes, codes_bytes, dir, (WsHeader *)base, n, d, m);
     if (e.packed && (long long)(e.pack.arena_base16 * 16ull) > codes_bytes) {
         set_error("code arena too small for the primary slots: %lld bytes", (long long)codes_bytes);
         return DME_EWORKSPACE;

@@ -9,7 +9,7 @@
 // coordinates so that the in-thread part of the prefix is a plain sequential sum):
 //   l1_kernel      : per-tile fp64 partial sums; the LAST tile of a row to finish reduces the partials in
 //                    index order and publishes the row constants (deterministic, no float atomics).
-//   quantize_tiles_kernel (quantize_tiles.cu): single pass over the rows in ticket order with a decoupled look-back.
+//   quantize_warp_kernel (quantize_warp.cu): single pass over the rows in ticket order with a decoupled look-back.
 //   decode_mean_kernel : tile-major over d, clients in order in registers, one write of the mean.
 #include <cstdlib>
 
@@ -55,7 +55,7 @@ __device__ __forceinline__ void load_tile_striped(const float *__restrict__ row,
 // grid (T, n).  partial[c*T + t] = sum over the tile of |x| in fp64 (fixed association).
 __global__ void __launch_bounds__(kThreads)
 l1_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t m, int64_t T,
-          double *__restrict__ partial, uint32_t *__restrict__ a_done, RowConst *__restrict__ consts, BinadeEntry *__restrict__ tabs,
+          double *__restrict__ partial, uint32_t *__restrict__ a_done, RowConst *__restrict__ consts,
           const float *__restrict__ x_inject, const float *__restrict__ l1_inject, uint64_t seed,
           uint64_t client0, float *__restrict__ l1_out) {
     __shared__ double s_red[kWarps];
@@ -83,10 +83,8 @@ l1_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t m, int64_t
     acc = block_sum_f64(acc, s_red);
     RowConstIn in;
     in.m = m; in.d = d; in.x_inject = x_inject; in.l1_inject = l1_inject; in.seed = seed; in.client0 = client0;
-    in.consts = consts; in.tabs = tabs; in.l1_out = l1_out;
+    in.consts = consts; in.l1_out = l1_out;
     if (threadIdx.x == 0) make_row_const(in, c, acc);
-    __syncthreads();
-    if (threadIdx.x < kBinades) make_binade_entry(in, c, (int)threadIdx.x);      // the table in parallel: short rows are bound by this tail
 }
 
 // ------------------------------------------------------------------ K7: decode + mean (tile-major)
@@ -124,7 +122,7 @@ __device__ __forceinline__ void decode_generic(const uint32_t *__restrict__ tw, 
                                                float mf, float nf, int biased, float (&acc)[kEpt]) {
     uint32_t words[W / 2];
 #pragma unroll
-    for (int q = 0; q < W / 2; ++q) words[q] = __ldg(tw + q * kThreads + chunk);
+    for (int q = 0; q < W / 2; ++q) words[q] = __ldg(tw + q * kCodeChunks + chunk);
     float lv[kLut];
 #pragma unroll
     for (int k = 0; k < kLut; ++k) lv[k] = (W <= 4) ? lutc[k] : 0.0f;
@@ -132,7 +130,7 @@ __device__ __forceinline__ void decode_generic(const uint32_t *__restrict__ tw, 
 }
 
 // One thread = one 16-coordinate chunk of a tile, all clients in order (est += q / n, ND:133-147), fp32.
-// 64-thread CTAs, 4 per tile, so that short rows still fill the GPU.  Clients are taken in batches of 8 whose code words
+// 64-thread CTAs, one per code tile, so that short rows still fill the GPU.  Clients are taken in batches of 8 whose code words
 // are loaded together, one batch ahead of the adds.
 constexpr int kBatch = 8;
 constexpr int kLutClients = 128;     // clients whose tables are staged in shared memory at a time
@@ -165,7 +163,7 @@ __device__ __forceinline__ void dec_fetch(DecBatch &b, const uint2 *sinfo, const
         const uint32_t *tw = cptr + (unsigned long long)inf.x * 4ull;
         b.wc[u] = inf.y;
         b.wa[u] = (inf.y == 2u || inf.y == 4u) ? __ldg(tw) : 0u;
-        b.wb[u] = (inf.y == 4u) ? __ldg(tw + kThreads) : 0u;
+        b.wb[u] = (inf.y == 4u) ? __ldg(tw + kCodeChunks) : 0u;
     }
 }
 
@@ -185,10 +183,10 @@ decode_mean_kernel(const uint32_t *__restrict__ codes, const uint64_t *__restric
     }
     const uint32_t lanebase = slut | ((threadIdx.x & 31u) << 3);
     const uint32_t lut16_base = (uint32_t)__cvta_generic_to_shared(lut16);
-    const int64_t t = tile0 + (blockIdx.x >> 2);
-    const int chunk = (int)(blockIdx.x & 3) * 64 + threadIdx.x;
+    const int64_t t = tile0 + blockIdx.x;                  // one CTA = one code tile (64 chunks of 16 coordinates)
+    const int chunk = threadIdx.x;
     const uint32_t *cptr = codes + chunk;
-    const int64_t i0 = t * kTile + (int64_t)chunk * kEpt;
+    const int64_t i0 = t * kCodeTile + (int64_t)chunk * kEpt;
     const bool live = i0 < d;
     pf2 acc2[kEpt / 2];
 #pragma unroll
@@ -335,7 +333,7 @@ int launch_l1(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const
     char *base = (char *)ws;
     dim3 grid((unsigned)L.T, (unsigned)n);
     l1_kernel<<<grid, kThreads, 0, st>>>(X, d, ld, m, L.T, (double *)(base + L.off_partial), (uint32_t *)(base + L.off_done),
-                                         (RowConst *)(base + L.off_consts), (BinadeEntry *)(base + L.off_tab), x_inject, l1_inject, seed, client0, l1_out);
+                                         (RowConst *)(base + L.off_consts), x_inject, l1_inject, seed, client0, l1_out);
     DME_LAUNCH_CHECK("l1_kernel");
     return DME_OK;
 }
@@ -343,14 +341,14 @@ int launch_l1(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const
 int biased_quantize(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
                     int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
                     uint32_t *codes, int64_t codes_bytes, uint64_t *dir, cudaStream_t st);   // reznik.cu
-int launch_quantize_tiles(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
+int launch_quantize_warp(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
                           int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
-                          uint32_t *codes, int64_t codes_bytes, uint64_t *dir, cudaStream_t st, bool packed);   // quantize_tiles.cu
+                          uint32_t *codes, int64_t codes_bytes, uint64_t *dir, cudaStream_t st, bool packed);   // quantize_warp.cu
 int launch_literal_rows(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
                         const float *x_inject, const float *l1_inject, uint64_t seed, uint64_t client0,
                         int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
                         uint32_t *codes, int64_t codes_bytes, uint64_t *dir, float *l1_out, cudaStream_t st, bool packed);   // quantize_literal.cu
-// Which implementation quantises the unbiased mode: 0 = l1_kernel + quantize_tiles_kernel (the product path),
+// Which implementation quantises the unbiased mode: 0 = l1_kernel + quantize_warp_kernel (the product path),
 // 1 = literal_rows_kernel (tests: an independent implementation).  dme_set_unbiased_path.
 static int g_unbiased_path = 0;
 
@@ -400,7 +398,7 @@ static int quantize_common(const float *X, int64_t n, int64_t d, int64_t ld, int
     if (rc) return rc;
     if (mode == DME_MODE_BIASED)
         return biased_quantize(X, n, d, ld, m, L, ws, k_out, sgn_out, deq_out, ld_out, codes, codes_bytes, dir, st);
-    rc = launch_quantize_tiles(X, n, d, ld, m, L, ws, k_out, sgn_out, deq_out, ld_out, codes, codes_bytes, dir, st, packed);
+    rc = launch_quantize_warp(X, n, d, ld, m, L, ws, k_out, sgn_out, deq_out, ld_out, codes, codes_bytes, dir, st, packed);
     if (rc) return rc;
     return DME_OK;
 }
@@ -425,11 +423,11 @@ extern "C" int dme_decode_mean_tiles(const void *codes, const uint64_t *dir, con
     DME_REQUIRE(codes && dir && l1 && mean, "null pointer argument");
     DME_REQUIRE(n >= 1 && d >= 1 && m >= 1 && n_total >= 1, "n, d, m, n_total must be >= 1");
     DME_REQUIRE(((uintptr_t)mean & 15u) == 0 && ((uintptr_t)codes & 15u) == 0, "mean and codes must be 16-byte aligned");
-    const int64_t T = (d + kTile - 1) / kTile;
+    const int64_t T = (d + kCodeTile - 1) / kCodeTile;
     DME_REQUIRE(tile0 >= 0 && tiles >= 0 && tile0 + tiles <= T, "tile range [%lld, %lld) outside [0, %lld)", (long long)tile0,
                 (long long)(tile0 + tiles), (long long)T);
     if (tiles > 0) {
-        decode_mean_kernel<<<(unsigned)(4 * tiles), 64, kSignLutBytes, (cudaStream_t)stream>>>(
+        decode_mean_kernel<<<(unsigned)tiles, kCodeChunks, kSignLutBytes, (cudaStream_t)stream>>>(
             (const uint32_t *)codes, dir, l1, n, d, T, (float)m, (float)n_total, mode == DME_MODE_BIASED, mean, accumulate, tile0);
         DME_LAUNCH_CHECK("decode_mean_kernel");
     }
@@ -438,7 +436,7 @@ extern "C" int dme_decode_mean_tiles(const void *codes, const uint64_t *dir, con
 
 extern "C" int dme_decode_mean(const void *codes, const uint64_t *dir, const float *l1, int64_t n, int64_t d, int64_t m, int mode,
                                int64_t n_total, float *mean, int accumulate, dme_stream_t stream) {
-    return dme_decode_mean_tiles(codes, dir, l1, n, d, m, mode, n_total, mean, accumulate, 0, d >= 1 ? (d + kTile - 1) / kTile : 0, stream);
+    return dme_decode_mean_tiles(codes, dir, l1, n, d, m, mode, n_total, mean, accumulate, 0, d >= 1 ? (d + kCodeTile - 1) / kCodeTile : 0, stream);
 }
 
 extern "C" int dme_set_unbiased_path(int path) {

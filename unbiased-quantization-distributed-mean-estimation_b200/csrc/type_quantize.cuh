@@ -21,17 +21,6 @@ struct __align__(64) RowConst {
 };
 constexpr uint32_t kRowExact = 1u, kRowGuardFloor = 2u;
 
-// Decoupled look-back record of one (client, tile).  state: 0 = nothing, 1 = aggregate valid,
-// 2 = aggregate + inclusive valid.  a_state: 1 = a_last valid.
-struct __align__(32) TileDesc {
-    long long aggregate;   // sum of fractional parts inside the tile, fixed point (exact associativity =>
-    long long inclusive;   // the look-back result does not depend on timing); inclusive = sum of aggregates 0..t
-    int a_last;         // floor(c - X) of the tile's last coordinate
-    uint32_t state;
-    uint32_t a_state;
-    uint32_t pad;
-};
-
 struct __align__(256) WsHeader {
     uint32_t ticket;          // scan-order ticket dispenser
     uint32_t status;          // sticky error bits: 1 = magnitude overflow, 2 = arena exhausted
@@ -40,21 +29,15 @@ struct __align__(256) WsHeader {
     uint32_t pad[59];
 };
 
-// Closed form of AS:636 inside one binade of the fp32 prefix (quantize_tiles.cu): for c32 in [2^e + 1, 2^(e+1)),
-// floor(RN32(RN32(c) - X)) = floor(c - Xp) when sigma = +1, ceil(c - Xp) - 1 when sigma = -1; sigma = 0: no closed form.
-struct __align__(16) BinadeEntry { double Xp; double sigma; };
-constexpr int kBinades = 24;
-
 struct WsLayout {
     int64_t T;            // tiles per row
     int64_t off_done;     // uint32 a_done[n]
     int64_t off_ready;    // uint32 row_ready[n]
     int64_t off_consts;   // RowConst consts[n]
     int64_t off_partial;  // double partial[n*T]
-    int64_t off_desc;     // look-back records: 16 bytes per tile, per block of 32 tiles, per super-block of 1024 tiles
-    int64_t desc_bytes;
+    int64_t off_desc;     // look-back records of quantize_warp_kernel: 8 bytes per code tile, 8 per block of 32 tiles, 16 per
+    int64_t desc_bytes;   // super-block of 1024 tiles
     int64_t off_sel;      // RowSelect sel[n] (biased mode)
-    int64_t off_tab;      // BinadeEntry tab[n][kBinades] (quantize_tiles_kernel: closed-form floor(c - X) per binade)
     int64_t zero_bytes;   // prefix that must be zeroed before each call (header + a_done)
     int64_t total;
 };
@@ -93,19 +76,18 @@ inline WsLayout ws_layout(int64_t n, int64_t d) {
     L.off_consts = o; o = align_up(o + (int64_t)sizeof(RowConst) * n, 256);
     L.off_partial = o; o = align_up(o + 8 * n * L.T, 256);
     {
-        const int64_t TB = (L.T + 31) / 32, TS = (TB + 31) / 32;
-        L.desc_bytes = 16 * n * (L.T + TB + TS);
+        const int64_t T4 = (d + kCodeTile - 1) / kCodeTile, TB = (T4 + 31) / 32, TS = (TB + 31) / 32;
+        L.desc_bytes = n * (8 * T4 + 8 * TB + 16 * TS) + 16;
     }
     L.off_desc = o; o = align_up(o + L.desc_bytes, 256);
     L.off_sel = o; o = align_up(o + (int64_t)sizeof(RowSelect) * n, 256);
-    L.off_tab = o; o = align_up(o + (int64_t)sizeof(BinadeEntry) * kBinades * n, 256);
     L.total = o;
     return L;
 }
 
 #ifdef __CUDACC__
 // Row constants + the binade table of AS:636's closed form (cold: once per client row).
-struct RowConstIn { int64_t m, d; const float *x_inject, *l1_inject; uint64_t seed, client0; RowConst *consts; BinadeEntry *tabs; float *l1_out; };
+struct RowConstIn { int64_t m, d; const float *x_inject, *l1_inject; uint64_t seed, client0; RowConst *consts; float *l1_out; };
 __device__ inline void make_row_const(const RowConstIn &a, int64_t c, double l1sum) {
     RowConst rc;
     rc.L1f = a.l1_inject ? a.l1_inject[c] : (float)l1sum;           // AS:624
@@ -123,7 +105,7 @@ __device__ inline void make_row_const(const RowConstIn &a, int64_t c, double l1s
     rc.flags = fl;
     int lg = 0;
     while (((int64_t)1 << lg) < a.d) ++lg;
-    rc.qshift = min(50, 62 - lg);
+    rc.qshift = min(43, 62 - lg);                                   // a block of 32 tile aggregates + its count fit one 64-bit word
     rc.pad0 = 0;
     rc.q_up = __longlong_as_double((long long)(1023 + rc.qshift) << 52);
     rc.q_dn = __longlong_as_double((long long)(1023 - rc.qshift) << 52);
@@ -131,30 +113,17 @@ __device__ inline void make_row_const(const RowConstIn &a, int64_t c, double l1s
     a.consts[c] = rc;
     if (a.l1_out) a.l1_out[c] = rc.L1f;
 }
-// Entry e of the row's binade table (closed form of AS:636): threads 0 .. kBinades-1 of the finishing CTA, one entry each.
-__device__ inline void make_binade_entry(const RowConstIn &a, int64_t c, int e) {
-    const RowConst &rc = a.consts[c];
-    BinadeEntry b; b.Xp = 0.0; b.sigma = 0.0;
-    if (!(rc.flags & kRowExact) && e >= 2 && e <= 22) {
-        const double Xd = (double)rc.X;
-        const double g = __longlong_as_double((long long)(1023 + e - 23) << 52), ginv = __longlong_as_double((long long)(1023 + 23 - e) << 52);
-        const double av = ceil(Xd * ginv - 0.5);                 // exact: X has 24 bits, X >= 2^-24 or X == 0
-        b.sigma = (((long long)av) & 1) ? -1.0 : 1.0;
-        b.Xp = -b.sigma * (g * (av - 0.5));                      // stored as -sigma * Xp: sigma (c - Xp) = fma(c, sigma, b.Xp)
-    }
-    a.tabs[c * kBinades + e] = b;
-}
-
 // ------------------------------------------------------------------ packed-code emit shared by both quantizer modes
-struct PackTarget { uint32_t *codes; int64_t codes_bytes; uint64_t *dir; WsHeader *hdr; int W0; unsigned long long arena_base16; int64_t n, T; };
-// Primary slots are laid out TILE-major (tile t of all n clients is one contiguous run of n * 512 * W0 bytes): the
-// decoder walks a tile's clients in order, so its reads are long sequential runs instead of 1 KB pieces 4 MB apart.
-__device__ __forceinline__ unsigned long long primary_off16(const PackTarget &p, int64_t c, int64_t t) {
-    return (unsigned long long)(t * p.n + c) * (32ull * (unsigned long long)p.W0);
+// Code tiles are kCodeTile = 1024 coordinates (64 chunks of 16); T4 = code tiles per client row.
+struct PackTarget { uint32_t *codes; int64_t codes_bytes; uint64_t *dir; WsHeader *hdr; int W0; unsigned long long arena_base16; int64_t n, T4; };
+// Primary slots are laid out TILE-major (code tile t of all n clients is one contiguous run of n * 128 * W0 bytes): the
+// decoder walks a tile's clients in order, so its reads are long sequential runs.
+__device__ __forceinline__ unsigned long long primary_off16(const PackTarget &p, int64_t c, int64_t t4) {
+    return (unsigned long long)(t4 * p.n + c) * (8ull * (unsigned long long)p.W0);
 }
-struct PackScratch { uint32_t u32[kWarps]; unsigned long long off16; };
+struct PackScratch { uint32_t u32[kWarps]; unsigned long long off16[kTile / kCodeTile]; };
 
-// Pack 16 (magnitude, sign) pairs of one thread with field width W into W/2 words.
+// Pack 16 (magnitude, sign) pairs of one thread with field width W into W/2 words of chunk `chunk` (0..63) of a code tile.
 template <int W>
 __device__ __forceinline__ void pack_store(const uint32_t (&k)[kEpt], const uint32_t (&sg)[kEpt], uint32_t *tile_words, int chunk) {
     constexpr int kPerWord = 32 / W;
@@ -167,19 +136,38 @@ __device__ __forceinline__ void pack_store(const uint32_t (&k)[kEpt], const uint
             const uint32_t field = (W == 32) ? ((sg[j] << 31) | k[j]) : ((sg[j] << (W - 1)) | k[j]);
             word |= field << ((W * e) & 31);
         }
-        tile_words[q * kThreads + chunk] = word;
+        tile_words[q * kCodeChunks + chunk] = word;
     }
 }
-template <int W>
-__device__ __forceinline__ void pack_store(const uint32_t (&k)[kEpt], const uint32_t (&sg)[kEpt], uint32_t *tile_words) {
-    pack_store<W>(k, sg, tile_words, (int)threadIdx.x);       // one chunk per thread
+__device__ __forceinline__ void pack_store_w(int W, const uint32_t (&k)[kEpt], const uint32_t (&sg)[kEpt], uint32_t *tw, int chunk) {
+    switch (W) {
+        case 2: pack_store<2>(k, sg, tw, chunk); break;
+        case 4: pack_store<4>(k, sg, tw, chunk); break;
+        case 8: pack_store<8>(k, sg, tw, chunk); break;
+        case 16: pack_store<16>(k, sg, tw, chunk); break;
+        default: pack_store<32>(k, sg, tw, chunk); break;
+    }
+}
+// Place one code tile of width W: the fixed primary slot when W <= W0, bump-allocated overflow space otherwise; writes the
+// directory entry.  One thread per code tile calls it.  ~0 = the arena is exhausted (status bit 2 set, entry 0).
+__device__ __forceinline__ unsigned long long place_code_tile(const PackTarget &p, int64_t c, int64_t t4, int W) {
+    unsigned long long off16;
+    if (W <= p.W0) off16 = primary_off16(p, c, t4);
+    else {
+        const unsigned long long units = 8ull * W;                  // 128 * W bytes / 16
+        off16 = p.arena_base16 + atomicAdd(&p.hdr->arena_top, units);
+        if ((long long)((off16 + units) * 16ull) > p.codes_bytes) { atomicOr(&p.hdr->status, 2u); off16 = ~0ull; }
+    }
+    p.dir[c * p.T4 + t4] = (off16 == ~0ull) ? 0ull : ((off16 << 8) | (unsigned long long)W);
+    return off16;
 }
 
-// Whole CTA: choose the tile's minimal field width, place it (fixed primary slot when W <= W0, bump-allocated
-// overflow space otherwise), write the directory entry and the words.  slot = client * T + tile.
-__device__ __forceinline__ void emit_packed_tile(const PackTarget &p, int64_t slot, const uint32_t (&k)[kEpt],
+// Whole CTA (kThreads threads, thread t owns coordinates [16t, 16t + 16) of CTA tile `t` of client c = four code tiles of
+// 64 threads each): every code tile gets its minimal field width, is placed and written.
+__device__ __forceinline__ void emit_packed_tile(const PackTarget &p, int64_t c, int64_t t, const uint32_t (&k)[kEpt],
                                                  const uint32_t (&sg)[kEpt], bool ovf, PackScratch &ps) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int quarter = threadIdx.x >> 6, chunk = threadIdx.x & (kCodeChunks - 1);
     uint32_t kmax = 0;
 #pragma unroll
     for (int j = 0; j < kEpt; ++j) kmax = max(kmax, k[j]);
@@ -187,36 +175,24 @@ __device__ __forceinline__ void emit_packed_tile(const PackTarget &p, int64_t sl
     kmax = __reduce_max_sync(0xffffffffu, kmax);
     if (lane == 0) ps.u32[warp] = kmax;
     __syncthreads();
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) kmax = max(kmax, ps.u32[w]);
+    kmax = max(ps.u32[2 * quarter], ps.u32[2 * quarter + 1]);
     int W = 2;
     while (W < 32 && kmax >= (1u << (W - 1))) W <<= 1;
-    unsigned long long off16;
-    if (W <= p.W0) {
-        off16 = primary_off16(p, slot / p.T, slot % p.T);
-        if (threadIdx.x == 0) p.dir[slot] = (off16 << 8) | (unsigned long long)W;
-    } else {
-        if (threadIdx.x == 0) {
-            const unsigned long long units = 32ull * W;                  // 512*W bytes / 16
-            unsigned long long off = p.arena_base16 + atomicAdd(&p.hdr->arena_top, units);
-            if ((long long)((off + units) * 16ull) > p.codes_bytes) { atomicOr(&p.hdr->status, 2u); off = ~0ull; }
-            ps.off16 = off;
-            p.dir[slot] = (off == ~0ull) ? 0ull : ((off << 8) | (unsigned long long)W);
-        }
-        __syncthreads();
-        off16 = ps.off16;
-    }
-    if (off16 != ~0ull) {
-        uint32_t *tw = p.codes + off16 * 4ull;
-        switch (W) {
-            case 2: pack_store<2>(k, sg, tw); break;
-            case 4: pack_store<4>(k, sg, tw); break;
-            case 8: pack_store<8>(k, sg, tw); break;
-            case 16: pack_store<16>(k, sg, tw); break;
-            default: pack_store<32>(k, sg, tw); break;
-        }
+    const int64_t t4 = t * (kTile / kCodeTile) + quarter;
+    const bool live = t4 < p.T4;                                     // the row ends before this quarter of the CTA tile
+    if (chunk == 0 && live) ps.off16[quarter] = place_code_tile(p, c, t4, W);
+    __syncthreads();
+    if (live) {
+        const unsigned long long off16 = ps.off16[quarter];
+        if (off16 != ~0ull) pack_store_w(W, k, sg, p.codes + off16 * 4ull, chunk);
     }
     __syncthreads();        // ps is reused by the caller's next tile
+}
+inline void init_pack_target(PackTarget &p, uint32_t *codes, int64_t codes_bytes, uint64_t *dir, WsHeader *hdr, int64_t n, int64_t d, int64_t m) {
+    p.codes = codes; p.codes_bytes = codes_bytes; p.dir = dir; p.hdr = hdr; p.n = n;
+    p.T4 = (d + kCodeTile - 1) / kCodeTile;
+    p.W0 = expected_width(m > 0 ? m : 1, d);
+    p.arena_base16 = (unsigned long long)(n * p.T4) * 8ull * (unsigned long long)p.W0;
 }
 #endif  // __CUDACC__
 

@@ -158,6 +158,17 @@ DME_API int dme_eden_encode(const float *X, int64_t n, int64_t d, int64_t ld, in
 DME_API int dme_eden_decode(const uint8_t *bins, const float *scale, int64_t n, int64_t d, int64_t dpad, int nbits,
                     uint64_t seed, uint64_t seed_stride, const float *diag_inject, float *work, float *out, int64_t ld_out,
                     dme_stream_t stream);
+/* Fractional rates (AS:352-368, AS:385-389, AS:401-421): coordinate i of client c is quantized with the nbits_high table where
+ * mask[c][i] is set and with the nbits_low table elsewhere; mask_inject (uint8 n x dpad, nullable) or Bernoulli(p_high) from
+ * Philox keyed by the client's mask seed (seed + c * seed_stride) * 7 + 13 -- sender and receiver derive the same mask.
+ * drop (uint8 n x dpad, nullable): coordinates the receiver zeroes (rates below 1 bit, AS:413-421); the others are divided
+ * by keep = 1 - pdrop. */
+DME_API int dme_eden_encode_frac(const float *X, int64_t n, int64_t d, int64_t ld, int64_t dpad, int nbits_low, int nbits_high,
+                    float p_high, const uint8_t *mask_inject, uint64_t seed, uint64_t seed_stride, const float *diag_inject,
+                    const float *norm_inject, float *rot, uint8_t *bins, float *scale, dme_stream_t stream);
+DME_API int dme_eden_decode_frac(const uint8_t *bins, const float *scale, int64_t n, int64_t d, int64_t dpad, int nbits_low,
+                    int nbits_high, float p_high, const uint8_t *mask_inject, const uint8_t *drop, float keep, uint64_t seed,
+                    uint64_t seed_stride, const float *diag_inject, float *work, float *out, int64_t ld_out, dme_stream_t stream);
 /* Xq: int32 n x dpad table rows; h: int32 n x dpad shared randomness; recv_table: (2^nbits) x h_len floats;
  * exact_mask (uint8, nullable) / exact_vals (per row: exact_off[c] .. exact_off[c+1]). */
 DME_API int dme_quicfl_decode(const int32_t *Xq, const int32_t *h, int64_t n, int64_t d, int64_t dpad, int h_len,

@@ -196,6 +196,82 @@ def eden(x, diag, nbits: int):
     return eden_decode(e["bins"], np.asarray(x).size, diag, nbits, e["scale"])
 
 
+EDEN_CENT = {1: np.array([-0.7978845608028654, 0.7978845608028654], np.float32),
+             2: np.array([-1.5104176087114887, -0.4527800398860679, 0.4527800398860679, 1.5104176087114887], np.float32)}   # AS:303-304
+
+
+def _eden_bnd(nbits):
+    c = EDEN_CENT[nbits]
+    return ((c[:-1] + c[1:]) / np.float32(2)).astype(np.float32)                       # AS:311-312
+
+
+def eden_encode_frac(x, diag, nbits_low: int, nbits_high: int, mask_high, norm_inject=None):
+    """EdenSender.compress for a fractional rate (AS:352-368, AS:385-389): bucketize with both tables, take the high-rate bin
+    where mask_high is set; scale = ||v||^2 / <centroids, v>.  The dot product accumulates in fp64 like the C port."""
+    v = rht(x, diag)                                                                     # AS:378-380
+    nrm = np.float32(np.sqrt(np.sum(v.astype(np.float64) ** 2))) if norm_inject is None else np.float32(norm_inject)
+    z = (v * np.float32(np.float64(v.size) ** 0.5)) / nrm                                # AS:354
+    mask = np.asarray(mask_high).astype(bool)
+    bl = np.searchsorted(_eden_bnd(nbits_low), z, side="left").astype(np.int32)          # torch.bucketize, right=False
+    bh = np.searchsorted(_eden_bnd(nbits_high), z, side="left").astype(np.int32)
+    bins = np.where(mask, bh, bl).astype(np.int32)                                       # AS:363
+    cent = np.where(mask, EDEN_CENT[nbits_high][bh], EDEN_CENT[nbits_low][bl]).astype(np.float32)    # AS:364
+    scale = np.float32((nrm * nrm) / np.float32(np.sum(cent.astype(np.float64) * v.astype(np.float64))))   # AS:366
+    return {"bins": bins, "scale": scale, "rot": v}
+
+
+def eden_decode_frac(bins, d: int, diag, nbits_low: int, nbits_high: int, mask_high, scale, drop=None, pdrop=0.0):
+    """EdenReceiver.decompress (AS:398-426) for a fractional rate or a rate below one bit (drop: the coordinates of AS:416-417)."""
+    mask = np.asarray(mask_high).astype(bool)
+    bins = np.asarray(bins)
+    vec = np.where(mask, EDEN_CENT[nbits_high][np.minimum(bins, EDEN_CENT[nbits_high].size - 1)],
+                   EDEN_CENT[nbits_low][np.minimum(bins, EDEN_CENT[nbits_low].size - 1)]).astype(np.float32)   # AS:401-411
+    if drop is not None:
+        vec = np.where(np.asarray(drop).astype(bool), np.float32(0), vec / np.float32(1.0 - pdrop)).astype(np.float32)   # AS:417-421
+    out = irht(vec, diag)                                                                # AS:425
+    return (np.float32(scale) * out)[:d].astype(np.float32)                              # AS:426
+
+
+def kashin_padded_dim(dim: int, pad_threshold: float = 0.85) -> int:
+    """AS:203-211."""
+    if dim & (dim - 1):
+        p = pad_pow2(dim)
+        return 2 * p if dim / p > pad_threshold else p
+    return 2 * dim
+
+
+def kashin(x, diag, bits: int, u, m0=None, eta=0.9, delta=1.0, niters=3, err=1e-6):
+    """Kashin_quantize (AS:834-854) = kashin_coefficients (AS:213-239) + StochasticQuantizationSender/Receiver (AS:67-90) + the
+    inverse transform (AS:262-267), fp32 elementwise like torch.  u: the uniforms behind torch.bernoulli (AS:81): bit = [u < p];
+    m0: the initial M (AS:221: an fp32 torch.norm in the reference; fp64-accumulated here when not injected)."""
+    x = _f32(x); diag = _f32(diag)
+    dim, pdim = x.size, diag.size
+    f32 = np.float32
+    coeff = np.zeros(pdim, f32)
+    resid = x.copy()
+    M = f32(m0) if m0 is not None else f32(f32(np.sqrt(np.sum(x.astype(np.float64) ** 2))) / f32(np.sqrt(delta * pdim)))
+    for i in range(niters):
+        padded = np.zeros(pdim, f32); padded[:dim] = resid
+        b = rht(padded, diag)                                                            # AS:225
+        b_hat = np.minimum(np.maximum(b, -M), M).astype(f32)                             # AS:228
+        coeff = (coeff + b_hat).astype(f32)                                              # AS:229
+        if i < niters - 1:
+            resid = (resid - irht(b_hat, diag)[:dim]).astype(f32)                        # AS:232-233
+            M = f32(M * f32(eta))                                                        # AS:234
+        e = np.sqrt(np.sum((x - irht(coeff, diag)[:dim]).astype(np.float64) ** 2)) / np.sqrt(np.sum(resid.astype(np.float64) ** 2))
+        if e < err:                                                                      # AS:236-238
+            break
+    nlevels = f32(2 ** bits)
+    vmin, vmax = coeff.min(), coeff.max()
+    step = f32((vmax - vmin) / (nlevels - f32(1)))                                       # AS:72
+    r = ((coeff - vmin) / step).astype(f32)                                              # AS:80
+    fl = np.floor(r).astype(f32)
+    bins = (fl + (_f32(u)[:pdim] < (r - fl).astype(f32)).astype(f32)).astype(f32)        # AS:81
+    deq = (vmin + (bins * step).astype(f32)).astype(f32)                                 # AS:90
+    out = irht(deq, diag)[:dim]                                                          # AS:267
+    return {"out": out, "coeff": coeff, "bins": bins, "min": vmin, "step": step}
+
+
 def quicfl_decode(X, h, d: int, h_len: int, recv_table, exact_mask, exact_vals, scale, diag):
     diag = _f32(diag)
     X = np.ascontiguousarray(X, np.int32); h = np.ascontiguousarray(h, np.int32)

@@ -213,5 +213,84 @@ def gen_scalar_and_mean():
     print("scalar:", k, "+ mean")
 
 
+def gen_eden_frac_and_kashin():
+    """Fractional EDEN rates (AS:352-368, AS:401-421) and Kashin_quantize (AS:834-854) from the unmodified reference.
+    Injected / recorded: the Bernoulli masks and uniforms, the dropped coordinates, EDEN's fp32 norm, Kashin's initial M."""
+    rng = np.random.default_rng(29)
+    H = AS.Hadamard(device="cpu")
+    recs = {}
+    k = 0
+    for d, nbits, seed in ((1000, 1.5, 17), (4096, 1.25, 64), (777, 1.75, 3), (2048, 0.5, 9), (1500, 0.75, 41)):
+        x = rng.standard_normal(d).astype(np.float32)
+        dpad = 1 << int(np.ceil(np.log2(d)))
+        diag = H.random_diagonal(dpad, seed).numpy()
+        snd, rcv = AS.EdenSender(device="cpu"), AS.EdenReceiver(device="cpu")
+        comp = snd.compress({"vec": torch.tensor(x).clone(), "seed": seed, "nbits": nbits, "rotation_seed": 123, "nlevels": 2 ** nbits})
+        rot = snd.randomized_hadamard_transform(torch.tensor(x).clone() if d == dpad else torch.cat([torch.tensor(x), torch.zeros(dpad - d)]), seed)
+        recs[f"f{k}_x"] = x; recs[f"f{k}_diag"] = diag; recs[f"f{k}_nbits"] = np.float64(nbits); recs[f"f{k}_seed"] = np.int64(seed)
+        recs[f"f{k}_bins"] = comp["bins"].numpy().astype(np.int32)
+        recs[f"f{k}_scale"] = np.float32(comp["scale"].item())
+        recs[f"f{k}_norm"] = np.float32(torch.norm(rot, 2).item())
+        if nbits > 1:
+            g = torch.Generator(device="cpu"); g.manual_seed(seed * 7 + 13)                     # AS:389 / AS:402
+            mask = torch.bernoulli(torch.ones(dpad) * (nbits - np.floor(nbits)), generator=g).bool().numpy()
+            recs[f"f{k}_mask"] = mask.astype(np.uint8)
+            recs[f"f{k}_drop"] = np.zeros(dpad, np.uint8)
+            q = rcv.decompress(dict(comp))
+        else:
+            recs[f"f{k}_mask"] = np.zeros(dpad, np.uint8)
+            perm = torch.randperm(dpad)
+            saved = torch.randperm
+            torch.randperm = lambda n_, device=None: perm                                      # AS:416: record the draw
+            try:
+                q = rcv.decompress(dict(comp))
+            finally:
+                torch.randperm = saved
+            drop = np.zeros(dpad, np.uint8); drop[perm[:round(dpad * (1 - nbits))].numpy()] = 1
+            recs[f"f{k}_drop"] = drop
+        recs[f"f{k}_q"] = np.asarray(q, np.float32)
+        k += 1
+    recs["n_frac"] = np.int64(k)
+    j = 0
+    for d, bits, seed in ((1000, 2, 5), (1024, 1, 77), (900, 4, 12), (3000, 3, 30)):
+        x = rng.standard_normal(d).astype(np.float32)
+        snd = AS.KashinStochasticQuantizationSender(device="cpu")
+        rcv = AS.KashinStochasticQuantizationReceiver(device="cpu")
+        pdim = snd.kashin_padded_dim(d, 0.85)
+        diag = H.random_diagonal(pdim, 123).numpy()
+        U = torch.tensor(rng.random(pdim).astype(np.float32))
+        # AS:81: Bernoulli(p) = [u < p] with recorded uniforms -- only inside StochasticQuantizationSender.compress (the rotation
+        # diagonal of AS:117-120 is a Bernoulli draw too and must stay the generator's)
+        saved, sq_compress, in_sq = torch.bernoulli, AS.StochasticQuantizationSender.compress, [False]
+
+        def _sq(self, data, _orig=sq_compress):
+            in_sq[0] = True
+            try:
+                return _orig(self, data)
+            finally:
+                in_sq[0] = False
+        torch.bernoulli = lambda p, generator=None: (U < p).to(p.dtype) if in_sq[0] else saved(p, generator=generator)
+        AS.StochasticQuantizationSender.compress = _sq
+        try:
+            data = snd.compress({"vec": torch.tensor(x).clone(), "seed": seed, "nbits": bits, "rotation_seed": 123,
+                                 "nlevels": 2 ** bits, "niters": 3})
+        finally:
+            torch.bernoulli = saved
+            AS.StochasticQuantizationSender.compress = sq_compress
+        coeff, _ = snd.kashin_coefficients({"vec": torch.tensor(x).clone(), "rotation_seed": 123})
+        q = rcv.decompress(data)
+        recs[f"k{j}_x"] = x; recs[f"k{j}_diag"] = diag; recs[f"k{j}_bits"] = np.int64(bits); recs[f"k{j}_u"] = U.numpy()
+        recs[f"k{j}_m0"] = np.float32((torch.norm(torch.tensor(x)) / np.sqrt(1.0 * pdim)).item())
+        recs[f"k{j}_coeff"] = coeff.numpy(); recs[f"k{j}_bins"] = data["data"]["bins"].numpy()
+        recs[f"k{j}_min"] = np.float32(data["data"]["min"].item()); recs[f"k{j}_step"] = np.float32(data["data"]["step"].item())
+        recs[f"k{j}_q"] = np.asarray(q, np.float32)
+        j += 1
+    recs["n_kashin"] = np.int64(j)
+    np.savez_compressed(os.path.join(OUT, "eden_frac_kashin.npz"), **recs)
+    print("eden_frac:", k, "kashin:", j)
+
+
 if __name__ == "__main__":
-    gen_type(); gen_hadamard(); gen_drive(); gen_eden(); gen_quicfl(); gen_scalar_and_mean()
+    if "--extra" not in sys.argv:                      # --extra: only the fixtures added in round 2
+        gen_type(); gen_hadamard(); gen_drive(); gen_eden(); gen_quicfl(); gen_scalar_and_mean()
+    gen_eden_frac_and_kashin()

@@ -159,6 +159,65 @@ def test_eden_batched_quality(dme):
         dme.eden_encode(X, 3)
 
 
+def test_eden_fractional_golden(dme, golden_dir):
+    """AS:352-368 / AS:401-421 under the reference's mask, fp32 norm and dropped coordinates: bins and decoded vector bit-exact."""
+    g = np.load(os.path.join(golden_dir, "eden_frac_kashin.npz"))
+    for k in range(int(g["n_frac"])):
+        x, diag, nb = g[f"f{k}_x"], g[f"f{k}_diag"], float(g[f"f{k}_nbits"])
+        enc = dme.eden_encode(x, nb, diag_inject=diag, norm_inject=[g[f"f{k}_norm"]], mask_inject=g[f"f{k}_mask"] if nb > 1 else None)
+        assert np.array_equal(enc["bins"][0].cpu().numpy().astype(np.int32), g[f"f{k}_bins"]), k
+        assert abs(float(enc["scale"][0]) - float(g[f"f{k}_scale"])) <= 2e-6 * abs(float(g[f"f{k}_scale"]))
+        enc["scale"] = torch.tensor([float(g[f"f{k}_scale"])], device="cuda")
+        out = dme.eden_decode(enc, diag_inject=diag, drop_inject=g[f"f{k}_drop"] if nb < 1 else None).cpu().numpy()
+        assert np.array_equal(_u32(out), _u32(g[f"f{k}_q"])), k
+
+
+def test_eden_fractional_own_draws(dme):
+    """Philox mask (sender and receiver derive the same one) and torch-drawn drops: the error sits between the neighbouring
+    integer rates, and a rate below one bit costs the dropped fraction."""
+    rng = np.random.default_rng(40)
+    X = rng.standard_normal((6, 30000)).astype(np.float32)
+    def nmse(Y):
+        return float(np.mean(np.sum((Y - X) ** 2, axis=1) / np.sum(X ** 2, axis=1)))
+    e1, e15, e2 = (nmse(dme.eden(X, b, seed=3).cpu().numpy()) for b in (1, 1.5, 2))
+    assert e2 < e15 < e1 and abs(e15 - 0.5 * (e1 + e2)) < 0.08 * e1
+    e05 = nmse(dme.eden(X, 0.5, seed=3).cpu().numpy())
+    assert e05 > 1.5 * e1
+    for bad in (3, 2.5, 0):
+        with pytest.raises(KeyError):
+            dme.eden_encode(X, bad)
+
+
+def test_kashin_golden(dme, golden_dir):
+    """Kashin_quantize (AS:834-854) with the rotation diagonal, the initial M and the Bernoulli uniforms of the reference run
+    injected: coefficients, bins, min, step and the decoded vector bit-exact; with own norm: same up to clamp-boundary cases."""
+    g = np.load(os.path.join(golden_dir, "eden_frac_kashin.npz"))
+    for k in range(int(g["n_kashin"])):
+        x, diag, bits = g[f"k{k}_x"], g[f"k{k}_diag"], int(g[f"k{k}_bits"])
+        r = dme.kashin(x, bits, diag_inject=diag, m0_inject=[g[f"k{k}_m0"]], u_inject=g[f"k{k}_u"], want_parts=True)
+        assert r["pdim"] == diag.size
+        assert np.array_equal(_u32(r["coeff"][0].cpu().numpy()), _u32(g[f"k{k}_coeff"])), k
+        assert np.array_equal(r["bins"][0].cpu().numpy(), g[f"k{k}_bins"]), k
+        assert float(r["min"][0]) == float(g[f"k{k}_min"]) and float(r["step"][0]) == float(g[f"k{k}_step"]), k
+        assert np.array_equal(_u32(r["out"].cpu().numpy()), _u32(g[f"k{k}_q"])), k
+        own = dme.kashin(x, bits, diag_inject=diag, u_inject=g[f"k{k}_u"]).cpu().numpy()
+        o = orc.kashin(x, diag, bits, g[f"k{k}_u"])["out"]
+        # own fp32 norm: M differs in the last bits, so everything moves by ~1e-7; a rounding that flips moves a coordinate by a step
+        assert np.max(np.abs(own - o)) <= 0.6 * float(g[f"k{k}_step"]) + 1e-6 and np.mean(np.abs(own - o) > 1e-4) < 0.01
+
+
+def test_kashin_batched_matches_per_row_and_quality(dme):
+    rng = np.random.default_rng(41)
+    X = rng.standard_normal((5, 3000)).astype(np.float32)
+    pdim = dme.kashin_padded_dim(3000)
+    U = rng.random((5, pdim)).astype(np.float32)
+    Y = dme.kashin(X, 3, u_inject=U).cpu().numpy()
+    for c in range(5):
+        assert np.array_equal(_u32(Y[c]), _u32(dme.kashin(X[c], 3, u_inject=U[c]).cpu().numpy())), c
+    err = np.sum((Y - X) ** 2, axis=1) / np.sum(X ** 2, axis=1)
+    assert np.all(err < 0.2), err
+
+
 # ------------------------------------------------------------------ QUIC-FL receiver
 def test_quicfl_receiver_golden(dme, golden_dir):
     g = np.load(os.path.join(golden_dir, "quicfl_recv.npz"))

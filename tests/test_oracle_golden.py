@@ -181,3 +181,32 @@ def test_pack_roundtrip_and_layout():
     assert w == 2 and words[1] == 0b1100 and words.sum() == 0b1100
     with pytest.raises(OverflowError):
         orc.pack_row(np.array([2 ** 31], np.int64), np.zeros(1, np.uint8))
+
+
+def test_eden_fractional_rates(golden_dir):
+    """AS:352-368 / AS:401-421: bins bit-exact under the reference's mask and fp32 norm; the decoded vector bit-exact from the
+    reference's bins and scale (mask / dropped coordinates recorded in the fixture)."""
+    g = _load(golden_dir, "eden_frac_kashin.npz")
+    for k in range(int(g["n_frac"])):
+        x, diag, nb = g[f"f{k}_x"], g[f"f{k}_diag"], float(g[f"f{k}_nbits"])
+        lo, hi = (int(np.floor(nb)), int(np.ceil(nb))) if nb > 1 else (1, 1)
+        e = orc.eden_encode_frac(x, diag, lo, hi, g[f"f{k}_mask"], norm_inject=g[f"f{k}_norm"])
+        assert np.array_equal(e["bins"], g[f"f{k}_bins"]), k
+        assert abs(float(e["scale"]) - float(g[f"f{k}_scale"])) <= 2e-6 * abs(float(g[f"f{k}_scale"]))
+        drop = g[f"f{k}_drop"] if nb < 1 else None
+        out = orc.eden_decode_frac(g[f"f{k}_bins"], x.size, diag, lo, hi, g[f"f{k}_mask"], g[f"f{k}_scale"], drop=drop, pdrop=max(0.0, 1 - nb))
+        assert np.array_equal(out.view(np.uint32), g[f"f{k}_q"].view(np.uint32)), k
+
+
+def test_kashin(golden_dir):
+    """AS:834-854 with the initial M and the Bernoulli uniforms injected: coefficients, bins, min, step and output bit-exact."""
+    g = _load(golden_dir, "eden_frac_kashin.npz")
+    for k in range(int(g["n_kashin"])):
+        x, diag, bits = g[f"k{k}_x"], g[f"k{k}_diag"], int(g[f"k{k}_bits"])
+        assert diag.size == orc.kashin_padded_dim(x.size)
+        r = orc.kashin(x, diag, bits, g[f"k{k}_u"], m0=g[f"k{k}_m0"])
+        assert np.array_equal(r["coeff"].view(np.uint32), g[f"k{k}_coeff"].view(np.uint32)), k
+        assert np.array_equal(r["bins"], g[f"k{k}_bins"]) and r["min"] == g[f"k{k}_min"] and r["step"] == g[f"k{k}_step"], k
+        assert np.array_equal(r["out"].view(np.uint32), g[f"k{k}_q"].view(np.uint32)), k
+        own = orc.kashin(x, diag, bits, g[f"k{k}_u"])                   # own fp64-accumulated norm: same up to clamp-boundary cases
+        assert np.max(np.abs(own["out"] - g[f"k{k}_q"])) <= 0.6 * float(g[f"k{k}_step"]) + 1e-6

@@ -35,10 +35,17 @@ Type_quantize_algo_rate_l_dict = {1: 0.21403, 2: 0.63752, 3: 1.41725, 4: 2.91504
 DRIVE_COMPAT = "reference"
 
 _calls = itertools.count()
+_keyed_to = None
 
 
 def _seed() -> int:
-    return (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + next(_calls) * 0xD1342543DE82EF95) & 0xFFFFFFFFFFFFFFFF
+    """Philox seed of the next call: torch's seed and a call counter that restarts whenever the seed changes, so that
+    `torch.manual_seed(s)` reproduces a run from that point on (the reference's draws come from torch's global generator)."""
+    global _calls, _keyed_to
+    s0 = int(torch.initial_seed())
+    if s0 != _keyed_to:
+        _keyed_to, _calls = s0, itertools.count()
+    return (s0 * 0x9E3779B97F4A7C15 + next(_calls) * 0xD1342543DE82EF95) & 0xFFFFFFFFFFFFFFFF
 
 
 def _vec(input_vector):
@@ -71,14 +78,12 @@ def Scalar_quantize(input_vector, bits_per_dimension=1):
 
 
 def EDEN_quantize_Hadamard(input_vector, bits_per_dimension=1):
-    """AS:793-812.  Returns a numpy array on the host like the reference (AS:812)."""
+    """AS:793-812.  Returns a numpy array on the host like the reference (AS:812).  Rates: 1, 2, below 1 (1-bit quantization,
+    the receiver drops coordinates, AS:413-421) and fractional rates between 1 and 2 (AS:352-368); any other rate has no
+    centroids in the reference either (AS:301-320) and raises KeyError like its table lookup."""
     x = _vec(input_vector)
     seed = int(torch.randint(0, 100, (1,)).item())                          # AS:800: per-call rotation seed
-    if bits_per_dimension not in (1, 2):
-        if bits_per_dimension == round(bits_per_dimension):
-            raise KeyError(int(bits_per_dimension))                        # AS:301-320: centroids for 1 and 2 bits only
-        raise NotImplementedError("fractional EDEN rates (AS:352-368) are not built yet")
-    return _api.eden(x, int(bits_per_dimension), seed=seed).cpu().numpy()
+    return _api.eden(x, bits_per_dimension, seed=seed).cpu().numpy()
 
 
 def QUICFL_quantize(input_vector, bits_per_dimension=1):
@@ -90,37 +95,22 @@ def QUICFL_quantize(input_vector, bits_per_dimension=1):
 
 def Kashin_quantize(input_vector, bits_per_dimension=1):
     """AS:834-854: Kashin frame coefficients (AS:191-239, eta=0.9, delta=1, pad_threshold=0.85, 3 iterations) then
-    min/max stochastic quantization (AS:62-91).  Rotations and the quantizer are the sm_100a kernels; the clamp /
-    residual updates between them are elementwise torch ops on the device.  Returns numpy (AS:854)."""
-    x = _vec(input_vector)
-    dim = x.numel()
-    seed, rot_seed = int(torch.randint(0, 100, (1,)).item()), 123
-    eta, delta, pad_threshold, niters = 0.9, 1.0, 0.85, 3
-    pdim = 1 << int(np.ceil(np.log2(dim))) if dim & (dim - 1) else 2 * dim                      # AS:203-211
-    if dim & (dim - 1) and dim / pdim > pad_threshold:
-        pdim *= 2
-    coeff = torch.zeros(pdim, device=x.device)
-    resid = x.clone()
-    M = torch.norm(resid) / np.sqrt(delta * pdim)                                                # AS:221
-    for i in range(niters):
-        padded = torch.zeros(pdim, device=x.device)
-        padded[:dim] = resid
-        b = _api.rht(padded, rot_seed)                                                           # AS:225
-        b_hat = torch.clamp(b, min=-M, max=M)
-        coeff += b_hat                                                                           # AS:229
-        if i < niters - 1:
-            resid = resid - _api.irht(b_hat, rot_seed)[:dim]                                     # AS:232-233
-            M = M * eta
-        err = (x - _api.irht(coeff, rot_seed)[:dim]).norm(2) / resid.norm(2)                     # AS:236
-        if err < 1e-6:
-            break
-    q = _api.scalar_quantize(coeff, bits_per_dimension, seed=seed * 1000003 + 17)                # AS:62-91 ("standard" step)
-    return _api.irht(q, rot_seed)[:dim].cpu().numpy()                                            # AS:262-267, AS:854
+    min/max stochastic quantization (AS:62-91) -- `dme_b200.kashin`.  Returns numpy (AS:854)."""
+    seed = int(torch.randint(0, 100, (1,)).item())                          # AS:841
+    return _api.kashin(_vec(input_vector), bits_per_dimension, seed=seed * 1000003 + (_seed() >> 20), rotation_seed=123).cpu().numpy()
 
 
 def No_quantize(input_vector, bits_per_dimension=1):
     """AS:856-859."""
     return _vec(input_vector).clone()
+
+
+def _write_back(arg, result):
+    """The reference's transforms work in place; keep that for tensors we can write to (same shape, fp32, CUDA)."""
+    if isinstance(arg, torch.Tensor) and arg.is_cuda and arg.dtype == torch.float32 and arg.shape == result.shape:
+        arg.copy_(result)
+        return arg
+    return result
 
 
 class Hadamard:
@@ -130,7 +120,8 @@ class Hadamard:
         self.device = device
 
     def hadamard(self, vec):
-        return _api.hadamard(vec)
+        """AS:100-115 transforms its argument in place and returns it: a CUDA fp32 tensor is written back."""
+        return _write_back(vec, _api.hadamard(vec))
 
     def random_diagonal(self, size, seed):
         return _api.rademacher(size, seed)
@@ -143,7 +134,8 @@ class HadamardSender(Hadamard):
 
 class HadamardReceiver(Hadamard):
     def randomized_inverse_hadamard_transform(self, vec, seed):
-        return _api.irht(vec, seed)
+        """AS:151-156 mutates its argument (AS:153) and returns it: a CUDA fp32 tensor is written back."""
+        return _write_back(vec, _api.irht(vec, seed))
 
 
 __all__ = ["Type_unbiased_quantize", "Type_biased_quantize", "DRIVE_quantize_Hadamard", "Scalar_quantize",

@@ -590,12 +590,30 @@ def drive(x, *, seed=0, dsign_inject=None, compat="reference"):
     return out[0] if was_1d else out
 
 
-def eden_encode(x, nbits=1, *, seed=0, diag_inject=None, norm_inject=None):
-    """EdenSender.compress (AS:370-390, integer nbits in {1,2}) -> dict(bins uint8 [n,dpad], scale [n], rot [n,dpad]).
-    Row c is rotated with the diagonal of seed + c (the reference draws a fresh seed per call, AS:800) unless a
-    diagonal is injected."""
-    if nbits not in (1, 2):
-        raise KeyError(nbits)           # AS:301-320 defines centroids for 1 and 2 bits only (SURVEY F8)
+def _eden_rates(nbits):
+    """AS:382-389: integer rates and rates below 1 bit use ONE table (ceil(nbits)); fractional rates above 1 mix the tables of
+    floor(nbits) and ceil(nbits) with probability nbits - floor(nbits) for the high one.  -> (low, high, p_high, pdrop)"""
+    nb = float(nbits)
+    if nb <= 0:
+        raise KeyError(nbits)
+    if nb == round(nb) or nb < 1:
+        b = int(np.ceil(nb))
+        if b not in (1, 2):
+            raise KeyError(nbits)       # AS:301-320 defines centroids for 1 and 2 bits only (SURVEY F8)
+        return b, b, 0.0, (1.0 - nb if nb < 1 else 0.0)
+    lo, hi = int(np.floor(nb)), int(np.ceil(nb))
+    if lo not in (1, 2) or hi not in (1, 2):
+        raise KeyError(nbits)
+    return lo, hi, nb - lo, 0.0
+
+
+def eden_encode(x, nbits=1, *, seed=0, diag_inject=None, norm_inject=None, mask_inject=None):
+    """EdenSender.compress (AS:370-390) -> dict(bins uint8 [n,dpad], scale [n], rot [n,dpad]).  nbits in {1, 2}, a rate below 1
+    (quantized at 1 bit; the receiver drops coordinates, AS:413-421) or a fractional rate in (1, 2) (AS:352-368: per-coordinate
+    Bernoulli mask between the 1- and 2-bit tables; mask_inject uint8 [n, dpad] or Philox keyed by seed * 7 + 13, AS:389).
+    Row c is rotated with the diagonal of seed + c (the reference draws a fresh seed per call, AS:800) unless a diagonal is
+    injected."""
+    lo, hi, p_high, pdrop = _eden_rates(nbits)
     X, n, d, was_1d = _rows(x)
     dpad = _pow2_ceil(d)
     dev = X.device
@@ -604,28 +622,119 @@ def eden_encode(x, nbits=1, *, seed=0, diag_inject=None, norm_inject=None):
     scale = torch.empty(n, dtype=torch.float32, device=dev)
     dg = _diag(diag_inject, dpad, dev)
     ni = _opt_vec(norm_inject, n, dev)
-    _check(_cabi.lib().dme_eden_encode(_ptr(X), n, d, _ld(X), dpad, nbits, seed, 1, _ptr(dg), _ptr(ni), _ptr(rot), _ptr(bins), _ptr(scale),
-                                       C.c_void_p(_stream())))
-    return {"bins": bins, "scale": scale, "rot": rot, "d": d, "dpad": dpad, "nbits": nbits, "seed": seed, "was_1d": was_1d}
+    mk = None
+    if mask_inject is not None:
+        mk = torch.as_tensor(mask_inject).to(dev, torch.uint8).reshape(n, dpad).contiguous()
+    if lo == hi:
+        _check(_cabi.lib().dme_eden_encode(_ptr(X), n, d, _ld(X), dpad, lo, seed, 1, _ptr(dg), _ptr(ni), _ptr(rot), _ptr(bins), _ptr(scale),
+                                           C.c_void_p(_stream())))
+    else:
+        _check(_cabi.lib().dme_eden_encode_frac(_ptr(X), n, d, _ld(X), dpad, lo, hi, float(p_high), _ptr(mk), seed, 1, _ptr(dg), _ptr(ni),
+                                                _ptr(rot), _ptr(bins), _ptr(scale), C.c_void_p(_stream())))
+    return {"bins": bins, "scale": scale, "rot": rot, "d": d, "dpad": dpad, "nbits": nbits, "seed": seed, "was_1d": was_1d, "mask": mk}
 
 
-def eden_decode(enc, *, diag_inject=None):
-    """EdenReceiver.decompress (AS:398-426)."""
+def eden_decode(enc, *, diag_inject=None, drop_inject=None, pdrop=0.0):
+    """EdenReceiver.decompress (AS:398-426).  Rates below 1 bit and pdrop > 0 zero round(dpad * p) coordinates per row (AS:413-421:
+    a random permutation's head, drawn with torch on the device; drop_inject uint8 [n, dpad] replaces the draw) and divide the
+    rest by 1 - p."""
     bins, scale = enc["bins"], enc["scale"]
     n, dpad = bins.shape
     d = enc["d"]
     dev = bins.device
+    lo, hi, p_high, p0 = _eden_rates(enc["nbits"])
+    p = p0 + (1.0 - p0) * float(pdrop) if pdrop > 0 else p0                               # AS:408-411
     work = torch.empty((n, dpad), dtype=torch.float32, device=dev)
     out = torch.empty((n, (d + 3) // 4 * 4), dtype=torch.float32, device=dev)
     dg = _diag(diag_inject, dpad, dev)
-    _check(_cabi.lib().dme_eden_decode(_ptr(bins), _ptr(scale), n, d, dpad, enc["nbits"], enc["seed"], 1, _ptr(dg), _ptr(work), _ptr(out),
-                                       out.stride(0), C.c_void_p(_stream())))
+    if lo == hi and p == 0:
+        _check(_cabi.lib().dme_eden_decode(_ptr(bins), _ptr(scale), n, d, dpad, lo, enc["seed"], 1, _ptr(dg), _ptr(work), _ptr(out),
+                                           out.stride(0), C.c_void_p(_stream())))
+    else:
+        drop = None
+        if p > 0:
+            if drop_inject is not None:
+                drop = torch.as_tensor(drop_inject).to(dev, torch.uint8).reshape(n, dpad).contiguous()
+            else:
+                k = int(round(dpad * p))                                                   # AS:416
+                drop = torch.zeros((n, dpad), dtype=torch.uint8, device=dev)
+                for c in range(n):
+                    drop[c, torch.randperm(dpad, device=dev)[:k]] = 1
+        _check(_cabi.lib().dme_eden_decode_frac(_ptr(bins), _ptr(scale), n, d, dpad, lo, hi, float(p_high), _ptr(enc.get("mask")), _ptr(drop),
+                                                float(1.0 - p), enc["seed"], 1, _ptr(dg), _ptr(work), _ptr(out), out.stride(0),
+                                                C.c_void_p(_stream())))
     out = out[:, :d]
     return out[0] if enc.get("was_1d") else out
 
 
 def eden(x, nbits=1, *, seed=0, diag_inject=None):
     return eden_decode(eden_encode(x, nbits, seed=seed, diag_inject=diag_inject), diag_inject=diag_inject)
+
+
+def kashin_padded_dim(dim: int, pad_threshold: float = 0.85) -> int:
+    """KashinSender.kashin_padded_dim (AS:203-211)."""
+    if dim & (dim - 1):
+        p = 1 << int(math.ceil(math.log2(dim)))
+        return 2 * p if dim / p > pad_threshold else p
+    return 2 * dim
+
+
+def kashin(x, bits_per_dimension=1, *, seed=0, rotation_seed=123, eta=0.9, delta=1.0, pad_threshold=0.85, niters=3, err=1e-6,
+           diag_inject=None, m0_inject=None, u_inject=None, want_parts=False):
+    """Kashin_quantize on every row (AS:834-854): Kashin frame coefficients (KashinSender.kashin_coefficients AS:213-239: niters
+    rounds of randomized Hadamard transform -> clamp to +-M -> accumulate -> residual, M *= eta) -> min/max stochastic
+    quantization of the coefficients (StochasticQuantizationSender AS:67-83, "standard" step, nlevels = 2^bits) -> receiver
+    (AS:90, AS:262-267): min + bins * step, inverse transform, [:dim].
+    The transforms are the FWHT kernels (all rows in one launch, shared diagonal of rotation_seed); the clamp / residual / rounding
+    steps are elementwise device ops.  No host synchronisation: the reference's early exit `if err < 1e-6: break` (AS:236-238)
+    is a per-row device flag that freezes the row's coefficients.
+    m0_inject [n]: the initial M (= ||x||_2 / sqrt(delta * pdim), an fp32 reduction without a defined order in the reference);
+    u_inject [n, pdim]: the uniforms of the Bernoulli draw of AS:81; diag_inject [pdim]: the rotation diagonal."""
+    X, n, d, was_1d = _rows(x)
+    dev = X.device
+    X = X[:, :d]
+    pdim = kashin_padded_dim(d, pad_threshold)
+    coeff = torch.zeros((n, pdim), dtype=torch.float32, device=dev)
+    resid = X.clone()
+    if m0_inject is not None:
+        M = _opt_vec(m0_inject, n, dev).reshape(n, 1)
+    else:
+        # tensor / tensor: torch's CUDA division by a SCALAR multiplies by its reciprocal, which is not the IEEE quotient
+        M = torch.linalg.vector_norm(X, dim=1, keepdim=True) / torch.full((n, 1), float(np.float32(np.sqrt(delta * pdim))), device=dev)   # AS:221
+    done = torch.zeros((n, 1), dtype=torch.bool, device=dev)
+    padded = torch.zeros((n, pdim), dtype=torch.float32, device=dev)
+    for i in range(int(niters)):
+        padded.zero_()
+        padded[:, :d] = resid                                                                   # AS:223-224
+        b = rht(padded, rotation_seed, diag_inject=diag_inject).reshape(n, pdim)                # AS:225
+        b_hat = torch.maximum(torch.minimum(b, M), -M)                                          # AS:228 (clamp(b, -M, M))
+        coeff = torch.where(done, coeff, coeff + b_hat)                                         # AS:229
+        if i < niters - 1:
+            back = irht(b_hat, rotation_seed, diag_inject=diag_inject).reshape(n, pdim)         # AS:232
+            resid = torch.where(done, resid, resid - back[:, :d])                               # AS:233
+            M = torch.where(done, M, M * np.float32(eta))                                       # AS:234
+        rec = irht(coeff, rotation_seed, diag_inject=diag_inject).reshape(n, pdim)[:, :d]
+        e = torch.linalg.vector_norm(X - rec, dim=1, keepdim=True) / torch.linalg.vector_norm(resid, dim=1, keepdim=True)   # AS:236
+        done = done | (e < err)                                                                 # AS:237-238
+    # StochasticQuantizationSender.compress (AS:67-83) / Receiver.decompress (AS:90), per row
+    nlevels = np.float32(2 ** bits_per_dimension)
+    vmin = coeff.min(dim=1, keepdim=True).values
+    vmax = coeff.max(dim=1, keepdim=True).values
+    step = (vmax - vmin) / torch.full((n, 1), float(nlevels - np.float32(1)), device=dev)       # AS:72 (IEEE quotient, see above)
+    r = (coeff - vmin) / step                                                                   # AS:80
+    fl = torch.floor(r)
+    if u_inject is not None:
+        u = torch.as_tensor(u_inject, dtype=torch.float32).to(dev).reshape(n, pdim)
+    else:
+        g = torch.Generator(device=dev).manual_seed(int(seed) & 0x7FFFFFFFFFFFFFFF)
+        u = torch.rand((n, pdim), dtype=torch.float32, device=dev, generator=g)
+    bins = fl + (u < (r - fl)).to(torch.float32)                                                # AS:81
+    deq = vmin + bins * step                                                                    # AS:90
+    out = irht(deq, rotation_seed, diag_inject=diag_inject).reshape(n, pdim)[:, :d]             # AS:267
+    out = out[0] if was_1d else out
+    if want_parts:
+        return {"out": out, "coeff": coeff, "bins": bins, "min": vmin.reshape(-1), "step": step.reshape(-1), "pdim": pdim}
+    return out
 
 
 def quicfl_decode(Xq, h, d, recv_table, scale, *, exact_mask=None, exact_vals=None, rotation_seed=123, diag_inject=None):

@@ -127,6 +127,50 @@ __global__ void eden_scale_kernel(const double *__restrict__ partial, int nb, in
     for (int b = 0; b < nb; ++b) s += partial[c * nb + b];
     scale[c] = __fdiv_rn(__fmul_rn(nrm[c], nrm[c]), (float)s);                     // AS:348
 }
+// Fractional rates (AS:352-368): coordinate i uses the high-rate table where mask_i is set, the low-rate table elsewhere.
+// mask_i = injected byte, or [u_i < p_high] with u_i from Philox keyed by the client's mask seed (AS:389: seed * 7 + 13).
+constexpr uint32_t kStreamEdenMask = 0x45444Du;  // "EDM"
+__device__ __forceinline__ bool eden_mask_bit(const uint8_t *__restrict__ mask, int64_t c, int64_t dpad, int64_t i, uint64_t mseed, float p_high) {
+    if (mask) return mask[c * dpad + i] != 0;
+    const Philox4 p = philox4x32_10(mseed, (uint32_t)(i >> 2), (uint32_t)((uint64_t)i >> 34), 0u, kStreamEdenMask);
+    const uint32_t w = (i & 3) == 0 ? p.x : (i & 3) == 1 ? p.y : (i & 3) == 2 ? p.z : p.w;
+    return u24_to_unit(w) < p_high;
+}
+__global__ void __launch_bounds__(256)
+eden_bucket_frac_kernel(const float *__restrict__ V, int64_t dpad, int64_t ld, int nb, const float *__restrict__ nrm, float sq, EdenTab tlo, EdenTab thi,
+                        const uint8_t *__restrict__ mask, uint64_t seed, uint64_t seed_stride, float p_high, uint8_t *__restrict__ bins,
+                        double *__restrict__ partial) {
+    __shared__ double s_red[kWarps];
+    const int64_t c = blockIdx.y;
+    const int64_t per = (dpad + nb - 1) / nb, lo = blockIdx.x * per, hi = min(dpad, lo + per);
+    const float nr = nrm[c];
+    const uint64_t mseed = (seed + seed_stride * (uint64_t)c) * 7ull + 13ull;
+    double s = 0.0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
+        const float v = V[c * ld + i];
+        const float z = __fdiv_rn(__fmul_rn(v, sq), nr);                           // AS:354-355
+        const EdenTab &tab = eden_mask_bit(mask, c, dpad, i, mseed, p_high) ? thi : tlo;     // AS:360-364
+        int b = 0;
+        while (b < tab.nc - 1 && tab.bnd[b] < z) ++b;
+        bins[c * dpad + i] = (uint8_t)b;
+        s += (double)tab.cent[b] * (double)v;                                      // AS:366
+    }
+    s = block_sum_f64(s, s_red);
+    if (threadIdx.x == 0) partial[c * nb + blockIdx.x] = s;
+}
+// AS:400-421: centroid look-up by the coordinate's table, then the optional drop (zero the coordinate, rescale the rest)
+__global__ void eden_lookup_frac_kernel(const uint8_t *__restrict__ bins, int64_t n, int64_t dpad, EdenTab tlo, EdenTab thi, const uint8_t *__restrict__ mask,
+                                        uint64_t seed, uint64_t seed_stride, float p_high, const uint8_t *__restrict__ drop, float inv_keep,
+                                        float *__restrict__ work) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n * dpad) return;
+    const int64_t c = k / dpad, i = k - c * dpad;
+    const uint64_t mseed = (seed + seed_stride * (uint64_t)c) * 7ull + 13ull;
+    const bool high = p_high >= 1.0f || (p_high > 0.0f && eden_mask_bit(mask, c, dpad, i, mseed, p_high));
+    float v = (high ? thi : tlo).cent[bins[k] & 3];
+    if (drop) v = drop[k] ? 0.0f : __fdiv_rn(v, inv_keep);                         // AS:419-421 (inv_keep = 1 - pdrop)
+    work[k] = v;
+}
 // four bins -> four centroids per thread (total is a multiple of 4: rows are padded to a power of two >= 4 or handled by the tail)
 __global__ void eden_lookup_kernel(const uint8_t *__restrict__ bins, int64_t total, EdenTab tab, float *__restrict__ work) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, i = 4 * q;
@@ -316,32 +360,56 @@ extern "C" int dme_drive(const float *X, int64_t n, int64_t d, int64_t ld, float
     return DME_OK;
 }
 
-extern "C" int dme_eden_encode(const float *X, int64_t n, int64_t d, int64_t ld, int64_t dpad, int nbits, uint64_t seed,
-                               uint64_t seed_stride, const float *diag_inject, const float *norm_inject, float *rot, uint8_t *bins, float *scale,
-                               dme_stream_t stream) {
+// stream-ordered scratch that is released on every exit path
+struct AsyncScratch {
+    void *p = nullptr; cudaStream_t st;
+    explicit AsyncScratch(cudaStream_t s) : st(s) {}
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes, st); }
+    ~AsyncScratch() { if (p) cudaFreeAsync(p, st); }
+};
+
+static int eden_encode_impl(const float *X, int64_t n, int64_t d, int64_t ld, int64_t dpad, int nbits_low, int nbits_high, float p_high,
+                            const uint8_t *mask_inject, uint64_t seed, uint64_t seed_stride, const float *diag_inject, const float *norm_inject,
+                            float *rot, uint8_t *bins, float *scale, cudaStream_t st) {
     DME_REQUIRE(X && rot && bins && scale && n >= 1 && n <= 65535, "bad argument");
-    DME_REQUIRE(nbits == 1 || nbits == 2, "EDEN centroids exist for 1 and 2 bits only (AS:301-320)");
-    cudaStream_t st = (cudaStream_t)stream;
+    DME_REQUIRE((nbits_low == 1 || nbits_low == 2) && (nbits_high == 1 || nbits_high == 2), "EDEN centroids exist for 1 and 2 bits only (AS:301-320)");
     int rc = fwht_rows(X, d, ld, rot, dpad, dpad, n, diag_inject, seed, seed_stride, 1, 0, st);                   // AS:378-380
     if (rc) return rc;
     const int nb = slices(dpad);
-    double *partial = nullptr;
-    DME_CUDA(cudaMallocAsync(&partial, sizeof(double) * (size_t)(n * nb), st));
-    float *nrm = nullptr;
-    DME_CUDA(cudaMallocAsync(&nrm, sizeof(float) * (size_t)n, st));
+    AsyncScratch partial(st), nrm(st);
+    DME_CUDA(partial.alloc(sizeof(double) * (size_t)(n * nb)));
+    DME_CUDA(nrm.alloc(sizeof(float) * (size_t)n));
     dim3 grid((unsigned)nb, (unsigned)n);
-    row_sumsq_kernel<<<grid, 256, 0, st>>>(rot, dpad, dpad, nb, partial);
+    row_sumsq_kernel<<<grid, 256, 0, st>>>(rot, dpad, dpad, nb, (double *)partial.p);
     DME_LAUNCH_CHECK("row_sumsq_kernel");
-    norm_finalize_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(partial, nb, n, norm_inject, nrm);
+    norm_finalize_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((double *)partial.p, nb, n, norm_inject, (float *)nrm.p);
     DME_LAUNCH_CHECK("norm_finalize_kernel");
     const float sq = (float)std::pow((double)dpad, 0.5);                                             // vec.numel() ** 0.5
-    eden_bucket_kernel<<<grid, 256, 0, st>>>(rot, dpad, dpad, nb, nrm, sq, eden_tab(nbits), bins, partial);
-    DME_LAUNCH_CHECK("eden_bucket_kernel");
-    eden_scale_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(partial, nb, n, nrm, scale);
+    if (nbits_low == nbits_high) {
+        eden_bucket_kernel<<<grid, 256, 0, st>>>(rot, dpad, dpad, nb, (float *)nrm.p, sq, eden_tab(nbits_low), bins, (double *)partial.p);
+        DME_LAUNCH_CHECK("eden_bucket_kernel");
+    } else {
+        eden_bucket_frac_kernel<<<grid, 256, 0, st>>>(rot, dpad, dpad, nb, (float *)nrm.p, sq, eden_tab(nbits_low), eden_tab(nbits_high), mask_inject,
+                                                     seed, seed_stride, p_high, bins, (double *)partial.p);
+        DME_LAUNCH_CHECK("eden_bucket_frac_kernel");
+    }
+    eden_scale_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((double *)partial.p, nb, n, (float *)nrm.p, scale);
     DME_LAUNCH_CHECK("eden_scale_kernel");
-    DME_CUDA(cudaFreeAsync(partial, st));
-    DME_CUDA(cudaFreeAsync(nrm, st));
     return DME_OK;
+}
+
+extern "C" int dme_eden_encode(const float *X, int64_t n, int64_t d, int64_t ld, int64_t dpad, int nbits, uint64_t seed,
+                               uint64_t seed_stride, const float *diag_inject, const float *norm_inject, float *rot, uint8_t *bins, float *scale,
+                               dme_stream_t stream) {
+    return eden_encode_impl(X, n, d, ld, dpad, nbits, nbits, 0.0f, nullptr, seed, seed_stride, diag_inject, norm_inject, rot, bins, scale,
+                            (cudaStream_t)stream);
+}
+extern "C" int dme_eden_encode_frac(const float *X, int64_t n, int64_t d, int64_t ld, int64_t dpad, int nbits_low, int nbits_high, float p_high,
+                                    const uint8_t *mask_inject, uint64_t seed, uint64_t seed_stride, const float *diag_inject,
+                                    const float *norm_inject, float *rot, uint8_t *bins, float *scale, dme_stream_t stream) {
+    DME_REQUIRE(p_high >= 0.0f && p_high <= 1.0f, "p_high=%f outside [0, 1]", (double)p_high);
+    return eden_encode_impl(X, n, d, ld, dpad, nbits_low, nbits_high, p_high, mask_inject, seed, seed_stride, diag_inject, norm_inject, rot, bins,
+                            scale, (cudaStream_t)stream);
 }
 
 extern "C" int dme_eden_decode(const uint8_t *bins, const float *scale, int64_t n, int64_t d, int64_t dpad, int nbits, uint64_t seed,
@@ -352,6 +420,25 @@ extern "C" int dme_eden_decode(const uint8_t *bins, const float *scale, int64_t 
     const int64_t total = n * dpad;
     eden_lookup_kernel<<<(unsigned)((total + 1023) / 1024), 256, 0, st>>>(bins, total, eden_tab(nbits), work);
     DME_LAUNCH_CHECK("eden_lookup_kernel");
+    int rc = fwht_rows(work, dpad, dpad, work, dpad, dpad, n, diag_inject, seed, seed_stride, 0, 1, st);   // AS:425
+    if (rc) return rc;
+    scale_rows_kernel<<<dim3((unsigned)((d + 1023) / 1024), (unsigned)n), 256, 0, st>>>(work, dpad, scale, n, d, out, ld_out);
+    DME_LAUNCH_CHECK("scale_rows_kernel");
+    return DME_OK;
+}
+// Fractional rates and drops (AS:401-421).  drop (n * dpad bytes, nullable): coordinates the receiver zeroes; the rest is divided
+// by keep = 1 - pdrop.
+extern "C" int dme_eden_decode_frac(const uint8_t *bins, const float *scale, int64_t n, int64_t d, int64_t dpad, int nbits_low, int nbits_high,
+                                    float p_high, const uint8_t *mask_inject, const uint8_t *drop, float keep, uint64_t seed, uint64_t seed_stride,
+                                    const float *diag_inject, float *work, float *out, int64_t ld_out, dme_stream_t stream) {
+    DME_REQUIRE(bins && scale && work && out && n >= 1 && d >= 1 && dpad >= d && ld_out >= d, "bad argument");
+    DME_REQUIRE((nbits_low == 1 || nbits_low == 2) && (nbits_high == 1 || nbits_high == 2), "EDEN centroids exist for 1 and 2 bits only (AS:301-320)");
+    DME_REQUIRE(p_high >= 0.0f && p_high <= 1.0f && (!drop || keep > 0.0f), "p_high / keep out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total = n * dpad;
+    eden_lookup_frac_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(bins, n, dpad, eden_tab(nbits_low), eden_tab(nbits_high), mask_inject, seed,
+                                                                            seed_stride, nbits_low == nbits_high ? 0.0f : p_high, drop, keep, work);
+    DME_LAUNCH_CHECK("eden_lookup_frac_kernel");
     int rc = fwht_rows(work, dpad, dpad, work, dpad, dpad, n, diag_inject, seed, seed_stride, 0, 1, st);   // AS:425
     if (rc) return rc;
     scale_rows_kernel<<<dim3((unsigned)((d + 1023) / 1024), (unsigned)n), 256, 0, st>>>(work, dpad, scale, n, d, out, ld_out);
@@ -381,8 +468,9 @@ extern "C" int dme_scalar_quantize(const float *X, int64_t n, int64_t d, int64_t
     DME_REQUIRE(X && out && n >= 1 && n <= 65535 && d >= 1 && ld >= d && ld_out >= d, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = slices_minmax(d);
-    float *pm = nullptr;
-    DME_CUDA(cudaMallocAsync(&pm, sizeof(float) * (size_t)(2 * n * nb), st));
+    AsyncScratch pms(st);
+    DME_CUDA(pms.alloc(sizeof(float) * (size_t)(2 * n * nb)));
+    float *pm = (float *)pms.p;
     dim3 grid((unsigned)nb, (unsigned)n);
     row_minmax_kernel<<<grid, 256, 0, st>>>(X, d, ld, nb, pm, pm + n * nb);
     DME_LAUNCH_CHECK("row_minmax_kernel");
@@ -391,6 +479,5 @@ extern "C" int dme_scalar_quantize(const float *X, int64_t n, int64_t d, int64_t
     dim3 grid2((unsigned)((d + per_cta - 1) / per_cta), (unsigned)n);
     scalar_kernel<<<grid2, 256, 0, st>>>(X, n, d, ld, nb, pm, pm + n * nb, nlevels, seed, client0, u_inject, out, ld_out, vec_ok);
     DME_LAUNCH_CHECK("scalar_kernel");
-    DME_CUDA(cudaFreeAsync(pm, st));
     return DME_OK;
 }

@@ -57,10 +57,7 @@ def _estimate(line: str, X: torch.Tensor, seed: int, kashin: bool):
     if line.startswith("Scalar_"):
         return api.mean_accumulate(api.scalar_quantize(X, int(line[-4]), seed=seed))
     if line.startswith("Kashin_") and kashin:
-        est = torch.zeros(X.shape[1], device=X.device)
-        for c in range(n):                       # Kashin's iteration is per vector (AS:191-239): the drop-in function
-            est += torch.as_tensor(All_Schemes.Kashin_quantize(X[c], int(line[-4])), device=X.device) / n
-        return est
+        return api.mean_accumulate(api.kashin(X, int(line[-4]), seed=seed))      # all rows per transform launch (AS:191-239, AS:834-854)
     return None                                  # QUIC-FL, Kashin when disabled
 
 

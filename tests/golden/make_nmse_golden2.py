@@ -1,0 +1,72 @@
+"""NMSE statistics of the UNMODIFIED reference (CPU), round 2: (a) the reference's OWN five distributions (Normal_dist.py:89,
+Laplace_dist.py:89, Gamma_dist.py:86, Bernoulli_dist.py:90, Lognormal_dist.py:90) at n=10, d=1024, 100 trials, with the
+Kashin and fractional-EDEN lines added; (b) a slice of BASELINE config 2: Gaussian, d = 2^16, n in {10, 100}.
+Standard NMSE = |est - mean|^2 / mean_i |x_i|^2.  Writes tests/golden/nmse_reference2.json.
+
+    python tests/golden/make_nmse_golden2.py [a|b]
+"""
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_adapter  # noqa: E402
+
+warnings.filterwarnings("ignore")
+AS = ref_adapter.load()
+torch.set_num_threads(8)
+OUT = os.path.join(ROOT, "tests", "golden", "nmse_reference2.json")
+
+DISTS = {
+    "normal": lambda rng, n, d: rng.normal(0, 1, (n, d)),
+    "laplace": lambda rng, n, d: rng.laplace(1, 2, (n, d)),
+    "gamma": lambda rng, n, d: rng.gamma(2, 2, (n, d)),
+    "bernoulli": lambda rng, n, d: rng.choice(np.arange(2), size=(n, d), p=[0.3, 0.7]),
+    "lognormal12": lambda rng, n, d: rng.lognormal(1, 2, (n, d)),
+}
+SCHEMES = {
+    "Type_unbiased R=1": lambda v: AS.Type_unbiased_quantize(v, 1), "Type_unbiased R=2": lambda v: AS.Type_unbiased_quantize(v, 2),
+    "Type_biased R=1": lambda v: AS.Type_biased_quantize(v, 1), "Type_biased R=2": lambda v: AS.Type_biased_quantize(v, 2),
+    "EDEN R=1": lambda v: AS.EDEN_quantize_Hadamard(v, 1), "EDEN R=2": lambda v: AS.EDEN_quantize_Hadamard(v, 2),
+    "EDEN R=1.5": lambda v: AS.EDEN_quantize_Hadamard(v, 1.5),
+    "DRIVE R=1": lambda v: AS.DRIVE_quantize_Hadamard(v, 1), "Scalar R=2": lambda v: AS.Scalar_quantize(v, 2),
+    "Kashin R=2": lambda v: AS.Kashin_quantize(v, 2),
+}
+
+
+def stats(dist, n, d, trials, names):
+    torch.manual_seed(42)
+    rng = np.random.default_rng(42)
+    vals = {k: [] for k in names}
+    for t in range(trials):
+        X = DISTS[dist](rng, n, d).astype(np.float32)
+        mean = X.sum(0) / n
+        den = float((X.astype(np.float64) ** 2).sum() / n)
+        for name in names:
+            est = np.zeros(d, np.float32)
+            for c in range(n):
+                est += np.asarray(torch.as_tensor(SCHEMES[name](X[c])), dtype=np.float32) / n          # ND:133-147
+            vals[name].append(float(((est - mean).astype(np.float64) ** 2).sum()) / den)
+    return {k: {"mean": float(np.mean(v)), "ci95": float(1.96 * np.std(v, ddof=1) / np.sqrt(trials))} for k, v in vals.items()}
+
+
+out = json.load(open(OUT)) if os.path.exists(OUT) else {"convention": "standard", "sets": {}}
+which = sys.argv[1] if len(sys.argv) > 1 else "ab"
+if "a" in which:
+    for dist in DISTS:
+        key = f"{dist} n=10 d=1024"
+        out["sets"][key] = {"dist": dist, "n": 10, "d": 1024, "trials": 100, "stats": stats(dist, 10, 1024, 100, list(SCHEMES))}
+        print(key, {k: (round(s["mean"], 5), round(s["ci95"], 5)) for k, s in out["sets"][key]["stats"].items()}, flush=True)
+        json.dump(out, open(OUT, "w"), indent=1)
+if "b" in which:
+    names = [k for k in SCHEMES if k != "Kashin R=2"]
+    for n, trials in ((10, 60), (100, 12)):
+        key = f"normal n={n} d=65536"
+        out["sets"][key] = {"dist": "normal", "n": n, "d": 65536, "trials": trials, "stats": stats("normal", n, 65536, trials, names)}
+        print(key, {k: (round(s["mean"], 6), round(s["ci95"], 6)) for k, s in out["sets"][key]["stats"].items()}, flush=True)
+        json.dump(out, open(OUT, "w"), indent=1)

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import struct
 from dataclasses import dataclass
 
 import numpy as np
@@ -15,6 +16,7 @@ import torch
 from . import _cabi
 
 TILE = 1024          # coordinates per tile of the packed code (DME_TILE)
+MSG_HEADER = struct.Struct("<8sIIIQQQQfI")      # PackedCodes.to_messages
 MODE = {"unbiased": 0, "biased": 1, 0: 0, 1: 1}
 
 # AS:614-620 (the API of the reference: R -> m/d; kept verbatim because it IS the interface)
@@ -92,7 +94,9 @@ def _ld(x) -> int:
 
 
 class Workspace:
-    """Caller-owned scratch for the type-quantizer entry points (grown on demand, one per device)."""
+    """Caller-owned scratch for the type-quantizer entry points (grown on demand), one per (device, CUDA stream): the kernels
+    of a call keep their ticket counter, look-back records and status word there, so two calls enqueued on different streams
+    must not share it."""
     _cache = {}
 
     def __init__(self, device):
@@ -101,7 +105,7 @@ class Workspace:
 
     @classmethod
     def get(cls, device) -> "Workspace":
-        key = (device.type, device.index)
+        key = (device.type, device.index, int(torch.cuda.current_stream(device).cuda_stream))
         if key not in cls._cache:
             cls._cache[key] = Workspace(device)
         return cls._cache[key]
@@ -152,6 +156,13 @@ def client_uniforms(seed: int, client0: int, n: int) -> np.ndarray:
 
 def _resolve_m(d, bits_per_dimension, m):
     return int(m) if m is not None else m_for_rate(bits_per_dimension, d)
+
+
+def _check_out(out, d, dev):
+    """A caller-supplied mean buffer: fp32, contiguous, on the device of the rows, at least d elements, 16-byte aligned."""
+    if not (isinstance(out, torch.Tensor) and out.dtype == torch.float32 and out.is_contiguous() and out.device == dev and
+            out.numel() >= d and out.data_ptr() % 16 == 0):
+        raise ValueError(f"out must be a contiguous 16-byte aligned float32 tensor on {dev} with at least {d} elements")
 
 
 def _opt_vec(v, n, dev):
@@ -225,6 +236,56 @@ class PackedCodes:
         w = (self.dir & 0xFF).sum().item()
         return int(w) * 128
 
+    def bits_per_coordinate(self) -> float:
+        """Rate of the code as sent by a client (payload + one width byte per tile + header), in bits per coordinate: to be
+        read against the table's R (AS:614-620) -- the fixed-width fields overshoot it."""
+        T = (self.d + TILE - 1) // TILE
+        return 8.0 * (self.payload_bytes() + self.n * (T + MSG_HEADER.size)) / float(self.n * self.d)
+
+    # ---- wire format: one self-contained message per client (what a client uploads, TU:216-229 ships a dense fp32 vector)
+    def to_messages(self, seed: int = 0, client0: int = 0):
+        """-> list of n `bytes`: header {magic "DMEP1", version, mode, tile, d, m, client id, seed, L1 fp32, tile count}, one
+        width byte per tile, then the tiles' words (little-endian uint32, 128 * width bytes each) in tile order."""
+        T = (self.d + TILE - 1) // TILE
+        dirh = self.dir.cpu().numpy().view(np.uint64).reshape(self.n, T)
+        arena = self.codes.cpu().numpy()
+        l1 = self.l1.cpu().numpy()
+        msgs = []
+        for c in range(self.n):
+            w = (dirh[c] & np.uint64(0xFF)).astype(np.uint8)
+            off = (dirh[c] >> np.uint64(8)).astype(np.int64) * 16
+            parts = [MSG_HEADER.pack(b"DMEP1\0\0\0", 1, self.mode, TILE, self.d, self.m, client0 + c, seed, float(l1[c]), T), w.tobytes()]
+            parts += [arena[off[t]: off[t] + 128 * int(w[t])].tobytes() for t in range(T)]
+            msgs.append(b"".join(parts))
+        return msgs
+
+    @classmethod
+    def from_messages(cls, msgs, device=None) -> "PackedCodes":
+        """Server side: n client messages -> device arena + directory + norms, ready for `decode_mean`."""
+        dev = _device(device)
+        heads = [MSG_HEADER.unpack_from(m, 0) for m in msgs]
+        magic, ver, mode, tile, d, mm, _, _, _, T = heads[0]
+        if magic != b"DMEP1\0\0\0" or ver != 1 or tile != TILE:
+            raise ValueError("not a DMEP1 message of this library's tile size")
+        n = len(msgs)
+        dirh = np.zeros((n, T), np.uint64)
+        l1 = np.zeros(n, np.float32)
+        chunks, pos = [], 0
+        for c, (m, h) in enumerate(zip(msgs, heads)):
+            if h[:6] != heads[0][:6] or h[9] != T:
+                raise ValueError(f"message {c} does not match the first one (mode / d / m)")
+            l1[c] = h[8]
+            w = np.frombuffer(m, np.uint8, T, MSG_HEADER.size).astype(np.int64)
+            if not np.all(np.isin(w, (2, 4, 8, 16, 32))) or len(m) != MSG_HEADER.size + T + 128 * int(w.sum()):
+                raise ValueError(f"message {c} is malformed")
+            starts = pos + np.concatenate([[0], np.cumsum(128 * w)[:-1]])
+            dirh[c] = ((starts // 16).astype(np.uint64) << np.uint64(8)) | w.astype(np.uint64)
+            chunks.append(np.frombuffer(m, np.uint8, 128 * int(w.sum()), MSG_HEADER.size + T))
+            pos += 128 * int(w.sum())
+        arena = np.concatenate(chunks + [np.zeros(16, np.uint8)])
+        return cls(torch.from_numpy(arena).to(dev), torch.from_numpy(dirh.reshape(-1).view(np.int64)).to(dev), torch.from_numpy(l1).to(dev),
+                   n, int(d), int(mm), int(mode))
+
 
 def type_encode(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, client0=0, x_inject=None, l1_inject=None,
                 codes_bytes=None, check=True) -> PackedCodes:
@@ -254,8 +315,12 @@ def type_encode(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, cli
     return PackedCodes(codes, dr, l1, n, d, mm, MODE[mode])
 
 
-def decode_mean(pc: PackedCodes, *, n_total=None, out=None, accumulate=False, tiles=None):
+def decode_mean(pc: PackedCodes, *, n_total=None, out=None, accumulate=False, tiles=None, weights=None):
     """Server side: dequantise (AS:640 / AS:687) and average, `est += q / n` in client order (ND:133-147).
+
+    weights [n] (positive integers, e.g. flwr's num_examples): the weighted mean sum_c w_c q_c / sum_c w_c of FedAvg's
+    aggregate (TU:260-269; flwr 1.11.1 aggregate()) -- client c's norm is scaled by w_c (exact in fp32 for w_c < 2^24 and a
+    norm with free low bits, one extra rounding otherwise) and the divisor becomes sum w.
 
     tiles=(tile0, count) decodes only coordinates [tile0 * TILE, (tile0 + count) * TILE) of `out` (slices of the mean
     complete in order, so a sharded run can all-reduce one slice while the next is decoded)."""
@@ -263,10 +328,19 @@ def decode_mean(pc: PackedCodes, *, n_total=None, out=None, accumulate=False, ti
     if out is None:
         out = torch.empty(pc.d, dtype=torch.float32, device=dev)
         accumulate = False
+    else:
+        _check_out(out, pc.d, dev)
     nt = pc.n if n_total is None else int(n_total)
+    l1 = pc.l1
+    if weights is not None:
+        w = torch.as_tensor(weights).to(dev).reshape(-1)
+        if w.numel() != pc.n or bool((w <= 0).any()):
+            raise ValueError("weights: one positive entry per client")
+        l1 = (pc.l1 * w.to(torch.float32)).contiguous()
+        nt = int(w.sum().item()) if n_total is None else int(n_total)
     T = (pc.d + TILE - 1) // TILE
     t0, cnt = (0, T) if tiles is None else (int(tiles[0]), int(tiles[1]))
-    _check(_cabi.lib().dme_decode_mean_tiles(_ptr(pc.codes), _ptr(pc.dir), _ptr(pc.l1), pc.n, pc.d, pc.m, pc.mode, nt, _ptr(out),
+    _check(_cabi.lib().dme_decode_mean_tiles(_ptr(pc.codes), _ptr(pc.dir), _ptr(l1), pc.n, pc.d, pc.m, pc.mode, nt, _ptr(out),
                                              int(bool(accumulate)), t0, cnt, C.c_void_p(_stream())))
     return out
 
@@ -284,6 +358,8 @@ def quantize_mean_sliced(x, bits_per_dimension=1, *, slices=4, on_slice=None, mo
     plan = _MeanPlan.get(n, d, mm, dev)
     if out is None:
         out = torch.empty(d, dtype=torch.float32, device=dev)
+    else:
+        _check_out(out, d, dev)
     xi = _opt_vec(x_inject, n, dev)
     nt = n if n_total is None else int(n_total)
     while True:
@@ -322,9 +398,11 @@ class _MeanPlan:
 
     @classmethod
     def get(cls, n, d, m, dev):
-        key = (n, d, m, dev.index)
+        st = int(torch.cuda.current_stream(dev).cuda_stream)
+        key = (n, d, m, dev.index, st)
         if key not in cls._cache:
-            cls._cache.clear()              # keep one plan: the arena can be GiBs
+            for k in [k for k in cls._cache if k[3] == dev.index and k[4] == st]:
+                del cls._cache[k]           # one plan per (device, stream): the arena can be GiBs; other streams keep theirs
             cls._cache[key] = _MeanPlan(n, d, m, dev)
         return cls._cache[key]
 
@@ -349,10 +427,21 @@ def quantize_mean(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, c
     if out is None:
         out = torch.empty(d, dtype=torch.float32, device=dev)
         accumulate = False
+    else:
+        _check_out(out, d, dev)
     xi = _opt_vec(x_inject, n, dev)
     nt = n if n_total is None else int(n_total)
     while True:
         try:
+            if accumulate and check:
+                # adding to `out` cannot be undone: encode first, read the status word, decode only a complete code (an arena
+                # overflow drops tiles).  check=False keeps the single fused call and does NOT detect dropped tiles.
+                _check(L.dme_type_encode(_ptr(X), n, d, _ld(X), mm, MODE[mode], _ptr(xi), None, seed, client0, _ptr(plan.codes), plan.cb,
+                                         _ptr(plan.dir), _ptr(plan.l1), ws, wsb, C.c_void_p(_stream())))
+                Workspace.get(dev).status()
+                _check(L.dme_decode_mean(_ptr(plan.codes), _ptr(plan.dir), _ptr(plan.l1), n, d, mm, MODE[mode], nt, _ptr(out), 1,
+                                         C.c_void_p(_stream())))
+                return out
             _check(L.dme_quantize_mean(_ptr(X), n, d, _ld(X), mm, MODE[mode], _ptr(xi), seed, client0, nt, _ptr(out),
                                        int(bool(accumulate)), _ptr(plan.codes), plan.cb, _ptr(plan.dir), _ptr(plan.l1), ws, wsb,
                                        C.c_void_p(_stream())))
@@ -360,7 +449,7 @@ def quantize_mean(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, c
                 Workspace.get(dev).status()
             return out
         except MemoryError:
-            if accumulate or plan.cb >= int(L.dme_codes_bytes(pn, d, mm, 0)):
+            if plan.cb >= int(L.dme_codes_bytes(pn, d, mm, 0)):
                 raise
             plan.grow_worst_case(pn, d, mm, dev)
 

@@ -96,8 +96,8 @@ def QUICFL_quantize(input_vector, bits_per_dimension=1):
 def Kashin_quantize(input_vector, bits_per_dimension=1):
     """AS:834-854: Kashin frame coefficients (AS:191-239, eta=0.9, delta=1, pad_threshold=0.85, 3 iterations) then
     min/max stochastic quantization (AS:62-91) -- `dme_b200.kashin`.  Returns numpy (AS:854)."""
-    seed = int(torch.randint(0, 100, (1,)).item())                          # AS:841
-    return _api.kashin(_vec(input_vector), bits_per_dimension, seed=seed * 1000003 + (_seed() >> 20), rotation_seed=123).cpu().numpy()
+    seed = int(torch.randint(0, 100, (1,)).item())                          # AS:841: one of 100 Bernoulli streams (AS:67)
+    return _api.kashin(_vec(input_vector), bits_per_dimension, seed=seed, rotation_seed=123).cpu().numpy()
 
 
 def No_quantize(input_vector, bits_per_dimension=1):

@@ -777,6 +777,7 @@ def kashin(x, bits_per_dimension=1, *, seed=0, rotation_seed=123, eta=0.9, delta
     The transforms are the FWHT kernels (all rows in one launch, shared diagonal of rotation_seed); the clamp / residual / rounding
     steps are elementwise device ops.  No host synchronisation: the reference's early exit `if err < 1e-6: break` (AS:236-238)
     is a per-row device flag that freezes the row's coefficients.
+    seed: an int (row c uses seed + c) or one seed per row.
     m0_inject [n]: the initial M (= ||x||_2 / sqrt(delta * pdim), an fp32 reduction without a defined order in the reference);
     u_inject [n, pdim]: the uniforms of the Bernoulli draw of AS:81; diag_inject [pdim]: the rotation diagonal."""
     X, n, d, was_1d = _rows(x)
@@ -815,8 +816,18 @@ def kashin(x, bits_per_dimension=1, *, seed=0, rotation_seed=123, eta=0.9, delta
     if u_inject is not None:
         u = torch.as_tensor(u_inject, dtype=torch.float32).to(dev).reshape(n, pdim)
     else:
-        g = torch.Generator(device=dev).manual_seed(int(seed) & 0x7FFFFFFFFFFFFFFF)
-        u = torch.rand((n, pdim), dtype=torch.float32, device=dev, generator=g)
+        # AS:67, AS:841: the Bernoulli stream of a vector is a function of its `seed` alone -- rows with equal seeds share their
+        # uniforms (the reference draws the seed from 100 values, so that happens and correlates the rounding errors)
+        seeds = [int(seed) + c for c in range(n)] if np.isscalar(seed) else [int(v) for v in seed]
+        if len(seeds) != n:
+            raise ValueError(f"expected {n} seeds")
+        u = torch.empty((n, pdim), dtype=torch.float32, device=dev)
+        g = torch.Generator(device=dev)
+        for sd in sorted(set(seeds)):
+            g.manual_seed(sd & 0x7FFFFFFFFFFFFFFF)
+            row = torch.rand(pdim, dtype=torch.float32, device=dev, generator=g)
+            for c in [c for c in range(n) if seeds[c] == sd]:
+                u[c] = row
     bins = fl + (u < (r - fl)).to(torch.float32)                                                # AS:81
     deq = vmin + bins * step                                                                    # AS:90
     out = irht(deq, rotation_seed, diag_inject=diag_inject).reshape(n, pdim)[:, :d]             # AS:267

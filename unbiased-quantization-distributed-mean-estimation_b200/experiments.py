@@ -57,7 +57,7 @@ def _estimate(line: str, X: torch.Tensor, seed: int, kashin: bool):
     if line.startswith("Scalar_"):
         return api.mean_accumulate(api.scalar_quantize(X, int(line[-4]), seed=seed))
     if line.startswith("Kashin_") and kashin:
-        return api.mean_accumulate(api.kashin(X, int(line[-4]), seed=seed))      # all rows per transform launch (AS:191-239, AS:834-854)
+        return api.mean_accumulate(api.kashin(X, int(line[-4]), seed=np.random.default_rng(seed).integers(0, 100, n)))      # all rows per transform launch (AS:191-239, AS:834-854)
     return None                                  # QUIC-FL, Kashin when disabled
 
 

@@ -291,7 +291,7 @@ def run_ours(a):
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            roof["traffic"] = json.load(open(tr)).get(a.workload, {}).get(dom)
+            roof["traffic"] = json.load(open(tr)).get(a.workload, {}).get(dom.split("<")[0])     # ncu dram read + write per launch, by workload
         except Exception:
             pass
 

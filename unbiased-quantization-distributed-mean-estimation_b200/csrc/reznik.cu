@@ -28,11 +28,44 @@ __device__ __forceinline__ void load_tile_blocked(const float *__restrict__ row,
     }
 }
 
+// striped: fully coalesced 128-bit loads for the passes where the order inside the tile does not matter (sums, histograms,
+// counts); element e of load q of thread t is coordinate tile0 + 1024 q + 4 t + e (zero past the end of the row)
+__device__ __forceinline__ void load_tile_striped(const float *__restrict__ row, int64_t d, int64_t tile0, float (&x)[kEpt]) {
+    if (tile0 + kTile <= d) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = ldg_stream_f4(row + tile0 + q * 1024 + 4 * threadIdx.x);
+            x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t i = tile0 + q * 1024 + 4 * threadIdx.x + e;
+                x[4 * q + e] = (i < d) ? row[i] : 0.0f;
+            }
+    }
+}
+__device__ __forceinline__ int64_t striped_index(int64_t tile0, int j) { return tile0 + (j >> 2) * 1024 + 4 * threadIdx.x + (j & 3); }
+
 // AS:648 + AS:654 for one coordinate: k' and the residual delta' = k' - m p (fp32, one rounding per op).
+// Rows inside the proven operand range of the fast chain (RowConst flags, type_quantize.cuh) get the same values from
+// Markstein's correction of |x| * RN(1/D) (= the correctly rounded quotient) and a magic-number floor (exact below 2^23):
+// 8 instructions instead of an IEEE division and a floorf per coordinate and pass.
 __device__ __forceinline__ void rz_round(float x, const RowConst &rc, float &kp, float &delta) {
-    const float p = __fdiv_rn(fabsf(x), rc.D);                 // AS:683
-    const float mp = __fmul_rn(rc.mf, p);
-    kp = floorf(__fadd_rn(mp, 0.5f));                          // AS:648
+    float mp;
+    if (!(rc.flags & (kRowExact | kRowGuardFloor))) {
+        const float ax = fabsf(x);
+        const float q0 = __fmul_rn(ax, rc.rcpD);
+        const float p = __fmaf_rn(__fmaf_rn(-q0, rc.D, ax), rc.rcpD, q0);          // AS:683
+        mp = __fmul_rn(rc.mf, p);
+        kp = __fsub_rn(__fadd_rz(__fadd_rn(mp, 0.5f), 8388608.0f), 8388608.0f);    // AS:648: floor(mp + 1/2), mp + 1/2 < 2^23
+    } else {
+        const float p = __fdiv_rn(fabsf(x), rc.D);             // AS:683
+        mp = __fmul_rn(rc.mf, p);
+        kp = floorf(__fadd_rn(mp, 0.5f));                      // AS:648
+    }
     delta = __fsub_rn(kp, mp);                                 // AS:654
 }
 // Order-preserving key of the value that torch.topk ranks: delta (Delta > 0) or -delta (Delta < 0).
@@ -47,9 +80,9 @@ __global__ void __launch_bounds__(kThreads)
 rz_sum_kernel(const float *__restrict__ X, int64_t d, int64_t ld, const RowConst *__restrict__ consts, RowSelect *sel) {
     __shared__ unsigned long long s_red[kWarps];
     const int64_t c = blockIdx.y, t = blockIdx.x;
-    const RowConst rc = consts[c];
     float x[kEpt];
-    load_tile_blocked(X + c * ld, d, t * kTile, x);
+    load_tile_striped(X + c * ld, d, t * kTile, x);            // issued first: the row constants' round trip overlaps with it
+    const RowConst rc = consts[c];
     unsigned long long s = 0;
 #pragma unroll
     for (int j = 0; j < kEpt; ++j) {
@@ -84,19 +117,18 @@ __global__ void __launch_bounds__(kThreads)
 rz_hist_kernel(const float *__restrict__ X, int64_t d, int64_t ld, const RowConst *__restrict__ consts, RowSelect *sel, int pass) {
     __shared__ uint32_t s_hist[256];
     const int64_t c = blockIdx.y, t = blockIdx.x;
+    float x[kEpt];
+    load_tile_striped(X + c * ld, d, t * kTile, x);            // issued first: the selection state's round trips overlap with it
     const long long Delta = sel[c].Delta;
     if (Delta == 0 || sel[c].remaining == 0) return;
     const RowConst rc = consts[c];
     const uint32_t prefix = sel[c].prefix;
     s_hist[threadIdx.x] = 0;
     __syncthreads();
-    float x[kEpt];
-    load_tile_blocked(X + c * ld, d, t * kTile, x);
-    const int64_t i0 = t * kTile + (int64_t)threadIdx.x * kEpt;
     const int shift = 24 - 8 * pass;
 #pragma unroll
     for (int j = 0; j < kEpt; ++j) {
-        if (i0 + j >= d) break;
+        if (striped_index(t * kTile, j) >= d) continue;
         float kp, dl;
         rz_round(x[j], rc, kp, dl);
         const uint32_t key = rz_key(dl, Delta < 0);
@@ -129,17 +161,16 @@ rz_tiecnt_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T, 
                  const RowSelect *__restrict__ sel, uint32_t *__restrict__ tie_cnt) {
     __shared__ uint32_t s_red[kWarps];
     const int64_t c = blockIdx.y, t = blockIdx.x;
+    float x[kEpt];
+    load_tile_striped(X + c * ld, d, t * kTile, x);
     const long long Delta = sel[c].Delta;
     uint32_t cnt = 0;
     if (Delta != 0) {
         const RowConst rc = consts[c];
         const uint32_t tie = sel[c].tie_key;
-        float x[kEpt];
-        load_tile_blocked(X + c * ld, d, t * kTile, x);
-        const int64_t i0 = t * kTile + (int64_t)threadIdx.x * kEpt;
 #pragma unroll
         for (int j = 0; j < kEpt; ++j) {
-            if (i0 + j >= d) break;
+            if (striped_index(t * kTile, j) >= d) continue;
             float kp, dl;
             rz_round(x[j], rc, kp, dl);
             cnt += (rz_key(dl, Delta < 0) == tie) ? 1u : 0u;
@@ -195,11 +226,11 @@ rz_apply_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T, c
     __shared__ PackScratch s_pack;
     const int64_t c = blockIdx.y, t = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float x[kEpt];
+    load_tile_blocked(X + c * ld, d, t * kTile, x);
     const RowConst rc = consts[c];
     const long long Delta = sel[c].Delta;
     const uint32_t tie = sel[c].tie_key, take = sel[c].tie_take;
-    float x[kEpt];
-    load_tile_blocked(X + c * ld, d, t * kTile, x);
     const int64_t i0 = t * kTile + (int64_t)threadIdx.x * kEpt;
     float kp[kEpt];
     uint32_t key[kEpt];

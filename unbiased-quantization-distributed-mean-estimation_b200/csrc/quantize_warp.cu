@@ -3,26 +3,27 @@
 // one GPU in ONE launch.  The per-client L1 norms and row constants come from l1_kernel (type_quantize.cu).
 //
 // Unit of work = one WARP and one code tile (1024 coordinates = one directory entry of the packed code).  Warps are independent:
-// no CTA barrier, no shared state between warps; a CTA is only a container for four of them.  A warp draws tickets (client-major
-// tile order), stages its tile with one TMA tensor copy (3-D map {32 floats, 128-byte rows, client}, SWIZZLE_128B, 4 KB box:
-// lane l owns row l = coordinates [32 l, 32 l + 32), its eight 16-byte pieces are conflict-free) into a private ring of three
-// buffers, and runs two phases that are one tile apart:
-//     B-phase (tile i)  : x / D (Markstein), * m, floor (magic add toward zero), fraction -- packed f32x2; every fraction becomes
-//                         a 32-bit fixed-point word (2^-32 units, parked in place of x) and enters the lane's exact fp64 sum;
-//                         lane sums -> 2^-43 fixed point -> warp aggregate (integer REDUX) -> published at once:
-//                         8-byte tile record, one 64-bit atomic on the record of its block of 32 tiles (value + count in one
-//                         word); the tile that completes a block forwards the block total to the super-block record;
+// no CTA barrier, no shared state between warps; a CTA is only a container for four of them.  Warp g works on tiles g, g + G,
+// g + 2G, ... of the client-major tile order (G = resident warps; dynamic tickets let the look-back form convoys),
+// stages its tile with one TMA tensor copy (3-D map {32 floats, 128-byte rows, client}, SWIZZLE_128B, 4 KB box: lane l owns
+// row l = coordinates [32 l, 32 l + 32), its eight 16-byte pieces are conflict-free) into a private ring of three buffers, and
+// runs two phases that are one tile apart:
+//     B-phase (tile i)  : x / D (Markstein), * m, floor (magic add toward zero), fraction -- packed f32x2; the exact fractions are
+//                         parked in place of x and enter the lane's fp64 sum; lane sums -> 2^-43 fixed point -> warp aggregate
+//                         (integer REDUX) -> published at once: 8-byte tile record, one 64-bit atomic on the record of its block
+//                         of 32 tiles (value + count in one word); the tile that completes a block forwards the block total to
+//                         the super-block record;
 //     C-phase (tile i-1): look-back window (<= 31 tile + 31 block + S super-block records, one load per lane) -> exclusive
 //                         prefix P -> every lane's start phase phi = frac(E - Xp) as a 32-bit integer -> the allocation of
-//                         AS:635-637 is the CARRY chain of phi + sum of the parked words: one add-with-carry-out and one
+//                         AS:635-637 is the CARRY chain of phi + sum of trunc(fraction * 2^32): one add-with-carry-out and one
 //                         add-with-carry-in (shift the carry into a mask) per coordinate; emit.
 // Why the carry chain is AS:636.  floor(RN32(RN32(c) - X)) = floor(c - Xp) or ceil(c - Xp) - 1 while the fp32 prefix stays in
 // one binade [2^e + 1, 2^(e+1)), Xp = 2^(e-24) (2a - 1), a = ceil(X / 2^(e-23) - 1/2) (tests/test_closed_form_floor.py): both
 // count the integers crossed by c - Xp and differ only when c - Xp IS an integer.  The integer chain carries truncation errors
-// (< 2^-23 per lane); a lane whose running phase ever comes within the band 2^-22 of an integer, whose prefixes cross a
-// binade, or whose row is outside the proven operand range re-reads its 32 inputs and evaluates AS:636 literally in fp64.
+// (< 2^-26 per lane); a lane whose running phase ever comes within the band 2^-24 of an integer, whose tile straddles a binade,
+// or whose row is outside the proven operand range evaluates AS:636 literally in fp64 from the parked fractions.
 // Integer addition is associative: prefixes do not depend on timing, results are run-to-run deterministic.
-// Every wait is on a smaller ticket whose B-phase never waits: no deadlock while all CTAs are resident.
+// Every wait is on a smaller tile whose B-phase never waits: no deadlock while all CTAs are resident.
 #include <cuda.h>
 
 #include <cmath>

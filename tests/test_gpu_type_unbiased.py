@@ -283,3 +283,23 @@ def test_weighted_mean_and_flower_adapter(dme):
     q2 = dme.type_quantize(d32, 1, seed=9)["deq"].cpu().numpy().astype(np.float64)      # client c is keyed (seed, c) in both calls
     ref2 = (q2 * np.asarray(w, np.float64)[:, None]).sum(0) / sum(w) + glob
     assert np.max(np.abs(new_flat - ref2)) <= 3e-6 * np.max(np.abs(ref2))
+
+
+def test_row_longer_than_32_super_blocks(dme):
+    """d = 2^26 + 12345 coordinates: 65 549 code tiles = 2049 blocks = 65 super-blocks, so the look-back walks more than 32
+    super-block records per lane (the loop path of quantize_warp_kernel) and the tail tile is partial.  Against the oracle."""
+    d = (1 << 26) + 12345
+    g = torch.Generator(device="cuda").manual_seed(11)
+    X = torch.randn((1, d), generator=g, device="cuda")
+    out = dme.type_quantize(X, 1, seed=77, want=("k", "sgn"))
+    m = dme.m_for_rate(1, d)
+    k = out["k"][0].cpu().numpy()
+    assert abs(int(k.sum()) - m) <= 1
+    Xs = dme.client_uniforms(77, 0, 1)
+    o = orc.type_unbiased(X[0].cpu().numpy(), m, float(Xs[0]))
+    assert float(out["l1"][0]) == float(o["L1"])
+    bad = int((k != o["k"]).sum())
+    print(f"d=2^26+12345: {bad} type-vector mismatches vs the sequential-fp64 oracle")
+    assert bad <= 32
+    pc = dme.type_encode(X, 1, seed=77)
+    assert torch.equal(dme.decode_mean(pc, n_total=1), dme.type_quantize(X, 1, seed=77)["deq"][0])

@@ -336,6 +336,24 @@ def run_ours(a):
             e2e = {"value": n_total * d / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(4 * n * d), "d2h_bytes_per_step": int(4 * d),
                    "ms_per_step": ems, "steps": a.e2e_steps, "api": api_name}
             del Xh
+            if a.kind == "type":
+                # the server-side deployment: clients upload packed codes; H2D of the codes, one decode-mean launch, D2H of the mean
+                pch = dme.codes_to_host(dme.type_encode(Xs[0], R, mode=a.mode, seed=77, client0=client0))
+                dme.decode_mean_host(pch, out_host=outh, n_total=n_total, reduce_fn=red)
+                sync()
+                t0 = time.perf_counter()
+                for i in range(a.e2e_steps):
+                    dme.decode_mean_host(pch, out_host=outh, n_total=n_total, reduce_fn=red)
+                sync()
+                sms = (time.perf_counter() - t0) * 1e3 / a.e2e_steps
+                if world > 1:
+                    t = torch.tensor([sms], device=dev, dtype=torch.float64)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    sms = float(t.item())
+                code_bytes = int(pch["codes"].numel() + 8 * pch["dir"].numel() + 4 * pch["l1"].numel())
+                e2e["server_side"] = {"value": n_total * d / (sms * 1e-3), "unit": UNIT, "ms_per_step": sms, "h2d_bytes_per_step": code_bytes,
+                                      "d2h_bytes_per_step": int(4 * d), "api": "dme_b200.decode_mean_host: packed codes in pinned host memory -> H2D -> decode-mean -> D2H of the mean"}
+                del pch
         except Exception as ex:  # pinned allocation can fail on a small host
             e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
 

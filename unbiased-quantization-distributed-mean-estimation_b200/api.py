@@ -345,6 +345,32 @@ def decode_mean(pc: PackedCodes, *, n_total=None, out=None, accumulate=False, ti
     return out
 
 
+def codes_to_host(pc: PackedCodes, pin=True):
+    """The device code as the server receives it: host copies (pinned by default) of arena, directory and norms."""
+    def h(t):
+        o = torch.empty(t.shape, dtype=t.dtype, pin_memory=bool(pin))
+        o.copy_(t)
+        return o
+    return {"codes": h(pc.codes), "dir": h(pc.dir), "l1": h(pc.l1), "n": pc.n, "d": pc.d, "m": pc.m, "mode": pc.mode}
+
+
+def decode_mean_host(codes_host, *, out_host=None, n_total=None, weights=None, reduce_fn=None):
+    """Server-side end to end with HOST buffers: the clients' packed codes (`codes_to_host` / `PackedCodes.from_messages` on the
+    host side of a deployment) go to the GPU -- 0.25-0.3 bytes per coordinate at R = 1 instead of the 4 of a dense upload --, one
+    decode-mean launch, D2H copy of the mean.  reduce_fn(mean_device) runs before the copy back (all-reduce of a sharded run)."""
+    dev = _device()
+    pc = PackedCodes(codes_host["codes"].to(dev, non_blocking=True), codes_host["dir"].to(dev, non_blocking=True),
+                     codes_host["l1"].to(dev, non_blocking=True), codes_host["n"], codes_host["d"], codes_host["m"], codes_host["mode"])
+    mean = decode_mean(pc, n_total=n_total, weights=weights)
+    if reduce_fn is not None:
+        reduce_fn(mean)
+    if out_host is None:
+        out_host = torch.empty(pc.d, dtype=torch.float32, pin_memory=True)
+    out_host.copy_(mean, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return out_host
+
+
 def quantize_mean_sliced(x, bits_per_dimension=1, *, slices=4, on_slice=None, mode="unbiased", m=None, seed=0, client0=0,
                          n_total=None, x_inject=None, out=None, check=True):
     """quantize_mean with the decode split into `slices` runs of tiles; on_slice(out[lo:hi]) is called right after the

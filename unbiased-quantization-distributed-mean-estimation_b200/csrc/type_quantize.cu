@@ -291,6 +291,128 @@ decode_mean_kernel(const uint32_t *__restrict__ codes, const uint64_t *__restric
     }
 }
 
+// Short rows (few code tiles, many clients: BASELINE config 2): the same walk over the clients in order, but FOUR coordinates per
+// thread -- four threads share a chunk's code word (one broadcast load) and four 64-thread CTAs share a tile, so d / 1024 tiles
+// give 4x the CTAs.  Same arithmetic per coordinate as decode_mean_kernel: bit-identical results.
+constexpr int kCptS = 4;
+__global__ void __launch_bounds__(64, 8)
+decode_mean_short_kernel(const uint32_t *__restrict__ codes, const uint64_t *__restrict__ dir, const float *__restrict__ l1,
+                         int64_t n, int64_t d, int64_t T, float mf, float nf, int biased, float *__restrict__ mean, int accumulate,
+                         int64_t tile0) {
+    __shared__ __align__(64) float lut16[kLutClients * 16];
+    __shared__ __align__(8) uint2 sinfo[kLutClients + kBatch];
+    __shared__ uint32_t sslow[kLutClients / kBatch];
+    extern __shared__ unsigned char dec_dyn[];
+    const uint32_t slut = ((uint32_t)__cvta_generic_to_shared(dec_dyn) + 4095u) & ~4095u;
+    for (int i = threadIdx.x; i < 512; i += 64) {
+        const int idx = i >> 5, f0 = idx & 3, f1 = idx >> 2;
+        const float s0 = (f0 & 1) ? ((f0 & 2) ? -1.0f : 1.0f) : 0.0f, s1 = (f1 & 1) ? ((f1 & 2) ? -1.0f : 1.0f) : 0.0f;
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(slut + (uint32_t)i * 8u), "f"(s0), "f"(s1) : "memory");
+    }
+    const uint32_t lanebase = slut | ((threadIdx.x & 31u) << 3);
+    const uint32_t lut16_base = (uint32_t)__cvta_generic_to_shared(lut16);
+    const int64_t t = tile0 + (blockIdx.x >> 2);
+    const int chunk = (int)(blockIdx.x & 3) * 16 + (int)(threadIdx.x >> 2), sub = threadIdx.x & 3;     // fields [4 sub, 4 sub + 4) of the chunk
+    const uint32_t *cptr = codes + chunk;
+    const int64_t i0 = t * kCodeTile + (int64_t)chunk * kEpt + sub * kCptS;
+    const bool live = i0 < d;
+    pf2 acc2[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+        acc2[p] = pf2_pack((accumulate && i0 + 2 * p < d) ? mean[i0 + 2 * p] : 0.0f, (accumulate && i0 + 2 * p + 1 < d) ? mean[i0 + 2 * p + 1] : 0.0f);
+    for (int64_t cb = 0; cb < n; cb += kLutClients) {
+        const int nc = (int)((cb + kLutClients < n) ? kLutClients : n - cb);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nc * kLut; i += 64) {
+            const int k = i & (kLut - 1), c = i >> 3;
+            const float v = k == 0 ? 0.0f : deq_over_n(__ldg(l1 + cb + c), (float)k, mf, nf, biased);
+            lut16[c * 16 + k] = v;
+            lut16[c * 16 + 8 + k] = k == 0 ? 0.0f : __uint_as_float(__float_as_uint(v) ^ 0x80000000u);
+        }
+        for (int i = threadIdx.x; i < kLutClients / kBatch; i += 64) sslow[i] = 0u;
+        __syncthreads();
+        for (int i = threadIdx.x; i < kLutClients + kBatch; i += 64) {
+            uint2 inf = make_uint2(0u, 0u);
+            if (i < nc) {
+                const uint64_t e = __ldg(dir + (cb + i) * T + t);
+                uint32_t W = (uint32_t)(e & 0xffu);
+                if (W > 4u || (e >> 40) != 0ull || (W == 2u && !(fabsf(lut16[i * 16 + 1]) <= 3.0e38f))) { W = kWSlow; atomicOr(&sslow[i / kBatch], 1u); }
+                inf = make_uint2((uint32_t)(e >> 8), W);
+            }
+            sinfo[i] = inf;
+        }
+        __syncthreads();
+        if (!live) continue;
+        DecBatch nx;
+        dec_fetch(nx, sinfo, cptr);
+        for (int c0 = 0; c0 < nc; c0 += kBatch) {
+            const DecBatch cur = nx;
+            dec_fetch(nx, sinfo + c0 + kBatch, cptr);
+            if (sslow[c0 / kBatch] == 0u) {
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    const uint32_t cbase = lut16_base + (uint32_t)(c0 + u) * 64u;
+                    if (cur.wc[u] == 2u) {
+                        const uint32_t w = cur.wa[u] >> (8 * sub);          // the thread's four 2-bit fields
+                        const float v = f32_lds(cbase + 4u);
+                        const pf2 vv = pf2_pack(v, v);
+                        acc2[0] = pf2_fma(pf2_lds(((w << 8) & 0xf00u) | lanebase), vv, acc2[0]);
+                        acc2[1] = pf2_fma(pf2_lds(((w << 4) & 0xf00u) | lanebase), vv, acc2[1]);
+                    } else if (cur.wc[u] == 4u) {
+                        const uint32_t w = ((sub & 2) ? cur.wb[u] : cur.wa[u]) >> (16 * (sub & 1));      // the thread's four nibbles
+#pragma unroll
+                        for (int p = 0; p < 2; ++p) {
+                            float lo, hi;
+                            pf2_unpack(acc2[p], lo, hi);
+                            lo = __fadd_rn(lo, f32_lds((((w >> (8 * p)) & 0xfu) << 2) | cbase));
+                            hi = __fadd_rn(hi, f32_lds((((w >> (8 * p + 4)) & 0xfu) << 2) | cbase));
+                            acc2[p] = pf2_pack(lo, hi);
+                        }
+                    }
+                }
+            } else {
+                // wide fields: decode the whole chunk with this thread's accumulators in place, keep its four coordinates
+                float acc[kEpt];
+#pragma unroll
+                for (int j = 0; j < kEpt; ++j) acc[j] = 0.0f;
+                float m4[4];
+                pf2_unpack(acc2[0], m4[0], m4[1]); pf2_unpack(acc2[1], m4[2], m4[3]);
+                for (int u = 0; u < kBatch; ++u) {
+                    if (c0 + u >= nc) break;
+                    const uint64_t e = __ldg(dir + (cb + c0 + u) * T + t);
+                    const int W = (int)(e & 0xffu);
+                    const uint32_t *tw = codes + (e >> 8) * 4ull;
+                    const float *lutc = lut16 + (c0 + u) * 16;
+                    const float L1c = __ldg(l1 + cb + c0 + u);
+#pragma unroll
+                    for (int j = 0; j < kEpt; ++j) acc[j] = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {                 // place the running sums where decode_generic adds this thread's fields
+                        if (sub == 0) acc[j] = m4[j]; else if (sub == 1) acc[4 + j] = m4[j]; else if (sub == 2) acc[8 + j] = m4[j]; else acc[12 + j] = m4[j];
+                    }
+                    if (W == 2) decode_generic<2>(tw, chunk, lutc, 0.0f, mf, nf, biased, acc);
+                    else if (W == 4) decode_generic<4>(tw, chunk, lutc, 0.0f, mf, nf, biased, acc);
+                    else if (W == 8) decode_generic<8>(tw, chunk, lutc, L1c, mf, nf, biased, acc);
+                    else if (W == 16) decode_generic<16>(tw, chunk, lutc, L1c, mf, nf, biased, acc);
+                    else if (W == 32) decode_generic<32>(tw, chunk, lutc, L1c, mf, nf, biased, acc);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) m4[j] = sub == 0 ? acc[j] : sub == 1 ? acc[4 + j] : sub == 2 ? acc[8 + j] : acc[12 + j];
+                }
+                acc2[0] = pf2_pack(m4[0], m4[1]); acc2[1] = pf2_pack(m4[2], m4[3]);
+            }
+        }
+    }
+    if (!live) return;
+    float m4[4];
+    pf2_unpack(acc2[0], m4[0], m4[1]); pf2_unpack(acc2[1], m4[2], m4[3]);
+    if (i0 + kCptS <= d) *reinterpret_cast<float4 *>(mean + i0) = make_float4(m4[0], m4[1], m4[2], m4[3]);
+    else {
+#pragma unroll
+        for (int j = 0; j < kCptS; ++j)
+            if (i0 + j < d) mean[i0 + j] = m4[j];
+    }
+}
+
 // mean (+)= sum_c Q[c] / n for dequantised rows (ND:133-147), coalesced, clients in order.
 __global__ void mean_accumulate_kernel(const float *__restrict__ Q, int64_t n, int64_t d, int64_t ld, float nf,
                                        float *__restrict__ mean, int accumulate) {
@@ -426,7 +548,12 @@ extern "C" int dme_decode_mean_tiles(const void *codes, const uint64_t *dir, con
     const int64_t T = (d + kCodeTile - 1) / kCodeTile;
     DME_REQUIRE(tile0 >= 0 && tiles >= 0 && tile0 + tiles <= T, "tile range [%lld, %lld) outside [0, %lld)", (long long)tile0,
                 (long long)(tile0 + tiles), (long long)T);
-    if (tiles > 0) {
+    if (tiles > 0 && tiles <= 256) {
+        // few tiles: four coordinates per thread, four CTAs per tile (the client walk is what takes the time: spread it wider)
+        decode_mean_short_kernel<<<(unsigned)(4 * tiles), 64, kSignLutBytes, (cudaStream_t)stream>>>(
+            (const uint32_t *)codes, dir, l1, n, d, T, (float)m, (float)n_total, mode == DME_MODE_BIASED, mean, accumulate, tile0);
+        DME_LAUNCH_CHECK("decode_mean_short_kernel");
+    } else if (tiles > 0) {
         decode_mean_kernel<<<(unsigned)tiles, kCodeChunks, kSignLutBytes, (cudaStream_t)stream>>>(
             (const uint32_t *)codes, dir, l1, n, d, T, (float)m, (float)n_total, mode == DME_MODE_BIASED, mean, accumulate, tile0);
         DME_LAUNCH_CHECK("decode_mean_kernel");

@@ -126,12 +126,13 @@ rz_hist_kernel(const float *__restrict__ X, int64_t d, int64_t ld, const RowCons
     s_hist[threadIdx.x] = 0;
     __syncthreads();
     const int shift = 24 - 8 * pass;
+    const bool neg = Delta < 0, full = (t + 1) * kTile <= d;
 #pragma unroll
     for (int j = 0; j < kEpt; ++j) {
-        if (striped_index(t * kTile, j) >= d) continue;
+        if (!full && striped_index(t * kTile, j) >= d) continue;
         float kp, dl;
         rz_round(x[j], rc, kp, dl);
-        const uint32_t key = rz_key(dl, Delta < 0);
+        const uint32_t key = rz_key(dl, neg);
         const bool match = pass == 0 ? true : ((key >> (shift + 8)) == prefix);
         if (match) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
     }
@@ -219,7 +220,7 @@ struct RzEmit {
     PackTarget pack; int packed;
 };
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 rz_apply_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T, const RowConst *__restrict__ consts,
                 const RowSelect *__restrict__ sel, const uint32_t *__restrict__ tie_base, RzEmit e) {
     __shared__ uint32_t s_w[kWarps];

@@ -9,32 +9,26 @@ L = C.CDLL(_cabi.lib()._name)
 X = torch.randn((n, d), device="cuda")
 out = torch.empty(d, device="cuda")
 T = n * (d // 1024)
-dbg = torch.zeros(T * 6, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(T * 12, dtype=torch.int64, device="cuda")
 dme.quantize_mean(X, 1, seed=0, out=out, check=False)
 torch.cuda.synchronize()
 L.dme_debug_buffer(C.c_void_p(dbg.data_ptr()))
 dme.quantize_mean(X, 1, seed=1, out=out, check=False)
 torch.cuda.synchronize()
 L.dme_debug_buffer(C.c_void_p(0))
-a = dbg.cpu().numpy().reshape(T, 6)
-t0 = a[:, 1][a[:, 1] > 0].min()
-draw, bst, pub, cst, cen = [(a[:, k] - t0) / 1e3 for k in range(5)]
-land = ((a[:, 5] >> 20) - (t0 & ((1 << 44) - 1))) / 1e3
-sm = (a[:, 5] >> 8) & 0xfff; wslot = a[:, 5] & 0xff
+a = dbg.cpu().numpy().reshape(T, 12)
 G = 148 * 16
-print("total us", cen.max())
-sel = slice(4 * G, T - 4 * G)
-print("B start -> publish us: median %.2f p90 %.2f p99 %.2f" % tuple(np.percentile((pub - bst)[sel], [50, 90, 99])))
-print("wait for TMA (B start -> landed) us: median %.2f p90 %.2f p99 %.2f" % tuple(np.percentile((land - bst)[sel], [50, 90, 99])))
-print("draw -> B start us: median %.2f p90 %.2f p99 %.2f" % tuple(np.percentile((bst - draw)[sel], [50, 90, 99])))
-print("publish -> C start us: median %.2f p90 %.2f" % tuple(np.percentile((cst - pub)[sel], [50, 90])))
-print("C start -> C end us: median %.2f p90 %.2f p99 %.2f" % tuple(np.percentile((cen - cst)[sel], [50, 90, 99])))
-# lateness: publish time of tile j relative to the running max of earlier publishes
-pm = np.maximum.accumulate(pub)
-late = pub[1:] - pm[:-1]
-print("tiles published after all their predecessors were (they set the pace): %.3f" % (late > 0).mean())
-# per hardware warp slot: B duration
-for w in sorted(set(wslot[sel].tolist()))[:16]:
-    m = wslot[sel] == w
-    print("warp slot %2d: tiles %6d  B dur median %.2f  iteration (C end - B start of same tile... ) draw->pub %.2f" % (w, m.sum(), np.median((pub - bst)[sel][m]), np.median((pub - draw)[sel][m])))
-np.save("gpurun_out/timeline.npy", a[: 64 * G])
+R = T // G
+t = a[: R * G].astype(np.float64).reshape(R, G, 12)
+t0 = t[:, :, 1][t[:, :, 1] > 0].min()
+t = (t - t0) / 1e3
+r = np.arange(4, R - 4)
+names = {0: "draw", 1: "Bstart", 5: "landed", 9: "Bmath_done", 2: "published", 3: "Cstart(window issued)", 4: "Cend(emit done)", 6: "forwarded", 7: "next_item", 8: "tma_issued"}
+print("total us", t[:, :, 4].max())
+print("round time (Bstart r+1 - Bstart r): %.3f" % np.median(t[r + 1, :, 1] - t[r, :, 1]))
+# events of iteration k of a warp: B tile = round k, C tile = round k-1
+seq = [("Bstart", t[r, :, 1]), ("landed", t[r, :, 5]), ("Bmath_done", t[r, :, 9]), ("published", t[r, :, 2]), ("Cstart", t[r - 1, :, 3]), ("Cend", t[r - 1, :, 4]),
+       ("forwarded", t[r - 1, :, 6]), ("next_item", t[r - 1, :, 7]), ("tma_issued", t[r - 1, :, 8]), ("next Bstart", t[r + 1, :, 1])]
+for (n0, a0), (n1, a1) in zip(seq[:-1], seq[1:]):
+    dd = (a1 - a0).ravel()
+    print("%-12s -> %-12s median %.3f  mean %.3f  p90 %.3f us" % (n0, n1, np.median(dd), dd.mean(), np.percentile(dd, 90)))

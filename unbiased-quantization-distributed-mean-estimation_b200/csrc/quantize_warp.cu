@@ -136,7 +136,7 @@ __device__ unsigned long long *g_dbg = nullptr;       // per ticket: draw, B sta
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t warpid_hw() { uint32_t r; asm volatile("mov.u32 %0, %%warpid;" : "=r"(r)); return r; }
-#define DBG_MARK(tk, f) do { if (g_dbg && lane == 0) g_dbg[(size_t)(tk) * 6 + (f)] = gtime(); } while (0)
+#define DBG_MARK(tk, f) do { if (g_dbg && lane == 0) g_dbg[(size_t)(tk) * 12 + (f)] = gtime(); } while (0)
 #else
 #define DBG_MARK(tk, f) do { } while (0)
 #endif
@@ -476,6 +476,21 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
         nb.sgw0 = nb.sgw1 = nb.flm = nb.L0 = nb.L1 = nb.ex32 = 0; nb.mxl = 0.0f; nb.fmf = 0.0f; nb.Aq = 0; nb.AI = 0;
         nb.fl4[0] = nb.fl4[1] = nb.fl4[2] = nb.fl4[3] = 0;
         unsigned long long blk_old = 0;
+        // Look-back loads of tile iC (earlier tiles of its block, earlier blocks of its super-block, earlier super-blocks): issued
+        // after tile iB has been published; the scan of tile iB runs under their round trip to L2.  (Issued before the B-phase:
+        // 4.4 ms instead of 3.4, right after its arithmetic: 3.5 -- the later, the more of the records are complete.)
+        const int pos = iC.w & 31, bpos = (iC.w >> 5) & 31, S = iC.w >> 10;
+        const unsigned long long *tp = a.trec + (iC.tk - 1u - (uint32_t)lane);
+        const unsigned long long *bp = a.brec + ((uint32_t)iC.c * a.TB + (uint32_t)(S * 32 + lane));
+        const SupRec *sp = a.srec + (uint32_t)iC.c * a.TS;
+        unsigned long long tv = 1ull, bv = 32ull << 58, slo = 32ull << kSupShift, shi = 32ull << kSupShift;
+        auto window_issue = [&]() {
+            if (iC.valid) {
+                if (lane < pos) tv = ld_rec(tp);
+                if (lane < bpos) bv = ld_rec(bp);
+                if (lane < S) ld_rec2(sp + lane, slo, shi);
+            }
+        };
         // ---------------------------------------------------------------- B-phase of tile iB
         if (iB.valid) {
             const RowConst *rcp = a.consts + iB.c;
@@ -485,7 +500,7 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
             DBG_MARK(iB.tk, 1);
             mbar_wait(bars + 8u * sB, (it / kRing) & 1u);
 #ifdef DME_TIMERS
-            if (g_dbg && lane == 0) g_dbg[(size_t)iB.tk * 6 + 5] = ((unsigned long long)smid() << 8) | warpid_hw() | (gtime() << 20);
+            if (g_dbg && lane == 0) g_dbg[(size_t)iB.tk * 12 + 5] = gtime();
 #endif
             if ((int64_t)iB.w * 32 >= a.rows32) {                   // nothing was copied: the tile is the row's tail only
 #pragma unroll
@@ -521,11 +536,12 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
             } else {
                 run = b_phase_body<false>(rowb, swz, D, rcpD, mf, nb);
             }
+            DBG_MARK(iB.tk, 9);
             // lane sum -> 2^-43 fixed point (run < 32): mantissa of run + 1.5 * 2^9
             const double tfx = __dadd_rn(run, 768.0);
-            const uint32_t slo = (uint32_t)__double2loint(tfx), shi = (uint32_t)__double2hiint(tfx) & 0x7ffffu;
-            nb.L0 = slo & 0xffffffu;
-            nb.L1 = __funnelshift_r(slo, shi, 24);
+            const uint32_t flo = (uint32_t)__double2loint(tfx), fhi = (uint32_t)__double2hiint(tfx) & 0x7ffffu;
+            nb.L0 = flo & 0xffffffu;
+            nb.L1 = __funnelshift_r(flo, fhi, 24);
             const uint32_t r0 = __reduce_add_sync(0xffffffffu, nb.L0), r1 = __reduce_add_sync(0xffffffffu, nb.L1);
             const unsigned long long A43 = (unsigned long long)r0 + ((unsigned long long)r1 << 24);
             nb.AI = (uint32_t)(A43 >> 43);
@@ -538,18 +554,7 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
             }
         }
         // ---------------------------------------------------------------- C-phase of tile iC: AS:635-637, emit
-        // its look-back loads (earlier tiles of the block, earlier blocks of the super-block, earlier super-blocks) are issued
-        // first; the scan of tile iB runs under their latency
-        const int pos = iC.w & 31, bpos = (iC.w >> 5) & 31, S = iC.w >> 10;
-        const unsigned long long *tp = a.trec + (iC.tk - 1u - (uint32_t)lane);
-        const unsigned long long *bp = a.brec + ((uint32_t)iC.c * a.TB + (uint32_t)(S * 32 + lane));
-        const SupRec *sp = a.srec + (uint32_t)iC.c * a.TS;
-        unsigned long long tv = 1ull, bv = 32ull << 58, slo = 32ull << kSupShift, shi = 32ull << kSupShift;
-        if (iC.valid) {
-            if (lane < pos) tv = ld_rec(tp);
-            if (lane < bpos) bv = ld_rec(bp);
-            if (lane < S) ld_rec2(sp + lane, slo, shi);
-        }
+        window_issue();
         if (iB.valid) nb.ex32 = warp_excl_scan_u32((nb.L0 >> 11) | (nb.L1 << 13), lane);      // lane sums in 2^-32 units (mod 2^32)
         // The tile that completed its block forwards the block total to the super-block record: at the end of the iteration (the
         // atomic's round trip hides behind the C-phase), but BEFORE this warp starts to wait for anything -- the look-back of a
@@ -710,10 +715,13 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
         }
         if (iC.valid) DBG_MARK(iC.tk, 4);
         if (fwd_pending) forward_block();
+        if (iC.valid) DBG_MARK(iC.tk, 6);
         // buffer sC is free: the tile after the one in flight goes there
         __syncwarp();
         Item iNN = iB.valid ? next_item() : Item{0, 0, 0u, false};
+        if (iC.valid) DBG_MARK(iC.tk, 7);
         if (lane == 0 && iNN.valid) issue_tile(a, &tmap, iNN, ring + (uint32_t)sC * kTileBytes, bars + 8u * sC, pol);
+        if (iC.valid) DBG_MARK(iC.tk, 8);
         iC = iB; iB = iN; iN = iNN;
         cy = nb;
         sB = sB == kRing - 1 ? 0 : sB + 1;

@@ -290,17 +290,19 @@ __device__ __noinline__ double b_phase_exact(uint32_t rowb, uint32_t swz, float 
 }
 
 // ---------------------------------------------------------------------------------------------------------------- C-phase
-// Carry chain over eight parked fractions: p = trunc(frac * 2^32); acc += p (carry out), bits = 2 bits + carry; running minimum
-// of acc for the band test.
-__device__ __forceinline__ void carry8(uint32_t &acc, uint32_t &bits, uint32_t &mn, const uint4 &a, const uint4 &b) {
+// The parked fractions as 32-bit fixed point, truncated: p = trunc(frac * 2^32) (done while the look-back loads are in flight).
+__device__ __forceinline__ void fx8(const uint4 &a, const uint4 &b, uint32_t (&p)[8]) {
     const f2 K = f2_pack(4294967296.0f, 4294967296.0f);
     float s0, s1, s2, s3, s4, s5, s6, s7;
     f2_unpack(f2_mul(f2_pack(__uint_as_float(a.x), __uint_as_float(a.y)), K), s0, s1);
     f2_unpack(f2_mul(f2_pack(__uint_as_float(a.z), __uint_as_float(a.w)), K), s2, s3);
     f2_unpack(f2_mul(f2_pack(__uint_as_float(b.x), __uint_as_float(b.y)), K), s4, s5);
     f2_unpack(f2_mul(f2_pack(__uint_as_float(b.z), __uint_as_float(b.w)), K), s6, s7);
-    const uint32_t p0 = __float2uint_rz(s0), p1 = __float2uint_rz(s1), p2 = __float2uint_rz(s2), p3 = __float2uint_rz(s3);
-    const uint32_t p4 = __float2uint_rz(s4), p5 = __float2uint_rz(s5), p6 = __float2uint_rz(s6), p7 = __float2uint_rz(s7);
+    p[0] = __float2uint_rz(s0); p[1] = __float2uint_rz(s1); p[2] = __float2uint_rz(s2); p[3] = __float2uint_rz(s3);
+    p[4] = __float2uint_rz(s4); p[5] = __float2uint_rz(s5); p[6] = __float2uint_rz(s6); p[7] = __float2uint_rz(s7);
+}
+// Carry chain over eight of them: acc += p (carry out), bits = 2 bits + carry; running minimum of acc for the band test.
+__device__ __forceinline__ void carry8(uint32_t &acc, uint32_t &bits, uint32_t &mn, const uint32_t (&p)[8]) {
     uint32_t t0, t1, t2, t3, t4, t5, t6;
     asm("add.cc.u32 %0, %8, %9;\n\taddc.u32 %7, %7, %7;\n\t"
         "add.cc.u32 %1, %0, %10;\n\taddc.u32 %7, %7, %7;\n\t"
@@ -311,7 +313,7 @@ __device__ __forceinline__ void carry8(uint32_t &acc, uint32_t &bits, uint32_t &
         "add.cc.u32 %6, %5, %15;\n\taddc.u32 %7, %7, %7;\n\t"
         "add.cc.u32 %8, %6, %16;\n\taddc.u32 %7, %7, %7;"
         : "=&r"(t0), "=&r"(t1), "=&r"(t2), "=&r"(t3), "=&r"(t4), "=&r"(t5), "=&r"(t6), "+r"(bits), "+r"(acc)
-        : "r"(p0), "r"(p1), "r"(p2), "r"(p3), "r"(p4), "r"(p5), "r"(p6), "r"(p7));
+        : "r"(p[0]), "r"(p[1]), "r"(p[2]), "r"(p[3]), "r"(p[4]), "r"(p[5]), "r"(p[6]), "r"(p[7]));
     mn = min(mn, min(t0, t1));
     mn = min(mn, min(t2, t3));
     mn = min(mn, min(t4, t5));
@@ -575,6 +577,13 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
             const float X = __ldg(&rcp->X);
             const uint32_t rflags = __ldg(&rcp->flags);
             const uint32_t buf = ring + (uint32_t)sC * kTileBytes, rowb = buf + rowoff;
+            // the parked fractions become fixed-point words while the look-back loads are in flight
+            uint32_t pw[4][8];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint4 va = lds128u(rowb + (((uint32_t)(2 * g) << 4) ^ swz)), vb = lds128u(rowb + (((uint32_t)(2 * g + 1) << 4) ^ swz));
+                fx8(va, vb, pw[g]);
+            }
             unsigned long long P;
             DBG_MARK(iC.tk, 3);
             for (;;) {
@@ -636,10 +645,7 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
             }
             uint32_t acc = phi + kBand, bits = 0, mn = acc;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const uint4 va = lds128u(rowb + (((uint32_t)(2 * g) << 4) ^ swz)), vb = lds128u(rowb + (((uint32_t)(2 * g + 1) << 4) ^ swz));
-                carry8(acc, bits, mn, va, vb);
-            }
+            for (int g = 0; g < 4; ++g) carry8(acc, bits, mn, pw[g]);
             uint32_t rm = __brev(bits);
             slow = slow || mn < 2u * kBand;
             if (__any_sync(0xffffffffu, slow)) {

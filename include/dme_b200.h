@@ -132,6 +132,16 @@ DME_API int dme_quantize_mean(const float *X, int64_t n, int64_t d, int64_t ld, 
 DME_API int dme_mean_accumulate(const float *Q, int64_t n, int64_t d, int64_t ld, int64_t n_total, float *mean,
                         int accumulate, dme_stream_t stream);
 
+/* The exchange step of a sharded run over NVLink peer memory: every rank's partial mean sits in a symmetric buffer
+ * (d floats rounded up to a multiple of 4, the same on every GPU, mapped into every process: bufs = DEVICE array of the `world`
+ * mappings of the allocations, the vector starts offset_bytes into each; multicast = the NVSwitch multicast mapping of the same
+ * allocations or NULL).  Rank `rank` sums slice `rank` of the vector
+ * over all ranks -- inside the switch when `multicast` is given (multimem.ld_reduce / multimem.st), else by peer loads in rank order
+ * 0..world-1 -- and writes it into every rank's buffer.  The caller separates it from the writers of the partial means and from the
+ * readers of the result by cross-GPU barriers (dme_b200/distributed.py uses the symmetric-memory barrier). */
+DME_API int dme_peer_sum_slice(float *const *bufs, float *multicast, int64_t offset_bytes, int rank, int world, int64_t d,
+                       dme_stream_t stream);
+
 /* ---- rotations ---- */
 /* In-place normalised natural-order Walsh-Hadamard transform of n rows of dpad (power of two) floats. */
 DME_API int dme_hadamard(float *V, int64_t n, int64_t dpad, int64_t ld, dme_stream_t stream);

@@ -30,6 +30,7 @@ SIGNATURES = {
     "dme_decode_mean_tiles": (ci, [vp, vp, vp, i64, i64, i64, ci, i64, vp, ci, i64, i64, vp]),
     "dme_quantize_mean": (ci, [vp, i64, i64, i64, i64, ci, vp, u64, u64, i64, vp, ci, vp, i64, vp, vp, vp, i64, vp]),
     "dme_mean_accumulate": (ci, [vp, i64, i64, i64, i64, vp, ci, vp]),
+    "dme_peer_sum_slice": (ci, [vp, vp, i64, ci, ci, i64, vp]),
     "dme_hadamard": (ci, [vp, i64, i64, i64, vp]),
     "dme_rht": (ci, [vp, i64, i64, i64, vp, i64, i64, u64, u64, vp, vp]),
     "dme_irht": (ci, [vp, i64, i64, i64, u64, u64, vp, vp]),

@@ -57,6 +57,60 @@ def rotated_quantize_mean_sharded(x_local, bits_per_dimension=1, *, n_total: int
     return back.contiguous()
 
 
+class PeerReduce:
+    """The sum of the ranks' partial means by OUR kernels over NVLink peer memory (csrc/peer_reduce.cu) instead of an NCCL
+    all-reduce: `buffer(d)` is a symmetric tensor (torch.distributed._symmetric_memory) to use as `out=` of the local fused path;
+    `sum_(t)` = barrier, every rank reduces and broadcasts its slice (in-switch multimem reduction when the box has a multicast
+    object, peer loads in rank order otherwise), barrier.  One instance per process and vector length."""
+    _cache: dict = {}
+
+    def __init__(self, d: int, group=None, multicast=True):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.d = int(d)
+        self.dpad = (self.d + 3) // 4 * 4
+        self.buf = symm.empty(self.dpad, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.rank, self.world = self.hdl.rank, self.hdl.world_size
+        self.mc = int(self.hdl.multicast_ptr) if (multicast and self.hdl.has_multicast_support and int(self.hdl.multicast_ptr) != 0) else 0
+        self._C = C
+
+    @classmethod
+    def get(cls, d: int, group=None, multicast=True) -> "PeerReduce":
+        key = (int(d), id(group), bool(multicast), torch.cuda.current_device())
+        if key not in cls._cache:
+            cls._cache[key] = PeerReduce(d, group, multicast)
+        return cls._cache[key]
+
+    def buffer(self) -> torch.Tensor:
+        return self.buf[: self.d]
+
+    def sum_(self) -> torch.Tensor:
+        from . import _cabi, api
+        C = self._C
+        self.hdl.barrier(channel=0)                         # every rank's partial mean is in its buffer
+        api._check(_cabi.lib().dme_peer_sum_slice(C.c_void_p(int(self.hdl.buffer_ptrs_dev)), C.c_void_p(self.mc) if self.mc else None,
+                                                  int(self.hdl.offset), self.rank, self.world, self.dpad, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self.hdl.barrier(channel=1)                         # every slice has been broadcast
+        return self.buffer()
+
+
+def quantize_mean_sharded_peer(x_local, bits_per_dimension=1, *, n_total: int, client0: int, seed: int = 0, mode="unbiased", out=None,
+                               group=None, multicast=True, check=False):
+    """quantize_mean_sharded with the exchange step over peer memory: the local fused path writes this rank's partial mean straight
+    into the symmetric buffer, `PeerReduce.sum_` adds the ranks' buffers in place."""
+    from . import api
+    X, n, d, _ = api._rows(x_local)
+    pr = PeerReduce.get(d, group, multicast)
+    api.quantize_mean(X, bits_per_dimension, mode=mode, seed=seed, client0=client0, n_total=n_total, out=pr.buffer(), check=check)
+    res = pr.sum_()
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
 class _Comm:
     """Side stream on which the per-slice all-reduces of quantize_mean_overlapped are enqueued (one per device)."""
     _streams: dict = {}

@@ -24,6 +24,17 @@
 // or whose row is outside the proven operand range evaluates AS:636 literally in fp64 from the parked fractions.
 // Integer addition is associative: prefixes do not depend on timing, results are run-to-run deterministic.
 // Every wait is on a smaller tile whose B-phase never waits: no deadlock while all CTAs are resident.
+//
+// FUSED variant (the product path): the L1 norms are computed by the same kernel, one client row AHEAD of the quantize pass, so
+// that the input is read from HBM once.  In the iteration in which a warp quantizes ticket t it also sums |x| of ticket
+// t + T4 + lead ("A-phase": one TMA tile, L2 evict_last; fp64 lane sums, xor-butterfly) -- a first touch that leaves the row in
+// L2, where the B-phase's copy (evict_first) finds it one row later.  Tile sums are published as tagged 64-bit words (sign bit =
+// written: no fence needed), a relaxed counter per block of 32 tiles elects the warp that adds the block's 32 sums in a fixed
+// order, a counter per row the warp that adds the block sums and publishes the row constants (release).  The order of the
+// additions does not depend on timing or on the grid.  The B-phase of a row's first tiles waits for the row constants (acquire);
+// the A-phase never waits for anything but its own copy, and runs at least one full round ahead: no deadlock.  The three tile
+// buffers of a warp rotate through the roles B-tile -> parked fractions -> A-tile: the next B-tile's copy is started after the
+// A-phase (into the A buffer), the next A-tile's after the C-phase (into the parked buffer).
 #include <cuda.h>
 
 #include <cmath>
@@ -77,6 +88,13 @@ __device__ __forceinline__ void tma_tile_g2s(uint32_t dst, const CUtensorMap *ma
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
 }
+__device__ __forceinline__ uint64_t policy_kind(int kind) {       // 0 evict_normal, 1 evict_last, 2 evict_first
+    uint64_t p;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ uint4 lds128u(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -129,7 +147,14 @@ struct WarpArgs {
     WsHeader *hdr;
     int32_t *k_out; uint8_t *sgn_out; float *deq_out; int64_t ld_out;     // array outputs (EMIT == 0)
     PackTarget pack;                                                    // packed output (EMIT == 1)
+    // FUSED: the A-phase (L1 norms one row ahead)
+    unsigned long long aoff;                   // A ticket = B ticket + aoff, aoff = T4 + lead (lead >= G: at least one round of slack)
+    int polA, polB;                            // L2 policies of the A / B copies
+    unsigned long long *apart, *absum;         // tagged tile sums [n][T4], tagged block sums [n][TB]
+    uint32_t *abcnt, *adone;                   // tiles finished per block [n][TB], blocks finished per row [n]
+    RowConstIn rin;
 };
+constexpr unsigned long long kTag = 1ull << 63;      // sign bit of a non-negative fp64 sum: "written"
 
 #ifdef DME_TIMERS
 __device__ unsigned long long *g_dbg = nullptr;       // per ticket: draw, B start, publish, C start, C end (globaltimer ns), smid << 8 | warp slot
@@ -406,6 +431,80 @@ __device__ __noinline__ void emit_arrays(const WarpArgs &a, int c, int w, int la
     if (ovf) atomicOr(&a.hdr->status, 1u);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------- A-phase (FUSED)
+// Rows of a tile that the tensor map does not cover: a tile that is the row's tail only was not copied at all (zero it), the last
+// d % 32 coordinates of a row arrive as zeros and are patched in by the lane that owns them.
+__device__ __forceinline__ void fix_tile_edges(const WarpArgs &a, int c, int w, uint32_t rowb, uint32_t swz, int lane) {
+    if ((int64_t)w * 32 >= a.rows32) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sts128u(rowb + ((uint32_t)q << 4), make_uint4(0u, 0u, 0u, 0u));
+    }
+    if (a.tail && w == (int)a.T4 - 1) {
+        __syncwarp();
+        if (lane == (int)(a.rows32 - (int64_t)w * 32)) {
+            const float *src = a.X + (int64_t)c * a.ld + a.rows32 * 32;
+            for (int j = 0; j < a.tail; ++j)
+                sts32(rowb + ((((uint32_t)(j >> 2)) << 4) ^ swz) + 4u * (uint32_t)(j & 3), __float_as_uint(src[j]));
+        }
+        __syncwarp();
+    }
+}
+__device__ __forceinline__ unsigned long long ld_tagged(const unsigned long long *p) {      // spin until the word has been written
+    unsigned long long v = ld_rec(p);
+    while (!(v & kTag)) { __nanosleep(64); v = ld_rec(p); }
+    return v;
+}
+// The warp that finished a block of 32 tiles (elected by the block's counter): block sum in a fixed order; the warp that finished
+// the row's last block: row sum in a fixed order, row constants, ready flag.  Cold (once per 32 tiles).
+__device__ __noinline__ void a_block_done(const WarpArgs &a, int c, int blk, int lane) {
+    const int left = (int)a.T4 - blk * 32, cnt = left < 32 ? left : 32;
+    double v = 0.0;
+    if (lane < cnt) v = __longlong_as_double((long long)(ld_tagged(a.apart + ((size_t)c * a.T4 + (size_t)blk * 32 + lane)) & ~kTag));
+    v = warp_sum_f64(v);
+    unsigned old = 0;
+    if (lane == 0) {
+        st_rec(a.absum + ((size_t)c * a.TB + blk), (unsigned long long)__double_as_longlong(v) | kTag);
+        old = atomicAdd(a.adone + c, 1u);
+    }
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old != a.TB - 1u) return;
+    double acc = 0.0;
+    for (uint32_t i = lane; i < a.TB; i += 32)
+        acc += __longlong_as_double((long long)(ld_tagged(a.absum + ((size_t)c * a.TB + i)) & ~kTag));
+    acc = warp_sum_f64(acc);
+    if (lane == 0) {
+        make_row_const(a.rin, c, acc);
+        __threadfence();
+        st_release_u32(&a.rin.consts[c].flags, a.rin.consts[c].flags | kRowReady);
+    }
+}
+// Sum of |x| over the tile in `buf` (client c, tile w): fp64, fixed order; published as a tagged word.  Returns (lane 0) the
+// block counter's previous value -- the caller looks at it later (the atomic's round trip hides behind the C-phase).
+__device__ __forceinline__ unsigned a_phase(const WarpArgs &a, int c, int w, uint32_t buf, int lane, uint32_t swz) {
+    const uint32_t rowb = buf + (uint32_t)lane * 128u;
+    fix_tile_edges(a, c, w, rowb, swz, lane);
+    double ra = 0.0, rb = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const uint4 v = lds128u(rowb + (((uint32_t)q << 4) ^ swz));
+        ra += (double)fabsf(__uint_as_float(v.x)); rb += (double)fabsf(__uint_as_float(v.y));
+        ra += (double)fabsf(__uint_as_float(v.z)); rb += (double)fabsf(__uint_as_float(v.w));
+    }
+    const double s = warp_sum_f64(ra + rb);
+    unsigned old = 0;
+    if (lane == 0) {
+        st_rec(a.apart + ((size_t)c * a.T4 + (size_t)w), (unsigned long long)__double_as_longlong(s) | kTag);
+        old = atomicAdd(a.abcnt + ((size_t)c * a.TB + ((uint32_t)w >> 5)), 1u);
+    }
+    return old;
+}
+__device__ __forceinline__ void a_check(const WarpArgs &a, int c, int w, unsigned old, int lane) {
+    old = __shfl_sync(0xffffffffu, old, 0);
+    const int blk = w >> 5, left = (int)a.T4 - blk * 32;
+    if (old == (unsigned)(left < 32 ? left : 32) - 1u) a_block_done(a, c, blk, lane);
+}
+
 // ---------------------------------------------------------------------------------------------------------------- the kernel
 __device__ __forceinline__ Item item_of(const WarpArgs &a, uint32_t tk) {
     Item it; it.c = 0; it.w = 0; it.tk = tk; it.valid = tk < a.total;
@@ -427,7 +526,7 @@ __device__ __forceinline__ void issue_tile(const WarpArgs &a, const CUtensorMap 
     }
 }
 
-template <int EMIT>
+template <int EMIT, bool FUSED>
 __global__ void __launch_bounds__(kQThreads, 4)
 quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char dyn_smem[];      // per warp: three 4 KB tile buffers; then the mbarriers
@@ -436,7 +535,7 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
     const uint32_t bars = smem_u32(dyn_smem) + (uint32_t)(kQWarps * kRing * kTileBytes) + (uint32_t)warp * 32u;
     const uint32_t scratch = smem_u32(dyn_smem) + (uint32_t)(kQWarps * kRing * kTileBytes) + (uint32_t)kQWarps * 32u + (uint32_t)threadIdx.x * 32u;
     const uint32_t swz = ((uint32_t)lane & 7u) << 4, rowoff = (uint32_t)lane * 128u;
-    const uint64_t pol = policy_evict_first();
+    const uint64_t pol = FUSED ? policy_kind(a.polB) : policy_evict_first();
     if (lane == 0) {
         for (int q = 0; q < kRing; ++q) mbar_init(bars + 8u * q, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -462,9 +561,39 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
     Item iB = item_of(a, gw), iN = item_of(a, G + gw), iC;
     if (!iN.valid) tk_more = false;
     iC.c = 0; iC.w = 0; iC.tk = 0; iC.valid = false;
+    uint32_t ph = 0;                            // bit q: parity of the phase buffer q's barrier completes next
+    int known = -1;                             // FUSED: the last row whose constants this warp has seen ready
+    if (FUSED) {
+        // Prologue: the A-phase of tickets [0, aoff), i.e. the first row and the lead, through all three buffers.
+        const unsigned long long npro = a.aoff < (unsigned long long)a.total ? a.aoff : (unsigned long long)a.total;
+        const uint64_t polA = policy_kind(a.polA);
+        if (lane == 0) {
+            for (int q = 0; q < kRing; ++q) {
+                const unsigned long long t = (unsigned long long)q * G + gw;
+                if (t < npro) issue_tile(a, &tmap, item_of(a, (uint32_t)t), ring + (uint32_t)q * kTileBytes, bars + 8u * q, polA);
+            }
+        }
+        int q = 0;
+        for (unsigned long long t = gw; t < npro; t += G) {
+            const Item ia = item_of(a, (uint32_t)t);
+            mbar_wait(bars + 8u * q, (ph >> q) & 1u);
+            ph ^= 1u << q;
+            const unsigned old = a_phase(a, ia.c, ia.w, ring + (uint32_t)q * kTileBytes, lane, swz);
+            __syncwarp();
+            const unsigned long long t3 = t + 3ull * G;
+            if (lane == 0 && t3 < npro) issue_tile(a, &tmap, item_of(a, (uint32_t)t3), ring + (uint32_t)q * kTileBytes, bars + 8u * q, polA);
+            a_check(a, ia.c, ia.w, old, lane);
+            q = q == kRing - 1 ? 0 : q + 1;
+        }
+        __syncwarp();
+    }
     if (lane == 0) {
         if (iB.valid) issue_tile(a, &tmap, iB, ring, bars, pol);
-        if (iN.valid) issue_tile(a, &tmap, iN, ring + kTileBytes, bars + 8u, pol);
+        if (FUSED) {
+            // the A-tile of the first iteration
+            const unsigned long long tA = (unsigned long long)gw + a.aoff;
+            if (iB.valid && tA < (unsigned long long)a.total) issue_tile(a, &tmap, item_of(a, (uint32_t)tA), ring + kTileBytes, bars + 8u, policy_kind(a.polA));
+        } else if (iN.valid) issue_tile(a, &tmap, iN, ring + kTileBytes, bars + 8u, pol);
     }
     Carry cy;                                   // of tile iC
     cy.sgw0 = cy.sgw1 = cy.flm = cy.L0 = cy.L1 = cy.ex32 = 0; cy.mxl = 0.0f; cy.fmf = 0.0f; cy.Aq = 0; cy.AI = 0;
@@ -473,7 +602,7 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
     int sB = 0;
     for (uint32_t it = 0;; ++it) {
         if (!iB.valid && !iC.valid) break;
-        const int sC = sB == 0 ? kRing - 1 : sB - 1;
+        const int sC = sB == 0 ? kRing - 1 : sB - 1, sA = sB == kRing - 1 ? 0 : sB + 1;
         Carry nb;                               // of tile iB
         nb.sgw0 = nb.sgw1 = nb.flm = nb.L0 = nb.L1 = nb.ex32 = 0; nb.mxl = 0.0f; nb.fmf = 0.0f; nb.Aq = 0; nb.AI = 0;
         nb.fl4[0] = nb.fl4[1] = nb.fl4[2] = nb.fl4[3] = 0;
@@ -496,28 +625,21 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
         // ---------------------------------------------------------------- B-phase of tile iB
         if (iB.valid) {
             const RowConst *rcp = a.consts + iB.c;
+            if (FUSED && iB.c != known) {
+                // the row's constants come from the A-phase of the warp that finished its L1 sum (normally long ago)
+                while (!(ld_acquire_u32(&rcp->flags) & kRowReady)) __nanosleep(128);
+                known = iB.c;
+            }
             const float D = __ldg(&rcp->D), rcpD = __ldg(&rcp->rcpD), mf = __ldg(&rcp->mf);
             const uint32_t rflags = __ldg(&rcp->flags);
             const uint32_t buf = ring + (uint32_t)sB * kTileBytes, rowb = buf + rowoff;
             DBG_MARK(iB.tk, 1);
-            mbar_wait(bars + 8u * sB, (it / kRing) & 1u);
+            mbar_wait(bars + 8u * sB, (ph >> sB) & 1u);
+            ph ^= 1u << sB;
 #ifdef DME_TIMERS
             if (g_dbg && lane == 0) g_dbg[(size_t)iB.tk * 12 + 5] = gtime();
 #endif
-            if ((int64_t)iB.w * 32 >= a.rows32) {                   // nothing was copied: the tile is the row's tail only
-#pragma unroll
-                for (int q = 0; q < 8; ++q) sts128u(rowb + ((uint32_t)q << 4), make_uint4(0u, 0u, 0u, 0u));
-            }
-            if (a.tail && iB.w == (int)a.T4 - 1) {
-                // the last d % 32 coordinates of the row are not covered by the tensor map (their row arrived as zeros)
-                __syncwarp();
-                if (lane == (int)(a.rows32 - (int64_t)iB.w * 32)) {
-                    const float *src = a.X + (int64_t)iB.c * a.ld + a.rows32 * 32;
-                    for (int j = 0; j < a.tail; ++j)
-                        sts32(rowb + ((((uint32_t)(j >> 2)) << 4) ^ swz) + 4u * (uint32_t)(j & 3), __float_as_uint(src[j]));
-                }
-                __syncwarp();
-            }
+            fix_tile_edges(a, iB.c, iB.w, rowb, swz, lane);
             bool exact = (rflags & kRowExact) != 0u;
             if (!exact && (rflags & kRowGuardFloor)) {
                 // m * p can reach 2^23 in this row: lanes that actually see such a value use floorf
@@ -558,6 +680,21 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
         // ---------------------------------------------------------------- C-phase of tile iC: AS:635-637, emit
         window_issue();
         if (iB.valid) nb.ex32 = warp_excl_scan_u32((nb.L0 >> 11) | (nb.L1 << 13), lane);      // lane sums in 2^-32 units (mod 2^32)
+        // ---------------------------------------------------------------- A-phase of ticket iB.tk + aoff (one row ahead)
+        unsigned a_old = 0;
+        Item iA; iA.c = 0; iA.w = 0; iA.tk = 0; iA.valid = false;
+        if (FUSED && iB.valid) {
+            const unsigned long long tA = (unsigned long long)iB.tk + a.aoff;
+            if (tA < (unsigned long long)a.total) {
+                iA = item_of(a, (uint32_t)tA);
+                mbar_wait(bars + 8u * sA, (ph >> sA) & 1u);
+                ph ^= 1u << sA;
+                a_old = a_phase(a, iA.c, iA.w, ring + (uint32_t)sA * kTileBytes, lane, swz);
+            }
+            // the A buffer is free: the next B-tile goes there (it comes from L2: the C-phase is time enough)
+            __syncwarp();
+            if (lane == 0 && iN.valid) issue_tile(a, &tmap, iN, ring + (uint32_t)sA * kTileBytes, bars + 8u * sA, pol);
+        }
         // The tile that completed its block forwards the block total to the super-block record: at the end of the iteration (the
         // atomic's round trip hides behind the C-phase), but BEFORE this warp starts to wait for anything -- the look-back of a
         // later super-block depends on it.
@@ -726,7 +863,13 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
         __syncwarp();
         Item iNN = iB.valid ? next_item() : Item{0, 0, 0u, false};
         if (iC.valid) DBG_MARK(iC.tk, 7);
-        if (lane == 0 && iNN.valid) issue_tile(a, &tmap, iNN, ring + (uint32_t)sC * kTileBytes, bars + 8u * sC, pol);
+        if (FUSED) {
+            // the parked buffer is free: the next iteration's A-tile (first touch, from HBM) goes there
+            const unsigned long long tA = (unsigned long long)iN.tk + a.aoff;
+            if (lane == 0 && iN.valid && tA < (unsigned long long)a.total)
+                issue_tile(a, &tmap, item_of(a, (uint32_t)tA), ring + (uint32_t)sC * kTileBytes, bars + 8u * sC, policy_kind(a.polA));
+            if (iA.valid) a_check(a, iA.c, iA.w, a_old, lane);
+        } else if (lane == 0 && iNN.valid) issue_tile(a, &tmap, iNN, ring + (uint32_t)sC * kTileBytes, bars + 8u * sC, pol);
         if (iC.valid) DBG_MARK(iC.tk, 8);
         iC = iB; iB = iN; iN = iNN;
         cy = nb;
@@ -737,7 +880,10 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
 // ------------------------------------------------------------------ host side
 // Function attributes, occupancy and the SM count are per device: set / queried once for every device the library is used on
 // (one process may drive several GPUs), under a mutex.
-struct WarpDevice { bool ready = false; int sms = 0; int occ[2] = {0, 0}; };
+struct WarpDevice { bool ready = false; int sms = 0; int occ[4] = {0, 0, 0, 0}; };      // occupancy of <EMIT, FUSED> at [EMIT + 2 * FUSED]
+// Tuning of the fused variant (dme_set_fused_tuning; defaults are the measured best): lead of the A-phase beyond one row, in
+// rounds of G tiles, and the L2 policies of the two copies.
+static int g_lead_rounds = 2, g_polA = 1, g_polB = 2;
 static WarpDevice g_warp_dev[64];
 static std::mutex g_warp_mu;
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -753,10 +899,14 @@ static int warp_device(WarpDevice **out) {
     std::lock_guard<std::mutex> lock(g_warp_mu);
     WarpDevice &D = g_warp_dev[dev];
     if (!D.ready) {
-        DME_CUDA(cudaFuncSetAttribute(quantize_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWarpDynSmem));
-        DME_CUDA(cudaFuncSetAttribute(quantize_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWarpDynSmem));
-        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.occ[0], quantize_warp_kernel<0>, kQThreads, kWarpDynSmem));
-        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.occ[1], quantize_warp_kernel<1>, kQThreads, kWarpDynSmem));
+        DME_CUDA(cudaFuncSetAttribute(quantize_warp_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWarpDynSmem));
+        DME_CUDA(cudaFuncSetAttribute(quantize_warp_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWarpDynSmem));
+        DME_CUDA(cudaFuncSetAttribute(quantize_warp_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWarpDynSmem));
+        DME_CUDA(cudaFuncSetAttribute(quantize_warp_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWarpDynSmem));
+        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.occ[0], quantize_warp_kernel<0, false>, kQThreads, kWarpDynSmem));
+        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.occ[1], quantize_warp_kernel<1, false>, kQThreads, kWarpDynSmem));
+        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.occ[2], quantize_warp_kernel<0, true>, kQThreads, kWarpDynSmem));
+        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.occ[3], quantize_warp_kernel<1, true>, kQThreads, kWarpDynSmem));
         DME_CUDA(cudaDeviceGetAttribute(&D.sms, cudaDevAttrMultiProcessorCount, dev));
         if (g_encode == nullptr) {
             cudaDriverEntryPointQueryResult qres;
@@ -771,10 +921,12 @@ static int warp_device(WarpDevice **out) {
     return DME_OK;
 }
 
-// The row constants are there already (l1_kernel, launched by the caller on the same stream).
+// fused == false: the row constants are there already (l1_kernel, launched by the caller on the same stream); fused == true: the
+// kernel computes them itself (x_inject, seed, client0, l1_out as for launch_l1), the workspace's zeroed regions include apart.
 int launch_quantize_warp(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
                          int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
-                         uint32_t *codes, int64_t codes_bytes, uint64_t *dir, cudaStream_t st, bool packed) {
+                         uint32_t *codes, int64_t codes_bytes, uint64_t *dir, cudaStream_t st, bool packed,
+                         bool fused, const float *x_inject, uint64_t seed, uint64_t client0, float *l1_out) {
     WarpDevice *D = nullptr;
     int rc = warp_device(&D);
     if (rc) return rc;
@@ -819,16 +971,32 @@ int launch_quantize_warp(const float *X, int64_t n, int64_t d, int64_t ld, int64
                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for n=%lld d=%lld ld=%lld", (int)r, (long long)n, (long long)d, (long long)ld); return DME_ECUDA; }
     }
-    const int occ = D->occ[packed ? 1 : 0];
+    const int occ = D->occ[(packed ? 1 : 0) + (fused ? 2 : 0)];
     if (occ < 1) { set_error("quantize_warp_kernel does not fit on an SM"); return DME_ECUDA; }
     int64_t G = (int64_t)D->sms * occ;             // every CTA resident: a look-back never waits on a warp that has not started
     const int64_t need = (nT + kQWarps - 1) / kQWarps;
     if (G > need) G = need;
-    if (packed) quantize_warp_kernel<1><<<(unsigned)G, kQThreads, kWarpDynSmem, st>>>(a, tmap);
-    else quantize_warp_kernel<0><<<(unsigned)G, kQThreads, kWarpDynSmem, st>>>(a, tmap);
-    DME_LAUNCH_CHECK("quantize_warp_kernel");
+    a.apart = (unsigned long long *)(base + L.off_apart);
+    a.absum = a.apart + nT;
+    a.abcnt = (uint32_t *)(a.absum + n * (int64_t)a.TB);
+    a.adone = (uint32_t *)(base + L.off_done);
+    a.rin.m = m; a.rin.d = d; a.rin.x_inject = x_inject; a.rin.l1_inject = nullptr; a.rin.seed = seed; a.rin.client0 = client0;
+    a.rin.consts = (RowConst *)(base + L.off_consts); a.rin.l1_out = l1_out;
+    a.polA = g_polA; a.polB = g_polB;
+    // lead >= G tiles: the A-phase of a row's last tile runs at least one full round before the B-phase of its first tile
+    a.aoff = (unsigned long long)a.T4 + (unsigned long long)(g_lead_rounds < 1 ? 1 : g_lead_rounds) * (unsigned long long)(G * kQWarps);
+    if (fused) {
+        if (packed) quantize_warp_kernel<1, true><<<(unsigned)G, kQThreads, kWarpDynSmem, st>>>(a, tmap);
+        else quantize_warp_kernel<0, true><<<(unsigned)G, kQThreads, kWarpDynSmem, st>>>(a, tmap);
+        DME_LAUNCH_CHECK("quantize_fused_kernel");
+    } else {
+        if (packed) quantize_warp_kernel<1, false><<<(unsigned)G, kQThreads, kWarpDynSmem, st>>>(a, tmap);
+        else quantize_warp_kernel<0, false><<<(unsigned)G, kQThreads, kWarpDynSmem, st>>>(a, tmap);
+        DME_LAUNCH_CHECK("quantize_warp_kernel");
+    }
     return DME_OK;
 }
+void set_fused_tuning(int lead_rounds, int polA, int polB) { g_lead_rounds = lead_rounds; g_polA = polA; g_polB = polB; }
 
 }  // namespace dme
 #ifdef DME_TIMERS

@@ -76,8 +76,9 @@ DME_API const char *dme_profile_name(int i);
  * launches; rows with injected norms always take it). */
 DME_API int dme_set_unbiased_path(int path);
 /* Development hook of the fused kernel: lead of its L1 pass beyond one row (rounds of resident warps, >= 1) and the L2 eviction
- * policies of its two copies (0 normal, 1 evict_last, 2 evict_first).  Defaults are the measured best. */
-DME_API int dme_set_fused_tuning(int lead_rounds, int pol_a, int pol_b);
+ * policies of its two copies (0 normal, 1 evict_last, 2 evict_first); align != 0 rounds the distance between the two passes up to a
+ * multiple of the resident warps (a tile is then summed and quantized by the same SM).  Defaults are the measured best. */
+DME_API int dme_set_fused_tuning(int lead_rounds, int pol_a, int pol_b, int align);
 
 /* X_c, the single uniform of client c (AS:634): Philox4x32-10, key = seed, counter = (client, 0, 0, 0x584D44),
  * top 24 bits -> [0,1).  Host-side helper so callers/tests can reproduce the draws. */

@@ -45,9 +45,9 @@ for sh in shapes:
     print(f"{sh}: mean {same_mean} l1 {same_l1} codes {same_codes}", flush=True)
     del cref, cgot, mref, mgot
     out = torch.empty(d, device="cuda")
-    variants = [("tiles", None), ("fused", (2, 1, 2))]
+    variants = [("tiles", None), ("fused", (2, 1, 2, 1))]
     if tune:
-        variants += [("fused", v) for v in [(1, 1, 2), (3, 1, 2), (2, 0, 2), (2, 1, 0), (2, 0, 0), (4, 1, 2)]]
+        variants += [("fused", v) for v in [(1, 1, 2, 1), (3, 1, 2, 1), (2, 1, 2, 0), (2, 0, 0, 1), (4, 1, 2, 1)]]
     for path, tv in variants:
         dme.set_unbiased_path(path)
         if tv:
@@ -55,6 +55,6 @@ for sh in shapes:
         res = [dme.profile_kernels(lambda: dme.quantize_mean(X, 1, seed=i, out=out, check=False), warm=0) for i in range(5)]
         tot = [round(sum(t for _, t in r), 3) for r in res[2:]]
         print(" ", path, tv, tot, [(nm, round(t, 3)) for nm, t in res[-1]], flush=True)
-    L.dme_set_fused_tuning(2, 1, 2)
+    L.dme_set_fused_tuning(2, 1, 2, 1)
     del X
 dme.set_unbiased_path("fused")

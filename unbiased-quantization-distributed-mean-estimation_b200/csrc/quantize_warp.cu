@@ -26,15 +26,15 @@
 // Every wait is on a smaller tile whose B-phase never waits: no deadlock while all CTAs are resident.
 //
 // FUSED variant (the product path): the L1 norms are computed by the same kernel, one client row AHEAD of the quantize pass, so
-// that the input is read from HBM once.  In the iteration in which a warp quantizes ticket t it also sums |x| of ticket
-// t + T4 + lead ("A-phase": one TMA tile, L2 evict_last; fp64 lane sums, xor-butterfly) -- a first touch that leaves the row in
-// L2, where the B-phase's copy (evict_first) finds it one row later.  Tile sums are published as tagged 64-bit words (sign bit =
-// written: no fence needed), a relaxed counter per block of 32 tiles elects the warp that adds the block's 32 sums in a fixed
-// order, a counter per row the warp that adds the block sums and publishes the row constants (release).  The order of the
-// additions does not depend on timing or on the grid.  The B-phase of a row's first tiles waits for the row constants (acquire);
-// the A-phase never waits for anything but its own copy, and runs at least one full round ahead: no deadlock.  The three tile
-// buffers of a warp rotate through the roles B-tile -> parked fractions -> A-tile: the next B-tile's copy is started after the
-// A-phase (into the A buffer), the next A-tile's after the C-phase (into the parked buffer).
+// that the input is read from HBM once.  In the iteration in which a warp quantizes ticket t it also sums |x| of ticket t + aoff
+// (aoff = one row + a lead of at least one round, a multiple of the resident warps: a tile is summed and quantized by the same
+// warp).  The A-tile is pulled into L2 two iterations earlier by a TMA prefetch (evict_last) and then read with plain 128-bit
+// loads (no shared memory: the B ring keeps its three buffers and its two iterations of flight); the B-phase's copy (evict_first)
+// finds the row in L2 one row later.  A warp adds the fp64 sums of its own tiles of a row in ticket order and publishes one
+// tagged word per row (sign bit = written: no fence, no atomics); the warp that sums the row's last tile polls the row's
+// participants, adds their words in a fixed order and publishes the row constants (release).  The order of the additions depends
+// on the grid, not on timing.  The B-phase of a row's first tiles waits for the row constants (acquire); an A-phase waits only
+// for A-phases of lower tickets: no deadlock.
 #include <cuda.h>
 
 #include <cmath>
@@ -85,6 +85,15 @@ __device__ __forceinline__ void tma_tile_g2s(uint32_t dst, const CUtensorMap *ma
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
         ::"r"(dst), "l"(map), "r"(0), "r"(row0), "r"(client), "r"(bar), "l"(policy) : "memory");
 }
+__device__ __forceinline__ void tma_tile_prefetch(const CUtensorMap *map, int row0, int client, uint64_t policy) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile.L2::cache_hint [%0, {%1, %2, %3}], %4;"
+                 ::"l"(map), "r"(0), "r"(row0), "r"(client), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
 }
@@ -131,6 +140,16 @@ __device__ __forceinline__ void f2_unpack(f2 v, float &lo, float &hi) { asm("mov
 __device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
+// Row constants: read-only for the two-launch kernel (non-coherent loads); written inside the fused kernel, whose loads must stay
+// behind the acquire of the row's ready flag (a non-coherent load may be hoisted by the compiler).
+template <bool FUSED> __device__ __forceinline__ float rc_f32(const float *p) {
+    if (!FUSED) return __ldg(p);
+    float v; asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory"); return v;
+}
+template <bool FUSED> __device__ __forceinline__ uint32_t rc_u32(const uint32_t *p) {
+    if (!FUSED) return __ldg(p);
+    uint32_t v; asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
 struct WarpArgs {
     const float *X; int64_t d, ld, n;
     uint32_t T4;                               // code tiles per client row
@@ -150,8 +169,8 @@ struct WarpArgs {
     // FUSED: the A-phase (L1 norms one row ahead)
     unsigned long long aoff;                   // A ticket = B ticket + aoff, aoff = T4 + lead (lead >= G: at least one round of slack)
     int polA, polB;                            // L2 policies of the A / B copies
-    unsigned long long *apart, *absum;         // tagged tile sums [n][T4], tagged block sums [n][TB]
-    uint32_t *abcnt, *adone;                   // tiles finished per block [n][TB], blocks finished per row [n]
+    unsigned long long *apart;                 // tagged fp64 sums: one word per (row, participating warp) [n][aslots]
+    uint32_t aslots;                           // min(T4, kMaxWarps)
     RowConstIn rin;
 };
 constexpr unsigned long long kTag = 1ull << 63;      // sign bit of a non-negative fp64 sum: "written"
@@ -455,54 +474,105 @@ __device__ __forceinline__ unsigned long long ld_tagged(const unsigned long long
     while (!(v & kTag)) { __nanosleep(64); v = ld_rec(p); }
     return v;
 }
-// The warp that finished a block of 32 tiles (elected by the block's counter): block sum in a fixed order; the warp that finished
-// the row's last block: row sum in a fixed order, row constants, ready flag.  Cold (once per 32 tiles).
-__device__ __noinline__ void a_block_done(const WarpArgs &a, int c, int blk, int lane) {
-    const int left = (int)a.T4 - blk * 32, cnt = left < 32 ? left : 32;
-    double v = 0.0;
-    if (lane < cnt) v = __longlong_as_double((long long)(ld_tagged(a.apart + ((size_t)c * a.T4 + (size_t)blk * 32 + lane)) & ~kTag));
-    v = warp_sum_f64(v);
-    unsigned old = 0;
-    if (lane == 0) {
-        st_rec(a.absum + ((size_t)c * a.TB + blk), (unsigned long long)__double_as_longlong(v) | kTag);
-        old = atomicAdd(a.adone + c, 1u);
+// The A-tile (client c, tile w): lane l loads the 16-byte pieces l, l + 32, .. of the tile (coalesced; the tile is in L2).
+struct ATile { float4 v[8]; };
+__device__ __forceinline__ void a_load(const WarpArgs &a, int c, int w, int lane, ATile &t) {
+    const int64_t i0 = (int64_t)w * kCodeTile + 4 * lane;
+    const float *src = a.X + (int64_t)c * a.ld + i0;
+    if ((int64_t)(w + 1) * kCodeTile <= a.d) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t.v[q] = ldg_stream_f4(src + 128 * q);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int64_t i = i0 + 128 * q;
+            t.v[q].x = i < a.d ? src[128 * q] : 0.0f;
+            t.v[q].y = i + 1 < a.d ? src[128 * q + 1] : 0.0f;
+            t.v[q].z = i + 2 < a.d ? src[128 * q + 2] : 0.0f;
+            t.v[q].w = i + 3 < a.d ? src[128 * q + 3] : 0.0f;
+        }
     }
-    old = __shfl_sync(0xffffffffu, old, 0);
-    if (old != a.TB - 1u) return;
+}
+// The lane's fp64 sum of |x| over its 32 values of the tile, fixed order.  fp32 -> fp64 by one integer multiply-add (the
+// conversion unit is what the C-phase's fixed-point conversions run on): exact for normal numbers; zeros and denormals come out
+// as values below 2^-126, so a lane whose sum is tiny is summed again with real conversions.
+__device__ __forceinline__ double abs_as_double(float x) {
+    return __longlong_as_double((long long)((unsigned long long)(__float_as_uint(x) & 0x7fffffffu) * 0x20000000ull + 0x3800000000000000ull));
+}
+__device__ __noinline__ double a_sum_exact(const WarpArgs &a, int c, int w, int lane) {      // cold: loads the tile again
+    ATile t;
+    a_load(a, c, w, lane, t);
+    double ra = 0.0, rb = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        ra += (double)fabsf(t.v[q].x); rb += (double)fabsf(t.v[q].y);
+        ra += (double)fabsf(t.v[q].z); rb += (double)fabsf(t.v[q].w);
+    }
+    return ra + rb;
+}
+__device__ __forceinline__ double a_sum(const WarpArgs &a, int c, int w, int lane, const ATile &t) {
+    double ra = 0.0, rb = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        ra += abs_as_double(t.v[q].x); rb += abs_as_double(t.v[q].y);
+        ra += abs_as_double(t.v[q].z); rb += abs_as_double(t.v[q].w);
+    }
+    double s = ra + rb;
+    if (!(s >= 8.673617379884035e-19 && s < 3.402823669209385e+38)) s = a_sum_exact(a, c, w, lane);      // [2^-60, 2^128): else zeros / denormals matter, or Inf / NaN
+    return s;
+}
+// Row sums.  A warp owns tiles w, w + G, .. of a row and flushes its word after the last of them, which is one of the row's last
+// P = min(T4, G) tiles: position p = w_last - (T4 - P).  Words are added in the order of p, in two levels: the warp at the end of
+// a group of 32 positions adds the group (it polls the 31 words before its own: lower tickets of the same round), the warp at
+// p = P - 1 (the row's last tile) then adds the group sums and publishes the row constants.  Cold (once per row and warp).
+constexpr int kAGroups = kMaxFusedWarps / 32;
+__device__ __noinline__ void a_group_done(const WarpArgs &a, int c, uint32_t p, uint32_t P, int lane) {
+    const uint32_t grp = p >> 5, left = P - grp * 32u, cnt = left < 32u ? left : 32u;
+    double v = 0.0;
+    if ((uint32_t)lane < cnt) v = __longlong_as_double((long long)(ld_tagged(a.apart + ((size_t)c * a.aslots + grp * 32u + lane)) & ~kTag));
+    v = warp_sum_f64(v);
+    unsigned long long *gw = a.apart + (size_t)a.n * a.aslots + (size_t)c * kAGroups;
+    if (lane == 0) st_rec(gw + grp, (unsigned long long)__double_as_longlong(v) | kTag);
+    if (p != P - 1u) return;
+    // the row's last tile: add the group sums (at most kAGroups = 128: four per lane, loaded together)
+    unsigned long long g4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const uint32_t j = 32u * u + lane;
+        g4[u] = kTag;
+        if (j < grp) g4[u] = ld_rec(gw + j);
+    }
     double acc = 0.0;
-    for (uint32_t i = lane; i < a.TB; i += 32)
-        acc += __longlong_as_double((long long)(ld_tagged(a.absum + ((size_t)c * a.TB + i)) & ~kTag));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const uint32_t j = 32u * u + lane;
+        if (j < grp) {
+            if (!(g4[u] & kTag)) g4[u] = ld_tagged(gw + j);
+            acc += __longlong_as_double((long long)(g4[u] & ~kTag));
+        } else if (j == grp) acc += v;          // this warp's own group
+    }
     acc = warp_sum_f64(acc);
     if (lane == 0) {
         make_row_const(a.rin, c, acc);
         __threadfence();
         st_release_u32(&a.rin.consts[c].flags, a.rin.consts[c].flags | kRowReady);
+#ifdef DME_TIMERS
+        if (g_dbg) g_dbg[(size_t)a.total * 12 + c] = gtime();
+#endif
     }
 }
-// Sum of |x| over the tile in `buf` (client c, tile w): fp64, fixed order; published as a tagged word.  Returns (lane 0) the
-// block counter's previous value -- the caller looks at it later (the atomic's round trip hides behind the C-phase).
-__device__ __forceinline__ unsigned a_phase(const WarpArgs &a, int c, int w, uint32_t buf, int lane, uint32_t swz) {
-    const uint32_t rowb = buf + (uint32_t)lane * 128u;
-    fix_tile_edges(a, c, w, rowb, swz, lane);
-    double ra = 0.0, rb = 0.0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const uint4 v = lds128u(rowb + (((uint32_t)q << 4) ^ swz));
-        ra += (double)fabsf(__uint_as_float(v.x)); rb += (double)fabsf(__uint_as_float(v.y));
-        ra += (double)fabsf(__uint_as_float(v.z)); rb += (double)fabsf(__uint_as_float(v.w));
+// Per-lane state of the A pass: the running sum of the lane's values over the warp's tiles of the current row.
+struct AState { double acc; };
+// The lane's sum s of tile (c, w) is in; `more` = the warp's next A ticket (this one + G) lies in the same row.
+__device__ __forceinline__ void a_account(const WarpArgs &a, AState &st, int c, int w, double s, bool more, uint32_t G, int lane) {
+    if ((uint32_t)w < G) st.acc = s;            // the warp's first tile of this row
+    else st.acc += s;
+    if (!more) {
+        const double tot = warp_sum_f64(st.acc);
+        const uint32_t P = a.T4 < G ? a.T4 : G, p = (uint32_t)w - (a.T4 - P);
+        if (lane == 0) st_rec(a.apart + ((size_t)c * a.aslots + p), (unsigned long long)__double_as_longlong(tot) | kTag);
+        if ((p & 31u) == 31u || p == P - 1u) a_group_done(a, c, p, P, lane);
     }
-    const double s = warp_sum_f64(ra + rb);
-    unsigned old = 0;
-    if (lane == 0) {
-        st_rec(a.apart + ((size_t)c * a.T4 + (size_t)w), (unsigned long long)__double_as_longlong(s) | kTag);
-        old = atomicAdd(a.abcnt + ((size_t)c * a.TB + ((uint32_t)w >> 5)), 1u);
-    }
-    return old;
-}
-__device__ __forceinline__ void a_check(const WarpArgs &a, int c, int w, unsigned old, int lane) {
-    old = __shfl_sync(0xffffffffu, old, 0);
-    const int blk = w >> 5, left = (int)a.T4 - blk * 32;
-    if (old == (unsigned)(left < 32 ? left : 32) - 1u) a_block_done(a, c, blk, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------------- the kernel
@@ -563,37 +633,29 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
     iC.c = 0; iC.w = 0; iC.tk = 0; iC.valid = false;
     uint32_t ph = 0;                            // bit q: parity of the phase buffer q's barrier completes next
     int known = -1;                             // FUSED: the last row whose constants this warp has seen ready
+    AState ast; ast.acc = 0.0;
     if (FUSED) {
-        // Prologue: the A-phase of tickets [0, aoff), i.e. the first row and the lead, through all three buffers.
+        // Prologue: the A-phase of tickets [0, aoff), i.e. the first row and the lead (first touch: prefetched all at once).
         const unsigned long long npro = a.aoff < (unsigned long long)a.total ? a.aoff : (unsigned long long)a.total;
-        const uint64_t polA = policy_kind(a.polA);
         if (lane == 0) {
-            for (int q = 0; q < kRing; ++q) {
-                const unsigned long long t = (unsigned long long)q * G + gw;
-                if (t < npro) issue_tile(a, &tmap, item_of(a, (uint32_t)t), ring + (uint32_t)q * kTileBytes, bars + 8u * q, polA);
+            const uint64_t polA = policy_kind(a.polA);
+            for (unsigned long long t = gw; t < npro + 2ull * G && t < (unsigned long long)a.total; t += G) {
+                const Item ip = item_of(a, (uint32_t)t);
+                if ((int64_t)ip.w * 32 < a.rows32) tma_tile_prefetch(&tmap, ip.w * 32, ip.c, polA);
             }
         }
-        int q = 0;
         for (unsigned long long t = gw; t < npro; t += G) {
             const Item ia = item_of(a, (uint32_t)t);
-            mbar_wait(bars + 8u * q, (ph >> q) & 1u);
-            ph ^= 1u << q;
-            const unsigned old = a_phase(a, ia.c, ia.w, ring + (uint32_t)q * kTileBytes, lane, swz);
-            __syncwarp();
-            const unsigned long long t3 = t + 3ull * G;
-            if (lane == 0 && t3 < npro) issue_tile(a, &tmap, item_of(a, (uint32_t)t3), ring + (uint32_t)q * kTileBytes, bars + 8u * q, polA);
-            a_check(a, ia.c, ia.w, old, lane);
-            q = q == kRing - 1 ? 0 : q + 1;
+            ATile at;
+            a_load(a, ia.c, ia.w, lane, at);
+            const double sa = a_sum(a, ia.c, ia.w, lane, at);
+            DBG_MARK(ia.tk, 11);
+            a_account(a, ast, ia.c, ia.w, sa, (uint32_t)ia.w + G < a.T4, G, lane);
         }
-        __syncwarp();
     }
     if (lane == 0) {
         if (iB.valid) issue_tile(a, &tmap, iB, ring, bars, pol);
-        if (FUSED) {
-            // the A-tile of the first iteration
-            const unsigned long long tA = (unsigned long long)gw + a.aoff;
-            if (iB.valid && tA < (unsigned long long)a.total) issue_tile(a, &tmap, item_of(a, (uint32_t)tA), ring + kTileBytes, bars + 8u, policy_kind(a.polA));
-        } else if (iN.valid) issue_tile(a, &tmap, iN, ring + kTileBytes, bars + 8u, pol);
+        if (iN.valid) issue_tile(a, &tmap, iN, ring + kTileBytes, bars + 8u, pol);
     }
     Carry cy;                                   // of tile iC
     cy.sgw0 = cy.sgw1 = cy.flm = cy.L0 = cy.L1 = cy.ex32 = 0; cy.mxl = 0.0f; cy.fmf = 0.0f; cy.Aq = 0; cy.AI = 0;
@@ -602,7 +664,7 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
     int sB = 0;
     for (uint32_t it = 0;; ++it) {
         if (!iB.valid && !iC.valid) break;
-        const int sC = sB == 0 ? kRing - 1 : sB - 1, sA = sB == kRing - 1 ? 0 : sB + 1;
+        const int sC = sB == 0 ? kRing - 1 : sB - 1;
         Carry nb;                               // of tile iB
         nb.sgw0 = nb.sgw1 = nb.flm = nb.L0 = nb.L1 = nb.ex32 = 0; nb.mxl = 0.0f; nb.fmf = 0.0f; nb.Aq = 0; nb.AI = 0;
         nb.fl4[0] = nb.fl4[1] = nb.fl4[2] = nb.fl4[3] = 0;
@@ -622,16 +684,26 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
                 if (lane < S) ld_rec2(sp + lane, slo, shi);
             }
         };
+        // the A-tile of this iteration (FUSED): ticket iB.tk + aoff, one row and the lead ahead; its loads are issued right after the
+        // B-phase's arithmetic and consumed after the look-back loads have been issued
+        ATile at;
+        Item iA; iA.c = 0; iA.w = 0; iA.tk = 0; iA.valid = false;
+        if (FUSED && iB.valid) {
+            const unsigned long long tA = (unsigned long long)iB.tk + a.aoff;
+            if (tA < (unsigned long long)a.total) iA = item_of(a, (uint32_t)tA);
+        }
         // ---------------------------------------------------------------- B-phase of tile iB
         if (iB.valid) {
             const RowConst *rcp = a.consts + iB.c;
+            DBG_MARK(iB.tk, 10);
             if (FUSED && iB.c != known) {
                 // the row's constants come from the A-phase of the warp that finished its L1 sum (normally long ago)
-                while (!(ld_acquire_u32(&rcp->flags) & kRowReady)) __nanosleep(128);
+                while (!(ld_relaxed_u32(&rcp->flags) & kRowReady)) __nanosleep(256);
+                (void)ld_acquire_u32(&rcp->flags);
                 known = iB.c;
             }
-            const float D = __ldg(&rcp->D), rcpD = __ldg(&rcp->rcpD), mf = __ldg(&rcp->mf);
-            const uint32_t rflags = __ldg(&rcp->flags);
+            const float D = rc_f32<FUSED>(&rcp->D), rcpD = rc_f32<FUSED>(&rcp->rcpD), mf = rc_f32<FUSED>(&rcp->mf);
+            const uint32_t rflags = rc_u32<FUSED>(&rcp->flags);
             const uint32_t buf = ring + (uint32_t)sB * kTileBytes, rowb = buf + rowoff;
             DBG_MARK(iB.tk, 1);
             mbar_wait(bars + 8u * sB, (ph >> sB) & 1u);
@@ -678,22 +750,19 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
             }
         }
         // ---------------------------------------------------------------- C-phase of tile iC: AS:635-637, emit
+#ifdef DME_AEARLY
+        if (FUSED && iA.valid) a_load(a, iA.c, iA.w, lane, at);
+#endif
         window_issue();
         if (iB.valid) nb.ex32 = warp_excl_scan_u32((nb.L0 >> 11) | (nb.L1 << 13), lane);      // lane sums in 2^-32 units (mod 2^32)
         // ---------------------------------------------------------------- A-phase of ticket iB.tk + aoff (one row ahead)
-        unsigned a_old = 0;
-        Item iA; iA.c = 0; iA.w = 0; iA.tk = 0; iA.valid = false;
-        if (FUSED && iB.valid) {
-            const unsigned long long tA = (unsigned long long)iB.tk + a.aoff;
-            if (tA < (unsigned long long)a.total) {
-                iA = item_of(a, (uint32_t)tA);
-                mbar_wait(bars + 8u * sA, (ph >> sA) & 1u);
-                ph ^= 1u << sA;
-                a_old = a_phase(a, iA.c, iA.w, ring + (uint32_t)sA * kTileBytes, lane, swz);
-            }
-            // the A buffer is free: the next B-tile goes there (it comes from L2: the C-phase is time enough)
-            __syncwarp();
-            if (lane == 0 && iN.valid) issue_tile(a, &tmap, iN, ring + (uint32_t)sA * kTileBytes, bars + 8u * sA, pol);
+        if (FUSED && iA.valid) {
+#ifndef DME_AEARLY
+            a_load(a, iA.c, iA.w, lane, at);
+#endif
+            const double sa = a_sum(a, iA.c, iA.w, lane, at);
+            DBG_MARK(iA.tk, 11);
+            a_account(a, ast, iA.c, iA.w, sa, (uint32_t)iA.w + G < a.T4, G, lane);
         }
         // The tile that completed its block forwards the block total to the super-block record: at the end of the iteration (the
         // atomic's round trip hides behind the C-phase), but BEFORE this warp starts to wait for anything -- the look-back of a
@@ -711,8 +780,8 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
         };
         if (iC.valid) {
             const RowConst *rcp = a.consts + iC.c;
-            const float X = __ldg(&rcp->X);
-            const uint32_t rflags = __ldg(&rcp->flags);
+            const float X = rc_f32<FUSED>(&rcp->X);
+            const uint32_t rflags = rc_u32<FUSED>(&rcp->flags);
             const uint32_t buf = ring + (uint32_t)sC * kTileBytes, rowb = buf + rowoff;
             // the parked fractions become fixed-point words while the look-back loads are in flight
             uint32_t pw[4][8];
@@ -799,7 +868,7 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
             }
             __syncwarp();
             if (EMIT == 0) {
-                emit_arrays(a, iC.c, iC.w, lane, __ldg(&rcp->L1f), __ldg(&rcp->D), __ldg(&rcp->mf), rm);
+                emit_arrays(a, iC.c, iC.w, lane, rc_f32<FUSED>(&rcp->L1f), rc_f32<FUSED>(&rcp->D), rc_f32<FUSED>(&rcp->mf), rm);
             } else {
                 const float fm = cy.fmf;
                 int W = 2;
@@ -816,7 +885,7 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
                                 for (int g = 0; g < 4; ++g)
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) hit |= ((cy.fl4[g] >> (4 * j)) & 15u) == 7u && ((rm >> (8 * g + j)) & 1u);
-                            } else hit = lane_hit_wide(a, iC.c, iC.w, lane, __ldg(&rcp->D), __ldg(&rcp->mf), fm, rm);
+                            } else hit = lane_hit_wide(a, iC.c, iC.w, lane, rc_f32<FUSED>(&rcp->D), rc_f32<FUSED>(&rcp->mf), fm, rm);
                         }
                         if (__any_sync(0xffffffffu, hit)) W = Wh;
                     }
@@ -851,7 +920,7 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
                             tw[(g & 1) * kCodeChunks + 2 * lane + (g >> 1)] = cy.fl4[g] + rs;       // k <= 7: no carry between nibbles
                         }
                     } else {
-                        emit_wide(a, iC.c, iC.w, lane, __ldg(&rcp->D), __ldg(&rcp->mf), rm, W, tw);
+                        emit_wide(a, iC.c, iC.w, lane, rc_f32<FUSED>(&rcp->D), rc_f32<FUSED>(&rcp->mf), rm, W, tw);
                     }
                 }
             }
@@ -863,13 +932,15 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
         __syncwarp();
         Item iNN = iB.valid ? next_item() : Item{0, 0, 0u, false};
         if (iC.valid) DBG_MARK(iC.tk, 7);
+        if (lane == 0 && iNN.valid) issue_tile(a, &tmap, iNN, ring + (uint32_t)sC * kTileBytes, bars + 8u * sC, pol);
         if (FUSED) {
-            // the parked buffer is free: the next iteration's A-tile (first touch, from HBM) goes there
-            const unsigned long long tA = (unsigned long long)iN.tk + a.aoff;
-            if (lane == 0 && iN.valid && tA < (unsigned long long)a.total)
-                issue_tile(a, &tmap, item_of(a, (uint32_t)tA), ring + (uint32_t)sC * kTileBytes, bars + 8u * sC, policy_kind(a.polA));
-            if (iA.valid) a_check(a, iA.c, iA.w, a_old, lane);
-        } else if (lane == 0 && iNN.valid) issue_tile(a, &tmap, iNN, ring + (uint32_t)sC * kTileBytes, bars + 8u * sC, pol);
+            // the A-tile of the iteration after the next one is pulled into L2 now
+            const unsigned long long tP = (unsigned long long)iNN.tk + a.aoff;
+            if (lane == 0 && iNN.valid && tP < (unsigned long long)a.total) {
+                const Item ip = item_of(a, (uint32_t)tP);
+                if ((int64_t)ip.w * 32 < a.rows32) tma_tile_prefetch(&tmap, ip.w * 32, ip.c, policy_kind(a.polA));
+            }
+        }
         if (iC.valid) DBG_MARK(iC.tk, 8);
         iC = iB; iB = iN; iN = iNN;
         cy = nb;
@@ -883,7 +954,7 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
 struct WarpDevice { bool ready = false; int sms = 0; int occ[4] = {0, 0, 0, 0}; };      // occupancy of <EMIT, FUSED> at [EMIT + 2 * FUSED]
 // Tuning of the fused variant (dme_set_fused_tuning; defaults are the measured best): lead of the A-phase beyond one row, in
 // rounds of G tiles, and the L2 policies of the two copies.
-static int g_lead_rounds = 2, g_polA = 1, g_polB = 2;
+static int g_lead_rounds = 2, g_polA = 1, g_polB = 2, g_align = 1;
 static WarpDevice g_warp_dev[64];
 static std::mutex g_warp_mu;
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -977,14 +1048,18 @@ int launch_quantize_warp(const float *X, int64_t n, int64_t d, int64_t ld, int64
     const int64_t need = (nT + kQWarps - 1) / kQWarps;
     if (G > need) G = need;
     a.apart = (unsigned long long *)(base + L.off_apart);
-    a.absum = a.apart + nT;
-    a.abcnt = (uint32_t *)(a.absum + n * (int64_t)a.TB);
-    a.adone = (uint32_t *)(base + L.off_done);
+    a.aslots = (uint32_t)(a.T4 < (uint32_t)kMaxFusedWarps ? (a.T4 + 1u) & ~1u : (uint32_t)kMaxFusedWarps);      // even: 16-byte aligned rows
+    if (fused && G * kQWarps > kMaxFusedWarps) G = kMaxFusedWarps / kQWarps;      // one slot per participating warp and row
     a.rin.m = m; a.rin.d = d; a.rin.x_inject = x_inject; a.rin.l1_inject = nullptr; a.rin.seed = seed; a.rin.client0 = client0;
     a.rin.consts = (RowConst *)(base + L.off_consts); a.rin.l1_out = l1_out;
     a.polA = g_polA; a.polB = g_polB;
     // lead >= G tiles: the A-phase of a row's last tile runs at least one full round before the B-phase of its first tile
-    a.aoff = (unsigned long long)a.T4 + (unsigned long long)(g_lead_rounds < 1 ? 1 : g_lead_rounds) * (unsigned long long)(G * kQWarps);
+    // aoff is a multiple of the resident warps: the warp (the SM) that summed a tile is the one that quantizes it, and a warp's A
+    // tickets are g, g + G, g + 2G, .. throughout (the per-row bookkeeping of a_account relies on it)
+    {
+        const unsigned long long GW = (unsigned long long)(G * kQWarps), lr = (unsigned long long)(g_lead_rounds < 1 ? 1 : g_lead_rounds);
+        a.aoff = (((unsigned long long)a.T4 + GW - 1) / GW + lr) * GW;
+    }
     if (fused) {
         if (packed) quantize_warp_kernel<1, true><<<(unsigned)G, kQThreads, kWarpDynSmem, st>>>(a, tmap);
         else quantize_warp_kernel<0, true><<<(unsigned)G, kQThreads, kWarpDynSmem, st>>>(a, tmap);
@@ -996,7 +1071,7 @@ int launch_quantize_warp(const float *X, int64_t n, int64_t d, int64_t ld, int64
     }
     return DME_OK;
 }
-void set_fused_tuning(int lead_rounds, int polA, int polB) { g_lead_rounds = lead_rounds; g_polA = polA; g_polB = polB; }
+void set_fused_tuning(int lead_rounds, int polA, int polB, int align) { g_lead_rounds = lead_rounds; g_polA = polA; g_polB = polB; g_align = align; }
 
 }  // namespace dme
 #ifdef DME_TIMERS

@@ -468,7 +468,7 @@ int launch_quantize_warp(const float *X, int64_t n, int64_t d, int64_t ld, int64
                           int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
                           uint32_t *codes, int64_t codes_bytes, uint64_t *dir, cudaStream_t st, bool packed,
                           bool fused, const float *x_inject, uint64_t seed, uint64_t client0, float *l1_out);   // quantize_warp.cu
-void set_fused_tuning(int lead_rounds, int polA, int polB);
+void set_fused_tuning(int lead_rounds, int polA, int polB, int align);
 int launch_literal_rows(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
                         const float *x_inject, const float *l1_inject, uint64_t seed, uint64_t client0,
                         int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
@@ -580,9 +580,9 @@ extern "C" int dme_set_unbiased_path(int path) {
     return DME_OK;
 }
 
-extern "C" int dme_set_fused_tuning(int lead_rounds, int pol_a, int pol_b) {
+extern "C" int dme_set_fused_tuning(int lead_rounds, int pol_a, int pol_b, int align) {
     DME_REQUIRE(lead_rounds >= 1 && lead_rounds <= 64 && pol_a >= 0 && pol_a <= 2 && pol_b >= 0 && pol_b <= 2, "bad argument");
-    set_fused_tuning(lead_rounds, pol_a, pol_b);
+    set_fused_tuning(lead_rounds, pol_a, pol_b, align);
     return DME_OK;
 }
 

@@ -30,6 +30,7 @@ struct __align__(256) WsHeader {
     uint32_t pad[59];
 };
 
+constexpr int kMaxFusedWarps = 4096;      // upper bound of the fused quantize kernel's resident warps (its grid is clipped to it)
 struct WsLayout {
     int64_t T;            // tiles per row
     int64_t off_done;     // uint32 a_done[n]
@@ -38,8 +39,8 @@ struct WsLayout {
     int64_t off_partial;  // double partial[n*T]
     int64_t off_desc;     // look-back records of quantize_warp_kernel: 8 bytes per code tile, 8 per block of 32 tiles, 16 per
     int64_t desc_bytes;   // super-block of 1024 tiles
-    int64_t off_apart;    // fused kernel, zeroed with the records: tagged fp64 |x| sums per code tile [n][T4], per block of 32 tiles
-    int64_t apart_bytes;  // [n][TB], then uint32 tiles-done counters per block [n][TB]
+    int64_t off_apart;    // fused kernel, zeroed with the records: tagged fp64 |x| sums, one word per row and participating warp
+    int64_t apart_bytes;  // [n][min(T4, kMaxFusedWarps)], then one per row and group of 32 of them [n][kMaxFusedWarps / 32]
     int64_t off_sel;      // RowSelect sel[n] (biased mode)
     int64_t zero_bytes;   // prefix that must be zeroed before each call (header + a_done)
     int64_t total;
@@ -84,8 +85,8 @@ inline WsLayout ws_layout(int64_t n, int64_t d) {
     }
     L.off_desc = o; o = align_up(o + L.desc_bytes, 256);
     {
-        const int64_t T4 = (d + kCodeTile - 1) / kCodeTile, TB = (T4 + 31) / 32;
-        L.apart_bytes = n * (8 * T4 + 8 * TB + 4 * TB);
+        const int64_t T4 = (d + kCodeTile - 1) / kCodeTile;
+        L.apart_bytes = n * 8 * ((T4 < kMaxFusedWarps ? (T4 + 1) / 2 * 2 : kMaxFusedWarps) + kMaxFusedWarps / 32);
     }
     L.off_apart = o; o = align_up(o + L.apart_bytes, 256);      // directly behind the records: one memset covers both
     L.off_sel = o; o = align_up(o + (int64_t)sizeof(RowSelect) * n, 256);

@@ -70,15 +70,9 @@ DME_API int64_t dme_launch_count(void);
 DME_API int dme_profile_enable(int on, dme_stream_t stream);
 DME_API int dme_profile_read(float *ms, int cap);
 DME_API const char *dme_profile_name(int i);
-/* Test hook: which implementation runs the unbiased mode.  0 (default) = the fused quantize kernel (L1 norms one client row ahead
- * of the quantize pass, one launch, the input is read from HBM once: the product path); 1 = literal_rows_kernel (AS:625-637 as
- * written, one CTA per row: an independent implementation for the parity tests); 2 = l1_kernel + quantize_warp_kernel (two
- * launches; rows with injected norms always take it). */
+/* Test hook: which implementation runs the unbiased mode.  0 (default) = l1_kernel + quantize_warp_kernel (the product path);
+ * 1 = literal_rows_kernel (AS:625-637 as written, one CTA per row: an independent implementation for the parity tests). */
 DME_API int dme_set_unbiased_path(int path);
-/* Development hook of the fused kernel: lead of its L1 pass beyond one row (rounds of resident warps, >= 1) and the L2 eviction
- * policies of its two copies (0 normal, 1 evict_last, 2 evict_first); align != 0 rounds the distance between the two passes up to a
- * multiple of the resident warps (a tile is then summed and quantized by the same SM).  Defaults are the measured best. */
-DME_API int dme_set_fused_tuning(int lead_rounds, int pol_a, int pol_b, int align);
 
 /* X_c, the single uniform of client c (AS:634): Philox4x32-10, key = seed, counter = (client, 0, 0, 0x584D44),
  * top 24 bits -> [0,1).  Host-side helper so callers/tests can reproduce the draws. */

@@ -19,14 +19,14 @@ def dme():
     return dme_b200
 
 
-@pytest.fixture(autouse=True, params=["fused", "tiles", "literal"])
+@pytest.fixture(autouse=True, params=["tiles", "literal"])
 def quantize_path(request, dme):
     """Every test of this file runs on both implementations of the unbiased quantizer: the product path (l1_kernel +
     quantize_warp_kernel, csrc/quantize_warp.cu) and the literal kernel (csrc/quantize_literal.cu: AS:625-637 as written,
     one CTA per row), an independent second implementation checked against the same oracle and goldens."""
     dme.set_unbiased_path(request.param)
     yield request.param
-    dme.set_unbiased_path("fused")
+    dme.set_unbiased_path("tiles")
 
 
 def _R(v):

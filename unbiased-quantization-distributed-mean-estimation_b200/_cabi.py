@@ -18,7 +18,6 @@ SIGNATURES = {
     "dme_profile_read": (ci, [vp, ci]),
     "dme_profile_name": (C.c_char_p, [ci]),
     "dme_set_unbiased_path": (ci, [ci]),
-    "dme_set_fused_tuning": (ci, [ci, ci, ci, ci]),
     "dme_uniform_x": (cf, [u64, u64]),
     "dme_workspace_bytes": (i64, [i64, i64]),
     "dme_codes_bytes": (i64, [i64, i64, i64, ci]),

@@ -122,14 +122,13 @@ class Workspace:
         _check(_cabi.lib().dme_status(C.c_void_p(self.buf.data_ptr() + off), C.c_void_p(_stream())))
 
 
-UNBIASED_PATHS = {"fused": 0, "literal": 1, "tiles": 2}
+UNBIASED_PATHS = {"tiles": 0, "literal": 1}
 
 
 def set_unbiased_path(path) -> None:
-    """Test hook (dme_set_unbiased_path): "fused" = the fused quantize kernel (L1 norms one row ahead of the quantize pass
-    in one launch; the product path, default), "tiles" = l1_kernel + quantize_warp_kernel (two launches; also what rows with
-    injected norms take), "literal" = AS:625-637 as written, one CTA per row (slow; an independent implementation the GPU
-    tests check against the same oracle)."""
+    """Test hook (dme_set_unbiased_path): "tiles" = l1_kernel + quantize_warp_kernel (the product path, default),
+    "literal" = AS:625-637 as written, one CTA per row (slow; an independent implementation the GPU tests check
+    against the same oracle)."""
     _check(_cabi.lib().dme_set_unbiased_path(UNBIASED_PATHS.get(path, path)))
 
 

@@ -24,17 +24,6 @@
 // or whose row is outside the proven operand range evaluates AS:636 literally in fp64 from the parked fractions.
 // Integer addition is associative: prefixes do not depend on timing, results are run-to-run deterministic.
 // Every wait is on a smaller tile whose B-phase never waits: no deadlock while all CTAs are resident.
-//
-// FUSED variant (the product path): the L1 norms are computed by the same kernel, one client row AHEAD of the quantize pass, so
-// that the input is read from HBM once.  In the iteration in which a warp quantizes ticket t it also sums |x| of ticket t + aoff
-// (aoff = one row + a lead of at least one round, a multiple of the resident warps: a tile is summed and quantized by the same
-// warp).  The A-tile is pulled into L2 two iterations earlier by a TMA prefetch (evict_last) and then read with plain 128-bit
-// loads (no shared memory: the B ring keeps its three buffers and its two iterations of flight); the B-phase's copy (evict_first)
-// finds the row in L2 one row later.  A warp adds the fp64 sums of its own tiles of a row in ticket order and publishes one
-// tagged word per row (sign bit = written: no fence, no atomics); the warp that sums the row's last tile polls the row's
-// participants, adds their words in a fixed order and publishes the row constants (release).  The order of the additions depends
-// on the grid, not on timing.  The B-phase of a row's first tiles waits for the row constants (acquire); an A-phase waits only
-// for A-phases of lower tickets: no deadlock.
 #include <cuda.h>
 
 #include <cmath>
@@ -85,24 +74,8 @@ __device__ __forceinline__ void tma_tile_g2s(uint32_t dst, const CUtensorMap *ma
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
         ::"r"(dst), "l"(map), "r"(0), "r"(row0), "r"(client), "r"(bar), "l"(policy) : "memory");
 }
-__device__ __forceinline__ void tma_tile_prefetch(const CUtensorMap *map, int row0, int client, uint64_t policy) {
-    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile.L2::cache_hint [%0, {%1, %2, %3}], %4;"
-                 ::"l"(map), "r"(0), "r"(row0), "r"(client), "l"(policy) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
-}
-__device__ __forceinline__ uint64_t policy_kind(int kind) {       // 0 evict_normal, 1 evict_last, 2 evict_first
-    uint64_t p;
-    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
-    return p;
 }
 __device__ __forceinline__ uint4 lds128u(uint32_t addr) {
     uint4 v;
@@ -140,16 +113,6 @@ __device__ __forceinline__ void f2_unpack(f2 v, float &lo, float &hi) { asm("mov
 __device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
-// Row constants: read-only for the two-launch kernel (non-coherent loads); written inside the fused kernel, whose loads must stay
-// behind the acquire of the row's ready flag (a non-coherent load may be hoisted by the compiler).
-template <bool FUSED> __device__ __forceinline__ float rc_f32(const float *p) {
-    if (!FUSED) return __ldg(p);
-    float v; asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory"); return v;
-}
-template <bool FUSED> __device__ __forceinline__ uint32_t rc_u32(const uint32_t *p) {
-    if (!FUSED) return __ldg(p);
-    uint32_t v; asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
-}
 struct WarpArgs {
     const float *X; int64_t d, ld, n;
     uint32_t T4;                               // code tiles per client row
@@ -166,14 +129,7 @@ struct WarpArgs {
     WsHeader *hdr;
     int32_t *k_out; uint8_t *sgn_out; float *deq_out; int64_t ld_out;     // array outputs (EMIT == 0)
     PackTarget pack;                                                    // packed output (EMIT == 1)
-    // FUSED: the A-phase (L1 norms one row ahead)
-    unsigned long long aoff;                   // A ticket = B ticket + aoff, aoff = T4 + lead (lead >= G: at least one round of slack)
-    int polA, polB;                            // L2 policies of the A / B copies
-    unsigned long long *apart;                 // tagged fp64 sums: one word per (row, participating warp) [n][aslots]
-    uint32_t aslots;                           // min(T4, kMaxWarps)
-    RowConstIn rin;
 };
-constexpr unsigned long long kTag = 1ull << 63;      // sign bit of a non-negative fp64 sum: "written"
 
 #ifdef DME_TIMERS
 __device__ unsigned long long *g_dbg = nullptr;       // per ticket: draw, B start, publish, C start, C end (globaltimer ns), smid << 8 | warp slot
@@ -450,131 +406,6 @@ __device__ __noinline__ void emit_arrays(const WarpArgs &a, int c, int w, int la
     if (ovf) atomicOr(&a.hdr->status, 1u);
 }
 
-
-// ---------------------------------------------------------------------------------------------------------------- A-phase (FUSED)
-// Rows of a tile that the tensor map does not cover: a tile that is the row's tail only was not copied at all (zero it), the last
-// d % 32 coordinates of a row arrive as zeros and are patched in by the lane that owns them.
-__device__ __forceinline__ void fix_tile_edges(const WarpArgs &a, int c, int w, uint32_t rowb, uint32_t swz, int lane) {
-    if ((int64_t)w * 32 >= a.rows32) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) sts128u(rowb + ((uint32_t)q << 4), make_uint4(0u, 0u, 0u, 0u));
-    }
-    if (a.tail && w == (int)a.T4 - 1) {
-        __syncwarp();
-        if (lane == (int)(a.rows32 - (int64_t)w * 32)) {
-            const float *src = a.X + (int64_t)c * a.ld + a.rows32 * 32;
-            for (int j = 0; j < a.tail; ++j)
-                sts32(rowb + ((((uint32_t)(j >> 2)) << 4) ^ swz) + 4u * (uint32_t)(j & 3), __float_as_uint(src[j]));
-        }
-        __syncwarp();
-    }
-}
-__device__ __forceinline__ unsigned long long ld_tagged(const unsigned long long *p) {      // spin until the word has been written
-    unsigned long long v = ld_rec(p);
-    while (!(v & kTag)) { __nanosleep(64); v = ld_rec(p); }
-    return v;
-}
-// The A-tile (client c, tile w): lane l loads the 16-byte pieces l, l + 32, .. of the tile (coalesced; the tile is in L2).
-struct ATile { float4 v[8]; };
-__device__ __forceinline__ void a_load(const WarpArgs &a, int c, int w, int lane, ATile &t) {
-    const int64_t i0 = (int64_t)w * kCodeTile + 4 * lane;
-    const float *src = a.X + (int64_t)c * a.ld + i0;
-    if ((int64_t)(w + 1) * kCodeTile <= a.d) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) t.v[q] = ldg_stream_f4(src + 128 * q);
-    } else {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int64_t i = i0 + 128 * q;
-            t.v[q].x = i < a.d ? src[128 * q] : 0.0f;
-            t.v[q].y = i + 1 < a.d ? src[128 * q + 1] : 0.0f;
-            t.v[q].z = i + 2 < a.d ? src[128 * q + 2] : 0.0f;
-            t.v[q].w = i + 3 < a.d ? src[128 * q + 3] : 0.0f;
-        }
-    }
-}
-// The lane's fp64 sum of |x| over its 32 values of the tile, fixed order.  fp32 -> fp64 by one integer multiply-add (the
-// conversion unit is what the C-phase's fixed-point conversions run on): exact for normal numbers; zeros and denormals come out
-// as values below 2^-126, so a lane whose sum is tiny is summed again with real conversions.
-__device__ __forceinline__ double abs_as_double(float x) {
-    return __longlong_as_double((long long)((unsigned long long)(__float_as_uint(x) & 0x7fffffffu) * 0x20000000ull + 0x3800000000000000ull));
-}
-__device__ __noinline__ double a_sum_exact(const WarpArgs &a, int c, int w, int lane) {      // cold: loads the tile again
-    ATile t;
-    a_load(a, c, w, lane, t);
-    double ra = 0.0, rb = 0.0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        ra += (double)fabsf(t.v[q].x); rb += (double)fabsf(t.v[q].y);
-        ra += (double)fabsf(t.v[q].z); rb += (double)fabsf(t.v[q].w);
-    }
-    return ra + rb;
-}
-__device__ __forceinline__ double a_sum(const WarpArgs &a, int c, int w, int lane, const ATile &t) {
-    double ra = 0.0, rb = 0.0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        ra += abs_as_double(t.v[q].x); rb += abs_as_double(t.v[q].y);
-        ra += abs_as_double(t.v[q].z); rb += abs_as_double(t.v[q].w);
-    }
-    double s = ra + rb;
-    if (!(s >= 8.673617379884035e-19 && s < 3.402823669209385e+38)) s = a_sum_exact(a, c, w, lane);      // [2^-60, 2^128): else zeros / denormals matter, or Inf / NaN
-    return s;
-}
-// Row sums.  A warp owns tiles w, w + G, .. of a row and flushes its word after the last of them, which is one of the row's last
-// P = min(T4, G) tiles: position p = w_last - (T4 - P).  Words are added in the order of p, in two levels: the warp at the end of
-// a group of 32 positions adds the group (it polls the 31 words before its own: lower tickets of the same round), the warp at
-// p = P - 1 (the row's last tile) then adds the group sums and publishes the row constants.  Cold (once per row and warp).
-constexpr int kAGroups = kMaxFusedWarps / 32;
-__device__ __noinline__ void a_group_done(const WarpArgs &a, int c, uint32_t p, uint32_t P, int lane) {
-    const uint32_t grp = p >> 5, left = P - grp * 32u, cnt = left < 32u ? left : 32u;
-    double v = 0.0;
-    if ((uint32_t)lane < cnt) v = __longlong_as_double((long long)(ld_tagged(a.apart + ((size_t)c * a.aslots + grp * 32u + lane)) & ~kTag));
-    v = warp_sum_f64(v);
-    unsigned long long *gw = a.apart + (size_t)a.n * a.aslots + (size_t)c * kAGroups;
-    if (lane == 0) st_rec(gw + grp, (unsigned long long)__double_as_longlong(v) | kTag);
-    if (p != P - 1u) return;
-    // the row's last tile: add the group sums (at most kAGroups = 128: four per lane, loaded together)
-    unsigned long long g4[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const uint32_t j = 32u * u + lane;
-        g4[u] = kTag;
-        if (j < grp) g4[u] = ld_rec(gw + j);
-    }
-    double acc = 0.0;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const uint32_t j = 32u * u + lane;
-        if (j < grp) {
-            if (!(g4[u] & kTag)) g4[u] = ld_tagged(gw + j);
-            acc += __longlong_as_double((long long)(g4[u] & ~kTag));
-        } else if (j == grp) acc += v;          // this warp's own group
-    }
-    acc = warp_sum_f64(acc);
-    if (lane == 0) {
-        make_row_const(a.rin, c, acc);
-        __threadfence();
-        st_release_u32(&a.rin.consts[c].flags, a.rin.consts[c].flags | kRowReady);
-#ifdef DME_TIMERS
-        if (g_dbg) g_dbg[(size_t)a.total * 12 + c] = gtime();
-#endif
-    }
-}
-// Per-lane state of the A pass: the running sum of the lane's values over the warp's tiles of the current row.
-struct AState { double acc; };
-// The lane's sum s of tile (c, w) is in; `more` = the warp's next A ticket (this one + G) lies in the same row.
-__device__ __forceinline__ void a_account(const WarpArgs &a, AState &st, int c, int w, double s, bool more, uint32_t G, int lane) {
-    if ((uint32_t)w < G) st.acc = s;            // the warp's first tile of this row
-    else st.acc += s;
-    if (!more) {
-        const double tot = warp_sum_f64(st.acc);
-        const uint32_t P = a.T4 < G ? a.T4 : G, p = (uint32_t)w - (a.T4 - P);
-        if (lane == 0) st_rec(a.apart + ((size_t)c * a.aslots + p), (unsigned long long)__double_as_longlong(tot) | kTag);
-        if ((p & 31u) == 31u || p == P - 1u) a_group_done(a, c, p, P, lane);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------- the kernel
 __device__ __forceinline__ Item item_of(const WarpArgs &a, uint32_t tk) {
     Item it; it.c = 0; it.w = 0; it.tk = tk; it.valid = tk < a.total;
@@ -596,7 +427,7 @@ __device__ __forceinline__ void issue_tile(const WarpArgs &a, const CUtensorMap 
     }
 }
 
-template <int EMIT, bool FUSED>
+template <int EMIT>
 __global__ void __launch_bounds__(kQThreads, 4)
 quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char dyn_smem[];      // per warp: three 4 KB tile buffers; then the mbarriers
@@ -605,7 +436,7 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
     const uint32_t bars = smem_u32(dyn_smem) + (uint32_t)(kQWarps * kRing * kTileBytes) + (uint32_t)warp * 32u;
     const uint32_t scratch = smem_u32(dyn_smem) + (uint32_t)(kQWarps * kRing * kTileBytes) + (uint32_t)kQWarps * 32u + (uint32_t)threadIdx.x * 32u;
     const uint32_t swz = ((uint32_t)lane & 7u) << 4, rowoff = (uint32_t)lane * 128u;
-    const uint64_t pol = FUSED ? policy_kind(a.polB) : policy_evict_first();
+    const uint64_t pol = policy_evict_first();
     if (lane == 0) {
         for (int q = 0; q < kRing; ++q) mbar_init(bars + 8u * q, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -631,28 +462,6 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
     Item iB = item_of(a, gw), iN = item_of(a, G + gw), iC;
     if (!iN.valid) tk_more = false;
     iC.c = 0; iC.w = 0; iC.tk = 0; iC.valid = false;
-    uint32_t ph = 0;                            // bit q: parity of the phase buffer q's barrier completes next
-    int known = -1;                             // FUSED: the last row whose constants this warp has seen ready
-    AState ast; ast.acc = 0.0;
-    if (FUSED) {
-        // Prologue: the A-phase of tickets [0, aoff), i.e. the first row and the lead (first touch: prefetched all at once).
-        const unsigned long long npro = a.aoff < (unsigned long long)a.total ? a.aoff : (unsigned long long)a.total;
-        if (lane == 0) {
-            const uint64_t polA = policy_kind(a.polA);
-            for (unsigned long long t = gw; t < npro + 2ull * G && t < (unsigned long long)a.total; t += G) {
-                const Item ip = item_of(a, (uint32_t)t);
-                if ((int64_t)ip.w * 32 < a.rows32) tma_tile_prefetch(&tmap, ip.w * 32, ip.c, polA);
-            }
-        }
-        for (unsigned long long t = gw; t < npro; t += G) {
-            const Item ia = item_of(a, (uint32_t)t);
-            ATile at;
-            a_load(a, ia.c, ia.w, lane, at);
-            const double sa = a_sum(a, ia.c, ia.w, lane, at);
-            DBG_MARK(ia.tk, 11);
-            a_account(a, ast, ia.c, ia.w, sa, (uint32_t)ia.w + G < a.T4, G, lane);
-        }
-    }
     if (lane == 0) {
         if (iB.valid) issue_tile(a, &tmap, iB, ring, bars, pol);
         if (iN.valid) issue_tile(a, &tmap, iN, ring + kTileBytes, bars + 8u, pol);
@@ -684,34 +493,31 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
                 if (lane < S) ld_rec2(sp + lane, slo, shi);
             }
         };
-        // the A-tile of this iteration (FUSED): ticket iB.tk + aoff, one row and the lead ahead; its loads are issued right after the
-        // B-phase's arithmetic and consumed after the look-back loads have been issued
-        ATile at;
-        Item iA; iA.c = 0; iA.w = 0; iA.tk = 0; iA.valid = false;
-        if (FUSED && iB.valid) {
-            const unsigned long long tA = (unsigned long long)iB.tk + a.aoff;
-            if (tA < (unsigned long long)a.total) iA = item_of(a, (uint32_t)tA);
-        }
         // ---------------------------------------------------------------- B-phase of tile iB
         if (iB.valid) {
             const RowConst *rcp = a.consts + iB.c;
-            DBG_MARK(iB.tk, 10);
-            if (FUSED && iB.c != known) {
-                // the row's constants come from the A-phase of the warp that finished its L1 sum (normally long ago)
-                while (!(ld_relaxed_u32(&rcp->flags) & kRowReady)) __nanosleep(256);
-                (void)ld_acquire_u32(&rcp->flags);
-                known = iB.c;
-            }
-            const float D = rc_f32<FUSED>(&rcp->D), rcpD = rc_f32<FUSED>(&rcp->rcpD), mf = rc_f32<FUSED>(&rcp->mf);
-            const uint32_t rflags = rc_u32<FUSED>(&rcp->flags);
+            const float D = __ldg(&rcp->D), rcpD = __ldg(&rcp->rcpD), mf = __ldg(&rcp->mf);
+            const uint32_t rflags = __ldg(&rcp->flags);
             const uint32_t buf = ring + (uint32_t)sB * kTileBytes, rowb = buf + rowoff;
             DBG_MARK(iB.tk, 1);
-            mbar_wait(bars + 8u * sB, (ph >> sB) & 1u);
-            ph ^= 1u << sB;
+            mbar_wait(bars + 8u * sB, (it / kRing) & 1u);
 #ifdef DME_TIMERS
             if (g_dbg && lane == 0) g_dbg[(size_t)iB.tk * 12 + 5] = gtime();
 #endif
-            fix_tile_edges(a, iB.c, iB.w, rowb, swz, lane);
+            if ((int64_t)iB.w * 32 >= a.rows32) {                   // nothing was copied: the tile is the row's tail only
+#pragma unroll
+                for (int q = 0; q < 8; ++q) sts128u(rowb + ((uint32_t)q << 4), make_uint4(0u, 0u, 0u, 0u));
+            }
+            if (a.tail && iB.w == (int)a.T4 - 1) {
+                // the last d % 32 coordinates of the row are not covered by the tensor map (their row arrived as zeros)
+                __syncwarp();
+                if (lane == (int)(a.rows32 - (int64_t)iB.w * 32)) {
+                    const float *src = a.X + (int64_t)iB.c * a.ld + a.rows32 * 32;
+                    for (int j = 0; j < a.tail; ++j)
+                        sts32(rowb + ((((uint32_t)(j >> 2)) << 4) ^ swz) + 4u * (uint32_t)(j & 3), __float_as_uint(src[j]));
+                }
+                __syncwarp();
+            }
             bool exact = (rflags & kRowExact) != 0u;
             if (!exact && (rflags & kRowGuardFloor)) {
                 // m * p can reach 2^23 in this row: lanes that actually see such a value use floorf
@@ -750,20 +556,8 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
             }
         }
         // ---------------------------------------------------------------- C-phase of tile iC: AS:635-637, emit
-#ifdef DME_AEARLY
-        if (FUSED && iA.valid) a_load(a, iA.c, iA.w, lane, at);
-#endif
         window_issue();
         if (iB.valid) nb.ex32 = warp_excl_scan_u32((nb.L0 >> 11) | (nb.L1 << 13), lane);      // lane sums in 2^-32 units (mod 2^32)
-        // ---------------------------------------------------------------- A-phase of ticket iB.tk + aoff (one row ahead)
-        if (FUSED && iA.valid) {
-#ifndef DME_AEARLY
-            a_load(a, iA.c, iA.w, lane, at);
-#endif
-            const double sa = a_sum(a, iA.c, iA.w, lane, at);
-            DBG_MARK(iA.tk, 11);
-            a_account(a, ast, iA.c, iA.w, sa, (uint32_t)iA.w + G < a.T4, G, lane);
-        }
         // The tile that completed its block forwards the block total to the super-block record: at the end of the iteration (the
         // atomic's round trip hides behind the C-phase), but BEFORE this warp starts to wait for anything -- the look-back of a
         // later super-block depends on it.
@@ -780,8 +574,8 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
         };
         if (iC.valid) {
             const RowConst *rcp = a.consts + iC.c;
-            const float X = rc_f32<FUSED>(&rcp->X);
-            const uint32_t rflags = rc_u32<FUSED>(&rcp->flags);
+            const float X = __ldg(&rcp->X);
+            const uint32_t rflags = __ldg(&rcp->flags);
             const uint32_t buf = ring + (uint32_t)sC * kTileBytes, rowb = buf + rowoff;
             // the parked fractions become fixed-point words while the look-back loads are in flight
             uint32_t pw[4][8];
@@ -868,7 +662,7 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
             }
             __syncwarp();
             if (EMIT == 0) {
-                emit_arrays(a, iC.c, iC.w, lane, rc_f32<FUSED>(&rcp->L1f), rc_f32<FUSED>(&rcp->D), rc_f32<FUSED>(&rcp->mf), rm);
+                emit_arrays(a, iC.c, iC.w, lane, __ldg(&rcp->L1f), __ldg(&rcp->D), __ldg(&rcp->mf), rm);
             } else {
                 const float fm = cy.fmf;
                 int W = 2;
@@ -885,7 +679,7 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
                                 for (int g = 0; g < 4; ++g)
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) hit |= ((cy.fl4[g] >> (4 * j)) & 15u) == 7u && ((rm >> (8 * g + j)) & 1u);
-                            } else hit = lane_hit_wide(a, iC.c, iC.w, lane, rc_f32<FUSED>(&rcp->D), rc_f32<FUSED>(&rcp->mf), fm, rm);
+                            } else hit = lane_hit_wide(a, iC.c, iC.w, lane, __ldg(&rcp->D), __ldg(&rcp->mf), fm, rm);
                         }
                         if (__any_sync(0xffffffffu, hit)) W = Wh;
                     }
@@ -920,7 +714,7 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
                             tw[(g & 1) * kCodeChunks + 2 * lane + (g >> 1)] = cy.fl4[g] + rs;       // k <= 7: no carry between nibbles
                         }
                     } else {
-                        emit_wide(a, iC.c, iC.w, lane, rc_f32<FUSED>(&rcp->D), rc_f32<FUSED>(&rcp->mf), rm, W, tw);
+                        emit_wide(a, iC.c, iC.w, lane, __ldg(&rcp->D), __ldg(&rcp->mf), rm, W, tw);
                     }
                 }
             }
@@ -933,14 +727,6 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
         Item iNN = iB.valid ? next_item() : Item{0, 0, 0u, false};
         if (iC.valid) DBG_MARK(iC.tk, 7);
         if (lane == 0 && iNN.valid) issue_tile(a, &tmap, iNN, ring + (uint32_t)sC * kTileBytes, bars + 8u * sC, pol);
-        if (FUSED) {
-            // the A-tile of the iteration after the next one is pulled into L2 now
-            const unsigned long long tP = (unsigned long long)iNN.tk + a.aoff;
-            if (lane == 0 && iNN.valid && tP < (unsigned long long)a.total) {
-                const Item ip = item_of(a, (uint32_t)tP);
-                if ((int64_t)ip.w * 32 < a.rows32) tma_tile_prefetch(&tmap, ip.w * 32, ip.c, policy_kind(a.polA));
-            }
-        }
         if (iC.valid) DBG_MARK(iC.tk, 8);
         iC = iB; iB = iN; iN = iNN;
         cy = nb;
@@ -951,10 +737,7 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
 // ------------------------------------------------------------------ host side
 // Function attributes, occupancy and the SM count are per device: set / queried once for every device the library is used on
 // (one process may drive several GPUs), under a mutex.
-struct WarpDevice { bool ready = false; int sms = 0; int occ[4] = {0, 0, 0, 0}; };      // occupancy of <EMIT, FUSED> at [EMIT + 2 * FUSED]
-// Tuning of the fused variant (dme_set_fused_tuning; defaults are the measured best): lead of the A-phase beyond one row, in
-// rounds of G tiles, and the L2 policies of the two copies.
-static int g_lead_rounds = 2, g_polA = 1, g_polB = 2, g_align = 1;
+struct WarpDevice { bool ready = false; int sms = 0; int occ[2] = {0, 0}; };
 static WarpDevice g_warp_dev[64];
 static std::mutex g_warp_mu;
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -970,14 +753,10 @@ static int warp_device(WarpDevice **out) {
     std::lock_guard<std::mutex> lock(g_warp_mu);
     WarpDevice &D = g_warp_dev[dev];
     if (!D.ready) {
-        DME_CUDA(cudaFuncSetAttribute(quantize_warp_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWarpDynSmem));
-        DME_CUDA(cudaFuncSetAttribute(quantize_warp_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWarpDynSmem));
-        DME_CUDA(cudaFuncSetAttribute(quantize_warp_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWarpDynSmem));
-        DME_CUDA(cudaFuncSetAttribute(quantize_warp_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWarpDynSmem));
-        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.occ[0], quantize_warp_kernel<0, false>, kQThreads, kWarpDynSmem));
-        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.occ[1], quantize_warp_kernel<1, false>, kQThreads, kWarpDynSmem));
-        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.occ[2], quantize_warp_kernel<0, true>, kQThreads, kWarpDynSmem));
-        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.occ[3], quantize_warp_kernel<1, true>, kQThreads, kWarpDynSmem));
+        DME_CUDA(cudaFuncSetAttribute(quantize_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWarpDynSmem));
+        DME_CUDA(cudaFuncSetAttribute(quantize_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWarpDynSmem));
+        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.occ[0], quantize_warp_kernel<0>, kQThreads, kWarpDynSmem));
+        DME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.occ[1], quantize_warp_kernel<1>, kQThreads, kWarpDynSmem));
         DME_CUDA(cudaDeviceGetAttribute(&D.sms, cudaDevAttrMultiProcessorCount, dev));
         if (g_encode == nullptr) {
             cudaDriverEntryPointQueryResult qres;
@@ -992,12 +771,10 @@ static int warp_device(WarpDevice **out) {
     return DME_OK;
 }
 
-// fused == false: the row constants are there already (l1_kernel, launched by the caller on the same stream); fused == true: the
-// kernel computes them itself (x_inject, seed, client0, l1_out as for launch_l1), the workspace's zeroed regions include apart.
+// The row constants are there already (l1_kernel, launched by the caller on the same stream).
 int launch_quantize_warp(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
                          int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
-                         uint32_t *codes, int64_t codes_bytes, uint64_t *dir, cudaStream_t st, bool packed,
-                         bool fused, const float *x_inject, uint64_t seed, uint64_t client0, float *l1_out) {
+                         uint32_t *codes, int64_t codes_bytes, uint64_t *dir, cudaStream_t st, bool packed) {
     WarpDevice *D = nullptr;
     int rc = warp_device(&D);
     if (rc) return rc;
@@ -1042,36 +819,16 @@ int launch_quantize_warp(const float *X, int64_t n, int64_t d, int64_t ld, int64
                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for n=%lld d=%lld ld=%lld", (int)r, (long long)n, (long long)d, (long long)ld); return DME_ECUDA; }
     }
-    const int occ = D->occ[(packed ? 1 : 0) + (fused ? 2 : 0)];
+    const int occ = D->occ[packed ? 1 : 0];
     if (occ < 1) { set_error("quantize_warp_kernel does not fit on an SM"); return DME_ECUDA; }
     int64_t G = (int64_t)D->sms * occ;             // every CTA resident: a look-back never waits on a warp that has not started
     const int64_t need = (nT + kQWarps - 1) / kQWarps;
     if (G > need) G = need;
-    a.apart = (unsigned long long *)(base + L.off_apart);
-    a.aslots = (uint32_t)(a.T4 < (uint32_t)kMaxFusedWarps ? (a.T4 + 1u) & ~1u : (uint32_t)kMaxFusedWarps);      // even: 16-byte aligned rows
-    if (fused && G * kQWarps > kMaxFusedWarps) G = kMaxFusedWarps / kQWarps;      // one slot per participating warp and row
-    a.rin.m = m; a.rin.d = d; a.rin.x_inject = x_inject; a.rin.l1_inject = nullptr; a.rin.seed = seed; a.rin.client0 = client0;
-    a.rin.consts = (RowConst *)(base + L.off_consts); a.rin.l1_out = l1_out;
-    a.polA = g_polA; a.polB = g_polB;
-    // lead >= G tiles: the A-phase of a row's last tile runs at least one full round before the B-phase of its first tile
-    // aoff is a multiple of the resident warps: the warp (the SM) that summed a tile is the one that quantizes it, and a warp's A
-    // tickets are g, g + G, g + 2G, .. throughout (the per-row bookkeeping of a_account relies on it)
-    {
-        const unsigned long long GW = (unsigned long long)(G * kQWarps), lr = (unsigned long long)(g_lead_rounds < 1 ? 1 : g_lead_rounds);
-        a.aoff = (((unsigned long long)a.T4 + GW - 1) / GW + lr) * GW;
-    }
-    if (fused) {
-        if (packed) quantize_warp_kernel<1, true><<<(unsigned)G, kQThreads, kWarpDynSmem, st>>>(a, tmap);
-        else quantize_warp_kernel<0, true><<<(unsigned)G, kQThreads, kWarpDynSmem, st>>>(a, tmap);
-        DME_LAUNCH_CHECK("quantize_fused_kernel");
-    } else {
-        if (packed) quantize_warp_kernel<1, false><<<(unsigned)G, kQThreads, kWarpDynSmem, st>>>(a, tmap);
-        else quantize_warp_kernel<0, false><<<(unsigned)G, kQThreads, kWarpDynSmem, st>>>(a, tmap);
-        DME_LAUNCH_CHECK("quantize_warp_kernel");
-    }
+    if (packed) quantize_warp_kernel<1><<<(unsigned)G, kQThreads, kWarpDynSmem, st>>>(a, tmap);
+    else quantize_warp_kernel<0><<<(unsigned)G, kQThreads, kWarpDynSmem, st>>>(a, tmap);
+    DME_LAUNCH_CHECK("quantize_warp_kernel");
     return DME_OK;
 }
-void set_fused_tuning(int lead_rounds, int polA, int polB, int align) { g_lead_rounds = lead_rounds; g_polA = polA; g_polB = polB; g_align = align; }
 
 }  // namespace dme
 #ifdef DME_TIMERS

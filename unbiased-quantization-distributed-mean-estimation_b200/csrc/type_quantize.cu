@@ -433,7 +433,7 @@ static int check_rows(const void *X, int64_t n, int64_t d, int64_t ld) {
     return DME_OK;
 }
 
-int ws_prepare(void *ws, int64_t ws_bytes, int64_t n, int64_t d, cudaStream_t st, WsLayout *out, bool need_desc, bool need_sel, bool need_apart) {
+int ws_prepare(void *ws, int64_t ws_bytes, int64_t n, int64_t d, cudaStream_t st, WsLayout *out, bool need_desc, bool need_sel) {
     const WsLayout L = ws_layout(n, d);
     DME_REQUIRE(ws != nullptr && ((uintptr_t)ws & 255u) == 0, "workspace must be non-null and 256-byte aligned");
     if (ws_bytes < L.total) {
@@ -443,8 +443,7 @@ int ws_prepare(void *ws, int64_t ws_bytes, int64_t n, int64_t d, cudaStream_t st
     char *base = (char *)ws;
     DME_CUDA(cudaMemsetAsync(base, 0, (size_t)L.zero_bytes, st));
     if (need_desc) {
-        // the fused kernel's tagged sums and counters lie directly behind the look-back records: one memset
-        DME_CUDA(cudaMemsetAsync(base + L.off_desc, 0, (size_t)(need_apart ? L.off_apart + L.apart_bytes - L.off_desc : L.desc_bytes), st));
+        DME_CUDA(cudaMemsetAsync(base + L.off_desc, 0, (size_t)L.desc_bytes, st));
     }
     if (need_sel) DME_CUDA(cudaMemsetAsync(base + L.off_sel, 0, sizeof(RowSelect) * (size_t)n, st));
     *out = L;
@@ -466,16 +465,13 @@ int biased_quantize(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m,
                     uint32_t *codes, int64_t codes_bytes, uint64_t *dir, cudaStream_t st);   // reznik.cu
 int launch_quantize_warp(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
                           int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
-                          uint32_t *codes, int64_t codes_bytes, uint64_t *dir, cudaStream_t st, bool packed,
-                          bool fused, const float *x_inject, uint64_t seed, uint64_t client0, float *l1_out);   // quantize_warp.cu
-void set_fused_tuning(int lead_rounds, int polA, int polB, int align);
+                          uint32_t *codes, int64_t codes_bytes, uint64_t *dir, cudaStream_t st, bool packed);   // quantize_warp.cu
 int launch_literal_rows(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
                         const float *x_inject, const float *l1_inject, uint64_t seed, uint64_t client0,
                         int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
                         uint32_t *codes, int64_t codes_bytes, uint64_t *dir, float *l1_out, cudaStream_t st, bool packed);   // quantize_literal.cu
-// Which implementation quantises the unbiased mode: 0 = the fused quantize kernel (L1 norms one row ahead of the quantize pass in
-// one launch: the product path; rows with injected norms take path 2), 1 = literal_rows_kernel (tests: an independent
-// implementation), 2 = l1_kernel + quantize_warp_kernel (two launches, the input is read twice).  dme_set_unbiased_path.
+// Which implementation quantises the unbiased mode: 0 = l1_kernel + quantize_warp_kernel (the product path),
+// 1 = literal_rows_kernel (tests: an independent implementation).  dme_set_unbiased_path.
 static int g_unbiased_path = 0;
 
 }  // namespace dme
@@ -489,7 +485,7 @@ extern "C" int dme_l1_norms(const float *X, int64_t n, int64_t d, int64_t ld, fl
     DME_REQUIRE(l1_out != nullptr, "l1_out is null");
     cudaStream_t st = (cudaStream_t)stream;
     WsLayout L;
-    rc = ws_prepare(ws, ws_bytes, n, d, st, &L, false, false, false);
+    rc = ws_prepare(ws, ws_bytes, n, d, st, &L, false, false);
     if (rc) return rc;
     return launch_l1(X, n, d, ld, 1, L, ws, nullptr, nullptr, 0, 0, l1_out, st);
 }
@@ -512,8 +508,7 @@ static int quantize_common(const float *X, int64_t n, int64_t d, int64_t ld, int
     }
     WsLayout L;
     const bool literal = mode == DME_MODE_UNBIASED && g_unbiased_path == 1;
-    const bool fused = mode == DME_MODE_UNBIASED && g_unbiased_path == 0 && l1_inject == nullptr;
-    rc = ws_prepare(ws, ws_bytes, n, d, st, &L, !literal, mode == DME_MODE_BIASED, fused);
+    rc = ws_prepare(ws, ws_bytes, n, d, st, &L, !literal, mode == DME_MODE_BIASED);
     if (rc) return rc;
     if (literal) {
         rc = launch_literal_rows(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, k_out, sgn_out, deq_out, ld_out, codes, codes_bytes,
@@ -521,14 +516,11 @@ static int quantize_common(const float *X, int64_t n, int64_t d, int64_t ld, int
         if (rc) return rc;
             return DME_OK;
     }
-    if (!fused) {
-        rc = launch_l1(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, l1_out, st);
-        if (rc) return rc;
-    }
+    rc = launch_l1(X, n, d, ld, m, L, ws, x_inject, l1_inject, seed, client0, l1_out, st);
+    if (rc) return rc;
     if (mode == DME_MODE_BIASED)
         return biased_quantize(X, n, d, ld, m, L, ws, k_out, sgn_out, deq_out, ld_out, codes, codes_bytes, dir, st);
-    rc = launch_quantize_warp(X, n, d, ld, m, L, ws, k_out, sgn_out, deq_out, ld_out, codes, codes_bytes, dir, st, packed,
-                              fused, x_inject, seed, client0, l1_out);
+    rc = launch_quantize_warp(X, n, d, ld, m, L, ws, k_out, sgn_out, deq_out, ld_out, codes, codes_bytes, dir, st, packed);
     if (rc) return rc;
     return DME_OK;
 }
@@ -575,14 +567,8 @@ extern "C" int dme_decode_mean(const void *codes, const uint64_t *dir, const flo
 }
 
 extern "C" int dme_set_unbiased_path(int path) {
-    DME_REQUIRE(path >= 0 && path <= 2, "path=%d unknown", path);
+    DME_REQUIRE(path == 0 || path == 1, "path=%d unknown", path);
     g_unbiased_path = path;
-    return DME_OK;
-}
-
-extern "C" int dme_set_fused_tuning(int lead_rounds, int pol_a, int pol_b, int align) {
-    DME_REQUIRE(lead_rounds >= 1 && lead_rounds <= 64 && pol_a >= 0 && pol_a <= 2 && pol_b >= 0 && pol_b <= 2, "bad argument");
-    set_fused_tuning(lead_rounds, pol_a, pol_b, align);
     return DME_OK;
 }
 

@@ -6,7 +6,7 @@
 namespace dme {
 
 // Per-client constants, written by the kernel that finishes the client's L1 reduction.
-struct __align__(128) RowConst {      // one 128-byte line per client: a line is written once, before anybody reads it
+struct __align__(64) RowConst {
     float L1f;   // fp32(sum |x|)  (AS:624) or injected
     float D;     // L1f + 1e-12f   (AS:625)
     float mf;    // float(m)
@@ -20,7 +20,6 @@ struct __align__(128) RowConst {      // one 128-byte line per client: a line is
     double pad1[2];
 };
 constexpr uint32_t kRowExact = 1u, kRowGuardFloor = 2u;
-constexpr uint32_t kRowReady = 0x80000000u;   // set (release) by the warp that finishes the row's L1 inside the fused quantize kernel
 
 struct __align__(256) WsHeader {
     uint32_t ticket;          // scan-order ticket dispenser
@@ -30,7 +29,6 @@ struct __align__(256) WsHeader {
     uint32_t pad[59];
 };
 
-constexpr int kMaxFusedWarps = 4096;      // upper bound of the fused quantize kernel's resident warps (its grid is clipped to it)
 struct WsLayout {
     int64_t T;            // tiles per row
     int64_t off_done;     // uint32 a_done[n]
@@ -39,8 +37,6 @@ struct WsLayout {
     int64_t off_partial;  // double partial[n*T]
     int64_t off_desc;     // look-back records of quantize_warp_kernel: 8 bytes per code tile, 8 per block of 32 tiles, 16 per
     int64_t desc_bytes;   // super-block of 1024 tiles
-    int64_t off_apart;    // fused kernel, zeroed with the records: tagged fp64 |x| sums, one word per row and participating warp
-    int64_t apart_bytes;  // [n][min(T4, kMaxFusedWarps)], then one per row and group of 32 of them [n][kMaxFusedWarps / 32]
     int64_t off_sel;      // RowSelect sel[n] (biased mode)
     int64_t zero_bytes;   // prefix that must be zeroed before each call (header + a_done)
     int64_t total;
@@ -76,19 +72,14 @@ inline WsLayout ws_layout(int64_t n, int64_t d) {
     int64_t o = (int64_t)sizeof(WsHeader);
     L.off_done = o; o = align_up(o + 4 * n, 256);
     L.off_ready = o; o = align_up(o + 4 * n, 256);
-    L.off_consts = o; o = align_up(o + (int64_t)sizeof(RowConst) * n, 256);
     L.zero_bytes = o;
+    L.off_consts = o; o = align_up(o + (int64_t)sizeof(RowConst) * n, 256);
     L.off_partial = o; o = align_up(o + 8 * n * L.T, 256);
     {
         const int64_t T4 = (d + kCodeTile - 1) / kCodeTile, TB = (T4 + 31) / 32, TS = (TB + 31) / 32;
         L.desc_bytes = n * (8 * T4 + 8 * TB + 16 * TS) + 16;
     }
     L.off_desc = o; o = align_up(o + L.desc_bytes, 256);
-    {
-        const int64_t T4 = (d + kCodeTile - 1) / kCodeTile;
-        L.apart_bytes = n * 8 * ((T4 < kMaxFusedWarps ? (T4 + 1) / 2 * 2 : kMaxFusedWarps) + kMaxFusedWarps / 32);
-    }
-    L.off_apart = o; o = align_up(o + L.apart_bytes, 256);      // directly behind the records: one memset covers both
     L.off_sel = o; o = align_up(o + (int64_t)sizeof(RowSelect) * n, 256);
     L.total = o;
     return L;

@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--mode", default=None, choices=["unbiased", "biased"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="call the eager API every step instead of replaying the captured CUDA graph")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     a = ap.parse_args()
@@ -231,7 +232,22 @@ def run_ours(a):
     def local_type(x, r, **kw):
         return dme.quantize_mean(x, r, check=False, **kw)
 
+    # The plain type path replays one captured CUDA graph per input copy (dme_b200.MeanGraph: uniforms of the round, workspace
+    # reset, l1, quantize, decode in one launch; the round seed lives on the device and advances with every replay); --eager and
+    # the rotated workload call the eager API.  The all-reduce (N > 1) follows the replay.
+    graphs = None
+    if a.kind != "rotated" and not a.eager:
+        graphs = [dme.MeanGraph(X, R, mode=a.mode, seed=1234 + 100000 * k, client0=client0, n_total=n_total, out=mean) for k, X in enumerate(Xs)]
+
     def step(i):
+        if graphs is not None:
+            graphs[i % copies]()
+            if world > 1:
+                dist.all_reduce(mean, op=dist.ReduceOp.SUM)
+            return
+        step_eager(i)
+
+    def step_eager(i):
         X = Xs[i % copies]
         if a.kind == "rotated":
             # every rank rotates its clients, averages them in the rotated domain with the global divisor, ONE all-reduce of the
@@ -248,7 +264,14 @@ def run_ours(a):
 
     for i in range(a.warmup):
         step(i)
-    dme.Workspace.get(dev).status()                      # a kernel-side error in warm-up fails loudly here
+    def status():
+        if graphs is not None:
+            for g in graphs:
+                g.status()
+        else:
+            dme.Workspace.get(dev).status()
+
+    status()                                             # a kernel-side error in warm-up fails loudly here
     sync()
     launches0 = L.dme_launch_count()
     clk = Clocks(local)
@@ -263,7 +286,7 @@ def run_ours(a):
     ms = e0.elapsed_time(e1)
     clocks = clk.stop() if rank == 0 else None
     launches = L.dme_launch_count() - launches0
-    dme.Workspace.get(dev).status()
+    status()
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -274,7 +297,7 @@ def run_ours(a):
     # ---- roofline leg: per-kernel CUDA-event times (events on the launching stream), outside the timed region
     peak, peak_src = peaks()
     B_alg = 4.0 * n * d + 4.0 * d
-    runs = [dme.profile_kernels(lambda: step(1000 + j), warm=0) for j in range(4)][1:]
+    runs = [dme.profile_kernels(lambda: step_eager(1000 + j), warm=0) for j in range(4)][1:]       # eager: one event per launch
     kern_ms = {}
     for run in runs:
         for name, t_ms in run:
@@ -369,7 +392,8 @@ def run_ours(a):
         line = {"metric": metric_name(a), "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 accumulate)", "data": "synthetic",
                 "config": {"workload": workload_name(a), "clients_total": n_total, "m": mm, "parallelism": f"clients sharded x{world}",
-                           "l2_hygiene": hyg},
+                           "l2_hygiene": hyg,
+                           "launch": "one CUDA graph replay per step (dme_b200.MeanGraph)" if graphs is not None else "eager API calls"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "e2e": e2e, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -77,6 +77,12 @@ DME_API int dme_set_unbiased_path(int path);
 /* X_c, the single uniform of client c (AS:634): Philox4x32-10, key = seed, counter = (client, 0, 0, 0x584D44),
  * top 24 bits -> [0,1).  Host-side helper so callers/tests can reproduce the draws. */
 DME_API float dme_uniform_x(uint64_t seed, uint64_t client);
+/* The same draws on the device: xu[c] = X_c of client client0 + c for the seed stored at *seed_dev (DEVICE memory), c < n;
+ * bump != 0 adds one to *seed_dev afterwards.  Lets a captured CUDA graph of the path (x_inject = xu) draw fresh uniforms on every
+ * replay without a host-side argument (dme_b200.api.MeanGraph). */
+DME_API int dme_fill_uniforms(float *xu, int64_t n, uint64_t *seed_dev, uint64_t client0, int bump, dme_stream_t stream);
+/* Adds n to dme_launch_count(): a graph replay launches kernels the library does not see. */
+DME_API void dme_add_launches(int64_t n);
 
 /* Scratch for the type-quantizer entry points (bytes). */
 DME_API int64_t dme_workspace_bytes(int64_t n, int64_t d);

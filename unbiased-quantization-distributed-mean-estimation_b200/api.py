@@ -480,6 +480,67 @@ def quantize_mean(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, c
             plan.grow_worst_case(pn, d, mm, dev)
 
 
+class MeanGraph:
+    """The north-star path of ONE shape as a captured CUDA graph: `g = MeanGraph(x, 1); mean = g()` replays
+    {uniforms of this round, workspace reset, l1_kernel, quantize_warp_kernel, decode_mean} with one launch.  For short rows and
+    few clients (the Flower hook's d = 122 626, n = 100: 30 us of kernels) the eager call is bound by its five launches and the
+    host code around them; the replay is not.  `x` is read in place on every replay (refill it between rounds), the result lands
+    in `out`.  Randomness: X_c comes from the device-resident round seed (dme_fill_uniforms), which every replay increments, so
+    replay k of MeanGraph(seed=s) is bit-identical to quantize_mean(..., seed=s + k); `g(seed=...)` resets it.  A graph cannot
+    read the status word back: call `g.status()` when convenient (an exhausted arena is reported there; build the graph with
+    worst_case=True to rule it out)."""
+
+    def __init__(self, x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, client0=0, n_total=None, out=None, accumulate=False,
+                 worst_case=False):
+        X, n, d, _ = _rows(x)
+        self.X, self.n, self.d = X, n, d
+        self.mm = _resolve_m(d, bits_per_dimension, m)
+        dev = X.device
+        L = _cabi.lib()
+        self.out = torch.empty(d, dtype=torch.float32, device=dev) if out is None else out
+        _check_out(self.out, d, dev)
+        nt = n if n_total is None else int(n_total)
+        self._seed_host = torch.empty(1, dtype=torch.int64).pin_memory()
+        self._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._xu = torch.empty(n, dtype=torch.float32, device=dev)
+        self._cb = int(L.dme_codes_bytes(n, d, self.mm, 0 if worst_case else 1))
+        self._codes = torch.empty(self._cb, dtype=torch.uint8, device=dev)
+        self._dir = torch.empty(int(L.dme_dir_entries(n, d)), dtype=torch.int64, device=dev)
+        self._l1 = torch.empty(n, dtype=torch.float32, device=dev)
+        wsb = int(L.dme_workspace_bytes(n, d))
+        self._ws = torch.empty(wsb + 256, dtype=torch.uint8, device=dev)
+        self._wsp = self._ws.data_ptr() + (-self._ws.data_ptr()) % 256
+        self._wsb = wsb
+        # one eager call first: per-device kernel attributes are set outside the capture
+        quantize_mean(X, bits_per_dimension, mode=mode, m=m, seed=seed, client0=client0, n_total=n_total, out=self.out if not accumulate else None,
+                      check=True)
+        self.set_seed(seed)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = L.dme_launch_count()
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            st = C.c_void_p(_stream())
+            _check(L.dme_fill_uniforms(_ptr(self._xu), n, _ptr(self._seed_dev), client0, 1, st))
+            _check(L.dme_quantize_mean(_ptr(X), n, d, _ld(X), self.mm, MODE[mode], _ptr(self._xu), 0, client0, nt, _ptr(self.out),
+                                       int(bool(accumulate)), _ptr(self._codes), self._cb, _ptr(self._dir), _ptr(self._l1),
+                                       C.c_void_p(self._wsp), self._wsb, st))
+        self.launches = int(L.dme_launch_count() - n0)        # kernels per replay
+
+    def set_seed(self, seed: int) -> None:
+        self._seed_host[0] = int(seed)
+        self._seed_dev.copy_(self._seed_host, non_blocking=True)
+
+    def __call__(self, seed=None) -> torch.Tensor:
+        if seed is not None:
+            self.set_seed(seed)
+        self.graph.replay()
+        _cabi.lib().dme_add_launches(self.launches)
+        return self.out
+
+    def status(self) -> None:
+        _check(_cabi.lib().dme_status(C.c_void_p(self._wsp), C.c_void_p(_stream())))
+
+
 class _HostPipe:
     """Two device staging buffers + a copy stream for quantize_mean_host (kept per device and row length)."""
     _cache: dict = {}

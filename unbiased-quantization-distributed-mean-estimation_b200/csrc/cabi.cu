@@ -42,6 +42,27 @@ extern "C" const char *dme_last_error(void) { return g_err; }
 extern "C" int dme_version(void) { return 100; }
 extern "C" int64_t dme_launch_count(void) { return (int64_t)g_launches.load(); }
 extern "C" float dme_uniform_x(uint64_t seed, uint64_t client) { return philox_client_uniform(seed, client); }
+extern "C" void dme_add_launches(int64_t n) { count_launch((int)n); }
+
+namespace dme {
+__global__ void fill_uniforms_kernel(float *xu, int64_t n, const uint64_t *seedp, uint64_t client0) {
+    const uint64_t seed = *seedp;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x)
+        xu[c] = philox_client_uniform(seed, client0 + (uint64_t)c);
+}
+__global__ void bump_seed_kernel(uint64_t *seedp) { *seedp += 1; }
+}  // namespace dme
+extern "C" int dme_fill_uniforms(float *xu, int64_t n, uint64_t *seed_dev, uint64_t client0, int bump, dme_stream_t stream) {
+    DME_REQUIRE(xu != nullptr && seed_dev != nullptr && n >= 1, "bad argument");
+    const int64_t blocks = (n + 255) / 256;
+    fill_uniforms_kernel<<<(unsigned)(blocks < 1024 ? blocks : 1024), 256, 0, (cudaStream_t)stream>>>(xu, n, seed_dev, client0);
+    DME_LAUNCH_CHECK("fill_uniforms_kernel");
+    if (bump) {
+        bump_seed_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(seed_dev);
+        DME_LAUNCH_CHECK("bump_seed_kernel");
+    }
+    return DME_OK;
+}
 
 extern "C" int64_t dme_workspace_bytes(int64_t n, int64_t d) {
     if (n < 1 || d < 1) return 0;

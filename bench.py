@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--eager", action="store_true", help="call the eager API every step instead of replaying the captured CUDA graph")
+    ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: sum of the ranks' partial means by our peer-memory kernel (dme_peer_sum_slice) or by ncclAllReduce")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     a = ap.parse_args()
@@ -235,6 +237,26 @@ def run_ours(a):
     # The plain type path replays one captured CUDA graph per input copy (dme_b200.MeanGraph: uniforms of the round, workspace
     # reset, l1, quantize, decode in one launch; the round seed lives on the device and advances with every replay); --eager and
     # the rotated workload call the eager API.  The all-reduce (N > 1) follows the replay.
+    # N > 1: the partial means are summed by our own kernel over NVLink peer memory (distributed.PeerReduce: symmetric buffer,
+    # every rank reduces and broadcasts its slice in rank order between two device-side barriers) -- the decode writes straight
+    # into the symmetric buffer; --reduce nccl (or a box without peer access) uses ncclAllReduce.
+    peer, reduce_name = None, "none (one rank)"
+    if world > 1:
+        reduce_name = "ncclAllReduce"
+        if a.reduce == "peer" and a.kind != "rotated":
+            try:
+                peer = dmed.PeerReduce.get(d, None, multicast=False)
+                mean = peer.buffer()
+                reduce_name = "dme_peer_sum_slice over symmetric memory (peer loads in rank order)"
+            except Exception as ex:            # said in the JSON line, not silent
+                reduce_name = f"ncclAllReduce (peer memory unavailable: {str(ex)[:80]})"
+
+    def reduce_mean():
+        if peer is not None:
+            peer.sum_()
+        elif world > 1:
+            dist.all_reduce(mean, op=dist.ReduceOp.SUM)
+
     graphs = None
     if a.kind != "rotated" and not a.eager:
         graphs = [dme.MeanGraph(X, R, mode=a.mode, seed=1234 + 100000 * k, client0=client0, n_total=n_total, out=mean) for k, X in enumerate(Xs)]
@@ -242,8 +264,7 @@ def run_ours(a):
     def step(i):
         if graphs is not None:
             graphs[i % copies]()
-            if world > 1:
-                dist.all_reduce(mean, op=dist.ReduceOp.SUM)
+            reduce_mean()
             return
         step_eager(i)
 
@@ -255,7 +276,11 @@ def run_ours(a):
             dmed.rotated_quantize_mean_sharded(X, R, n_total=n_total, client0=client0, seed=1234 + i, mode=a.mode, out=mean)
         else:
             # N > 1: every rank quantizes + decodes its own clients with the global divisor, then ONE all-reduce
-            dmed.quantize_mean_sharded(X, R, n_total=n_total, client0=client0, seed=1234 + i, mode=a.mode, out=mean, local_fn=local_type)
+            if peer is not None:
+                local_type(X, R, n_total=n_total, client0=client0, seed=1234 + i, mode=a.mode, out=mean)
+                peer.sum_()
+            else:
+                dmed.quantize_mean_sharded(X, R, n_total=n_total, client0=client0, seed=1234 + i, mode=a.mode, out=mean, local_fn=local_type)
 
     def sync():
         if world > 1:
@@ -393,6 +418,7 @@ def run_ours(a):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 accumulate)", "data": "synthetic",
                 "config": {"workload": workload_name(a), "clients_total": n_total, "m": mm, "parallelism": f"clients sharded x{world}",
                            "l2_hygiene": hyg,
+                           "reduce": reduce_name,
                            "launch": "one CUDA graph replay per step (dme_b200.MeanGraph)" if graphs is not None else "eager API calls"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "e2e": e2e, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)

@@ -30,6 +30,8 @@ def test_graph_replays_match_eager(dme, n, d, R, mode):
     got = gm(seed=5).clone()
     assert torch.equal(got, dme.quantize_mean(X, R, mode=mode, seed=5, client0=3))
     assert gm.launches >= 3
+    if d % 4:
+        assert gm._src is not None      # unaligned rows are re-staged inside the graph
 
 
 def test_fill_uniforms_matches_host_philox(dme):

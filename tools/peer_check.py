@@ -17,11 +17,11 @@ def timeit(fn, reps=20):
     t = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t)
 
-for d in (1 << 24, 122626, 1000):
+for d in (1 << 24, 1 << 20, 122626, 1000):
     g = torch.Generator(device="cuda").manual_seed(100 + rank)
     part = torch.randn(d, generator=g, device="cuda")
-    ref = part.clone(); dist.all_reduce(ref)
     for mc in (True, False):
+        ref = part.clone(); dist.all_reduce(ref)
         try:
             pr = dmed.PeerReduce.get(d, None, mc)
         except Exception as ex:

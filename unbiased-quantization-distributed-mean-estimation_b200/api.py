@@ -494,6 +494,11 @@ class MeanGraph:
                  worst_case=False):
         X, n, d, _ = _rows(x)
         self.X, self.n, self.d = X, n, d
+        # rows that are not 16-byte aligned (d % 4 != 0 in a dense matrix) were staged into a padded copy: the graph re-stages
+        # them on every replay, so that `x` is still read "in place"
+        self._src = x if (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 2 and x.data_ptr() != X.data_ptr()) else None
+        if self._src is None and not (isinstance(x, torch.Tensor) and x.is_cuda and x.data_ptr() == X.data_ptr()):
+            raise ValueError("MeanGraph needs a CUDA fp32 tensor (a vector or a matrix of client rows) that stays alive")
         self.mm = _resolve_m(d, bits_per_dimension, m)
         dev = X.device
         L = _cabi.lib()
@@ -520,6 +525,8 @@ class MeanGraph:
         n0 = L.dme_launch_count()
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             st = C.c_void_p(_stream())
+            if self._src is not None:
+                X.copy_(self._src)
             _check(L.dme_fill_uniforms(_ptr(self._xu), n, _ptr(self._seed_dev), client0, 1, st))
             _check(L.dme_quantize_mean(_ptr(X), n, d, _ld(X), self.mm, MODE[mode], _ptr(self._xu), 0, client0, nt, _ptr(self.out),
                                        int(bool(accumulate)), _ptr(self._codes), self._cb, _ptr(self._dir), _ptr(self._l1),

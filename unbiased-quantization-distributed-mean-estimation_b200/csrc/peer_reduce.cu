@@ -12,28 +12,60 @@
 
 namespace dme {
 
+// Four 16-byte pieces per thread and iteration (independent loads in flight: the loads cross NVLink).
+constexpr int kPeerUnroll = 4;
 __global__ void __launch_bounds__(256)
 peer_sum_slice_kernel(float *const *__restrict__ bufs, int64_t off, int rank, int world, int64_t lo, int64_t hi) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
-    for (int64_t i = lo + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < hi; i += stride) {
-        float4 s = *reinterpret_cast<const float4 *>(bufs[0] + off + i);
-        for (int p = 1; p < world; ++p) {
-            const float4 v = *reinterpret_cast<const float4 *>(bufs[p] + off + i);
-            s.x = __fadd_rn(s.x, v.x); s.y = __fadd_rn(s.y, v.y); s.z = __fadd_rn(s.z, v.z); s.w = __fadd_rn(s.w, v.w);
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i0 = lo + tid * 4; i0 < hi; i0 += nthr * 4 * kPeerUnroll) {
+        float4 s[kPeerUnroll];
+#pragma unroll
+        for (int u = 0; u < kPeerUnroll; ++u) {
+            const int64_t i = i0 + (int64_t)u * nthr * 4;
+            s[u] = i < hi ? *reinterpret_cast<const float4 *>(bufs[0] + off + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        for (int p = 0; p < world; ++p) *reinterpret_cast<float4 *>(bufs[p] + off + i) = s;
+        for (int p = 1; p < world; ++p) {
+            float4 v[kPeerUnroll];
+#pragma unroll
+            for (int u = 0; u < kPeerUnroll; ++u) {
+                const int64_t i = i0 + (int64_t)u * nthr * 4;
+                v[u] = i < hi ? *reinterpret_cast<const float4 *>(bufs[p] + off + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < kPeerUnroll; ++u) {
+                s[u].x = __fadd_rn(s[u].x, v[u].x); s[u].y = __fadd_rn(s[u].y, v[u].y);
+                s[u].z = __fadd_rn(s[u].z, v[u].z); s[u].w = __fadd_rn(s[u].w, v[u].w);
+            }
+        }
+        for (int p = 0; p < world; ++p) {
+#pragma unroll
+            for (int u = 0; u < kPeerUnroll; ++u) {
+                const int64_t i = i0 + (int64_t)u * nthr * 4;
+                if (i < hi) *reinterpret_cast<float4 *>(bufs[p] + off + i) = s[u];
+            }
+        }
     }
 }
 
 __global__ void __launch_bounds__(256)
 multimem_sum_slice_kernel(float *mc, int64_t lo, int64_t hi) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
-    for (int64_t i = lo + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < hi; i += stride) {
-        float4 s;
-        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(s.x), "=f"(s.y), "=f"(s.z), "=f"(s.w) : "l"(mc + i) : "memory");
-        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
-                     ::"l"(mc + i), "f"(s.x), "f"(s.y), "f"(s.z), "f"(s.w) : "memory");
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i0 = lo + tid * 4; i0 < hi; i0 += nthr * 4 * kPeerUnroll) {
+        float4 s[kPeerUnroll];
+#pragma unroll
+        for (int u = 0; u < kPeerUnroll; ++u) {
+            const int64_t i = i0 + (int64_t)u * nthr * 4;
+            if (i < hi)
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(s[u].x), "=f"(s[u].y), "=f"(s[u].z), "=f"(s[u].w) : "l"(mc + i) : "memory");
+        }
+#pragma unroll
+        for (int u = 0; u < kPeerUnroll; ++u) {
+            const int64_t i = i0 + (int64_t)u * nthr * 4;
+            if (i < hi)
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                             ::"l"(mc + i), "f"(s[u].x), "f"(s[u].y), "f"(s[u].z), "f"(s[u].w) : "memory");
+        }
     }
 }
 
@@ -50,7 +82,7 @@ extern "C" int dme_peer_sum_slice(float *const *bufs, float *multicast, int64_t 
     const int64_t quads = (d + 3) / 4, per = (quads + world - 1) / world * 4;
     const int64_t lo = (int64_t)rank * per, hi = lo + per < (d + 3) / 4 * 4 ? lo + per : (d + 3) / 4 * 4;
     if (lo >= hi) return DME_OK;
-    const int64_t threads = (hi - lo) / 4;
+    const int64_t threads = ((hi - lo) / 4 + kPeerUnroll - 1) / kPeerUnroll;
     int64_t blocks = (threads + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (multicast) multimem_sum_slice_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(multicast + off, lo, hi);

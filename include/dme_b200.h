@@ -185,8 +185,20 @@ DME_API int dme_eden_encode_frac(const float *X, int64_t n, int64_t d, int64_t l
 DME_API int dme_eden_decode_frac(const uint8_t *bins, const float *scale, int64_t n, int64_t d, int64_t dpad, int nbits_low,
                     int nbits_high, float p_high, const uint8_t *mask_inject, const uint8_t *drop, float keep, uint64_t seed,
                     uint64_t seed_stride, const float *diag_inject, float *work, float *out, int64_t ld_out, dme_stream_t stream);
+/* QuicFLSender.compress (AS:455-503) for n rows: shared rotation (rotation_seed or diag_inject), scale = sqrt(dpad) / ||.||_2,
+ * coordinates with |z| > exact_threshold are sent exactly (exact_mask, and z itself in exact_dense, 0 elsewhere), the others are
+ * rounded stochastically to the grid of step delta ((x_len - 1) / 2 points either side of 0) and looked up in the sender
+ * tables send_X (int8) / send_p (fp32), both x_len x h_len: index X and the probability of X + 1 for grid point x and shared
+ * randomness h.  The reference's tree does not ship these tables; dme_b200/quicfl_tables.py derives them from the receiver
+ * table.  Outputs Xq, h_out (int32), exact_mask (uint8), exact_dense (fp32): all n x dpad; rot: n x dpad scratch; scale_out [n].
+ * dpad: power of two >= max(d, 4).  Randomness: Philox keyed by (seed, client0 + row). */
+DME_API int dme_quicfl_encode(const float *X, int64_t n, int64_t d, int64_t ld, int64_t dpad, int h_len, int x_len, float delta,
+                    float exact_threshold, const int8_t *send_X, const float *send_p, uint64_t seed, uint64_t client0,
+                    uint64_t rotation_seed, const float *diag_inject, float *rot, int32_t *Xq, int32_t *h_out,
+                    uint8_t *exact_mask, float *exact_dense, float *scale_out, dme_stream_t stream);
 /* Xq: int32 n x dpad table rows; h: int32 n x dpad shared randomness; recv_table: (2^nbits) x h_len floats;
- * exact_mask (uint8, nullable) / exact_vals (per row: exact_off[c] .. exact_off[c+1]). */
+ * exact_mask (uint8, nullable) with exact_vals either compacted per row (exact_off[c] .. exact_off[c+1], the reference's
+ * format) or, with exact_off == NULL, dense n x dpad (dme_quicfl_encode's exact_dense). */
 DME_API int dme_quicfl_decode(const int32_t *Xq, const int32_t *h, int64_t n, int64_t d, int64_t dpad, int h_len,
                       const float *recv_table, int table_len, const uint8_t *exact_mask, const float *exact_vals,
                       const int64_t *exact_off, const float *scale, uint64_t rotation_seed,

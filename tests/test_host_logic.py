@@ -62,8 +62,8 @@ def test_dropin_module_mirrors_reference_names():
         sig = inspect.signature(fn)
         assert list(sig.parameters) == ["input_vector", "bits_per_dimension"] and sig.parameters["bits_per_dimension"].default == 1
     assert AS.Type_quantize_algo_rate_l_dict[2] == 0.63752
-    with pytest.raises(FileNotFoundError):
-        AS.QUICFL_quantize(np.zeros(4, np.float32), 1)                           # as in the reference
+    with pytest.raises(KeyError):
+        AS.QUICFL_quantize(np.zeros(4, np.float32), 5)                           # tables exist for 1-4 bits (AS:430)
 
 
 def test_no_cpu_fallback():

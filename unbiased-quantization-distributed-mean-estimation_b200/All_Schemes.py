@@ -87,10 +87,14 @@ def EDEN_quantize_Hadamard(input_vector, bits_per_dimension=1):
 
 
 def QUICFL_quantize(input_vector, bits_per_dimension=1):
-    """AS:814-832.  The reference cannot run this either: its sender tables are not shipped.  The
-    receiver is available as `dme_b200.quicfl_decode`."""
-    raise FileNotFoundError("QUIC-FL sender tables (*_sender_table_X.pt / *_sender_table_p.pt) are not part of the "
-                            "reference tree; only the receiver (dme_b200.quicfl_decode) can be built from it")
+    """AS:814-832: QuicFLSender.compress + QuicFLReceiver.decompress, rotation seed 123, per-call seed in [0, 100) (AS:820); returns
+    numpy (AS:832).  The reference itself raises FileNotFoundError here, because its sender tables are not in its tree (SURVEY F7);
+    `dme_b200.quicfl` derives them from the shipped receiver tables (quicfl_tables.py).  Rates 1-4 bits (AS:430); other rates raise KeyError
+    like the reference's table lookup."""
+    if bits_per_dimension not in (1, 2, 3, 4):
+        raise KeyError(bits_per_dimension)
+    seed = int(torch.randint(0, 100, (1,)).item())                          # AS:820
+    return _api.quicfl(_vec(input_vector), int(bits_per_dimension), seed=seed, rotation_seed=123).cpu().numpy()
 
 
 def Kashin_quantize(input_vector, bits_per_dimension=1):

@@ -43,6 +43,7 @@ SIGNATURES = {
     "dme_eden_decode": (ci, [vp, vp, i64, i64, i64, ci, u64, u64, vp, vp, vp, i64, vp]),
     "dme_eden_encode_frac": (ci, [vp, i64, i64, i64, i64, ci, ci, cf, vp, u64, u64, vp, vp, vp, vp, vp, vp]),
     "dme_eden_decode_frac": (ci, [vp, vp, i64, i64, i64, ci, ci, cf, vp, vp, cf, u64, u64, vp, vp, vp, i64, vp]),
+    "dme_quicfl_encode": (ci, [vp, i64, i64, i64, i64, ci, ci, cf, cf, vp, vp, u64, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp]),
     "dme_quicfl_decode": (ci, [vp, vp, i64, i64, i64, ci, vp, ci, vp, vp, vp, vp, u64, vp, vp, vp, i64, vp]),
     "dme_scalar_quantize": (ci, [vp, i64, i64, i64, cf, u64, u64, vp, vp, i64, vp]),
 }

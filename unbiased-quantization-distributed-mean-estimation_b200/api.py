@@ -960,6 +960,65 @@ def quicfl_decode(Xq, h, d, recv_table, scale, *, exact_mask=None, exact_vals=No
     return out[0] if was_1d else out
 
 
+_quic_dev: dict = {}
+
+
+def _quicfl_tables(nbits, dev, prefix=None):
+    """Receiver and derived sender tables of one rate on the device (quicfl_tables.py), cached."""
+    from . import quicfl_tables as quicfl
+    key = (int(nbits), prefix, dev.index)
+    if key not in _quic_dev:
+        t = quicfl.tables_for(nbits, prefix)
+        _quic_dev[key] = dict(t, recv_dev=torch.from_numpy(np.ascontiguousarray(t["recv"])).to(dev),
+                              send_X_dev=torch.from_numpy(np.ascontiguousarray(t["send_X"])).to(dev),
+                              send_p_dev=torch.from_numpy(np.ascontiguousarray(t["send_p"])).to(dev))
+    return _quic_dev[key]
+
+
+def quicfl_encode(x, nbits=1, *, seed=0, client0=0, rotation_seed=123, diag_inject=None, tables=None):
+    """QuicFLSender.compress (AS:455-503) for the rows of x -> dict {X, h (int32 [n, dpad]), exact_mask (uint8), exact_dense (fp32: the
+    exactly sent values at their positions), scale [n], nbits, d, dpad}.  The sender tables are derived from the receiver table
+    (dme_b200/quicfl_tables.py; the reference does not ship them); `tables` = a reference-style tables directory, default the packaged copy."""
+    X, n, d, was_1d = _rows(x)
+    dev = X.device
+    from . import quicfl_tables as quicfl
+    t = _quicfl_tables(nbits, dev, tables)
+    dpad = max(_pow2_ceil(d), 4)
+    rot = torch.empty((n, dpad), dtype=torch.float32, device=dev)
+    Xq = torch.empty((n, dpad), dtype=torch.int32, device=dev)
+    h = torch.empty((n, dpad), dtype=torch.int32, device=dev)
+    em = torch.empty((n, dpad), dtype=torch.uint8, device=dev)
+    ed = torch.empty((n, dpad), dtype=torch.float32, device=dev)
+    sc = torch.empty(n, dtype=torch.float32, device=dev)
+    dg = _diag(diag_inject, dpad, dev)
+    _check(_cabi.lib().dme_quicfl_encode(_ptr(X), n, d, _ld(X), dpad, t["h_len"], t["x_len"], float(np.float32(t["delta"])),
+                                         float(np.float32(quicfl.EXACT_THRESHOLD)), _ptr(t["send_X_dev"]), _ptr(t["send_p_dev"]), seed, client0,
+                                         rotation_seed, _ptr(dg), _ptr(rot), _ptr(Xq), _ptr(h), _ptr(em), _ptr(ed), _ptr(sc), C.c_void_p(_stream())))
+    return {"X": Xq, "h": h, "exact_mask": em, "exact_dense": ed, "scale": sc, "nbits": int(nbits), "d": d, "dpad": dpad, "was_1d": was_1d,
+            "rotation_seed": rotation_seed, "tables": tables}
+
+
+def quicfl_decode_dense(enc, *, diag_inject=None):
+    """QuicFLReceiver.decompress (AS:526-535) of quicfl_encode's output (exact values in place, no compaction, no host sync)."""
+    dev = enc["X"].device
+    t = _quicfl_tables(enc["nbits"], dev, enc.get("tables"))
+    n, dpad, d = enc["X"].shape[0], enc["dpad"], enc["d"]
+    work = torch.empty((n, dpad), dtype=torch.float32, device=dev)
+    out = torch.empty((n, (d + 3) // 4 * 4), dtype=torch.float32, device=dev)
+    dg = _diag(diag_inject, dpad, dev)
+    tab = t["recv_dev"]
+    _check(_cabi.lib().dme_quicfl_decode(_ptr(enc["X"]), _ptr(enc["h"]), n, d, dpad, t["h_len"], _ptr(tab), tab.numel(), _ptr(enc["exact_mask"]),
+                                         _ptr(enc["exact_dense"]), None, _ptr(enc["scale"]), enc["rotation_seed"], _ptr(dg), _ptr(work), _ptr(out),
+                                         out.stride(0), C.c_void_p(_stream())))
+    out = out[:, :d]
+    return out[0] if enc["was_1d"] else out
+
+
+def quicfl(x, nbits=1, *, seed=0, client0=0, rotation_seed=123, tables=None):
+    """QUICFL_quantize (AS:814-832): sender + receiver for every row of x."""
+    return quicfl_decode_dense(quicfl_encode(x, nbits, seed=seed, client0=client0, rotation_seed=rotation_seed, tables=tables))
+
+
 def scalar_quantize(x, bits_per_dimension=1, *, seed=0, client0=0, u_inject=None):
     """Scalar_quantize (AS:755-790)."""
     X, n, d, was_1d = _rows(x)

@@ -244,7 +244,7 @@ quicfl_gather_kernel(const int32_t *__restrict__ Xq, const int32_t *__restrict__
             int64_t idx = (int64_t)Xq[c * dpad + i] * h_len + h[c * dpad + i];
             idx = idx < 0 ? 0 : (idx >= table_len ? table_len - 1 : idx);
             float val = table[idx];                                                               // AS:530
-            if (mk) val = exact_vals[exact_off[c] + carry + wbase + inc - 1];                      // AS:531
+            if (mk) val = exact_off ? exact_vals[exact_off[c] + carry + wbase + inc - 1] : exact_vals[c * dpad + i];   // AS:531 (or dense)
             work[c * dpad + i] = __fdiv_rn(val, sc);                                               // AS:532
         }
         __syncthreads();
@@ -452,7 +452,7 @@ extern "C" int dme_quicfl_decode(const int32_t *Xq, const int32_t *h, int64_t n,
                                  float *work, float *out, int64_t ld_out, dme_stream_t stream) {
     DME_REQUIRE(Xq && h && recv_table && scale && work && out, "null pointer argument");
     DME_REQUIRE(n >= 1 && d >= 1 && dpad >= d && h_len >= 1 && table_len >= h_len && ld_out >= d, "bad geometry");
-    DME_REQUIRE(!exact_mask || (exact_vals && exact_off), "exact_mask needs exact_vals and exact_off");
+    DME_REQUIRE(!exact_mask || exact_vals, "exact_mask needs exact_vals (compacted with exact_off, or dense n x dpad without)");
     cudaStream_t st = (cudaStream_t)stream;
     quicfl_gather_kernel<<<(unsigned)n, 256, 0, st>>>(Xq, h, dpad, h_len, recv_table, table_len, exact_mask, exact_vals, exact_off, scale, work);
     DME_LAUNCH_CHECK("quicfl_gather_kernel");
@@ -460,6 +460,82 @@ extern "C" int dme_quicfl_decode(const int32_t *Xq, const int32_t *h, int64_t n,
     if (rc) return rc;
     scale_rows_kernel<<<dim3((unsigned)((d + 1023) / 1024), (unsigned)n), 256, 0, st>>>(work, dpad, nullptr, n, d, out, ld_out);
     DME_LAUNCH_CHECK("scale_rows_kernel");
+    return DME_OK;
+}
+
+// ------------------------------------------------------------------ QUIC-FL sender (AS:455-503)
+// After the rotation and the scaling to unit variance: coordinates beyond the tail threshold are sent exactly; the others are
+// rounded stochastically to the grid of step delta, and the sender table of the (grid point, shared randomness h) pair gives
+// the index X and the probability of X + 1.  Four coordinates per thread; two Philox blocks per group: word j of the first
+// gives coordinate j its h (low bits) and the uniform of the grid rounding (top 24 bits), word j of the second the uniform of
+// the X / X + 1 choice.  (The reference draws h from a torch generator that sender and receiver seed alike and the last
+// Bernoulli from the global generator, AS:457-490; here both sides get h from the sender's output.)
+constexpr uint32_t kStreamQuic = 0x514643u;   // "QFC"
+__global__ void __launch_bounds__(256)
+quicfl_encode_kernel(const float *__restrict__ rot, int64_t dpad, const float *__restrict__ nrm, float sqd, int h_len, int x_len, float delta,
+                     float thr, const int8_t *__restrict__ send_X, const float *__restrict__ send_p, uint64_t seed, uint64_t client0,
+                     int32_t *__restrict__ Xq, int32_t *__restrict__ h_out, uint8_t *__restrict__ exact_mask, float *__restrict__ exact_dense,
+                     float *__restrict__ scale_out) {
+    const int64_t c = blockIdx.y;
+    const float scale = __fdiv_rn(sqd, nrm[c]);                                                       // AS:466 / AS:470
+    if (blockIdx.x == 0 && threadIdx.x == 0) scale_out[c] = scale;
+    const uint64_t cl = client0 + (uint64_t)c;
+    const uint64_t key = seed ^ (cl * 0x9E3779B97F4A7C15ull);
+    const int half = (x_len - 1) / 2;
+    const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x, i0 = g * 4;
+    if (i0 >= dpad) return;
+    const float4 v4 = *reinterpret_cast<const float4 *>(rot + c * dpad + i0);
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    const Philox4 pa = philox4x32_10(key, (uint32_t)g, (uint32_t)((uint64_t)g >> 32), 0u, kStreamQuic);
+    const Philox4 pb = philox4x32_10(key, (uint32_t)g, (uint32_t)((uint64_t)g >> 32), 1u, kStreamQuic);
+    const uint32_t wa[4] = {pa.x, pa.y, pa.z, pa.w}, wb[4] = {pb.x, pb.y, pb.z, pb.w};
+    int xs[4], hs[4];
+    uint32_t em = 0;
+    float ev[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float z = __fmul_rn(v[j], scale);                                                       // AS:472
+        const bool exact = z > thr || z < -thr;                                                       // AS:478
+        float q = __fdiv_rn(z, delta);                                                                // AS:480
+        if (exact) q = 0.0f;                                                                          // AS:481
+        const float fl = floorf(q), p = __fsub_rn(q, fl);                                             // AS:483
+        int iq = (int)fl + ((u24_to_unit(wa[j]) < p) ? 1 : 0);                                        // AS:484
+        iq = iq < -half ? -half : (iq > half ? half : iq);
+        const int h = (int)(wa[j] & 0xffu) % h_len;
+        const int64_t idx = (int64_t)(iq + half) * h_len + h;                                         // AS:486
+        const int X = (int)send_X[idx] + ((u24_to_unit(wb[j]) < send_p[idx]) ? 1 : 0);                // AS:486-489
+        xs[j] = X; hs[j] = h; ev[j] = exact ? z : 0.0f;
+        em |= (exact ? 1u : 0u) << (8 * j);
+    }
+    *reinterpret_cast<int4 *>(Xq + c * dpad + i0) = make_int4(xs[0], xs[1], xs[2], xs[3]);
+    *reinterpret_cast<int4 *>(h_out + c * dpad + i0) = make_int4(hs[0], hs[1], hs[2], hs[3]);
+    *reinterpret_cast<uint32_t *>(exact_mask + c * dpad + i0) = em;
+    *reinterpret_cast<float4 *>(exact_dense + c * dpad + i0) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+}
+
+extern "C" int dme_quicfl_encode(const float *X, int64_t n, int64_t d, int64_t ld, int64_t dpad, int h_len, int x_len, float delta,
+                                 float exact_threshold, const int8_t *send_X, const float *send_p, uint64_t seed, uint64_t client0,
+                                 uint64_t rotation_seed, const float *diag_inject, float *rot, int32_t *Xq, int32_t *h_out,
+                                 uint8_t *exact_mask, float *exact_dense, float *scale_out, dme_stream_t stream) {
+    DME_REQUIRE(X && send_X && send_p && rot && Xq && h_out && exact_mask && exact_dense && scale_out, "null pointer argument");
+    DME_REQUIRE(n >= 1 && n <= 65535 && d >= 1 && dpad >= d && dpad >= 4, "bad geometry");
+    DME_REQUIRE(h_len >= 1 && h_len <= 256 && x_len >= 3 && (x_len & 1) && delta > 0.0f, "bad table geometry");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = fwht_rows(X, d, ld, rot, dpad, dpad, n, diag_inject, rotation_seed, 0, 1, 0, st);       // AS:464 / AS:468 (shared rotation)
+    if (rc) return rc;
+    const int nb = slices(dpad);
+    AsyncScratch partial(st), nrm(st);
+    DME_CUDA(partial.alloc(sizeof(double) * (size_t)(n * nb)));
+    DME_CUDA(nrm.alloc(sizeof(float) * (size_t)n));
+    row_sumsq_kernel<<<dim3((unsigned)nb, (unsigned)n), 256, 0, st>>>(rot, dpad, dpad, nb, (double *)partial.p);
+    DME_LAUNCH_CHECK("row_sumsq_kernel");
+    norm_finalize_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((double *)partial.p, nb, n, nullptr, (float *)nrm.p);
+    DME_LAUNCH_CHECK("norm_finalize_kernel");
+    const float sq = (float)std::sqrt((double)dpad);
+    quicfl_encode_kernel<<<dim3((unsigned)((dpad / 4 + 255) / 256), (unsigned)n), 256, 0, st>>>(
+        rot, dpad, (const float *)nrm.p, sq, h_len, x_len, delta, exact_threshold, send_X, send_p, seed, client0, Xq, h_out, exact_mask,
+        exact_dense, scale_out);
+    DME_LAUNCH_CHECK("quicfl_encode_kernel");
     return DME_OK;
 }
 

@@ -56,9 +56,12 @@ def _estimate(line: str, X: torch.Tensor, seed: int, kashin: bool):
         return api.mean_accumulate(api.eden(X, int(line[-4]), seed=seed))
     if line.startswith("Scalar_"):
         return api.mean_accumulate(api.scalar_quantize(X, int(line[-4]), seed=seed))
+    if line.startswith("QUICFL_"):
+        # one sender seed per client in [0, 100) like AS:820 would draw; here Philox is keyed by (seed, client)
+        return api.mean_accumulate(api.quicfl(X, int(line[-4]), seed=seed))
     if line.startswith("Kashin_") and kashin:
         return api.mean_accumulate(api.kashin(X, int(line[-4]), seed=np.random.default_rng(seed).integers(0, 100, n)))      # all rows per transform launch (AS:191-239, AS:834-854)
-    return None                                  # QUIC-FL, Kashin when disabled
+    return None                                  # Kashin when disabled
 
 
 def run(dist="normal", dim=2048, num_users_list=None, num_instances=50, num_trials=50, seed=42, lines=None, kashin=True,

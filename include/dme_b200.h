@@ -44,6 +44,8 @@ extern "C" {
 #define DME_ECUDA (-2)     /* CUDA runtime error / no device */
 #define DME_EWORKSPACE (-3)/* workspace or code arena too small */
 #define DME_EOVERFLOW (-4) /* a magnitude does not fit the requested output (reported by dme_status) */
+#define DME_ERETRY (-5)    /* biased mode: a tie-heavy row overflowed the fast selection (reported by dme_status): rerun the call after
+                            * dme_set_biased_path(1) */
 
 #define DME_MODE_UNBIASED 0
 #define DME_MODE_BIASED 1
@@ -73,6 +75,11 @@ DME_API const char *dme_profile_name(int i);
 /* Test hook: which implementation runs the unbiased mode.  0 (default) = l1_kernel + quantize_warp_kernel (the product path);
  * 1 = literal_rows_kernel (AS:625-637 as written, one CTA per row: an independent implementation for the parity tests). */
 DME_API int dme_set_unbiased_path(int path);
+/* Which selection the biased mode's mass repair (AS:655-664) uses: 0 (default) = one linear histogram of the residuals + a compact
+ * candidate list of the threshold bin (4 passes over the rows); 1 = MSB-first radix select over all coordinates (8 passes; any
+ * input, however many ties).  Path 0 reports DME_ERETRY through dme_status when a row's threshold bin does not fit its candidate
+ * list; both paths give the same result when path 0 succeeds (ties: lowest index first). */
+DME_API int dme_set_biased_path(int path);
 
 /* X_c, the single uniform of client c (AS:634): Philox4x32-10, key = seed, counter = (client, 0, 0, 0x584D44),
  * top 24 bits -> [0,1).  Host-side helper so callers/tests can reproduce the draws. */

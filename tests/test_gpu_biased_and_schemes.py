@@ -32,7 +32,16 @@ def _u32(a):
 
 
 # ------------------------------------------------------------------ biased
-def test_golden_biased_vs_oracle_and_reference(dme, golden_dir):
+@pytest.fixture(params=["linear", "radix"])
+def biased_path(request, dme):
+    """Both selections of the mass repair (csrc/reznik.cu): the linear-histogram path (default; tie-heavy rows fall back to the
+    radix path through dme_status, inside the API) and the radix select over all coordinates."""
+    dme.set_biased_path(request.param)
+    yield request.param
+    dme.set_biased_path("linear")
+
+
+def test_golden_biased_vs_oracle_and_reference(dme, golden_dir, biased_path):
     g = np.load(os.path.join(golden_dir, "type_quantizers.npz"))
     n = int(g["n_biased"])
     same_as_ref = 0
@@ -48,7 +57,7 @@ def test_golden_biased_vs_oracle_and_reference(dme, golden_dir):
 
 @pytest.mark.parametrize("n,d", [(1, 1), (3, 17), (2, 4096), (3, 4097), (4, 65536), (2, 122626), (1, 1 << 20)])
 @pytest.mark.parametrize("R", [1, 2, 4])
-def test_biased_random_rows(dme, n, d, R):
+def test_biased_random_rows(dme, n, d, R, biased_path):
     rng = np.random.default_rng(7 * n + d)
     X = rng.standard_normal((n, d)).astype(np.float32)
     if d > 100:
@@ -68,7 +77,7 @@ def test_biased_random_rows(dme, n, d, R):
 
 
 @pytest.mark.parametrize("dist", ["uniform", "bernoulli", "lognormal12", "onehot", "zeros"])
-def test_biased_tie_heavy_and_edge_inputs(dme, dist):
+def test_biased_tie_heavy_and_edge_inputs(dme, dist, biased_path):
     rng = np.random.default_rng(3)
     d = 30000
     x = {"uniform": rng.uniform(-1, 1, d), "bernoulli": (rng.random(d) < 0.7).astype(np.float64),
@@ -81,7 +90,25 @@ def test_biased_tie_heavy_and_edge_inputs(dme, dist):
         assert np.array_equal(_u32(out["deq"].cpu().numpy()), _u32(o["deq"])), (dist, R)
 
 
-def test_biased_packed_and_mean(dme):
+@pytest.mark.parametrize("n,d,R,scale", [(3, 1 << 20, 1, 1.0), (2, (1 << 22) + 777, 2, 1.0), (40, 65536, 1, 1.0), (4, 300000, 4, 1.0), (3, 1 << 20, 1, 0.0)])
+def test_biased_linear_equals_radix(dme, n, d, R, scale):
+    """Long rows: the two selections must agree bit for bit (k, hence everything); scale = 0: heavy-tailed rows (lognormal)."""
+    g = torch.Generator(device="cuda").manual_seed(d % 1000 + n)
+    X = torch.randn((n, d), generator=g, device="cuda")
+    if scale == 0.0:
+        X = torch.exp(2.0 * X) * torch.sign(torch.randn((n, d), generator=g, device="cuda"))
+    res = {}
+    for path in ("linear", "radix"):
+        dme.set_biased_path(path)
+        out = dme.type_quantize(X, R, mode="biased", want=("k", "deq"))
+        res[path] = (out["k"].clone(), out["deq"].clone(), out["m"])
+    dme.set_biased_path("linear")
+    assert torch.equal(res["linear"][0], res["radix"][0])
+    assert torch.equal(res["linear"][1].view(torch.int32), res["radix"][1].view(torch.int32))
+    assert (res["linear"][0].sum(dim=1) == res["linear"][2]).all()            # mass repaired exactly
+
+
+def test_biased_packed_and_mean(dme, biased_path):
     rng = np.random.default_rng(21)
     n, d = 5, 2 * 4096 + 777
     X = rng.standard_normal((n, d)).astype(np.float32)

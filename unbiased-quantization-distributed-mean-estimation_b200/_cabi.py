@@ -18,6 +18,7 @@ SIGNATURES = {
     "dme_profile_read": (ci, [vp, ci]),
     "dme_profile_name": (C.c_char_p, [ci]),
     "dme_set_unbiased_path": (ci, [ci]),
+    "dme_set_biased_path": (ci, [ci]),
     "dme_fill_uniforms": (ci, [vp, i64, vp, u64, ci, vp]),
     "dme_add_launches": (None, [i64]),
     "dme_uniform_x": (cf, [u64, u64]),

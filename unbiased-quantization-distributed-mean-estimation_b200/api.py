@@ -31,6 +31,29 @@ class DmeError(RuntimeError):
     pass
 
 
+class _RetryBiased(DmeError):
+    """dme_status: a tie-heavy row overflowed the biased mode's fast selection; the call is repeated on the radix path."""
+
+
+def _biased_retry(fn):
+    """Run fn(); when the status word asks for it, run it again with the radix selection (dme_set_biased_path)."""
+    try:
+        return fn()
+    except _RetryBiased:
+        L = _cabi.lib()
+        _check(L.dme_set_biased_path(1))
+        try:
+            return fn()
+        finally:
+            _check(L.dme_set_biased_path(0))
+
+
+def set_biased_path(path) -> None:
+    """Test hook (dme_set_biased_path): "linear" (default) = one linear histogram of the residuals + a candidate list of the
+    threshold bin; "radix" = MSB-first radix select over all coordinates (any number of ties)."""
+    _check(_cabi.lib().dme_set_biased_path({"linear": 0, "radix": 1}.get(path, path)))
+
+
 def m_for_rate(bits_per_dimension, d: int) -> int:
     """AS:622-623.  Unknown rates raise KeyError exactly like the reference's dict lookup."""
     return int(RATE_TABLE[bits_per_dimension] * d)
@@ -46,6 +69,8 @@ def _check(rc: int):
         raise MemoryError(msg)
     if rc == -4:
         raise OverflowError(msg)
+    if rc == -5:
+        raise _RetryBiased(msg)
     raise DmeError(f"libdme_b200 error {rc}: {msg}")
 
 
@@ -201,10 +226,12 @@ def type_quantize(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, c
     q = torch.empty((n, ldo), dtype=torch.float32, device=dev) if "deq" in want else None
     l1 = torch.empty(n, dtype=torch.float32, device=dev)
     xi, li = _opt_vec(x_inject, n, dev), _opt_vec(l1_inject, n, dev)
-    _check(_cabi.lib().dme_type_quantize(_ptr(X), n, d, _ld(X), mm, MODE[mode], _ptr(xi), _ptr(li), seed, client0,
-                                         _ptr(k), _ptr(s), _ptr(q), ldo, _ptr(l1), ws, wsb, C.c_void_p(_stream())))
-    if check and k is not None:
-        Workspace.get(dev).status()
+    def call():
+        _check(_cabi.lib().dme_type_quantize(_ptr(X), n, d, _ld(X), mm, MODE[mode], _ptr(xi), _ptr(li), seed, client0,
+                                             _ptr(k), _ptr(s), _ptr(q), ldo, _ptr(l1), ws, wsb, C.c_void_p(_stream())))
+        if check and (k is not None or mode == "biased"):        # biased: the fast selection reports tie-heavy rows here
+            Workspace.get(dev).status()
+    _biased_retry(call)
     out = {"m": mm, "l1": l1}
     for name, t in (("k", k), ("sgn", s), ("deq", q)):
         if t is not None:
@@ -301,11 +328,13 @@ def type_encode(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, cli
         codes = torch.empty(cb, dtype=torch.uint8, device=dev)
         dr = torch.empty(int(L.dme_dir_entries(n, d)), dtype=torch.int64, device=dev)
         l1 = torch.empty(n, dtype=torch.float32, device=dev)
-        try:
+        def call():
             _check(L.dme_type_encode(_ptr(X), n, d, _ld(X), mm, MODE[mode], _ptr(xi), _ptr(li), seed, client0, _ptr(codes), cb,
                                      _ptr(dr), _ptr(l1), ws, wsb, C.c_void_p(_stream())))
             if check:
                 Workspace.get(dev).status()
+        try:
+            _biased_retry(call)
             break
         except MemoryError:
             worst = int(L.dme_codes_bytes(n, d, mm, 0))
@@ -457,23 +486,26 @@ def quantize_mean(x, bits_per_dimension=1, *, mode="unbiased", m=None, seed=0, c
         _check_out(out, d, dev)
     xi = _opt_vec(x_inject, n, dev)
     nt = n if n_total is None else int(n_total)
+    def run():
+        if accumulate and check:
+            # adding to `out` cannot be undone: encode first, read the status word, decode only a complete code (an arena
+            # overflow drops tiles).  check=False keeps the single fused call and does NOT detect dropped tiles.
+            _check(L.dme_type_encode(_ptr(X), n, d, _ld(X), mm, MODE[mode], _ptr(xi), None, seed, client0, _ptr(plan.codes), plan.cb,
+                                     _ptr(plan.dir), _ptr(plan.l1), ws, wsb, C.c_void_p(_stream())))
+            Workspace.get(dev).status()
+            _check(L.dme_decode_mean(_ptr(plan.codes), _ptr(plan.dir), _ptr(plan.l1), n, d, mm, MODE[mode], nt, _ptr(out), 1,
+                                     C.c_void_p(_stream())))
+            return out
+        _check(L.dme_quantize_mean(_ptr(X), n, d, _ld(X), mm, MODE[mode], _ptr(xi), seed, client0, nt, _ptr(out),
+                                   int(bool(accumulate)), _ptr(plan.codes), plan.cb, _ptr(plan.dir), _ptr(plan.l1), ws, wsb,
+                                   C.c_void_p(_stream())))
+        if check:
+            Workspace.get(dev).status()
+        return out
+
     while True:
         try:
-            if accumulate and check:
-                # adding to `out` cannot be undone: encode first, read the status word, decode only a complete code (an arena
-                # overflow drops tiles).  check=False keeps the single fused call and does NOT detect dropped tiles.
-                _check(L.dme_type_encode(_ptr(X), n, d, _ld(X), mm, MODE[mode], _ptr(xi), None, seed, client0, _ptr(plan.codes), plan.cb,
-                                         _ptr(plan.dir), _ptr(plan.l1), ws, wsb, C.c_void_p(_stream())))
-                Workspace.get(dev).status()
-                _check(L.dme_decode_mean(_ptr(plan.codes), _ptr(plan.dir), _ptr(plan.l1), n, d, mm, MODE[mode], nt, _ptr(out), 1,
-                                         C.c_void_p(_stream())))
-                return out
-            _check(L.dme_quantize_mean(_ptr(X), n, d, _ld(X), mm, MODE[mode], _ptr(xi), seed, client0, nt, _ptr(out),
-                                       int(bool(accumulate)), _ptr(plan.codes), plan.cb, _ptr(plan.dir), _ptr(plan.l1), ws, wsb,
-                                       C.c_void_p(_stream())))
-            if check:
-                Workspace.get(dev).status()
-            return out
+            return _biased_retry(run)
         except MemoryError:
             if plan.cb >= int(L.dme_codes_bytes(pn, d, mm, 0)):
                 raise

@@ -292,11 +292,287 @@ rz_apply_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T, c
     }
 }
 
+// ================================================================== linear selection (default path)
+// The residuals delta' = k' - m p lie in [-1/2, 1/2] and are spread evenly there, so ONE histogram over B linear bins
+// (bin = floor((delta' + 1/2) B), monotone in delta') locates the |Delta|-th largest (smallest) residual up to a bin that
+// holds about d / B coordinates.  Passes over the rows:
+//   rz_sumhist : k', m' = sum k' and the bin histogram, a run of tiles per CTA (one flush of the bins per run)
+//   rz_linpick : Delta, the threshold bin b* (bins beyond it are adjusted entirely) and how many of b*'s coordinates are needed
+//   rz_compact : the coordinates of bin b* -> candidate list {exact order-preserving key, index} of the row
+//   rz_linselect (one CTA per row, on the list): the threshold key, how many threshold-equal coordinates are needed, and the
+//                index below which they are taken (ties: lowest index first, as in the radix path)
+//   rz_linapply: k = k' -/+ 1 for the selected coordinates, emit
+// A row whose threshold bin does not fit the list (many equal residuals: a constant or mostly-zero row with a large |Delta|)
+// sets status bit 4; the host reruns the call on the radix path (dme_set_biased_path(1)).
+__device__ __forceinline__ int lin_bin(float delta, int B) {
+    float t = __fmul_rn(__fadd_rn(delta, 0.5f), (float)B);
+    t = fminf(fmaxf(t, 0.0f), (float)(B - 1));                 // NaN -> 0
+    return (int)t;
+}
+
+__global__ void __launch_bounds__(kThreads)
+rz_sumhist_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T, int tiles_per_cta, int B, const RowConst *__restrict__ consts,
+                  RowSelect *sel, uint32_t *__restrict__ hist) {
+    extern __shared__ uint32_t s_lin[];                        // B bins
+    __shared__ unsigned long long s_red[kWarps];
+    const int64_t c = blockIdx.y;
+    const int64_t t0 = (int64_t)blockIdx.x * tiles_per_cta, t1 = t0 + tiles_per_cta < T ? t0 + tiles_per_cta : T;
+    for (int b = threadIdx.x; b < B; b += kThreads) s_lin[b] = 0;
+    const RowConst rc = consts[c];
+    __syncthreads();
+    unsigned long long s = 0;
+    for (int64_t t = t0; t < t1; ++t) {
+        float x[kEpt];
+        load_tile_striped(X + c * ld, d, t * kTile, x);
+        const bool full = (t + 1) * kTile <= d;
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) {
+            if (!full && striped_index(t * kTile, j) >= d) continue;
+            float kp, dl;
+            rz_round(x[j], rc, kp, dl);
+            s += (unsigned long long)kp;
+            atomicAdd(&s_lin[lin_bin(dl, B)], 1u);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long tot = 0;
+        for (int w = 0; w < kWarps; ++w) tot += s_red[w];
+        if (tot) atomicAdd(&sel[c].mprime, tot);
+    }
+    for (int b = threadIdx.x; b < B; b += kThreads) {
+        const uint32_t v = s_lin[b];
+        if (v) atomicAdd(&hist[c * B + b], v);
+    }
+}
+
+// One warp per row: Delta, then the walk over the bins from the end the adjustment starts at (position q of the walk is bin
+// B - 1 - q for Delta > 0, bin q for Delta < 0): every lane sums a run of B / 32 positions, a warp scan finds the run in which
+// the wanted rank falls, that lane walks its run.
+__global__ void rz_linpick_kernel(RowSelect *sel, const uint32_t *__restrict__ hist, int64_t n, int64_t m, int64_t d, int B) {
+    const int64_t c = blockIdx.x;
+    const int lane = threadIdx.x;
+    RowSelect &s = sel[c];
+    const long long Delta = (long long)s.mprime - (long long)m;            // AS:655
+    long long need = Delta < 0 ? -Delta : Delta;
+    if (need > d) need = d;            // the reference's topk raises when |Delta| > d; here every coordinate is adjusted once
+    if (lane == 0) { s.Delta = Delta; s.lin_ncand = 0; s.lin_cut = 0; s.tie_key = 0; s.tie_take = 0; }
+    if (need == 0) {                   // Delta == 0: nothing is adjusted
+        if (lane == 0) { s.lin_bstar = -1; s.lin_need = 0; }
+        return;
+    }
+    const uint32_t *h = hist + c * B;
+    const int per = B / 32;            // B is a power of two >= 64
+    const bool down = Delta > 0;
+    unsigned long long run = 0;
+    for (int q = lane * per; q < (lane + 1) * per; ++q) run += h[down ? B - 1 - q : q];
+    unsigned long long incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    const uint32_t hit = __ballot_sync(0xffffffffu, incl >= (unsigned long long)need);      // non-empty: the total is d >= need
+    if (hit == 0u || lane != __ffs(hit) - 1) return;
+    unsigned long long cum = incl - run;
+    int q = lane * per;
+    for (; q < (lane + 1) * per - 1; ++q) {
+        const uint32_t v = h[down ? B - 1 - q : q];
+        if (cum + v >= (unsigned long long)need) break;
+        cum += v;
+    }
+    s.lin_bstar = down ? B - 1 - q : q;
+    s.lin_need = (uint32_t)((unsigned long long)need - cum);               // >= 1, <= the threshold bin's count
+}
+
+__global__ void __launch_bounds__(kThreads)
+rz_compact_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T, int tiles_per_cta, int B, int64_t cap,
+                  const RowConst *__restrict__ consts, RowSelect *sel, uint2 *__restrict__ cand, WsHeader *hdr) {
+    const int64_t c = blockIdx.y;
+    const long long Delta = sel[c].Delta;
+    if (Delta == 0) return;
+    const int bstar = sel[c].lin_bstar;
+    const RowConst rc = consts[c];
+    const bool neg = Delta < 0;
+    const int64_t t0 = (int64_t)blockIdx.x * tiles_per_cta, t1 = t0 + tiles_per_cta < T ? t0 + tiles_per_cta : T;
+    for (int64_t t = t0; t < t1; ++t) {
+        float x[kEpt];
+        load_tile_striped(X + c * ld, d, t * kTile, x);
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) {
+            const int64_t i = striped_index(t * kTile, j);
+            if (i >= d) continue;
+            float kp, dl;
+            rz_round(x[j], rc, kp, dl);
+            if (lin_bin(dl, B) != bstar) continue;
+            const uint32_t pos = atomicAdd(&sel[c].lin_ncand, 1u);
+            if ((int64_t)pos < cap) cand[c * cap + pos] = make_uint2(rz_key(dl, neg), (uint32_t)i);
+            else atomicOr(&hdr->status, 4u);
+        }
+    }
+}
+
+// CTA-wide radix select on a list in global memory: the `want`-th largest (descending) / smallest (!descending) value of field
+// .x (keys) or .y (indices) among the entries that pass the filter (key == fkey when filter_on).  Returns the value and how many
+// entries lie strictly beyond it in the chosen direction.  want >= 1 and <= the number of entries that pass.
+__device__ uint32_t cta_select(const uint2 *list, uint32_t n, uint32_t want, bool descending, bool field_y, bool filter_on, uint32_t fkey,
+                               uint32_t *s_hist /* 256 */, uint32_t *s_misc /* 2 */, uint32_t &beyond) {
+    uint32_t prefix = 0, rem = want, passed = 0;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        s_hist[threadIdx.x] = 0;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += kThreads) {
+            const uint2 e = list[i];
+            if (filter_on && e.x != fkey) continue;
+            const uint32_t v = field_y ? e.y : e.x;
+            if (pass == 0 || (v >> (shift + 8)) == prefix) atomicAdd(&s_hist[(v >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t cum = 0;
+            int b = descending ? 255 : 0;
+            for (;;) {
+                const uint32_t h = s_hist[b];
+                if (cum + h >= rem) break;
+                cum += h;
+                b += descending ? -1 : 1;
+                if (b < 0 || b > 255) { b = descending ? 0 : 255; break; }      // cannot happen for a valid `want`
+            }
+            s_misc[0] = (uint32_t)b; s_misc[1] = cum;
+        }
+        __syncthreads();
+        prefix = (prefix << 8) | s_misc[0];
+        passed += s_misc[1];
+        rem -= s_misc[1];
+        __syncthreads();
+    }
+    beyond = passed;
+    return prefix;
+}
+
+__global__ void __launch_bounds__(kThreads)
+rz_linselect_kernel(RowSelect *sel, const uint2 *__restrict__ cand, int64_t cap) {
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_misc[2];
+    const int64_t c = blockIdx.x;
+    RowSelect &s = sel[c];
+    if (s.Delta == 0 || s.lin_need == 0) return;
+    const uint32_t n = s.lin_ncand < (uint32_t)cap ? s.lin_ncand : (uint32_t)cap;
+    if (s.lin_ncand > (uint32_t)cap || s.lin_need > n) return;             // overflow: status bit 4 is set, the host reruns the call
+    const uint2 *list = cand + c * cap;
+    uint32_t above = 0, before = 0;
+    const uint32_t tie = cta_select(list, n, s.lin_need, true, false, false, 0u, s_hist, s_misc, above);
+    const uint32_t take = s.lin_need - above;                               // >= 1 threshold-equal candidates are adjusted
+    const uint32_t cut = cta_select(list, n, take, false, true, true, tie, s_hist, s_misc, before);      // the take-th smallest index
+    if (threadIdx.x == 0) { s.tie_key = tie; s.tie_take = take; s.lin_cut = cut + 1u; }
+}
+
+__global__ void __launch_bounds__(kThreads, 4)
+rz_linapply_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T, int B, const RowConst *__restrict__ consts,
+                   const RowSelect *__restrict__ sel, RzEmit e) {
+    __shared__ PackScratch s_pack;
+    const int64_t c = blockIdx.y, t = blockIdx.x;
+    float x[kEpt];
+    load_tile_blocked(X + c * ld, d, t * kTile, x);
+    const RowConst rc = consts[c];
+    const long long Delta = sel[c].Delta;
+    const int bstar = sel[c].lin_bstar;
+    const uint32_t tie = sel[c].tie_key, cut = sel[c].lin_cut;
+    const int64_t i0 = t * kTile + (int64_t)threadIdx.x * kEpt;
+    const bool neg = Delta < 0;
+    const float adj = Delta > 0 ? -1.0f : 1.0f;
+    float kp[kEpt];
+#pragma unroll
+    for (int j = 0; j < kEpt; ++j) {
+        float dl;
+        rz_round(x[j], rc, kp[j], dl);
+        if (Delta == 0 || i0 + j >= d) continue;
+        const int b = lin_bin(dl, B);
+        bool selct = neg ? b < bstar : b > bstar;
+        if (b == bstar) {
+            const uint32_t key = rz_key(dl, neg);
+            selct = key > tie || (key == tie && (uint32_t)(i0 + j) < cut);
+        }
+        if (selct) kp[j] = __fadd_rn(kp[j], adj);                          // AS:660 / AS:664
+    }
+    if (!e.packed) {
+        bool ovf = false;
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) {
+            const int64_t i = i0 + j;
+            if (i >= d) break;
+            if (e.deq_out) {
+                const float sg = (x[j] > 0.0f) ? 1.0f : ((x[j] < 0.0f) ? -1.0f : 0.0f);     // AS:682 signs of the input
+                e.deq_out[c * e.ld_out + i] = __fmul_rn(__fmul_rn(rc.L1f, sg), __fdiv_rn(kp[j], rc.mf));   // AS:666, AS:687
+            }
+            if (e.k_out) {
+                if (kp[j] >= 2147483648.0f) { ovf = true; e.k_out[c * e.ld_out + i] = 0x7fffffff; }
+                else e.k_out[c * e.ld_out + i] = (int32_t)kp[j];
+            }
+            if (e.sgn_out) e.sgn_out[c * e.ld_out + i] = (uint8_t)(__float_as_uint(x[j]) >> 31);
+        }
+        if (ovf) atomicOr(&e.pack.hdr->status, 1u);
+    } else {
+        uint32_t k[kEpt], sg[kEpt];
+        bool ovf = false;
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) {
+            const float kk = (i0 + j < d) ? kp[j] : 0.0f;
+            if (kk >= 2147483648.0f) { ovf = true; k[j] = 0x7fffffffu; } else k[j] = (uint32_t)kk;
+            sg[j] = __float_as_uint(x[j]) >> 31;
+        }
+        emit_packed_tile(e.pack, c, t, k, sg, ovf, s_pack);
+    }
+}
+
+static int g_biased_path = 0;
+void set_biased_path(int path) { g_biased_path = path; }
+
+static int biased_quantize_linear(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws, RzEmit e,
+                                  cudaStream_t st) {
+    char *base = (char *)ws;
+    const RowConst *consts = (const RowConst *)(base + L.off_consts);
+    RowSelect *sel = (RowSelect *)(base + L.off_sel);
+    uint32_t *hist = (uint32_t *)(base + L.off_lin);
+    uint2 *cand = (uint2 *)(base + L.off_lin + L.lin_hist_bytes);
+    const int B = (int)L.lin_bins;
+    // a run of tiles per CTA: one flush of the bins per run, and still a few thousand CTAs
+    int64_t tp = (n * L.T) / 4096;
+    tp = tp < 1 ? 1 : (tp > 64 ? 64 : tp);
+    const dim3 grun((unsigned)((L.T + tp - 1) / tp), (unsigned)n), grid((unsigned)L.T, (unsigned)n);
+    rz_sumhist_kernel<<<grun, kThreads, (size_t)B * 4, st>>>(X, d, ld, L.T, (int)tp, B, consts, sel, hist);
+    DME_LAUNCH_CHECK("rz_sumhist_kernel");
+    rz_linpick_kernel<<<(unsigned)n, 32, 0, st>>>(sel, hist, n, m, d, B);
+    DME_LAUNCH_CHECK("rz_linpick_kernel");
+    rz_compact_kernel<<<grun, kThreads, 0, st>>>(X, d, ld, L.T, (int)tp, B, L.lin_cap, consts, sel, cand, (WsHeader *)base);
+    DME_LAUNCH_CHECK("rz_compact_kernel");
+    rz_linselect_kernel<<<(unsigned)n, kThreads, 0, st>>>(sel, cand, L.lin_cap);
+    DME_LAUNCH_CHECK("rz_linselect_kernel");
+    rz_linapply_kernel<<<grid, kThreads, 0, st>>>(X, d, ld, L.T, B, consts, sel, e);
+    DME_LAUNCH_CHECK("rz_linapply_kernel");
+    return DME_OK;
+}
+
 // Called after l1_kernel has published the row constants.
 int biased_quantize(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
                     int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
                     uint32_t *codes, int64_t codes_bytes, uint64_t *dir, cudaStream_t st) {
     char *base = (char *)ws;
+    if (g_biased_path == 0) {
+        RzEmit e0;
+        e0.k_out = k_out; e0.sgn_out = sgn_out; e0.deq_out = deq_out; e0.ld_out = ld_out;
+        e0.packed = codes != nullptr;
+        init_pack_target(e0.pack, codes, codes_bytes, dir, (WsHeader *)base, n, d, m);
+        if (e0.packed && (long long)(e0.pack.arena_base16 * 16ull) > codes_bytes) {
+            set_error("code arena too small for the primary slots: %lld bytes", (long long)codes_bytes);
+            return DME_EWORKSPACE;
+        }
+        return biased_quantize_linear(X, n, d, ld, m, L, ws, e0, st);
+    }
     const RowConst *consts = (const RowConst *)(base + L.off_consts);
     RowSelect *sel = (RowSelect *)(base + L.off_sel);
     uint32_t *tie_cnt = (uint32_t *)(base + L.off_partial);         // the L1 partials are dead by now

@@ -445,7 +445,10 @@ int ws_prepare(void *ws, int64_t ws_bytes, int64_t n, int64_t d, cudaStream_t st
     if (need_desc) {
         DME_CUDA(cudaMemsetAsync(base + L.off_desc, 0, (size_t)L.desc_bytes, st));
     }
-    if (need_sel) DME_CUDA(cudaMemsetAsync(base + L.off_sel, 0, sizeof(RowSelect) * (size_t)n, st));
+    if (need_sel) {
+        DME_CUDA(cudaMemsetAsync(base + L.off_sel, 0, sizeof(RowSelect) * (size_t)n, st));
+        DME_CUDA(cudaMemsetAsync(base + L.off_lin, 0, (size_t)L.lin_hist_bytes, st));
+    }
     *out = L;
     return DME_OK;
 }
@@ -463,6 +466,7 @@ int launch_l1(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const
 int biased_quantize(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
                     int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
                     uint32_t *codes, int64_t codes_bytes, uint64_t *dir, cudaStream_t st);   // reznik.cu
+void set_biased_path(int path);                                                                        // reznik.cu
 int launch_quantize_warp(const float *X, int64_t n, int64_t d, int64_t ld, int64_t m, const WsLayout &L, void *ws,
                           int32_t *k_out, uint8_t *sgn_out, float *deq_out, int64_t ld_out,
                           uint32_t *codes, int64_t codes_bytes, uint64_t *dir, cudaStream_t st, bool packed);   // quantize_warp.cu
@@ -566,6 +570,12 @@ extern "C" int dme_decode_mean(const void *codes, const uint64_t *dir, const flo
     return dme_decode_mean_tiles(codes, dir, l1, n, d, m, mode, n_total, mean, accumulate, 0, d >= 1 ? (d + kCodeTile - 1) / kCodeTile : 0, stream);
 }
 
+extern "C" int dme_set_biased_path(int path) {
+    DME_REQUIRE(path == 0 || path == 1, "path=%d unknown", path);
+    set_biased_path(path);
+    return DME_OK;
+}
+
 extern "C" int dme_set_unbiased_path(int path) {
     DME_REQUIRE(path == 0 || path == 1, "path=%d unknown", path);
     g_unbiased_path = path;
@@ -594,6 +604,7 @@ extern "C" int dme_status(const void *ws, dme_stream_t stream) {
     uint32_t st = 0;
     DME_CUDA(cudaMemcpyAsync(&st, &((const WsHeader *)ws)->status, sizeof(st), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     DME_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (st & 4u) { set_error("biased selection: a row's threshold bin overflowed its candidate list (tie-heavy row): rerun with dme_set_biased_path(1)"); return DME_ERETRY; }
     if (st & 2u) { set_error("code arena exhausted: enlarge codes_bytes (dme_codes_bytes(..., expect=0) is always enough)"); return DME_EWORKSPACE; }
     if (st & 1u) { set_error("a magnitude does not fit the requested integer output"); return DME_EOVERFLOW; }
     return DME_OK;

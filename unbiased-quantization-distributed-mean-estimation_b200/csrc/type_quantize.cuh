@@ -38,6 +38,9 @@ struct WsLayout {
     int64_t off_desc;     // look-back records of quantize_warp_kernel: 8 bytes per code tile, 8 per block of 32 tiles, 16 per
     int64_t desc_bytes;   // super-block of 1024 tiles
     int64_t off_sel;      // RowSelect sel[n] (biased mode)
+    int64_t off_lin;      // biased mode, linear selection: uint32 hist[n][lin_bins], then uint2 cand[n][lin_cap]
+    int64_t lin_hist_bytes, lin_bytes;
+    int64_t lin_bins, lin_cap;
     int64_t zero_bytes;   // prefix that must be zeroed before each call (header + a_done)
     int64_t total;
 };
@@ -54,6 +57,11 @@ struct __align__(16) RowSelect {
     uint32_t hist[4][256];       // per-pass histograms
     uint32_t done[4];            // tiles finished per pass
     uint32_t tie_seen;           // running count for the ordered tie scan
+    // linear-histogram selection (reznik.cu, the default path)
+    int32_t lin_bstar;           // threshold bin: bins beyond it are adjusted entirely
+    uint32_t lin_need;           // how many of the threshold bin's coordinates are adjusted
+    uint32_t lin_ncand;          // coordinates of the threshold bin appended to the candidate list so far
+    uint32_t lin_cut;            // threshold-equal candidates with index < lin_cut are adjusted
     uint32_t pad[3];
 };
 
@@ -65,6 +73,12 @@ inline int expected_width(int64_t m, int64_t d) {
     while (w < 32 && 4.0 * ell + 1.0 >= (double)(1u << (w - 1))) w <<= 1;
     return w;
 }
+
+// Linear selection of the biased mode: bins of the residual histogram (about 8 coordinates per bin for short rows, at most 2048)
+// and capacity of a row's candidate list (the threshold bin holds d / bins coordinates on average: eight times that, plus slack).
+constexpr int kLinBinsMax = 2048;
+inline int64_t lin_bins_for(int64_t d) { int64_t b = 64; while (b < kLinBinsMax && b * 8 < d) b <<= 1; return b; }
+inline int64_t lin_cap_for(int64_t d) { const int64_t c = 8 * (d / lin_bins_for(d)) + 512; return c < d ? c : d; }
 
 inline WsLayout ws_layout(int64_t n, int64_t d) {
     WsLayout L;
@@ -81,6 +95,11 @@ inline WsLayout ws_layout(int64_t n, int64_t d) {
     }
     L.off_desc = o; o = align_up(o + L.desc_bytes, 256);
     L.off_sel = o; o = align_up(o + (int64_t)sizeof(RowSelect) * n, 256);
+    L.lin_bins = lin_bins_for(d);
+    L.lin_cap = lin_cap_for(d);
+    L.lin_hist_bytes = align_up(n * L.lin_bins * 4, 256);
+    L.lin_bytes = L.lin_hist_bytes + n * L.lin_cap * 8;
+    L.off_lin = o; o = align_up(o + L.lin_bytes, 256);
     L.total = o;
     return L;
 }

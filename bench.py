@@ -222,7 +222,9 @@ def run_ours(a):
     copies = max(1, -(-L2_BYTES // (4 * n * d)))          # small inputs: rotate over enough copies to defeat L2
     Xs = []
     for k in range(copies):
-        X = torch.empty((n, d), dtype=torch.float32, device=dev)
+        # client rows in a row-aligned buffer (row stride = d rounded up to 4 floats: 16-byte aligned rows, what the kernels read
+        # in place; a dense (n, d) matrix with d % 4 != 0 would be staged into such a buffer on every call)
+        X = torch.empty((n, (d + 3) // 4 * 4), dtype=torch.float32, device=dev)[:, :d]
         for c in range(n):                                   # row by row: keeps the generator's scratch small
             X[c].normal_(generator=gen)
         Xs.append(X)

@@ -304,9 +304,9 @@ rz_apply_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T, c
 //   rz_linapply: k = k' -/+ 1 for the selected coordinates, emit
 // A row whose threshold bin does not fit the list (many equal residuals: a constant or mostly-zero row with a large |Delta|)
 // sets status bit 4; the host reruns the call on the radix path (dme_set_biased_path(1)).
-__device__ __forceinline__ int lin_bin(float delta, int B) {
-    float t = __fmul_rn(__fadd_rn(delta, 0.5f), (float)B);
-    t = fminf(fmaxf(t, 0.0f), (float)(B - 1));                 // NaN -> 0
+__device__ __forceinline__ int lin_bin(float delta, float Bf, float Bm1) {          // Bf = float(B), Bm1 = float(B - 1)
+    float t = __fmul_rn(__fadd_rn(delta, 0.5f), Bf);
+    t = fminf(fmaxf(t, 0.0f), Bm1);                            // NaN -> 0
     return (int)t;
 }
 
@@ -321,17 +321,30 @@ rz_sumhist_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T,
     const RowConst rc = consts[c];
     __syncthreads();
     unsigned long long s = 0;
+    const float Bf = (float)B, Bm1 = (float)(B - 1);
+    const bool small_k = rc.mf <= 16777216.0f && !(rc.flags & kRowGuardFloor);      // k' <= m p + 1/2 < 2^25: sixteen of them fit 32 bits
     for (int64_t t = t0; t < t1; ++t) {
         float x[kEpt];
         load_tile_striped(X + c * ld, d, t * kTile, x);
-        const bool full = (t + 1) * kTile <= d;
+        if ((t + 1) * kTile <= d && small_k) {
+            uint32_t s32 = 0;
 #pragma unroll
-        for (int j = 0; j < kEpt; ++j) {
-            if (!full && striped_index(t * kTile, j) >= d) continue;
-            float kp, dl;
-            rz_round(x[j], rc, kp, dl);
-            s += (unsigned long long)kp;
-            atomicAdd(&s_lin[lin_bin(dl, B)], 1u);
+            for (int j = 0; j < kEpt; ++j) {
+                float kp, dl;
+                rz_round(x[j], rc, kp, dl);
+                s32 += (uint32_t)kp;
+                atomicAdd(&s_lin[lin_bin(dl, Bf, Bm1)], 1u);
+            }
+            s += s32;
+        } else {
+#pragma unroll
+            for (int j = 0; j < kEpt; ++j) {
+                if (striped_index(t * kTile, j) >= d) continue;
+                float kp, dl;
+                rz_round(x[j], rc, kp, dl);
+                s += (unsigned long long)kp;
+                atomicAdd(&s_lin[lin_bin(dl, Bf, Bm1)], 1u);
+            }
         }
     }
 #pragma unroll
@@ -398,18 +411,27 @@ rz_compact_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T,
     const RowConst rc = consts[c];
     const bool neg = Delta < 0;
     const int64_t t0 = (int64_t)blockIdx.x * tiles_per_cta, t1 = t0 + tiles_per_cta < T ? t0 + tiles_per_cta : T;
+    const float Bf = (float)B, Bm1 = (float)(B - 1);
     for (int64_t t = t0; t < t1; ++t) {
         float x[kEpt];
         load_tile_striped(X + c * ld, d, t * kTile, x);
+        const bool full = (t + 1) * kTile <= d;
+        uint32_t hits = 0;                                     // bit j: coordinate j of this thread lies in the threshold bin
+        float dls[kEpt];
 #pragma unroll
         for (int j = 0; j < kEpt; ++j) {
+            float kp;
+            rz_round(x[j], rc, kp, dls[j]);
+            hits |= (lin_bin(dls[j], Bf, Bm1) == bstar ? 1u : 0u) << j;
+        }
+        if (hits == 0u) continue;                              // the threshold bin holds one coordinate in B
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) {
+            if (!((hits >> j) & 1u)) continue;
             const int64_t i = striped_index(t * kTile, j);
-            if (i >= d) continue;
-            float kp, dl;
-            rz_round(x[j], rc, kp, dl);
-            if (lin_bin(dl, B) != bstar) continue;
+            if (!full && i >= d) continue;
             const uint32_t pos = atomicAdd(&sel[c].lin_ncand, 1u);
-            if ((int64_t)pos < cap) cand[c * cap + pos] = make_uint2(rz_key(dl, neg), (uint32_t)i);
+            if ((int64_t)pos < cap) cand[c * cap + pos] = make_uint2(rz_key(dls[j], neg), (uint32_t)i);
             else atomicOr(&hdr->status, 4u);
         }
     }
@@ -485,19 +507,22 @@ rz_linapply_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T
     const int64_t i0 = t * kTile + (int64_t)threadIdx.x * kEpt;
     const bool neg = Delta < 0;
     const float adj = Delta > 0 ? -1.0f : 1.0f;
+    const float Bf = (float)B, Bm1 = (float)(B - 1);
+    const int sdir = neg ? -1 : 1;                             // bins beyond the threshold bin: (b - b*) * sdir > 0
+    // coordinates past the end of the row read as zero: k' = 0, and they are never written, so no index test is needed up to the
+    // threshold bin itself (a padded zero has delta' = 0, which may be the threshold bin: the index test is there)
     float kp[kEpt];
 #pragma unroll
     for (int j = 0; j < kEpt; ++j) {
         float dl;
         rz_round(x[j], rc, kp[j], dl);
-        if (Delta == 0 || i0 + j >= d) continue;
-        const int b = lin_bin(dl, B);
-        bool selct = neg ? b < bstar : b > bstar;
-        if (b == bstar) {
+        const int rel = (lin_bin(dl, Bf, Bm1) - bstar) * sdir;
+        bool selct = rel > 0;
+        if (rel == 0) {                                        // rare: one coordinate in B
             const uint32_t key = rz_key(dl, neg);
             selct = key > tie || (key == tie && (uint32_t)(i0 + j) < cut);
         }
-        if (selct) kp[j] = __fadd_rn(kp[j], adj);                          // AS:660 / AS:664
+        kp[j] = __fadd_rn(kp[j], (selct && Delta != 0) ? adj : 0.0f);      // AS:660 / AS:664
     }
     if (!e.packed) {
         bool ovf = false;

@@ -512,17 +512,25 @@ rz_linapply_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T
     // coordinates past the end of the row read as zero: k' = 0, and they are never written, so no index test is needed up to the
     // threshold bin itself (a padded zero has delta' = 0, which may be the threshold bin: the index test is there)
     float kp[kEpt];
+    uint32_t rare = 0;                                         // bit j: coordinate j lies in the threshold bin (one in B does)
+    const float adj0 = Delta != 0 ? adj : 0.0f;
 #pragma unroll
     for (int j = 0; j < kEpt; ++j) {
         float dl;
         rz_round(x[j], rc, kp[j], dl);
         const int rel = (lin_bin(dl, Bf, Bm1) - bstar) * sdir;
-        bool selct = rel > 0;
-        if (rel == 0) {                                        // rare: one coordinate in B
+        rare |= (rel == 0 ? 1u : 0u) << j;
+        kp[j] = __fadd_rn(kp[j], rel > 0 ? adj0 : 0.0f);                   // AS:660 / AS:664
+    }
+    if (rare != 0u && Delta != 0) {
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) {
+            if (!((rare >> j) & 1u)) continue;
+            float k0, dl;
+            rz_round(x[j], rc, k0, dl);
             const uint32_t key = rz_key(dl, neg);
-            selct = key > tie || (key == tie && (uint32_t)(i0 + j) < cut);
+            if (key > tie || (key == tie && (uint32_t)(i0 + j) < cut)) kp[j] = __fadd_rn(k0, adj);
         }
-        kp[j] = __fadd_rn(kp[j], (selct && Delta != 0) ? adj : 0.0f);      // AS:660 / AS:664
     }
     if (!e.packed) {
         bool ovf = false;

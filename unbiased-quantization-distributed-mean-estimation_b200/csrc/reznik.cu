@@ -53,9 +53,10 @@ __device__ __forceinline__ int64_t striped_index(int64_t tile0, int j) { return 
 // Rows inside the proven operand range of the fast chain (RowConst flags, type_quantize.cuh) get the same values from
 // Markstein's correction of |x| * RN(1/D) (= the correctly rounded quotient) and a magic-number floor (exact below 2^23):
 // 8 instructions instead of an IEEE division and a floorf per coordinate and pass.
-__device__ __forceinline__ void rz_round(float x, const RowConst &rc, float &kp, float &delta) {
+template <bool FAST>
+__device__ __forceinline__ void rz_round_t(float x, const RowConst &rc, float &kp, float &delta) {
     float mp;
-    if (!(rc.flags & (kRowExact | kRowGuardFloor))) {
+    if (FAST) {
         const float ax = fabsf(x);
         const float q0 = __fmul_rn(ax, rc.rcpD);
         const float p = __fmaf_rn(__fmaf_rn(-q0, rc.D, ax), rc.rcpD, q0);          // AS:683
@@ -67,6 +68,10 @@ __device__ __forceinline__ void rz_round(float x, const RowConst &rc, float &kp,
         kp = floorf(__fadd_rn(mp, 0.5f));                      // AS:648
     }
     delta = __fsub_rn(kp, mp);                                 // AS:654
+}
+__device__ __forceinline__ bool rz_fast_row(const RowConst &rc) { return !(rc.flags & (kRowExact | kRowGuardFloor)); }
+__device__ __forceinline__ void rz_round(float x, const RowConst &rc, float &kp, float &delta) {
+    if (rz_fast_row(rc)) rz_round_t<true>(x, rc, kp, delta); else rz_round_t<false>(x, rc, kp, delta);
 }
 // Order-preserving key of the value that torch.topk ranks: delta (Delta > 0) or -delta (Delta < 0).
 __device__ __forceinline__ uint32_t rz_key(float delta, bool neg) {
@@ -493,31 +498,24 @@ rz_linselect_kernel(RowSelect *sel, const uint2 *__restrict__ cand, int64_t cap)
     if (threadIdx.x == 0) { s.tie_key = tie; s.tie_take = take; s.lin_cut = cut + 1u; }
 }
 
-__global__ void __launch_bounds__(kThreads, 4)
-rz_linapply_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T, int B, const RowConst *__restrict__ consts,
-                   const RowSelect *__restrict__ sel, RzEmit e) {
-    __shared__ PackScratch s_pack;
-    const int64_t c = blockIdx.y, t = blockIdx.x;
-    float x[kEpt];
-    load_tile_blocked(X + c * ld, d, t * kTile, x);
-    const RowConst rc = consts[c];
-    const long long Delta = sel[c].Delta;
-    const int bstar = sel[c].lin_bstar;
-    const uint32_t tie = sel[c].tie_key, cut = sel[c].lin_cut;
+// FAST: the row is inside the proven operand range of the fast chain and k' < 2^25 (no overflow test); FULL: the tile lies inside
+// the row (no index tests).  One instantiation per combination: the per-coordinate loops carry no row- or tile-uniform branches.
+template <bool FAST, bool FULL>
+__device__ __forceinline__ void rz_linapply_tile(const float (&x)[kEpt], const RowConst &rc, long long Delta, int bstar, uint32_t tie, uint32_t cut,
+                                                 int B, int64_t d, int64_t c, int64_t t, const RzEmit &e, PackScratch &s_pack) {
     const int64_t i0 = t * kTile + (int64_t)threadIdx.x * kEpt;
     const bool neg = Delta < 0;
     const float adj = Delta > 0 ? -1.0f : 1.0f;
     const float Bf = (float)B, Bm1 = (float)(B - 1);
     const int sdir = neg ? -1 : 1;                             // bins beyond the threshold bin: (b - b*) * sdir > 0
-    // coordinates past the end of the row read as zero: k' = 0, and they are never written, so no index test is needed up to the
-    // threshold bin itself (a padded zero has delta' = 0, which may be the threshold bin: the index test is there)
+    // coordinates past the end of the row read as zero: k' = 0, and they are never written
     float kp[kEpt];
     uint32_t rare = 0;                                         // bit j: coordinate j lies in the threshold bin (one in B does)
     const float adj0 = Delta != 0 ? adj : 0.0f;
 #pragma unroll
     for (int j = 0; j < kEpt; ++j) {
         float dl;
-        rz_round(x[j], rc, kp[j], dl);
+        rz_round_t<FAST>(x[j], rc, kp[j], dl);
         const int rel = (lin_bin(dl, Bf, Bm1) - bstar) * sdir;
         rare |= (rel == 0 ? 1u : 0u) << j;
         kp[j] = __fadd_rn(kp[j], rel > 0 ? adj0 : 0.0f);                   // AS:660 / AS:664
@@ -527,7 +525,7 @@ rz_linapply_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T
         for (int j = 0; j < kEpt; ++j) {
             if (!((rare >> j) & 1u)) continue;
             float k0, dl;
-            rz_round(x[j], rc, k0, dl);
+            rz_round_t<FAST>(x[j], rc, k0, dl);
             const uint32_t key = rz_key(dl, neg);
             if (key > tie || (key == tie && (uint32_t)(i0 + j) < cut)) kp[j] = __fadd_rn(k0, adj);
         }
@@ -537,13 +535,13 @@ rz_linapply_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T
 #pragma unroll
         for (int j = 0; j < kEpt; ++j) {
             const int64_t i = i0 + j;
-            if (i >= d) break;
+            if (!FULL && i >= d) break;
             if (e.deq_out) {
                 const float sg = (x[j] > 0.0f) ? 1.0f : ((x[j] < 0.0f) ? -1.0f : 0.0f);     // AS:682 signs of the input
                 e.deq_out[c * e.ld_out + i] = __fmul_rn(__fmul_rn(rc.L1f, sg), __fdiv_rn(kp[j], rc.mf));   // AS:666, AS:687
             }
             if (e.k_out) {
-                if (kp[j] >= 2147483648.0f) { ovf = true; e.k_out[c * e.ld_out + i] = 0x7fffffff; }
+                if (!FAST && kp[j] >= 2147483648.0f) { ovf = true; e.k_out[c * e.ld_out + i] = 0x7fffffff; }
                 else e.k_out[c * e.ld_out + i] = (int32_t)kp[j];
             }
             if (e.sgn_out) e.sgn_out[c * e.ld_out + i] = (uint8_t)(__float_as_uint(x[j]) >> 31);
@@ -554,12 +552,29 @@ rz_linapply_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T
         bool ovf = false;
 #pragma unroll
         for (int j = 0; j < kEpt; ++j) {
-            const float kk = (i0 + j < d) ? kp[j] : 0.0f;
-            if (kk >= 2147483648.0f) { ovf = true; k[j] = 0x7fffffffu; } else k[j] = (uint32_t)kk;
+            const float kk = (FULL || i0 + j < d) ? kp[j] : 0.0f;
+            if (!FAST && kk >= 2147483648.0f) { ovf = true; k[j] = 0x7fffffffu; } else k[j] = (uint32_t)kk;
             sg[j] = __float_as_uint(x[j]) >> 31;
         }
         emit_packed_tile(e.pack, c, t, k, sg, ovf, s_pack);
     }
+}
+
+__global__ void __launch_bounds__(kThreads, 3)
+rz_linapply_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T, int B, const RowConst *__restrict__ consts,
+                   const RowSelect *__restrict__ sel, RzEmit e) {
+    __shared__ PackScratch s_pack;
+    const int64_t c = blockIdx.y, t = blockIdx.x;
+    float x[kEpt];
+    load_tile_blocked(X + c * ld, d, t * kTile, x);
+    const RowConst rc = consts[c];
+    const long long Delta = sel[c].Delta;
+    const int bstar = sel[c].lin_bstar;
+    const uint32_t tie = sel[c].tie_key, cut = sel[c].lin_cut;
+    const bool fast = rz_fast_row(rc) && rc.mf <= 16777216.0f, full = (t + 1) * kTile <= d;
+    if (fast && full) rz_linapply_tile<true, true>(x, rc, Delta, bstar, tie, cut, B, d, c, t, e, s_pack);
+    else if (fast) rz_linapply_tile<true, false>(x, rc, Delta, bstar, tie, cut, B, d, c, t, e, s_pack);
+    else rz_linapply_tile<false, false>(x, rc, Delta, bstar, tie, cut, B, d, c, t, e, s_pack);
 }
 
 static int g_biased_path = 0;

@@ -247,9 +247,12 @@ def run_ours(a):
         reduce_name = "ncclAllReduce"
         if a.reduce == "peer" and a.kind != "rotated":
             try:
-                peer = dmed.PeerReduce.get(d, None, multicast=False)
+                # measured (profiles/r02f_peer_check_n2/n4.txt, r02g_peer_check_n8.txt; 64 MiB): peer loads win at N = 2 (0.126 ms vs
+                # multimem 0.20 / NCCL 0.146), the in-switch reduction at N = 8 (0.212 vs 0.314 / 0.256); a tie at N = 4
+                peer = dmed.PeerReduce.get(d, None, multicast=world >= 4)
                 mean = peer.buffer()
-                reduce_name = "dme_peer_sum_slice over symmetric memory (peer loads in rank order)"
+                reduce_name = ("dme_peer_sum_slice over symmetric memory (" +
+                               ("multimem.ld_reduce / multimem.st through the NVSwitch" if peer.mc else "peer loads in rank order") + ")")
             except Exception as ex:            # said in the JSON line, not silent
                 reduce_name = f"ncclAllReduce (peer memory unavailable: {str(ex)[:80]})"
 

@@ -80,16 +80,36 @@ __global__ void __launch_bounds__(256) fwht_contig_kernel(FwhtIo io, int64_t n, 
     if (io.d >= 16) {
         const int64_t row = g0 / io.d, col = g0 - row * io.d;
         const bool live = g0 < total;
+        const bool vec = ((io.src_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(io.src) & 15) == 0);
+        if (vec && io.d >= 4096 && io.src_d == io.d) {
+            // the block is 4096 consecutive columns of ONE dense row: coalesced 128-bit loads (piece q * 256 + t of the block),
+            // handed to their owners (thread t: elements 16 t .. 16 t + 15) through the padded shared-memory array
+            const int64_t b0 = (int64_t)blockIdx.x * 4096;
+            const int64_t brow = b0 / io.d;
+            const float *bsrc = io.src + brow * io.src_ld + (b0 - brow * io.d);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int e = 4 * (q * 256 + t);
+                const float4 x = *reinterpret_cast<const float4 *>(bsrc + e);
+                float *dstp = sm + padded(e);                // e .. e + 3 share one 32-block: no pad inside
+                dstp[0] = x.x; dstp[1] = x.y; dstp[2] = x.z; dstp[3] = x.w;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = sm[padded(16 * t + j)];
+            __syncthreads();
+        } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int64_t c0 = col + 4 * q;
-            if (live && c0 + 4 <= io.src_d && ((io.src_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(io.src) & 15) == 0)) {
+            if (live && c0 + 4 <= io.src_d && vec) {
                 const float4 x = *reinterpret_cast<const float4 *>(io.src + row * io.src_ld + c0);
                 v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[4 * q + j] = (live && c0 + j < io.src_d) ? io.src[row * io.src_ld + c0 + j] : 0.0f;
             }
+        }
         }
         if (io.pre_diag && live) {
             const uint32_t sb = diag_bits16(io, col, row);
@@ -135,6 +155,21 @@ __global__ void __launch_bounds__(256) fwht_contig_kernel(FwhtIo io, int64_t n, 
             for (int j = 0; j < 16; ++j) sm[padded(hi * 256 + j * 16 + lo)] = v[j];
         }
         __syncthreads();
+        if (io.d >= 4096 && !(io.finalize && io.post_diag) && ((io.dst_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(io.dst) & 15) == 0)) {
+            // no per-column sign to apply: the block (4096 consecutive columns of one row) leaves as coalesced 128-bit pieces
+            const int64_t b0 = (int64_t)blockIdx.x * 4096;
+            const int64_t brow = b0 / io.d;
+            float *bdst = io.dst + brow * io.dst_ld + (b0 - brow * io.d);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int e = 4 * (q * 256 + t);
+                const float *sp = sm + padded(e);
+                float4 y = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                if (io.finalize) { y.x = __fdiv_rn(y.x, io.sq); y.y = __fdiv_rn(y.y, io.sq); y.z = __fdiv_rn(y.z, io.sq); y.w = __fdiv_rn(y.w, io.sq); }   // AS:113
+                *reinterpret_cast<float4 *>(bdst + e) = y;
+            }
+            return;
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = sm[padded(16 * t + j)];
     }

@@ -34,7 +34,8 @@
 namespace dme {
 
 constexpr int kCpl = 32;                          // coordinates per lane
-constexpr int kRing = 3;                          // tile buffers per warp: parked (C), current (B), in flight
+constexpr int kLag = 1;                           // the C-phase of a tile runs kLag iterations after its B-phase: 1 (default) or 2 (measured: no gain)
+constexpr int kRing = 2 + kLag;                   // tile buffers per warp: parked (C; kLag of them), current (B), in flight
 constexpr int kQWarps = 4;                        // warps per CTA
 constexpr int kQThreads = kQWarps * 32;
 constexpr int kTileBytes = kCodeTile * 4;
@@ -428,7 +429,7 @@ __device__ __forceinline__ void issue_tile(const WarpArgs &a, const CUtensorMap 
 }
 
 template <int EMIT>
-__global__ void __launch_bounds__(kQThreads, 4)
+__global__ void __launch_bounds__(kQThreads, kLag == 2 ? 3 : 4)
 quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char dyn_smem[];      // per warp: three 4 KB tile buffers; then the mbarriers
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -459,21 +460,24 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
         if (it.valid) DBG_MARK(it.tk, 0);
         return it;
     };
-    Item iB = item_of(a, gw), iN = item_of(a, G + gw), iC;
+    Item iB = item_of(a, gw), iN = item_of(a, G + gw), iC, iC1;      // kLag == 2: iC1 = the tile parked between its B- and C-phase
+    iC1.c = 0; iC1.w = 0; iC1.tk = 0; iC1.valid = false;
     if (!iN.valid) tk_more = false;
     iC.c = 0; iC.w = 0; iC.tk = 0; iC.valid = false;
     if (lane == 0) {
         if (iB.valid) issue_tile(a, &tmap, iB, ring, bars, pol);
         if (iN.valid) issue_tile(a, &tmap, iN, ring + kTileBytes, bars + 8u, pol);
     }
-    Carry cy;                                   // of tile iC
+    Carry cy, cy1;                              // of tile iC (and of iC1)
+    cy1.sgw0 = cy1.sgw1 = cy1.flm = cy1.L0 = cy1.L1 = cy1.ex32 = 0; cy1.mxl = 0.0f; cy1.fmf = 0.0f; cy1.Aq = 0; cy1.AI = 0;
+    cy1.fl4[0] = cy1.fl4[1] = cy1.fl4[2] = cy1.fl4[3] = 0;
     cy.sgw0 = cy.sgw1 = cy.flm = cy.L0 = cy.L1 = cy.ex32 = 0; cy.mxl = 0.0f; cy.fmf = 0.0f; cy.Aq = 0; cy.AI = 0;
     cy.fl4[0] = cy.fl4[1] = cy.fl4[2] = cy.fl4[3] = 0;
     const int qshift = a.qshift, sh = 43 - a.qshift;
     int sB = 0;
     for (uint32_t it = 0;; ++it) {
-        if (!iB.valid && !iC.valid) break;
-        const int sC = sB == 0 ? kRing - 1 : sB - 1;
+        if (!iB.valid && !iC.valid && !(kLag == 2 && iC1.valid)) break;
+        const int sC = (sB + kRing - kLag) % kRing;
         Carry nb;                               // of tile iB
         nb.sgw0 = nb.sgw1 = nb.flm = nb.L0 = nb.L1 = nb.ex32 = 0; nb.mxl = 0.0f; nb.fmf = 0.0f; nb.Aq = 0; nb.AI = 0;
         nb.fl4[0] = nb.fl4[1] = nb.fl4[2] = nb.fl4[3] = 0;
@@ -493,6 +497,9 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
                 if (lane < S) ld_rec2(sp + lane, slo, shi);
             }
         };
+        // kLag == 2: tile iC was published a whole iteration ago, and so were its predecessors (the warps move in lock-step rounds):
+        // the window is complete now, and its round trip to L2 hides behind the B-phase
+        if (kLag == 2) window_issue();
         // ---------------------------------------------------------------- B-phase of tile iB
         if (iB.valid) {
             const RowConst *rcp = a.consts + iB.c;
@@ -556,7 +563,7 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
             }
         }
         // ---------------------------------------------------------------- C-phase of tile iC: AS:635-637, emit
-        window_issue();
+        if (kLag == 1) window_issue();
         if (iB.valid) nb.ex32 = warp_excl_scan_u32((nb.L0 >> 11) | (nb.L1 << 13), lane);      // lane sums in 2^-32 units (mod 2^32)
         // The tile that completed its block forwards the block total to the super-block record: at the end of the iteration (the
         // atomic's round trip hides behind the C-phase), but BEFORE this warp starts to wait for anything -- the look-back of a
@@ -728,8 +735,9 @@ quantize_warp_kernel(const __grid_constant__ WarpArgs a, const __grid_constant__
         if (iC.valid) DBG_MARK(iC.tk, 7);
         if (lane == 0 && iNN.valid) issue_tile(a, &tmap, iNN, ring + (uint32_t)sC * kTileBytes, bars + 8u * sC, pol);
         if (iC.valid) DBG_MARK(iC.tk, 8);
-        iC = iB; iB = iN; iN = iNN;
-        cy = nb;
+        if (kLag == 2) { iC = iC1; iC1 = iB; cy = cy1; cy1 = nb; }
+        else { iC = iB; cy = nb; }
+        iB = iN; iN = iNN;
         sB = sB == kRing - 1 ? 0 : sB + 1;
     }
 }

@@ -500,6 +500,8 @@ rz_linselect_kernel(RowSelect *sel, const uint2 *__restrict__ cand, int64_t cap)
 
 // FAST: the row is inside the proven operand range of the fast chain and k' < 2^25 (no overflow test); FULL: the tile lies inside
 // the row (no index tests).  One instantiation per combination: the per-coordinate loops carry no row- or tile-uniform branches.
+// The largest float below a positive integer-valued float.
+__device__ __forceinline__ float pred_pos(float v) { return __uint_as_float(__float_as_uint(v) - 1u); }      // v >= 1
 template <bool FAST, bool FULL>
 __device__ __forceinline__ void rz_linapply_tile(const float (&x)[kEpt], const RowConst &rc, long long Delta, int bstar, uint32_t tie, uint32_t cut,
                                                  int B, int64_t d, int64_t c, int64_t t, const RzEmit &e, PackScratch &s_pack) {
@@ -512,13 +514,34 @@ __device__ __forceinline__ void rz_linapply_tile(const float (&x)[kEpt], const R
     float kp[kEpt];
     uint32_t rare = 0;                                         // bit j: coordinate j lies in the threshold bin (one in B does)
     const float adj0 = Delta != 0 ? adj : 0.0f;
+    if (FAST) {
+        // No NaN in a fast row, and t = (delta' + 1/2) B >= 0: bin = floor(min(t, B - 1)), so "bin beyond b*" and "bin == b*" are two
+        // comparisons of u = +-t (the sign of the walk folded into B) with constants -- no clamp, no conversion, no integer
+        // arithmetic.  Delta > 0: beyond <=> t >= b* + 1 (never for b* = B - 1), in or beyond <=> t >= b*.  Delta < 0: beyond <=>
+        // t < b* <=> -t >= -pred(b*), in or beyond <=> t < b* + 1 <=> -t >= -pred(b* + 1) (always for b* = B - 1: the clamp).
+        const float inf = __int_as_float(0x7f800000);
+        const float lo = (float)bstar, hi = bstar >= B - 1 ? inf : (float)(bstar + 1);      // bins are < 2^11: exact
+        const float sB = neg ? -Bf : Bf;
+        const float A = neg ? (bstar <= 0 ? inf : -pred_pos(lo)) : hi;      // u >= A: beyond the threshold bin (b* = 0, Delta < 0: never)
+        const float C = neg ? (bstar >= B - 1 ? -inf : -pred_pos(hi)) : lo;      // u >= C: in the threshold bin or beyond it
 #pragma unroll
-    for (int j = 0; j < kEpt; ++j) {
-        float dl;
-        rz_round_t<FAST>(x[j], rc, kp[j], dl);
-        const int rel = (lin_bin(dl, Bf, Bm1) - bstar) * sdir;
-        rare |= (rel == 0 ? 1u : 0u) << j;
-        kp[j] = __fadd_rn(kp[j], rel > 0 ? adj0 : 0.0f);                   // AS:660 / AS:664
+        for (int j = 0; j < kEpt; ++j) {
+            float dl;
+            rz_round_t<true>(x[j], rc, kp[j], dl);
+            const float u = __fmul_rn(__fadd_rn(dl, 0.5f), sB);
+            const bool beyond = u >= A;
+            rare |= ((u >= C && !beyond) ? 1u : 0u) << j;
+            kp[j] = __fadd_rn(kp[j], beyond ? adj0 : 0.0f);                // AS:660 / AS:664
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kEpt; ++j) {
+            float dl;
+            rz_round_t<FAST>(x[j], rc, kp[j], dl);
+            const int rel = (lin_bin(dl, Bf, Bm1) - bstar) * sdir;
+            rare |= (rel == 0 ? 1u : 0u) << j;
+            kp[j] = __fadd_rn(kp[j], rel > 0 ? adj0 : 0.0f);               // AS:660 / AS:664
+        }
     }
     if (rare != 0u && Delta != 0) {
 #pragma unroll

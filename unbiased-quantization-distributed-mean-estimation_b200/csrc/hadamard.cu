@@ -37,6 +37,7 @@ __device__ __forceinline__ void reg_stages(float (&v)[16], int nb) {
 struct FwhtIo {
     const float *src; int64_t src_d, src_ld;   // source rows (length src_d <= d, zero padded)
     float *dst; int64_t d, dst_ld;             // destination rows (length d = power of two)
+    int logd;                                  // d = 2^logd: rows and columns of a flattened index by shift and mask (a 64-bit division is a ~100-instruction call)
     const float *diag;                         // injected +-1 diagonal (d entries) or null
     uint64_t seed, seed_stride; int use_philox; // Philox diagonal of row r is keyed by seed + r * seed_stride
     int pre_diag, post_diag;                   // multiply by the diagonal before the first stage / after the scaling
@@ -70,33 +71,38 @@ __device__ __forceinline__ int padded(int e) { return e + (e >> 5); }
 
 // One CTA = one 4096-element block of the flattened (row-major, dense) index space of n rows x d.
 // logL = min(log2 d, 12) stages are done here.
-__global__ void __launch_bounds__(256) fwht_contig_kernel(FwhtIo io, int64_t n, int logL) {
+__global__ void __launch_bounds__(256, 5) fwht_contig_kernel(FwhtIo io, int64_t n, int logL) {
     __shared__ float sm[kPad];
     const int t = threadIdx.x;
+    // padded(e) = e + (e >> 5) for the four layouts of the block, as base + compile-time offset (the address arithmetic was 40 % of
+    // the kernel's instructions): A: element 16 t + j; B: 256 hi + 16 j + lo; C: 256 j + t; S (coalesced pieces): 1024 q + 4 t + k
+    float *const pA = sm + 16 * t + (t >> 1);                   // [j]
+    float *const pB = sm + (t >> 4) * 264 + (t & 15);           // [16 j + (j >> 1)]
+    float *const pC = sm + t + (t >> 5);                        // [264 j]
+    float *const pS = sm + 4 * t + (t >> 3);                    // [1056 q + k]
     const int64_t g0 = (int64_t)blockIdx.x * 4096 + 16 * t;      // first flattened element of this thread
     const int64_t total = n * io.d;
     float v[16];
     // ---- load (+ zero padding, + diagonal)
     if (io.d >= 16) {
-        const int64_t row = g0 / io.d, col = g0 - row * io.d;
+        const int64_t row = g0 >> io.logd, col = g0 & (io.d - 1);
         const bool live = g0 < total;
         const bool vec = ((io.src_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(io.src) & 15) == 0);
         if (vec && io.d >= 4096 && io.src_d == io.d) {
             // the block is 4096 consecutive columns of ONE dense row: coalesced 128-bit loads (piece q * 256 + t of the block),
             // handed to their owners (thread t: elements 16 t .. 16 t + 15) through the padded shared-memory array
             const int64_t b0 = (int64_t)blockIdx.x * 4096;
-            const int64_t brow = b0 / io.d;
-            const float *bsrc = io.src + brow * io.src_ld + (b0 - brow * io.d);
+            const int64_t brow = b0 >> io.logd;
+            const float *bsrc = io.src + brow * io.src_ld + (b0 & (io.d - 1));
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int e = 4 * (q * 256 + t);
-                const float4 x = *reinterpret_cast<const float4 *>(bsrc + e);
-                float *dstp = sm + padded(e);                // e .. e + 3 share one 32-block: no pad inside
+                const float4 x = *reinterpret_cast<const float4 *>(bsrc + 4 * (q * 256 + t));
+                float *dstp = pS + 1056 * q;                  // the piece's four elements share one 32-block: no pad inside
                 dstp[0] = x.x; dstp[1] = x.y; dstp[2] = x.z; dstp[3] = x.w;
             }
             __syncthreads();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = sm[padded(16 * t + j)];
+            for (int j = 0; j < 16; ++j) v[j] = pA[j];
             __syncthreads();
         } else {
 #pragma unroll
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(256) fwht_contig_kernel(FwhtIo io, int64_t n, 
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int64_t g = g0 + j;
-            const int64_t row = g / io.d, col = g - row * io.d;
+            const int64_t row = g >> io.logd, col = g & (io.d - 1);
             float x = (g < total && col < io.src_d) ? io.src[row * io.src_ld + col] : 0.0f;
             if (io.pre_diag && g < total) x = __fmul_rn(x, diag_at(io, col, row));
             v[j] = x;
@@ -131,39 +137,38 @@ __global__ void __launch_bounds__(256) fwht_contig_kernel(FwhtIo io, int64_t n, 
     if (logL > 4) {
         // ---- phase B: bits 4..7.  thread (lo = t & 15, hi = t >> 4) takes e = hi*256 + j*16 + lo
 #pragma unroll
-        for (int j = 0; j < 16; ++j) sm[padded(16 * t + j)] = v[j];
+        for (int j = 0; j < 16; ++j) pA[j] = v[j];
         __syncthreads();
-        const int lo = t & 15, hi = t >> 4;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = sm[padded(hi * 256 + j * 16 + lo)];
+        for (int j = 0; j < 16; ++j) v[j] = pB[16 * j + (j >> 1)];
         reg_stages<4>(v, logL - 4);
         if (logL > 8) {
             // ---- phase C: bits 8..11.  thread t takes e = j*256 + t
             __syncthreads();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) sm[padded(hi * 256 + j * 16 + lo)] = v[j];
+            for (int j = 0; j < 16; ++j) pB[16 * j + (j >> 1)] = v[j];
             __syncthreads();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = sm[padded(j * 256 + t)];
+            for (int j = 0; j < 16; ++j) v[j] = pC[264 * j];
             reg_stages<4>(v, logL - 8);
             __syncthreads();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) sm[padded(j * 256 + t)] = v[j];
+            for (int j = 0; j < 16; ++j) pC[264 * j] = v[j];
         } else {
             __syncthreads();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) sm[padded(hi * 256 + j * 16 + lo)] = v[j];
+            for (int j = 0; j < 16; ++j) pB[16 * j + (j >> 1)] = v[j];
         }
         __syncthreads();
         if (io.d >= 4096 && !(io.finalize && io.post_diag) && ((io.dst_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(io.dst) & 15) == 0)) {
             // no per-column sign to apply: the block (4096 consecutive columns of one row) leaves as coalesced 128-bit pieces
             const int64_t b0 = (int64_t)blockIdx.x * 4096;
-            const int64_t brow = b0 / io.d;
-            float *bdst = io.dst + brow * io.dst_ld + (b0 - brow * io.d);
+            const int64_t brow = b0 >> io.logd;
+            float *bdst = io.dst + brow * io.dst_ld + (b0 & (io.d - 1));
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int e = 4 * (q * 256 + t);
-                const float *sp = sm + padded(e);
+                const float *sp = pS + 1056 * q;
                 float4 y = make_float4(sp[0], sp[1], sp[2], sp[3]);
                 if (io.finalize) { y.x = __fdiv_rn(y.x, io.sq); y.y = __fdiv_rn(y.y, io.sq); y.z = __fdiv_rn(y.z, io.sq); y.w = __fdiv_rn(y.w, io.sq); }   // AS:113
                 *reinterpret_cast<float4 *>(bdst + e) = y;
@@ -171,14 +176,14 @@ __global__ void __launch_bounds__(256) fwht_contig_kernel(FwhtIo io, int64_t n, 
             return;
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = sm[padded(16 * t + j)];
+        for (int j = 0; j < 16; ++j) v[j] = pA[j];
     }
     // ---- store (+ scaling, + diagonal)
     if (io.d >= 16) {
         // the thread's 16 elements are consecutive columns of one row: one row / column computation, one sign word, and
         // 128-bit stores when the destination allows
         if (g0 >= total) return;
-        const int64_t row = g0 / io.d, col = g0 - row * io.d;
+        const int64_t row = g0 >> io.logd, col = g0 & (io.d - 1);
         uint32_t sb = 0xffffu;
         if (io.finalize && io.post_diag) sb = diag_bits16(io, col, row);
 #pragma unroll
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(256) fwht_contig_kernel(FwhtIo io, int64_t n, 
     for (int j = 0; j < 16; ++j) {
         const int64_t g = g0 + j;
         if (g >= total) break;
-        const int64_t row = g / io.d, col = g - row * io.d;
+        const int64_t row = g >> io.logd, col = g & (io.d - 1);
         float y = v[j];
         if (io.finalize) {
             y = __fdiv_rn(y, io.sq);                                        // AS:113
@@ -217,7 +222,7 @@ __global__ void __launch_bounds__(256) fwht_strided_kernel(FwhtIo io, int64_t n,
     const int64_t cols_per_row = io.d >> p;                     // independent (hi, col) groups per row
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= n * cols_per_row) return;
-    const int64_t row = gid / cols_per_row, w = gid - row * cols_per_row;
+    const int64_t row = gid >> (io.logd - p), w = gid & (cols_per_row - 1);
     const int64_t col = w & (((int64_t)1 << s) - 1), hi = w >> s;
     float *base = io.dst + row * io.dst_ld + (hi << (s + p)) + col;
     const int R = 1 << p;
@@ -249,9 +254,9 @@ __global__ void __launch_bounds__(256) fwht_strided_wide_kernel(FwhtIo io, int64
     __shared__ float sm[R * kStride];
     const int t = threadIdx.x, col_l = t % C, q = t / C;
     const int64_t tiles_per_row = io.d >> 12;
-    const int64_t row = blockIdx.x / tiles_per_row, w = blockIdx.x - row * tiles_per_row;
-    const int64_t cblocks = ((int64_t)1 << s) / C;          // column blocks inside one 2^s run
-    const int64_t hi = w / cblocks, col0 = (w - hi * cblocks) * C;
+    const int64_t row = (int64_t)blockIdx.x >> (io.logd - 12), w = (int64_t)blockIdx.x & (tiles_per_row - 1);
+    const int lcb = s - 12 + P;                             // log2 of the column blocks inside one 2^s run (2^s / C)
+    const int64_t hi = w >> lcb, col0 = (w & (((int64_t)1 << lcb) - 1)) * C;
     float *base = io.dst + row * io.dst_ld + (hi << (s + P)) + col0 + col_l;
     float v[16];
 #pragma unroll
@@ -340,6 +345,7 @@ int fwht_rows(const float *src, int64_t src_d, int64_t src_ld, float *dst, int64
     io.src = src; io.src_d = src_d; io.src_ld = src_ld; io.dst = dst; io.d = d; io.dst_ld = dst_ld;
     io.diag = diag; io.seed = seed; io.seed_stride = seed_stride; io.use_philox = diag == nullptr; io.pre_diag = pre_diag; io.post_diag = post_diag;
     io.sq = (float)std::sqrt((double)d);
+    io.logd = logd;
     const int logL = logd < 12 ? logd : 12;
     io.finalize = (logd <= 12);
     const int64_t blocks = (n * d + 4095) / 4096;

@@ -322,16 +322,29 @@ rz_sumhist_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T,
     __shared__ unsigned long long s_red[kWarps];
     const int64_t c = blockIdx.y;
     const int64_t t0 = (int64_t)blockIdx.x * tiles_per_cta, t1 = t0 + tiles_per_cta < T ? t0 + tiles_per_cta : T;
-    for (int b = threadIdx.x; b < B; b += kThreads) s_lin[b] = 0;
+    for (int b = threadIdx.x; b < B + 2; b += kThreads) s_lin[b] = 0;
     const RowConst rc = consts[c];
     __syncthreads();
     unsigned long long s = 0;
     const float Bf = (float)B, Bm1 = (float)(B - 1);
     const bool small_k = rc.mf <= 16777216.0f && !(rc.flags & kRowGuardFloor);      // k' <= m p + 1/2 < 2^25: sixteen of them fit 32 bits
+    const bool fast = rz_fast_row(rc);
     for (int64_t t = t0; t < t1; ++t) {
         float x[kEpt];
         load_tile_striped(X + c * ld, d, t * kTile, x);
-        if ((t + 1) * kTile <= d && small_k) {
+        if ((t + 1) * kTile <= d && small_k && fast) {
+            // fast rows hold no NaN and 0 <= (delta' + 1/2) B <= B (+ one rounding): no clamp -- the rare bin B (delta' = 1/2) has
+            // its own counter and is folded into bin B - 1 at the flush
+            uint32_t s32 = 0;
+#pragma unroll
+            for (int j = 0; j < kEpt; ++j) {
+                float kp, dl;
+                rz_round_t<true>(x[j], rc, kp, dl);
+                s32 += (uint32_t)kp;
+                atomicAdd(&s_lin[(int)__fmul_rn(__fadd_rn(dl, 0.5f), Bf)], 1u);
+            }
+            s += s32;
+        } else if ((t + 1) * kTile <= d && small_k) {
             uint32_t s32 = 0;
 #pragma unroll
             for (int j = 0; j < kEpt; ++j) {
@@ -362,7 +375,7 @@ rz_sumhist_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T,
         if (tot) atomicAdd(&sel[c].mprime, tot);
     }
     for (int b = threadIdx.x; b < B; b += kThreads) {
-        const uint32_t v = s_lin[b];
+        const uint32_t v = s_lin[b] + (b == B - 1 ? s_lin[B] + s_lin[B + 1] : 0u);
         if (v) atomicAdd(&hist[c * B + b], v);
     }
 }
@@ -417,17 +430,30 @@ rz_compact_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T,
     const bool neg = Delta < 0;
     const int64_t t0 = (int64_t)blockIdx.x * tiles_per_cta, t1 = t0 + tiles_per_cta < T ? t0 + tiles_per_cta : T;
     const float Bf = (float)B, Bm1 = (float)(B - 1);
+    const bool fast = rz_fast_row(rc);
+    const float blo = (float)bstar, bhi = bstar >= B - 1 ? __int_as_float(0x7f800000) : (float)(bstar + 1);
     for (int64_t t = t0; t < t1; ++t) {
         float x[kEpt];
         load_tile_striped(X + c * ld, d, t * kTile, x);
         const bool full = (t + 1) * kTile <= d;
         uint32_t hits = 0;                                     // bit j: coordinate j of this thread lies in the threshold bin
         float dls[kEpt];
+        if (fast) {
+            // bin == b* <=> b* <= t < b* + 1 with t = (delta' + 1/2) B (b* = B - 1 takes the clamped t >= B as well)
 #pragma unroll
-        for (int j = 0; j < kEpt; ++j) {
-            float kp;
-            rz_round(x[j], rc, kp, dls[j]);
-            hits |= (lin_bin(dls[j], Bf, Bm1) == bstar ? 1u : 0u) << j;
+            for (int j = 0; j < kEpt; ++j) {
+                float kp;
+                rz_round_t<true>(x[j], rc, kp, dls[j]);
+                const float tb = __fmul_rn(__fadd_rn(dls[j], 0.5f), Bf);
+                hits |= ((tb >= blo && tb < bhi) ? 1u : 0u) << j;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kEpt; ++j) {
+                float kp;
+                rz_round_t<false>(x[j], rc, kp, dls[j]);
+                hits |= (lin_bin(dls[j], Bf, Bm1) == bstar ? 1u : 0u) << j;
+            }
         }
         if (hits == 0u) continue;                              // the threshold bin holds one coordinate in B
 #pragma unroll
@@ -583,7 +609,7 @@ __device__ __forceinline__ void rz_linapply_tile(const float (&x)[kEpt], const R
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 rz_linapply_kernel(const float *__restrict__ X, int64_t d, int64_t ld, int64_t T, int B, const RowConst *__restrict__ consts,
                    const RowSelect *__restrict__ sel, RzEmit e) {
     __shared__ PackScratch s_pack;
@@ -615,7 +641,7 @@ static int biased_quantize_linear(const float *X, int64_t n, int64_t d, int64_t 
     int64_t tp = (n * L.T) / 4096;
     tp = tp < 1 ? 1 : (tp > 64 ? 64 : tp);
     const dim3 grun((unsigned)((L.T + tp - 1) / tp), (unsigned)n), grid((unsigned)L.T, (unsigned)n);
-    rz_sumhist_kernel<<<grun, kThreads, (size_t)B * 4, st>>>(X, d, ld, L.T, (int)tp, B, consts, sel, hist);
+    rz_sumhist_kernel<<<grun, kThreads, (size_t)(B + 2) * 4, st>>>(X, d, ld, L.T, (int)tp, B, consts, sel, hist);
     DME_LAUNCH_CHECK("rz_sumhist_kernel");
     rz_linpick_kernel<<<(unsigned)n, 32, 0, st>>>(sel, hist, n, m, d, B);
     DME_LAUNCH_CHECK("rz_linpick_kernel");

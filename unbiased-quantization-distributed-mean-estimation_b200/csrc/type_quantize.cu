@@ -168,10 +168,27 @@ __device__ __forceinline__ void dec_fetch(DecBatch &b, const uint2 *sinfo, const
     }
 }
 
+// Entry i = 8 c + k of a block of clients starting at cb: table[c][k] = q(k) / n, table[c][8 + k] = -q(k) / n (k = 0: +0 both).
+__device__ __forceinline__ void decode_lut_entry(const float *__restrict__ l1, int64_t cb, int i, float mf, float nf, int biased, float *table) {
+    const int k = i & (kLut - 1), c = i >> 3;
+    const float v = k == 0 ? 0.0f : deq_over_n(__ldg(l1 + cb + c), (float)k, mf, nf, biased);
+    table[c * 16 + k] = v;
+    table[c * 16 + 8 + k] = k == 0 ? 0.0f : __uint_as_float(__float_as_uint(v) ^ 0x80000000u);
+}
+// The same tables for all n clients, once per fused call (workspace, WsLayout::off_lut): the decode kernels' CTAs (one or four per code
+// tile) otherwise each repeat the 2 n IEEE divisions per entry -- a sixth of decode_mean_kernel at n = 128, half of
+// decode_mean_short_kernel at n = 1000.
+__global__ void decode_lut_kernel(const float *__restrict__ l1, int64_t n, float mf, float nf, int biased, float *__restrict__ lut) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * kLut) return;
+    const int64_t cb = (i >> 3) & ~(int64_t)127;            // blocks of 128 clients, so that the in-block entry index fits an int
+    decode_lut_entry(l1, cb, (int)(i - cb * kLut), mf, nf, biased, lut + cb * 16);
+}
+
 __global__ void __launch_bounds__(64, 8)
 decode_mean_kernel(const uint32_t *__restrict__ codes, const uint64_t *__restrict__ dir, const float *__restrict__ l1,
                    int64_t n, int64_t d, int64_t T, float mf, float nf, int biased, float *__restrict__ mean, int accumulate,
-                   int64_t tile0) {
+                   int64_t tile0, const float *__restrict__ glut) {
     __shared__ __align__(64) float lut16[kLutClients * 16];    // [client][sign << 3 | k] = +-q(k) / n for k < 8
     __shared__ __align__(8) uint2 sinfo[kLutClients + kBatch]; // per staged client: {code offset / 16, width code}
     __shared__ uint32_t sslow[kLutClients / kBatch];           // per batch: some client needs decode_generic
@@ -196,11 +213,12 @@ decode_mean_kernel(const uint32_t *__restrict__ codes, const uint64_t *__restric
     for (int64_t cb = 0; cb < n; cb += kLutClients) {
         const int nc = (int)((cb + kLutClients < n) ? kLutClients : n - cb);
         __syncthreads();
-        for (int i = threadIdx.x; i < nc * kLut; i += 64) {
-            const int k = i & (kLut - 1), c = i >> 3;
-            const float v = k == 0 ? 0.0f : deq_over_n(__ldg(l1 + cb + c), (float)k, mf, nf, biased);
-            lut16[c * 16 + k] = v;
-            lut16[c * 16 + 8 + k] = k == 0 ? 0.0f : __uint_as_float(__float_as_uint(v) ^ 0x80000000u);
+        if (glut) {
+            // the fused call computed the tables once (decode_lut_kernel): every CTA copies instead of dividing
+            const float4 *src = reinterpret_cast<const float4 *>(glut + cb * 16);
+            for (int i = threadIdx.x; i < nc * 4; i += 64) reinterpret_cast<float4 *>(lut16)[i] = __ldg(src + i);
+        } else {
+            for (int i = threadIdx.x; i < nc * kLut; i += 64) decode_lut_entry(l1, cb, i, mf, nf, biased, lut16);
         }
         for (int i = threadIdx.x; i < kLutClients / kBatch; i += 64) sslow[i] = 0u;
         __syncthreads();
@@ -299,7 +317,7 @@ constexpr int kCptS = 4;
 __global__ void __launch_bounds__(64, 8)
 decode_mean_short_kernel(const uint32_t *__restrict__ codes, const uint64_t *__restrict__ dir, const float *__restrict__ l1,
                          int64_t n, int64_t d, int64_t T, float mf, float nf, int biased, float *__restrict__ mean, int accumulate,
-                         int64_t tile0) {
+                         int64_t tile0, const float *__restrict__ glut) {
     __shared__ __align__(64) float lut16[kLutClients * 16];
     __shared__ __align__(8) uint2 sinfo[kLutClients + kBatch];
     __shared__ uint32_t sslow[kLutClients / kBatch];
@@ -324,11 +342,12 @@ decode_mean_short_kernel(const uint32_t *__restrict__ codes, const uint64_t *__r
     for (int64_t cb = 0; cb < n; cb += kLutClients) {
         const int nc = (int)((cb + kLutClients < n) ? kLutClients : n - cb);
         __syncthreads();
-        for (int i = threadIdx.x; i < nc * kLut; i += 64) {
-            const int k = i & (kLut - 1), c = i >> 3;
-            const float v = k == 0 ? 0.0f : deq_over_n(__ldg(l1 + cb + c), (float)k, mf, nf, biased);
-            lut16[c * 16 + k] = v;
-            lut16[c * 16 + 8 + k] = k == 0 ? 0.0f : __uint_as_float(__float_as_uint(v) ^ 0x80000000u);
+        if (glut) {
+            // the fused call computed the tables once (decode_lut_kernel): every CTA copies instead of dividing
+            const float4 *src = reinterpret_cast<const float4 *>(glut + cb * 16);
+            for (int i = threadIdx.x; i < nc * 4; i += 64) reinterpret_cast<float4 *>(lut16)[i] = __ldg(src + i);
+        } else {
+            for (int i = threadIdx.x; i < nc * kLut; i += 64) decode_lut_entry(l1, cb, i, mf, nf, biased, lut16);
         }
         for (int i = threadIdx.x; i < kLutClients / kBatch; i += 64) sslow[i] = 0u;
         __syncthreads();
@@ -545,8 +564,8 @@ extern "C" int dme_type_encode(const float *X, int64_t n, int64_t d, int64_t ld,
                            (uint32_t *)codes, codes_bytes, dir, l1_out, ws, ws_bytes, (cudaStream_t)stream, true);
 }
 
-extern "C" int dme_decode_mean_tiles(const void *codes, const uint64_t *dir, const float *l1, int64_t n, int64_t d, int64_t m, int mode,
-                                     int64_t n_total, float *mean, int accumulate, int64_t tile0, int64_t tiles, dme_stream_t stream) {
+static int decode_launch(const void *codes, const uint64_t *dir, const float *l1, int64_t n, int64_t d, int64_t m, int mode,
+                         int64_t n_total, float *mean, int accumulate, int64_t tile0, int64_t tiles, dme_stream_t stream, const float *glut) {
     DME_REQUIRE(codes && dir && l1 && mean, "null pointer argument");
     DME_REQUIRE(n >= 1 && d >= 1 && m >= 1 && n_total >= 1, "n, d, m, n_total must be >= 1");
     DME_REQUIRE(((uintptr_t)mean & 15u) == 0 && ((uintptr_t)codes & 15u) == 0, "mean and codes must be 16-byte aligned");
@@ -556,14 +575,19 @@ extern "C" int dme_decode_mean_tiles(const void *codes, const uint64_t *dir, con
     if (tiles > 0 && tiles <= 256) {
         // few tiles: four coordinates per thread, four CTAs per tile (the client walk is what takes the time: spread it wider)
         decode_mean_short_kernel<<<(unsigned)(4 * tiles), 64, kSignLutBytes, (cudaStream_t)stream>>>(
-            (const uint32_t *)codes, dir, l1, n, d, T, (float)m, (float)n_total, mode == DME_MODE_BIASED, mean, accumulate, tile0);
+            (const uint32_t *)codes, dir, l1, n, d, T, (float)m, (float)n_total, mode == DME_MODE_BIASED, mean, accumulate, tile0, glut);
         DME_LAUNCH_CHECK("decode_mean_short_kernel");
     } else if (tiles > 0) {
         decode_mean_kernel<<<(unsigned)tiles, kCodeChunks, kSignLutBytes, (cudaStream_t)stream>>>(
-            (const uint32_t *)codes, dir, l1, n, d, T, (float)m, (float)n_total, mode == DME_MODE_BIASED, mean, accumulate, tile0);
+            (const uint32_t *)codes, dir, l1, n, d, T, (float)m, (float)n_total, mode == DME_MODE_BIASED, mean, accumulate, tile0, glut);
         DME_LAUNCH_CHECK("decode_mean_kernel");
     }
     return DME_OK;
+}
+
+extern "C" int dme_decode_mean_tiles(const void *codes, const uint64_t *dir, const float *l1, int64_t n, int64_t d, int64_t m, int mode,
+                                     int64_t n_total, float *mean, int accumulate, int64_t tile0, int64_t tiles, dme_stream_t stream) {
+    return decode_launch(codes, dir, l1, n, d, m, mode, n_total, mean, accumulate, tile0, tiles, stream, nullptr);
 }
 
 extern "C" int dme_decode_mean(const void *codes, const uint64_t *dir, const float *l1, int64_t n, int64_t d, int64_t m, int mode,
@@ -588,7 +612,12 @@ extern "C" int dme_quantize_mean(const float *X, int64_t n, int64_t d, int64_t l
                                  int64_t codes_bytes, uint64_t *dir, float *l1_out, void *ws, int64_t ws_bytes, dme_stream_t stream) {
     int rc = dme_type_encode(X, n, d, ld, m, mode, x_inject, nullptr, seed, client0, codes, codes_bytes, dir, l1_out, ws, ws_bytes, stream);
     if (rc) return rc;
-    return dme_decode_mean(codes, dir, l1_out, n, d, m, mode, n_total, mean, accumulate, stream);
+    DME_REQUIRE(n_total >= 1, "n_total must be >= 1");
+    // the decoder's per-client value tables, once for all of its CTAs (the workspace has room for them: WsLayout::off_lut)
+    float *lut = (float *)((char *)ws + ws_layout(n, d).off_lut);
+    decode_lut_kernel<<<(unsigned)((n * kLut + 255) / 256), 256, 0, (cudaStream_t)stream>>>(l1_out, n, (float)m, (float)n_total, mode == DME_MODE_BIASED, lut);
+    DME_LAUNCH_CHECK("decode_lut_kernel");
+    return decode_launch(codes, dir, l1_out, n, d, m, mode, n_total, mean, accumulate, 0, (d + kCodeTile - 1) / kCodeTile, stream, lut);
 }
 
 extern "C" int dme_mean_accumulate(const float *Q, int64_t n, int64_t d, int64_t ld, int64_t n_total, float *mean, int accumulate,

@@ -34,6 +34,7 @@ struct WsLayout {
     int64_t off_done;     // uint32 a_done[n]
     int64_t off_ready;    // uint32 row_ready[n]
     int64_t off_consts;   // RowConst consts[n]
+    int64_t off_lut;      // float lut[n][16]: the decoder's per-client value tables (+-q(k) / n_total, k < 8), fused call only
     int64_t off_partial;  // double partial[n*T]
     int64_t off_desc;     // look-back records of quantize_warp_kernel: 8 bytes per code tile, 8 per block of 32 tiles, 16 per
     int64_t desc_bytes;   // super-block of 1024 tiles
@@ -88,6 +89,7 @@ inline WsLayout ws_layout(int64_t n, int64_t d) {
     L.off_ready = o; o = align_up(o + 4 * n, 256);
     L.zero_bytes = o;
     L.off_consts = o; o = align_up(o + (int64_t)sizeof(RowConst) * n, 256);
+    L.off_lut = o; o = align_up(o + 64 * n, 256);
     L.off_partial = o; o = align_up(o + 8 * n * L.T, 256);
     {
         const int64_t T4 = (d + kCodeTile - 1) / kCodeTile, TB = (T4 + 31) / 32, TS = (TB + 31) / 32;

@@ -32,7 +32,6 @@ struct __align__(256) WsHeader {
 struct WsLayout {
     int64_t T;            // tiles per row
     int64_t off_done;     // uint32 a_done[n]
-    int64_t off_ready;    // uint32 row_ready[n]
     int64_t off_consts;   // RowConst consts[n]
     int64_t off_lut;      // float lut[n][16]: the decoder's per-client value tables (+-q(k) / n_total, k < 8), fused call only
     int64_t off_partial;  // double partial[n*T]
@@ -86,7 +85,6 @@ inline WsLayout ws_layout(int64_t n, int64_t d) {
     L.T = (d + kTile - 1) / kTile;
     int64_t o = (int64_t)sizeof(WsHeader);
     L.off_done = o; o = align_up(o + 4 * n, 256);
-    L.off_ready = o; o = align_up(o + 4 * n, 256);
     L.zero_bytes = o;
     L.off_consts = o; o = align_up(o + (int64_t)sizeof(RowConst) * n, 256);
     L.off_lut = o; o = align_up(o + 64 * n, 256);

@@ -233,6 +233,25 @@ def test_many_short_rows_packed_path(dme, n, d):
         assert np.array_equal(_u32(got), _u32(ref)), (n, d, R)
 
 
+def test_fused_decoder_tables_many_clients_long_rows(dme):
+    """More than one block of 128 clients AND more than 256 code tiles: decode_mean_kernel with the value tables of the fused call
+    (decode_lut_kernel, computed once) against the standalone decoder (tables built by every CTA) and against the oracle."""
+    rng = np.random.default_rng(77)
+    n, d = 200, 300 * 1024 + 77
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    Xg = torch.from_numpy(X).cuda()
+    for mode in ("unbiased", "biased"):
+        fused = dme.quantize_mean(Xg, 1, seed=3, mode=mode).cpu().numpy()
+        pc = dme.type_encode(Xg, 1, seed=3, mode=mode)
+        alone = dme.decode_mean(pc).cpu().numpy()
+        assert np.array_equal(_u32(fused), _u32(alone)), mode
+    m = dme.m_for_rate(1, d)
+    Xs = dme.client_uniforms(seed=3, client0=0, n=n)
+    fused = dme.quantize_mean(Xg, 1, seed=3).cpu().numpy()
+    ref = orc.mean_of([orc.type_unbiased(X[c], m, float(Xs[c]))["deq"] for c in range(n)])
+    assert np.array_equal(_u32(fused), _u32(ref))
+
+
 def test_wire_messages_roundtrip_and_rate(dme):
     """One DMEP1 message per client (header, width bytes, tiles): server-side reassembly decodes to the same mean, bit for bit;
     the message's rate is reported against the table's R."""

@@ -102,7 +102,7 @@ class PeerReduce:
         C = self._C
         cnt = min((int(count) + 3) // 4 * 4, self.dpad - int(lo))
         self.hdl.barrier(channel=0)
-        api._check(_cabi.lib().dme_peer_sum_slice(C.c_void_p(int(self.hdl.buffer_ptrs_dev)), C.c_void_p(self.mc + 4 * int(lo)) if self.mc else None,
+        api._check(_cabi.lib().dme_peer_sum_slice(C.c_void_p(int(self.hdl.buffer_ptrs_dev)), C.c_void_p(self.mc) if self.mc else None,       # the library adds offset_bytes to either mapping
                                                   int(self.hdl.offset) + 4 * int(lo), self.rank, self.world, cnt,
                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         self.hdl.barrier(channel=1)
@@ -129,7 +129,8 @@ def quantize_mean_overlapped_peer(x_local, bits_per_dimension=1, *, n_total: int
     of tiles, each finished run is summed over the ranks (PeerReduce.sum_range_, on a side stream) while the next one is decoded.
     Bit-equal to quantize_mean_sharded_peer.  Measured on 2 B200s at d = 2^24, n = 128 per GPU (tools/overlap_exchange.py): 5.097 ms with
     2, 4 or 8 slices against 5.072 ms for the exchange after the decode -- two device-side barriers per slice and the decoder's tables
-    rebuilt per CTA cost what the overlap hides of a 0.13 ms exchange; bench.py uses the plain call."""
+    rebuilt per CTA cost what the overlap hides of a 0.13 ms exchange; on 4 B200s (in-switch variant) 5.205-5.213 ms against 5.192 ms;
+    bench.py uses the plain call."""
     from . import api
     X, n, d, _ = api._rows(x_local)
     pr = PeerReduce.get(d, group, multicast)
